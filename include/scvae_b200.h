@@ -1,0 +1,177 @@
+/*
+ * scvae_b200.h -- C ABI of the B200-native scVAE hot path (libscvae_b200.so).
+ *
+ * The reference (scvae/scvae v2.1.4) has no FFI: its hot path is entered through
+ * tf.Session.run (scvae/models/variational_autoencoder.py:1026-1029,
+ * gaussian_mixture_variational_autoencoder.py:1109-1112) and every op below is a stock
+ * TensorFlow / TensorFlow-Probability CPU op in that graph.  Each entry point cites the
+ * reference graph fragment it replaces.  Abbreviations:
+ *   VAE   = scvae/models/variational_autoencoder.py
+ *   GMVAE = scvae/models/gaussian_mixture_variational_autoencoder.py
+ *   MU    = scvae/models/utilities.py
+ *   DU    = scvae/distributions/utilities.py
+ *   ZI    = scvae/distributions/zero_inflated.py
+ *
+ * Conventions
+ *   - plain pointers and sizes; every pointer is a DEVICE pointer unless marked [host];
+ *   - caller owns all buffers, no hidden allocation, no hidden synchronisation;
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*;
+ *   - return 0 on success, non-zero on error; the message is at scvae_last_error()
+ *     (thread-local);
+ *   - all matrices are row-major fp32 with an explicit leading dimension (in elements);
+ *   - "augmented" activations: an activation matrix of logical width K is stored with
+ *     width Kp >= K+1, column K == 1.0f and columns > K == 0, so that biases live in
+ *     column K of the (out, Kp) weight matrices and need no separate kernel
+ *     (fully_connected's BiasAdd, MU:53-59, and its gradient, fold into the GEMMs).
+ */
+#ifndef SCVAE_B200_H
+#define SCVAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCVAE_B200_ABI_VERSION 1
+
+/* Count likelihoods (DU:206-305). Head order = the reference's parameter order. */
+#define SCVAE_LIK_POISSON 0 /* heads: log_lambda           DU:206-216 */
+#define SCVAE_LIK_NB      1 /* heads: p, log_r             DU:266-281 */
+#define SCVAE_LIK_ZIP     2 /* heads: pi, log_lambda       DU:247-264, ZI:180-199 */
+#define SCVAE_LIK_ZINB    3 /* heads: pi, p, log_r         DU:283-305, ZI:180-199 */
+
+/* GEMM operand layouts. C is always (M, N) row-major. */
+#define SCVAE_GEMM_NT 0 /* A (M,K) row-major, B (N,K) row-major : forward  Y = A W^T       */
+#define SCVAE_GEMM_NN 1 /* A (M,K) row-major, B (K,N) row-major : dgrad    dA = dY W       */
+#define SCVAE_GEMM_TN 2 /* A (K,M) row-major, B (K,N) row-major : wgrad    dW = dY^T A     */
+
+int         scvae_abi_version(void);
+const char *scvae_last_error(void);
+int         scvae_num_heads(int kind);
+
+/* ---- a1: minibatch gather  (VAE:994-998  x_train[idx].toarray()) --------------------
+ * CSR (indptr int64 [n_rows+1], indices int32, values fp32) -> dense (B, ldx) fp32.
+ * Row b of the output is CSR row rows[b] (rows == NULL: row b).  Columns [G, ldx) are
+ * written as 1.0f at column G (if ldx > G) and 0 after it (augmented layout).
+ * row_const (nullable, [B]) receives sum_g lgamma(1 + x[b,g]), the data-only constant of
+ * every count log-likelihood. */
+int scvae_csr_densify(const int64_t *indptr, const int32_t *indices, const float *values,
+                      const int64_t *rows, int B, int G, float *x, int64_t ldx,
+                      float *row_const, void *stream);
+
+/* ---- a2: dense layers  (MU:38-76 fully_connected; its gradients) ----------------------
+ * C[M,N] (+)= op(A) op(B), fp32 in / fp32 out.  `accumulate` != 0 adds into C.
+ * scvae_gemm_f32 : exact fp32 FFMA kernel, any shape/alignment (small layers, parity).
+ * scvae_gemm_tf32: tcgen05 tensor-core kernel (kind::tf32, TMA-staged, TMEM accumulators);
+ *   requires 16-byte aligned bases and leading dimensions that are multiples of 4.
+ *   `workspace` (nullable) of `workspace_bytes` enables deterministic split-K. */
+int scvae_gemm_f32(int layout, int M, int N, int K, const float *A, int64_t lda,
+                   const float *B, int64_t ldb, float *C, int64_t ldc, int accumulate,
+                   void *stream);
+int scvae_gemm_tf32(int layout, int M, int N, int K, const float *A, int64_t lda,
+                    const float *B, int64_t ldb, float *C, int64_t ldc, int accumulate,
+                    void *workspace, int64_t workspace_bytes, void *stream);
+int64_t scvae_gemm_tf32_workspace_bytes(int layout, int M, int N, int K);
+
+/* ---- a2: batch normalisation + ReLU  (MU:62-74; tf.contrib batch_norm center=True,
+ * scale=False, epsilon 1e-3, decay 0.999) ---------------------------------------------
+ * y (M, ldy) pre-activations, H logical columns; rows form `groups` consecutive groups of
+ * M/groups rows with separate batch statistics (GMVAE: one BN op per cluster k,
+ * GMVAE:2859-2877).  training != 0: batch stats (saved to save_mean/save_rstd
+ * [groups*H]) and moving-average update (Bessel-corrected variance), applied group by
+ * group in order; training == 0: moving stats.  relu != 0 applies max(.,0).
+ * out (M, ldo) is written in augmented layout (col H = 1, cols > H = 0).
+ * `scratch` must hold scvae_bn_scratch_floats(M, H, groups) floats. */
+int64_t scvae_bn_scratch_floats(int M, int H, int groups);
+int scvae_bn_act_fwd(const float *y, int64_t ldy, int M, int H, int groups,
+                     const float *beta, float *moving_mean, float *moving_var,
+                     int training, int update_moving, int relu, float *out, int64_t ldo,
+                     float *save_mean, float *save_rstd, float *scratch, void *stream);
+/* dout (M, lddo) gradient w.r.t. `out`; writes dy (M, lddy) and dbeta[H] (+= if
+ * accumulate_dbeta).  Needs y, out and the saved statistics of the forward call. */
+int scvae_bn_act_bwd(const float *dout, int64_t lddo, const float *y, int64_t ldy,
+                     const float *out, int64_t ldo, int M, int H, int groups,
+                     const float *save_mean, const float *save_rstd, int relu, float *dy,
+                     int64_t lddy, float *dbeta, int accumulate_dbeta, float *scratch,
+                     void *stream);
+/* No-BN variant (minibatch_normalisation False): out = relu(y), augmented. */
+int scvae_act_fwd(const float *y, int64_t ldy, int M, int H, int relu, float *out,
+                  int64_t ldo, void *stream);
+int scvae_act_bwd(const float *dout, int64_t lddo, const float *out, int64_t ldo, int M,
+                  int H, int relu, float *dy, int64_t lddy, void *stream);
+
+/* ---- a3/a6: Gaussian posterior, reparameterisation, analytic KL  (VAE:2243-2369,
+ * VAE:2624-2656, DU:31-50) -------------------------------------------------------------
+ * ph (B, ldph): columns [0,L) = mu pre-activation, [L,2L) = log_sigma pre-activation
+ * (clipped to [-3,3]; ignored when unit_variance).  eps (RS*B, L) contiguous standard
+ * normal noise, sample-major; deterministic != 0 -> z = mu, RS treated as 1.
+ * z (RS*B, ldz) augmented.  kl_row[B] = sum_l KL(N(mu,sigma)||N(0,1)); kl_elem (nullable,
+ * (B, L) contiguous) the per-neuron terms. */
+int scvae_gaussian_latent_fwd(const float *ph, int64_t ldph, int B, int L, int RS,
+                              const float *eps, int unit_variance, int deterministic,
+                              float *z, int64_t ldz, float *kl_row, float *kl_elem,
+                              void *stream);
+/* dz (RS*B, lddz): gradient w.r.t. z.  kl_coef = d loss / d KL[b] (= warm_up*kl_weight/B).
+ * dph (B, lddph) gradient w.r.t. the head pre-activations (clip has zero gradient outside
+ * [-3,3]). */
+int scvae_gaussian_latent_bwd(const float *ph, int64_t ldph, int B, int L, int RS,
+                              const float *eps, int unit_variance, const float *dz,
+                              int64_t lddz, float kl_coef, float *dph, int64_t lddph,
+                              void *stream);
+
+/* ---- a5: count log-likelihood + reduction over genes  (VAE:2583-2590, DU:206-305,
+ * ZI:194-199) --------------------------------------------------------------------------
+ * a: head pre-activations (the FC outputs, before sigmoid / clip): head h of row m, gene g
+ * at a[m*lda + h*head_stride + g].  t (t_rows, ldt) targets; row m uses t row m % t_rows
+ * (replaces tf.tile, VAE:2564-2566).  row_const (nullable, [t_rows]) = sum_g lgamma(1+t).
+ * logp[m] = sum_g log p(t[m,g] | theta[m,g]). */
+int scvae_likelihood_fwd(int kind, const float *t, int64_t ldt, int t_rows, const float *a,
+                         int64_t lda, int64_t head_stride, int M, int G,
+                         const float *row_const, float *logp, void *stream);
+/* Fused forward + backward: da (same layout as a: ldda, dhead_stride) = go[m] *
+ * d logp[m] / d a  (go == NULL -> go_scalar for every row); logp nullable. */
+int scvae_likelihood_bwd(int kind, const float *t, int64_t ldt, int t_rows, const float *a,
+                         int64_t lda, int64_t head_stride, int M, int G,
+                         const float *row_const, const float *go, float go_scalar,
+                         float *da, int64_t ldda, int64_t dhead_stride, float *logp,
+                         void *stream);
+
+/* ---- a7: evaluate-only moments  (VAE:2534-2552, VAE:2665-2713, ZI:180-192;
+ * GMVAE:3312-3386) ---------------------------------------------------------------------
+ * a has K*RS*B rows ordered (k, rs, b).  y (nullable, (B, ldy)) cluster weights q(y|x)
+ * (K == 1 and y == NULL for the VAE).  Outputs (B, ldo), any nullable:
+ * p_x_mean, p_x_stddev, stddev_of_p_x_given_z_mean. */
+int scvae_likelihood_moments(int kind, const float *a, int64_t lda, int64_t head_stride,
+                             int B, int G, int RS, int K, const float *y, int64_t ldy,
+                             float *p_x_mean, float *p_x_stddev, float *stddev_of_mean,
+                             int64_t ldo, void *stream);
+
+/* ---- a6: VAE bound  (VAE:2715-2734, MU:129-137) -----------------------------------------
+ * logp[R*S*B] (r, s, b), kl_row[B].  out[4] = {lower_bound, lower_bound_weighted,
+ * reconstruction_error, kl_divergence}.  go (nullable, [R*S*B]) = d(-lower_bound_weighted)
+ * / d logp = -softmax_r(logp - w kl)/(S B).  weight = warm_up_weight * kl_weight. */
+int scvae_vae_bound(const float *logp, const float *kl_row, int R, int S, int B,
+                    float weight, float *out, float *go, void *stream);
+
+/* ---- a8: optimiser  (VAE:2736-2770) elementwise clip to [-clip, clip] + TF Adam -------
+ * One fused pass over the flat parameter buffer.  `step` [device, int64] is read (t =
+ * *step + 1) for the bias correction lr_t = lr sqrt(1-b2^t)/(1-b1^t); the caller advances
+ * it with scvae_step_advance (kept separate so the pair is CUDA-graph capturable).
+ * grad_scale multiplies the gradient before clipping (data-parallel mean). */
+int scvae_adam_clip_step(float *param, const float *grad, float *m, float *v, int64_t n,
+                         const int64_t *step, float lr, float beta1, float beta2,
+                         float epsilon, float clip, float grad_scale, void *stream);
+int scvae_step_advance(int64_t *step, void *stream);
+
+/* ---- small helpers used by the shells ------------------------------------------------- */
+/* out[c] = (1/rows) * sum_r x[r, c]  (kl_divergence_neurons, VAE:2643-2646). */
+int scvae_col_mean(const float *x, int64_t ldx, int rows, int cols, float *out,
+                   void *stream);
+/* Philox-4x32-10 standard-normal fill (tf.random_normal stand-in, VAE:2363). */
+int scvae_fill_normal(float *out, int64_t n, uint64_t seed, uint64_t offset, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCVAE_B200_H */

@@ -1,0 +1,58 @@
+// a1: minibatch gather.  Replaces the host-side x_train[idx].toarray() (VAE:994-998,
+// GMVAE:1078-1082): the CSR count matrix lives in HBM and each step densifies B rows into the
+// augmented (B, ldx) fp32 layout the GEMMs and the likelihood kernels read.  HBM-write-bound.
+#include "common.cuh"
+
+namespace scvae {
+
+__global__ void __launch_bounds__(256)
+csr_densify_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                   const float *__restrict__ values, const int64_t *__restrict__ rows, int G,
+                   float *__restrict__ x, int64_t ldx, float *__restrict__ row_const) {
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    const int64_t row = rows ? rows[b] : b;
+    float *xr = x + (int64_t)b * ldx;
+    // zero fill (+ the augmented ones column)
+    if ((ldx & 3) == 0 && aligned16(x)) {
+        float4 *x4 = reinterpret_cast<float4 *>(xr);
+        const int n4 = (int)(ldx >> 2);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int c = i << 2;
+            if (G >= c && G < c + 4) (&z.x)[G - c] = 1.f;
+            x4[i] = z;
+        }
+    } else {
+        for (int i = threadIdx.x; i < ldx; i += blockDim.x) xr[i] = (i == G) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    const int64_t s = indptr[row], e = indptr[row + 1];
+    float acc = 0.f;
+    for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) {
+        const float v = values[i];
+        const int c = indices[i];
+        if (c >= 0 && c < G) xr[c] = v;
+        if (v > 0.f) acc += lgammaf(1.f + v);
+    }
+    if (row_const) {
+        const float tot = block_sum(acc, red);
+        if (threadIdx.x == 0) row_const[b] = tot;
+    }
+}
+
+}  // namespace scvae
+
+extern "C" int scvae_csr_densify(const int64_t *indptr, const int32_t *indices, const float *values,
+                                 const int64_t *rows, int B, int G, float *x, int64_t ldx,
+                                 float *row_const, void *stream) {
+    using namespace scvae;
+    SCVAE_CHECK_ARG(indptr && indices && values && x, "csr_densify: NULL pointer");
+    SCVAE_CHECK_ARG(B >= 0 && G > 0 && ldx >= G, "csr_densify: bad shape (B=%d G=%d ldx=%lld)", B, G,
+                    (long long)ldx);
+    if (B == 0) return 0;
+    csr_densify_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(indptr, indices, values, rows, G, x, ldx,
+                                                            row_const);
+    SCVAE_CHECK_LAUNCH("csr_densify");
+    return 0;
+}

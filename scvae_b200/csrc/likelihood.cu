@@ -1,0 +1,374 @@
+// Count log-likelihood kernels: Poisson / negative binomial / zero-inflated variants.
+//
+// Replaces p_x_given_z.log_prob(t_tiled) + reduce_sum over genes (VAE:2583-2590,
+// GMVAE:3295-3304) and its autodiff gradient, for the distributions of DU:206-305 and the
+// zero-inflation wrapper ZI:180-199.  HBM-bound: one CTA per (sample, cell) row streams the
+// row of targets and P head rows with 128-bit loads, reduces over genes with warp shuffles.
+//
+// Numerics.  The reference feeds p = clip(sigmoid(a), tiny, 1) to TFP, which recomputes
+// logits = log p - log1p(-p); mathematically logits == max(a, log tiny).  The kernels use
+// the pre-activation a directly (strictly more accurate).  Zero entries
+// (93-98 % of single-cell counts) need no lgamma: lgamma(r+0) - lgamma(r) = 0, and
+// sum_g lgamma(1+t) is a per-cell constant that the densify kernel precomputes.
+#include "common.cuh"
+
+namespace scvae {
+
+template <int KIND>
+struct Lik;
+template <>
+struct Lik<SCVAE_LIK_POISSON> { static constexpr int P = 1; static constexpr bool NB = false; static constexpr bool ZI = false; };
+template <>
+struct Lik<SCVAE_LIK_NB> { static constexpr int P = 2; static constexpr bool NB = true; static constexpr bool ZI = false; };
+template <>
+struct Lik<SCVAE_LIK_ZIP> { static constexpr int P = 2; static constexpr bool NB = false; static constexpr bool ZI = true; };
+template <>
+struct Lik<SCVAE_LIK_ZINB> { static constexpr int P = 3; static constexpr bool NB = true; static constexpr bool ZI = true; };
+
+// tf.clip_by_value gradient mask: passes inside [lo, hi] (boundaries included).
+__device__ __forceinline__ float clip_mask(float a, float lo, float hi) {
+    return (a < lo || a > hi) ? 0.f : 1.f;
+}
+
+// Everything of one (cell, gene) term except the x>0-only special functions:
+//   lp  : log p without [lgamma(r+x) - lgamma(r)] and without lgamma(1+x)
+//   g[] : d lp / d a[] without the digamma part of log_r
+//   r, cr : total_count and the coefficient of [digamma(r+x) - digamma(r)] in g[log_r]
+template <int KIND, bool BWD>
+__device__ __forceinline__ void lik_elem(float x, const float (&a)[3], float &lp, float (&g)[3],
+                                         float &r, float &cr) {
+    using T = Lik<KIND>;
+    constexpr int iD = T::ZI ? 1 : 0;  // first head of the wrapped count distribution
+    const bool pos = x > 0.f;
+
+    // wrapped distribution: lp_d (x-linear part), its gradients, log p_d(0)
+    float lp_d, l0, gd0 = 0.f, gd1 = 0.f;
+    if (T::NB) {
+        const float ap_raw = a[iD], ar_raw = a[iD + 1];
+        const float ap = fmaxf(ap_raw, kLogitFloor);
+        const float lr = fminf(fmaxf(ar_raw, -10.f), 10.f);
+        r = __expf(lr);
+        float e;
+        const float sp = softplus_e(ap, e);  // -log(1-p)
+        l0 = -r * sp;
+        lp_d = l0 + x * (ap - sp);
+        if (BWD) {
+            const float p = sigmoid_from_e(ap, e);
+            const float mp = ap_raw < kLogitFloor ? 0.f : 1.f;
+            const float mr = clip_mask(ar_raw, -10.f, 10.f);
+            gd0 = (x - (x + r) * p) * mp;
+            gd1 = l0 * mr;
+            cr = r * mr;
+        }
+    } else {
+        const float al = a[iD];
+        const float ll = fminf(fmaxf(al, -10.f), 10.f);
+        const float lam = __expf(ll);
+        r = 0.f;
+        cr = 0.f;
+        l0 = -lam;
+        lp_d = x * ll - lam;
+        if (BWD) gd0 = (x - lam) * clip_mask(al, -10.f, 10.f);
+    }
+
+    if (!T::ZI) {
+        lp = lp_d;
+        if (BWD) {
+            g[0] = gd0;
+            g[1] = gd1;
+        }
+        return;
+    }
+    // zero inflation (ZI:194-199) with pi = sigmoid(a_pi):
+    //   x > 0 : log(1-pi) + lp_d                = -softplus(a_pi) + lp_d
+    //   x <= 0: log(pi + (1-pi) exp(l0))        = softplus(l0 - a_pi) - softplus(-a_pi)
+    const float api_raw = a[0];
+    const float api = fmaxf(api_raw, kLogitFloor);
+    float e_pi, e_u;
+    const float sp_pi = softplus_e(api, e_pi);
+    const float u = l0 - api;
+    const float sp_u = softplus_e(u, e_u);
+    lp = pos ? (lp_d - sp_pi) : (sp_u - (sp_pi - api));
+    if (BWD) {
+        const float pi = sigmoid_from_e(api, e_pi);
+        const float wz = sigmoid_from_e(u, e_u);  // (1-pi) e^{l0} / (pi + (1-pi) e^{l0})
+        const float mpi = api_raw < kLogitFloor ? 0.f : 1.f;
+        g[0] = (pos ? -pi : (1.f - pi) - wz) * mpi;
+        const float w = pos ? 1.f : wz;
+        g[1] = gd0 * w;
+        g[2] = gd1 * w;  // NB only; unused for ZIP
+        cr = pos ? cr : 0.f;
+    }
+}
+
+template <int W>
+struct Vec;
+template <>
+struct Vec<4> {
+    static __device__ __forceinline__ void load(const float *p, float (&v)[4]) {
+        const float4 q = ldg_stream4(p);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
+    static __device__ __forceinline__ void store(float *p, const float (&v)[4]) {
+        stg_stream4(p, make_float4(v[0], v[1], v[2], v[3]));
+    }
+};
+template <>
+struct Vec<1> {
+    static __device__ __forceinline__ void load(const float *p, float (&v)[1]) { v[0] = __ldg(p); }
+    static __device__ __forceinline__ void store(float *p, const float (&v)[1]) { p[0] = v[0]; }
+};
+
+constexpr int kLikThreads = 256;
+
+template <int KIND, bool BWD, int W>
+__global__ void __launch_bounds__(kLikThreads)
+likelihood_kernel(const float *__restrict__ t, int64_t ldt, int t_rows,
+                  const float *__restrict__ a, int64_t lda, int64_t head_stride, int G,
+                  const float *__restrict__ row_const, const float *__restrict__ go,
+                  float go_scalar, float *__restrict__ da, int64_t ldda, int64_t dhead_stride,
+                  float *__restrict__ logp) {
+    using T = Lik<KIND>;
+    constexpr int P = T::P;
+    __shared__ float red[32];
+    const int64_t row = blockIdx.x;
+    const int64_t trow = row % t_rows;
+    const float *trp = t + trow * ldt;
+    const float *arp = a + row * lda;
+    float *drp = BWD ? da + row * ldda : nullptr;
+    const float gscale = BWD ? (go ? go[row] : go_scalar) : 0.f;
+    const bool has_const = row_const != nullptr;
+
+    float acc = 0.f;
+    const int nvec = G / W;
+#pragma unroll 2
+    for (int c = threadIdx.x; c < nvec; c += kLikThreads) {
+        const int col = c * W;
+        float x[W], av[3][W];
+        Vec<W>::load(trp + col, x);
+#pragma unroll
+        for (int h = 0; h < P; ++h) Vec<W>::load(arp + h * head_stride + col, av[h]);
+
+        float gv[3][W], rv[W], crv[W];
+        unsigned nz = 0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const float aj[3] = {av[0][j], P > 1 ? av[1][j] : 0.f, P > 2 ? av[2][j] : 0.f};
+            float lp, g[3] = {0.f, 0.f, 0.f};
+            lik_elem<KIND, BWD>(x[j], aj, lp, g, rv[j], crv[j]);
+            acc += lp;
+            if (BWD) {
+                gv[0][j] = g[0];
+                gv[1][j] = g[1];
+                gv[2][j] = g[2];
+            }
+            nz |= (x[j] > 0.f ? 1u : 0u) << j;
+        }
+        // x > 0 entries (rare): lgamma / digamma differences, one entry per trip so that a
+        // warp loops max-popcount times instead of once per vector lane.
+        if (T::NB || !has_const) {
+            while (nz) {
+                const int j = __ffs(nz) - 1;
+                nz &= nz - 1;
+                float xj = x[0], rj = rv[0], cj = crv[0];
+#pragma unroll
+                for (int q = 1; q < W; ++q) {
+                    xj = j == q ? x[q] : xj;
+                    rj = j == q ? rv[q] : rj;
+                    cj = j == q ? crv[q] : cj;
+                }
+                float extra = 0.f;
+                if (T::NB) {
+                    float D, Pd;
+                    lgamma_diff(rj, xj, D, Pd);
+                    extra = D;
+                    if (BWD) {
+                        const float add = cj * Pd;
+                        constexpr int ir = P - 1;  // log_r is the last head
+#pragma unroll
+                        for (int q = 0; q < W; ++q) gv[ir][q] += (j == q) ? add : 0.f;
+                    }
+                }
+                if (!has_const) extra -= lgammaf(1.f + xj);
+                acc += extra;
+            }
+        }
+        if (BWD) {
+#pragma unroll
+            for (int h = 0; h < P; ++h) {
+                float o[W];
+#pragma unroll
+                for (int j = 0; j < W; ++j) o[j] = gv[h][j] * gscale;
+                Vec<W>::store(drp + h * dhead_stride + col, o);
+            }
+        }
+    }
+    const float total = block_sum(acc, red);
+    if (threadIdx.x == 0 && logp) logp[row] = total - (has_const ? row_const[trow] : 0.f);
+}
+
+template <int KIND, bool BWD>
+static int launch_lik(const float *t, int64_t ldt, int t_rows, const float *a, int64_t lda,
+                      int64_t head_stride, int M, int G, const float *row_const, const float *go,
+                      float go_scalar, float *da, int64_t ldda, int64_t dhead_stride, float *logp,
+                      cudaStream_t s) {
+    bool vec = (G % 4 == 0) && aligned16(t) && aligned16(a) && ldt % 4 == 0 && lda % 4 == 0 &&
+               head_stride % 4 == 0;
+    if (BWD) vec = vec && aligned16(da) && ldda % 4 == 0 && dhead_stride % 4 == 0;
+    if (vec)
+        likelihood_kernel<KIND, BWD, 4><<<M, kLikThreads, 0, s>>>(
+            t, ldt, t_rows, a, lda, head_stride, G, row_const, go, go_scalar, da, ldda,
+            dhead_stride, logp);
+    else
+        likelihood_kernel<KIND, BWD, 1><<<M, kLikThreads, 0, s>>>(
+            t, ldt, t_rows, a, lda, head_stride, G, row_const, go, go_scalar, da, ldda,
+            dhead_stride, logp);
+    SCVAE_CHECK_LAUNCH("likelihood");
+    return 0;
+}
+
+template <bool BWD>
+static int dispatch_lik(int kind, const float *t, int64_t ldt, int t_rows, const float *a,
+                        int64_t lda, int64_t head_stride, int M, int G, const float *row_const,
+                        const float *go, float go_scalar, float *da, int64_t ldda,
+                        int64_t dhead_stride, float *logp, cudaStream_t s) {
+    SCVAE_CHECK_ARG(t && a && M >= 0 && G > 0 && t_rows > 0, "likelihood: bad arguments");
+    SCVAE_CHECK_ARG(!BWD || da, "likelihood_bwd: da is NULL");
+    if (M == 0) return 0;
+    switch (kind) {
+#define CASE(K)                                                                                 \
+    case K:                                                                                     \
+        return launch_lik<K, BWD>(t, ldt, t_rows, a, lda, head_stride, M, G, row_const, go,     \
+                                  go_scalar, da, ldda, dhead_stride, logp, s);
+        CASE(SCVAE_LIK_POISSON)
+        CASE(SCVAE_LIK_NB)
+        CASE(SCVAE_LIK_ZIP)
+        CASE(SCVAE_LIK_ZINB)
+#undef CASE
+    }
+    set_error("likelihood: unknown kind %d", kind);
+    return 1;
+}
+
+// ---- moments (evaluate path) --------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ void lik_moments(const float (&a)[3], float &m, float &v) {
+    using T = Lik<KIND>;
+    constexpr int iD = T::ZI ? 1 : 0;
+    if (T::NB) {
+        const float ap = fmaxf(a[iD], kLogitFloor);
+        const float r = __expf(fminf(fmaxf(a[iD + 1], -10.f), 10.f));
+        const float ea = __expf(ap);
+        m = r * ea;             // r p / (1 - p)
+        v = m * (1.f + ea);     // m / (1 - p)
+    } else {
+        m = __expf(fminf(fmaxf(a[iD], -10.f), 10.f));
+        v = m;
+    }
+    if (T::ZI) {
+        const float api = fmaxf(a[0], kLogitFloor);
+        const float q = 1.f - __frcp_rn(1.f + __expf(-api));  // 1 - pi
+        const float zm = q * m;
+        v = q * (v + m * m) - zm * zm;  // ZI:186-192
+        m = zm;
+    }
+}
+
+template <int KIND>
+__global__ void moments_kernel(const float *__restrict__ a, int64_t lda, int64_t head_stride, int B,
+                               int G, int RS, int K, const float *__restrict__ y, int64_t ldy,
+                               float *__restrict__ p_x_mean, float *__restrict__ p_x_stddev,
+                               float *__restrict__ stddev_of_mean, int64_t ldo) {
+    constexpr int P = Lik<KIND>::P;
+    const int g = blockIdx.y * blockDim.x + threadIdx.x;
+    const int b = blockIdx.x;
+    if (g >= G) return;
+    const float inv = 1.f / (float)RS;
+    float mean_tot = 0.f, var_of_mean = 0.f, mean_of_var = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const float w = y ? y[(int64_t)b * ldy + k] : 1.f;
+        float ms = 0.f, vs = 0.f;
+        for (int s = 0; s < RS; ++s) {
+            const float *ap = a + ((int64_t)(k * RS + s) * B + b) * lda + g;
+            float av[3] = {ap[0], P > 1 ? ap[head_stride] : 0.f, P > 2 ? ap[2 * head_stride] : 0.f};
+            float m, v;
+            lik_moments<KIND>(av, m, v);
+            ms += m;
+            vs += v;
+        }
+        const float pm = ms * inv * w;  // y-weighted per-k mean (GMVAE:3323-3329, quirk Q7)
+        float dev = 0.f;
+        for (int s = 0; s < RS; ++s) {
+            const float *ap = a + ((int64_t)(k * RS + s) * B + b) * lda + g;
+            float av[3] = {ap[0], P > 1 ? ap[head_stride] : 0.f, P > 2 ? ap[2 * head_stride] : 0.f};
+            float m, v;
+            lik_moments<KIND>(av, m, v);
+            dev += (m - pm) * (m - pm);
+        }
+        mean_tot += pm;
+        var_of_mean += dev * inv * w;
+        mean_of_var += vs * inv * w;
+    }
+    const int64_t o = (int64_t)b * ldo + g;
+    if (p_x_mean) p_x_mean[o] = mean_tot;
+    if (p_x_stddev) p_x_stddev[o] = sqrtf(var_of_mean + mean_of_var);
+    if (stddev_of_mean) stddev_of_mean[o] = sqrtf(var_of_mean);
+}
+
+}  // namespace scvae
+
+using namespace scvae;
+
+extern "C" int scvae_num_heads(int kind) {
+    switch (kind) {
+        case SCVAE_LIK_POISSON: return 1;
+        case SCVAE_LIK_NB: return 2;
+        case SCVAE_LIK_ZIP: return 2;
+        case SCVAE_LIK_ZINB: return 3;
+    }
+    return -1;
+}
+
+extern "C" int scvae_likelihood_fwd(int kind, const float *t, int64_t ldt, int t_rows,
+                                    const float *a, int64_t lda, int64_t head_stride, int M, int G,
+                                    const float *row_const, float *logp, void *stream) {
+    SCVAE_CHECK_ARG(logp, "likelihood_fwd: logp is NULL");
+    return dispatch_lik<false>(kind, t, ldt, t_rows, a, lda, head_stride, M, G, row_const, nullptr,
+                               0.f, nullptr, 0, 0, logp, (cudaStream_t)stream);
+}
+
+extern "C" int scvae_likelihood_bwd(int kind, const float *t, int64_t ldt, int t_rows,
+                                    const float *a, int64_t lda, int64_t head_stride, int M, int G,
+                                    const float *row_const, const float *go, float go_scalar,
+                                    float *da, int64_t ldda, int64_t dhead_stride, float *logp,
+                                    void *stream) {
+    return dispatch_lik<true>(kind, t, ldt, t_rows, a, lda, head_stride, M, G, row_const, go,
+                              go_scalar, da, ldda, dhead_stride, logp, (cudaStream_t)stream);
+}
+
+extern "C" int scvae_likelihood_moments(int kind, const float *a, int64_t lda, int64_t head_stride,
+                                        int B, int G, int RS, int K, const float *y, int64_t ldy,
+                                        float *p_x_mean, float *p_x_stddev, float *stddev_of_mean,
+                                        int64_t ldo, void *stream) {
+    SCVAE_CHECK_ARG(a && B > 0 && G > 0 && RS > 0 && K > 0, "likelihood_moments: bad arguments");
+    SCVAE_CHECK_ARG(K == 1 || y, "likelihood_moments: K > 1 needs cluster weights y");
+    dim3 grid(B, (G + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (kind) {
+#define CASE(KK)                                                                              \
+    case KK:                                                                                  \
+        moments_kernel<KK><<<grid, 256, 0, s>>>(a, lda, head_stride, B, G, RS, K, y, ldy,     \
+                                                p_x_mean, p_x_stddev, stddev_of_mean, ldo);   \
+        break;
+        CASE(SCVAE_LIK_POISSON)
+        CASE(SCVAE_LIK_NB)
+        CASE(SCVAE_LIK_ZIP)
+        CASE(SCVAE_LIK_ZINB)
+#undef CASE
+        default:
+            set_error("likelihood_moments: unknown kind %d", kind);
+            return 1;
+    }
+    SCVAE_CHECK_LAUNCH("likelihood_moments");
+    return 0;
+}

@@ -1,0 +1,486 @@
+"""Step engines: the per-minibatch hot path of the reference as a fixed sequence of
+``libscvae_b200`` kernel launches over statically allocated HBM buffers.
+
+``VAEEngine`` replaces the TensorFlow graph built by
+``VariationalAutoencoder._setup_model_graph/_setup_loss_function/_setup_optimiser``
+(scvae/models/variational_autoencoder.py:2219-2770) and its execution through
+``session.run([optimiser, lower_bound])`` (:1026-1029).  Backward is written out by hand (the
+analytic gradients of SURVEY A.8) -- there is no autograd tape and no torch math on the path;
+torch only owns the device allocations and the stream.
+
+Data layout in HBM (all fp32, row-major):
+  * activations are "augmented": logical width K stored as Kp = round4(K+1) columns with
+    column K == 1 and the rest 0, so biases are column K of the weight matrices;
+  * weights are stored (out, in_p) -- K-major for the forward product -- inside ONE flat
+    parameter buffer; gradients and both Adam slots are flat buffers of the same layout, so
+    the optimiser is one fused launch and data-parallel training is one all-reduce;
+  * likelihood-head weights of the P heads are concatenated: (P * Gn, Hp), Gn = round4(G),
+    and their pre-activations land in one (rows, P * Gn) buffer.
+"""
+
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import kernels as K
+
+ADAM_BETA1, ADAM_BETA2, ADAM_EPSILON = 0.9, 0.999, 1e-8   # tf.train.AdamOptimizer defaults
+GRADIENT_CLIP = 1.0                                          # VAE:2753
+
+
+def round4(n):
+    return (n + 3) & ~3
+
+
+def aug(n):
+    """Stored width of an augmented activation with n logical columns."""
+    return round4(n + 1)
+
+
+class _Layer:
+    """One dense layer: weight (n_out, in_p) with the bias in column n_in, optional BN."""
+
+    def __init__(self, name, n_in, n_out, bn):
+        self.name, self.n_in, self.n_out, self.bn = name, n_in, n_out, bn
+        self.in_p = aug(n_in)
+        self.w = self.dw = None          # views into the flat buffers
+        self.beta = self.dbeta = None
+        self.moving_mean = self.moving_var = None
+
+
+class ParameterStore:
+    """Flat fp32 buffers: parameters, gradients, Adam m / v; 16-byte aligned views."""
+
+    def __init__(self, device):
+        self.device = device
+        self.specs = []     # (key, shape)
+        self.offsets = {}
+        self.total = 0
+
+    def add(self, key, shape):
+        n = 1
+        for s in shape:
+            n *= s
+        self.offsets[key] = (self.total, tuple(shape))
+        self.specs.append(key)
+        self.total += round4(n)
+
+    def allocate(self):
+        dev = self.device
+        self.param = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.step = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def view(self, buf, key):
+        off, shape = self.offsets[key]
+        n = 1
+        for s in shape:
+            n *= s
+        return buf[off:off + n].view(shape)
+
+
+class VAEEngine:
+    def __init__(self, feature_size, latent_size, hidden_sizes=(100,),
+                 reconstruction_distribution="poisson", latent_distribution="gaussian",
+                 minibatch_normalisation=True, kl_weight=1.0, device="cuda", seed=0,
+                 tensor_cores=True):
+        if reconstruction_distribution not in K.LIKELIHOOD_KINDS:
+            raise ValueError("reconstruction distribution `{}` is not supported by the "
+                             "B200 hot path".format(reconstruction_distribution))
+        if latent_distribution not in ("gaussian", "unit-variance gaussian"):
+            raise ValueError("latent distribution `{}` not supported for the VAE".format(
+                latent_distribution))
+        self.G, self.L = int(feature_size), int(latent_size)
+        self.hidden_sizes = [int(h) for h in hidden_sizes]
+        self.kind_name = reconstruction_distribution
+        self.kind = K.LIKELIHOOD_KINDS[reconstruction_distribution]
+        self.heads = K.LIKELIHOOD_HEADS[reconstruction_distribution]
+        self.P = len(self.heads)
+        self.unit_variance = latent_distribution == "unit-variance gaussian"
+        self.bn = bool(minibatch_normalisation)
+        self.kl_weight = float(kl_weight)
+        self.device = torch.device(device)
+        self.tensor_cores = bool(tensor_cores)
+        self.Gn = round4(self.G)
+        self.Gp = aug(self.G)
+        self.world_size = 1
+        self._all_reduce = None
+        self._plans = {}
+
+        n = len(self.hidden_sizes)
+        self.enc = []
+        width = self.G
+        for i, h in enumerate(self.hidden_sizes):
+            self.enc.append(_Layer("ENCODER/{}".format(i + 1), width, h, self.bn))
+            width = h
+        self.nL = self.L if self.unit_variance else 2 * self.L
+        self.post = _Layer("POSTERIOR", width, self.nL, False)
+        self.dec = []
+        width = self.L
+        for i, h in enumerate(self.hidden_sizes[::-1]):
+            self.dec.append(_Layer("DECODER/{}".format(n - i), width, h, self.bn))
+            width = h
+        self.head = _Layer("X_TILDE", width, self.P * self.Gn, False)
+
+        store = ParameterStore(self.device)
+        for layer in self.enc + [self.post] + self.dec + [self.head]:
+            store.add(layer.name + "/W", (layer.n_out, layer.in_p))
+            if layer.bn:
+                store.add(layer.name + "/beta", (layer.n_out,))
+        store.allocate()
+        self.store = store
+        self.state = {}
+        for layer in self.enc + [self.post] + self.dec + [self.head]:
+            layer.w = store.view(store.param, layer.name + "/W")
+            layer.dw = store.view(store.grad, layer.name + "/W")
+            if layer.bn:
+                layer.beta = store.view(store.param, layer.name + "/beta")
+                layer.dbeta = store.view(store.grad, layer.name + "/beta")
+                layer.moving_mean = torch.zeros(layer.n_out, dtype=torch.float32,
+                                                device=self.device)
+                layer.moving_var = torch.ones(layer.n_out, dtype=torch.float32,
+                                              device=self.device)
+        self.initialise(seed)
+
+    # ------------------------------------------------------------------ parameters ---------
+    def _tf_names(self):
+        """(engine layer, row slice, TF scope) triples in reference variable order."""
+        out = []
+        for layer in self.enc:
+            out.append((layer, slice(0, layer.n_out), layer.name))
+        if self.unit_variance:
+            out.append((self.post, slice(0, self.L), "POSTERIOR/MU"))
+        else:
+            out.append((self.post, slice(0, self.L), "POSTERIOR/MU"))
+            out.append((self.post, slice(self.L, 2 * self.L), "POSTERIOR/LOG_SIGMA"))
+        for layer in self.dec:
+            out.append((layer, slice(0, layer.n_out), layer.name))
+        for p, head in enumerate(self.heads):
+            out.append((self.head, slice(p * self.Gn, p * self.Gn + self.G),
+                        "X_TILDE/" + head.upper()))
+        return out
+
+    def initialise(self, seed=0):
+        """Xavier-uniform weights, zero biases (tf.contrib fully_connected defaults), BN
+        beta 0 / moving mean 0 / moving variance 1; Adam slots and step reset."""
+        gen = torch.Generator().manual_seed(int(seed))
+        params = OrderedDict()
+        for layer, rows, scope in self._tf_names():
+            fan_in, fan_out = layer.n_in, rows.stop - rows.start
+            limit = math.sqrt(6.0 / (fan_in + fan_out))
+            w = torch.rand((fan_in, fan_out), generator=gen, dtype=torch.float64)
+            params[scope + "/DENSE/weights"] = ((2.0 * w - 1.0) * limit).float()
+            params[scope + "/DENSE/biases"] = torch.zeros(fan_out)
+        self.import_parameters(params, strict=False)
+        for buf in (self.store.grad, self.store.m, self.store.v):
+            buf.zero_()
+        self.store.step.zero_()
+        for layer in self.enc + self.dec:
+            if layer.bn:
+                layer.beta.zero_()
+                layer.moving_mean.zero_()
+                layer.moving_var.fill_(1.0)
+
+    def import_parameters(self, params, strict=True):
+        """Load variables given by their TF names in the reference layout (weights (in,out))."""
+        for layer, rows, scope in self._tf_names():
+            w = params[scope + "/DENSE/weights"].to(self.device, torch.float32)
+            b = params[scope + "/DENSE/biases"].to(self.device, torch.float32)
+            layer.w[rows, :layer.n_in] = w.t()
+            layer.w[rows, layer.n_in] = b
+            layer.w[rows, layer.n_in + 1:] = 0
+            if layer.bn:
+                for key, dst in (("beta", layer.beta), ("moving_mean", layer.moving_mean),
+                                 ("moving_variance", layer.moving_var)):
+                    name = scope + "/BATCH_NORM/" + key
+                    if name in params:
+                        dst.copy_(params[name].to(self.device, torch.float32))
+                    elif strict:
+                        raise KeyError(name)
+
+    def export_parameters(self):
+        out = OrderedDict()
+        for layer, rows, scope in self._tf_names():
+            out[scope + "/DENSE/weights"] = layer.w[rows, :layer.n_in].t().contiguous().cpu()
+            out[scope + "/DENSE/biases"] = layer.w[rows, layer.n_in].contiguous().cpu()
+            if layer.bn:
+                out[scope + "/BATCH_NORM/beta"] = layer.beta.cpu().clone()
+                out[scope + "/BATCH_NORM/moving_mean"] = layer.moving_mean.cpu().clone()
+                out[scope + "/BATCH_NORM/moving_variance"] = layer.moving_var.cpu().clone()
+        return out
+
+    def export_gradients(self):
+        """Last computed raw gradients (before clipping) under the TF variable names."""
+        out = OrderedDict()
+        for layer, rows, scope in self._tf_names():
+            out[scope + "/DENSE/weights"] = layer.dw[rows, :layer.n_in].t().contiguous().cpu()
+            out[scope + "/DENSE/biases"] = layer.dw[rows, layer.n_in].contiguous().cpu()
+            if layer.bn:
+                out[scope + "/BATCH_NORM/beta"] = layer.dbeta.cpu().clone()
+        return out
+
+    def state_dict(self):
+        sd = {"param": self.store.param.cpu(), "m": self.store.m.cpu(), "v": self.store.v.cpu(),
+              "step": self.store.step.cpu()}
+        for layer in self.enc + self.dec:
+            if layer.bn:
+                sd[layer.name + "/moving_mean"] = layer.moving_mean.cpu()
+                sd[layer.name + "/moving_variance"] = layer.moving_var.cpu()
+        return sd
+
+    def load_state_dict(self, sd):
+        self.store.param.copy_(sd["param"])
+        self.store.m.copy_(sd["m"])
+        self.store.v.copy_(sd["v"])
+        self.store.step.copy_(sd["step"])
+        for layer in self.enc + self.dec:
+            if layer.bn:
+                layer.moving_mean.copy_(sd[layer.name + "/moving_mean"])
+                layer.moving_var.copy_(sd[layer.name + "/moving_variance"])
+
+    @property
+    def global_step(self):
+        return int(self.store.step.item())
+
+    # ------------------------------------------------------------------ buffers ------------
+    def _plan(self, B, RS):
+        key = (B, RS)
+        if key in self._plans:
+            return self._plans[key]
+        dev, f32 = self.device, torch.float32
+        M = RS * B
+        p = type("Plan", (), {})()
+        p.B, p.RS, p.M = B, RS, M
+
+        def zeros(*shape):
+            return torch.zeros(*shape, dtype=f32, device=dev)
+
+        p.X = zeros(B, self.Gp)
+        p.X[:, self.G] = 1.0
+        p.T = None                       # separate targets only when t != x
+        p.row_const = zeros(B)
+        p.have_row_const = False
+        p.encY = [zeros(B, round4(l.n_out)) for l in self.enc]
+        p.encH = [zeros(B, aug(l.n_out)) for l in self.enc]
+        p.enc_mean = [zeros(l.n_out) for l in self.enc]
+        p.enc_rstd = [zeros(l.n_out) for l in self.enc]
+        p.PH = zeros(B, round4(self.nL))
+        p.eps = zeros(M, self.L)
+        p.Z = zeros(M, aug(self.L))
+        p.kl_row = zeros(B)
+        p.kl_elem = zeros(B, self.L)
+        p.kl_neurons = zeros(self.L)
+        p.decY = [zeros(M, round4(l.n_out)) for l in self.dec]
+        p.decH = [zeros(M, aug(l.n_out)) for l in self.dec]
+        p.dec_mean = [zeros(l.n_out) for l in self.dec]
+        p.dec_rstd = [zeros(l.n_out) for l in self.dec]
+        p.A = zeros(M, self.P * self.Gn)
+        p.logp = zeros(M)
+        p.go = zeros(M)
+        p.bound = zeros(4)
+        # backward
+        p.dA = None
+        p.bwd_ready = False
+        scratch = 1
+        for l, rows in [(l, B) for l in self.enc] + [(l, M) for l in self.dec]:
+            scratch = max(scratch, K.bn_scratch_floats(rows, l.n_out, 1))
+        p.bn_scratch = zeros(scratch)
+        p.workspace = None
+        p.ws_bytes = 0
+        self._plans[key] = p
+        return p
+
+    def _plan_backward(self, p):
+        if p.bwd_ready:
+            return
+        dev, f32 = self.device, torch.float32
+
+        def zeros(*shape):
+            return torch.zeros(*shape, dtype=f32, device=dev)
+
+        B, M = p.B, p.M
+        p.dA = zeros(M, self.P * self.Gn)
+        p.d_decH = [zeros(M, aug(l.n_out)) for l in self.dec]
+        p.d_decY = [zeros(M, round4(l.n_out)) for l in self.dec]
+        p.dZ = zeros(M, aug(self.L))
+        p.dPH = zeros(B, round4(self.nL))
+        p.d_encH = [zeros(B, aug(l.n_out)) for l in self.enc]
+        p.d_encY = [zeros(B, round4(l.n_out)) for l in self.enc]
+        p.bwd_ready = True
+
+    def _use_tc(self, M, N, Kd):
+        return self.tensor_cores and M * N * Kd >= (1 << 25)
+
+    def _gemm(self, p, layout, M, N, Kd, A, Bm, C, accumulate=False):
+        tc = self._use_tc(M, N, Kd)
+        ws = None
+        if tc:
+            need = K.gemm_workspace_bytes(layout, M, N, Kd)
+            if need > 0:
+                if p.ws_bytes < need:
+                    p.workspace = torch.empty(need // 4, dtype=torch.float32, device=self.device)
+                    p.ws_bytes = need
+                ws = p.workspace
+        K.gemm(layout, M, N, Kd, A, Bm, C, accumulate=accumulate, tensor_cores=tc, workspace=ws)
+
+    # ------------------------------------------------------------------ inputs -------------
+    def set_batch_dense(self, p, x, t=None):
+        """Dense (B, G) minibatch already on the device (tests / small data)."""
+        p.X[:, :self.G].copy_(x)
+        p.have_row_const = False
+        if t is not None and t is not x:
+            if p.T is None:
+                p.T = torch.zeros(p.B, self.Gn, dtype=torch.float32, device=self.device)
+            p.T[:, :self.G].copy_(t)
+            p.use_T = True
+        else:
+            p.use_T = False
+
+    def set_batch_csr(self, p, indptr, indices, values, rows=None):
+        """Gather + densify B rows of a device-resident CSR matrix (a1)."""
+        K.csr_densify(indptr, indices, values, rows, self.G, p.X, p.row_const)
+        p.have_row_const = True
+        p.use_T = False
+
+    # ------------------------------------------------------------------ forward ------------
+    def forward(self, p, is_training, R, S, warm_up_weight=1.0, deterministic=False,
+                update_moving=None, want_go=False, fused_backward=False):
+        """encoder -> posterior -> z -> decoder -> heads -> log-likelihood -> bound.
+        With ``fused_backward`` (R == 1) the likelihood kernel also emits dA in the same pass."""
+        B = p.B
+        RS = 1 if deterministic else R * S
+        M = RS * B
+        if update_moving is None:
+            update_moving = is_training
+        h, h_cols = p.X, self.G
+        for i, l in enumerate(self.enc):
+            self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, h, l.w, p.encY[i])
+            if l.bn:
+                K.bn_act_fwd(p.encY[i], l.n_out, l.beta, l.moving_mean, l.moving_var, p.encH[i],
+                             p.enc_mean[i], p.enc_rstd[i], p.bn_scratch, training=is_training,
+                             update_moving=update_moving, relu=True)
+            else:
+                K.act_fwd(p.encY[i], l.n_out, p.encH[i], relu=True)
+            h = p.encH[i]
+        l = self.post
+        self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, h, l.w, p.PH)
+        K.gaussian_latent_fwd(p.PH, B, self.L, RS, p.eps, p.Z, p.kl_row, p.kl_elem,
+                              unit_variance=self.unit_variance, deterministic=deterministic)
+        d = p.Z
+        for j, l in enumerate(self.dec):
+            self._gemm(p, K.GEMM_NT, M, l.n_out, l.n_in + 1, d, l.w, p.decY[j][:M])
+            if l.bn:
+                K.bn_act_fwd(p.decY[j][:M], l.n_out, l.beta, l.moving_mean, l.moving_var,
+                             p.decH[j][:M], p.dec_mean[j], p.dec_rstd[j], p.bn_scratch,
+                             training=is_training, update_moving=update_moving, relu=True)
+            else:
+                K.act_fwd(p.decY[j][:M], l.n_out, p.decH[j][:M], relu=True)
+            d = p.decH[j]
+        l = self.head
+        self._gemm(p, K.GEMM_NT, M, l.n_out, l.n_in + 1, d, l.w, p.A[:M])
+        tgt = p.T if getattr(p, "use_T", False) else p.X
+        rc = p.row_const if p.have_row_const else None
+        weight = warm_up_weight * self.kl_weight
+        if fused_backward:
+            assert R == 1 and not deterministic
+            self._plan_backward(p)
+            K.likelihood_bwd(self.kind, tgt, p.A[:M], self.Gn, M, self.G, p.dA[:M], logp=p.logp,
+                             row_const=rc, go=None, go_scalar=-1.0 / (S * B))
+            K.vae_bound(p.logp, p.kl_row, R, S, B, weight, p.bound, None)
+        else:
+            K.likelihood_fwd(self.kind, tgt, p.A[:M], self.Gn, M, self.G, p.logp, row_const=rc)
+            K.vae_bound(p.logp, p.kl_row, 1 if deterministic else R, 1 if deterministic else S,
+                        B, weight, p.bound, p.go if want_go else None)
+        return p
+
+    # ------------------------------------------------------------------ backward -----------
+    def backward(self, p, R, S, warm_up_weight=1.0, dA_ready=False):
+        """Gradients of -lower_bound_weighted w.r.t. every parameter into the flat grad buffer."""
+        self._plan_backward(p)
+        B, M = p.B, p.M
+        tgt = p.T if getattr(p, "use_T", False) else p.X
+        rc = p.row_const if p.have_row_const else None
+        if not dA_ready:
+            K.likelihood_bwd(self.kind, tgt, p.A, self.Gn, M, self.G, p.dA, logp=None,
+                             row_const=rc, go=p.go)
+        l = self.head
+        d_in = p.decH[-1] if self.dec else p.Z
+        dd_in = p.d_decH[-1] if self.dec else p.dZ
+        # wgrad (bias gradient = the augmented ones column) and dgrad of the heads
+        self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, M, p.dA, d_in, l.dw)
+        self._gemm(p, K.GEMM_NN, M, l.n_in, l.n_out, p.dA, l.w, dd_in)
+        for j in range(len(self.dec) - 1, -1, -1):
+            l = self.dec[j]
+            if l.bn:
+                K.bn_act_bwd(p.d_decH[j], p.decY[j], p.decH[j], l.n_out, p.dec_mean[j],
+                             p.dec_rstd[j], p.d_decY[j], l.dbeta, p.bn_scratch, relu=True)
+            else:
+                K.act_bwd(p.d_decH[j], p.decH[j], l.n_out, p.d_decY[j], relu=True)
+            d_in = p.decH[j - 1] if j > 0 else p.Z
+            dd_in = p.d_decH[j - 1] if j > 0 else p.dZ
+            self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, M, p.d_decY[j], d_in, l.dw)
+            self._gemm(p, K.GEMM_NN, M, l.n_in, l.n_out, p.d_decY[j], l.w, dd_in)
+        kl_coef = warm_up_weight * self.kl_weight / B
+        K.gaussian_latent_bwd(p.PH, B, self.L, p.RS, p.eps, p.dZ, kl_coef, p.dPH,
+                              unit_variance=self.unit_variance)
+        l = self.post
+        h_in = p.encH[-1] if self.enc else p.X
+        self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.dPH, h_in, l.dw)
+        if self.enc:
+            self._gemm(p, K.GEMM_NN, B, l.n_in, l.n_out, p.dPH, l.w, p.d_encH[-1])
+        for i in range(len(self.enc) - 1, -1, -1):
+            l = self.enc[i]
+            if l.bn:
+                K.bn_act_bwd(p.d_encH[i], p.encY[i], p.encH[i], l.n_out, p.enc_mean[i],
+                             p.enc_rstd[i], p.d_encY[i], l.dbeta, p.bn_scratch, relu=True)
+            else:
+                K.act_bwd(p.d_encH[i], p.encH[i], l.n_out, p.d_encY[i], relu=True)
+            h_in = p.encH[i - 1] if i > 0 else p.X
+            self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.d_encY[i], h_in, l.dw)
+            if i > 0:
+                self._gemm(p, K.GEMM_NN, B, l.n_in, l.n_out, p.d_encY[i], l.w, p.d_encH[i - 1])
+
+    def optimiser_step(self, learning_rate):
+        """[all-reduce] -> clip to [-1, 1] -> TF Adam (VAE:2742-2759), one fused launch."""
+        s = self.store
+        if self._all_reduce is not None:
+            self._all_reduce(s.grad)
+        K.adam_clip_step(s.param, s.grad, s.m, s.v, s.step, learning_rate, ADAM_BETA1,
+                         ADAM_BETA2, ADAM_EPSILON, GRADIENT_CLIP, 1.0 / self.world_size)
+        K.step_advance(s.step)
+
+    def train_step(self, p, R, S, learning_rate, warm_up_weight=1.0):
+        """One ``session.run([optimiser, lower_bound])`` (VAE:1026-1029)."""
+        if R == 1:
+            self.forward(p, True, R, S, warm_up_weight, fused_backward=True)
+            self.backward(p, R, S, warm_up_weight, dA_ready=True)
+        else:
+            self.forward(p, True, R, S, warm_up_weight, want_go=True)
+            self.backward(p, R, S, warm_up_weight)
+        self.optimiser_step(learning_rate)
+        return p.bound
+
+    # ------------------------------------------------------------------ noise --------------
+    def sample_noise(self, p, seed, offset):
+        K.fill_normal(p.eps, seed, offset)
+
+    def set_data_parallel(self, world_size, all_reduce):
+        """Data-parallel training: ``all_reduce(flat_grad)`` must sum in place over ranks."""
+        self.world_size = int(world_size)
+        self._all_reduce = all_reduce if world_size > 1 else None
+
+    # ------------------------------------------------------------------ evaluate extras ----
+    def moments(self, p, R, S, deterministic=False):
+        """p_x_mean, p_x_stddev, stddev_of_p_x_given_z_mean (VAE:2665-2713) for the batch."""
+        RS = 1 if deterministic else R * S
+        outs = [torch.empty(p.B, self.Gn, dtype=torch.float32, device=self.device)
+                for _ in range(3)]
+        K.likelihood_moments(self.kind, p.A, self.Gn, p.B, self.G, RS, 1, None, *outs)
+        return [o[:, :self.G] for o in outs]
+
+    def kl_neurons(self, p):
+        K.col_mean(p.kl_elem, p.B, self.L, p.kl_neurons)
+        return p.kl_neurons

