@@ -107,14 +107,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, version 1.
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor), version 1.  layout_type:
+// 2 = SWIZZLE_128B (16-byte chunks, K-major operands), 1 = SWIZZLE_128B_BASE32B (32-byte
+// chunks: the only layout the tensor core accepts for MN-major 32-bit operands).
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
     uint64_t d = 0;
     d |= (uint64_t)((addr >> 4) & 0x3fff);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
     d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;  // LayoutType::SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 
@@ -229,8 +232,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * kStageBytes);
                     const uint32_t sb = sa + kTileBytes;
-                    const uint64_t da = A_MN ? make_desc(sa, p.mn_lbo, p.mn_sbo) : make_desc(sa, 16, 1024);
-                    const uint64_t db = B_MN ? make_desc(sb, p.mn_lbo, p.mn_sbo) : make_desc(sb, 16, 1024);
+                    const uint64_t da = A_MN ? make_desc(sa, p.mn_lbo, p.mn_sbo, 1) : make_desc(sa, 16, 1024, 2);
+                    const uint64_t db = B_MN ? make_desc(sb, p.mn_lbo, p.mn_sbo, 1) : make_desc(sb, 16, 1024, 2);
                     // per UMMA_K = 8 fp32 step: K-major +32 B inside the swizzle row; MN-major +8 K-rows
                     const uint64_t sta = A_MN ? (1024 >> 4) : (32 >> 4);
                     const uint64_t stb = B_MN ? (1024 >> 4) : (32 >> 4);
@@ -332,7 +335,7 @@ static EncodeTiledFn get_encode() {
 
 // 2-D fp32 tensor map over a row-major (rows, cols) matrix with leading dimension ld.
 static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
-                    int box_rows) {
+                    int box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn enc = get_encode();
     SCVAE_CHECK_ARG(enc, "gemm_tf32: cuTensorMapEncodeTiled unavailable");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -340,7 +343,7 @@ static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t c
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SCVAE_CHECK_ARG(r == CUDA_SUCCESS, "gemm_tf32: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld",
                     (int)r, (long long)rows, (long long)cols, (long long)ld);
@@ -404,10 +407,11 @@ extern "C" int scvae_gemm_tf32(int layout, int M, int N, int K, const float *A, 
     CUtensorMap tmA, tmB, tmC;
     const bool a_mn = (layout == SCVAE_GEMM_TN), b_mn = (layout != SCVAE_GEMM_NT);
     // K-major operand (rows = M or N, cols = K): box 32 (K) x 128 (rows).
-    // MN-major operand (rows = K, cols = M or N): box 32 (MN) x 32 (K rows), four per tile.
-    if (a_mn) { if (make_map(&tmA, A, K, M, lda, 32, 32)) return 1; }
+    // MN-major operand (rows = K, cols = M or N): box 32 (MN) x 32 (K rows), four per tile,
+    // swizzled in 32-byte chunks (Swizzle<2,5,2>, atom = 128 B of MN x 4 K rows).
+    if (a_mn) { if (make_map(&tmA, A, K, M, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1; }
     else      { if (make_map(&tmA, A, M, K, lda, 32, 128)) return 1; }
-    if (b_mn) { if (make_map(&tmB, B, K, N, ldb, 32, 32)) return 1; }
+    if (b_mn) { if (make_map(&tmB, B, K, N, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1; }
     else      { if (make_map(&tmB, B, N, K, ldb, 32, 128)) return 1; }
     if (sp.nsplit > 1) {
         if (make_map(&tmC, (const float *)workspace, (int64_t)sp.nsplit * ws_rows, N, ldw, 32, 128)) return 1;
@@ -419,7 +423,7 @@ extern "C" int scvae_gemm_tf32(int layout, int M, int N, int K, const float *A, 
     p.tiles_m = sp.tiles_m; p.tiles_n = sp.tiles_n; p.nsplit = sp.nsplit;
     p.kb_per_split = sp.kb_per_split; p.nkb = sp.nkb;
     p.accumulate = accumulate; p.ws_rows = ws_rows;
-    p.mn_lbo = 4096; p.mn_sbo = 1024;
+    p.mn_lbo = 4096; p.mn_sbo = 512;  // MN-group (TMA box) stride; 4-row K-group stride
     if (const char *e = getenv("SCVAE_TC_MN_LBO")) p.mn_lbo = (uint32_t)atoi(e);
     if (const char *e = getenv("SCVAE_TC_MN_SBO")) p.mn_sbo = (uint32_t)atoi(e);
 

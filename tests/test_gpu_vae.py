@@ -34,6 +34,13 @@ def _setup(case, tensor_cores):
     x, _ = O.synthetic_counts(B, G, n_types=3, seed=5, target_zero_fraction=0.8)
     x = numpy.minimum(x, 500.0)
     eps = torch.randn(R * S, B, L, generator=gen, dtype=torch.float64)
+    if bn:  # plausible moving statistics: the batch statistics of this batch, perturbed
+        upd = []
+        O.vae_forward(cfg, params, torch.tensor(x, dtype=torch.float64),
+                      torch.tensor(x, dtype=torch.float64), eps, True, bn_updates=upd)
+        for scope, mean, var in upd:
+            params[scope + "/BATCH_NORM/moving_mean"] = mean[0] * 0.9
+            params[scope + "/BATCH_NORM/moving_variance"] = var[0] * 1.1
     eng = VAEEngine(G, L, hidden, lik, latent, bn, kl_weight=0.7, device="cuda:0",
                     tensor_cores=tensor_cores)
     eng.import_parameters(params)
@@ -74,19 +81,22 @@ def test_vae_forward_backward_step(case, tensor_cores):
     # raw gradients of every variable
     got = eng.export_gradients()
     gtol = 2e-4 if not tensor_cores else 1e-2
+    gmax = max(g.abs().max().item() for g in grads.values())
     for k, g in grads.items():
         scale = g.abs().max().item()
         err = (got[k].double() - g).abs().max().item()
-        assert err <= gtol * scale + 1e-7, (k, err, scale)
-    # parameters after clip + Adam, BN moving statistics
+        # biases in front of a batch norm have an exactly-zero gradient: absolute floor
+        assert err <= gtol * scale + 1e-5 * gmax, (k, err, scale)
+    # parameters after clip + Adam, BN moving statistics.  Adam's first step is
+    # lr * g / (|g| + eps'): where |g| is at fp32-noise level the sign is noise in ANY fp32
+    # implementation (the reference included), so those entries are excluded.
     new = eng.export_parameters()
+    noise = (1e-3 if not tensor_cores else 3e-2) * gmax
     for k, v in ref_params.items():
-        err = (new[k].double() - v).abs().max().item()
-        # Adam's first step is +-lr wherever |g| >> eps; allow sign flips only on ~zero grads
-        if k in grads and tensor_cores:
-            big = grads[k].abs() > 1e-4 * grads[k].abs().max()
-            err = ((new[k].double() - v).abs() * big).max().item()
-        assert err <= 1e-4 * max(v.abs().max().item(), 1e-3) + (2e-3 if tensor_cores and k in grads else 0) * 1e-3, (k, err)
+        diff = (new[k].double() - v).abs()
+        if k in grads:
+            diff = diff * (grads[k].abs() > noise)
+        assert diff.max().item() <= 1e-5 * max(v.abs().max().item(), 1.0), (k, diff.max().item())
     assert eng.global_step == 1
 
 
