@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""Benchmark of the scVAE training hot path (BASELINE.json metric):
+cells/sec of VAE training, negative-binomial likelihood, 20 k genes, on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository (CUDA path)
+    python bench.py --impl reference --steps K --warmup W    # reference CPU path (restated)
+
+A "step" is one pass of the hot path over one minibatch: CSR gather/densify -> encoder ->
+reparameterise -> decoder -> NB log-likelihood -> backward -> [all-reduce] -> clip + Adam,
+exactly what the reference runs per ``session.run([optimiser, lower_bound])``
+(scvae/models/variational_autoencoder.py:987-1029).  Workload = BASELINE.json configs[1]:
+68 000 cells x 20 000 genes (10x-PBMC-shaped synthetic, ~7 % non-zero), NB, latent 50,
+hidden [100] (reference default), R = S = 1.  One JSON line is printed by rank 0.
+"""
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cells/sec VAE training (NB, 20k genes)"
+UNIT = "cells/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=68000)
+    ap.add_argument("--genes", type=int, default=20000)
+    ap.add_argument("--latent", type=int, default=50)
+    ap.add_argument("--hidden", type=int, nargs="*", default=[100])
+    ap.add_argument("--likelihood", default="negative binomial")
+    ap.add_argument("--minibatch", type=int, default=4096, help="cells per step per GPU")
+    ap.add_argument("--density", type=float, default=0.07)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic data: ZINB-flavoured sparse counts, built as CSR
+# ---------------------------------------------------------------------------------------------
+def make_csr(n_cells, n_genes, density, seed, device=None):
+    """Returns scipy CSR (host).  Generated on the GPU when one is given (fast), else numpy."""
+    import scipy.sparse
+    if device is not None:
+        gen = torch.Generator(device=device).manual_seed(seed)
+        gene_rate = torch.rand(n_genes, generator=gen, device=device) * 2.0 * density
+        indptr = [torch.zeros(1, dtype=torch.int64, device=device)]
+        cols, vals = [], []
+        chunk = 4096
+        total = 0
+        for s in range(0, n_cells, chunk):
+            rows = min(chunk, n_cells - s)
+            mask = torch.rand(rows, n_genes, generator=gen, device=device) < gene_rate
+            nz = mask.nonzero()
+            counts = torch.bincount(nz[:, 0], minlength=rows)
+            indptr.append(total + torch.cumsum(counts, 0))
+            total += int(nz.shape[0])
+            cols.append(nz[:, 1].to(torch.int32))
+            # geometric-ish count values >= 1 (mostly 1-3, heavy tail)
+            u = torch.rand(nz.shape[0], generator=gen, device=device)
+            vals.append(torch.floor(1.0 - torch.log(u) * 1.2).clamp_(1, 500))
+        indptr = torch.cat(indptr).cpu().numpy()
+        indices = torch.cat(cols).cpu().numpy()
+        data = torch.cat(vals).cpu().numpy().astype(numpy.float32)
+    else:
+        rng = numpy.random.RandomState(seed)
+        gene_rate = rng.rand(n_genes) * 2.0 * density
+        indptr = [0]
+        cols, vals = [], []
+        for s in range(0, n_cells, 1024):
+            rows = min(1024, n_cells - s)
+            mask = rng.rand(rows, n_genes) < gene_rate
+            r, c = numpy.nonzero(mask)
+            indptr.extend((indptr[-1] + numpy.cumsum(numpy.bincount(r, minlength=rows))).tolist())
+            cols.append(c.astype(numpy.int32))
+            vals.append(numpy.clip(numpy.floor(1.0 - numpy.log(rng.rand(len(c))) * 1.2), 1, 500))
+        indptr = numpy.asarray(indptr, dtype=numpy.int64)
+        indices = numpy.concatenate(cols)
+        data = numpy.concatenate(vals).astype(numpy.float32)
+    return scipy.sparse.csr_matrix((data, indices, indptr), shape=(n_cells, n_genes))
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(numpy.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference CPU path (restated: the oracle, see oracle/scvae_oracle.py header)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(args, csr, steps, warmup, budget_s):
+    """Times the restated reference training step on the host cores: per step
+    ``x[idx].toarray()`` twice (VAE:997-998), forward, autograd backward, clip, Adam."""
+    from oracle import scvae_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.VAEConfig(args.genes, args.latent, args.hidden, args.likelihood)
+    params = O.vae_init_params(cfg, seed=0, dtype=torch.float32)
+    state = O.AdamState(params)
+    rng = numpy.random.RandomState(2)
+    gen = torch.Generator().manual_seed(1)
+    B = min(args.minibatch, csr.shape[0])
+    n = csr.shape[0]
+
+    def one(b):
+        idx = rng.randint(0, n, size=b)
+        x = torch.from_numpy(csr[idx].toarray())
+        t = torch.from_numpy(csr[idx].toarray())
+        eps = torch.randn(1, b, args.latent, generator=gen)
+        out, _ = O.train_step(cfg, params, state, x, t, eps, 1e-4)
+        return float(out["lower_bound"])
+
+    t0 = time.perf_counter()
+    one(B)
+    first = time.perf_counter() - t0
+    # bound the whole run: shrink the per-step sample if needed
+    if first * (steps + warmup) > budget_s:
+        B = max(256, int(B * budget_s / (first * (steps + warmup))))
+    for _ in range(max(warmup - 1, 0)):
+        one(B)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one(B)
+    dt = time.perf_counter() - t0
+    return {"value": steps * B / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "{} timed minibatches of {} cells (+{} warm-up) of the same workload; "
+                      "restated reference CPU path (PyTorch-CPU fp32 oracle; TF 1.15 is not "
+                      "installable, SURVEY 8c)".format(steps, B, warmup)}, dt / steps * 1e3, B
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    csr = make_csr(min(args.cells, 16384), args.genes, args.density, seed=60)
+    base, ms, B = cpu_reference_run(args, csr, args.steps, max(args.warmup, 1), budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, B), "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, minibatch):
+    return {
+        "workload": "C2: VAE, {} cells x {} genes synthetic (10x-PBMC-shaped, {:.0f}% non-zero), "
+                    "{}, latent {}, hidden {}, R=S=1".format(
+                        args.cells, args.genes, args.density * 100, args.likelihood, args.latent,
+                        args.hidden),
+        "minibatch_per_gpu": minibatch,
+        "l2": "per-step working set (~2.6 GB of (cells x genes) fp32 tensors at B=4096) exceeds "
+              "the 126 MB L2; minibatch rows change every step",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# this repository's arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from scvae_b200 import _lib
+    from scvae_b200.engine import VAEEngine
+    from scvae_b200.hotloop import ResidentCSR, StreamedCSR, TrainLoop
+    from scvae_b200 import kernels as K
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the scVAE hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    # ---- data (each rank owns its own shard of `cells` cells: weak scaling) ---------------
+    csr = make_csr(args.cells, args.genes, args.density, seed=60 + rank, device=dev)
+    B = min(args.minibatch, args.cells)
+    data = ResidentCSR(csr, dev)
+    eng = VAEEngine(args.genes, args.latent, args.hidden, args.likelihood, device=dev, seed=0)
+    if world > 1:
+        eng.set_data_parallel(world, lambda g: dist.all_reduce(g))
+    loop = TrainLoop(eng, B, seed=1 + rank, use_graph=not args.no_graph)
+    n_batches = args.cells // B
+    perm = torch.from_numpy(numpy.random.RandomState(2).permutation(args.cells)).to(dev)
+
+    def step(i):
+        b = i % n_batches
+        loop.rows.copy_(perm[b * B:(b + 1) * B])
+        return loop.step(data, 1e-4, 1.0)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # count our kernel launches per step (eager, outside the timed region)
+    step(0)
+    torch.cuda.synchronize()
+    l0 = lib.scvae_launch_count()
+    loop.use_graph, saved = False, loop.use_graph
+    step(0)
+    torch.cuda.synchronize()
+    launches_per_step = lib.scvae_launch_count() - l0
+    loop.use_graph = saved
+
+    for i in range(args.warmup):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = e0.elapsed_time(e1)
+    t = torch.tensor([elapsed_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    bound = loop.plan.bound.cpu().tolist()
+    value = args.steps * B * world / (elapsed_ms * 1e-3)
+
+    # ---- dominant kernel, timed live with CUDA events (eager steps, same workload) ---------
+    p = loop.plan
+    evs = []
+    orig = K.likelihood_bwd
+
+    def timed_lik(*a, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        orig(*a, **kw)
+        e.record()
+        evs.append((s, e))
+    K.likelihood_bwd = timed_lik
+    loop.use_graph = False
+    for i in range(min(args.steps, 20)):
+        step(args.warmup + args.steps + i)
+    torch.cuda.synchronize()
+    K.likelihood_bwd = orig
+    loop.use_graph = saved
+    lik_ms = float(numpy.mean([s.elapsed_time(e) for s, e in evs]))
+    P = eng.P
+    # algorithmic bytes per (cell, gene): fp32 target + P head pre-activations read, P
+    # gradients written (NB backward = 20 B/gene)
+    lik_bytes = (1 + 2 * P) * 4.0 * B * args.genes + 8.0 * B
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = json.load(open(peaks_path))["hbm_gbs"]
+        peak_src = "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = lik_bytes / (lik_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            if tj.get("minibatch") == B and tj.get("genes") == args.genes:
+                traffic = tj.get("likelihood_bwd_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "likelihood_kernel<NB, BWD> (fused log-prob + gradient)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": lik_bytes, "launch_ms": lik_ms,
+                "share_of_step": lik_ms / (elapsed_ms / args.steps)}
+
+    # ---- end to end: host CSR in pinned memory, per-step H2D of the row slab, D2H of ELBO ---
+    e2e = None
+    if not args.no_e2e:
+        stream = StreamedCSR(csr[perm.cpu().numpy()], dev, B)   # pre-shuffled epoch order
+        compute = torch.cuda.current_stream()
+        h2d = 0
+
+        def e2e_step(i, pending):
+            nonlocal h2d
+            b = i % n_batches
+            slot = pending
+            nxt = stream.fetch((i + 1) % 2, ((i + 1) % n_batches) * B, ((i + 1) % n_batches + 1) * B)
+            compute.wait_event(slot["ready"])
+            out = loop.step(slot, 1e-4, 1.0)
+            slot["free"].record(compute)
+            h2d += slot["bytes"]
+            elbo = out.cpu()          # D2H of the step's result: synchronises, like session.run
+            return nxt, elbo
+
+        pending = stream.fetch(0, 0, B)
+        for i in range(args.warmup):
+            pending, _ = e2e_step(i, pending)
+        sync_all()
+        h2d = 0
+        t0 = time.perf_counter()
+        for i in range(args.warmup, args.warmup + args.steps):
+            pending, elbo = e2e_step(i, pending)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": args.steps * B * world / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": 16,
+               "path": "pinned host CSR slab -> H2D (copy stream, double-buffered) -> densify "
+                       "-> train step -> D2H of the bound"}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sub = csr[:min(args.cells, 16384)]
+        cpu_base, _, _ = cpu_reference_run(args, sub, steps=2, warmup=1, budget_s=40.0)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+            "data": "synthetic", "config": workload_config(args, B), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": roofline, "cpu_baseline": cpu_base,
+            "lower_bound_last_step": bound[0],
+            "cuda_graph": bool(saved),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

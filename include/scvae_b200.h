@@ -49,16 +49,20 @@ extern "C" {
 int         scvae_abi_version(void);
 const char *scvae_last_error(void);
 int         scvae_num_heads(int kind);
+/* Number of kernels this library has launched in the calling process (bench evidence). */
+long long   scvae_launch_count(void);
 
 /* ---- a1: minibatch gather  (VAE:994-998  x_train[idx].toarray()) --------------------
  * CSR (indptr int64 [n_rows+1], indices int32, values fp32) -> dense (B, ldx) fp32.
  * Row b of the output is CSR row rows[b] (rows == NULL: row b).  Columns [G, ldx) are
  * written as 1.0f at column G (if ldx > G) and 0 after it (augmented layout).
  * row_const (nullable, [B]) receives sum_g lgamma(1 + x[b,g]), the data-only constant of
- * every count log-likelihood. */
+ * every count log-likelihood.  rebase != 0: `indptr` holds absolute offsets of
+ * a row slab whose nonzeros start at indices[0]/values[0] (offsets are taken relative to
+ * indptr[0]) -- the streaming path ships one such slab per step from pinned host memory. */
 int scvae_csr_densify(const int64_t *indptr, const int32_t *indices, const float *values,
                       const int64_t *rows, int B, int G, float *x, int64_t ldx,
-                      float *row_const, void *stream);
+                      float *row_const, int rebase, void *stream);
 
 /* ---- a2: dense layers  (MU:38-76 fully_connected; its gradients) ----------------------
  * C[M,N] (+)= op(A) op(B), fp32 in / fp32 out.  `accumulate` != 0 adds into C.
@@ -168,8 +172,11 @@ int scvae_step_advance(int64_t *step, void *stream);
 /* out[c] = (1/rows) * sum_r x[r, c]  (kl_divergence_neurons, VAE:2643-2646). */
 int scvae_col_mean(const float *x, int64_t ldx, int rows, int cols, float *out,
                    void *stream);
-/* Philox-4x32-10 standard-normal fill (tf.random_normal stand-in, VAE:2363). */
-int scvae_fill_normal(float *out, int64_t n, uint64_t seed, uint64_t offset, void *stream);
+/* Philox-4x32-10 standard-normal fill (tf.random_normal stand-in, VAE:2363).  The Philox
+ * offset is `offset + *offset_dev` (offset_dev nullable, device int64: normally the optimiser
+ * step counter, which keeps the launch CUDA-graph capturable). */
+int scvae_fill_normal(float *out, int64_t n, uint64_t seed, uint64_t offset,
+                      const int64_t *offset_dev, void *stream);
 
 #ifdef __cplusplus
 }

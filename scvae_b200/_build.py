@@ -23,13 +23,29 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _stale():
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def source_hash():
+    """Content hash of every source the library is built from (mtimes do not survive the
+    snapshot copy to the GPU box, contents do)."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
     deps.append(os.path.join(INCLUDE, "scvae_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
+        return True
+    with open(HASH_PATH) as fh:
+        return fh.read().strip() != source_hash()
 
 
 def find_nvcc():
@@ -66,6 +82,8 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
     os.replace(tmp, LIB_PATH)
+    with open(HASH_PATH, "w") as fh:
+        fh.write(source_hash())
     return LIB_PATH
 
 

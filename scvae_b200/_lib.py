@@ -21,8 +21,9 @@ SIGNATURES = {
     "scvae_abi_version": (c_int, []),
     "scvae_last_error": (ctypes.c_char_p, []),
     "scvae_num_heads": (c_int, [c_int]),
+    "scvae_launch_count": (ctypes.c_longlong, []),
     "scvae_csr_densify": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_i64, c_ptr,
-                                  c_ptr]),
+                                  c_int, c_ptr]),
     "scvae_gemm_f32": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_i64, c_ptr, c_i64, c_ptr,
                                c_i64, c_int, c_ptr]),
     "scvae_gemm_tf32": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_i64, c_ptr, c_i64, c_ptr,
@@ -52,7 +53,7 @@ SIGNATURES = {
                                      c_f32, c_f32, c_f32, c_f32, c_ptr]),
     "scvae_step_advance": (c_int, [c_ptr, c_ptr]),
     "scvae_col_mean": (c_int, [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr]),
-    "scvae_fill_normal": (c_int, [c_ptr, c_i64, c_u64, c_u64, c_ptr]),
+    "scvae_fill_normal": (c_int, [c_ptr, c_i64, c_u64, c_u64, c_ptr, c_ptr]),
 }
 
 _LIB = None

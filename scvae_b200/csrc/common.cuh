@@ -11,6 +11,7 @@ namespace scvae {
 
 // ---- error plumbing ---------------------------------------------------------------------
 void set_error(const char *fmt, ...);
+void count_launch();
 
 #define SCVAE_CHECK_ARG(cond, ...)                 \
     do {                                           \
@@ -22,6 +23,7 @@ void set_error(const char *fmt, ...);
 
 #define SCVAE_CHECK_LAUNCH(name)                                                   \
     do {                                                                           \
+        ::scvae::count_launch();                                                   \
         cudaError_t e_ = cudaGetLastError();                                       \
         if (e_ != cudaSuccess) {                                                   \
             ::scvae::set_error("%s: launch failed: %s", name, cudaGetErrorString(e_)); \

@@ -12,7 +12,10 @@ void set_error(const char *fmt, ...) {
     vsnprintf(g_error, sizeof(g_error), fmt, ap);
     va_end(ap);
 }
+static long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
 }  // namespace scvae
 
 extern "C" int scvae_abi_version(void) { return SCVAE_B200_ABI_VERSION; }
 extern "C" const char *scvae_last_error(void) { return scvae::g_error; }
+extern "C" long long scvae_launch_count(void) { return __atomic_load_n(&scvae::g_launches, __ATOMIC_RELAXED); }

@@ -8,7 +8,7 @@ namespace scvae {
 __global__ void __launch_bounds__(256)
 csr_densify_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                    const float *__restrict__ values, const int64_t *__restrict__ rows, int G,
-                   float *__restrict__ x, int64_t ldx, float *__restrict__ row_const) {
+                   float *__restrict__ x, int64_t ldx, float *__restrict__ row_const, int rebase) {
     __shared__ float red[32];
     const int b = blockIdx.x;
     const int64_t row = rows ? rows[b] : b;
@@ -27,7 +27,8 @@ csr_densify_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict
         for (int i = threadIdx.x; i < ldx; i += blockDim.x) xr[i] = (i == G) ? 1.f : 0.f;
     }
     __syncthreads();
-    const int64_t s = indptr[row], e = indptr[row + 1];
+    const int64_t base = rebase ? indptr[0] : 0;
+    const int64_t s = indptr[row] - base, e = indptr[row + 1] - base;
     float acc = 0.f;
     for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) {
         const float v = values[i];
@@ -45,14 +46,14 @@ csr_densify_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict
 
 extern "C" int scvae_csr_densify(const int64_t *indptr, const int32_t *indices, const float *values,
                                  const int64_t *rows, int B, int G, float *x, int64_t ldx,
-                                 float *row_const, void *stream) {
+                                 float *row_const, int rebase, void *stream) {
     using namespace scvae;
     SCVAE_CHECK_ARG(indptr && indices && values && x, "csr_densify: NULL pointer");
     SCVAE_CHECK_ARG(B >= 0 && G > 0 && ldx >= G, "csr_densify: bad shape (B=%d G=%d ldx=%lld)", B, G,
                     (long long)ldx);
     if (B == 0) return 0;
     csr_densify_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(indptr, indices, values, rows, G, x, ldx,
-                                                            row_const);
+                                                            row_const, rebase);
     SCVAE_CHECK_LAUNCH("csr_densify");
     return 0;
 }

@@ -141,11 +141,13 @@ __global__ void col_mean_kernel(const float *__restrict__ x, int64_t ldx, int ro
     }
 }
 
-__global__ void fill_normal_kernel(float *__restrict__ out, int64_t n, uint64_t seed, uint64_t offset) {
+__global__ void fill_normal_kernel(float *__restrict__ out, int64_t n, uint64_t seed, uint64_t offset,
+                                   const int64_t *__restrict__ offset_dev) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t base = tid * 4;
     if (base >= n) return;
     curandStatePhilox4_32_10_t st;
+    if (offset_dev) offset += (uint64_t)(*offset_dev);
     curand_init(seed, (unsigned long long)tid, offset, &st);
     const float4 v = curand_normal4(&st);
     const float vv[4] = {v.x, v.y, v.z, v.w};
@@ -199,11 +201,12 @@ extern "C" int scvae_col_mean(const float *x, int64_t ldx, int rows, int cols, f
     return 0;
 }
 
-extern "C" int scvae_fill_normal(float *out, int64_t n, uint64_t seed, uint64_t offset, void *stream) {
+extern "C" int scvae_fill_normal(float *out, int64_t n, uint64_t seed, uint64_t offset,
+                                 const int64_t *offset_dev, void *stream) {
     SCVAE_CHECK_ARG(out && n >= 0, "fill_normal: bad arguments");
     if (n == 0) return 0;
     const int64_t threads = (n + 3) / 4;
-    fill_normal_kernel<<<(int)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset);
+    fill_normal_kernel<<<(int)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset, offset_dev);
     SCVAE_CHECK_LAUNCH("fill_normal");
     return 0;
 }

@@ -1,0 +1,153 @@
+"""Minibatch loops around the step engine: device-resident and streamed CSR inputs,
+CUDA-graph replay of the training step.
+
+Replaces the reference's per-step host work (VAE:985-1029): ``x_train[idx].toarray()`` on
+the host, a feed_dict copy of two dense (B, G) fp32 arrays and a ``session.run``.  Here the
+count matrix stays CSR; either all of it lives in HBM and a step ships only row indices
+(``ResidentCSR``), or each step's row slab is copied from pinned host memory on a side stream
+while the previous step computes (``StreamedCSR``).  The step itself (densify -> noise ->
+forward -> backward -> clip+Adam) is captured once per minibatch shape into a CUDA graph.
+"""
+
+import numpy
+import torch
+
+from . import kernels as K
+
+
+def _as_csr_arrays(matrix):
+    """scipy CSR (or anything with indptr/indices/data) -> (int64, int32, float32) arrays."""
+    import scipy.sparse
+    if not scipy.sparse.isspmatrix_csr(matrix):
+        matrix = scipy.sparse.csr_matrix(matrix)
+    return (numpy.ascontiguousarray(matrix.indptr, dtype=numpy.int64),
+            numpy.ascontiguousarray(matrix.indices, dtype=numpy.int32),
+            numpy.ascontiguousarray(matrix.data, dtype=numpy.float32),
+            matrix.shape)
+
+
+class ResidentCSR:
+    """The whole (cells x genes) count matrix in HBM as CSR; steps gather rows by index."""
+
+    def __init__(self, matrix, device):
+        indptr, indices, data, shape = _as_csr_arrays(matrix)
+        self.shape = shape
+        self.device = torch.device(device)
+        self.indptr = torch.from_numpy(indptr).to(self.device)
+        self.indices = torch.from_numpy(indices).to(self.device)
+        self.values = torch.from_numpy(data).to(self.device)
+        self.nbytes = indptr.nbytes + indices.nbytes + data.nbytes
+
+    @property
+    def number_of_examples(self):
+        return self.shape[0]
+
+
+class StreamedCSR:
+    """CSR kept in pinned host memory; ``fetch(i0, i1)`` copies the slab of rows [i0, i1) to
+    one of two device staging buffers on a copy stream (double buffering)."""
+
+    def __init__(self, matrix, device, max_rows):
+        indptr, indices, data, shape = _as_csr_arrays(matrix)
+        self.shape = shape
+        self.device = torch.device(device)
+        self.indptr = torch.from_numpy(indptr).pin_memory()
+        self.indices = torch.from_numpy(indices).pin_memory()
+        self.values = torch.from_numpy(data).pin_memory()
+        n = shape[0]
+        row_nnz = numpy.diff(indptr)
+        # worst-case slab of max_rows consecutive rows
+        csum = numpy.concatenate([[0], numpy.cumsum(row_nnz)])
+        hi = numpy.minimum(numpy.arange(n) + max_rows, n)
+        self.max_nnz = int((csum[hi] - csum[numpy.arange(n)]).max()) if n else 0
+        self.max_rows = max_rows
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.slots = []
+        for _ in range(2):
+            self.slots.append({
+                "indptr": torch.empty(max_rows + 1, dtype=torch.int64, device=self.device),
+                "indices": torch.empty(max(self.max_nnz, 1), dtype=torch.int32, device=self.device),
+                "values": torch.empty(max(self.max_nnz, 1), dtype=torch.float32, device=self.device),
+                "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "bytes": 0,
+            })
+        for s in self.slots:
+            s["free"].record()
+
+    def fetch(self, slot_id, i0, i1):
+        """Enqueue the H2D copy of rows [i0, i1) into staging slot ``slot_id``."""
+        s = self.slots[slot_id]
+        lo, hi = int(self.indptr[i0]), int(self.indptr[i1])
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(s["free"])
+            s["indptr"][: i1 - i0 + 1].copy_(self.indptr[i0:i1 + 1], non_blocking=True)
+            s["indices"][: hi - lo].copy_(self.indices[lo:hi], non_blocking=True)
+            s["values"][: hi - lo].copy_(self.values[lo:hi], non_blocking=True)
+            s["ready"].record(self.copy_stream)
+        s["bytes"] = (i1 - i0 + 1) * 8 + (hi - lo) * 8
+        return s
+
+
+class TrainLoop:
+    """One (engine, minibatch size) training loop with a CUDA-graph-captured step."""
+
+    def __init__(self, engine, minibatch_size, R=1, S=1, seed=1, use_graph=True):
+        self.engine = engine
+        self.B = int(minibatch_size)
+        self.R, self.S = int(R), int(S)
+        self.seed = int(seed)
+        self.use_graph = bool(use_graph)
+        self.plan = engine._plan(self.B, self.R * self.S)
+        self.rows = torch.zeros(self.B, dtype=torch.int64, device=engine.device)
+        self._graph = None
+        self._graph_key = None
+        self._src = None
+
+    # the captured body: everything that is identical from step to step
+    def _body(self, src, lr, w):
+        eng, p = self.engine, self.plan
+        if isinstance(src, ResidentCSR):
+            eng.set_batch_csr(p, src.indptr, src.indices, src.values, self.rows)
+        else:  # staging slot of a StreamedCSR
+            K.csr_densify(src["indptr"], src["indices"], src["values"], None, eng.G, p.X,
+                          p.row_const, rebase=True)
+            p.have_row_const = True
+            p.use_T = False
+        K.fill_normal(p.eps, self.seed, 0, eng.store.step)
+        eng.train_step(p, self.R, self.S, lr, w)
+
+    def step(self, src, lr, warm_up_weight=1.0):
+        """Run one optimiser step on the minibatch described by ``src`` (+ ``self.rows``)."""
+        key = (id(src), float(lr), float(warm_up_weight))
+        if not self.use_graph:
+            self._body(src, lr, warm_up_weight)
+            return self.plan.bound
+        if self._graph is None or self._graph_key != key:
+            if self._graph is None or self._graph_key is None:
+                pass
+            graphs = getattr(self, "_graphs", None)
+            if graphs is None:
+                graphs = self._graphs = {}
+            if key not in graphs:
+                # eager warm-up allocates every lazily created buffer before capture; the
+                # optimiser state is snapshotted so that warm-up + capture are side-effect free
+                eng = self.engine
+                snap = (eng.store.param.clone(), eng.store.m.clone(), eng.store.v.clone(),
+                        eng.store.step.clone(),
+                        [(l.moving_mean.clone(), l.moving_var.clone())
+                         for l in eng.enc + eng.dec if l.bn])
+                self._body(src, lr, warm_up_weight)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._body(src, lr, warm_up_weight)
+                eng.store.param.copy_(snap[0])
+                eng.store.m.copy_(snap[1])
+                eng.store.v.copy_(snap[2])
+                eng.store.step.copy_(snap[3])
+                for l, (mm, mv) in zip([l for l in eng.enc + eng.dec if l.bn], snap[4]):
+                    l.moving_mean.copy_(mm)
+                    l.moving_var.copy_(mv)
+                graphs[key] = (g, src)   # keep src alive: its buffers are baked into the graph
+            self._graph, self._graph_key = graphs[key][0], key
+        self._graph.replay()
+        return self.plan.bound

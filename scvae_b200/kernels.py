@@ -49,11 +49,12 @@ def _ld(t):
     return t.stride(0)
 
 
-def csr_densify(indptr, indices, values, rows, G, x, row_const=None):
+def csr_densify(indptr, indices, values, rows, G, x, row_const=None, rebase=False):
     B = x.shape[0]
     lib = _lib.load()
     _lib.check(lib.scvae_csr_densify(_p(indptr), _p(indices), _p(values), _p(rows), B, G, _p(x),
-                                     _ld(x), _p(row_const), _stream()), "csr_densify")
+                                     _ld(x), _p(row_const), int(rebase), _stream()),
+               "csr_densify")
 
 
 def gemm(layout, M, N, K, A, B, C, accumulate=False, tensor_cores=True, workspace=None):
@@ -181,7 +182,7 @@ def col_mean(x, rows, cols, out):
     _lib.check(lib.scvae_col_mean(_p(x), _ld(x), rows, cols, _p(out), _stream()), "col_mean")
 
 
-def fill_normal(out, seed, offset=0):
+def fill_normal(out, seed, offset=0, offset_dev=None):
     lib = _lib.load()
-    _lib.check(lib.scvae_fill_normal(_p(out), out.numel(), int(seed), int(offset), _stream()),
-               "fill_normal")
+    _lib.check(lib.scvae_fill_normal(_p(out), out.numel(), int(seed), int(offset),
+                                     _p(offset_dev), _stream()), "fill_normal")
