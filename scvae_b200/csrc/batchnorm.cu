@@ -69,22 +69,42 @@ bn_partial_kernel(const float *__restrict__ y, int64_t ldy, int n, int H, int nc
     }
 }
 
-// Combine chunk partials of one group/column in fixed order -> (mean, biased var).
-__device__ __forceinline__ void bn_combine(const float *pmean, const float *pm2, int group, int nchunks,
-                                           int n, int H32, int c, float &mean, float &var) {
-    float cnt = 0.f, mu = 0.f, m2 = 0.f;
-    for (int k = 0; k < nchunks; ++k) {
-        const int64_t o = ((int64_t)group * nchunks + k) * H32 + c;
-        const float nb = (float)(min((k + 1) * kBnRows, n) - k * kBnRows);
-        const float mb = pmean[o], qb = pm2[o];
-        const float tot = cnt + nb;
+// Chan's pairwise update of (count, mean, M2) with another partial (nb, mb, qb).
+__device__ __forceinline__ void chan_merge(float &cnt, float &mu, float &m2, float nb, float mb, float qb) {
+    const float tot = cnt + nb;
+    if (tot > 0.f) {
         const float delta = mb - mu;
-        mu += delta * (nb / tot);
-        m2 += qb + delta * delta * (cnt * nb / tot);
+        const float f = nb / tot;
+        mu += delta * f;
+        m2 += qb + delta * delta * (cnt * f);
         cnt = tot;
     }
+}
+
+// Combine the chunk partials of one group/column -> (mean, biased var).  The 8 row lanes of
+// the CTA each fold every 8th partial, then lane 0 folds the 8 results: fixed order
+// (deterministic), sequential depth nchunks/8 + 8 instead of nchunks.  All threads must call.
+__device__ __forceinline__ void bn_combine(const float *pmean, const float *pm2, int group, int nchunks,
+                                           int n, int H32, int c, bool ok, float (*sh)[3][kBnCols + 1],
+                                           float &mean, float &var) {
+    float cnt = 0.f, mu = 0.f, m2 = 0.f;
+    if (ok) {
+        for (int k = threadIdx.y; k < nchunks; k += kBnLanes) {
+            const int64_t o = ((int64_t)group * nchunks + k) * H32 + c;
+            const float nb = (float)(min((k + 1) * kBnRows, n) - k * kBnRows);
+            chan_merge(cnt, mu, m2, nb, pmean[o], pm2[o]);
+        }
+    }
+    sh[threadIdx.y][0][threadIdx.x] = cnt;
+    sh[threadIdx.y][1][threadIdx.x] = mu;
+    sh[threadIdx.y][2][threadIdx.x] = m2;
+    __syncthreads();
+    cnt = 0.f; mu = 0.f; m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kBnLanes; ++i)
+        chan_merge(cnt, mu, m2, sh[i][0][threadIdx.x], sh[i][1][threadIdx.x], sh[i][2][threadIdx.x]);
     mean = mu;
-    var = m2 / cnt;
+    var = cnt > 0.f ? m2 / cnt : 0.f;
 }
 
 __global__ void __launch_bounds__(kBnCols *kBnLanes)
@@ -94,30 +114,32 @@ bn_apply_kernel(const float *__restrict__ y, int64_t ldy, int n, int H, int nchu
                 const float *__restrict__ moving_var, int training, int relu,
                 float *__restrict__ out, int64_t ldo, float *__restrict__ save_mean,
                 float *__restrict__ save_rstd, float *__restrict__ var_unbiased) {
+    __shared__ float sh[kBnLanes][3][kBnCols + 1];
     const int c = blockIdx.y * kBnCols + threadIdx.x;
     const int chunk = blockIdx.x % nchunks, group = blockIdx.x / nchunks;
     const int r0 = chunk * kBnRows, r1 = min(r0 + kBnRows, n);
     const float *base = y + ((int64_t)group * n) * ldy;
     float *obase = out + ((int64_t)group * n) * ldo;
-    if (c >= ldo) return;
-    if (c >= H) {  // augmented columns
-        const float v = (c == H) ? 1.f : 0.f;
-        for (int r = r0 + threadIdx.y; r < r1; r += kBnLanes) obase[(int64_t)r * ldo + c] = v;
-        return;
-    }
-    float mean, rstd;
-    if (training) {
+    const bool ok = c < H;
+    float mean = 0.f, rstd = 1.f;
+    if (training) {  // uniform branch: every thread of the CTA takes part in the combine
         float var;
-        bn_combine(pmean, pm2, group, nchunks, n, H32, c, mean, var);
+        bn_combine(pmean, pm2, group, nchunks, n, H32, c, ok, sh, mean, var);
         rstd = rsqrtf(var + kBnEps);
-        if (chunk == 0 && threadIdx.y == 0) {
+        if (ok && chunk == 0 && threadIdx.y == 0) {
             save_mean[group * H + c] = mean;
             save_rstd[group * H + c] = rstd;
             var_unbiased[group * H32 + c] = var * ((float)n / (float)max(n - 1, 1));
         }
-    } else {
+    } else if (ok) {
         mean = moving_mean[c];
         rstd = rsqrtf(moving_var[c] + kBnEps);
+    }
+    if (c >= ldo) return;
+    if (!ok) {  // augmented columns
+        const float v = (c == H) ? 1.f : 0.f;
+        for (int r = r0 + threadIdx.y; r < r1; r += kBnLanes) obase[(int64_t)r * ldo + c] = v;
+        return;
     }
     const float bt = beta[c];
     for (int r = r0 + threadIdx.y; r < r1; r += kBnLanes) {
@@ -194,18 +216,31 @@ bn_bwd_apply_kernel(const float *__restrict__ dout, int64_t lddo, const float *_
     const int chunk = blockIdx.x % nchunks, group = blockIdx.x / nchunks;
     const int r0 = chunk * kBnRows, r1 = min(r0 + kBnRows, n);
     const int64_t g0 = (int64_t)group * n;
-    if (c >= H) return;
-    float s1 = 0.f, s2 = 0.f;
-    for (int k = 0; k < nchunks; ++k) {
-        const int64_t o = ((int64_t)group * nchunks + k) * H32 + c;
-        s1 += p1[o];
-        s2 += p2[o];
+    __shared__ float sh[kBnLanes][3][kBnCols + 1];
+    const bool ok = c < H;
+    float s1 = 0.f, s2 = 0.f, tot = 0.f;
+    if (ok) {
+        for (int k = threadIdx.y; k < nchunks; k += kBnLanes) {
+            const int64_t o = ((int64_t)group * nchunks + k) * H32 + c;
+            s1 += p1[o];
+            s2 += p2[o];
+        }
+        if (blockIdx.x == 0)
+            for (int k = threadIdx.y; k < groups * nchunks; k += kBnLanes) tot += p1[(int64_t)k * H32 + c];
     }
-    if (blockIdx.x == 0 && threadIdx.y == 0) {
-        float tot = 0.f;
-        for (int k = 0; k < groups * nchunks; ++k) tot += p1[(int64_t)k * H32 + c];
-        dbeta[c] = accumulate_dbeta ? dbeta[c] + tot : tot;
+    sh[threadIdx.y][0][threadIdx.x] = s1;
+    sh[threadIdx.y][1][threadIdx.x] = s2;
+    sh[threadIdx.y][2][threadIdx.x] = tot;
+    __syncthreads();
+    if (!ok) return;
+    s1 = 0.f; s2 = 0.f; tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kBnLanes; ++i) {
+        s1 += sh[i][0][threadIdx.x];
+        s2 += sh[i][1][threadIdx.x];
+        tot += sh[i][2][threadIdx.x];
     }
+    if (blockIdx.x == 0 && threadIdx.y == 0) dbeta[c] = accumulate_dbeta ? dbeta[c] + tot : tot;
     const float mean = save_mean[group * H + c], rstd = save_rstd[group * H + c];
     const float inv_n = 1.f / (float)n;
     const float m1 = s1 * inv_n, m2 = s2 * inv_n;

@@ -46,7 +46,8 @@ constexpr float kBnDecay = 0.999f;
 // ---- streaming 128-bit global access ----------------------------------------------------
 __device__ __forceinline__ float4 ldg_stream4(const float *p) {
     float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+    // not volatile: read-only data, so the compiler may hoist these above earlier stores (MLP)
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                  : "l"(p));
     return v;
@@ -82,22 +83,44 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
 }
 
 // ---- scalar math ------------------------------------------------------------------------
-// log1p for e in [0, 1]: exact-ish series below 2^-6, log(1+e) above.
-__device__ __forceinline__ float log1p_unit(float e) {
-    const float series = e * (1.f - e * (0.5f - e * (0.33333334f - 0.25f * e)));
-    const float direct = __logf(1.f + e);
-    return e < 0.015625f ? series : direct;
+// single-MUFU special functions (no denormal fix-up code around them)
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
-// softplus(a) = log(1 + exp(a)); also returns e = exp(-|a|) for the sigmoid.
+__device__ __forceinline__ float fast_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_exp(float x) { return fast_ex2(x * kLog2e); }
+// log1p(e) for e in [0, 1]: lg2(u) ln2 with u = 1 + e, plus the first-order compensation of
+// the rounding of u (e - (u - 1) is exact), which keeps small e accurate without a series.
+__device__ __forceinline__ float log1p_from_u(float e, float u) {
+    return fmaf(fast_lg2(u), kLn2, e - (u - 1.f));
+}
+// softplus(a) = log(1 + exp(a)); also returns e = exp(-|a|) and u = 1 + e for the sigmoid.
+__device__ __forceinline__ float softplus_eu(float a, float &e, float &u) {
+    e = fast_ex2(-fabsf(a) * kLog2e);
+    u = 1.f + e;
+    return fmaxf(a, 0.f) + log1p_from_u(e, u);
+}
 __device__ __forceinline__ float softplus_e(float a, float &e) {
-    e = __expf(-fabsf(a));
-    return fmaxf(a, 0.f) + log1p_unit(e);
+    float u;
+    return softplus_eu(a, e, u);
 }
-// sigmoid(a) from e = exp(-|a|)
-__device__ __forceinline__ float sigmoid_from_e(float a, float e) {
-    const float inv = __frcp_rn(1.f + e);
+// sigmoid(a) from e = exp(-|a|), u = 1 + e
+__device__ __forceinline__ float sigmoid_from_eu(float a, float e, float u) {
+    const float inv = fast_rcp(u);
     return a >= 0.f ? inv : e * inv;
 }
+__device__ __forceinline__ float sigmoid_from_e(float a, float e) { return sigmoid_from_eu(a, e, 1.f + e); }
 
 // Stirling series, z >= 8 (truncation error < 3e-8).
 __device__ __forceinline__ float lgamma_big(float z) {
@@ -135,25 +158,13 @@ __device__ __forceinline__ void lgamma_digamma_pos(float z, float &lg, float &dg
     }
 }
 // D = lgamma(r + x) - lgamma(r), P = digamma(r + x) - digamma(r), for r > 0, x > 0.
-// Cancellation-free for the common cases (small integer counts; large r).
-__device__ __forceinline__ void lgamma_diff(float r, float x, float &D, float &P) {
-    if (x <= 8.f && x == floorf(x)) {
-        // x integer in [1, 8]: Gamma(r+x)/Gamma(r) = prod_{i<x} (r+i)
-        float p = r, dp = 1.f;
-        const int n = (int)x;
-        for (int i = 1; i < n; ++i) {
-            const float f = r + (float)i;
-            dp = dp * f + p;
-            p = p * f;
-        }
-        D = logf(p);
-        P = __fdividef(dp, p);
-    } else if (r >= 8.f) {
+// Slow path (large or non-integer x): kept out of line, it is rare.
+static __device__ __noinline__ void lgamma_diff_slow(float r, float x, float &D, float &P) {
+    if (r >= 8.f) {  // cancellation-free Stirling difference
         const float s = r + x;
         const float q = __fdividef(x, r);
-        // log1p(q) for any q > 0
         const float l1p = q < 0.015625f ? q * (1.f - q * (0.5f - q * (0.33333334f - 0.25f * q)))
-                                        : __logf(1.f + q);
+                                        : logf(1.f + q);
         const float ir = __frcp_rn(r), is = __frcp_rn(s);
         const float ir2 = ir * ir, is2 = is * is;
         D = x * logf(s) + ((r - 0.5f) * l1p - x) +
@@ -167,6 +178,26 @@ __device__ __forceinline__ void lgamma_diff(float r, float x, float &D, float &P
         lgamma_digamma_pos(r, lg0, dg0);
         D = lg1 - lg0;
         P = dg1 - dg0;
+    }
+}
+// Fast path: x integer in [1, 8] (almost every non-zero single-cell count):
+// Gamma(r+x)/Gamma(r) = prod_{i<x} (r+i); its log-derivative is dp/p.
+__device__ __forceinline__ void lgamma_diff(float r, float x, float &D, float &P) {
+    const int n = (int)x;
+    if (x == (float)n && n <= 8) {
+        float p = r, dp = 1.f;
+#pragma unroll
+        for (int i = 1; i < 8; ++i) {
+            if (i < n) {
+                const float f = r + (float)i;
+                dp = fmaf(dp, f, p);
+                p = p * f;
+            }
+        }
+        D = fast_lg2(p) * kLn2;
+        P = dp * fast_rcp(p);
+    } else {
+        lgamma_diff_slow(r, x, D, P);
     }
 }
 

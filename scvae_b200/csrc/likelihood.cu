@@ -47,28 +47,30 @@ __device__ __forceinline__ void lik_elem(float x, const float (&a)[3], float &lp
         const float ap_raw = a[iD], ar_raw = a[iD + 1];
         const float ap = fmaxf(ap_raw, kLogitFloor);
         const float lr = fminf(fmaxf(ar_raw, -10.f), 10.f);
-        r = __expf(lr);
-        float e;
-        const float sp = softplus_e(ap, e);  // -log(1-p)
+        r = fast_ex2(lr * kLog2e);
+        float e, u;
+        const float sp = softplus_eu(ap, e, u);  // -log(1-p)
         l0 = -r * sp;
-        lp_d = l0 + x * (ap - sp);
+        // x == 1 (about half of all non-zero counts): lgamma(r+1) - lgamma(r) = log r exactly
+        const bool one = (x == 1.f);
+        lp_d = fmaf(x, ap - sp, l0) + (one ? lr : 0.f);
         if (BWD) {
-            const float p = sigmoid_from_e(ap, e);
+            const float p = sigmoid_from_eu(ap, e, u);
             const float mp = ap_raw < kLogitFloor ? 0.f : 1.f;
-            const float mr = clip_mask(ar_raw, -10.f, 10.f);
-            gd0 = (x - (x + r) * p) * mp;
-            gd1 = l0 * mr;
+            const float mr = fabsf(ar_raw) > 10.f ? 0.f : 1.f;
+            gd0 = fmaf(-(x + r), p, x) * mp;
+            gd1 = (l0 + (one ? 1.f : 0.f)) * mr;  // r (digamma(r+1) - digamma(r)) = 1
             cr = r * mr;
         }
     } else {
         const float al = a[iD];
         const float ll = fminf(fmaxf(al, -10.f), 10.f);
-        const float lam = __expf(ll);
+        const float lam = fast_ex2(ll * kLog2e);
         r = 0.f;
         cr = 0.f;
         l0 = -lam;
-        lp_d = x * ll - lam;
-        if (BWD) gd0 = (x - lam) * clip_mask(al, -10.f, 10.f);
+        lp_d = fmaf(x, ll, -lam);
+        if (BWD) gd0 = (x - lam) * (fabsf(al) > 10.f ? 0.f : 1.f);
     }
 
     if (!T::ZI) {
@@ -84,14 +86,14 @@ __device__ __forceinline__ void lik_elem(float x, const float (&a)[3], float &lp
     //   x <= 0: log(pi + (1-pi) exp(l0))        = softplus(l0 - a_pi) - softplus(-a_pi)
     const float api_raw = a[0];
     const float api = fmaxf(api_raw, kLogitFloor);
-    float e_pi, e_u;
-    const float sp_pi = softplus_e(api, e_pi);
+    float e_pi, u_pi, e_u, u_u;
+    const float sp_pi = softplus_eu(api, e_pi, u_pi);
     const float u = l0 - api;
-    const float sp_u = softplus_e(u, e_u);
+    const float sp_u = softplus_eu(u, e_u, u_u);
     lp = pos ? (lp_d - sp_pi) : (sp_u - (sp_pi - api));
     if (BWD) {
-        const float pi = sigmoid_from_e(api, e_pi);
-        const float wz = sigmoid_from_e(u, e_u);  // (1-pi) e^{l0} / (pi + (1-pi) e^{l0})
+        const float pi = sigmoid_from_eu(api, e_pi, u_pi);
+        const float wz = sigmoid_from_eu(u, e_u, u_u);  // (1-pi) e^{l0} / (pi + (1-pi) e^{l0})
         const float mpi = api_raw < kLogitFloor ? 0.f : 1.f;
         g[0] = (pos ? -pi : (1.f - pi) - wz) * mpi;
         const float w = pos ? 1.f : wz;
@@ -162,10 +164,11 @@ likelihood_kernel(const float *__restrict__ t, int64_t ldt, int t_rows,
                 gv[1][j] = g[1];
                 gv[2][j] = g[2];
             }
-            nz |= (x[j] > 0.f ? 1u : 0u) << j;
+            nz |= ((x[j] > 0.f && x[j] != 1.f) ? 1u : 0u) << j;
         }
-        // x > 0 entries (rare): lgamma / digamma differences, one entry per trip so that a
-        // warp loops max-popcount times instead of once per vector lane.
+        // counts >= 2 (rare): lgamma / digamma differences, one entry per trip so that a warp
+        // loops max-popcount times instead of once per vector lane (x == 1 is handled above;
+        // lgamma(1 + 1) = 0, so it needs no fix-up without the row constant either).
         if (T::NB || !has_const) {
             while (nz) {
                 const int j = __ffs(nz) - 1;

@@ -312,7 +312,9 @@ class VAEEngine:
         p.bwd_ready = True
 
     def _use_tc(self, M, N, Kd):
-        return self.tensor_cores and M * N * Kd >= (1 << 25)
+        """tcgen05 kernel for every product with a long reduction or a large tile count; the
+        exact-fp32 FFMA kernel keeps the tiny ones (e.g. 100 x 100 x 101 at minibatch 100)."""
+        return self.tensor_cores and (Kd >= 256 or M * N * Kd >= (1 << 22))
 
     def _gemm(self, p, layout, M, N, Kd, A, Bm, C, accumulate=False):
         tc = self._use_tc(M, N, Kd)
