@@ -398,6 +398,23 @@ class VAEEngine:
                         B, weight, p.bound, p.go if want_go else None)
         return p
 
+    def decode(self, p, rows):
+        """Decoder-only entry point (``session.run(p_x_mean, feed_dict={z: ...})``, VAE:1706-1721):
+        p.Z[:rows, :L] holds the latent samples; runs decoder + heads with moving statistics."""
+        K.act_fwd(p.Z[:rows], self.L, p.Z[:rows], relu=False)   # (re)write the augmented columns
+        d = p.Z
+        for j, l in enumerate(self.dec):
+            self._gemm(p, K.GEMM_NT, rows, l.n_out, l.n_in + 1, d, l.w, p.decY[j][:rows])
+            if l.bn:
+                K.bn_act_fwd(p.decY[j][:rows], l.n_out, l.beta, l.moving_mean, l.moving_var,
+                             p.decH[j][:rows], p.dec_mean[j], p.dec_rstd[j], p.bn_scratch,
+                             training=False, update_moving=False, relu=True)
+            else:
+                K.act_fwd(p.decY[j][:rows], l.n_out, p.decH[j][:rows], relu=True)
+            d = p.decH[j]
+        l = self.head
+        self._gemm(p, K.GEMM_NT, rows, l.n_out, l.n_in + 1, d, l.w, p.A[:rows])
+
     # ------------------------------------------------------------------ backward -----------
     def backward(self, p, R, S, warm_up_weight=1.0, dA_ready=False):
         """Gradients of -lower_bound_weighted w.r.t. every parameter into the flat grad buffer."""

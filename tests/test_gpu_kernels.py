@@ -194,6 +194,7 @@ def test_batch_norm(M, H, groups):
               "s/BATCH_NORM/moving_mean": torch.randn(H, dtype=torch.float64),
               "s/BATCH_NORM/moving_variance": torch.rand(H, dtype=torch.float64) + 0.5}
     upd = []
+    params_before = dict(params)
     out = torch.relu(O.batch_norm(y, "s", params, True, upd, groups))
     dout = torch.randn(M, H, dtype=torch.float64)
     (out * dout).sum().backward()
@@ -221,8 +222,16 @@ def test_batch_norm(M, H, groups):
     dbeta = torch.zeros(H, device=dev)
     K.bn_act_bwd(doutd, yd, outd, H, sm, sr, dy, dbeta, scratch, relu=True, groups=groups)
     scale = y.grad.abs().max().item()
-    assert (dy[:, :H].cpu().double() - y.grad).abs().max().item() <= 2e-5 * scale + 1e-6
-    assert torch.allclose(dbeta.cpu().double(), beta.grad, atol=1e-4 * beta.grad.abs().max().item())
+    # a pre-activation within fp32 rounding of 0 may take the other ReLU branch than the fp64
+    # oracle: exclude those (isolated) elements and the columns they feed
+    pre = O.batch_norm(y.detach(), "s", params_before, True, None, groups)
+    amb = pre.abs() < 1e-5
+    good_cols = ~amb.any(dim=0)
+    derr = (dy[:, :H].cpu().double() - y.grad).abs()
+    assert derr[:, good_cols].max().item() <= 2e-5 * scale + 1e-6
+    assert amb.sum().item() <= 3
+    assert torch.allclose(dbeta.cpu().double()[good_cols], beta.grad[good_cols],
+                          atol=1e-4 * beta.grad.abs().max().item())
     # eval mode uses the moving statistics
     out_eval = torch.relu(O.batch_norm(y.detach(), "s", params, False, None))
     K.bn_act_fwd(yd, H, betad, mm, mv, outd, sm, sr, scratch, training=False, relu=True)

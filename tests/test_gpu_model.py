@@ -1,0 +1,96 @@
+"""The reference-facing model class on the GPU: train / resume / evaluate / sample, on-disk
+contract (checkpoint naming, event tags) and epoch-level parity with the oracle."""
+import os
+
+import numpy
+import pytest
+import scipy.sparse
+import torch
+
+from oracle import scvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n=300, g=60, seed=3):
+    from scvae_b200.data_set import DataSet
+    x, labels = O.synthetic_counts(n, g, n_types=3, seed=seed, target_zero_fraction=0.8)
+    x = numpy.minimum(x, 50.0)
+    return DataSet("toy", values=scipy.sparse.csr_matrix(x), labels=labels.astype(str))
+
+
+def test_train_resume_evaluate_sample(tmp_path):
+    from scvae_b200.variational_autoencoder import VariationalAutoencoder
+    from scvae_b200 import model_utilities as MU
+    full = _data()
+    training, validation, test = full.split()
+    model = VariationalAutoencoder(
+        feature_size=60, latent_size=4, hidden_sizes=[32], reconstruction_distribution="negative binomial",
+        number_of_warm_up_epochs=2, log_directory=str(tmp_path), seed=1)
+    assert model.train(training, validation, number_of_epochs=3, minibatch_size=50,
+                       learning_rate=1e-2, shuffle_seed=0) == 0
+    directory = model.log_directory()
+    assert open(os.path.join(directory, "checkpoint")).readline().strip() == 'model_checkpoint_path: "model.ckpt-3"'
+    assert os.path.exists(os.path.join(directory, "model.ckpt-3.pt"))
+    assert not os.path.exists(os.path.join(directory, "model.ckpt-2.pt"))      # max_to_keep=1
+    assert os.path.isdir(os.path.join(directory, "best"))
+    assert model.has_been_trained()
+    curves = MU.load_learning_curves(model, ["training", "validation"])
+    assert len(curves["training"]["lower_bound"]) == 3
+    assert curves["training"]["lower_bound"][-1] > curves["training"]["lower_bound"][0]
+    assert MU.load_number_of_epochs_trained(model) == 3
+    kl = MU.load_kl_divergences(model, "training")
+    assert kl.shape == (3, 4)
+    assert os.path.exists(os.path.join(directory, "metadata_log-0-3.log"))
+    # resume: two more epochs, learning curve continues at step 4
+    assert model.train(training, validation, number_of_epochs=5, minibatch_size=50,
+                       learning_rate=1e-2, shuffle_seed=1) == 0
+    assert MU.load_number_of_epochs_trained(model) == 5
+    assert model.train(training, validation, number_of_epochs=5, minibatch_size=50) == 0  # no-op
+
+    transformed, reconstructed, latent = model.evaluate(
+        test, minibatch_size=64, evaluation_subset_indices={0, 5, 7}, output_versions="all")
+    assert transformed is test
+    assert reconstructed.values.shape == (test.number_of_examples, 60)
+    assert reconstructed.total_standard_deviations[5].toarray().max() > 0
+    assert reconstructed.total_standard_deviations[1].toarray().max() == 0
+    assert latent["z"].values.shape == (test.number_of_examples, 4)
+    assert numpy.isfinite(reconstructed.values).all()
+    ev = MU.load_learning_curves(model, "evaluation")
+    assert ev["lower_bound"] is not None
+    only_latent = model.evaluate(test, output_versions="latent", use_best_model=True)
+    assert set(only_latent) == {"z"}
+    sample_set, sample_latent = model.sample(sample_size=37, minibatch_size=16)
+    assert sample_set.values.shape == (37, 60) and sample_latent["z"].values.shape == (37, 4)
+    untrained = VariationalAutoencoder(feature_size=60, latent_size=3, log_directory=str(tmp_path))
+    with pytest.raises(Exception, match="not been trained"):
+        untrained.evaluate(test)
+
+
+def test_one_epoch_matches_oracle(tmp_path):
+    """train() for one epoch (2 steps) == oracle with the same permutation and noise."""
+    from scvae_b200.variational_autoencoder import VariationalAutoencoder
+    from scvae_b200 import kernels as K
+    ds = _data(n=200, g=48, seed=9)
+    model = VariationalAutoencoder(
+        feature_size=48, latent_size=3, hidden_sizes=[16], reconstruction_distribution="poisson",
+        log_directory=str(tmp_path), seed=4, tensor_cores=False)
+    model.train(ds, number_of_epochs=1, minibatch_size=100, learning_rate=1e-3, shuffle_seed=5,
+                noise_seed=21, use_cuda_graph=False)
+    cfg = O.VAEConfig(48, 3, [16], "poisson")
+    params = O.vae_init_params(cfg, seed=4, dtype=torch.float64)
+    state = O.AdamState(params)
+    perm = numpy.random.RandomState(5).permutation(200)
+    x = torch.tensor(ds.values.toarray(), dtype=torch.float64)
+    for step in range(2):
+        eps = torch.zeros(100, 3, device="cuda")
+        K.fill_normal(eps, 21, 0, torch.tensor([step], dtype=torch.int64, device="cuda"))
+        xb = x[perm[step * 100:(step + 1) * 100]]
+        O.train_step(cfg, params, state, xb, xb, eps.cpu().double().reshape(1, 100, 3), 1e-3)
+    got = model._get_engine().export_parameters()
+    for k, v in params.items():
+        assert (got[k].double() - v).abs().max().item() <= 2e-5 * max(v.abs().max().item(), 1.0), k
+    # the logged training ELBO is the eval-mode pass with the reference's N/B divisor (A.7)
+    from scvae_b200 import model_utilities as MU
+    logged = MU.load_learning_curves(model, "training")["lower_bound"][0]
+    assert numpy.isfinite(logged)

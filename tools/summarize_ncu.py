@@ -28,6 +28,8 @@ FULL_METRICS = [
 
 def launches(src, dst, title):
     lines = [l for l in open(src) if not l.startswith("==")]
+    while lines and "Kernel Name" not in lines[0]:
+        lines.pop(0)
     agg = collections.OrderedDict()
     order = []
     for row in csv.DictReader(lines):
