@@ -168,6 +168,51 @@ int scvae_adam_clip_step(float *param, const float *grad, float *m, float *v, in
                          float epsilon, float clip, float grad_scale, void *stream);
 int scvae_step_advance(int64_t *step, void *stream);
 
+/* ---- a9/a10: Gaussian-mixture VAE pieces  (GMVAE:2788-3434) ------------------------------
+ * The K cluster passes are K consecutive row groups of one tall matrix, rows ordered
+ * (k, sample, cell); dense layers / batch norm (groups = K) / likelihood are shared with the VAE.
+ *
+ * group_offset: y[k*B + b, :H] = x[b, :H] + t[k, :H]  -- the one-hot concat [x, e_k] of
+ * GMVAE:2942-2947 (t = rows of the weight block acting on e_k; x W_x is computed once).
+ * Backward: dx[b] = sum_k dy[k*B+b] (nullable), dt[k] = sum_b dy[k*B+b] (nullable, += if
+ * accumulate_dt).  With B == 1 it is FC(one_hot_k) = W[k] + b of GMVAE:3009-3048. */
+int scvae_group_offset_fwd(const float *x, int64_t ldx, const float *t, int64_t ldt, int K,
+                           int B, int H, float *y, int64_t ldy, void *stream);
+int scvae_group_offset_bwd(const float *dy, int64_t lddy, int K, int B, int H, float *dx,
+                           int64_t lddx, float *dt, int64_t lddt, int accumulate_dt,
+                           void *stream);
+/* q(y|x) = Cat(logits)  (GMVAE:3050-3092): y, logy (B, K) contiguous. */
+int scvae_softmax_fwd(const float *logits, int64_t ldl, int B, int K, float *y, float *logy,
+                      void *stream);
+/* q(z|x,y=k) = N(mean, sqrt(softplus(s))), z = mean + scale*eps, sampled
+ * KL_z = sum_l log q(z) - log p(z|y=k)  (GMVAE:2936-3048, 3270-3289; DU:52-73).
+ * qh (K*B, ldq) = [mean | s]; pz (K, 2L) contiguous = [mean | s] of p(z|y=k);
+ * eps (K*RS*B, L); z (K*RS*B, ldz) augmented; klz [K*RS*B]; kl_elem nullable (K*RS*B, L). */
+int scvae_gmvae_latent_fwd(const float *qh, int64_t ldq, const float *pz, int K, int B, int L,
+                           int RS, const float *eps, float *z, int64_t ldz, float *klz,
+                           float *kl_elem, void *stream);
+/* coef [K*RS*B] = d loss / d klz; dz decoder gradient; dqh (K*B, lddq), dpz (K, 2L). */
+int scvae_gmvae_latent_bwd(const float *qh, int64_t ldq, const float *pz, int K, int B, int L,
+                           int RS, const float *eps, const float *dz, int64_t lddz,
+                           const float *coef, float *dqh, int64_t lddq, float *dpz,
+                           void *stream);
+/* go = -y[b,k]/(B RS) (gradient of the loss w.r.t. each row's log-likelihood),
+ * coef = weight * y[b,k]/(B RS) (w.r.t. each row's KL_z); both [K*RS*B]. */
+int scvae_gmvae_row_coefficients(const float *y, int K, int RS, int B, float weight, float *go,
+                                 float *coef, void *stream);
+/* y-marginalised bound (GMVAE:3242-3410). logp, klz [K*RS*B]; log_py [K] (log prior
+ * probabilities; -log K for the uniform prior). out[6] = {lower_bound, lower_bound_weighted,
+ * reconstruction_error, kl_divergence_z, kl_divergence_y, kl_divergence_y after free nats}.
+ * dlogits (nullable, (B,K)), dpy_logits (nullable, [K]); ll_mean, klz_mean (K, B) scratch /
+ * outputs (sample means, not y-weighted). */
+int scvae_gmvae_bound(const float *y, const float *logy, const float *logp, const float *klz,
+                      const float *log_py, int K, int RS, int B, float weight,
+                      float free_nats_threshold, int uniform_prior, float *out, float *dlogits,
+                      float *dpy_logits, float *ll_mean, float *klz_mean, void *stream);
+/* z_mean[b] = sum_k y[b,k] mean_k[b]  (GMVAE:2896-2899); z_mean (B, L) contiguous. */
+int scvae_gmvae_z_mean(const float *qh, int64_t ldq, const float *y, int K, int B, int L,
+                       float *z_mean, void *stream);
+
 /* ---- small helpers used by the shells ------------------------------------------------- */
 /* out[c] = (1/rows) * sum_r x[r, c]  (kl_divergence_neurons, VAE:2643-2646). */
 int scvae_col_mean(const float *x, int64_t ldx, int rows, int cols, float *out,

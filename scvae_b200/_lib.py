@@ -52,6 +52,19 @@ SIGNATURES = {
     "scvae_adam_clip_step": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_f32, c_f32,
                                      c_f32, c_f32, c_f32, c_f32, c_ptr]),
     "scvae_step_advance": (c_int, [c_ptr, c_ptr]),
+    "scvae_group_offset_fwd": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_i64,
+                                       c_ptr]),
+    "scvae_group_offset_bwd": (c_int, [c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_i64, c_ptr, c_i64,
+                                       c_int, c_ptr]),
+    "scvae_softmax_fwd": (c_int, [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "scvae_gmvae_latent_fwd": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr,
+                                       c_i64, c_ptr, c_ptr, c_ptr]),
+    "scvae_gmvae_latent_bwd": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr,
+                                       c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    "scvae_gmvae_row_coefficients": (c_int, [c_ptr, c_int, c_int, c_int, c_f32, c_ptr, c_ptr, c_ptr]),
+    "scvae_gmvae_bound": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_f32,
+                                  c_f32, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "scvae_gmvae_z_mean": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr]),
     "scvae_col_mean": (c_int, [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr]),
     "scvae_fill_normal": (c_int, [c_ptr, c_i64, c_u64, c_u64, c_ptr, c_ptr]),
 }

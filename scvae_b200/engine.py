@@ -241,6 +241,9 @@ class VAEEngine:
                 layer.moving_mean.copy_(sd[layer.name + "/moving_mean"])
                 layer.moving_var.copy_(sd[layer.name + "/moving_variance"])
 
+    def bn_layers(self):
+        return [l for l in self.enc + self.dec if l.bn]
+
     @property
     def global_step(self):
         return int(self.store.step.item())

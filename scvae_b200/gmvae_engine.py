@@ -1,0 +1,501 @@
+"""Step engine of the Gaussian-mixture VAE: the graph of
+``GaussianMixtureVariationalAutoencoder._setup_model_graph/_setup_loss_function``
+(scvae/models/gaussian_mixture_variational_autoencoder.py:2788-3434) as a fixed launch sequence.
+
+Batching of the K cluster passes (the GMVAE hot loop): all K passes of
+q(z|x,y=k) and p(x|z_k) share weights, so they run as K consecutive row groups of one tall
+matrix (rows ordered (k, sample, cell)) through the same GEMM / batch-norm (groups = K) /
+likelihood kernels as the VAE.  ``x W_x`` of the first q(z|x,y) layer is computed once and the
+one-hot part of the concat [x, e_k] becomes a per-group row offset.  The decoder + heads +
+likelihood + their backward are processed in chunks of clusters so that the (rows x P*genes)
+head buffers stay bounded; weight gradients accumulate across chunks inside the GEMM epilogue
+(TMA reduce-add).
+"""
+
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import kernels as K
+from .engine import (ADAM_BETA1, ADAM_BETA2, ADAM_EPSILON, GRADIENT_CLIP, ParameterStore, VAEEngine,
+                     _Layer, aug, round4)
+
+
+class GMVAEEngine(VAEEngine):
+    def __init__(self, feature_size, latent_size, number_of_latent_clusters, hidden_sizes=(100,),
+                 reconstruction_distribution="poisson", minibatch_normalisation=True, kl_weight=1.0,
+                 prior_probabilities_method="uniform", prior_probabilities=None,
+                 proportion_of_free_nats_for_y_kl_divergence=0.0, device="cuda", seed=0,
+                 tensor_cores=True, head_buffer_bytes=4 << 30):
+        if reconstruction_distribution not in K.LIKELIHOOD_KINDS:
+            raise ValueError("reconstruction distribution `{}` is not supported by the "
+                             "B200 hot path".format(reconstruction_distribution))
+        if prior_probabilities_method not in ("uniform", "learn", "custom"):
+            raise ValueError("unknown prior probabilities method `{}`".format(
+                prior_probabilities_method))
+        self.G, self.L, self.K = int(feature_size), int(latent_size), int(number_of_latent_clusters)
+        self.hidden_sizes = [int(h) for h in hidden_sizes]
+        if not self.hidden_sizes:
+            raise ValueError("the GMVAE engine needs at least one hidden layer")
+        self.kind_name = reconstruction_distribution
+        self.kind = K.LIKELIHOOD_KINDS[reconstruction_distribution]
+        self.heads = K.LIKELIHOOD_HEADS[reconstruction_distribution]
+        self.P = len(self.heads)
+        self.bn = bool(minibatch_normalisation)
+        self.kl_weight = float(kl_weight)
+        self.prior_method = prior_probabilities_method
+        self.free_nats = float(proportion_of_free_nats_for_y_kl_divergence)
+        self.device = torch.device(device)
+        self.tensor_cores = bool(tensor_cores)
+        self.head_buffer_bytes = int(head_buffer_bytes)
+        self.Gn, self.Gp = round4(self.G), aug(self.G)
+        self.world_size, self._all_reduce, self._plans = 1, None, {}
+        self.unit_variance = False
+        self.nL = 2 * self.L
+
+        def stack(prefix, first_in):
+            layers, width = [], first_in
+            for i, h in enumerate(self.hidden_sizes):
+                layers.append(_Layer("{}/LAYER_{}".format(prefix, i + 1), width, h, self.bn))
+                width = h
+            return layers, width
+
+        self.qy_enc, width = stack("Y/CATEGORICAL/ENCODER", self.G)
+        self.qy_logits = _Layer("Y/CATEGORICAL/LOGITS", width, self.K, False)
+        self.qz_enc, width = stack("Z/Q/ENCODER", self.G)
+        self.qz_head = _Layer("Z/Q/SOFTPLUS_GAUSSIAN", width, 2 * self.L, False)
+        self.dec, width = [], self.L
+        for i, h in enumerate(self.hidden_sizes[::-1]):
+            self.dec.append(_Layer("X/DECODER/LAYER_{}".format(i + 1), width, h, self.bn))
+            width = h
+        self.head = _Layer("X/DISTRIBUTION", width, self.P * self.Gn, False)
+        self.enc = self.qy_enc + self.qz_enc          # every batch-normed encoder layer
+        self._dense = self.qy_enc + [self.qy_logits] + self.qz_enc + [self.qz_head] + self.dec + \
+            [self.head]
+
+        H1p = round4(self.hidden_sizes[0])
+        store = ParameterStore(self.device)
+        for layer in self._dense:
+            store.add(layer.name + "/W", (layer.n_out, layer.in_p))
+            if layer.bn:
+                store.add(layer.name + "/beta", (layer.n_out,))
+        store.add("Z/Q/WY", (self.K, H1p))            # rows of LAYER_1 weights acting on e_k
+        store.add("Z/P/W", (self.K, 2 * self.L))      # p(z|y): [mean | softplus_scale] weights
+        store.add("Z/P/B", (1, 2 * self.L))
+        if self.prior_method == "learn":
+            store.add("Y/P/LOGITS", (self.K,))
+        store.allocate()
+        self.store = store
+        for layer in self._dense:
+            layer.w = store.view(store.param, layer.name + "/W")
+            layer.dw = store.view(store.grad, layer.name + "/W")
+            if layer.bn:
+                layer.beta = store.view(store.param, layer.name + "/beta")
+                layer.dbeta = store.view(store.grad, layer.name + "/beta")
+                layer.moving_mean = torch.zeros(layer.n_out, dtype=torch.float32, device=self.device)
+                layer.moving_var = torch.ones(layer.n_out, dtype=torch.float32, device=self.device)
+        for key, attr in (("Z/Q/WY", "qz_wy"), ("Z/P/W", "pz_w"), ("Z/P/B", "pz_b")):
+            setattr(self, attr, store.view(store.param, key))
+            setattr(self, "d_" + attr, store.view(store.grad, key))
+        if self.prior_method == "learn":
+            self.py_logits = store.view(store.param, "Y/P/LOGITS")
+            self.d_py_logits = store.view(store.grad, "Y/P/LOGITS")
+        else:
+            self.py_logits = self.d_py_logits = None
+        if self.prior_method == "custom":
+            probs = torch.as_tensor(prior_probabilities, dtype=torch.float64)
+            self.log_py = torch.log(probs / probs.sum()).float().to(self.device)
+        else:
+            self.log_py = torch.full((self.K,), -math.log(self.K), dtype=torch.float32,
+                                     device=self.device)
+        self.initialise(seed)
+
+    # ------------------------------------------------------------------ parameters ---------
+    def _tf_dense(self):
+        """(layer, output-row slice, TF scope, input-row slice of the TF weight) in the
+        reference's variable creation order (GMVAE:2788-2934)."""
+        out = []
+        for layer in self.qy_enc:
+            out.append((layer, slice(0, layer.n_out), layer.name, slice(0, layer.n_in)))
+        out.append((self.qy_logits, slice(0, self.K), self.qy_logits.name, slice(0, self.qy_logits.n_in)))
+        for layer in self.qz_enc:
+            out.append((layer, slice(0, layer.n_out), layer.name, slice(0, layer.n_in)))
+        base = "Z/Q/SOFTPLUS_GAUSSIAN/"
+        n_in = self.qz_head.n_in
+        out.append((self.qz_head, slice(0, self.L), base + "MEAN", slice(0, n_in)))
+        out.append((self.qz_head, slice(self.L, 2 * self.L), base + "SOFTPLUS_SCALE", slice(0, n_in)))
+        return out
+
+    def _tf_tail(self):
+        out = [(layer, slice(0, layer.n_out), layer.name, slice(0, layer.n_in)) for layer in self.dec]
+        for p, head in enumerate(self.heads):
+            out.append((self.head, slice(p * self.Gn, p * self.Gn + self.G),
+                        "X/DISTRIBUTION/" + head.upper(), slice(0, self.head.n_in)))
+        return out
+
+    def initialise(self, seed=0):
+        gen = torch.Generator().manual_seed(int(seed))
+
+        def xavier(fan_in, fan_out):
+            limit = math.sqrt(6.0 / (fan_in + fan_out))
+            w = torch.rand((fan_in, fan_out), generator=gen, dtype=torch.float64)
+            return ((2.0 * w - 1.0) * limit).float()
+
+        params = OrderedDict()
+        if self.prior_method == "learn":
+            params["Y/P/LOGITS"] = torch.zeros(self.K)
+        for layer, rows, scope, _ in self._tf_dense():
+            fan_in = layer.n_in + (self.K if scope == "Z/Q/ENCODER/LAYER_1" else 0)
+            params[scope + "/DENSE/weights"] = xavier(fan_in, rows.stop - rows.start)
+            params[scope + "/DENSE/biases"] = torch.zeros(rows.stop - rows.start)
+            if scope == "Z/Q/SOFTPLUS_GAUSSIAN/SOFTPLUS_SCALE":
+                for name in ("MEAN", "SOFTPLUS_SCALE"):
+                    params["Z/P/SOFTPLUS_GAUSSIAN/{}/DENSE/weights".format(name)] = xavier(self.K, self.L)
+                    params["Z/P/SOFTPLUS_GAUSSIAN/{}/DENSE/biases".format(name)] = torch.zeros(self.L)
+        for layer, rows, scope, _ in self._tf_tail():
+            params[scope + "/DENSE/weights"] = xavier(layer.n_in, rows.stop - rows.start)
+            params[scope + "/DENSE/biases"] = torch.zeros(rows.stop - rows.start)
+        self.import_parameters(params, strict=False)
+        for buf in (self.store.grad, self.store.m, self.store.v):
+            buf.zero_()
+        self.store.step.zero_()
+        for layer in self.bn_layers():
+            layer.beta.zero_()
+            layer.moving_mean.zero_()
+            layer.moving_var.fill_(1.0)
+
+    def import_parameters(self, params, strict=True):
+        dev = self.device
+        for layer, rows, scope, _ in self._tf_dense() + self._tf_tail():
+            w = params[scope + "/DENSE/weights"].to(dev, torch.float32)
+            b = params[scope + "/DENSE/biases"].to(dev, torch.float32)
+            if scope == "Z/Q/ENCODER/LAYER_1":       # rows [G, G+K) act on the one-hot e_k
+                self.qz_wy[:, :layer.n_out] = w[self.G:]
+                self.qz_wy[:, layer.n_out:] = 0
+                w = w[:self.G]
+            layer.w[rows, :layer.n_in] = w.t()
+            layer.w[rows, layer.n_in] = b
+            layer.w[rows, layer.n_in + 1:] = 0
+            if layer.bn:
+                for key, dst in (("beta", layer.beta), ("moving_mean", layer.moving_mean),
+                                 ("moving_variance", layer.moving_var)):
+                    name = scope + "/BATCH_NORM/" + key
+                    if name in params:
+                        dst.copy_(params[name].to(dev, torch.float32))
+                    elif strict:
+                        raise KeyError(name)
+        for j, name in enumerate(("MEAN", "SOFTPLUS_SCALE")):
+            cols = slice(j * self.L, (j + 1) * self.L)
+            scope = "Z/P/SOFTPLUS_GAUSSIAN/" + name
+            self.pz_w[:, cols] = params[scope + "/DENSE/weights"].to(dev, torch.float32)
+            self.pz_b[0, cols] = params[scope + "/DENSE/biases"].to(dev, torch.float32)
+        if self.prior_method == "learn" and "Y/P/LOGITS" in params:
+            self.py_logits.copy_(params["Y/P/LOGITS"].to(dev, torch.float32))
+
+    def _export(self, grads):
+        out = OrderedDict()
+        pick = (lambda l: l.dw) if grads else (lambda l: l.w)
+        if self.prior_method == "learn":
+            out["Y/P/LOGITS"] = (self.d_py_logits if grads else self.py_logits).cpu().clone()
+
+        def dense(layer, rows, scope):
+            w = pick(layer)[rows, :layer.n_in].t().contiguous().cpu()
+            if scope == "Z/Q/ENCODER/LAYER_1":
+                wy = (self.d_qz_wy if grads else self.qz_wy)[:, :layer.n_out].cpu()
+                w = torch.cat([w, wy], dim=0)
+            out[scope + "/DENSE/weights"] = w
+            out[scope + "/DENSE/biases"] = pick(layer)[rows, layer.n_in].contiguous().cpu()
+            if layer.bn:
+                out[scope + "/BATCH_NORM/beta"] = (layer.dbeta if grads else layer.beta).cpu().clone()
+                if not grads:
+                    out[scope + "/BATCH_NORM/moving_mean"] = layer.moving_mean.cpu().clone()
+                    out[scope + "/BATCH_NORM/moving_variance"] = layer.moving_var.cpu().clone()
+
+        for layer, rows, scope, _ in self._tf_dense():
+            dense(layer, rows, scope)
+        for j, name in enumerate(("MEAN", "SOFTPLUS_SCALE")):
+            cols = slice(j * self.L, (j + 1) * self.L)
+            scope = "Z/P/SOFTPLUS_GAUSSIAN/" + name
+            out[scope + "/DENSE/weights"] = (self.d_pz_w if grads else self.pz_w)[:, cols].cpu().clone()
+            out[scope + "/DENSE/biases"] = (self.d_pz_b if grads else self.pz_b)[0, cols].cpu().clone()
+        for layer, rows, scope, _ in self._tf_tail():
+            dense(layer, rows, scope)
+        return out
+
+    def export_parameters(self):
+        return self._export(False)
+
+    def export_gradients(self):
+        return self._export(True)
+
+    # ------------------------------------------------------------------ buffers ------------
+    def _plan(self, B, RS):
+        key = (B, RS)
+        if key in self._plans:
+            return self._plans[key]
+        dev, f32 = self.device, torch.float32
+        Kc, L = self.K, self.L
+        KB, M = Kc * B, Kc * RS * B
+        # clusters per decoder chunk: bound the two (rows, P*Gn) head buffers
+        per_cluster = RS * B * self.P * self.Gn * 4 * 2
+        chunk = max(1, min(Kc, self.head_buffer_bytes // max(per_cluster, 1)))
+        p = type("Plan", (), {})()
+        p.B, p.RS, p.M, p.KB, p.chunk = B, RS, M, KB, chunk
+        Mc = chunk * RS * B
+
+        def zeros(*shape):
+            return torch.zeros(*shape, dtype=f32, device=dev)
+
+        p.X = zeros(B, self.Gp)
+        p.X[:, self.G] = 1.0
+        p.T, p.use_T = None, False
+        p.row_const, p.have_row_const = zeros(B), False
+        # q(y|x)
+        p.qyY = [zeros(B, round4(l.n_out)) for l in self.qy_enc]
+        p.qyH = [zeros(B, aug(l.n_out)) for l in self.qy_enc]
+        p.qy_mean = [zeros(l.n_out) for l in self.qy_enc]
+        p.qy_rstd = [zeros(l.n_out) for l in self.qy_enc]
+        p.logits = zeros(B, round4(Kc))
+        p.y, p.logy = zeros(B, Kc), zeros(B, Kc)
+        # q(z|x,y)
+        H1 = self.hidden_sizes[0]
+        p.XW = zeros(B, round4(H1))
+        p.qzY = [zeros(KB, round4(l.n_out)) for l in self.qz_enc]
+        p.qzH = [zeros(KB, aug(l.n_out)) for l in self.qz_enc]
+        p.qz_mean = [zeros(Kc * l.n_out) for l in self.qz_enc]
+        p.qz_rstd = [zeros(Kc * l.n_out) for l in self.qz_enc]
+        p.QH = zeros(KB, round4(2 * L))
+        p.PZ = zeros(Kc, 2 * L)
+        p.eps = zeros(M, L)
+        p.Z = zeros(M, aug(L))
+        p.klz = zeros(M)
+        p.kl_elem = None
+        p.go, p.coef, p.logp = zeros(M), zeros(M), zeros(M)
+        # decoder chunk buffers
+        p.decY = [zeros(Mc, round4(l.n_out)) for l in self.dec]
+        p.decH = [zeros(Mc, aug(l.n_out)) for l in self.dec]
+        p.dec_mean = [zeros(chunk * l.n_out) for l in self.dec]
+        p.dec_rstd = [zeros(chunk * l.n_out) for l in self.dec]
+        p.A = zeros(Mc, self.P * self.Gn)
+        p.bound = zeros(6)
+        p.ll_mean, p.klz_mean = zeros(Kc, B), zeros(Kc, B)
+        p.z_mean = zeros(B, L)
+        scratch = 1
+        for l in self.qy_enc:
+            scratch = max(scratch, K.bn_scratch_floats(B, l.n_out, 1))
+        for l in self.qz_enc:
+            scratch = max(scratch, K.bn_scratch_floats(KB, l.n_out, Kc))
+        for l in self.dec:
+            scratch = max(scratch, K.bn_scratch_floats(Mc, l.n_out, chunk))
+        p.bn_scratch = zeros(scratch)
+        p.workspace, p.ws_bytes = None, 0
+        p.bwd_ready = False
+        self._plans[key] = p
+        return p
+
+    def _plan_backward(self, p):
+        if p.bwd_ready:
+            return
+        dev, f32 = self.device, torch.float32
+
+        def zeros(*shape):
+            return torch.zeros(*shape, dtype=f32, device=dev)
+
+        B, KB, M, Kc, L = p.B, p.KB, p.M, self.K, self.L
+        Mc = p.chunk * p.RS * B
+        p.dA = zeros(Mc, self.P * self.Gn)
+        p.d_decH = [zeros(Mc, aug(l.n_out)) for l in self.dec]
+        p.d_decY = [zeros(Mc, round4(l.n_out)) for l in self.dec]
+        p.dZ = zeros(M, aug(L))
+        p.dQH = zeros(KB, round4(2 * L))
+        p.dPZ = zeros(Kc, 2 * L)
+        p.d_qzH = [zeros(KB, aug(l.n_out)) for l in self.qz_enc]
+        p.d_qzY = [zeros(KB, round4(l.n_out)) for l in self.qz_enc]
+        p.dXW = zeros(B, round4(self.hidden_sizes[0]))
+        p.dlogits = zeros(B, round4(Kc))
+        p.dlogits_c = zeros(B, Kc)
+        p.d_qyH = [zeros(B, aug(l.n_out)) for l in self.qy_enc]
+        p.d_qyY = [zeros(B, round4(l.n_out)) for l in self.qy_enc]
+        p.bwd_ready = True
+
+    # ------------------------------------------------------------------ layer helpers -------
+    def _bn_fwd(self, p, layer, Y, H, mean, rstd, training, update_moving, groups):
+        if layer.bn:
+            K.bn_act_fwd(Y, layer.n_out, layer.beta, layer.moving_mean, layer.moving_var, H, mean,
+                         rstd, p.bn_scratch, training=training, update_moving=update_moving,
+                         relu=True, groups=groups)
+        else:
+            K.act_fwd(Y, layer.n_out, H, relu=True)
+
+    def _bn_bwd(self, p, layer, dH, Y, H, mean, rstd, dY, groups, accumulate):
+        if layer.bn:
+            K.bn_act_bwd(dH, Y, H, layer.n_out, mean, rstd, dY, layer.dbeta, p.bn_scratch,
+                         relu=True, groups=groups, accumulate_dbeta=accumulate)
+        else:
+            K.act_bwd(dH, H, layer.n_out, dY, relu=True)
+
+    # ------------------------------------------------------------------ forward ------------
+    def forward(self, p, is_training, R, S, warm_up_weight=1.0, update_moving=None,
+                with_backward=False, deterministic=False):
+        """Full pass; with ``with_backward`` the decoder chunks also run their backward (the
+        gradient of each row's log-likelihood, -y_bk/(B RS), is known before the decoder runs)."""
+        if deterministic:
+            raise NotImplementedError("the GMVAE graph has no deterministic-z mode (as in the "
+                                      "reference)")
+        B, Kc, L, RS = p.B, self.K, self.L, p.RS
+        KB = p.KB
+        if update_moving is None:
+            update_moving = is_training
+        weight = warm_up_weight * self.kl_weight
+        if with_backward:
+            self._plan_backward(p)
+        # --- q(y|x) ---------------------------------------------------------------------------
+        h = p.X
+        for i, l in enumerate(self.qy_enc):
+            self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, h, l.w, p.qyY[i])
+            self._bn_fwd(p, l, p.qyY[i], p.qyH[i], p.qy_mean[i], p.qy_rstd[i], is_training,
+                         update_moving, 1)
+            h = p.qyH[i]
+        l = self.qy_logits
+        self._gemm(p, K.GEMM_NT, B, Kc, l.n_in + 1, h, l.w, p.logits)
+        K.softmax_fwd(p.logits, B, Kc, p.y, p.logy)
+        if self.prior_method == "learn":
+            self._refresh_log_py()
+        # --- q(z|x, y=k) for all k ----------------------------------------------------------
+        l = self.qz_enc[0]
+        self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, p.X, l.w, p.XW)
+        K.group_offset_fwd(p.XW, self.qz_wy, Kc, B, l.n_out, p.qzY[0])
+        self._bn_fwd(p, l, p.qzY[0], p.qzH[0], p.qz_mean[0], p.qz_rstd[0], is_training,
+                     update_moving, Kc)
+        for i in range(1, len(self.qz_enc)):
+            l = self.qz_enc[i]
+            self._gemm(p, K.GEMM_NT, KB, l.n_out, l.n_in + 1, p.qzH[i - 1], l.w, p.qzY[i])
+            self._bn_fwd(p, l, p.qzY[i], p.qzH[i], p.qz_mean[i], p.qz_rstd[i], is_training,
+                         update_moving, Kc)
+        l = self.qz_head
+        self._gemm(p, K.GEMM_NT, KB, l.n_out, l.n_in + 1, p.qzH[-1], l.w, p.QH)
+        # --- p(z|y=k) = FC(e_k) ---------------------------------------------------------------
+        K.group_offset_fwd(self.pz_b, self.pz_w, Kc, 1, 2 * L, p.PZ)
+        K.gmvae_latent_fwd(p.QH, p.PZ, Kc, B, L, RS, p.eps, p.Z, p.klz, p.kl_elem)
+        K.gmvae_row_coefficients(p.y, Kc, RS, B, weight, p.go, p.coef)
+        # --- p(x|z_k): decoder + heads + likelihood, cluster chunk by cluster chunk -----------
+        tgt = p.T if p.use_T else p.X
+        rc = p.row_const if p.have_row_const else None
+        rows_per_k = RS * B
+        for c0 in range(0, Kc, p.chunk):
+            kc = min(p.chunk, Kc - c0)
+            r0, rows = c0 * rows_per_k, kc * rows_per_k
+            d = p.Z[r0:r0 + rows]
+            for j, l in enumerate(self.dec):
+                self._gemm(p, K.GEMM_NT, rows, l.n_out, l.n_in + 1, d, l.w, p.decY[j][:rows])
+                self._bn_fwd(p, l, p.decY[j][:rows], p.decH[j][:rows], p.dec_mean[j], p.dec_rstd[j],
+                             is_training, update_moving, kc)
+                d = p.decH[j]
+            l = self.head
+            self._gemm(p, K.GEMM_NT, rows, l.n_out, l.n_in + 1, d, l.w, p.A[:rows])
+            if with_backward:
+                K.likelihood_bwd(self.kind, tgt, p.A[:rows], self.Gn, rows, self.G, p.dA[:rows],
+                                 logp=p.logp[r0:r0 + rows], row_const=rc, go=p.go[r0:r0 + rows])
+                self._decoder_backward(p, r0, rows, kc, accumulate=c0 > 0)
+            else:
+                K.likelihood_fwd(self.kind, tgt, p.A[:rows], self.Gn, rows, self.G,
+                                 p.logp[r0:r0 + rows], row_const=rc)
+            if getattr(p, "on_chunk", None) is not None:
+                p.on_chunk(c0, kc, rows)
+        thr = 0.0
+        if self.free_nats:
+            # threshold = proportion * H[p(y)] (GMVAE:3260-3261)
+            thr = self.free_nats * float(-(torch.exp(self.log_py) * self.log_py).sum())
+        K.gmvae_bound(p.y, p.logy, p.logp, p.klz, self.log_py, Kc, RS, B, weight, thr,
+                      self.prior_method == "uniform", p.bound,
+                      p.dlogits_c if with_backward else None,
+                      self.d_py_logits if (with_backward and self.prior_method == "learn") else None,
+                      p.ll_mean, p.klz_mean)
+        return p
+
+    def _refresh_log_py(self):
+        # log_softmax of K learned logits (K floats: host-side glue of the shell)
+        self.log_py = torch.log_softmax(self.py_logits.detach(), dim=0)
+
+    def _decoder_backward(self, p, r0, rows, kc, accumulate):
+        l = self.head
+        d_in = p.decH[-1] if self.dec else p.Z[r0:r0 + rows]
+        dd_in = p.d_decH[-1] if self.dec else p.dZ[r0:r0 + rows]
+        self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, rows, p.dA[:rows], d_in[:rows], l.dw,
+                   accumulate=accumulate)
+        self._gemm(p, K.GEMM_NN, rows, l.n_in, l.n_out, p.dA[:rows], l.w, dd_in[:rows])
+        for j in range(len(self.dec) - 1, -1, -1):
+            l = self.dec[j]
+            self._bn_bwd(p, l, p.d_decH[j][:rows], p.decY[j][:rows], p.decH[j][:rows],
+                         p.dec_mean[j], p.dec_rstd[j], p.d_decY[j][:rows], kc, accumulate)
+            d_in = p.decH[j - 1][:rows] if j > 0 else p.Z[r0:r0 + rows]
+            dd_in = p.d_decH[j - 1][:rows] if j > 0 else p.dZ[r0:r0 + rows]
+            self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, rows, p.d_decY[j][:rows], d_in, l.dw,
+                       accumulate=accumulate)
+            self._gemm(p, K.GEMM_NN, rows, l.n_in, l.n_out, p.d_decY[j][:rows], l.w, dd_in)
+
+    # ------------------------------------------------------------------ backward -----------
+    def backward(self, p, R, S, warm_up_weight=1.0):
+        """Everything upstream of z (the decoder part already ran chunk-wise in forward)."""
+        B, Kc, L, RS, KB = p.B, self.K, self.L, p.RS, p.KB
+        K.gmvae_latent_bwd(p.QH, p.PZ, Kc, B, L, RS, p.eps, p.dZ, p.coef, p.dQH, p.dPZ)
+        # p(z|y) parameters: W[k] gets dPZ[k], the shared bias their sum
+        self.d_pz_w.copy_(p.dPZ)
+        K.group_offset_bwd(p.dPZ, 1, Kc, 2 * L, dt=self.d_pz_b)
+        # q(z|x,y) encoder on K*B rows
+        l = self.qz_head
+        self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, KB, p.dQH, p.qzH[-1], l.dw)
+        self._gemm(p, K.GEMM_NN, KB, l.n_in, l.n_out, p.dQH, l.w, p.d_qzH[-1])
+        for i in range(len(self.qz_enc) - 1, -1, -1):
+            l = self.qz_enc[i]
+            self._bn_bwd(p, l, p.d_qzH[i], p.qzY[i], p.qzH[i], p.qz_mean[i], p.qz_rstd[i],
+                         p.d_qzY[i], Kc, False)
+            if i > 0:
+                self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, KB, p.d_qzY[i], p.qzH[i - 1], l.dw)
+                self._gemm(p, K.GEMM_NN, KB, l.n_in, l.n_out, p.d_qzY[i], l.w, p.d_qzH[i - 1])
+            else:
+                K.group_offset_bwd(p.d_qzY[0], Kc, B, l.n_out, dx=p.dXW, dt=self.d_qz_wy)
+                self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.dXW, p.X, l.dw)
+        # q(y|x) encoder
+        p.dlogits[:, :Kc].copy_(p.dlogits_c)
+        l = self.qy_logits
+        self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.dlogits, p.qyH[-1], l.dw)
+        self._gemm(p, K.GEMM_NN, B, l.n_in, l.n_out, p.dlogits, l.w, p.d_qyH[-1])
+        for i in range(len(self.qy_enc) - 1, -1, -1):
+            l = self.qy_enc[i]
+            self._bn_bwd(p, l, p.d_qyH[i], p.qyY[i], p.qyH[i], p.qy_mean[i], p.qy_rstd[i],
+                         p.d_qyY[i], 1, False)
+            h_in = p.qyH[i - 1] if i > 0 else p.X
+            self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.d_qyY[i], h_in, l.dw)
+            if i > 0:
+                self._gemm(p, K.GEMM_NN, B, l.n_in, l.n_out, p.d_qyY[i], l.w, p.d_qyH[i - 1])
+
+    def train_step(self, p, R, S, learning_rate, warm_up_weight=1.0):
+        """One ``session.run([optimiser, lower_bound])`` (GMVAE:1109-1112)."""
+        self.forward(p, True, R, S, warm_up_weight, with_backward=True)
+        self.backward(p, R, S, warm_up_weight)
+        self.optimiser_step(learning_rate)
+        return p.bound
+
+    # ------------------------------------------------------------------ evaluate extras ----
+    def z_mean(self, p):
+        K.gmvae_z_mean(p.QH, p.y, self.K, p.B, self.L, p.z_mean)
+        return p.z_mean
+
+    def moments(self, p, R, S, deterministic=False):
+        """p_x_mean, p_x_stddev, stddev_of_p_x_given_z_mean marginalised over y
+        (GMVAE:3312-3386, including the y-weighted per-cluster mean of quirk Q7).  Needs the
+        head pre-activations of all K clusters, i.e. a plan whose decoder runs in one chunk."""
+        if p.chunk != self.K:
+            raise ValueError("moments need a single-chunk plan: lower the evaluation minibatch "
+                             "size or raise head_buffer_bytes")
+        outs = [torch.empty(p.B, self.Gn, dtype=torch.float32, device=self.device)
+                for _ in range(3)]
+        K.likelihood_moments(self.kind, p.A, self.Gn, p.B, self.G, p.RS, self.K, p.y, *outs)
+        return [o[:, :self.G] for o in outs]
+
+    def max_single_chunk_minibatch(self, RS):
+        """Largest minibatch whose K cluster passes fit the head buffers in one chunk."""
+        per_cell = self.K * RS * self.P * self.Gn * 4 * 2
+        return max(1, self.head_buffer_bytes // per_cell)

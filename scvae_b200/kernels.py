@@ -186,3 +186,59 @@ def fill_normal(out, seed, offset=0, offset_dev=None):
     lib = _lib.load()
     _lib.check(lib.scvae_fill_normal(_p(out), out.numel(), int(seed), int(offset),
                                      _p(offset_dev), _stream()), "fill_normal")
+
+
+# ---- Gaussian-mixture VAE pieces --------------------------------------------------------------
+def group_offset_fwd(x, t, K_, B, H, y):
+    lib = _lib.load()
+    _lib.check(lib.scvae_group_offset_fwd(_p(x), _ld(x), _p(t), _ld(t), K_, B, H, _p(y), _ld(y),
+                                          _stream()), "group_offset_fwd")
+
+
+def group_offset_bwd(dy, K_, B, H, dx=None, dt=None, accumulate_dt=False):
+    lib = _lib.load()
+    _lib.check(lib.scvae_group_offset_bwd(_p(dy), _ld(dy), K_, B, H, _p(dx),
+                                          _ld(dx) if dx is not None else 0, _p(dt),
+                                          _ld(dt) if dt is not None else 0, int(accumulate_dt),
+                                          _stream()), "group_offset_bwd")
+
+
+def softmax_fwd(logits, B, K_, y, logy):
+    lib = _lib.load()
+    _lib.check(lib.scvae_softmax_fwd(_p(logits), _ld(logits), B, K_, _p(y), _p(logy), _stream()),
+               "softmax_fwd")
+
+
+def gmvae_latent_fwd(qh, pz, K_, B, L, RS, eps, z, klz, kl_elem=None):
+    lib = _lib.load()
+    _lib.check(lib.scvae_gmvae_latent_fwd(_p(qh), _ld(qh), _p(pz), K_, B, L, RS, _p(eps), _p(z),
+                                          _ld(z), _p(klz), _p(kl_elem), _stream()),
+               "gmvae_latent_fwd")
+
+
+def gmvae_latent_bwd(qh, pz, K_, B, L, RS, eps, dz, coef, dqh, dpz):
+    lib = _lib.load()
+    _lib.check(lib.scvae_gmvae_latent_bwd(_p(qh), _ld(qh), _p(pz), K_, B, L, RS, _p(eps), _p(dz),
+                                          _ld(dz), _p(coef), _p(dqh), _ld(dqh), _p(dpz),
+                                          _stream()), "gmvae_latent_bwd")
+
+
+def gmvae_row_coefficients(y, K_, RS, B, weight, go, coef):
+    lib = _lib.load()
+    _lib.check(lib.scvae_gmvae_row_coefficients(_p(y), K_, RS, B, float(weight), _p(go), _p(coef),
+                                                _stream()), "gmvae_row_coefficients")
+
+
+def gmvae_bound(y, logy, logp, klz, log_py, K_, RS, B, weight, free_nats_threshold, uniform_prior,
+                out, dlogits, dpy_logits, ll_mean, klz_mean):
+    lib = _lib.load()
+    _lib.check(lib.scvae_gmvae_bound(_p(y), _p(logy), _p(logp), _p(klz), _p(log_py), K_, RS, B,
+                                     float(weight), float(free_nats_threshold), int(uniform_prior),
+                                     _p(out), _p(dlogits), _p(dpy_logits), _p(ll_mean),
+                                     _p(klz_mean), _stream()), "gmvae_bound")
+
+
+def gmvae_z_mean(qh, y, K_, B, L, z_mean):
+    lib = _lib.load()
+    _lib.check(lib.scvae_gmvae_z_mean(_p(qh), _ld(qh), _p(y), K_, B, L, _p(z_mean), _stream()),
+               "gmvae_z_mean")

@@ -402,6 +402,11 @@ class VariationalAutoencoder:
             minibatch_size = int(numpy.ceil(minibatch_size / (R * S)))
 
         engine = self._get_engine()
+        # data-parallel: active iff a torch.distributed process group exists
+        from . import distributed as D
+        rank, world = D.rank(), D.world_size()
+        is_main = rank == 0
+        D.attach(engine)
         x_train, t_train = self._inputs(training_set, self.reconstruction_distribution_name)
         n_train = training_set.number_of_examples
         minibatch_size = min(minibatch_size, n_train)
@@ -414,9 +419,10 @@ class VariationalAutoencoder:
             valid_data = ResidentCSR(scipy.sparse.csr_matrix(x_valid, dtype=numpy.float32),
                                      engine.device)
 
-        training_writer = SummaryWriter(os.path.join(log_directory, "training"))
+        training_writer = SummaryWriter(os.path.join(log_directory, "training")) \
+            if is_main else None
         validation_writer = SummaryWriter(os.path.join(log_directory, "validation")) \
-            if validation_set else None
+            if (validation_set and is_main) else None
 
         restored = self._restore(engine, log_directory)
         if restored is not None:
@@ -440,6 +446,7 @@ class VariationalAutoencoder:
                 lower_bound_valid_early_stopping = -numpy.inf
                 self.stopped_early = False
         metadata_log["epochs trained"] = (epoch_start, number_of_epochs)
+        D.broadcast_parameters(engine)
 
         rng = numpy.random.RandomState(kwargs["shuffle_seed"]) if "shuffle_seed" in kwargs \
             else numpy.random
@@ -459,11 +466,20 @@ class VariationalAutoencoder:
                 warm_up_weight = float(min(epoch / self.number_of_warm_up_epochs, 1.0))
             else:
                 warm_up_weight = 1.0
-            shuffled = torch.from_numpy(numpy.asarray(rng.permutation(n_train))).to(engine.device)
+            if world > 1:
+                shuffled = D.broadcast_permutation(n_train, rng, engine.device)
+            else:
+                shuffled = torch.from_numpy(numpy.asarray(rng.permutation(n_train))).to(
+                    engine.device)
             n_steps = -(-n_train // minibatch_size)
             step_bounds = torch.zeros(n_steps, 4, dtype=torch.float32, device=engine.device)
             for s, i in enumerate(range(0, n_train, minibatch_size)):
                 rows = min(minibatch_size, n_train - i)
+                if world > 1:   # this rank's slice of the global minibatch
+                    i, hi = D.shard_bounds(i, rows, rank, world)
+                    rows = hi - i
+                    if rows == 0:
+                        continue
                 if rows not in loops:
                     loops[rows] = TrainLoop(engine, rows, R, S, seed=noise_seed,
                                             use_graph=use_graph)
@@ -498,13 +514,18 @@ class VariationalAutoencoder:
                 if kind == "validation" or not validation_set:   # VAE:1184, 1334
                     scalars.update(self._centroid_scalars(result))
                 writer = training_writer if kind == "training" else validation_writer
-                writer.add_scalars(scalars, global_step=epoch + 1)
-                writer.flush()
+                if writer is not None:
+                    writer.add_scalars(scalars, global_step=epoch + 1)
+                    writer.flush()
+                if not is_main:
+                    continue
                 set_kind = training_set.kind if kind == "training" else validation_set.kind
                 print("    {} set: ELBO: {:.5g}, ENRE: {:.5g}, KL: {:.5g}.".format(
                     set_kind.capitalize(), result["lower_bound"], result["reconstruction_error"],
                     result["kl_divergence"]))
 
+            if not is_main:
+                continue
             # early stopping (VAE:1385-1441)
             if validation_set and not self.stopped_early:
                 lower_bound_valid = results["validation"]["lower_bound"]
@@ -546,6 +567,8 @@ class VariationalAutoencoder:
                          analyses_directory=kwargs.get("analyses_directory",
                                                        defaults["analyses"]["directory"]))
 
+        if not is_main:
+            return 0
         training_writer.close()
         if validation_writer:
             validation_writer.close()

@@ -1,0 +1,68 @@
+"""world_size-2 gloo tests of the data-parallel host logic (no GPU): sharding, permutation
+broadcast and the exactness of 'sum of per-shard mean-gradients / W == global-batch gradient'."""
+import os
+import sys
+
+import numpy
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, results):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from oracle import scvae_oracle as O
+    from scvae_b200 import distributed as D
+    torch.set_num_threads(1)
+    r, w = D.initialise_from_environment(backend="gloo")
+    assert (r, w) == (rank, world) and D.is_active()
+    perm = D.broadcast_permutation(40, numpy.random.RandomState(100 + rank))
+    # every rank must hold rank 0's permutation
+    expected = numpy.random.RandomState(100).permutation(40)
+    assert numpy.array_equal(perm.numpy(), expected)
+
+    cfg = O.VAEConfig(12, 3, [6], "negative binomial", minibatch_normalisation=False)
+    params = O.vae_init_params(cfg, seed=0, dtype=torch.float64)
+    x = torch.tensor(O.synthetic_counts(40, 12, seed=1)[0], dtype=torch.float64).clamp(max=20)
+    eps = torch.randn(1, 40, 3, generator=torch.Generator().manual_seed(2), dtype=torch.float64)
+    B = 16
+    lo, hi = D.shard_bounds(8, B, rank, world)
+    assert hi - lo == B // world
+    rows = perm[lo:hi]
+    names = O.trainable_names(params)
+
+    def grads(idx):
+        leaves = {k: params[k].clone().requires_grad_(True) for k in names}
+        local = {k: leaves.get(k, v) for k, v in params.items()}
+        out = O.vae_forward(cfg, local, x[idx], x[idx], eps[:, idx], True)
+        g = torch.autograd.grad(-out["lower_bound_weighted"], [leaves[k] for k in names])
+        return torch.cat([t.reshape(-1) for t in g])
+
+    flat = grads(rows)
+    D.all_reduce_sum_(flat)
+    flat /= world                                   # the optimiser kernel's grad_scale
+    full = grads(perm[8:8 + B])
+    results[rank] = (flat - full).abs().max().item() / full.abs().max().item()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_average_is_exact():
+    port = 29500 + (os.getpid() % 2000)
+    manager = mp.Manager()
+    results = manager.dict()
+    mp.spawn(_worker, args=(2, port, results), nprocs=2, join=True)
+    assert len(results) == 2
+    assert max(results.values()) < 1e-12
+
+
+def test_shard_bounds_cover_minibatch():
+    from scvae_b200 import distributed as D
+    spans = [D.shard_bounds(100, 64, r, 4) for r in range(4)]
+    assert spans == [(100, 116), (116, 132), (132, 148), (148, 164)]
+    assert D.shard_bounds(0, 10, 1, 4) == (2, 4)     # remainder dropped: equal work per rank
+    assert D.rank() == 0 and D.world_size() == 1 and not D.is_active()

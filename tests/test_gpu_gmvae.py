@@ -1,0 +1,103 @@
+"""GPU parity of the GMVAE step engine against the CPU oracle (forward, gradients, Adam step,
+evaluate moments), including cluster-chunked decoder passes."""
+import numpy
+import pytest
+import torch
+
+from oracle import scvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, G, L, K, hidden, likelihood, R, S, B, prior, free_nats, head_buffer_bytes
+    ("nb-uniform", 96, 5, 4, [24], "negative binomial", 1, 1, 40, "uniform", 0.0, 4 << 30),
+    ("zinb-chunked", 64, 4, 5, [20, 12], "zero-inflated negative binomial", 1, 2, 24, "uniform", 0.0, 60000),
+    ("poisson-learn", 80, 3, 3, [16], "poisson", 2, 1, 32, "learn", 0.0, 4 << 30),
+    ("nb-freenats", 72, 4, 6, [16], "negative binomial", 1, 1, 30, "uniform", 0.9, 4 << 30),
+]
+
+
+def _setup(case, tensor_cores):
+    from scvae_b200.gmvae_engine import GMVAEEngine
+    name, G, L, Kc, hidden, lik, R, S, B, prior, free_nats, hbb = case
+    cfg = O.GMVAEConfig(G, L, Kc, hidden, lik, R, S, True, kl_weight=0.8,
+                        prior_probabilities_method=prior,
+                        proportion_of_free_nats_for_y_kl_divergence=free_nats)
+    params = O.gmvae_init_params(cfg, seed=2, dtype=torch.float64)
+    gen = torch.Generator().manual_seed(5)
+    for k in params:
+        if k.endswith("biases") or k.endswith("beta") or k.endswith("LOGITS"):
+            params[k] = torch.randn(params[k].shape, generator=gen, dtype=torch.float64) * 0.2
+    x, _ = O.synthetic_counts(B, G, n_types=3, seed=8, target_zero_fraction=0.8)
+    x = numpy.minimum(x, 300.0)
+    eps = torch.randn(Kc, R * S, B, L, generator=gen, dtype=torch.float64)
+    eng = GMVAEEngine(G, L, Kc, hidden, lik, True, 0.8, prior, None, free_nats, device="cuda:0",
+                      tensor_cores=tensor_cores, head_buffer_bytes=hbb)
+    eng.import_parameters(params)
+    plan = eng._plan(B, R * S)
+    eng.set_batch_dense(plan, torch.tensor(x).cuda())
+    plan.eps.copy_(eps.reshape(-1, L).float())
+    return cfg, params, torch.tensor(x, dtype=torch.float64), eps, eng, plan
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("tensor_cores", [False, True], ids=["fp32", "tf32"])
+def test_gmvae_forward_backward_step(case, tensor_cores):
+    name, G, L, Kc, hidden, lik, R, S, B, prior, free_nats, hbb = case
+    cfg, params, x, eps, eng, plan = _setup(case, tensor_cores)
+    if name == "zinb-chunked":
+        assert plan.chunk < Kc
+    w = 0.7
+    tol = 5e-5 if not tensor_cores else 2e-3
+    state = O.AdamState(params)
+    ref = {k: v.clone() for k, v in params.items()}
+    out, grads = O.train_step(cfg, ref, state, x, x, eps, 1e-3, warm_up_weight=w)
+    bound = eng.train_step(plan, R, S, 1e-3, warm_up_weight=w).cpu().numpy()
+    torch.cuda.synchronize()
+    names = ["lower_bound", "lower_bound_weighted", "reconstruction_error", "kl_divergence_z",
+             "kl_divergence_y"]
+    for i, n in enumerate(names):
+        assert abs(bound[i] - out[n].item()) <= tol * abs(out[n].item()) + 1e-5, (n, bound[i], out[n].item())
+    assert (plan.logits[:, :Kc].cpu().double() - out["q_y_logits"]).abs().max().item() <= \
+        tol * out["q_y_logits"].abs().max().item() + 1e-5
+    lp_ref = out["log_p_x_given_z"].reshape(-1)
+    assert ((plan.logp.cpu().double() - lp_ref).abs().max() / lp_ref.abs().max()).item() <= tol
+    klz_ref = out["kl_z"].reshape(-1)
+    assert ((plan.klz.cpu().double() - klz_ref).abs().max() / klz_ref.abs().max()).item() <= tol
+    got = eng.export_gradients()
+    gtol = 3e-4 if not tensor_cores else 1e-2
+    gmax = max(g.abs().max().item() for g in grads.values())
+    for k, g in grads.items():
+        err = (got[k].double() - g).abs().max().item()
+        assert err <= gtol * g.abs().max().item() + 1e-5 * gmax, (k, err, g.abs().max().item())
+    new = eng.export_parameters()
+    noise = (1e-3 if not tensor_cores else 3e-2) * gmax
+    for k, v in ref.items():
+        diff = (new[k].double() - v).abs()
+        if k in grads:
+            diff = diff * (grads[k].abs() > noise)
+        assert diff.max().item() <= 1e-5 * max(v.abs().max().item(), 1.0), (k, diff.max().item())
+
+
+def test_gmvae_evaluate_mode():
+    case = CASES[0]
+    name, G, L, Kc, hidden, lik, R, S, B, prior, free_nats, hbb = case
+    cfg, params, x, eps, eng, plan = _setup(case, False)
+    upd = []
+    O.gmvae_forward(cfg, params, x, x, eps, True, bn_updates=upd)
+    for scope, mean, var in upd:            # plausible moving statistics
+        params[scope + "/BATCH_NORM/moving_mean"] = mean[0] * 0.9
+        params[scope + "/BATCH_NORM/moving_variance"] = var[0] * 1.1
+    eng.import_parameters(params)
+    out = O.gmvae_forward(cfg, params, x, x, eps, is_training=False, moments=True)
+    eng.forward(plan, False, R, S, 1.0)
+    m = eng.moments(plan, R, S)
+    zm = eng.z_mean(plan)
+    torch.cuda.synchronize()
+    b = plan.bound.cpu().numpy()
+    assert abs(b[0] - out["lower_bound"].item()) <= 5e-5 * abs(out["lower_bound"].item())
+    assert (zm.cpu().double() - out["z_mean"]).abs().max().item() <= 5e-5 * out["z_mean"].abs().max().item() + 1e-6
+    scale = out["p_x_mean"].abs().max().item()
+    assert (m[0].cpu().double() - out["p_x_mean"]).abs().max().item() <= 1e-4 * scale
+    assert (m[1].cpu().double() - out["p_x_stddev"]).abs().max().item() <= 1e-4 * out["p_x_stddev"].abs().max().item()
+    assert (m[2].cpu().double() - out["stddev_of_p_x_given_z_mean"]).abs().max().item() <= 1e-4 * scale
