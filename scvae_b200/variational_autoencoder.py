@@ -453,8 +453,7 @@ class VariationalAutoencoder:
         loops = {}
         noise_seed = kwargs.get("noise_seed", 1)
         use_graph = kwargs.get("use_cuda_graph", True)
-        learning_curves = {"training": {k: [] for k in
-                                        ("lower_bound", "reconstruction_error", "kl_divergence")}}
+        learning_curves = {"training": {k: [] for k in self._loss_keys}}
         if validation_set:
             learning_curves["validation"] = copy.deepcopy(learning_curves["training"])
         training_time_start = time()
@@ -506,23 +505,17 @@ class VariationalAutoencoder:
                                           .format(kind))
                 for key in learning_curves[kind]:
                     learning_curves[kind][key].append(result[key])
-                scalars = {"losses/lower_bound": result["lower_bound"],
-                           "losses/reconstruction_error": result["reconstruction_error"],
-                           "losses/kl_divergence": result["kl_divergence"]}
-                for j, value in enumerate(result["kl_divergence_neurons"]):
-                    scalars["kl_divergence_neurons/{}".format(j)] = value
-                if kind == "validation" or not validation_set:   # VAE:1184, 1334
-                    scalars.update(self._centroid_scalars(result))
+                subset = training_set if kind == "training" else validation_set
+                scalars = self._summary_scalars(
+                    result, subset, with_centroids=(kind == "validation" or not validation_set))
                 writer = training_writer if kind == "training" else validation_writer
                 if writer is not None:
                     writer.add_scalars(scalars, global_step=epoch + 1)
                     writer.flush()
                 if not is_main:
                     continue
-                set_kind = training_set.kind if kind == "training" else validation_set.kind
-                print("    {} set: ELBO: {:.5g}, ENRE: {:.5g}, KL: {:.5g}.".format(
-                    set_kind.capitalize(), result["lower_bound"], result["reconstruction_error"],
-                    result["kl_divergence"]))
+                print("    {} set: {}.".format(subset.kind.capitalize(),
+                                               self._result_string(result)))
 
             if not is_main:
                 continue
@@ -561,7 +554,7 @@ class VariationalAutoencoder:
             if analyser:
                 last = results["validation" if validation_set else "training"]
                 analyser(epoch=epoch, learning_curves=learning_curves, epoch_start=epoch_start,
-                         model_type=self.type, latent_values=last["q_z_mean"],
+                         model_type=self.type, latent_values=last[self._latent_key],
                          data_set=validation_set or training_set,
                          centroids=self._centroids(last), model_name=self.name, run_id=run_id,
                          analyses_directory=kwargs.get("analyses_directory",
@@ -583,6 +576,22 @@ class VariationalAutoencoder:
             for key, value in metadata_log.items():
                 handle.write("{}: {}\n".format(key, value))
         return 0
+
+    # --- hooks specialised by the GMVAE -------------------------------------------------------
+    _loss_keys = ("lower_bound", "reconstruction_error", "kl_divergence")
+    _latent_key = "q_z_mean"
+
+    def _result_string(self, result):
+        return "ELBO: {:.5g}, ENRE: {:.5g}, KL: {:.5g}".format(
+            result["lower_bound"], result["reconstruction_error"], result["kl_divergence"])
+
+    def _summary_scalars(self, result, data_set, with_centroids):
+        scalars = {"losses/" + key: result[key] for key in self._loss_keys}
+        for j, value in enumerate(result["kl_divergence_neurons"]):
+            scalars["kl_divergence_neurons/{}".format(j)] = value
+        if with_centroids:   # VAE:1184, 1334
+            scalars.update(self._centroid_scalars(result))
+        return scalars
 
     def _centroid_scalars(self, result):
         """prior/cluster_0 tags of the single standard-normal prior (VAE:1184-1214; the
@@ -675,17 +684,12 @@ class VariationalAutoencoder:
             raise ArithmeticError("Aborting. The ELBO for the evaluation set became indefinite.")
         if log_results:
             writer = SummaryWriter(os.path.join(directory, "evaluation"))
-            scalars = {"losses/lower_bound": result["lower_bound"],
-                       "losses/reconstruction_error": result["reconstruction_error"],
-                       "losses/kl_divergence": result["kl_divergence"]}
-            for j, value in enumerate(result["kl_divergence_neurons"]):
-                scalars["kl_divergence_neurons/{}".format(j)] = value
-            scalars.update(self._centroid_scalars(result))
-            writer.add_scalars(scalars, global_step=epoch)
+            writer.add_scalars(self._summary_scalars(result, evaluation_set, True),
+                               global_step=epoch)
             writer.close()
-        print("    {} set ({}): ELBO: {:.5g}, ENRE: {:.5g}, KL: {:.5g}.".format(
+        print("    {} set ({}): {}.".format(
             evaluation_set.kind.capitalize(), format_duration(time() - evaluating_time_start),
-            result["lower_bound"], result["reconstruction_error"], result["kl_divergence"]))
+            self._result_string(result)))
         self.last_evaluation = result
 
         outputs = []

@@ -101,7 +101,8 @@ def test_vae_forward_backward_step(case, tensor_cores):
         diff = (new[k].double() - v).abs()
         if k in grads:
             diff = diff * (grads[k].abs() > noise)
-        assert diff.max().item() <= 1e-5 * max(v.abs().max().item(), 1.0), (k, diff.max().item())
+        rtol = 5e-5 if "moving" in k else 1e-5   # fp32 batch variance of raw-count layers
+        assert diff.max().item() <= rtol * max(v.abs().max().item(), 1.0), (k, diff.max().item())
     assert eng.global_step == 1
 
 
