@@ -1,0 +1,329 @@
+"""``GaussianMixtureVariationalAutoencoder``: the reference's GMVAE class
+(scvae/models/gaussian_mixture_variational_autoencoder.py:51) on the B200 step engine.
+
+Shares the train / evaluate / sample shell with ``VariationalAutoencoder`` and specialises what
+the reference specialises: constructor keywords (``prior_probabilities_method``,
+``prior_probabilities``, ``number_of_latent_clusters``,
+``proportion_of_free_nats_for_y_kl_divergence``), the model name, the fetched quantities
+(KL_z / KL_y, q(y|x) logits, cluster statistics), the cluster -> label accuracy logged per
+epoch (GMVAE:1299-1333) and the ``{"z", "y"}`` latent outputs of ``evaluate``.
+"""
+
+import os
+
+import numpy
+
+from .data_set import DataSet
+from .defaults import defaults
+from .model_utilities import normalise_string
+from .variational_autoencoder import VariationalAutoencoder
+
+GMVAE_LATENT_DISTRIBUTIONS = ["gaussian mixture", "full-covariance gaussian mixture",
+                              "legacy gaussian mixture"]
+
+
+def map_cluster_ids_to_label_ids(label_ids, cluster_ids, excluded_class_ids=()):
+    """Each cluster predicts the most frequent label among its members
+    (scvae/analyses/prediction.py:134-146)."""
+    predicted = numpy.zeros_like(cluster_ids)
+    for cluster in numpy.unique(cluster_ids):
+        members = cluster_ids == cluster
+        labels = label_ids[members]
+        for excluded in excluded_class_ids:
+            labels = labels[labels != excluded]
+        if labels.size:
+            values, counts = numpy.unique(labels, return_counts=True)
+            predicted[members] = values[counts.argmax()]     # smallest label wins ties (mode)
+    return predicted
+
+
+def accuracy(label_ids, predicted_label_ids, excluded_class_ids=()):
+    """Fraction of correctly mapped labels, ignoring excluded classes
+    (scvae/analyses/metrics/clustering.py:145-148)."""
+    keep = numpy.ones(len(label_ids), dtype=bool)
+    for excluded in excluded_class_ids:
+        keep &= label_ids != excluded
+    return float(numpy.mean(predicted_label_ids[keep] == label_ids[keep])) if keep.any() else None
+
+
+class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
+    _model_type = "GMVAE"
+    _loss_keys = ("lower_bound", "reconstruction_error", "kl_divergence_z", "kl_divergence_y")
+    _latent_key = "z_mean"
+
+    def __init__(self, feature_size, latent_size=None, hidden_sizes=None,
+                 reconstruction_distribution=None, number_of_reconstruction_classes=None,
+                 prior_probabilities_method=None, prior_probabilities=None,
+                 number_of_latent_clusters=None, minibatch_normalisation=None,
+                 batch_correction=None, number_of_batches=None,
+                 proportion_of_free_nats_for_y_kl_divergence=None, number_of_warm_up_epochs=None,
+                 log_directory=None, **kwargs):
+        d = defaults["models"]
+        if prior_probabilities_method is None:
+            prior_probabilities_method = d["prior_probabilities_method"]
+        self.prior_probabilities_method = prior_probabilities_method
+        self.prior_probabilities = prior_probabilities
+        if prior_probabilities_method == "custom" and prior_probabilities is None:
+            raise TypeError("No prior probabilities supplied for custom method.")
+        if proportion_of_free_nats_for_y_kl_divergence is None:
+            proportion_of_free_nats_for_y_kl_divergence = d[
+                "proportion_of_free_nats_for_y_kl_divergence"]
+        self.proportion_of_free_nats_for_y_kl_divergence = (
+            proportion_of_free_nats_for_y_kl_divergence)
+        if number_of_latent_clusters is None and prior_probabilities is not None:
+            number_of_latent_clusters = len(prior_probabilities)
+        kwargs["number_of_latent_clusters"] = number_of_latent_clusters
+        latent_distribution = kwargs.pop("latent_distribution", None)
+        super().__init__(
+            feature_size, latent_size=latent_size, hidden_sizes=hidden_sizes,
+            reconstruction_distribution=reconstruction_distribution,
+            number_of_reconstruction_classes=number_of_reconstruction_classes,
+            latent_distribution=latent_distribution,
+            minibatch_normalisation=minibatch_normalisation, batch_correction=batch_correction,
+            number_of_batches=number_of_batches,
+            number_of_warm_up_epochs=number_of_warm_up_epochs, log_directory=log_directory,
+            **kwargs)
+        self.n_clusters = self.number_of_latent_clusters
+        # the flag only affects the model name for the GMVAE (quirk Q8)
+        self.analytical_kl_term = bool(kwargs.get("analytical_kl_term") or False)
+        if self.latent_distribution_name != "gaussian mixture":
+            raise NotImplementedError(
+                "Not on the B200 hot path yet (SURVEY §8 f4): latent distribution `{}`.".format(
+                    self.latent_distribution_name))
+
+    def _latent_choices(self):
+        return GMVAE_LATENT_DISTRIBUTIONS
+
+    @property
+    def name(self):
+        """Same scheme as GMVAE:441-502."""
+        latent = [normalise_string(self.latent_distribution_name),
+                  "c_{}".format(self.number_of_latent_clusters)]
+        if self.prior_probabilities_method != "uniform":
+            latent.append("p_" + self.prior_probabilities_method)
+        minor = [normalise_string(self.reconstruction_distribution_name)]
+        if self.k_max:
+            minor.append("k_{}".format(self.k_max))
+        if self.use_count_sum_as_feature:
+            minor.append("sum")
+        minor.append("l_{}".format(self.latent_size))
+        minor.append("h_" + "_".join(str(h) for h in self.hidden_sizes))
+        minor.append("mc_{}".format(self.number_of_monte_carlo_samples["training"]))
+        minor.append("iw_{}".format(self.number_of_importance_samples["training"]))
+        if self.analytical_kl_term:
+            minor.append("kl")
+        if self.minibatch_normalisation:
+            minor.append("bn")
+        if self.batch_correction:
+            minor.append("bc")
+        if self.dropout_parts:
+            minor.append("dropout_" + "_".join(self.dropout_parts))
+        if self.kl_weight_value != 1:
+            minor.append("klw_{}".format(self.kl_weight_value))
+        if self.number_of_warm_up_epochs:
+            minor.append("wu_{}".format(self.number_of_warm_up_epochs))
+        if self.proportion_of_free_nats_for_y_kl_divergence:
+            minor.append("fn_{}".format(self.proportion_of_free_nats_for_y_kl_divergence))
+        return os.path.join(self.type, "-".join(latent), "-".join(minor))
+
+    @property
+    def description(self):
+        text = super().description
+        extra = ["prior probabilities: " + self.prior_probabilities_method]
+        if self.proportion_of_free_nats_for_y_kl_divergence:
+            extra.append("proportion of free nats for y KL divergence: {}".format(
+                self.proportion_of_free_nats_for_y_kl_divergence))
+        return text + "\n    " + "\n    ".join(extra)
+
+    # ------------------------------------------------------------------------------------------
+    def _build_engine(self):
+        from .gmvae_engine import GMVAEEngine
+        return GMVAEEngine(
+            self.feature_size, self.latent_size, self.number_of_latent_clusters, self.hidden_sizes,
+            self.reconstruction_distribution_name, self.minibatch_normalisation,
+            self.kl_weight_value, self.prior_probabilities_method, self.prior_probabilities,
+            self.proportion_of_free_nats_for_y_kl_divergence, device=self._device,
+            seed=self._seed, tensor_cores=self._tensor_cores)
+
+    def _evaluate_pass(self, engine, x_csr, t_csr, minibatch_size, R, S, deterministic=False,
+                       seed=0, on_batch=None):
+        """Forward-only pass; fetches what GMVAE:1229-1240 / 2438-2452 fetch."""
+        import torch
+        from .hotloop import ResidentCSR
+        from . import kernels as K
+        if t_csr is not None and t_csr is not x_csr:
+            raise NotImplementedError("Separate preprocessed inputs are not supported by the "
+                                      "GMVAE engine yet.")
+        n = x_csr.shape[0]
+        Kc, L = self.number_of_latent_clusters, self.latent_size
+        dev = engine.device
+        data = x_csr if isinstance(x_csr, ResidentCSR) else ResidentCSR(x_csr, dev)
+        minibatch_size = min(minibatch_size, engine.max_single_chunk_minibatch(R * S))
+        n_batches = -(-n // minibatch_size)
+        log = torch.zeros(n_batches, 6, dtype=torch.float32, device=dev)
+        stats = torch.zeros(n_batches, 2, Kc, L, dtype=torch.float32, device=dev)
+        q_y_probabilities = torch.zeros(n_batches, Kc, dtype=torch.float32, device=dev)
+        z_mean = torch.zeros(n, L, dtype=torch.float32, device=dev)
+        y_mean = torch.zeros(n, Kc, dtype=torch.float32, device=dev)
+        logits = torch.zeros(n, Kc, dtype=torch.float32, device=dev)
+        for b, i in enumerate(range(0, n, minibatch_size)):
+            rows = min(minibatch_size, n - i)
+            plan = engine._plan(rows, R * S)
+            idx = torch.arange(i, i + rows, dtype=torch.int64, device=dev)
+            engine.set_batch_csr(plan, data.indptr, data.indices, data.values, idx)
+            K.fill_normal(plan.eps, seed, b)
+            engine.forward(plan, False, R, S, 1.0)
+            log[b].copy_(plan.bound)
+            z_mean[i:i + rows].copy_(engine.z_mean(plan))
+            y_mean[i:i + rows].copy_(plan.y)
+            logits[i:i + rows].copy_(plan.logits[:, :Kc])
+            K.col_mean(plan.y, rows, Kc, q_y_probabilities[b])
+            # q(z|x,y=k) means / variances averaged over the batch (GMVAE:2881-2885)
+            qh = plan.QH.view(Kc, rows, -1)
+            for k in range(Kc):
+                K.col_mean(qh[k], rows, L, stats[b, 0, k])
+            stats[b, 1].copy_(self._posterior_variances(plan, rows, L))
+            if on_batch is not None:
+                on_batch(plan, i, rows)
+        log = log.cpu().numpy().astype(numpy.float64)
+        divisor = n / minibatch_size
+        stats = stats.cpu().numpy().astype(numpy.float64).sum(axis=0) / divisor
+        prior = engine.export_parameters()
+        softplus = lambda a: numpy.log1p(numpy.exp(-numpy.abs(a))) + numpy.maximum(a, 0)
+        p_mean = (prior["Z/P/SOFTPLUS_GAUSSIAN/MEAN/DENSE/weights"]
+                  + prior["Z/P/SOFTPLUS_GAUSSIAN/MEAN/DENSE/biases"]).numpy()
+        p_var = softplus((prior["Z/P/SOFTPLUS_GAUSSIAN/SOFTPLUS_SCALE/DENSE/weights"]
+                          + prior["Z/P/SOFTPLUS_GAUSSIAN/SOFTPLUS_SCALE/DENSE/biases"]).numpy())
+        result = {
+            "lower_bound": log[:, 0].sum() / divisor,
+            "reconstruction_error": log[:, 2].sum() / divisor,
+            "kl_divergence_z": log[:, 3].sum() / divisor,
+            "kl_divergence_y": log[:, 4].sum() / divisor,
+            "z_mean": z_mean.cpu().numpy(), "y_mean": y_mean.cpu().numpy(),
+            "q_y_logits": logits.cpu().numpy(),
+            "q_y_probabilities": q_y_probabilities.cpu().numpy().sum(axis=0) / divisor,
+            "q_z_means": stats[0], "q_z_variances": stats[1],
+            "p_y_probabilities": numpy.exp(engine.log_py.cpu().numpy()),
+            "p_z_means": p_mean, "p_z_variances": p_var,
+        }
+        result["kl_divergence"] = result["kl_divergence_z"] + result["kl_divergence_y"]
+        result["kl_divergence_neurons"] = numpy.array([result["kl_divergence"]])  # GMVAE:3401
+        return result
+
+    @staticmethod
+    def _posterior_variances(plan, rows, L):
+        """mean_b softplus(s_k[b]) per cluster (K, L): a K*L-sized statistic that only feeds the
+        TensorBoard centroid tags (GMVAE:2883-2885), computed with torch on the device."""
+        import torch
+        s = plan.QH.view(-1, rows, plan.QH.shape[1])
+        return torch.nn.functional.softplus(s[:, :, L:2 * L]).mean(dim=1)
+
+    # ------------------------------------------------------------------------------------------
+    def _result_string(self, result):
+        text = "ELBO: {:.5g}, ENRE: {:.5g}, KL_z: {:.5g}, KL_y: {:.5g}".format(
+            result["lower_bound"], result["reconstruction_error"], result["kl_divergence_z"],
+            result["kl_divergence_y"])
+        if result.get("accuracy") is not None:
+            text += ", Acc: {:.5g}".format(result["accuracy"])
+        return text
+
+    def _summary_scalars(self, result, data_set, with_centroids):
+        if data_set is not None and data_set.has_labels and "accuracy" not in result:
+            names = numpy.unique(data_set.labels)
+            label_ids = numpy.searchsorted(names, data_set.labels)
+            cluster_ids = result["q_y_logits"].argmax(axis=1)
+            excluded = [i for i, name in enumerate(names)
+                        if name in getattr(data_set, "excluded_classes", [])]
+            predicted = map_cluster_ids_to_label_ids(label_ids, cluster_ids, excluded)
+            result["accuracy"] = accuracy(label_ids, predicted, excluded)
+            result["cluster_ids"] = cluster_ids
+            result["predicted_labels"] = names[predicted]
+        scalars = {"losses/" + key: result[key] for key in self._loss_keys}
+        if result.get("accuracy") is not None:
+            scalars["accuracy"] = result["accuracy"]
+        scalars["kl_divergence_neurons/0"] = result["kl_divergence"]
+        if with_centroids:
+            scalars.update(self._centroid_scalars(result))
+        return scalars
+
+    def _centroid_scalars(self, result):
+        scalars = {}
+        for k in range(self.number_of_latent_clusters):
+            scalars["prior/cluster_{}/probability".format(k)] = result["p_y_probabilities"][k]
+            scalars["posterior/cluster_{}/probability".format(k)] = result["q_y_probabilities"][k]
+            for l in range(self.latent_size):
+                for dist, key in (("prior", "p_z"), ("posterior", "q_z")):
+                    scalars["{}/cluster_{}/mean/dimension_{}".format(dist, k, l)] = \
+                        result[key + "_means"][k, l]
+                    scalars["{}/cluster_{}/variance/dimension_{}".format(dist, k, l)] = \
+                        result[key + "_variances"][k, l]
+        return scalars
+
+    def _centroids(self, result):
+        def pack(probabilities, means, variances):
+            return {"probabilities": probabilities, "means": means,
+                    "covariance_matrices": numpy.stack([numpy.diag(v) for v in variances])}
+        return {"prior": pack(result["p_y_probabilities"], result["p_z_means"],
+                              result["p_z_variances"]),
+                "posterior": pack(result["q_y_probabilities"], result["q_z_means"],
+                                  result["q_z_variances"])}
+
+    def _latent_sets(self, evaluation_set, result, common):
+        L, Kc = self.latent_size, self.number_of_latent_clusters
+        z = DataSet(evaluation_set.name, values=result["z_mean"], version="z", feature_names=(
+            numpy.array(["z variable {}".format(i + 1) for i in range(L)])), **common)
+        y = DataSet(evaluation_set.name, values=result["y_mean"], version="y", feature_names=(
+            numpy.array(["y variable {}".format(i + 1) for i in range(Kc)])), **common)
+        for subset in (z, y):
+            subset.predicted_cluster_ids = result.get("cluster_ids",
+                                                      result["q_y_logits"].argmax(axis=1))
+            subset.predicted_labels = result.get("predicted_labels")
+        return {"z": z, "y": y}
+
+    # ------------------------------------------------------------------------------------------
+    def sample(self, sample_size=None, minibatch_size=None, run_id=None,
+               use_early_stopping_model=False, use_best_model=False, **kwargs):
+        """y ~ p(y), z ~ p(z|y), x = E[x|z] (GMVAE:1949-2160): returns
+        ``(sample DataSet, {"z": ..., "y": ...})``."""
+        import torch
+        from . import kernels as K
+        if sample_size is None:
+            sample_size = defaults["models"]["sample_size"]
+        if minibatch_size is None:
+            minibatch_size = defaults["models"]["minibatch_size"]
+        engine, _, _ = self._load_for_inference(run_id, use_early_stopping_model, use_best_model,
+                                                "sample from")
+        L, G, Kc = self.latent_size, self.feature_size, self.number_of_latent_clusters
+        rng = numpy.random.RandomState(kwargs.get("noise_seed", 11))
+        p_y = numpy.exp(engine.log_py.cpu().numpy().astype(numpy.float64))
+        clusters = rng.choice(Kc, size=sample_size, p=p_y / p_y.sum())
+        prior = engine.export_parameters()
+        softplus = lambda a: numpy.log1p(numpy.exp(-numpy.abs(a))) + numpy.maximum(a, 0)
+        means = (prior["Z/P/SOFTPLUS_GAUSSIAN/MEAN/DENSE/weights"]
+                 + prior["Z/P/SOFTPLUS_GAUSSIAN/MEAN/DENSE/biases"]).numpy()
+        scales = numpy.sqrt(softplus((prior["Z/P/SOFTPLUS_GAUSSIAN/SOFTPLUS_SCALE/DENSE/weights"]
+                                      + prior["Z/P/SOFTPLUS_GAUSSIAN/SOFTPLUS_SCALE/DENSE/biases"])
+                                     .numpy()))
+        z = (means[clusters] + scales[clusters] * rng.standard_normal((sample_size, L))).astype(
+            numpy.float32)
+        x = numpy.empty((sample_size, G), numpy.float32)
+        from .engine import VAEEngine
+        for i in range(0, sample_size, minibatch_size):
+            rows = min(minibatch_size, sample_size - i)
+            plan = engine._plan(rows, 1)
+            plan.Z[:rows, :L].copy_(torch.from_numpy(z[i:i + rows]))
+            VAEEngine.decode(engine, plan, rows)       # decoder only, moving statistics, 1 group
+            outs = [torch.empty(rows, engine.Gn, dtype=torch.float32, device=engine.device)
+                    for _ in range(3)]
+            K.likelihood_moments(engine.kind, plan.A[:rows], engine.Gn, rows, G, 1, 1, None, *outs)
+            x[i:i + rows] = outs[0][:, :G].cpu().numpy()
+        names = numpy.array(["example {}".format(i + 1) for i in range(sample_size)])
+        y = numpy.eye(Kc, dtype=numpy.float32)[clusters]
+        sample_set = DataSet("sample", values=x, example_names=names, kind="sample")
+        latent = {
+            "z": DataSet("sample", values=z, example_names=names, kind="sample", version="z",
+                         feature_names=numpy.array(["z variable {}".format(i + 1) for i in range(L)])),
+            "y": DataSet("sample", values=y, example_names=names, kind="sample", version="y",
+                         feature_names=numpy.array(["y variable {}".format(i + 1) for i in range(Kc)])),
+        }
+        return sample_set, latent

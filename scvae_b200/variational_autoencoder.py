@@ -53,7 +53,7 @@ class VariationalAutoencoder:
                  number_of_batches=None, number_of_warm_up_epochs=None, log_directory=None,
                  **kwargs):
         d = defaults["models"]
-        self.type = "VAE"
+        self.type = self._model_type
         self.feature_size = feature_size
         self.latent_size = d["latent_size"] if latent_size is None else latent_size
         self.hidden_sizes = list(d["hidden_sizes"] if hidden_sizes is None else hidden_sizes)
@@ -578,6 +578,7 @@ class VariationalAutoencoder:
         return 0
 
     # --- hooks specialised by the GMVAE -------------------------------------------------------
+    _model_type = "VAE"
     _loss_keys = ("lower_bound", "reconstruction_error", "kl_divergence")
     _latent_key = "q_z_mean"
 

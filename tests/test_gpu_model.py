@@ -96,3 +96,31 @@ def test_one_epoch_matches_oracle(tmp_path):
     from scvae_b200 import model_utilities as MU
     logged = MU.load_learning_curves(model, "training")["lower_bound"][0]
     assert numpy.isfinite(logged)
+
+
+def test_gmvae_train_evaluate_sample(tmp_path):
+    from scvae_b200.gaussian_mixture_variational_autoencoder import (
+        GaussianMixtureVariationalAutoencoder)
+    from scvae_b200 import model_utilities as MU
+    full = _data(n=240, g=40, seed=4)
+    training, validation, test = full.split()
+    model = GaussianMixtureVariationalAutoencoder(
+        feature_size=40, latent_size=3, hidden_sizes=[24], number_of_latent_clusters=3,
+        reconstruction_distribution="zero-inflated negative binomial", log_directory=str(tmp_path),
+        seed=2)
+    assert model.type == "GMVAE" and "c_3" in model.name
+    assert model.train(training, validation, number_of_epochs=2, minibatch_size=48,
+                       learning_rate=5e-3, shuffle_seed=0) == 0
+    curves = MU.load_learning_curves(model, ["training", "validation"])
+    assert len(curves["training"]["kl_divergence_y"]) == 2
+    assert MU.load_accuracies(model, "training") is not None
+    centroids = MU.load_centroids(model, "validation")
+    assert centroids["posterior"]["means"].shape == (2, 3, 3)
+    transformed, reconstructed, latent = model.evaluate(test, minibatch_size=32)
+    assert set(latent) == {"z", "y"}
+    assert latent["y"].values.shape == (test.number_of_examples, 3)
+    assert numpy.allclose(latent["y"].values.sum(1), 1, atol=1e-5)
+    assert reconstructed.values.shape == (test.number_of_examples, 40)
+    assert latent["z"].predicted_cluster_ids.shape == (test.number_of_examples,)
+    sample_set, sample_latent = model.sample(sample_size=20, minibatch_size=8)
+    assert sample_set.values.shape == (20, 40) and sample_latent["y"].values.shape == (20, 3)
