@@ -124,3 +124,22 @@ def test_gmvae_train_evaluate_sample(tmp_path):
     assert latent["z"].predicted_cluster_ids.shape == (test.number_of_examples,)
     sample_set, sample_latent = model.sample(sample_size=20, minibatch_size=8)
     assert sample_set.values.shape == (20, 40) and sample_latent["y"].values.shape == (20, 3)
+
+
+def test_cli_train_and_evaluate_on_tsv(tmp_path):
+    """BASELINE config C1 in miniature: TSV count matrix -> `scvae train` -> `scvae evaluate`."""
+    import pandas
+    from scvae_b200 import cli
+    ds = _data(n=120, g=30, seed=6)
+    frame = pandas.DataFrame(ds.values.toarray().astype(int),
+                             index=["cell {}".format(i) for i in range(120)],
+                             columns=["gene {}".format(j) for j in range(30)])
+    path = tmp_path / "counts.tsv"
+    frame.to_csv(path, sep="\t")
+    models = str(tmp_path / "models")
+    assert cli.main(["train", str(path), "-r", "poisson", "-l", "3", "-H", "16", "-e", "2",
+                     "-B", "40", "-M", models, "--split-data-set"]) == 0
+    assert cli.main(["evaluate", str(path), "-r", "poisson", "-l", "3", "-H", "16", "-B", "40",
+                     "-M", models, "--split-data-set"]) == 0
+    found = [f for _, _, files in os.walk(models) for f in files]
+    assert "checkpoint" in found and any(f.startswith("model.ckpt-2") for f in found)
