@@ -471,7 +471,7 @@ class VariationalAutoencoder:
                 shuffled = torch.from_numpy(numpy.asarray(rng.permutation(n_train))).to(
                     engine.device)
             n_steps = -(-n_train // minibatch_size)
-            step_bounds = torch.zeros(n_steps, 4, dtype=torch.float32, device=engine.device)
+            step_bounds = torch.zeros(n_steps, 8, dtype=torch.float32, device=engine.device)
             for s, i in enumerate(range(0, n_train, minibatch_size)):
                 rows = min(minibatch_size, n_train - i)
                 if world > 1:   # this rank's slice of the global minibatch
@@ -484,7 +484,8 @@ class VariationalAutoencoder:
                                             use_graph=use_graph)
                 loop = loops[rows]
                 loop.rows.copy_(shuffled[i:i + rows])
-                step_bounds[s].copy_(loop.step(data, learning_rate, warm_up_weight))
+                bound = loop.step(data, learning_rate, warm_up_weight)
+                step_bounds[s, :bound.numel()].copy_(bound)
             bounds = step_bounds.cpu().numpy()
             if numpy.isnan(bounds[:, 0]).any():
                 raise ArithmeticError("Aborting. The ELBO became indefinite during training.")
