@@ -228,6 +228,12 @@ def workload_config(args, minibatch):
 # ---------------------------------------------------------------------------------------------
 # this repository's arm
 # ---------------------------------------------------------------------------------------------
+def _dbg(msg):
+    if os.environ.get("SCVAE_BENCH_DEBUG"):
+        print("[bench rank {}] {}".format(os.environ.get("RANK", "0"), msg), file=sys.stderr,
+              flush=True)
+
+
 def run_b200(args):
     import torch.distributed as dist
     from scvae_b200 import _lib
@@ -268,8 +274,10 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    _dbg("data + engine ready")
     # count our kernel launches per step (eager, outside the timed region)
     step(0)
+    _dbg("first step (graph captured) done")
     torch.cuda.synchronize()
     l0 = lib.scvae_launch_count()
     loop.use_graph, saved = False, loop.use_graph
@@ -281,6 +289,7 @@ def run_b200(args):
     for i in range(args.warmup):
         step(i)
     sync_all()
+    _dbg("warm-up done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -296,6 +305,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
+    _dbg("timed region done")
     bound = loop.plan.bound.cpu().tolist()
     value = args.steps * B * world / (elapsed_ms * 1e-3)
 
@@ -318,6 +328,7 @@ def run_b200(args):
     K.likelihood_bwd = orig
     loop.use_graph = saved
     lik_ms = float(numpy.mean([s.elapsed_time(e) for s, e in evs]))
+    _dbg("kernel timing done")
     P = eng.P
     # algorithmic bytes per (cell, gene): fp32 target + P head pre-activations read, P
     # gradients written (NB backward = 20 B/gene)
@@ -363,6 +374,7 @@ def run_b200(args):
             elbo = out.cpu()          # D2H of the step's result: synchronises, like session.run
             return nxt, elbo
 
+        _dbg("e2e: streamed CSR ready")
         pending = stream.fetch(0, 0, B)
         for i in range(args.warmup):
             pending, _ = e2e_step(i, pending)
@@ -398,9 +410,24 @@ def run_b200(args):
             "lower_bound_last_step": bound[0],
             "cuda_graph": bool(saved),
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # CUDA graphs that captured NCCL kernels must die before the communicator does; guard
+        # the teardown with a watchdog so a stuck destroy can never hang the launcher
+        torch.cuda.synchronize()
+        dist.barrier()
+        loop._graphs = {}
+        loop._graph = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        watchdog = threading.Timer(15.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
         dist.destroy_process_group()
+        watchdog.cancel()
 
 
 def main():
