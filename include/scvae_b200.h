@@ -77,6 +77,17 @@ int scvae_gemm_tf32(int layout, int M, int N, int K, const float *A, int64_t lda
                     const float *B, int64_t ldb, float *C, int64_t ldc, int accumulate,
                     void *workspace, int64_t workspace_bytes, void *stream);
 int64_t scvae_gemm_tf32_workspace_bytes(int layout, int M, int N, int K);
+/* Same kernel with fp16 operands (kind::f16, fp32 accumulation, fp32 output scaled by alpha):
+ * A, B are IEEE half matrices, leading dimensions (in elements) multiples of 8.  Used where a
+ * (cells x genes)-sized operand is kept in 16 bits to halve its HBM traffic. */
+int scvae_gemm_f16(int layout, int M, int N, int K, const void *A, int64_t lda, const void *B,
+                   int64_t ldb, float *C, int64_t ldc, int accumulate, float alpha,
+                   void *workspace, int64_t workspace_bytes, void *stream);
+int64_t scvae_gemm_f16_workspace_bytes(int layout, int M, int N, int K);
+/* dst (rows, ldd) fp16 = scale * src (rows, lds) fp32 for the first `cols` columns, zero in
+ * columns [cols, ldd): fp16 operand copies of fp32 master tensors. */
+int scvae_f32_to_f16(const float *src, int64_t lds, int64_t rows, int cols, void *dst,
+                     int64_t ldd, float scale, void *stream);
 
 /* ---- a2: batch normalisation + ReLU  (MU:62-74; tf.contrib batch_norm center=True,
  * scale=False, epsilon 1e-3, decay 0.999) ---------------------------------------------

@@ -14,10 +14,7 @@
 //   * persistent CTAs (<= one per SM) walk (m-tile, n-tile, k-split) work items; skinny
 //     products (N ~ 100, K ~ 20000) are split along K into a workspace and reduced in a fixed
 //     order by a second tiny kernel, so results are deterministic.
-#include <cuda.h>
-#include <stdlib.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace scvae {
 
@@ -30,108 +27,20 @@ constexpr int kSmemBytes = kStages * kStageBytes + 2 * kEpiBytes + 1024 /*align*
 constexpr int kTmemCols = 2 * BN;                // double-buffered fp32 accumulator
 constexpr int kThreads = 256;
 
-// ---- PTX wrappers -----------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, uint32_t src) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map),
-                 "r"(c0), "r"(c1), "r"(src)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *map, int c0, int c1, uint32_t src) {
-    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map),
-                 "r"(c0), "r"(c1), "r"(src)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor), version 1.  layout_type:
-// 2 = SWIZZLE_128B (16-byte chunks, K-major operands), 1 = SWIZZLE_128B_BASE32B (32-byte
-// chunks: the only layout the tensor core accepts for MN-major 32-bit operands).
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                              uint32_t layout_type) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr >> 4) & 0x3fff);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-    d |= (uint64_t)layout_type << 61;
-    return d;
-}
-
 struct GemmParams {
     int M, N, K;
     int tiles_m, tiles_n, nsplit, kb_per_split, nkb;
     int accumulate;     // TMA reduce-add into C (only when nsplit == 1)
     int ws_rows;        // rows per split slice of the workspace (multiple of BM)
     uint32_t mn_lbo, mn_sbo;  // descriptor strides of MN-major operand tiles
+    float alpha;              // accumulator scale applied in the epilogue
 };
 
-template <bool A_MN, bool B_MN>
+// F16: operands are fp16 (kind::f16, 64-element k-blocks, plain 128B swizzle for both majors);
+// otherwise fp32 consumed as tf32 (32-element k-blocks, 32-byte-atom swizzle for MN-major).
+template <bool F16, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -145,6 +54,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int EB = F16 ? 2 : 4;             // operand element bytes
+    constexpr int BKE = 128 / EB;               // elements per k-block (one 128-byte swizzle row)
+    constexpr int UK = 32 / EB;                 // elements per tcgen05.mma along K
+    constexpr int MN_BOX = 128 / EB;            // MN elements per TMA box of an MN-major tile
+    constexpr int MN_BOXES = BM / MN_BOX;       // boxes per 128-wide tile
+    constexpr int MN_BOX_BYTES = BKE * 128;     // BKE k-rows of 128 bytes
+    constexpr uint32_t MN_LAYOUT = F16 ? 2u : 1u;   // SWIZZLE_128B vs SWIZZLE_128B_BASE32B
+    constexpr uint32_t MN_KSTEP = UK * 128;     // bytes per UMMA K step in an MN-major tile
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -194,15 +111,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_expect_tx(full, kStageBytes);
                     if (A_MN) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) tma_load_2d(sa + j * 4096, &tmA, tm * BM + 32 * j, kb * BK, full);
+                        for (int j = 0; j < MN_BOXES; ++j)
+                            tma_load_2d(sa + j * MN_BOX_BYTES, &tmA, tm * BM + MN_BOX * j, kb * BKE, full);
                     } else {
-                        tma_load_2d(sa, &tmA, kb * BK, tm * BM, full);
+                        tma_load_2d(sa, &tmA, kb * BKE, tm * BM, full);
                     }
                     if (B_MN) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) tma_load_2d(sb + j * 4096, &tmB, tn * BN + 32 * j, kb * BK, full);
+                        for (int j = 0; j < MN_BOXES; ++j)
+                            tma_load_2d(sb + j * MN_BOX_BYTES, &tmB, tn * BN + MN_BOX * j, kb * BKE, full);
                     } else {
-                        tma_load_2d(sb, &tmB, kb * BK, tn * BN, full);
+                        tma_load_2d(sb, &tmB, kb * BKE, tn * BN, full);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -211,8 +130,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, M=128, N=128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32|f16, M=128, N=128
+            constexpr uint32_t FMT = F16 ? 0u : 2u;
+            const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((A_MN ? 1u : 0u) << 15) |
                                    ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)(BM >> 4) << 24);
             int stage = 0;
@@ -232,14 +152,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * kStageBytes);
                     const uint32_t sb = sa + kTileBytes;
-                    const uint64_t da = A_MN ? make_desc(sa, p.mn_lbo, p.mn_sbo, 1) : make_desc(sa, 16, 1024, 2);
-                    const uint64_t db = B_MN ? make_desc(sb, p.mn_lbo, p.mn_sbo, 1) : make_desc(sb, 16, 1024, 2);
-                    // per UMMA_K = 8 fp32 step: K-major +32 B inside the swizzle row; MN-major +8 K-rows
-                    const uint64_t sta = A_MN ? (1024 >> 4) : (32 >> 4);
-                    const uint64_t stb = B_MN ? (1024 >> 4) : (32 >> 4);
+                    const uint64_t da = A_MN ? make_desc(sa, p.mn_lbo, p.mn_sbo, MN_LAYOUT) : make_desc(sa, 16, 1024, 2);
+                    const uint64_t db = B_MN ? make_desc(sb, p.mn_lbo, p.mn_sbo, MN_LAYOUT) : make_desc(sb, 16, 1024, 2);
+                    // per UMMA K step: K-major +32 B inside the swizzle row; MN-major +UK k-rows
+                    const uint64_t sta = A_MN ? (MN_KSTEP >> 4) : (32 >> 4);
+                    const uint64_t stb = B_MN ? (MN_KSTEP >> 4) : (32 >> 4);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k)
-                        tc_mma_tf32(tmem_d, da + k * sta, db + k * stb, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < BKE / UK; ++k) {
+                        if (F16)
+                            tc_mma_f16(tmem_d, da + k * sta, db + k * stb, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        else
+                            tc_mma_tf32(tmem_d, da + k * sta, db + k * stb, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
                     tc_commit(bar_empty + 8 * stage);  // frees the smem slot once the MMAs retire
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -271,6 +195,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (issuer) tma_wait_read<1>();       // staging buffer `buf` is free again
                 epi_bar_sync();
                 uint8_t *dst = epi + buf * kEpiBytes + row * 128;
+                if (p.alpha != 1.f) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * p.alpha);
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const uint4 val = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -306,7 +234,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 // C[m, n] (+)= sum_s ws[s][m][n], fixed order.
 __global__ void splitk_reduce_kernel(const float *__restrict__ ws, int64_t ldw, int ws_rows, int nsplit, int M,
-                                     int N, float *__restrict__ C, int64_t ldc, int accumulate) {
+                                     int N, float *__restrict__ C, int64_t ldc, int accumulate, float alpha) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int m = blockIdx.y;
     if (n >= N) return;
@@ -316,49 +244,15 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ ws, int64_t ldw, 
     *c = accumulate ? *c + acc : acc;
 }
 
-// ---- host side ----------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)ptr;
-    }
-    return fn;
-}
-
-// 2-D fp32 tensor map over a row-major (rows, cols) matrix with leading dimension ld.
-static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
-                    int box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
-    EncodeTiledFn enc = get_encode();
-    SCVAE_CHECK_ARG(enc, "gemm_tf32: cuTensorMapEncodeTiled unavailable");
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SCVAE_CHECK_ARG(r == CUDA_SUCCESS, "gemm_tf32: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld",
-                    (int)r, (long long)rows, (long long)cols, (long long)ld);
-    return 0;
-}
-
 struct SplitPlan {
     int tiles_m, tiles_n, nkb, nsplit, kb_per_split;
 };
 
-static SplitPlan plan_split(int M, int N, int K) {
+static SplitPlan plan_split(int M, int N, int K, int bke = BK) {
     SplitPlan s;
     s.tiles_m = (M + BM - 1) / BM;
     s.tiles_n = (N + BN - 1) / BN;
-    s.nkb = (K + BK - 1) / BK;
+    s.nkb = (K + bke - 1) / bke;
     const int tiles = s.tiles_m * s.tiles_n;
     int nsplit = 1;
     if (tiles < 111 && s.nkb >= 16) {
@@ -374,45 +268,44 @@ static SplitPlan plan_split(int M, int N, int K) {
     return s;
 }
 
-}  // namespace scvae
-
-using namespace scvae;
-
-extern "C" int64_t scvae_gemm_tf32_workspace_bytes(int layout, int M, int N, int K) {
-    (void)layout;
+static int64_t workspace_bytes(int M, int N, int K, int bke) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
-    const SplitPlan s = plan_split(M, N, K);
+    const SplitPlan s = plan_split(M, N, K, bke);
     if (s.nsplit == 1) return 0;
     const int64_t ldw = (N + 3) & ~3;
     return (int64_t)s.nsplit * s.tiles_m * BM * ldw * 4;
 }
 
-extern "C" int scvae_gemm_tf32(int layout, int M, int N, int K, const float *A, int64_t lda, const float *B,
-                               int64_t ldb, float *C, int64_t ldc, int accumulate, void *workspace,
-                               int64_t workspace_bytes, void *stream) {
-    SCVAE_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "gemm_tf32: bad arguments");
-    SCVAE_CHECK_ARG(aligned16(A) && aligned16(B) && aligned16(C) && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0,
-                    "gemm_tf32: operands must be 16-byte aligned with leading dimensions multiple of 4");
-    cudaStream_t s = (cudaStream_t)stream;
-    SplitPlan sp = plan_split(M, N, K);
+template <bool F16>
+static int launch_gemm(const char *name, int layout, int M, int N, int K, const void *A, int64_t lda, const void *B,
+                       int64_t ldb, float *C, int64_t ldc, int accumulate, float alpha, void *workspace,
+                       int64_t workspace_bytes_given, cudaStream_t s) {
+    constexpr int EB = F16 ? 2 : 4;
+    constexpr int BKE = 128 / EB;
+    constexpr int LDM = 16 / EB;   // leading dimensions must be multiples of 16 bytes
+    SCVAE_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "%s: bad arguments", name);
+    SCVAE_CHECK_ARG(aligned16(A) && aligned16(B) && aligned16(C) && lda % LDM == 0 && ldb % LDM == 0 && ldc % 4 == 0,
+                    "%s: operands must be 16-byte aligned with 16-byte-multiple leading dimensions", name);
+    SplitPlan sp = plan_split(M, N, K, BKE);
     const int64_t ldw = (N + 3) & ~3;
     const int ws_rows = sp.tiles_m * BM;
     if (sp.nsplit > 1) {
         const int64_t need = (int64_t)sp.nsplit * ws_rows * ldw * 4;
-        if (!workspace || workspace_bytes < need) {  // no workspace: run unsplit
+        if (!workspace || workspace_bytes_given < need) {  // no workspace: run unsplit
             sp.nsplit = 1;
             sp.kb_per_split = sp.nkb;
         }
     }
     CUtensorMap tmA, tmB, tmC;
     const bool a_mn = (layout == SCVAE_GEMM_TN), b_mn = (layout != SCVAE_GEMM_NT);
-    // K-major operand (rows = M or N, cols = K): box 32 (K) x 128 (rows).
-    // MN-major operand (rows = K, cols = M or N): box 32 (MN) x 32 (K rows), four per tile,
-    // swizzled in 32-byte chunks (Swizzle<2,5,2>, atom = 128 B of MN x 4 K rows).
-    if (a_mn) { if (make_map(&tmA, A, K, M, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1; }
-    else      { if (make_map(&tmA, A, M, K, lda, 32, 128)) return 1; }
-    if (b_mn) { if (make_map(&tmB, B, K, N, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1; }
-    else      { if (make_map(&tmB, B, N, K, ldb, 32, 128)) return 1; }
+    // K-major operand (rows = M or N, cols = K): box BKE (K) x 128 (rows), SWIZZLE_128B.
+    // MN-major operand (rows = K, cols = M or N): boxes of 128 bytes (MN) x BKE (K rows); fp32
+    // needs the 32-byte-atom swizzle (Swizzle<2,5,2>, atom = 128 B of MN x 4 K rows).
+    const CUtensorMapSwizzle mn_sw = F16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if (a_mn) { if (make_map(&tmA, A, K, M, lda, 128 / EB, BKE, mn_sw, EB)) return 1; }
+    else      { if (make_map(&tmA, A, M, K, lda, BKE, 128, CU_TENSOR_MAP_SWIZZLE_128B, EB)) return 1; }
+    if (b_mn) { if (make_map(&tmB, B, K, N, ldb, 128 / EB, BKE, mn_sw, EB)) return 1; }
+    else      { if (make_map(&tmB, B, N, K, ldb, BKE, 128, CU_TENSOR_MAP_SWIZZLE_128B, EB)) return 1; }
     if (sp.nsplit > 1) {
         if (make_map(&tmC, (const float *)workspace, (int64_t)sp.nsplit * ws_rows, N, ldw, 32, 128)) return 1;
     } else {
@@ -423,51 +316,76 @@ extern "C" int scvae_gemm_tf32(int layout, int M, int N, int K, const float *A, 
     p.tiles_m = sp.tiles_m; p.tiles_n = sp.tiles_n; p.nsplit = sp.nsplit;
     p.kb_per_split = sp.kb_per_split; p.nkb = sp.nkb;
     p.accumulate = accumulate; p.ws_rows = ws_rows;
-    p.mn_lbo = 4096; p.mn_sbo = 512;  // MN-group (TMA box) stride; 4-row K-group stride
+    p.alpha = sp.nsplit > 1 ? 1.f : alpha;
+    // MN-group (TMA box) stride; K-group stride (4 rows for the 32-byte-atom swizzle, else 8)
+    p.mn_lbo = BKE * 128; p.mn_sbo = F16 ? 1024 : 512;
     if (const char *e = getenv("SCVAE_TC_MN_LBO")) p.mn_lbo = (uint32_t)atoi(e);
     if (const char *e = getenv("SCVAE_TC_MN_SBO")) p.mn_sbo = (uint32_t)atoi(e);
 
     const int total = sp.tiles_m * sp.tiles_n * sp.nsplit;
-    int sms = 148;
-    {
-        static int cached = 0;
-        if (!cached) {
-            int dev = 0, n = 0;
-            if (cudaGetDevice(&dev) == cudaSuccess &&
-                cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-                cached = n;
-            else
-                cached = 148;
-        }
-        sms = cached;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            sms = n;
+        else
+            sms = 148;
     }
     const int grid = total < sms ? total : sms;
 #define LAUNCH(AM, BMN)                                                                                     \
     do {                                                                                                    \
         static bool attr_set = false;                                                                       \
         if (!attr_set) {                                                                                    \
-            cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<AM, BMN>,                                 \
+            cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<F16, AM, BMN>,                              \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);  \
-            SCVAE_CHECK_ARG(e == cudaSuccess, "gemm_tf32: cannot set smem attribute: %s",                   \
+            SCVAE_CHECK_ARG(e == cudaSuccess, "%s: cannot set smem attribute: %s", name,                    \
                             cudaGetErrorString(e));                                                         \
             attr_set = true;                                                                                \
         }                                                                                                   \
-        gemm_tf32_kernel<AM, BMN><<<grid, kThreads, kSmemBytes, s>>>(tmA, tmB, tmC, p);                     \
+        gemm_tc_kernel<F16, AM, BMN><<<grid, kThreads, kSmemBytes, s>>>(tmA, tmB, tmC, p);                  \
     } while (0)
     switch (layout) {
         case SCVAE_GEMM_NT: LAUNCH(false, false); break;
         case SCVAE_GEMM_NN: LAUNCH(false, true); break;
         case SCVAE_GEMM_TN: LAUNCH(true, true); break;
-        default: set_error("gemm_tf32: unknown layout %d", layout); return 1;
+        default: set_error("%s: unknown layout %d", name, layout); return 1;
     }
 #undef LAUNCH
-    SCVAE_CHECK_LAUNCH("gemm_tf32");
+    SCVAE_CHECK_LAUNCH(name);
     if (sp.nsplit > 1) {
         const dim3 grid2((N + 127) / 128, M);
-        SCVAE_CHECK_ARG(M <= 65535, "gemm_tf32: split-K reduce supports M <= 65535");
+        SCVAE_CHECK_ARG(M <= 65535, "%s: split-K reduce supports M <= 65535", name);
         splitk_reduce_kernel<<<grid2, 128, 0, s>>>((const float *)workspace, ldw, ws_rows, sp.nsplit, M, N, C, ldc,
-                                                   accumulate);
+                                                   accumulate, alpha);
         SCVAE_CHECK_LAUNCH("splitk_reduce");
     }
     return 0;
+}
+
+}  // namespace scvae
+
+using namespace scvae;
+
+extern "C" int64_t scvae_gemm_tf32_workspace_bytes(int layout, int M, int N, int K) {
+    (void)layout;
+    return workspace_bytes(M, N, K, 32);
+}
+extern "C" int64_t scvae_gemm_f16_workspace_bytes(int layout, int M, int N, int K) {
+    (void)layout;
+    return workspace_bytes(M, N, K, 64);
+}
+
+extern "C" int scvae_gemm_tf32(int layout, int M, int N, int K, const float *A, int64_t lda, const float *B,
+                               int64_t ldb, float *C, int64_t ldc, int accumulate, void *workspace,
+                               int64_t workspace_bytes, void *stream) {
+    return launch_gemm<false>("gemm_tf32", layout, M, N, K, A, lda, B, ldb, C, ldc, accumulate, 1.f, workspace,
+                              workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int scvae_gemm_f16(int layout, int M, int N, int K, const void *A, int64_t lda, const void *B,
+                              int64_t ldb, float *C, int64_t ldc, int accumulate, float alpha, void *workspace,
+                              int64_t workspace_bytes, void *stream) {
+    return launch_gemm<true>("gemm_f16", layout, M, N, K, A, lda, B, ldb, C, ldc, accumulate, alpha, workspace,
+                             workspace_bytes, (cudaStream_t)stream);
 }

@@ -1,6 +1,8 @@
 // a8: elementwise gradient clip + TensorFlow-style Adam (VAE:2736-2770), one fused pass over
 // the flat parameter buffer.  tf.train.AdamOptimizer: lr_t = lr sqrt(1-b2^t)/(1-b1^t),
 // theta -= lr_t m / (sqrt(v) + eps)  (epsilon outside the bias correction).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace scvae {
@@ -29,6 +31,14 @@ adam_clip_kernel(float *__restrict__ p, const float *__restrict__ g, float *__re
     }
 }
 
+// fp16 operand copy of an fp32 master tensor, zero padded to the destination width
+__global__ void f32_to_f16_kernel(const float *__restrict__ src, int64_t lds, int cols, __half *__restrict__ dst,
+                                  int64_t ldd, float scale) {
+    const int64_t r = blockIdx.x;
+    for (int c = threadIdx.x + blockIdx.y * blockDim.x; c < ldd; c += blockDim.x * gridDim.y)
+        dst[r * ldd + c] = __float2half_rn(c < cols ? src[r * lds + c] * scale : 0.f);
+}
+
 __global__ void step_advance_kernel(int64_t *step) { *step += 1; }
 
 }  // namespace scvae
@@ -53,5 +63,15 @@ extern "C" int scvae_step_advance(int64_t *step, void *stream) {
     SCVAE_CHECK_ARG(step, "step_advance: NULL");
     step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
     SCVAE_CHECK_LAUNCH("step_advance");
+    return 0;
+}
+
+extern "C" int scvae_f32_to_f16(const float *src, int64_t lds, int64_t rows, int cols, void *dst, int64_t ldd,
+                                float scale, void *stream) {
+    using namespace scvae;
+    SCVAE_CHECK_ARG(src && dst && rows > 0 && cols > 0 && ldd >= cols, "f32_to_f16: bad arguments");
+    const dim3 grid((unsigned)rows, (unsigned)((ldd + 1023) / 1024));
+    f32_to_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, lds, cols, (__half *)dst, ldd, scale);
+    SCVAE_CHECK_LAUNCH("f32_to_f16");
     return 0;
 }

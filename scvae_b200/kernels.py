@@ -72,6 +72,25 @@ def gemm(layout, M, N, K, A, B, C, accumulate=False, tensor_cores=True, workspac
                                       _ld(C), int(accumulate), _stream()), "gemm_f32")
 
 
+def gemm_f16(layout, M, N, K, A, B, C, accumulate=False, alpha=1.0, workspace=None):
+    """fp16 operands (torch.float16 2-D row-major views), fp32 output."""
+    lib = _lib.load()
+    ws_bytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
+    _lib.check(lib.scvae_gemm_f16(layout, M, N, K, _p(A), _ld(A), _p(B), _ld(B), _p(C), _ld(C),
+                                  int(accumulate), float(alpha), _p(workspace), ws_bytes,
+                                  _stream()), "gemm_f16")
+
+
+def gemm_f16_workspace_bytes(layout, M, N, K):
+    return int(_lib.load().scvae_gemm_f16_workspace_bytes(layout, M, N, K))
+
+
+def f32_to_f16(src, cols, dst, scale=1.0):
+    lib = _lib.load()
+    _lib.check(lib.scvae_f32_to_f16(_p(src), _ld(src), src.shape[0], cols, _p(dst), _ld(dst),
+                                    float(scale), _stream()), "f32_to_f16")
+
+
 def gemm_workspace_bytes(layout, M, N, K):
     return int(_lib.load().scvae_gemm_tf32_workspace_bytes(layout, M, N, K))
 

@@ -306,6 +306,48 @@ def test_gemm_tf32(layout, M, N, Kd):
     assert err <= 2 * tol, ("accumulate", layout, M, N, Kd, err)
 
 
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("M,N,Kd", [(128, 128, 64), (256, 384, 192), (100, 104, 2001), (4096, 104, 5001),
+                                    (1000, 2100, 101)])
+def test_gemm_f16(layout, M, N, Kd):
+    """tcgen05 kind::f16 GEMM: exact products of the fp16 operands, fp32 accumulation."""
+    from scvae_b200 import kernels as K
+    gen = torch.Generator().manual_seed(layout * 10 + N)
+    A, B = _gemm_operands(layout, M, N, Kd, gen)
+    dev = _dev()
+
+    def pad16(t):
+        ld = (t.shape[1] + 7) & ~7
+        out = torch.zeros(t.shape[0], ld, dtype=torch.float16, device=dev)
+        out[:, :t.shape[1]] = t.to(torch.float16)
+        return out
+    Ad, Bd = pad16(A), pad16(B)
+    A16 = Ad[:, :A.shape[1]].cpu().double()
+    B16 = Bd[:, :B.shape[1]].cpu().double()
+    ref = _gemm_ref(layout, A16, B16)
+    C = torch.full((M, (N + 3) & ~3), 3.0, device=dev)
+    ws = torch.empty(max(K.gemm_f16_workspace_bytes(layout, M, N, Kd) // 4, 1), device=dev)
+    K.gemm_f16(layout, M, N, Kd, Ad, Bd, C, alpha=0.5, workspace=ws)
+    torch.cuda.synchronize()
+    tol = 1e-6 * math.sqrt(Kd) * 30
+    err = (C[:, :N].cpu().double() - 0.5 * ref).abs().max().item()
+    assert err <= tol, (layout, M, N, Kd, err, tol)
+    K.gemm_f16(layout, M, N, Kd, Ad, Bd, C, accumulate=True, alpha=0.5, workspace=ws)
+    torch.cuda.synchronize()
+    err = (C[:, :N].cpu().double() - ref).abs().max().item()
+    assert err <= 2 * tol, ("accumulate", layout, M, N, Kd, err)
+
+
+def test_f32_to_f16():
+    from scvae_b200 import kernels as K
+    dev = _dev()
+    src = torch.randn(37, 104, device=dev)
+    dst = torch.full((37, 128), 9.0, dtype=torch.float16, device=dev)
+    K.f32_to_f16(src, 101, dst, scale=2.0)
+    assert torch.equal(dst[:, :101], (src[:, :101] * 2.0).half())
+    assert torch.all(dst[:, 101:] == 0)
+
+
 def test_adam_clip_step():
     from scvae_b200 import kernels as K
     torch.manual_seed(2)
