@@ -240,6 +240,7 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ ws, int64_t ldw, 
     if (n >= N) return;
     float acc = 0.f;
     for (int s = 0; s < nsplit; ++s) acc += ws[((int64_t)s * ws_rows + m) * ldw + n];
+    acc *= alpha;
     float *c = C + (int64_t)m * ldc + n;
     *c = accumulate ? *c + acc : acc;
 }
