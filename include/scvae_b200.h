@@ -59,10 +59,15 @@ long long   scvae_launch_count(void);
  * row_const (nullable, [B]) receives sum_g lgamma(1 + x[b,g]), the data-only constant of
  * every count log-likelihood.  rebase != 0: `indptr` holds absolute offsets of
  * a row slab whose nonzeros start at indices[0]/values[0] (offsets are taken relative to
- * indptr[0]) -- the streaming path ships one such slab per step from pinned host memory. */
+ * indptr[0]) -- the streaming path ships one such slab per step from pinned host memory.
+ * t16 (nullable, (B, ldt16) uint16, ldt16 % 8 == 0): 16-bit copy of the counts (clamped to
+ * 65535) for the fused likelihood heads. */
 int scvae_csr_densify(const int64_t *indptr, const int32_t *indices, const float *values,
                       const int64_t *rows, int B, int G, float *x, int64_t ldx,
-                      float *row_const, int rebase, void *stream);
+                      float *row_const, int rebase, void *t16, int64_t ldt16, void *stream);
+/* Dense fp32 counts -> uint16 (clamped), zero padded to ldt16 columns. */
+int scvae_f32_to_u16(const float *x, int64_t ldx, int64_t rows, int G, void *t16, int64_t ldt16,
+                     void *stream);
 
 /* ---- a2: dense layers  (MU:38-76 fully_connected; its gradients) ----------------------
  * C[M,N] (+)= op(A) op(B), fp32 in / fp32 out.  `accumulate` != 0 adds into C.
@@ -151,6 +156,23 @@ int scvae_likelihood_bwd(int kind, const float *t, int64_t ldt, int t_rows, cons
                          const float *row_const, const float *go, float go_scalar,
                          float *da, int64_t ldda, int64_t dhead_stride, float *logp,
                          void *stream);
+
+/* ---- a4 + a5 fused: likelihood heads without the (cells x P*genes) round trip ----------------
+ * One kernel computes a = d W^T (tcgen05, fp16 operands), log p(t | a) summed over genes, its
+ * gradient da and the decoder gradient dd = da W; only da (fp16, scaled by `scale`) is written
+ * to HBM, for the weight-gradient product dW = da^T d (scvae_gemm_f16 with alpha = 1/scale).
+ *   d16  (M, 128) fp16: decoder output, augmented, zero padded to 128 columns (n_in + 1 <= 128)
+ *   w16  (P*head_stride, 128) fp16: head weights, head h at rows [h*head_stride, +G), zero
+ *        padded; head_stride % 64 == 0
+ *   t16  (t_rows, ldt) uint16 targets (row m uses t row m % t_rows; t_rows % 128 == 0 or == M)
+ *   da16 (M, P*head_stride) fp16 out; dd (M, lddd) fp32 out (first dd_cols columns);
+ *   logp [M] out; workspace: scvae_heads_fused_workspace_floats(M, G) floats. */
+int64_t scvae_heads_fused_workspace_floats(int M, int G);
+int scvae_heads_fused_bwd(int kind, const void *d16, const void *w16, int64_t head_stride,
+                          const void *t16, int64_t ldt, int t_rows, int M, int G,
+                          const float *row_const, const float *go, float go_scalar, float scale,
+                          void *da16, float *dd, int64_t lddd, int dd_cols, float *logp,
+                          float *workspace, void *stream);
 
 /* ---- a7: evaluate-only moments  (VAE:2534-2552, VAE:2665-2713, ZI:180-192;
  * GMVAE:3312-3386) ---------------------------------------------------------------------

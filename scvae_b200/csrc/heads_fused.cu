@@ -1,0 +1,458 @@
+// Fused likelihood heads: GEMM -> count likelihood -> (log p, d log p/d a) -> dgrad GEMM in ONE
+// kernel, so the (cells x P*genes) head pre-activations never exist in HBM.
+//
+// Replaces, for one training step, the chain
+//     X_TILDE/<param> fully_connected  (VAE:2466-2489)   a   = d W^T          (cells x P*genes)
+//     p_x_given_z.log_prob + reduce_sum (VAE:2583-2590)  logp, da             (cells x P*genes)
+//     autodiff of the heads w.r.t. the decoder output     dd  = da W           (cells x H)
+// and leaves only `da` (in fp16) for the weight-gradient product dW = da^T d, which is a plain
+// tcgen05 GEMM (scvae_gemm_f16).  Per step at C2 this removes ~2.6 GB of HBM traffic.
+//
+// Structure (one CTA = 128 cells x a range of 64-gene tiles, 12 warps, 1 CTA/SM):
+//   warp 0     TMA producer: decoder-output tile d (128 x 128 fp16, once), then per gene tile the
+//              head-weight tiles W_p (64 x 128 fp16) and the target tile t (128 x 64 u16);
+//   warp 1     one thread issues tcgen05.mma kind::f16:
+//                MMA1  S_p[128 x 64]  = d . W_p^T            (TMEM, double buffered)
+//                MMA2  dd[128 x 128] += da_p . W_p            (TMEM, accumulated over all tiles;
+//                      W_p is the SAME smem tile read as an MN-major operand)
+//   warps 4-11 epilogue: tcgen05.ld S -> likelihood math (likelihood_math.cuh) -> row-sum of
+//              log p in registers, da_p -> fp16 -> swizzled smem (operand of MMA2 AND source of
+//              the TMA store of da to HBM);
+//   MMA1 of tile n+1 overlaps the epilogue of tile n (issue order: MMA1(n+1), MMA2(n)).
+// Gene-range partial sums (log p per cell, dd) are combined deterministically / by TMA
+// reduce-add.  Gradients are scaled by `scale` before the fp16 conversion and un-scaled in the
+// consumers (loss-scaling against fp16 underflow).
+#include "likelihood_math.cuh"
+#include "tc_common.cuh"
+
+namespace scvae {
+
+constexpr int FM = 128;        // cells per CTA
+constexpr int FG = 64;         // genes per tile
+constexpr int FK = 128;        // padded hidden width (fp16 elements)
+constexpr int FThreads = 384;  // 4 control warps + 8 epilogue warps
+constexpr int FDBytes = FM * FK * 2;         // 32 KB
+constexpr int FWBytes = FG * FK * 2;         // 16 KB per head
+constexpr int FABytes = FM * FG * 2;         // 16 KB per head (da tile)
+constexpr int FTBytes = FM * FG * 2;         // 16 KB (u16 targets)
+
+__host__ __device__ constexpr int fused_smem_bytes(int P) {
+    return FDBytes + 2 * P * FWBytes + P * FABytes + 2 * FTBytes + 1024 /*align*/ + 2048 /*barriers, partials*/;
+}
+
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void bar_sync_n(int id, int n) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+struct FusedParams {
+    int M, G, t_rows;
+    int tiles_per_cta, n_tiles, gsplit;
+    int64_t head_stride;      // columns between heads in W16 rows / da16 columns (multiple of 64)
+    int64_t part_stride;      // rows per split slice of logp_part
+    const float *go;          // nullable per-row upstream gradient
+    float go_scalar, scale, inv_scale;
+    int has_const;            // sum_g lgamma(1+t) is subtracted by the finish kernel
+    float *logp_part;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(FThreads, 1)
+heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmW,
+                   const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmDA,
+                   const __grid_constant__ CUtensorMap tmDD, const FusedParams p) {
+    constexpr int P = Lik<KIND>::P;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sD = smem;
+    uint8_t *sW = sD + FDBytes;                 // [2 stages][P][2 k-halves][64 genes][128 B]
+    uint8_t *sA = sW + 2 * P * FWBytes;         // [P][128 rows][128 B]
+    uint8_t *sT = sA + P * FABytes;             // [2 stages][128 rows][128 B]
+    uint64_t *bars = (uint64_t *)(sT + 2 * FTBytes);
+    enum { D_FULL = 0, W_FULL = 1, W_EMPTY = 3, T_FULL = 5, T_EMPTY = 7, S_FULL = 9, S_EMPTY = 11,
+           A_FULL = 13, A_EMPTY = 14, DD_FULL = 15, NBARS = 16 };
+    const uint32_t bar0 = smem_u32(bars);
+    auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    uint32_t *tmem_slot = (uint32_t *)(bars + NBARS);
+    float *s_part = (float *)(bars + NBARS + 1);   // [2][128] log p partials of the two halves
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rt = blockIdx.x / p.gsplit, gs = blockIdx.x % p.gsplit;
+    const int row0 = rt * FM;
+    const int tile0 = gs * p.tiles_per_cta;
+    const int tile1 = min(tile0 + p.tiles_per_cta, p.n_tiles);
+    const int ntile = tile1 - tile0;             // >= 1 by construction
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmT) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDD) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(bar(D_FULL), 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar(W_FULL + i), 1);
+            mbar_init(bar(W_EMPTY + i), 1);
+            mbar_init(bar(T_FULL + i), 1);
+            mbar_init(bar(T_EMPTY + i), 8);
+            mbar_init(bar(S_FULL + i), 1);
+            mbar_init(bar(S_EMPTY + i), 8);
+        }
+        mbar_init(bar(A_FULL), 1);
+        mbar_init(bar(A_EMPTY), 1);
+        mbar_init(bar(DD_FULL), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base;                     // [2][P][64 columns]
+    const uint32_t tmem_DD = tmem_base + 2 * P * FG;       // 128 columns
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_expect_tx(bar(D_FULL), FDBytes);
+            tma_load_2d(smem_u32(sD), &tmD, 0, row0, bar(D_FULL));
+            tma_load_2d(smem_u32(sD) + FDBytes / 2, &tmD, 64, row0, bar(D_FULL));
+            const int trow0 = row0 % p.t_rows;
+            for (int n = 0; n < ntile; ++n) {
+                const int st = n & 1;
+                const uint32_t ph = (n >> 1) & 1;
+                const int g0 = (tile0 + n) * FG;
+                mbar_wait(bar(W_EMPTY + st), ph ^ 1);
+                mbar_expect_tx(bar(W_FULL + st), P * FWBytes);
+#pragma unroll
+                for (int h = 0; h < P; ++h) {
+                    const uint32_t dst = smem_u32(sW + (st * P + h) * FWBytes);
+                    const int wrow = (int)(h * p.head_stride) + g0;
+                    tma_load_2d(dst, &tmW, 0, wrow, bar(W_FULL + st));
+                    tma_load_2d(dst + FWBytes / 2, &tmW, 64, wrow, bar(W_FULL + st));
+                }
+                mbar_wait(bar(T_EMPTY + st), ph ^ 1);
+                mbar_expect_tx(bar(T_FULL + st), FTBytes);
+                tma_load_2d(smem_u32(sT + st * FTBytes), &tmT, g0, trow0, bar(T_FULL + st));
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // D = f32, A = B = f16; MMA1: 128 x 64, both K-major; MMA2: 128 x 128, B MN-major
+            const uint32_t idesc1 = (1u << 4) | ((uint32_t)(FG >> 3) << 17) | ((uint32_t)(FM >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (1u << 16) | ((uint32_t)(FK >> 3) << 17) |
+                                    ((uint32_t)(FM >> 4) << 24);
+            mbar_wait(bar(D_FULL), 0);
+            tc_fence_after();
+            const uint32_t aD = smem_u32(sD);
+            auto mma2 = [&](int n) {   // dd += da(n) . W(n)
+                const int st = n & 1;
+                mbar_wait(bar(A_FULL), (uint32_t)(n & 1));
+                tc_fence_after();
+#pragma unroll
+                for (int h = 0; h < P; ++h) {
+                    const uint32_t aA = smem_u32(sA + h * FABytes);
+                    const uint32_t aW = smem_u32(sW + (st * P + h) * FWBytes);
+#pragma unroll
+                    for (int j = 0; j < FG / 16; ++j) {
+                        const uint64_t da = make_desc(aA + 32 * j, 16, 1024, 2);
+                        const uint64_t db = make_desc(aW + 2048 * j, FWBytes / 2, 1024, 2);
+                        tc_mma_f16(tmem_DD, da, db, idesc2, (n > 0 || h > 0 || j > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(bar(A_EMPTY));
+                tc_commit(bar(W_EMPTY + st));
+            };
+            for (int n = 0; n < ntile; ++n) {
+                const int st = n & 1;
+                const uint32_t ph = (n >> 1) & 1;
+                mbar_wait(bar(W_FULL + st), ph);
+                mbar_wait(bar(S_EMPTY + st), ph ^ 1);
+                tc_fence_after();
+#pragma unroll
+                for (int h = 0; h < P; ++h) {
+                    const uint32_t aW = smem_u32(sW + (st * P + h) * FWBytes);
+                    const uint32_t dS = tmem_S + (st * P + h) * FG;
+#pragma unroll
+                    for (int kk = 0; kk < FK / 16; ++kk) {
+                        const uint32_t off = (kk >> 2) * (FDBytes / 2) + (kk & 3) * 32;
+                        const uint32_t offw = (kk >> 2) * (FWBytes / 2) + (kk & 3) * 32;
+                        tc_mma_f16(dS, make_desc(aD + off, 16, 1024, 2), make_desc(aW + offw, 16, 1024, 2),
+                                   idesc1, kk > 0 ? 1u : 0u);
+                    }
+                }
+                tc_commit(bar(S_FULL + st));
+                if (n > 0) mma2(n - 1);
+            }
+            mma2(ntile - 1);
+            tc_commit(bar(DD_FULL));
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const int e = warp - 4;
+        const int q = e & 3;                     // TMEM lane quadrant (== warp % 4)
+        const int half = e >> 2;                 // which 32 genes of the 64-gene tile
+        const int row = q * 32 + lane;
+        const bool issuer = (threadIdx.x == 128);
+        const int grow = row0 + row;
+        const float gs_row = (grow < p.M ? (p.go ? p.go[grow] : p.go_scalar) : 0.f) * p.scale;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        float acc = 0.f;
+        for (int n = 0; n < ntile; ++n) {
+            const int st = n & 1;
+            const uint32_t ph = (n >> 1) & 1;
+            const int g0 = (tile0 + n) * FG;
+            mbar_wait(bar(S_FULL + st), ph);
+            mbar_wait(bar(T_FULL + st), ph);
+            tc_fence_after();
+            // da(n-1) has been consumed by MMA2 and read by its TMA store before we overwrite it
+            if (n > 0) mbar_wait(bar(A_EMPTY), (uint32_t)((n - 1) & 1));
+            if (issuer) tma_wait_read<0>();
+            bar_sync_n(1, 256);
+            const uint8_t *trow = sT + st * FTBytes + row * 128;
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+                const int gc = half * 32 + sub * 16;          // first gene of this 16-gene chunk
+                uint32_t sv[3][16];
+#pragma unroll
+                for (int h = 0; h < P; ++h) tc_ld16(tmem_S + lane_addr + (st * P + h) * FG + gc, sv[h]);
+                const int c0 = gc >> 3;                         // 16-byte chunk index in the row
+                const uint4 t0 = *reinterpret_cast<const uint4 *>(trow + (((c0) ^ (row & 7)) << 4));
+                const uint4 t1 = *reinterpret_cast<const uint4 *>(trow + (((c0 + 1) ^ (row & 7)) << 4));
+                const uint32_t tw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+                tc_wait_ld();
+                uint32_t packed[3][8];
+#pragma unroll
+                for (int grp = 0; grp < 4; ++grp) {
+                    float x[4], av[3][4], gv[3][4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t w = tw[grp * 2 + (j >> 1)];
+                        x[j] = (float)((j & 1) ? (w >> 16) : (w & 0xffffu));
+#pragma unroll
+                        for (int h = 0; h < P; ++h) av[h][j] = __uint_as_float(sv[h][grp * 4 + j]);
+                    }
+                    float lp = 0.f;
+                    lik_group<KIND, true, 4>(x, av, p.has_const != 0, lp, gv);
+                    const bool valid = (g0 + gc + grp * 4) < p.G;   // G % 4 == 0
+                    acc += valid ? lp : 0.f;
+                    const float gsv = valid ? gs_row : 0.f;
+#pragma unroll
+                    for (int h = 0; h < P; ++h) {
+                        packed[h][grp * 2] = pack_half2(gv[h][0] * gsv, gv[h][1] * gsv);
+                        packed[h][grp * 2 + 1] = pack_half2(gv[h][2] * gsv, gv[h][3] * gsv);
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < P; ++h) {
+                    uint8_t *arow = sA + h * FABytes + row * 128;
+                    *reinterpret_cast<uint4 *>(arow + (((c0) ^ (row & 7)) << 4)) =
+                        make_uint4(packed[h][0], packed[h][1], packed[h][2], packed[h][3]);
+                    *reinterpret_cast<uint4 *>(arow + (((c0 + 1) ^ (row & 7)) << 4)) =
+                        make_uint4(packed[h][4], packed[h][5], packed[h][6], packed[h][7]);
+                }
+            }
+            // S(n) and t(n) are in registers / consumed: release them
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar(S_EMPTY + st));
+                mbar_arrive(bar(T_EMPTY + st));
+            }
+            fence_async_smem();
+            bar_sync_n(1, 256);
+            if (issuer) {
+#pragma unroll
+                for (int h = 0; h < P; ++h)
+                    tma_store_2d(&tmDA, (int)(h * p.head_stride) + g0, row0, smem_u32(sA + h * FABytes));
+                tma_commit();
+                mbar_arrive(bar(A_FULL));
+            }
+        }
+        // ---- log p partial of this gene range: combine the two halves, fixed order ----
+        s_part[half * 128 + row] = acc;
+        bar_sync_n(1, 256);
+        if (half == 0 && grow < p.M)
+            p.logp_part[(int64_t)gs * p.part_stride + grow] = s_part[row] + s_part[128 + row];
+        // ---- dd partial: TMEM -> staging smem (the t stages) -> TMA reduce-add ----
+        mbar_wait(bar(DD_FULL), 0);
+        tc_fence_after();
+        if (issuer) tma_wait_read<0>();
+        bar_sync_n(1, 256);
+        uint8_t *stage = sT + half * FTBytes;       // 128 rows x 32 fp32 columns
+        const bool half_issuer = (lane == 0 && q == 0);
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tc_ld32(tmem_DD + lane_addr + half * 64 + c * 32, v);
+            tc_wait_ld();
+            if (c > 0) {
+                if (half_issuer) tma_wait_read<0>();
+                bar_sync_n(2 + half, 128);
+            }
+            uint8_t *dst = stage + row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint4 val = make_uint4(
+                    __float_as_uint(__uint_as_float(v[4 * j]) * p.inv_scale),
+                    __float_as_uint(__uint_as_float(v[4 * j + 1]) * p.inv_scale),
+                    __float_as_uint(__uint_as_float(v[4 * j + 2]) * p.inv_scale),
+                    __float_as_uint(__uint_as_float(v[4 * j + 3]) * p.inv_scale));
+                *reinterpret_cast<uint4 *>(dst + ((j ^ (row & 7)) << 4)) = val;
+            }
+            fence_async_smem();
+            bar_sync_n(2 + half, 128);
+            if (half_issuer) {
+                tma_reduce_add_2d(&tmDD, half * 64 + c * 32, row0, smem_u32(stage));
+                tma_commit();
+            }
+        }
+        if (half_issuer || issuer) tma_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+// logp[m] = sum_s part[s][m] - row_const[m % t_rows]
+__global__ void fused_finish_kernel(const float *__restrict__ part, int64_t part_stride, int gsplit, int M,
+                                    const float *__restrict__ row_const, int t_rows, float *__restrict__ logp) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    float acc = 0.f;
+    for (int s = 0; s < gsplit; ++s) acc += part[(int64_t)s * part_stride + m];
+    logp[m] = acc - (row_const ? row_const[m % t_rows] : 0.f);
+}
+
+static inline int make_map_u16(CUtensorMap *map, const void *base, int64_t rows, int64_t cols, int64_t ld,
+                               int box_cols, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    SCVAE_CHECK_ARG(enc, "heads_fused: cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, (void *)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SCVAE_CHECK_ARG(r == CUDA_SUCCESS, "heads_fused: tensor map (u16) failed (%d)", (int)r);
+    return 0;
+}
+
+struct FusedPlan {
+    int row_tiles, n_tiles, gsplit, tiles_per_cta;
+};
+static FusedPlan fused_plan(int M, int G) {
+    FusedPlan f;
+    f.row_tiles = (M + FM - 1) / FM;
+    f.n_tiles = (G + FG - 1) / FG;
+    int target = (2 * 148 + f.row_tiles / 2) / f.row_tiles;   // about two waves of CTAs
+    if (target < 1) target = 1;
+    if (target > f.n_tiles) target = f.n_tiles;
+    f.tiles_per_cta = (f.n_tiles + target - 1) / target;
+    f.gsplit = (f.n_tiles + f.tiles_per_cta - 1) / f.tiles_per_cta;
+    return f;
+}
+
+template <int KIND>
+static int launch_fused(const void *d16, const void *w16, const void *t16, int64_t ldt, int t_rows, int M, int G,
+                        int64_t head_stride, const float *go, float go_scalar, float scale, void *da16,
+                        float *dd, int64_t lddd, int dd_cols, float *logp_part, const float *row_const,
+                        float *logp, cudaStream_t s) {
+    constexpr int P = Lik<KIND>::P;
+    const FusedPlan f = fused_plan(M, G);
+    CUtensorMap tmD, tmW, tmT, tmDA, tmDD;
+    if (make_map(&tmD, d16, M, FK, FK, 64, FM, CU_TENSOR_MAP_SWIZZLE_128B, 2)) return 1;
+    if (make_map(&tmW, w16, (int64_t)P * head_stride, FK, FK, 64, FG, CU_TENSOR_MAP_SWIZZLE_128B, 2)) return 1;
+    if (make_map_u16(&tmT, t16, t_rows, G, ldt, FG, FM)) return 1;
+    if (make_map(&tmDA, da16, M, (int64_t)P * head_stride, (int64_t)P * head_stride, FG, FM,
+                 CU_TENSOR_MAP_SWIZZLE_128B, 2))
+        return 1;
+    if (make_map(&tmDD, dd, M, dd_cols, lddd, 32, FM)) return 1;
+    FusedParams p;
+    p.M = M; p.G = G; p.t_rows = t_rows;
+    p.tiles_per_cta = f.tiles_per_cta; p.n_tiles = f.n_tiles; p.gsplit = f.gsplit;
+    p.head_stride = head_stride;
+    p.part_stride = (int64_t)f.row_tiles * FM;
+    p.go = go; p.go_scalar = go_scalar; p.scale = scale; p.inv_scale = 1.f / scale;
+    p.logp_part = logp_part;
+    p.has_const = row_const != nullptr;
+    constexpr int smem = fused_smem_bytes(P);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(heads_fused_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             smem);
+        SCVAE_CHECK_ARG(e == cudaSuccess, "heads_fused: cannot set smem attribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    cudaError_t e = cudaMemsetAsync(dd, 0, (size_t)M * lddd * sizeof(float), s);
+    SCVAE_CHECK_ARG(e == cudaSuccess, "heads_fused: memset failed: %s", cudaGetErrorString(e));
+    heads_fused_kernel<KIND><<<f.row_tiles * f.gsplit, FThreads, smem, s>>>(tmD, tmW, tmT, tmDA, tmDD, p);
+    SCVAE_CHECK_LAUNCH("heads_fused");
+    fused_finish_kernel<<<(M + 255) / 256, 256, 0, s>>>(logp_part, p.part_stride, f.gsplit, M, row_const, t_rows,
+                                                        logp);
+    SCVAE_CHECK_LAUNCH("heads_fused_finish");
+    return 0;
+}
+
+}  // namespace scvae
+
+using namespace scvae;
+
+extern "C" int64_t scvae_heads_fused_workspace_floats(int M, int G) {
+    if (M <= 0 || G <= 0) return 0;
+    const FusedPlan f = fused_plan(M, G);
+    return (int64_t)f.gsplit * f.row_tiles * FM;
+}
+
+extern "C" int scvae_heads_fused_bwd(int kind, const void *d16, const void *w16, int64_t head_stride,
+                                     const void *t16, int64_t ldt, int t_rows, int M, int G,
+                                     const float *row_const, const float *go, float go_scalar, float scale,
+                                     void *da16, float *dd, int64_t lddd, int dd_cols, float *logp,
+                                     float *workspace, void *stream) {
+    SCVAE_CHECK_ARG(d16 && w16 && t16 && da16 && dd && logp && workspace, "heads_fused_bwd: NULL pointer");
+    SCVAE_CHECK_ARG(M > 0 && G > 0 && G % 4 == 0 && t_rows > 0, "heads_fused_bwd: bad shape (G must be a multiple of 4)");
+    SCVAE_CHECK_ARG(head_stride % 64 == 0 && head_stride >= G, "heads_fused_bwd: head_stride must be a multiple of 64");
+    SCVAE_CHECK_ARG(ldt % 8 == 0 && lddd % 4 == 0 && dd_cols <= FK, "heads_fused_bwd: bad leading dimensions");
+    SCVAE_CHECK_ARG(M == t_rows || t_rows % FM == 0,
+                    "heads_fused_bwd: targets must tile in multiples of 128 rows (t_rows=%d, M=%d)", t_rows, M);
+    SCVAE_CHECK_ARG(scale > 0.f, "heads_fused_bwd: scale must be positive");
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (kind) {
+#define CASE(KK)                                                                                              \
+    case KK:                                                                                                  \
+        return launch_fused<KK>(d16, w16, t16, ldt, t_rows, M, G, head_stride, go, go_scalar, scale, da16, dd, \
+                                lddd, dd_cols, workspace, row_const, logp, s);
+        CASE(SCVAE_LIK_POISSON)
+        CASE(SCVAE_LIK_NB)
+        CASE(SCVAE_LIK_ZIP)
+        CASE(SCVAE_LIK_ZINB)
+#undef CASE
+    }
+    set_error("heads_fused_bwd: unknown kind %d", kind);
+    return 1;
+}

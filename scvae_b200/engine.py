@@ -86,7 +86,7 @@ class VAEEngine:
     def __init__(self, feature_size, latent_size, hidden_sizes=(100,),
                  reconstruction_distribution="poisson", latent_distribution="gaussian",
                  minibatch_normalisation=True, kl_weight=1.0, device="cuda", seed=0,
-                 tensor_cores=True):
+                 tensor_cores=True, fused_heads=True):
         if reconstruction_distribution not in K.LIKELIHOOD_KINDS:
             raise ValueError("reconstruction distribution `{}` is not supported by the "
                              "B200 hot path".format(reconstruction_distribution))
@@ -104,8 +104,10 @@ class VAEEngine:
         self.kl_weight = float(kl_weight)
         self.device = torch.device(device)
         self.tensor_cores = bool(tensor_cores)
+        self.fused_heads = bool(fused_heads) and self.tensor_cores
         self.Gn = round4(self.G)
         self.Gp = aug(self.G)
+        self.Gh = (self.G + 63) & ~63      # head stride of the fp16 buffers of the fused heads
         self.world_size = 1
         self._all_reduce = None
         self._plans = {}
@@ -293,8 +295,33 @@ class VAEEngine:
         p.bn_scratch = zeros(scratch)
         p.workspace = None
         p.ws_bytes = 0
+        p.have_t16 = False
+        p.fused_ready = False
+        p.fused_done = False
         self._plans[key] = p
         return p
+
+    # ---- fused likelihood heads (heads_fused.cu) -------------------------------------------
+    def _fused_possible(self, M, B):
+        """n_in + 1 <= 128 hidden columns, genes a multiple of 4, targets tiling in 128 rows."""
+        return (self.fused_heads and self.head.n_in + 1 <= 128 and self.G % 4 == 0
+                and (M == B or B % 128 == 0))
+
+    def _plan_fused(self, p, M):
+        if p.fused_ready:
+            return
+        dev = self.device
+        p.D16 = torch.zeros(M, 128, dtype=torch.float16, device=dev)
+        p.W16 = torch.zeros(self.P * self.Gh, 128, dtype=torch.float16, device=dev)
+        p.dA16 = torch.zeros(M, self.P * self.Gh, dtype=torch.float16, device=dev)
+        p.fused_ws = torch.zeros(K.heads_fused_workspace_floats(M, self.G), dtype=torch.float32,
+                                 device=dev)
+        p.fused_ready = True
+
+    def _t16(self, p):
+        if getattr(p, "T16", None) is None:
+            p.T16 = torch.zeros(p.B, self.Gh, dtype=torch.int16, device=self.device)
+        return p.T16
 
     def _plan_backward(self, p):
         if p.bwd_ready:
@@ -336,6 +363,12 @@ class VAEEngine:
         """Dense (B, G) minibatch already on the device (tests / small data)."""
         p.X[:, :self.G].copy_(x)
         p.have_row_const = False
+        p.have_t16 = False
+        if self.fused_heads and (t is None or t is x):
+            # 16-bit targets are exact only for integer counts below 65536
+            if bool(((x == x.round()) & (x >= 0) & (x <= 65535)).all()):
+                K.f32_to_u16(p.X, self.G, self._t16(p))
+                p.have_t16 = True
         if t is not None and t is not x:
             if p.T is None:
                 p.T = torch.zeros(p.B, self.Gn, dtype=torch.float32, device=self.device)
@@ -344,10 +377,14 @@ class VAEEngine:
         else:
             p.use_T = False
 
-    def set_batch_csr(self, p, indptr, indices, values, rows=None):
-        """Gather + densify B rows of a device-resident CSR matrix (a1)."""
-        K.csr_densify(indptr, indices, values, rows, self.G, p.X, p.row_const)
+    def set_batch_csr(self, p, indptr, indices, values, rows=None, rebase=False, u16_ok=False):
+        """Gather + densify B rows of a device-resident CSR matrix (a1).  ``u16_ok``: the counts
+        are integers below 65536, so a 16-bit copy for the fused likelihood heads is exact."""
+        t16 = self._t16(p) if (u16_ok and self.fused_heads) else None
+        K.csr_densify(indptr, indices, values, rows, self.G, p.X, p.row_const, rebase=rebase,
+                      t16=t16)
         p.have_row_const = True
+        p.have_t16 = t16 is not None
         p.use_T = False
 
     # ------------------------------------------------------------------ forward ------------
@@ -385,10 +422,29 @@ class VAEEngine:
                 K.act_fwd(p.decY[j][:M], l.n_out, p.decH[j][:M], relu=True)
             d = p.decH[j]
         l = self.head
-        self._gemm(p, K.GEMM_NT, M, l.n_out, l.n_in + 1, d, l.w, p.A[:M])
         tgt = p.T if getattr(p, "use_T", False) else p.X
         rc = p.row_const if p.have_row_const else None
         weight = warm_up_weight * self.kl_weight
+        p.fused_done = False
+        if (fused_backward and p.have_t16 and not getattr(p, "use_T", False)
+                and self._fused_possible(M, B)):
+            # heads GEMM + likelihood + decoder gradient in one kernel; da stays fp16
+            assert R == 1 and not deterministic
+            self._plan_backward(p)
+            self._plan_fused(p, M)
+            K.f32_to_f16(d, l.in_p, p.D16)
+            for h in range(self.P):
+                K.f32_to_f16(l.w[h * self.Gn:(h + 1) * self.Gn], l.in_p,
+                             p.W16[h * self.Gh:h * self.Gh + self.Gn])
+            p.fused_scale = 2.0 ** round(math.log2(max(S * B, 16) / 16.0))
+            dd = p.d_decH[-1] if self.dec else p.dZ
+            K.heads_fused_bwd(self.kind, p.D16, p.W16, self.Gh, p.T16, M, self.G, p.dA16, dd,
+                              l.n_in, p.logp, p.fused_ws, row_const=rc, go=None,
+                              go_scalar=-1.0 / (S * B), scale=p.fused_scale)
+            K.vae_bound(p.logp, p.kl_row, R, S, B, weight, p.bound, None)
+            p.fused_done = True
+            return p
+        self._gemm(p, K.GEMM_NT, M, l.n_out, l.n_in + 1, d, l.w, p.A[:M])
         if fused_backward:
             assert R == 1 and not deterministic
             self._plan_backward(p)
@@ -431,9 +487,16 @@ class VAEEngine:
         l = self.head
         d_in = p.decH[-1] if self.dec else p.Z
         dd_in = p.d_decH[-1] if self.dec else p.dZ
-        # wgrad (bias gradient = the augmented ones column) and dgrad of the heads
-        self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, M, p.dA, d_in, l.dw)
-        self._gemm(p, K.GEMM_NN, M, l.n_in, l.n_out, p.dA, l.w, dd_in)
+        if p.fused_done:
+            # dd came out of the fused kernel; dW = da^T d from the fp16 da (per head)
+            for h in range(self.P):
+                K.gemm_f16(K.GEMM_TN, self.Gn, l.in_p, M,
+                           p.dA16[:, h * self.Gh:h * self.Gh + self.Gn], p.D16,
+                           l.dw[h * self.Gn:(h + 1) * self.Gn], alpha=1.0 / p.fused_scale)
+        else:
+            # wgrad (bias gradient = the augmented ones column) and dgrad of the heads
+            self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, M, p.dA, d_in, l.dw)
+            self._gemm(p, K.GEMM_NN, M, l.n_in, l.n_out, p.dA, l.w, dd_in)
         for j in range(len(self.dec) - 1, -1, -1):
             l = self.dec[j]
             if l.bn:

@@ -48,6 +48,8 @@ class GMVAEEngine(VAEEngine):
         self.free_nats = float(proportion_of_free_nats_for_y_kl_divergence)
         self.device = torch.device(device)
         self.tensor_cores = bool(tensor_cores)
+        self.fused_heads = False               # the fused heads kernel is wired into the VAE only
+        self.Gh = (self.G + 63) & ~63
         self.head_buffer_bytes = int(head_buffer_bytes)
         self.Gn, self.Gp = round4(self.G), aug(self.G)
         self.world_size, self._all_reduce, self._plans = 1, None, {}
@@ -291,6 +293,9 @@ class GMVAEEngine(VAEEngine):
         p.bn_scratch = zeros(scratch)
         p.workspace, p.ws_bytes = None, 0
         p.bwd_ready = False
+        p.have_t16 = False
+        p.fused_ready = False
+        p.fused_done = False
         self._plans[key] = p
         return p
 

@@ -26,6 +26,12 @@ def _as_csr_arrays(matrix):
             matrix.shape)
 
 
+def _counts_fit_u16(data):
+    """Integer counts below 65536: the 16-bit target copy of the fused heads is exact."""
+    return bool(data.size == 0 or (data.min() >= 0 and data.max() <= 65535
+                                   and numpy.array_equal(data, numpy.floor(data))))
+
+
 class ResidentCSR:
     """The whole (cells x genes) count matrix in HBM as CSR; steps gather rows by index."""
 
@@ -37,6 +43,7 @@ class ResidentCSR:
         self.indices = torch.from_numpy(indices).to(self.device)
         self.values = torch.from_numpy(data).to(self.device)
         self.nbytes = indptr.nbytes + indices.nbytes + data.nbytes
+        self.u16_ok = _counts_fit_u16(data)
 
     @property
     def number_of_examples(self):
@@ -61,6 +68,7 @@ class StreamedCSR:
         hi = numpy.minimum(numpy.arange(n) + max_rows, n)
         self.max_nnz = int((csum[hi] - csum[numpy.arange(n)]).max()) if n else 0
         self.max_rows = max_rows
+        self.u16_ok = _counts_fit_u16(data)
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.slots = []
         for _ in range(2):
@@ -69,6 +77,7 @@ class StreamedCSR:
                 "indices": torch.empty(max(self.max_nnz, 1), dtype=torch.int32, device=self.device),
                 "values": torch.empty(max(self.max_nnz, 1), dtype=torch.float32, device=self.device),
                 "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "bytes": 0,
+                "u16_ok": self.u16_ok,
             })
         for s in self.slots:
             s["free"].record()
@@ -106,12 +115,11 @@ class TrainLoop:
     def _body(self, src, lr, w):
         eng, p = self.engine, self.plan
         if isinstance(src, ResidentCSR):
-            eng.set_batch_csr(p, src.indptr, src.indices, src.values, self.rows)
+            eng.set_batch_csr(p, src.indptr, src.indices, src.values, self.rows,
+                              u16_ok=src.u16_ok)
         else:  # staging slot of a StreamedCSR
-            K.csr_densify(src["indptr"], src["indices"], src["values"], None, eng.G, p.X,
-                          p.row_const, rebase=True)
-            p.have_row_const = True
-            p.use_T = False
+            eng.set_batch_csr(p, src["indptr"], src["indices"], src["values"], None, rebase=True,
+                              u16_ok=src["u16_ok"])
         K.fill_normal(p.eps, self.seed, 0, eng.store.step)
         eng.train_step(p, self.R, self.S, lr, w)
 

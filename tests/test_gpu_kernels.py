@@ -348,6 +348,57 @@ def test_f32_to_f16():
     assert torch.all(dst[:, 101:] == 0)
 
 
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("M,G,H,tile", [(200, 200, 100, 1), (128, 64, 20, 1), (256, 1000, 127, 2)])
+def test_heads_fused_bwd(kind, M, G, H, tile):
+    """Fused heads GEMM + likelihood + dgrad vs fp64 on the same fp16-rounded operands."""
+    from scvae_b200 import kernels as K
+    rng = numpy.random.RandomState(7)
+    P = len(O.LIKELIHOODS[kind])
+    B = M // tile
+    Gh = (G + 63) & ~63
+    dev = _dev()
+    d = numpy.abs(rng.randn(M, H)).astype(numpy.float32)
+    d_aug = numpy.concatenate([d, numpy.ones((M, 1), numpy.float32)], axis=1)
+    w = (rng.randn(P, G, H + 1) * 0.3).astype(numpy.float32)
+    t = _counts(rng, B, G, 0.85)
+    go = (-(0.5 + rng.rand(M)) / M).astype(numpy.float32)
+    scale = 2.0 ** 10
+    d16 = torch.zeros(M, 128, dtype=torch.float16, device=dev)
+    d16[:, :H + 1] = torch.tensor(d_aug).half()
+    w16 = torch.zeros(P * Gh, 128, dtype=torch.float16, device=dev)
+    for h in range(P):
+        w16[h * Gh:h * Gh + G, :H + 1] = torch.tensor(w[h]).half()
+    t16 = torch.zeros(B, Gh, dtype=torch.int16, device=dev)
+    K.f32_to_u16(torch.tensor(t).to(dev), G, t16)
+    rc = torch.lgamma(1.0 + torch.tensor(t, dtype=torch.float64)).sum(dim=1).float().to(dev)
+    da16 = torch.zeros(M, P * Gh, dtype=torch.float16, device=dev)
+    dd = torch.full((M, 104 if H <= 100 else 128), 5.0, device=dev)
+    logp = torch.zeros(M, device=dev)
+    ws = torch.zeros(K.heads_fused_workspace_floats(M, G), device=dev)
+    K.heads_fused_bwd(K.LIKELIHOOD_KINDS[kind], d16, w16, Gh, t16, M, G, da16, dd, H, logp, ws,
+                      row_const=rc, go=torch.tensor(go).to(dev), scale=scale)
+    torch.cuda.synchronize()
+    # fp64 reference on the rounded operands
+    d64 = d16[:, :H + 1].cpu().double()
+    w64 = torch.stack([w16[h * Gh:h * Gh + G, :H + 1].cpu().double() for h in range(P)])
+    a64 = [(d64 @ w64[h].t()).requires_grad_(True) for h in range(P)]
+    t64 = torch.tensor(t, dtype=torch.float64).repeat(tile, 1)
+    lp = _oracle_logp(kind, t64, a64).sum(dim=1)
+    (lp * torch.tensor(go, dtype=torch.float64)).sum().backward()
+    ref = lp.detach().numpy()
+    assert numpy.abs(logp.cpu().numpy() - ref).max() <= 3e-5 * numpy.abs(ref).max() + 1e-4
+    dd_ref = sum(a64[h].grad @ w64[h] for h in range(P))[:, :H]
+    got_da = da16.cpu().double() / scale
+    for h in range(P):
+        g = a64[h].grad
+        err = (got_da[:, h * Gh:h * Gh + G] - g).abs().max().item()
+        assert err <= 2e-3 * g.abs().max().item(), (kind, h, err)
+        assert got_da[:, h * Gh + G:(h + 1) * Gh].abs().max().item() == 0
+    err = (dd[:, :H].cpu().double() - dd_ref).abs().max().item()
+    assert err <= 3e-3 * dd_ref.abs().max().item(), (kind, err, dd_ref.abs().max().item())
+
+
 def test_adam_clip_step():
     from scvae_b200 import kernels as K
     torch.manual_seed(2)
@@ -382,9 +433,12 @@ def test_csr_densify():
     Gp = (G + 4) & ~3
     x = torch.full((17, Gp), 5.0, device=dev)
     rc = torch.zeros(17, device=dev)
-    K.csr_densify(indptr, indices, values, rows, G, x, rc)
+    t16 = torch.full((17, (G + 7) & ~7), 7, dtype=torch.int16, device=dev)
+    K.csr_densify(indptr, indices, values, rows, G, x, rc, t16=t16)
     sel = dense[rows.cpu().numpy()]
     assert numpy.array_equal(x[:, :G].cpu().numpy(), sel)
+    assert numpy.array_equal(t16[:, :G].cpu().numpy().view(numpy.uint16), sel.astype(numpy.uint16))
+    assert torch.all(t16[:, G:] == 0)
     assert torch.all(x[:, G] == 1) and torch.all(x[:, G + 1:] == 0)
     exp = torch.lgamma(1.0 + torch.tensor(sel, dtype=torch.float64)).sum(1)
     assert torch.allclose(rc.cpu().double(), exp, rtol=1e-5, atol=1e-4)
