@@ -360,10 +360,10 @@ def test_heads_fused_bwd(kind, M, G, H, tile):
     dev = _dev()
     d = numpy.abs(rng.randn(M, H)).astype(numpy.float32)
     d_aug = numpy.concatenate([d, numpy.ones((M, 1), numpy.float32)], axis=1)
-    w = (rng.randn(P, G, H + 1) * 0.3).astype(numpy.float32)
+    w = (rng.randn(P, G, H + 1) * (1.0 / math.sqrt(H))).astype(numpy.float32)
     t = _counts(rng, B, G, 0.85)
     go = (-(0.5 + rng.rand(M)) / M).astype(numpy.float32)
-    scale = 2.0 ** 10
+    scale = 2.0 ** round(math.log2(M / 16.0))   # go * scale ~ 2^-4: fp16 range for the gradients
     d16 = torch.zeros(M, 128, dtype=torch.float16, device=dev)
     d16[:, :H + 1] = torch.tensor(d_aug).half()
     w16 = torch.zeros(P * Gh, 128, dtype=torch.float16, device=dev)
