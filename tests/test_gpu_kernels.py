@@ -394,7 +394,8 @@ def test_heads_fused_bwd(kind, M, G, H, tile):
         g = a64[h].grad
         err = (got_da[:, h * Gh:h * Gh + G] - g).abs().max().item()
         assert err <= 2e-3 * g.abs().max().item(), (kind, h, err)
-        assert got_da[:, h * Gh + G:(h + 1) * Gh].abs().max().item() == 0
+        if Gh > G:
+            assert got_da[:, h * Gh + G:(h + 1) * Gh].abs().max().item() == 0
     err = (dd[:, :H].cpu().double() - dd_ref).abs().max().item()
     assert err <= 3e-3 * dd_ref.abs().max().item(), (kind, err, dd_ref.abs().max().item())
 
