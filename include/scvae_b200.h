@@ -60,11 +60,14 @@ long long   scvae_launch_count(void);
  * every count log-likelihood.  rebase != 0: `indptr` holds absolute offsets of
  * a row slab whose nonzeros start at indices[0]/values[0] (offsets are taken relative to
  * indptr[0]) -- the streaming path ships one such slab per step from pinned host memory.
- * t16 (nullable, (B, ldt16) uint16, ldt16 % 8 == 0): 16-bit copy of the counts (clamped to
- * 65535) for the fused likelihood heads. */
+ * Further optional outputs (x, t16, x16 are each nullable, at least one must be given):
+ * t16 ((B, ldt16) uint16, ldt16 % 8 == 0): counts clamped to 65535, targets of the fused
+ * likelihood heads; x16 ((B, ldx16) fp16 augmented, ldx16 % 8 == 0, ldx16 > G): operand of the
+ * fp16 tensor-core first layer.  Every output byte is written exactly once. */
 int scvae_csr_densify(const int64_t *indptr, const int32_t *indices, const float *values,
                       const int64_t *rows, int B, int G, float *x, int64_t ldx,
-                      float *row_const, int rebase, void *t16, int64_t ldt16, void *stream);
+                      float *row_const, int rebase, void *t16, int64_t ldt16, void *x16,
+                      int64_t ldx16, void *stream);
 /* Dense fp32 counts -> uint16 (clamped), zero padded to ldt16 columns. */
 int scvae_f32_to_u16(const float *x, int64_t ldx, int64_t rows, int G, void *t16, int64_t ldt16,
                      void *stream);
@@ -164,12 +167,13 @@ int scvae_likelihood_bwd(int kind, const float *t, int64_t ldt, int t_rows, cons
  *   d16  (M, 128) fp16: decoder output, augmented, zero padded to 128 columns (n_in + 1 <= 128)
  *   w16  (P*head_stride, 128) fp16: head weights, head h at rows [h*head_stride, +G), zero
  *        padded; head_stride % 64 == 0
- *   t16  (t_rows, ldt) uint16 targets (row m uses t row m % t_rows; t_rows % 128 == 0 or == M)
+ *   t16  (t_rows, ldt) targets, uint16 (t_is_half == 0) or fp16 (t_is_half != 0, exact for
+ *        counts <= 2048); row m uses t row m % t_rows; t_rows % 128 == 0 or == M
  *   da16 (M, P*head_stride) fp16 out; dd (M, lddd) fp32 out (first dd_cols columns);
  *   logp [M] out; workspace: scvae_heads_fused_workspace_floats(M, G) floats. */
 int64_t scvae_heads_fused_workspace_floats(int M, int G);
 int scvae_heads_fused_bwd(int kind, const void *d16, const void *w16, int64_t head_stride,
-                          const void *t16, int64_t ldt, int t_rows, int M, int G,
+                          const void *t16, int64_t ldt, int t_is_half, int t_rows, int M, int G,
                           const float *row_const, const float *go, float go_scalar, float scale,
                           void *da16, float *dd, int64_t lddd, int dd_cols, float *logp,
                           float *workspace, void *stream);

@@ -1,49 +1,99 @@
 // a1: minibatch gather.  Replaces the host-side x_train[idx].toarray() (VAE:994-998,
 // GMVAE:1078-1082): the CSR count matrix lives in HBM and each step densifies B rows into the
 // augmented (B, ldx) fp32 layout the GEMMs and the likelihood kernels read.  HBM-write-bound.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace scvae {
 
+constexpr int kChunk = 2048;   // genes staged in shared memory per pass
+
+// One CTA per output row.  The row is assembled chunk by chunk in shared memory (zero, scatter
+// the row's non-zeros that fall into the chunk, write out), so every output byte is written
+// exactly once with coalesced 128-bit stores -- to up to three destinations:
+//   x   fp32 augmented (column G = 1)          -> exact-fp32 / evaluation paths
+//   x16 fp16 augmented (column G = 1)          -> fp16 tensor-core first layer
+//   t16 uint16 (clamped to 65535), zero padded -> targets of the fused likelihood heads
 __global__ void __launch_bounds__(256)
 csr_densify_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                    const float *__restrict__ values, const int64_t *__restrict__ rows, int G,
                    float *__restrict__ x, int64_t ldx, float *__restrict__ row_const, int rebase,
-                   uint16_t *__restrict__ t16, int64_t ldt16) {
+                   uint16_t *__restrict__ t16, int64_t ldt16, __half *__restrict__ x16, int64_t ldx16) {
     __shared__ float red[32];
+    __shared__ __align__(16) float buf[kChunk];
     const int b = blockIdx.x;
     const int64_t row = rows ? rows[b] : b;
-    float *xr = x + (int64_t)b * ldx;
-    // zero fill (+ the augmented ones column)
-    if ((ldx & 3) == 0 && aligned16(x)) {
-        float4 *x4 = reinterpret_cast<float4 *>(xr);
-        const int n4 = (int)(ldx >> 2);
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int c = i << 2;
-            if (G >= c && G < c + 4) (&z.x)[G - c] = 1.f;
-            x4[i] = z;
-        }
-    } else {
-        for (int i = threadIdx.x; i < ldx; i += blockDim.x) xr[i] = (i == G) ? 1.f : 0.f;
-    }
-    if (t16) {  // 16-bit copy of the counts for the fused likelihood heads (zero fill)
-        uint4 *t4 = reinterpret_cast<uint4 *>(t16 + (int64_t)b * ldt16);
-        const int n8 = (int)(ldt16 >> 3);
-        for (int i = threadIdx.x; i < n8; i += blockDim.x) t4[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    __syncthreads();
     const int64_t base = rebase ? indptr[0] : 0;
     const int64_t s = indptr[row] - base, e = indptr[row + 1] - base;
+    int64_t width = 0;
+    if (x) width = ldx;
+    if (t16 && ldt16 > width) width = ldt16;
+    if (x16 && ldx16 > width) width = ldx16;
     float acc = 0.f;
-    for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) {
-        const float v = values[i];
-        const int c = indices[i];
-        if (c >= 0 && c < G) {
-            xr[c] = v;
-            if (t16) t16[(int64_t)b * ldt16 + c] = (uint16_t)fminf(fmaxf(v, 0.f), 65535.f);
+    for (int c0 = 0; c0 < width; c0 += kChunk) {
+        for (int i = threadIdx.x; i < kChunk; i += blockDim.x) buf[i] = 0.f;
+        __syncthreads();
+        for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) {
+            const int c = indices[i];
+            if (c >= c0 && c < c0 + kChunk && c < G) {
+                const float v = values[i];
+                buf[c - c0] = v;
+                if (v > 0.f) acc += lgammaf(1.f + v);
+            }
         }
-        if (v > 0.f) acc += lgammaf(1.f + v);
+        if (G >= c0 && G < c0 + kChunk && threadIdx.x == 0) buf[G - c0] = 1.f;   // augmented ones column
+        __syncthreads();
+        // write-out, 8 columns per thread per trip
+        for (int i = threadIdx.x * 8; i < kChunk; i += blockDim.x * 8) {
+            const int c = c0 + i;
+            if (c >= width) break;
+            const float4 lo = *reinterpret_cast<const float4 *>(buf + i);
+            const float4 hi = *reinterpret_cast<const float4 *>(buf + i + 4);
+            const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            if (x) {
+                float *xr = x + (int64_t)b * ldx + c;
+                if (c + 8 <= ldx && (ldx & 3) == 0) {
+                    *reinterpret_cast<float4 *>(xr) = lo;
+                    *reinterpret_cast<float4 *>(xr + 4) = hi;
+                } else {
+                    for (int j = 0; j < 8 && c + j < ldx; ++j) xr[j] = v[j];
+                }
+            }
+            if (x16) {
+                __half *hr = x16 + (int64_t)b * ldx16 + c;
+                if (c + 8 <= ldx16) {
+                    uint4 pk;
+                    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+                    __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+                    pk.x = *reinterpret_cast<uint32_t *>(&h0);
+                    pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                    pk.z = *reinterpret_cast<uint32_t *>(&h2);
+                    pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                    *reinterpret_cast<uint4 *>(hr) = pk;
+                } else {
+                    for (int j = 0; j < 8 && c + j < ldx16; ++j) hr[j] = __float2half_rn(v[j]);
+                }
+            }
+            if (t16) {
+                uint16_t *tr = t16 + (int64_t)b * ldt16 + c;
+                uint16_t u[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    u[j] = (c + j < G) ? (uint16_t)fminf(fmaxf(v[j], 0.f), 65535.f) : (uint16_t)0;
+                if (c + 8 <= ldt16) {
+                    uint4 pk;
+                    pk.x = u[0] | ((uint32_t)u[1] << 16);
+                    pk.y = u[2] | ((uint32_t)u[3] << 16);
+                    pk.z = u[4] | ((uint32_t)u[5] << 16);
+                    pk.w = u[6] | ((uint32_t)u[7] << 16);
+                    *reinterpret_cast<uint4 *>(tr) = pk;
+                } else {
+                    for (int j = 0; j < 8 && c + j < ldt16; ++j) tr[j] = u[j];
+                }
+            }
+        }
+        __syncthreads();
     }
     if (row_const) {
         const float tot = block_sum(acc, red);
@@ -63,15 +113,18 @@ __global__ void f32_to_u16_kernel(const float *__restrict__ x, int64_t ldx, int 
 
 extern "C" int scvae_csr_densify(const int64_t *indptr, const int32_t *indices, const float *values,
                                  const int64_t *rows, int B, int G, float *x, int64_t ldx,
-                                 float *row_const, int rebase, void *t16, int64_t ldt16, void *stream) {
+                                 float *row_const, int rebase, void *t16, int64_t ldt16, void *x16,
+                                 int64_t ldx16, void *stream) {
     using namespace scvae;
-    SCVAE_CHECK_ARG(indptr && indices && values && x, "csr_densify: NULL pointer");
-    SCVAE_CHECK_ARG(B >= 0 && G > 0 && ldx >= G, "csr_densify: bad shape (B=%d G=%d ldx=%lld)", B, G,
+    SCVAE_CHECK_ARG(indptr && indices && values && (x || x16 || t16), "csr_densify: NULL pointer");
+    SCVAE_CHECK_ARG(B >= 0 && G > 0 && (!x || ldx >= G), "csr_densify: bad shape (B=%d G=%d ldx=%lld)", B, G,
                     (long long)ldx);
+    SCVAE_CHECK_ARG(!x || (ldx % 4 == 0 && aligned16(x)) || true, "csr_densify: x layout");
     SCVAE_CHECK_ARG(!t16 || (ldt16 % 8 == 0 && ldt16 >= G && aligned16(t16)), "csr_densify: bad t16 layout");
+    SCVAE_CHECK_ARG(!x16 || (ldx16 % 8 == 0 && ldx16 > G && aligned16(x16)), "csr_densify: bad x16 layout");
     if (B == 0) return 0;
-    csr_densify_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(indptr, indices, values, rows, G, x, ldx,
-                                                            row_const, rebase, (uint16_t *)t16, ldt16);
+    csr_densify_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(indptr, indices, values, rows, G, x, ldx, row_const,
+                                                            rebase, (uint16_t *)t16, ldt16, (__half *)x16, ldx16);
     SCVAE_CHECK_LAUNCH("csr_densify");
     return 0;
 }

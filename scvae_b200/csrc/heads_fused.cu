@@ -65,6 +65,7 @@ struct FusedParams {
     const float *go;          // nullable per-row upstream gradient
     float go_scalar, scale, inv_scale;
     int has_const;            // sum_g lgamma(1+t) is subtracted by the finish kernel
+    int t_is_half;            // targets are fp16 (exact for counts <= 2048) instead of uint16
     float *logp_part;
 };
 
@@ -82,7 +83,7 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
     uint8_t *sT = sA + P * FABytes;             // [2 stages][128 rows][128 B]
     uint64_t *bars = (uint64_t *)(sT + 2 * FTBytes);
     enum { D_FULL = 0, W_FULL = 1, W_EMPTY = 3, T_FULL = 5, T_EMPTY = 7, S_FULL = 9, S_EMPTY = 11,
-           A_FULL = 13, A_EMPTY = 14, DD_FULL = 15, NBARS = 16 };
+           A_FULL = 13, A_EMPTY = 14, DD_FULL = 15, A_STORED = 16, NBARS = 17 };
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     uint32_t *tmem_slot = (uint32_t *)(bars + NBARS);
@@ -112,8 +113,9 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
             mbar_init(bar(S_FULL + i), 1);
             mbar_init(bar(S_EMPTY + i), 8);
         }
-        mbar_init(bar(A_FULL), 1);
+        mbar_init(bar(A_FULL), 8);
         mbar_init(bar(A_EMPTY), 1);
+        mbar_init(bar(A_STORED), 1);
         mbar_init(bar(DD_FULL), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -207,6 +209,21 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
             mma2(ntile - 1);
             tc_commit(bar(DD_FULL));
         }
+    } else if (warp == 3) {
+        // ===== da store warp: smem da tile -> HBM (fp16), releases the tile for the next epilogue
+        if (lane == 0) {
+            for (int n = 0; n < ntile; ++n) {
+                const int g0 = (tile0 + n) * FG;
+                mbar_wait(bar(A_FULL), (uint32_t)(n & 1));
+#pragma unroll
+                for (int h = 0; h < P; ++h)
+                    tma_store_2d(&tmDA, (int)(h * p.head_stride) + g0, row0, smem_u32(sA + h * FABytes));
+                tma_commit();
+                tma_wait_read<0>();
+                mbar_arrive(bar(A_STORED));
+            }
+            tma_wait_all();
+        }
     } else if (warp >= 4) {
         // ===== epilogue =====
         const int e = warp - 4;
@@ -226,9 +243,10 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
             mbar_wait(bar(T_FULL + st), ph);
             tc_fence_after();
             // da(n-1) has been consumed by MMA2 and read by its TMA store before we overwrite it
-            if (n > 0) mbar_wait(bar(A_EMPTY), (uint32_t)((n - 1) & 1));
-            if (issuer) tma_wait_read<0>();
-            bar_sync_n(1, 256);
+            if (n > 0) {
+                mbar_wait(bar(A_EMPTY), (uint32_t)((n - 1) & 1));
+                mbar_wait(bar(A_STORED), (uint32_t)((n - 1) & 1));
+            }
             const uint8_t *trow = sT + st * FTBytes + row * 128;
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
@@ -248,7 +266,8 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint32_t w = tw[grp * 2 + (j >> 1)];
-                        x[j] = (float)((j & 1) ? (w >> 16) : (w & 0xffffu));
+                        const uint16_t bits = (uint16_t)((j & 1) ? (w >> 16) : (w & 0xffffu));
+                        x[j] = p.t_is_half ? __half2float(__ushort_as_half(bits)) : (float)bits;
 #pragma unroll
                         for (int h = 0; h < P; ++h) av[h][j] = __uint_as_float(sv[h][grp * 4 + j]);
                     }
@@ -280,14 +299,8 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
                 mbar_arrive(bar(T_EMPTY + st));
             }
             fence_async_smem();
-            bar_sync_n(1, 256);
-            if (issuer) {
-#pragma unroll
-                for (int h = 0; h < P; ++h)
-                    tma_store_2d(&tmDA, (int)(h * p.head_stride) + g0, row0, smem_u32(sA + h * FABytes));
-                tma_commit();
-                mbar_arrive(bar(A_FULL));
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(A_FULL));
         }
         // ---- log p partial of this gene range: combine the two halves, fixed order ----
         s_part[half * 128 + row] = acc;
@@ -297,8 +310,6 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
         // ---- dd partial: TMEM -> staging smem (the t stages) -> TMA reduce-add ----
         mbar_wait(bar(DD_FULL), 0);
         tc_fence_after();
-        if (issuer) tma_wait_read<0>();
-        bar_sync_n(1, 256);
         uint8_t *stage = sT + half * FTBytes;       // 128 rows x 32 fp32 columns
         const bool half_issuer = (lane == 0 && q == 0);
 #pragma unroll 1
@@ -327,7 +338,7 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
                 tma_commit();
             }
         }
-        if (half_issuer || issuer) tma_wait_all();
+        if (half_issuer) tma_wait_all();
     }
 
     tc_fence_before();
@@ -379,7 +390,8 @@ static FusedPlan fused_plan(int M, int G) {
 }
 
 template <int KIND>
-static int launch_fused(const void *d16, const void *w16, const void *t16, int64_t ldt, int t_rows, int M, int G,
+static int launch_fused(const void *d16, const void *w16, const void *t16, int64_t ldt, int t_is_half, int t_rows,
+                        int M, int G,
                         int64_t head_stride, const float *go, float go_scalar, float scale, void *da16,
                         float *dd, int64_t lddd, int dd_cols, float *logp_part, const float *row_const,
                         float *logp, cudaStream_t s) {
@@ -401,6 +413,7 @@ static int launch_fused(const void *d16, const void *w16, const void *t16, int64
     p.go = go; p.go_scalar = go_scalar; p.scale = scale; p.inv_scale = 1.f / scale;
     p.logp_part = logp_part;
     p.has_const = row_const != nullptr;
+    p.t_is_half = t_is_half;
     constexpr int smem = fused_smem_bytes(P);
     static bool attr_set = false;
     if (!attr_set) {
@@ -430,7 +443,7 @@ extern "C" int64_t scvae_heads_fused_workspace_floats(int M, int G) {
 }
 
 extern "C" int scvae_heads_fused_bwd(int kind, const void *d16, const void *w16, int64_t head_stride,
-                                     const void *t16, int64_t ldt, int t_rows, int M, int G,
+                                     const void *t16, int64_t ldt, int t_is_half, int t_rows, int M, int G,
                                      const float *row_const, const float *go, float go_scalar, float scale,
                                      void *da16, float *dd, int64_t lddd, int dd_cols, float *logp,
                                      float *workspace, void *stream) {
@@ -445,7 +458,7 @@ extern "C" int scvae_heads_fused_bwd(int kind, const void *d16, const void *w16,
     switch (kind) {
 #define CASE(KK)                                                                                              \
     case KK:                                                                                                  \
-        return launch_fused<KK>(d16, w16, t16, ldt, t_rows, M, G, head_stride, go, go_scalar, scale, da16, dd, \
+        return launch_fused<KK>(d16, w16, t16, ldt, t_is_half, t_rows, M, G, head_stride, go, go_scalar, scale, da16, dd, \
                                 lddd, dd_cols, workspace, row_const, logp, s);
         CASE(SCVAE_LIK_POISSON)
         CASE(SCVAE_LIK_NB)

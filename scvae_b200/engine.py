@@ -296,6 +296,8 @@ class VAEEngine:
         p.workspace = None
         p.ws_bytes = 0
         p.have_t16 = False
+        p.have_x = True
+        p.t16_is_x16 = False
         p.fused_ready = False
         p.fused_done = False
         self._plans[key] = p
@@ -322,6 +324,13 @@ class VAEEngine:
         if getattr(p, "T16", None) is None:
             p.T16 = torch.zeros(p.B, self.Gh, dtype=torch.int16, device=self.device)
         return p.T16
+
+    def _x16(self, p):
+        """fp16 augmented copy of the minibatch: operand of the fp16 first layer and, when all
+        counts are <= 2048 (exact in fp16), also the target matrix of the fused heads."""
+        if getattr(p, "X16", None) is None:
+            p.X16 = torch.zeros(p.B, (self.G + 8) & ~7, dtype=torch.float16, device=self.device)
+        return p.X16
 
     def _plan_backward(self, p):
         if p.bwd_ready:
@@ -358,16 +367,30 @@ class VAEEngine:
                 ws = p.workspace
         K.gemm(layout, M, N, Kd, A, Bm, C, accumulate=accumulate, tensor_cores=tc, workspace=ws)
 
+    def _gemm16(self, p, layout, M, N, Kd, A, Bm, C, accumulate=False, alpha=1.0):
+        need = K.gemm_f16_workspace_bytes(layout, M, N, Kd)
+        ws = None
+        if need > 0:
+            if p.ws_bytes < need:
+                p.workspace = torch.empty(need // 4, dtype=torch.float32, device=self.device)
+                p.ws_bytes = need
+            ws = p.workspace
+        K.gemm_f16(layout, M, N, Kd, A, Bm, C, accumulate=accumulate, alpha=alpha, workspace=ws)
+
     # ------------------------------------------------------------------ inputs -------------
     def set_batch_dense(self, p, x, t=None):
         """Dense (B, G) minibatch already on the device (tests / small data)."""
         p.X[:, :self.G].copy_(x)
         p.have_row_const = False
         p.have_t16 = False
+        p.have_x = True
         if self.fused_heads and (t is None or t is x):
-            # 16-bit targets are exact only for integer counts below 65536
+            # 16-bit copies are exact only for integer counts below 65536 (fp16: <= 2048)
             if bool(((x == x.round()) & (x >= 0) & (x <= 65535)).all()):
-                K.f32_to_u16(p.X, self.G, self._t16(p))
+                p.t16_is_x16 = bool((x <= 2048).all())
+                K.f32_to_f16(p.X, self.G + 1, self._x16(p))
+                if not p.t16_is_x16:
+                    K.f32_to_u16(p.X, self.G, self._t16(p))
                 p.have_t16 = True
         if t is not None and t is not x:
             if p.T is None:
@@ -377,14 +400,24 @@ class VAEEngine:
         else:
             p.use_T = False
 
-    def set_batch_csr(self, p, indptr, indices, values, rows=None, rebase=False, u16_ok=False):
-        """Gather + densify B rows of a device-resident CSR matrix (a1).  ``u16_ok``: the counts
-        are integers below 65536, so a 16-bit copy for the fused likelihood heads is exact."""
-        t16 = self._t16(p) if (u16_ok and self.fused_heads) else None
-        K.csr_densify(indptr, indices, values, rows, self.G, p.X, p.row_const, rebase=rebase,
-                      t16=t16)
+    def set_batch_csr(self, p, indptr, indices, values, rows=None, rebase=False, u16_ok=False,
+                      f16_exact=False, train16=False):
+        """Gather + densify B rows of a device-resident CSR matrix (a1).
+        ``u16_ok``: counts are integers < 65536; ``f16_exact``: all counts <= 2048.
+        ``train16``: the caller will run the fused 16-bit training step, so only the 16-bit
+        copies are produced (fp16 input + uint16 targets when fp16 is not exact) and the fp32
+        matrix is not written at all."""
+        use16 = bool(train16 and u16_ok and self.fused_heads and self._fused_possible(p.M, p.B)
+                     and p.RS == 1)
+        if use16:
+            p.t16_is_x16 = bool(f16_exact)
+            K.csr_densify(indptr, indices, values, rows, self.G, None, p.row_const, rebase=rebase,
+                          t16=None if f16_exact else self._t16(p), x16=self._x16(p))
+        else:
+            K.csr_densify(indptr, indices, values, rows, self.G, p.X, p.row_const, rebase=rebase)
+        p.have_x = not use16
         p.have_row_const = True
-        p.have_t16 = t16 is not None
+        p.have_t16 = use16
         p.use_T = False
 
     # ------------------------------------------------------------------ forward ------------
@@ -397,9 +430,22 @@ class VAEEngine:
         M = RS * B
         if update_moving is None:
             update_moving = is_training
+        use16 = bool(fused_backward and p.have_t16 and not getattr(p, "use_T", False)
+                     and self._fused_possible(M, B))
+        if not use16 and not getattr(p, "have_x", True):
+            raise RuntimeError("this minibatch was densified for the fused 16-bit training step "
+                               "only; call set_batch_csr without train16 for other passes")
         h, h_cols = p.X, self.G
         for i, l in enumerate(self.enc):
-            self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, h, l.w, p.encY[i])
+            if i == 0 and use16:
+                # (cells x genes) operand in fp16: half the HBM traffic of the tf32 path
+                if getattr(p, "W1_16", None) is None:
+                    p.W1_16 = torch.zeros(l.n_out, p.X16.shape[1], dtype=torch.float16,
+                                          device=self.device)
+                K.f32_to_f16(l.w, l.n_in + 1, p.W1_16)
+                self._gemm16(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, p.X16, p.W1_16, p.encY[i])
+            else:
+                self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, h, l.w, p.encY[i])
             if l.bn:
                 K.bn_act_fwd(p.encY[i], l.n_out, l.beta, l.moving_mean, l.moving_var, p.encH[i],
                              p.enc_mean[i], p.enc_rstd[i], p.bn_scratch, training=is_training,
@@ -426,8 +472,7 @@ class VAEEngine:
         rc = p.row_const if p.have_row_const else None
         weight = warm_up_weight * self.kl_weight
         p.fused_done = False
-        if (fused_backward and p.have_t16 and not getattr(p, "use_T", False)
-                and self._fused_possible(M, B)):
+        if use16:
             # heads GEMM + likelihood + decoder gradient in one kernel; da stays fp16
             assert R == 1 and not deterministic
             self._plan_backward(p)
@@ -438,7 +483,8 @@ class VAEEngine:
                              p.W16[h * self.Gh:h * self.Gh + self.Gn])
             p.fused_scale = 2.0 ** round(math.log2(max(S * B, 16) / 16.0))
             dd = p.d_decH[-1] if self.dec else p.dZ
-            K.heads_fused_bwd(self.kind, p.D16, p.W16, self.Gh, p.T16, M, self.G, p.dA16, dd,
+            t16 = p.X16 if p.t16_is_x16 else p.T16
+            K.heads_fused_bwd(self.kind, p.D16, p.W16, self.Gh, t16, M, self.G, p.dA16, dd,
                               l.n_in, p.logp, p.fused_ws, row_const=rc, go=None,
                               go_scalar=-1.0 / (S * B), scale=p.fused_scale)
             K.vae_bound(p.logp, p.kl_row, R, S, B, weight, p.bound, None)
@@ -524,7 +570,16 @@ class VAEEngine:
             else:
                 K.act_bwd(p.d_encH[i], p.encH[i], l.n_out, p.d_encY[i], relu=True)
             h_in = p.encH[i - 1] if i > 0 else p.X
-            self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.d_encY[i], h_in, l.dw)
+            if i == 0 and p.fused_done:
+                # dW1 = dY1^T X with the fp16 minibatch (dY1 scaled into fp16 range)
+                if getattr(p, "dY1_16", None) is None:
+                    p.dY1_16 = torch.zeros(B, (l.n_out + 7) & ~7, dtype=torch.float16,
+                                           device=self.device)
+                K.f32_to_f16(p.d_encY[0], l.n_out, p.dY1_16, scale=p.fused_scale)
+                self._gemm16(p, K.GEMM_TN, l.n_out, l.in_p, B, p.dY1_16, p.X16, l.dw,
+                             alpha=1.0 / p.fused_scale)
+            else:
+                self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.d_encY[i], h_in, l.dw)
             if i > 0:
                 self._gemm(p, K.GEMM_NN, B, l.n_in, l.n_out, p.d_encY[i], l.w, p.d_encH[i - 1])
 

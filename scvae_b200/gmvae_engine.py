@@ -294,6 +294,8 @@ class GMVAEEngine(VAEEngine):
         p.workspace, p.ws_bytes = None, 0
         p.bwd_ready = False
         p.have_t16 = False
+        p.have_x = True
+        p.t16_is_x16 = False
         p.fused_ready = False
         p.fused_done = False
         self._plans[key] = p

@@ -44,6 +44,7 @@ class ResidentCSR:
         self.values = torch.from_numpy(data).to(self.device)
         self.nbytes = indptr.nbytes + indices.nbytes + data.nbytes
         self.u16_ok = _counts_fit_u16(data)
+        self.f16_exact = bool(self.u16_ok and (data.size == 0 or data.max() <= 2048))
 
     @property
     def number_of_examples(self):
@@ -69,6 +70,7 @@ class StreamedCSR:
         self.max_nnz = int((csum[hi] - csum[numpy.arange(n)]).max()) if n else 0
         self.max_rows = max_rows
         self.u16_ok = _counts_fit_u16(data)
+        self.f16_exact = bool(self.u16_ok and (data.size == 0 or data.max() <= 2048))
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.slots = []
         for _ in range(2):
@@ -77,7 +79,7 @@ class StreamedCSR:
                 "indices": torch.empty(max(self.max_nnz, 1), dtype=torch.int32, device=self.device),
                 "values": torch.empty(max(self.max_nnz, 1), dtype=torch.float32, device=self.device),
                 "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "bytes": 0,
-                "u16_ok": self.u16_ok,
+                "u16_ok": self.u16_ok, "f16_exact": self.f16_exact,
             })
         for s in self.slots:
             s["free"].record()
@@ -116,10 +118,11 @@ class TrainLoop:
         eng, p = self.engine, self.plan
         if isinstance(src, ResidentCSR):
             eng.set_batch_csr(p, src.indptr, src.indices, src.values, self.rows,
-                              u16_ok=src.u16_ok)
+                              u16_ok=src.u16_ok, f16_exact=src.f16_exact, train16=self.R == 1)
         else:  # staging slot of a StreamedCSR
             eng.set_batch_csr(p, src["indptr"], src["indices"], src["values"], None, rebase=True,
-                              u16_ok=src["u16_ok"])
+                              u16_ok=src["u16_ok"], f16_exact=src["f16_exact"],
+                              train16=self.R == 1)
         K.fill_normal(p.eps, self.seed, 0, eng.store.step)
         eng.train_step(p, self.R, self.S, lr, w)
 

@@ -49,12 +49,15 @@ def _ld(t):
     return t.stride(0)
 
 
-def csr_densify(indptr, indices, values, rows, G, x, row_const=None, rebase=False, t16=None):
-    B = x.shape[0]
+def csr_densify(indptr, indices, values, rows, G, x, row_const=None, rebase=False, t16=None,
+                x16=None):
+    """CSR rows -> dense minibatch; any of x (fp32), t16 (uint16), x16 (fp16) may be None."""
+    B = next(t for t in (x, t16, x16) if t is not None).shape[0]
     lib = _lib.load()
     _lib.check(lib.scvae_csr_densify(_p(indptr), _p(indices), _p(values), _p(rows), B, G, _p(x),
-                                     _ld(x), _p(row_const), int(rebase), _p(t16),
-                                     _ld(t16) if t16 is not None else 0, _stream()),
+                                     _ld(x) if x is not None else 0, _p(row_const), int(rebase),
+                                     _p(t16), _ld(t16) if t16 is not None else 0, _p(x16),
+                                     _ld(x16) if x16 is not None else 0, _stream()),
                "csr_densify")
 
 
@@ -70,10 +73,11 @@ def heads_fused_workspace_floats(M, G):
 
 def heads_fused_bwd(kind, d16, w16, head_stride, t16, M, G, da16, dd, dd_cols, logp, workspace,
                     row_const=None, go=None, go_scalar=1.0, scale=1.0):
-    """Fused heads GEMM + likelihood forward/backward + decoder-gradient GEMM."""
+    """Fused heads GEMM + likelihood forward/backward + decoder-gradient GEMM.  ``t16`` is a
+    uint16 (torch.int16 storage) or a torch.float16 target matrix."""
     lib = _lib.load()
     _lib.check(lib.scvae_heads_fused_bwd(kind, _p(d16), _p(w16), head_stride, _p(t16), _ld(t16),
-                                         t16.shape[0], M, G, _p(row_const), _p(go),
+                                         int(t16.dtype == torch.float16), t16.shape[0], M, G, _p(row_const), _p(go),
                                          float(go_scalar), float(scale), _p(da16), _p(dd), _ld(dd),
                                          dd_cols, _p(logp), _p(workspace), _stream()),
                "heads_fused_bwd")
