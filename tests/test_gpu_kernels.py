@@ -437,13 +437,13 @@ def test_csr_densify():
     t16 = torch.full((17, (G + 7) & ~7), 7, dtype=torch.int16, device=dev)
     x16 = torch.full((17, (G + 8) & ~7), 3.0, dtype=torch.float16, device=dev)
     K.csr_densify(indptr, indices, values, rows, G, x, rc, t16=t16, x16=x16)
+    sel = dense[rows.cpu().numpy()]
+    assert numpy.array_equal(x[:, :G].cpu().numpy(), sel)
     assert numpy.array_equal(x16[:, :G].float().cpu().numpy(), sel)
     assert torch.all(x16[:, G] == 1) and torch.all(x16[:, G + 1:] == 0)
     x_only16 = torch.zeros_like(x16)
     K.csr_densify(indptr, indices, values, rows, G, None, None, x16=x_only16)
     assert torch.equal(x_only16, x16)
-    sel = dense[rows.cpu().numpy()]
-    assert numpy.array_equal(x[:, :G].cpu().numpy(), sel)
     assert numpy.array_equal(t16[:, :G].cpu().numpy().view(numpy.uint16), sel.astype(numpy.uint16))
     assert torch.all(t16[:, G:] == 0)
     assert torch.all(x[:, G] == 1) and torch.all(x[:, G + 1:] == 0)
