@@ -7,7 +7,7 @@
 
 namespace scvae {
 
-constexpr int kChunk = 2048;   // genes staged in shared memory per pass
+constexpr int kChunk = 8192;   // genes staged in shared memory per pass (32 KB)
 
 // One CTA per output row.  The row is assembled chunk by chunk in shared memory (zero, scatter
 // the row's non-zeros that fall into the chunk, write out), so every output byte is written
@@ -32,7 +32,8 @@ csr_densify_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict
     if (x16 && ldx16 > width) width = ldx16;
     float acc = 0.f;
     for (int c0 = 0; c0 < width; c0 += kChunk) {
-        for (int i = threadIdx.x; i < kChunk; i += blockDim.x) buf[i] = 0.f;
+        for (int i = threadIdx.x * 4; i < kChunk; i += blockDim.x * 4)
+            *reinterpret_cast<float4 *>(buf + i) = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
         for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) {
             const int c = indices[i];

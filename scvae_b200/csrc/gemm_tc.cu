@@ -34,6 +34,52 @@ struct GemmParams {
     int ws_rows;        // rows per split slice of the workspace (multiple of BM)
     uint32_t mn_lbo, mn_sbo;  // descriptor strides of MN-major operand tiles
     float alpha;              // accumulator scale applied in the epilogue
+    int streamk;              // 1: CTAs own equal contiguous ranges of (tile, k-block) units
+    int units_per_cta, total_units;
+};
+
+// One unit of work of a CTA: k-blocks [kb0, kb1) of output tile (tm, tn).
+struct Segment {
+    int tm, tn, kb0, kb1, out_row;
+    bool partial;             // tile shared with another CTA: combine with TMA reduce-add
+};
+
+// Work sequence of this CTA; the producer, MMA and epilogue roles all walk the same sequence.
+//   tile/split mode: items blockIdx.x, blockIdx.x + gridDim.x, ... of the (m-tile, n-tile, k-split)
+//     list; a split writes its partial tile into its own workspace slice (reduced afterwards in
+//     fixed order);
+//   stream-K mode (tile count just above the SM count): the CTA owns units_per_cta consecutive
+//     (tile, k-block) units; units_per_cta >= k-blocks per tile, so a tile is shared by at most
+//     two CTAs and the reduce-add of two partials into a zeroed C is order independent.
+struct WorkIter {
+    int it = 0, u = -1;
+    __device__ __forceinline__ bool next(const GemmParams &p, Segment &s) {
+        if (p.streamk) {
+            const int u1 = min(((int)blockIdx.x + 1) * p.units_per_cta, p.total_units);
+            if (u < 0) u = (int)blockIdx.x * p.units_per_cta;
+            if (u >= u1) return false;
+            const int tile = u / p.nkb;
+            s.kb0 = u % p.nkb;
+            s.kb1 = min(p.nkb, s.kb0 + (u1 - u));
+            u += s.kb1 - s.kb0;
+            s.tm = tile % p.tiles_m;
+            s.tn = tile / p.tiles_m;
+            s.out_row = s.tm * BM;
+            s.partial = !(s.kb0 == 0 && s.kb1 == p.nkb);
+            return true;
+        }
+        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        if (item >= p.tiles_m * p.tiles_n * p.nsplit) return false;
+        ++it;
+        s.tm = item % p.tiles_m;
+        s.tn = (item / p.tiles_m) % p.tiles_n;
+        const int sp = item / (p.tiles_m * p.tiles_n);
+        s.kb0 = sp * p.kb_per_split;
+        s.kb1 = min(s.kb0 + p.kb_per_split, p.nkb);
+        s.out_row = (p.nsplit > 1 ? sp * p.ws_rows : 0) + s.tm * BM;
+        s.partial = false;
+        return true;
+    }
 };
 
 // F16: operands are fp16 (kind::f16, 64-element k-blocks, plain 128B swizzle for both majors);
@@ -90,19 +136,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total = p.tiles_m * p.tiles_n * p.nsplit;
-
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = blockIdx.x; item < total; item += gridDim.x) {
-                const int tm = item % p.tiles_m;
-                const int tn = (item / p.tiles_m) % p.tiles_n;
-                const int sp = item / (p.tiles_m * p.tiles_n);
-                const int kb0 = sp * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, p.nkb);
+            WorkIter work;
+            Segment sg;
+            while (work.next(p, sg)) {
+                const int tm = sg.tm, tn = sg.tn, kb0 = sg.kb0, kb1 = sg.kb1;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t sa = smem_u32(smem + stage * kStageBytes);
@@ -138,10 +180,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             int t = 0;
-            for (int item = blockIdx.x; item < total; item += gridDim.x, ++t) {
-                const int sp = item / (p.tiles_m * p.tiles_n);
-                const int kb0 = sp * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, p.nkb);
+            WorkIter work;
+            Segment sg;
+            for (; work.next(p, sg); ++t) {
+                const int kb0 = sg.kb0, kb1 = sg.kb1;
                 const int acc = t & 1;
                 const uint32_t acc_phase = (t >> 1) & 1;
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
@@ -177,15 +219,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool issuer = (threadIdx.x == 128);
         int t = 0;
         int buf = 0;
-        for (int item = blockIdx.x; item < total; item += gridDim.x, ++t) {
-            const int tm = item % p.tiles_m;
-            const int tn = (item / p.tiles_m) % p.tiles_n;
-            const int sp = item / (p.tiles_m * p.tiles_n);
+        WorkIter work;
+        Segment sg;
+        for (; work.next(p, sg); ++t) {
+            const int tn = sg.tn;
             const int acc = t & 1;
             const uint32_t acc_phase = (t >> 1) & 1;
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            const int out_row = (p.nsplit > 1 ? sp * p.ws_rows : 0) + tm * BM;
+            const int out_row = sg.out_row;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 if (tn * BN + c * 32 >= p.N) break;   // uniform: nothing to store
@@ -208,7 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 epi_bar_sync();
                 if (issuer) {
                     const uint32_t src = smem_u32(epi + buf * kEpiBytes);
-                    if (p.accumulate && p.nsplit == 1)
+                    if ((p.accumulate && p.nsplit == 1) || sg.partial)
                         tma_reduce_add_2d(&tmC, tn * BN + c * 32, out_row, src);
                     else
                         tma_store_2d(&tmC, tn * BN + c * 32, out_row, src);
@@ -247,25 +289,63 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ ws, int64_t ldw, 
 
 struct SplitPlan {
     int tiles_m, tiles_n, nkb, nsplit, kb_per_split;
+    int streamk, units_per_cta, grid;
 };
 
-static SplitPlan plan_split(int M, int N, int K, int bke = BK) {
+static int num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            sms = n;
+        else
+            sms = 148;
+    }
+    return sms;
+}
+
+// Wave efficiency of `items` equal work items on `sms` persistent CTAs.
+static double wave_efficiency(int items, int sms) {
+    const int rounds = (items + sms - 1) / sms;
+    return (double)items / ((double)rounds * sms);
+}
+
+static SplitPlan plan_split(int M, int N, int K, int bke = BK, bool allow_streamk = false) {
     SplitPlan s;
+    const int sms = num_sms();
     s.tiles_m = (M + BM - 1) / BM;
     s.tiles_n = (N + BN - 1) / BN;
     s.nkb = (K + bke - 1) / bke;
+    s.streamk = 0;
+    s.units_per_cta = 0;
     const int tiles = s.tiles_m * s.tiles_n;
     int nsplit = 1;
-    if (tiles < 111 && s.nkb >= 16) {
-        nsplit = (148 + tiles - 1) / tiles;
-        const int cap = s.nkb / 8;  // at least 8 k-blocks (32 KB x 8) per work item
-        if (nsplit > cap) nsplit = cap;
-        if (nsplit < 1) nsplit = 1;
+    if (tiles < sms && s.nkb >= 16) {
+        // split K so that the work items fill whole waves of SMs; among near-best choices take
+        // the smallest split (least workspace traffic); >= 8 k-blocks per item
+        const int cap = s.nkb / 8 < 64 ? s.nkb / 8 : 64;
+        double best = wave_efficiency(tiles, sms);
+        for (int ns = 2; ns <= cap; ++ns) {
+            const int kbp = (s.nkb + ns - 1) / ns;
+            const int eff_ns = (s.nkb + kbp - 1) / kbp;
+            const double e = wave_efficiency(tiles * eff_ns, sms);
+            if (e > best + 0.03) {
+                best = e;
+                nsplit = ns;
+            }
+        }
+    } else if (allow_streamk && tiles > sms && tiles < 4 * sms && s.nkb >= 8 &&
+               wave_efficiency(tiles, sms) < 0.85) {
+        s.streamk = 1;
+        s.units_per_cta = (int)(((int64_t)tiles * s.nkb + sms - 1) / sms);   // >= nkb since tiles > sms
     }
     const char *force = getenv("SCVAE_TC_NSPLIT");
-    if (force && atoi(force) > 0) nsplit = atoi(force);
+    if (force && atoi(force) > 0) { nsplit = atoi(force); s.streamk = 0; }
     s.kb_per_split = (s.nkb + nsplit - 1) / nsplit;
     s.nsplit = (s.nkb + s.kb_per_split - 1) / s.kb_per_split;  // no empty splits
+    const int total = tiles * s.nsplit;
+    s.grid = s.streamk ? sms : (total < sms ? total : sms);
     return s;
 }
 
@@ -287,7 +367,7 @@ static int launch_gemm(const char *name, int layout, int M, int N, int K, const 
     SCVAE_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "%s: bad arguments", name);
     SCVAE_CHECK_ARG(aligned16(A) && aligned16(B) && aligned16(C) && lda % LDM == 0 && ldb % LDM == 0 && ldc % 4 == 0,
                     "%s: operands must be 16-byte aligned with 16-byte-multiple leading dimensions", name);
-    SplitPlan sp = plan_split(M, N, K, BKE);
+    SplitPlan sp = plan_split(M, N, K, BKE, /*allow_streamk=*/!accumulate);
     const int64_t ldw = (N + 3) & ~3;
     const int ws_rows = sp.tiles_m * BM;
     if (sp.nsplit > 1) {
@@ -323,17 +403,19 @@ static int launch_gemm(const char *name, int layout, int M, int N, int K, const 
     if (const char *e = getenv("SCVAE_TC_MN_LBO")) p.mn_lbo = (uint32_t)atoi(e);
     if (const char *e = getenv("SCVAE_TC_MN_SBO")) p.mn_sbo = (uint32_t)atoi(e);
 
-    const int total = sp.tiles_m * sp.tiles_n * sp.nsplit;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            sms = n;
-        else
-            sms = 148;
+    p.streamk = sp.streamk;
+    p.units_per_cta = sp.units_per_cta;
+    p.total_units = sp.tiles_m * sp.tiles_n * sp.nkb;
+    if (sp.nsplit > 1) {   // (the no-workspace fallback above may have changed the item count)
+        sp.grid = sp.tiles_m * sp.tiles_n * sp.nsplit < num_sms() ? sp.tiles_m * sp.tiles_n * sp.nsplit : num_sms();
+    } else if (!sp.streamk) {
+        sp.grid = sp.tiles_m * sp.tiles_n < num_sms() ? sp.tiles_m * sp.tiles_n : num_sms();
     }
-    const int grid = total < sms ? total : sms;
+    const int grid = sp.grid;
+    if (sp.streamk) {   // partial tiles are reduce-added into C
+        cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), s);
+        SCVAE_CHECK_ARG(e == cudaSuccess, "%s: memset failed: %s", name, cudaGetErrorString(e));
+    }
 #define LAUNCH(AM, BMN)                                                                                     \
     do {                                                                                                    \
         static bool attr_set = false;                                                                       \

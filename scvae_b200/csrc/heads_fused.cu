@@ -242,11 +242,6 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
             mbar_wait(bar(S_FULL + st), ph);
             mbar_wait(bar(T_FULL + st), ph);
             tc_fence_after();
-            // da(n-1) has been consumed by MMA2 and read by its TMA store before we overwrite it
-            if (n > 0) {
-                mbar_wait(bar(A_EMPTY), (uint32_t)((n - 1) & 1));
-                mbar_wait(bar(A_STORED), (uint32_t)((n - 1) & 1));
-            }
             const uint8_t *trow = sT + st * FTBytes + row * 128;
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
@@ -281,6 +276,12 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
                         packed[h][grp * 2] = pack_half2(gv[h][0] * gsv, gv[h][1] * gsv);
                         packed[h][grp * 2 + 1] = pack_half2(gv[h][2] * gsv, gv[h][3] * gsv);
                     }
+                }
+                if (sub == 0 && n > 0) {
+                    // da(n-1) must have been consumed by MMA2 and read by its TMA store before
+                    // it is overwritten; waiting here (after the math) hides both latencies
+                    mbar_wait(bar(A_EMPTY), (uint32_t)((n - 1) & 1));
+                    mbar_wait(bar(A_STORED), (uint32_t)((n - 1) & 1));
                 }
 #pragma unroll
                 for (int h = 0; h < P; ++h) {

@@ -78,7 +78,7 @@ gaussian_latent_bwd_kernel(const float *__restrict__ ph, int64_t ldph, int B, in
 }
 
 // lower_bound = mean_{s,b} logmeanexp_r(logp - kl); weighted variant; go = -softmax_r / (S B).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 vae_bound_kernel(const float *__restrict__ logp, const float *__restrict__ kl_row, int R, int S,
                  int B, float weight, float *__restrict__ out, float *__restrict__ go) {
     __shared__ float red[32];
@@ -188,7 +188,9 @@ extern "C" int scvae_gaussian_latent_bwd(const float *ph, int64_t ldph, int B, i
 extern "C" int scvae_vae_bound(const float *logp, const float *kl_row, int R, int S, int B,
                                float weight, float *out, float *go, void *stream) {
     SCVAE_CHECK_ARG(logp && kl_row && out && R > 0 && S > 0 && B > 0, "vae_bound: bad arguments");
-    vae_bound_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logp, kl_row, R, S, B, weight, out, go);
+    // one CTA (deterministic tree); 1024 threads keep the serial depth at S*B/1024 terms
+    const int threads = (S * B >= 1024) ? 1024 : 256;
+    vae_bound_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(logp, kl_row, R, S, B, weight, out, go);
     SCVAE_CHECK_LAUNCH("vae_bound");
     return 0;
 }

@@ -277,7 +277,9 @@ def test_gemm_f32(layout, M, N, Kd):
 
 
 TC_SHAPES = [(128, 128, 32), (128, 128, 256), (256, 384, 96), (100, 104, 2001), (300, 40, 5000),
-             (1000, 2100, 101), (4096, 104, 20001)]
+             (1000, 2100, 101), (4096, 104, 20001),
+             (384, 7040, 1024),     # 165 tiles: stream-K scheduling (tiles just above the SM count)
+             (100, 20004, 700)]     # 157 tiles, the encoder wgrad shape
 
 
 @pytest.mark.parametrize("layout", [0, 1, 2])
@@ -308,7 +310,7 @@ def test_gemm_tf32(layout, M, N, Kd):
 
 @pytest.mark.parametrize("layout", [0, 1, 2])
 @pytest.mark.parametrize("M,N,Kd", [(128, 128, 64), (256, 384, 192), (100, 104, 2001), (4096, 104, 5001),
-                                    (1000, 2100, 101)])
+                                    (1000, 2100, 101), (384, 7040, 1024), (20000, 104, 1000)])
 def test_gemm_f16(layout, M, N, Kd):
     """tcgen05 kind::f16 GEMM: exact products of the fp16 operands, fp32 accumulation."""
     from scvae_b200 import kernels as K
