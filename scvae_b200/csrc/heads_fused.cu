@@ -30,14 +30,17 @@ namespace scvae {
 constexpr int FM = 128;        // cells per CTA
 constexpr int FG = 64;         // genes per tile
 constexpr int FK = 128;        // padded hidden width (fp16 elements)
-constexpr int FThreads = 384;  // 4 control warps + 8 epilogue warps
+// 4 control warps + EW epilogue warps: 12 (three per scheduler) when the register budget allows
+// (P <= 2: 512 threads x 128 registers), else 8
+__host__ __device__ constexpr int fused_epi_warps(int P) { return P <= 2 ? 12 : 8; }
+__host__ __device__ constexpr int fused_threads(int P) { return 128 + 32 * fused_epi_warps(P); }
 constexpr int FDBytes = FM * FK * 2;         // 32 KB
 constexpr int FWBytes = FG * FK * 2;         // 16 KB per head
 constexpr int FABytes = FM * FG * 2;         // 16 KB per head (da tile)
 constexpr int FTBytes = FM * FG * 2;         // 16 KB (u16 targets)
 
 __host__ __device__ constexpr int fused_smem_bytes(int P) {
-    return FDBytes + 2 * P * FWBytes + P * FABytes + 2 * FTBytes + 1024 /*align*/ + 2048 /*barriers, partials*/;
+    return FDBytes + 2 * P * FWBytes + P * FABytes + 2 * FTBytes + 1024 /*align*/ + 4096 /*barriers, partials*/;
 }
 
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -70,11 +73,13 @@ struct FusedParams {
 };
 
 template <int KIND>
-__global__ void __launch_bounds__(FThreads, 1)
+__global__ void __launch_bounds__(fused_threads(Lik<KIND>::P), 1)
 heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmDA,
                    const __grid_constant__ CUtensorMap tmDD, const FusedParams p) {
     constexpr int P = Lik<KIND>::P;
+    constexpr int EW = fused_epi_warps(P);       // epilogue warps
+    constexpr int EJ = EW / 4;                   // epilogue warps per TMEM lane quadrant
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sD = smem;
@@ -87,7 +92,7 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     uint32_t *tmem_slot = (uint32_t *)(bars + NBARS);
-    float *s_part = (float *)(bars + NBARS + 1);   // [2][128] log p partials of the two halves
+    float *s_part = (float *)(bars + NBARS + 1);   // [EJ][128] log p partials of the warps of a quadrant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rt = blockIdx.x / p.gsplit, gs = blockIdx.x % p.gsplit;
@@ -109,11 +114,11 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
             mbar_init(bar(W_FULL + i), 1);
             mbar_init(bar(W_EMPTY + i), 1);
             mbar_init(bar(T_FULL + i), 1);
-            mbar_init(bar(T_EMPTY + i), 8);
+            mbar_init(bar(T_EMPTY + i), EW);
             mbar_init(bar(S_FULL + i), 1);
-            mbar_init(bar(S_EMPTY + i), 8);
+            mbar_init(bar(S_EMPTY + i), EW);
         }
-        mbar_init(bar(A_FULL), 8);
+        mbar_init(bar(A_FULL), EW);
         mbar_init(bar(A_EMPTY), 1);
         mbar_init(bar(A_STORED), 1);
         mbar_init(bar(DD_FULL), 1);
@@ -228,7 +233,8 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
         // ===== epilogue =====
         const int e = warp - 4;
         const int q = e & 3;                     // TMEM lane quadrant (== warp % 4)
-        const int half = e >> 2;                 // which 32 genes of the 64-gene tile
+        const int ej = e >> 2;                   // index among the EJ warps sharing this quadrant
+        const int half = ej;                     // (dd epilogue: warps ej < 2 take 64 columns each)
         const int row = q * 32 + lane;
         const bool issuer = (threadIdx.x == 128);
         const int grow = row0 + row;
@@ -243,9 +249,11 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
             mbar_wait(bar(T_FULL + st), ph);
             tc_fence_after();
             const uint8_t *trow = sT + st * FTBytes + row * 128;
-#pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
-                const int gc = half * 32 + sub * 16;          // first gene of this 16-gene chunk
+            bool first_write = true;
+#pragma unroll 1
+            for (int sub = 0; sub < 4; ++sub) {
+                if ((n * 4 + sub) % EJ != ej) continue;        // dealt round-robin over tiles
+                const int gc = sub * 16;                       // first gene of this 16-gene chunk
                 uint32_t sv[3][16];
 #pragma unroll
                 for (int h = 0; h < P; ++h) tc_ld16(tmem_S + lane_addr + (st * P + h) * FG + gc, sv[h]);
@@ -277,12 +285,13 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
                         packed[h][grp * 2 + 1] = pack_half2(gv[h][2] * gsv, gv[h][3] * gsv);
                     }
                 }
-                if (sub == 0 && n > 0) {
+                if (first_write && n > 0) {
                     // da(n-1) must have been consumed by MMA2 and read by its TMA store before
                     // it is overwritten; waiting here (after the math) hides both latencies
                     mbar_wait(bar(A_EMPTY), (uint32_t)((n - 1) & 1));
                     mbar_wait(bar(A_STORED), (uint32_t)((n - 1) & 1));
                 }
+                first_write = false;
 #pragma unroll
                 for (int h = 0; h < P; ++h) {
                     uint8_t *arow = sA + h * FABytes + row * 128;
@@ -304,17 +313,21 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
             if (lane == 0) mbar_arrive(bar(A_FULL));
         }
         // ---- log p partial of this gene range: combine the two halves, fixed order ----
-        s_part[half * 128 + row] = acc;
-        bar_sync_n(1, 256);
-        if (half == 0 && grow < p.M)
-            p.logp_part[(int64_t)gs * p.part_stride + grow] = s_part[row] + s_part[128 + row];
+        s_part[ej * 128 + row] = acc;
+        bar_sync_n(1, 32 * EW);
+        if (ej == 0 && grow < p.M) {
+            float tot = 0.f;
+#pragma unroll
+            for (int j = 0; j < EJ; ++j) tot += s_part[j * 128 + row];
+            p.logp_part[(int64_t)gs * p.part_stride + grow] = tot;
+        }
         // ---- dd partial: TMEM -> staging smem (the t stages) -> TMA reduce-add ----
         mbar_wait(bar(DD_FULL), 0);
         tc_fence_after();
         uint8_t *stage = sT + half * FTBytes;       // 128 rows x 32 fp32 columns
         const bool half_issuer = (lane == 0 && q == 0);
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < 2 && ej < 2; ++c) {
             uint32_t v[32];
             tc_ld32(tmem_DD + lane_addr + half * 64 + c * 32, v);
             tc_wait_ld();
@@ -339,7 +352,7 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
                 tma_commit();
             }
         }
-        if (half_issuer) tma_wait_all();
+        if (half_issuer && ej < 2) tma_wait_all();
     }
 
     tc_fence_before();
@@ -425,7 +438,7 @@ static int launch_fused(const void *d16, const void *w16, const void *t16, int64
     }
     cudaError_t e = cudaMemsetAsync(dd, 0, (size_t)M * lddd * sizeof(float), s);
     SCVAE_CHECK_ARG(e == cudaSuccess, "heads_fused: memset failed: %s", cudaGetErrorString(e));
-    heads_fused_kernel<KIND><<<f.row_tiles * f.gsplit, FThreads, smem, s>>>(tmD, tmW, tmT, tmDA, tmDD, p);
+    heads_fused_kernel<KIND><<<f.row_tiles * f.gsplit, fused_threads(P), smem, s>>>(tmD, tmW, tmT, tmDA, tmDD, p);
     SCVAE_CHECK_LAUNCH("heads_fused");
     fused_finish_kernel<<<(M + 255) / 256, 256, 0, s>>>(logp_part, p.part_stride, f.gsplit, M, row_const, t_rows,
                                                         logp);
