@@ -186,13 +186,11 @@ __device__ __forceinline__ void lgamma_diff(float r, float x, float &D, float &P
     const int n = (int)x;
     if (x == (float)n && n <= 8) {
         float p = r, dp = 1.f;
-#pragma unroll
-        for (int i = 1; i < 8; ++i) {
-            if (i < n) {
-                const float f = r + (float)i;
-                dp = fmaf(dp, f, p);
-                p = p * f;
-            }
+#pragma unroll 1
+        for (int i = 1; i < n; ++i) {   // typical counts are 2-3: one or two trips
+            const float f = r + (float)i;
+            dp = fmaf(dp, f, p);
+            p = p * f;
         }
         D = fast_lg2(p) * kLn2;
         P = dp * fast_rcp(p);

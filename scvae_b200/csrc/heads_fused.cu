@@ -264,26 +264,27 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
                 tc_wait_ld();
                 uint32_t packed[3][8];
 #pragma unroll
-                for (int grp = 0; grp < 4; ++grp) {
-                    float x[4], av[3][4], gv[3][4];
+                for (int blk = 0; blk < 2; ++blk) {      // two blocks of 8 genes
+                    float x[8], av[3][8], gv[3][8];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t w = tw[grp * 2 + (j >> 1)];
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t w = tw[blk * 4 + (j >> 1)];
                         const uint16_t bits = (uint16_t)((j & 1) ? (w >> 16) : (w & 0xffffu));
                         x[j] = p.t_is_half ? __half2float(__ushort_as_half(bits)) : (float)bits;
 #pragma unroll
-                        for (int h = 0; h < P; ++h) av[h][j] = __uint_as_float(sv[h][grp * 4 + j]);
+                        for (int h = 0; h < P; ++h) av[h][j] = __uint_as_float(sv[h][blk * 8 + j]);
                     }
-                    float lp = 0.f;
-                    lik_group<KIND, true, 4>(x, av, p.has_const != 0, lp, gv);
-                    const bool valid = (g0 + gc + grp * 4) < p.G;   // G % 4 == 0
-                    acc += valid ? lp : 0.f;
+                    float acc8 = 0.f;
+                    lik_group<KIND, true, 8>(x, av, p.has_const != 0, acc8, gv);
+                    // genes >= G only exist in the last tile; G % 8 == 0 keeps blocks uniform
+                    const bool valid = (g0 + gc + blk * 8) < p.G;
+                    acc += valid ? acc8 : 0.f;
                     const float gsv = valid ? gs_row : 0.f;
 #pragma unroll
-                    for (int h = 0; h < P; ++h) {
-                        packed[h][grp * 2] = pack_half2(gv[h][0] * gsv, gv[h][1] * gsv);
-                        packed[h][grp * 2 + 1] = pack_half2(gv[h][2] * gsv, gv[h][3] * gsv);
-                    }
+                    for (int h = 0; h < P; ++h)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            packed[h][blk * 4 + j] = pack_half2(gv[h][2 * j] * gsv, gv[h][2 * j + 1] * gsv);
                 }
                 if (first_write && n > 0) {
                     // da(n-1) must have been consumed by MMA2 and read by its TMA store before
@@ -462,7 +463,7 @@ extern "C" int scvae_heads_fused_bwd(int kind, const void *d16, const void *w16,
                                      void *da16, float *dd, int64_t lddd, int dd_cols, float *logp,
                                      float *workspace, void *stream) {
     SCVAE_CHECK_ARG(d16 && w16 && t16 && da16 && dd && logp && workspace, "heads_fused_bwd: NULL pointer");
-    SCVAE_CHECK_ARG(M > 0 && G > 0 && G % 4 == 0 && t_rows > 0, "heads_fused_bwd: bad shape (G must be a multiple of 4)");
+    SCVAE_CHECK_ARG(M > 0 && G > 0 && G % 8 == 0 && t_rows > 0, "heads_fused_bwd: bad shape (G must be a multiple of 8)");
     SCVAE_CHECK_ARG(head_stride % 64 == 0 && head_stride >= G, "heads_fused_bwd: head_stride must be a multiple of 64");
     SCVAE_CHECK_ARG(ldt % 8 == 0 && lddd % 4 == 0 && dd_cols <= FK, "heads_fused_bwd: bad leading dimensions");
     SCVAE_CHECK_ARG(M == t_rows || t_rows % FM == 0,

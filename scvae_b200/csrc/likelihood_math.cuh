@@ -97,14 +97,17 @@ __device__ __forceinline__ void lik_elem(float x, const float (&a)[3], float &lp
 
 
 // One group of W (cell, gene) terms of a single cell: accumulates log p into `acc`, writes
-// d log p / d a (unscaled) into gv.  Counts >= 2 (rare) go through a per-thread loop over the
-// group's non-zeros so that a warp loops max-popcount times instead of once per element
-// (x == 1 is handled branch-free in lik_elem; lgamma(1 + 1) = 0 needs no fix-up either).
+// d log p / d a (unscaled) into gv.  The branch-free part of all W elements comes first (W
+// independent dependency chains for the scheduler); counts >= 2 (rare) are then fixed up quad
+// by quad with a per-thread loop over the quad's non-zeros, so that a warp loops max-popcount
+// times instead of once per element (x == 1 is handled branch-free in lik_elem; lgamma(1 + 1)
+// = 0 needs no fix-up either).  W is 1 or a multiple of 4.
 template <int KIND, bool BWD, int W>
 __device__ __forceinline__ void lik_group(const float (&x)[W], const float (&av)[3][W], bool has_const,
                                           float &acc, float (&gv)[3][W]) {
     using T = Lik<KIND>;
     constexpr int P = T::P;
+    constexpr int Q = W >= 4 ? 4 : W;     // fix-up granularity
     float rv[W], crv[W];
     unsigned nz = 0;
 #pragma unroll
@@ -121,30 +124,34 @@ __device__ __forceinline__ void lik_group(const float (&x)[W], const float (&av)
         nz |= ((x[j] > 0.f && x[j] != 1.f) ? 1u : 0u) << j;
     }
     if (T::NB || !has_const) {
-        while (nz) {
-            const int j = __ffs(nz) - 1;
-            nz &= nz - 1;
-            float xj = x[0], rj = rv[0], cj = crv[0];
 #pragma unroll
-            for (int q = 1; q < W; ++q) {
-                xj = j == q ? x[q] : xj;
-                rj = j == q ? rv[q] : rj;
-                cj = j == q ? crv[q] : cj;
-            }
-            float extra = 0.f;
-            if (T::NB) {
-                float D, Pd;
-                lgamma_diff(rj, xj, D, Pd);
-                extra = D;
-                if (BWD) {
-                    const float add = cj * Pd;
-                    constexpr int ir = P - 1;  // log_r is the last head
+        for (int b = 0; b < W; b += Q) {
+            unsigned m = (nz >> b) & ((1u << Q) - 1u);
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                float xj = x[b], rj = rv[b], cj = crv[b];
 #pragma unroll
-                    for (int q = 0; q < W; ++q) gv[ir][q] += (j == q) ? add : 0.f;
+                for (int q = 1; q < Q; ++q) {
+                    xj = j == q ? x[b + q] : xj;
+                    rj = j == q ? rv[b + q] : rj;
+                    cj = j == q ? crv[b + q] : cj;
                 }
+                float extra = 0.f;
+                if (T::NB) {
+                    float D, Pd;
+                    lgamma_diff(rj, xj, D, Pd);
+                    extra = D;
+                    if (BWD) {
+                        const float add = cj * Pd;
+                        constexpr int ir = P - 1;  // log_r is the last head
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) gv[ir][b + q] += (j == q) ? add : 0.f;
+                    }
+                }
+                if (!has_const) extra -= lgammaf(1.f + xj);
+                acc += extra;
             }
-            if (!has_const) extra -= lgammaf(1.f + xj);
-            acc += extra;
         }
     }
 }

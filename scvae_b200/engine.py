@@ -305,8 +305,8 @@ class VAEEngine:
 
     # ---- fused likelihood heads (heads_fused.cu) -------------------------------------------
     def _fused_possible(self, M, B):
-        """n_in + 1 <= 128 hidden columns, genes a multiple of 4, targets tiling in 128 rows."""
-        return (self.fused_heads and self.head.n_in + 1 <= 128 and self.G % 4 == 0
+        """n_in + 1 <= 128 hidden columns, genes a multiple of 8, targets tiling in 128 rows."""
+        return (self.fused_heads and self.head.n_in + 1 <= 128 and self.G % 8 == 0
                 and (M == B or B % 128 == 0))
 
     def _plan_fused(self, p, M):
