@@ -68,6 +68,12 @@ int scvae_csr_densify(const int64_t *indptr, const int32_t *indices, const float
                       const int64_t *rows, int B, int G, float *x, int64_t ldx,
                       float *row_const, int rebase, void *t16, int64_t ldt16, void *x16,
                       int64_t ldx16, void *stream);
+/* Same with a compact CSR (uint16 column indices, G <= 65536, and uint16 integer counts):
+ * 4 bytes per non-zero instead of 8 -- the format the streaming path ships over PCIe. */
+int scvae_csr_densify_u16(const int64_t *indptr, const void *indices_u16, const void *values_u16,
+                          const int64_t *rows, int B, int G, float *x, int64_t ldx,
+                          float *row_const, int rebase, void *t16, int64_t ldt16, void *x16,
+                          int64_t ldx16, void *stream);
 /* Dense fp32 counts -> uint16 (clamped), zero padded to ldt16 columns. */
 int scvae_f32_to_u16(const float *x, int64_t ldx, int64_t rows, int G, void *t16, int64_t ldt16,
                      void *stream);

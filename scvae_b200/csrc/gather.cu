@@ -15,9 +15,10 @@ constexpr int kChunk = 8192;   // genes staged in shared memory per pass (32 KB)
 //   x   fp32 augmented (column G = 1)          -> exact-fp32 / evaluation paths
 //   x16 fp16 augmented (column G = 1)          -> fp16 tensor-core first layer
 //   t16 uint16 (clamped to 65535), zero padded -> targets of the fused likelihood heads
+template <typename IdxT, typename ValT>
 __global__ void __launch_bounds__(256)
-csr_densify_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
-                   const float *__restrict__ values, const int64_t *__restrict__ rows, int G,
+csr_densify_kernel(const int64_t *__restrict__ indptr, const IdxT *__restrict__ indices,
+                   const ValT *__restrict__ values, const int64_t *__restrict__ rows, int G,
                    float *__restrict__ x, int64_t ldx, float *__restrict__ row_const, int rebase,
                    uint16_t *__restrict__ t16, int64_t ldt16, __half *__restrict__ x16, int64_t ldx16) {
     __shared__ float red[32];
@@ -36,9 +37,9 @@ csr_densify_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict
             *reinterpret_cast<float4 *>(buf + i) = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
         for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) {
-            const int c = indices[i];
+            const int c = (int)indices[i];
             if (c >= c0 && c < c0 + kChunk && c < G) {
-                const float v = values[i];
+                const float v = (float)values[i];
                 buf[c - c0] = v;
                 if (v > 0.f) acc += lgammaf(1.f + v);
             }
@@ -124,9 +125,26 @@ extern "C" int scvae_csr_densify(const int64_t *indptr, const int32_t *indices, 
     SCVAE_CHECK_ARG(!t16 || (ldt16 % 8 == 0 && ldt16 >= G && aligned16(t16)), "csr_densify: bad t16 layout");
     SCVAE_CHECK_ARG(!x16 || (ldx16 % 8 == 0 && ldx16 > G && aligned16(x16)), "csr_densify: bad x16 layout");
     if (B == 0) return 0;
-    csr_densify_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(indptr, indices, values, rows, G, x, ldx, row_const,
-                                                            rebase, (uint16_t *)t16, ldt16, (__half *)x16, ldx16);
+    csr_densify_kernel<int32_t, float><<<B, 256, 0, (cudaStream_t)stream>>>(
+        indptr, indices, values, rows, G, x, ldx, row_const, rebase, (uint16_t *)t16, ldt16, (__half *)x16, ldx16);
     SCVAE_CHECK_LAUNCH("csr_densify");
+    return 0;
+}
+
+extern "C" int scvae_csr_densify_u16(const int64_t *indptr, const void *indices_u16, const void *values_u16,
+                                     const int64_t *rows, int B, int G, float *x, int64_t ldx, float *row_const,
+                                     int rebase, void *t16, int64_t ldt16, void *x16, int64_t ldx16,
+                                     void *stream) {
+    using namespace scvae;
+    SCVAE_CHECK_ARG(indptr && indices_u16 && values_u16 && (x || x16 || t16), "csr_densify_u16: NULL pointer");
+    SCVAE_CHECK_ARG(B >= 0 && G > 0 && G <= 65536 && (!x || ldx >= G), "csr_densify_u16: bad shape");
+    SCVAE_CHECK_ARG(!t16 || (ldt16 % 8 == 0 && ldt16 >= G && aligned16(t16)), "csr_densify_u16: bad t16 layout");
+    SCVAE_CHECK_ARG(!x16 || (ldx16 % 8 == 0 && ldx16 > G && aligned16(x16)), "csr_densify_u16: bad x16 layout");
+    if (B == 0) return 0;
+    csr_densify_kernel<uint16_t, uint16_t><<<B, 256, 0, (cudaStream_t)stream>>>(
+        indptr, (const uint16_t *)indices_u16, (const uint16_t *)values_u16, rows, G, x, ldx, row_const, rebase,
+        (uint16_t *)t16, ldt16, (__half *)x16, ldx16);
+    SCVAE_CHECK_LAUNCH("csr_densify_u16");
     return 0;
 }
 

@@ -59,9 +59,17 @@ class StreamedCSR:
         indptr, indices, data, shape = _as_csr_arrays(matrix)
         self.shape = shape
         self.device = torch.device(device)
+        self.u16_ok = _counts_fit_u16(data)
+        # compact wire format (4 instead of 8 bytes per non-zero) when columns and counts fit 16 bits
+        self.compact = bool(self.u16_ok and shape[1] <= 65536)
         self.indptr = torch.from_numpy(indptr).pin_memory()
-        self.indices = torch.from_numpy(indices).pin_memory()
-        self.values = torch.from_numpy(data).pin_memory()
+        if self.compact:
+            self.indices = torch.from_numpy(indices.astype(numpy.uint16).view(numpy.int16)).pin_memory()
+            self.values = torch.from_numpy(data.astype(numpy.uint16).view(numpy.int16)).pin_memory()
+        else:
+            self.indices = torch.from_numpy(indices).pin_memory()
+            self.values = torch.from_numpy(data).pin_memory()
+        self.bytes_per_nnz = 4 if self.compact else 8
         n = shape[0]
         row_nnz = numpy.diff(indptr)
         # worst-case slab of max_rows consecutive rows
@@ -76,8 +84,10 @@ class StreamedCSR:
         for _ in range(2):
             self.slots.append({
                 "indptr": torch.empty(max_rows + 1, dtype=torch.int64, device=self.device),
-                "indices": torch.empty(max(self.max_nnz, 1), dtype=torch.int32, device=self.device),
-                "values": torch.empty(max(self.max_nnz, 1), dtype=torch.float32, device=self.device),
+                "indices": torch.empty(max(self.max_nnz, 1), dtype=self.indices.dtype,
+                                       device=self.device),
+                "values": torch.empty(max(self.max_nnz, 1), dtype=self.values.dtype,
+                                      device=self.device),
                 "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "bytes": 0,
                 "u16_ok": self.u16_ok, "f16_exact": self.f16_exact,
             })
@@ -94,7 +104,7 @@ class StreamedCSR:
             s["indices"][: hi - lo].copy_(self.indices[lo:hi], non_blocking=True)
             s["values"][: hi - lo].copy_(self.values[lo:hi], non_blocking=True)
             s["ready"].record(self.copy_stream)
-        s["bytes"] = (i1 - i0 + 1) * 8 + (hi - lo) * 8
+        s["bytes"] = (i1 - i0 + 1) * 8 + (hi - lo) * self.bytes_per_nnz
         return s
 
 

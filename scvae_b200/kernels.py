@@ -54,7 +54,11 @@ def csr_densify(indptr, indices, values, rows, G, x, row_const=None, rebase=Fals
     """CSR rows -> dense minibatch; any of x (fp32), t16 (uint16), x16 (fp16) may be None."""
     B = next(t for t in (x, t16, x16) if t is not None).shape[0]
     lib = _lib.load()
-    _lib.check(lib.scvae_csr_densify(_p(indptr), _p(indices), _p(values), _p(rows), B, G, _p(x),
+    compact = indices.dtype == torch.int16
+    if compact != (values.dtype == torch.int16):
+        raise TypeError("compact CSR needs both indices and values as uint16 (int16 storage)")
+    fn = lib.scvae_csr_densify_u16 if compact else lib.scvae_csr_densify
+    _lib.check(fn(_p(indptr), _p(indices), _p(values), _p(rows), B, G, _p(x),
                                      _ld(x) if x is not None else 0, _p(row_const), int(rebase),
                                      _p(t16), _ld(t16) if t16 is not None else 0, _p(x16),
                                      _ld(x16) if x16 is not None else 0, _stream()),

@@ -446,6 +446,12 @@ def test_csr_densify():
     x_only16 = torch.zeros_like(x16)
     K.csr_densify(indptr, indices, values, rows, G, None, None, x16=x_only16)
     assert torch.equal(x_only16, x16)
+    # compact wire format: uint16 indices and counts
+    ci = torch.tensor(csr.indices.astype(numpy.uint16).view(numpy.int16)).to(dev)
+    cv = torch.tensor(csr.data.astype(numpy.uint16).view(numpy.int16)).to(dev)
+    x_c = torch.zeros_like(x)
+    K.csr_densify(indptr, ci, cv, rows, G, x_c, None)
+    assert torch.equal(x_c, x)
     assert numpy.array_equal(t16[:, :G].cpu().numpy().view(numpy.uint16), sel.astype(numpy.uint16))
     assert torch.all(t16[:, G:] == 0)
     assert torch.all(x[:, G] == 1) and torch.all(x[:, G + 1:] == 0)
