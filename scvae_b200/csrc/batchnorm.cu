@@ -113,7 +113,8 @@ bn_apply_kernel(const float *__restrict__ y, int64_t ldy, int n, int H, int nchu
                 const float *__restrict__ beta, const float *__restrict__ moving_mean,
                 const float *__restrict__ moving_var, int training, int relu,
                 float *__restrict__ out, int64_t ldo, float *__restrict__ save_mean,
-                float *__restrict__ save_rstd, float *__restrict__ var_unbiased) {
+                float *__restrict__ save_rstd, float *__restrict__ var_unbiased, float *__restrict__ mov_mean_out,
+                float *__restrict__ mov_var_out) {
     __shared__ float sh[kBnLanes][3][kBnCols + 1];
     const int c = blockIdx.y * kBnCols + threadIdx.x;
     const int chunk = blockIdx.x % nchunks, group = blockIdx.x / nchunks;
@@ -129,7 +130,12 @@ bn_apply_kernel(const float *__restrict__ y, int64_t ldy, int n, int H, int nchu
         if (ok && chunk == 0 && threadIdx.y == 0) {
             save_mean[group * H + c] = mean;
             save_rstd[group * H + c] = rstd;
-            var_unbiased[group * H32 + c] = var * ((float)n / (float)max(n - 1, 1));
+            const float vu = var * ((float)n / (float)max(n - 1, 1));
+            var_unbiased[group * H32 + c] = vu;
+            if (mov_mean_out) {   // single group: the moving-average update rides along
+                mov_mean_out[c] -= (1.f - kBnDecay) * (mov_mean_out[c] - mean);
+                mov_var_out[c] -= (1.f - kBnDecay) * (mov_var_out[c] - vu);
+            }
         }
     } else if (ok) {
         mean = moving_mean[c];
@@ -310,9 +316,11 @@ extern "C" int scvae_bn_act_fwd(const float *y, int64_t ldy, int M, int H, int g
     const dim3 grid2(groups * nchunks, (int)((ldo + kBnCols - 1) / kBnCols));
     bn_apply_kernel<<<grid2, block, 0, s>>>(y, ldy, n, H, nchunks, sc.H32, sc.p0, sc.p1, beta,
                                             moving_mean, moving_var, training, relu, out, ldo,
-                                            save_mean, save_rstd, sc.var);
+                                            save_mean, save_rstd, sc.var,
+                                            (training && update_moving && groups == 1) ? moving_mean : nullptr,
+                                            moving_var);
     SCVAE_CHECK_LAUNCH("bn_apply");
-    if (training && update_moving) {
+    if (training && update_moving && groups > 1) {
         bn_moving_kernel<<<(H + 127) / 128, 128, 0, s>>>(H, groups, sc.H32, save_mean, sc.var,
                                                          moving_mean, moving_var);
         SCVAE_CHECK_LAUNCH("bn_moving");

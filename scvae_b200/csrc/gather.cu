@@ -103,6 +103,87 @@ csr_densify_kernel(const int64_t *__restrict__ indptr, const IdxT *__restrict__ 
     }
 }
 
+// 16-bit outputs only (the fused training path): the whole row is assembled in shared memory as
+// uint16 counts in ONE pass (zero, scatter, write), then written as fp16 (x16, augmented) and/or
+// uint16 (t16).  Dynamic shared memory: 2 * row_width bytes.
+template <typename IdxT, typename ValT>
+__global__ void __launch_bounds__(256)
+csr_densify16_kernel(const int64_t *__restrict__ indptr, const IdxT *__restrict__ indices,
+                     const ValT *__restrict__ values, const int64_t *__restrict__ rows, int G,
+                     float *__restrict__ row_const, int rebase, uint16_t *__restrict__ t16, int64_t ldt16,
+                     __half *__restrict__ x16, int64_t ldx16, int width8) {
+    extern __shared__ __align__(16) uint16_t row16[];
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    const int64_t row = rows ? rows[b] : b;
+    const int64_t base = rebase ? indptr[0] : 0;
+    const int64_t s = indptr[row] - base, e = indptr[row + 1] - base;
+    uint4 *row4 = reinterpret_cast<uint4 *>(row16);
+    for (int i = threadIdx.x; i < width8; i += blockDim.x) row4[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    float acc = 0.f;
+    for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) {
+        const int c = (int)indices[i];
+        const float v = (float)values[i];
+        if (c >= 0 && c < G) {
+            row16[c] = (uint16_t)fminf(fmaxf(v, 0.f), 65535.f);
+            if (v > 0.f) acc += lgammaf(1.f + v);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < width8; i += blockDim.x) {
+        const int c = i << 3;
+        const uint4 pk = row4[i];
+        if (t16 && c < ldt16) *reinterpret_cast<uint4 *>(t16 + (int64_t)b * ldt16 + c) = pk;
+        if (x16 && c < ldx16) {
+            const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float lo = (float)(w[j] & 0xffffu), hi = (float)(w[j] >> 16);
+                if (c + 2 * j == G) lo = 1.f;          // augmented ones column
+                if (c + 2 * j + 1 == G) hi = 1.f;
+                const __half2 h = __floats2half2_rn(lo, hi);
+                o[j] = *reinterpret_cast<const uint32_t *>(&h);
+            }
+            *reinterpret_cast<uint4 *>(x16 + (int64_t)b * ldx16 + c) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    if (row_const) {
+        const float tot = block_sum(acc, red);
+        if (threadIdx.x == 0) row_const[b] = tot;
+    }
+}
+
+template <typename IdxT, typename ValT>
+static int launch_densify(const int64_t *indptr, const IdxT *indices, const ValT *values, const int64_t *rows,
+                          int B, int G, float *x, int64_t ldx, float *row_const, int rebase, uint16_t *t16,
+                          int64_t ldt16, __half *x16, int64_t ldx16, cudaStream_t s) {
+    if (!x) {   // 16-bit outputs only: single pass through shared memory
+        int64_t width = 0;
+        if (t16) width = ldt16;
+        if (x16 && ldx16 > width) width = ldx16;
+        const int width8 = (int)((width + 7) >> 3);
+        const int smem = width8 * 16;
+        if (smem <= 200 * 1024) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaFuncSetAttribute(csr_densify16_kernel<IdxT, ValT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     200 * 1024);
+                attr_set = true;
+            }
+            csr_densify16_kernel<IdxT, ValT><<<B, 256, smem, s>>>(indptr, indices, values, rows, G, row_const, rebase,
+                                                                  t16, ldt16, x16, ldx16, width8);
+            SCVAE_CHECK_LAUNCH("csr_densify16");
+            return 0;
+        }
+    }
+    csr_densify_kernel<IdxT, ValT><<<B, 256, 0, s>>>(indptr, indices, values, rows, G, x, ldx, row_const, rebase, t16,
+                                                     ldt16, x16, ldx16);
+    SCVAE_CHECK_LAUNCH("csr_densify");
+    return 0;
+}
+
 // dense fp32 counts -> u16 (clamped), zero padded to ldt16 columns
 __global__ void f32_to_u16_kernel(const float *__restrict__ x, int64_t ldx, int G, uint16_t *__restrict__ t16,
                                   int64_t ldt16) {
@@ -125,10 +206,8 @@ extern "C" int scvae_csr_densify(const int64_t *indptr, const int32_t *indices, 
     SCVAE_CHECK_ARG(!t16 || (ldt16 % 8 == 0 && ldt16 >= G && aligned16(t16)), "csr_densify: bad t16 layout");
     SCVAE_CHECK_ARG(!x16 || (ldx16 % 8 == 0 && ldx16 > G && aligned16(x16)), "csr_densify: bad x16 layout");
     if (B == 0) return 0;
-    csr_densify_kernel<int32_t, float><<<B, 256, 0, (cudaStream_t)stream>>>(
-        indptr, indices, values, rows, G, x, ldx, row_const, rebase, (uint16_t *)t16, ldt16, (__half *)x16, ldx16);
-    SCVAE_CHECK_LAUNCH("csr_densify");
-    return 0;
+    return launch_densify<int32_t, float>(indptr, indices, values, rows, B, G, x, ldx, row_const, rebase,
+                                          (uint16_t *)t16, ldt16, (__half *)x16, ldx16, (cudaStream_t)stream);
 }
 
 extern "C" int scvae_csr_densify_u16(const int64_t *indptr, const void *indices_u16, const void *values_u16,
@@ -141,11 +220,9 @@ extern "C" int scvae_csr_densify_u16(const int64_t *indptr, const void *indices_
     SCVAE_CHECK_ARG(!t16 || (ldt16 % 8 == 0 && ldt16 >= G && aligned16(t16)), "csr_densify_u16: bad t16 layout");
     SCVAE_CHECK_ARG(!x16 || (ldx16 % 8 == 0 && ldx16 > G && aligned16(x16)), "csr_densify_u16: bad x16 layout");
     if (B == 0) return 0;
-    csr_densify_kernel<uint16_t, uint16_t><<<B, 256, 0, (cudaStream_t)stream>>>(
-        indptr, (const uint16_t *)indices_u16, (const uint16_t *)values_u16, rows, G, x, ldx, row_const, rebase,
-        (uint16_t *)t16, ldt16, (__half *)x16, ldx16);
-    SCVAE_CHECK_LAUNCH("csr_densify_u16");
-    return 0;
+    return launch_densify<uint16_t, uint16_t>(indptr, (const uint16_t *)indices_u16, (const uint16_t *)values_u16,
+                                              rows, B, G, x, ldx, row_const, rebase, (uint16_t *)t16, ldt16,
+                                              (__half *)x16, ldx16, (cudaStream_t)stream);
 }
 
 extern "C" int scvae_f32_to_u16(const float *x, int64_t ldx, int64_t rows, int G, void *t16, int64_t ldt16,

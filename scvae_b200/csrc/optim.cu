@@ -20,15 +20,29 @@ adam_clip_kernel(float *__restrict__ p, const float *__restrict__ g, float *__re
     const float lr_t = s_lr_t;
     const float ob1 = 1.f - beta1, ob2 = 1.f - beta2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float gi = g[i] * gscale;
-        gi = fminf(fmaxf(gi, -clip), clip);
-        const float mi = beta1 * m[i] + ob1 * gi;
-        const float vi = beta2 * v[i] + ob2 * gi * gi;
-        m[i] = mi;
-        v[i] = vi;
-        p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    auto update = [&](float &pi, float gi, float &mi, float &vi) {
+        gi = fminf(fmaxf(gi * gscale, -clip), clip);
+        mi = beta1 * mi + ob1 * gi;
+        vi = beta2 * vi + ob2 * gi * gi;
+        pi = pi - lr_t * mi / (sqrtf(vi) + eps);
+    };
+    const bool vec = aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v);
+    const int64_t n4 = vec ? (n >> 2) : 0;
+    for (int64_t i = tid; i < n4; i += stride) {
+        float4 p4 = reinterpret_cast<float4 *>(p)[i];
+        const float4 g4 = reinterpret_cast<const float4 *>(g)[i];
+        float4 m4 = reinterpret_cast<float4 *>(m)[i];
+        float4 v4 = reinterpret_cast<float4 *>(v)[i];
+        update(p4.x, g4.x, m4.x, v4.x);
+        update(p4.y, g4.y, m4.y, v4.y);
+        update(p4.z, g4.z, m4.z, v4.z);
+        update(p4.w, g4.w, m4.w, v4.w);
+        reinterpret_cast<float4 *>(p)[i] = p4;
+        reinterpret_cast<float4 *>(m)[i] = m4;
+        reinterpret_cast<float4 *>(v)[i] = v4;
     }
+    for (int64_t i = (n4 << 2) + tid; i < n; i += stride) update(p[i], g[i], m[i], v[i]);
 }
 
 // fp16 operand copy of an fp32 master tensor, zero padded to the destination width.
