@@ -111,28 +111,32 @@ __global__ void __launch_bounds__(256)
 csr_densify16_kernel(const int64_t *__restrict__ indptr, const IdxT *__restrict__ indices,
                      const ValT *__restrict__ values, const int64_t *__restrict__ rows, int G,
                      float *__restrict__ row_const, int rebase, uint16_t *__restrict__ t16, int64_t ldt16,
-                     __half *__restrict__ x16, int64_t ldx16, int width8) {
+                     __half *__restrict__ x16, int64_t ldx16, int width8, int part8) {
+    // blockIdx.y selects a column part of the row (part8 groups of 8 columns each): more CTAs in
+    // flight hide the dependent indptr -> indices -> values load chain
     extern __shared__ __align__(16) uint16_t row16[];
     __shared__ float red[32];
     const int b = blockIdx.x;
+    const int g8_lo = blockIdx.y * part8;
+    const int g8_hi = min(g8_lo + part8, width8);
+    const int c_lo = g8_lo << 3, c_hi = g8_hi << 3;
     const int64_t row = rows ? rows[b] : b;
     const int64_t base = rebase ? indptr[0] : 0;
     const int64_t s = indptr[row] - base, e = indptr[row + 1] - base;
     uint4 *row4 = reinterpret_cast<uint4 *>(row16);
-    for (int i = threadIdx.x; i < width8; i += blockDim.x) row4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < g8_hi - g8_lo; i += blockDim.x) row4[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     float acc = 0.f;
     for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) {
         const int c = (int)indices[i];
         const float v = (float)values[i];
-        if (c >= 0 && c < G) {
-            row16[c] = (uint16_t)fminf(fmaxf(v, 0.f), 65535.f);
-            if (v > 0.f) acc += lgammaf(1.f + v);
-        }
+        if (c >= c_lo && c < c_hi && c < G) row16[c - c_lo] = (uint16_t)fminf(fmaxf(v, 0.f), 65535.f);
+        // the per-cell constant sum_g lgamma(1 + x) is accumulated by part 0 over the whole row
+        if (row_const && blockIdx.y == 0 && c >= 0 && c < G && v > 0.f) acc += lgammaf(1.f + v);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < width8; i += blockDim.x) {
-        const int c = i << 3;
+    for (int i = threadIdx.x; i < g8_hi - g8_lo; i += blockDim.x) {
+        const int c = (g8_lo + i) << 3;
         const uint4 pk = row4[i];
         if (t16 && c < ldt16) *reinterpret_cast<uint4 *>(t16 + (int64_t)b * ldt16 + c) = pk;
         if (x16 && c < ldx16) {
@@ -149,7 +153,7 @@ csr_densify16_kernel(const int64_t *__restrict__ indptr, const IdxT *__restrict_
             *reinterpret_cast<uint4 *>(x16 + (int64_t)b * ldx16 + c) = make_uint4(o[0], o[1], o[2], o[3]);
         }
     }
-    if (row_const) {
+    if (row_const && blockIdx.y == 0) {
         const float tot = block_sum(acc, red);
         if (threadIdx.x == 0) row_const[b] = tot;
     }
@@ -164,7 +168,11 @@ static int launch_densify(const int64_t *indptr, const IdxT *indices, const ValT
         if (t16) width = ldt16;
         if (x16 && ldx16 > width) width = ldx16;
         const int width8 = (int)((width + 7) >> 3);
-        const int smem = width8 * 16;
+        // column parts of <= 8 KB of shared memory each, so that 8 CTAs per SM stay resident
+        int parts = (width8 + 511) / 512;
+        if (parts < 1) parts = 1;
+        const int part8 = (width8 + parts - 1) / parts;
+        const int smem = part8 * 16;
         if (smem <= 200 * 1024) {
             static bool attr_set = false;
             if (!attr_set) {
@@ -172,8 +180,8 @@ static int launch_densify(const int64_t *indptr, const IdxT *indices, const ValT
                                      200 * 1024);
                 attr_set = true;
             }
-            csr_densify16_kernel<IdxT, ValT><<<B, 256, smem, s>>>(indptr, indices, values, rows, G, row_const, rebase,
-                                                                  t16, ldt16, x16, ldx16, width8);
+            csr_densify16_kernel<IdxT, ValT><<<dim3(B, parts), 256, smem, s>>>(
+                indptr, indices, values, rows, G, row_const, rebase, t16, ldt16, x16, ldx16, width8, part8);
             SCVAE_CHECK_LAUNCH("csr_densify16");
             return 0;
         }
