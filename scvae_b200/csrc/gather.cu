@@ -127,12 +127,26 @@ csr_densify16_kernel(const int64_t *__restrict__ indptr, const IdxT *__restrict_
     for (int i = threadIdx.x; i < g8_hi - g8_lo; i += blockDim.x) row4[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     float acc = 0.f;
-    for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) {
-        const int c = (int)indices[i];
-        const float v = (float)values[i];
-        if (c >= c_lo && c < c_hi && c < G) row16[c - c_lo] = (uint16_t)fminf(fmaxf(v, 0.f), 65535.f);
-        // the per-cell constant sum_g lgamma(1 + x) is accumulated by part 0 over the whole row
-        if (row_const && blockIdx.y == 0 && c >= 0 && c < G && v > 0.f) acc += lgammaf(1.f + v);
+    // four (index, value) pairs per thread per trip are loaded before any is consumed, so the
+    // row's non-zeros stream in with 8 independent loads in flight per thread
+    for (int64_t i0 = s + threadIdx.x; i0 < e; i0 += 4 * blockDim.x) {
+        int cc[4];
+        float vv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = i0 + (int64_t)k * blockDim.x;
+            const bool in = i < e;
+            cc[k] = in ? (int)indices[i] : -1;
+            vv[k] = in ? (float)values[i] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = cc[k];
+            const float v = vv[k];
+            if (c >= c_lo && c < c_hi && c < G) row16[c - c_lo] = (uint16_t)fminf(fmaxf(v, 0.f), 65535.f);
+            // the per-cell constant sum_g lgamma(1 + x) is accumulated by part 0 over the whole row
+            if (row_const && blockIdx.y == 0 && c >= 0 && c < G && v > 0.f) acc += lgammaf(1.f + v);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < g8_hi - g8_lo; i += blockDim.x) {
@@ -168,8 +182,9 @@ static int launch_densify(const int64_t *indptr, const IdxT *indices, const ValT
         if (t16) width = ldt16;
         if (x16 && ldx16 > width) width = ldx16;
         const int width8 = (int)((width + 7) >> 3);
-        // column parts of <= 8 KB of shared memory each, so that 8 CTAs per SM stay resident
-        int parts = (width8 + 511) / 512;
+        // one CTA per row while the row fits 64 KB of shared memory (re-scanning the row's
+        // non-zeros per column part costs more than the lost occupancy); parts beyond that
+        int parts = (width8 + 4095) / 4096;
         if (parts < 1) parts = 1;
         const int part8 = (width8 + parts - 1) / parts;
         const int smem = part8 * 16;
