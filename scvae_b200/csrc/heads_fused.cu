@@ -22,7 +22,7 @@
 // Gene-range partial sums (log p per cell, dd) are combined deterministically / by TMA
 // reduce-add.  Gradients are scaled by `scale` before the fp16 conversion and un-scaled in the
 // consumers (loss-scaling against fp16 underflow).
-#include "likelihood_math.cuh"
+#include "fused_math.cuh"
 #include "tc_common.cuh"
 
 namespace scvae {
@@ -30,17 +30,28 @@ namespace scvae {
 constexpr int FM = 128;        // cells per CTA
 constexpr int FG = 64;         // genes per tile
 constexpr int FK = 128;        // padded hidden width (fp16 elements)
-// 4 control warps + EW epilogue warps: 12 (three per scheduler) when the register budget allows
-// (P <= 2: 512 threads x 128 registers), else 8
-__host__ __device__ constexpr int fused_epi_warps(int P) { return P <= 2 ? 12 : 8; }
+// 4 control warps + EW epilogue warps.  A tile has 16 (32-row x 16-gene) chunks and all epilogue
+// warps meet at the da tile once per tile, so EW must divide 16: 8 warps x 2 chunks
+// chunks each (2 per scheduler, 168 registers) or 16 warps x 1 chunk (4 per scheduler, 96
+// registers and 2 KB of total_count scratch each: P <= 2 only)
+__host__ __device__ constexpr int fused_epi_warps(int P) { return P <= 2 ? 16 : 8; }
 __host__ __device__ constexpr int fused_threads(int P) { return 128 + 32 * fused_epi_warps(P); }
+// head-weight ring: a stage is held from its TMA load until MMA2 of its tile has finished, i.e.
+// for two tiles; a third stage takes the reload off the critical path (smem allows it for P <= 2)
+__host__ __device__ constexpr int fused_w_stages(int P) { return P <= 2 ? 3 : 2; }
+// da tile buffers: with two, an epilogue warp may run one tile ahead of MMA2 / the TMA store, so
+// the warps drift apart and MUFU-bound math overlaps the latency-bound x >= 2 fix-ups of others
+__host__ __device__ constexpr int fused_a_bufs(int P) { return 1; }
 constexpr int FDBytes = FM * FK * 2;         // 32 KB
 constexpr int FWBytes = FG * FK * 2;         // 16 KB per head
 constexpr int FABytes = FM * FG * 2;         // 16 KB per head (da tile)
 constexpr int FTBytes = FM * FG * 2;         // 16 KB (u16 targets)
+constexpr int FRBytes = 32 * 16 * 2;         // per epilogue warp: fp16 total_count of a 16-gene chunk
 
 __host__ __device__ constexpr int fused_smem_bytes(int P) {
-    return FDBytes + 2 * P * FWBytes + P * FABytes + 2 * FTBytes + 1024 /*align*/ + 4096 /*barriers, partials*/;
+    return FDBytes + fused_w_stages(P) * P * FWBytes + fused_a_bufs(P) * P * FABytes + 2 * FTBytes +
+           fused_epi_warps(P) * FRBytes +
+           1024 /*align*/ + 256 /*barriers*/;
 }
 
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -51,6 +62,31 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
+}
+// explicit shared-space accesses (generic LD/ST to shared memory take the long L1TEX path)
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint16_t lds_u16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint16_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
 }
 __device__ __forceinline__ void bar_sync_n(int id, int n) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
@@ -68,11 +104,55 @@ struct FusedParams {
     const float *go;          // nullable per-row upstream gradient
     float go_scalar, scale, inv_scale;
     int has_const;            // sum_g lgamma(1+t) is subtracted by the finish kernel
-    int t_is_half;            // targets are fp16 (exact for counts <= 2048) instead of uint16
     float *logp_part;
+    long long *dbg;           // development aid: per-tile clock64 timeline of CTA 0 (NULL in production)
 };
+#define FUSED_DBG(n, ev)                                                        \
+    do {                                                                        \
+        if (p.dbg && blockIdx.x == 0 && (n) < 40) p.dbg[(n) * 16 + (ev)] = clock64(); \
+    } while (0)
 
-template <int KIND>
+// A 16-gene chunk in which a clip of the reference is active (fused_math.cuh): exact masked math
+// of likelihood_math.cuh, out of line (rare; keeps the register budget of the fast path small).
+struct FusedSlowIn {
+    uint32_t tw[8];
+    uint32_t sv[3][16];
+};
+struct FusedSlowOut {
+    uint32_t packed[3][8];
+    float acc;
+};
+template <int KIND, bool T_HALF>
+__device__ __noinline__ FusedSlowOut fused_slow_chunk(FusedSlowIn in, float gs_row, int g_first, int G,
+                                                      bool has_const) {
+    constexpr int P = Lik<KIND>::P;
+    FusedSlowOut out;
+    out.acc = 0.f;
+#pragma unroll 1
+    for (int blk = 0; blk < 2; ++blk) {
+        float x[8], av[3][8], gv[3][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) fused_cvt2<T_HALF>(in.tw[blk * 4 + i], x[2 * i], x[2 * i + 1]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int h = 0; h < P; ++h) av[h][j] = __uint_as_float(in.sv[h][blk * 8 + j]);
+        float acc8 = 0.f;
+        lik_group<KIND, true, 8>(x, av, has_const, acc8, gv);
+        const bool valid = (g_first + blk * 8) < G;
+        out.acc += valid ? acc8 : 0.f;
+        const float gsv = valid ? gs_row : 0.f;
+#pragma unroll
+        for (int h = 0; h < P; ++h)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                out.packed[h][blk * 4 + j] = pack_half2(gv[h][2 * j] * gsv, gv[h][2 * j + 1] * gsv);
+    }
+    return out;
+}
+
+// T_HALF: targets are fp16 (exact for counts <= 2048) instead of uint16
+template <int KIND, bool T_HALF>
 __global__ void __launch_bounds__(fused_threads(Lik<KIND>::P), 1)
 heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmDA,
@@ -83,16 +163,19 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sD = smem;
-    uint8_t *sW = sD + FDBytes;                 // [2 stages][P][2 k-halves][64 genes][128 B]
-    uint8_t *sA = sW + 2 * P * FWBytes;         // [P][128 rows][128 B]
-    uint8_t *sT = sA + P * FABytes;             // [2 stages][128 rows][128 B]
-    uint64_t *bars = (uint64_t *)(sT + 2 * FTBytes);
-    enum { D_FULL = 0, W_FULL = 1, W_EMPTY = 3, T_FULL = 5, T_EMPTY = 7, S_FULL = 9, S_EMPTY = 11,
-           A_FULL = 13, A_EMPTY = 14, DD_FULL = 15, A_STORED = 16, NBARS = 17 };
+    constexpr int NW = fused_w_stages(P);        // head-weight ring depth
+    uint8_t *sW = sD + FDBytes;                 // [NW stages][P][2 k-halves][64 genes][128 B]
+    constexpr int NA = fused_a_bufs(P);          // da tile buffers
+    uint8_t *sA = sW + NW * P * FWBytes;        // [NA][P][128 rows][128 B]
+    uint8_t *sT = sA + NA * P * FABytes;        // [2 stages][128 rows][128 B]
+    uint8_t *sR = sT + 2 * FTBytes;             // [EW warps][4 chunks][32 lanes][16 B]
+    uint64_t *bars = (uint64_t *)(sR + EW * FRBytes);
+    enum { D_FULL = 0, W_FULL = 1, W_EMPTY = W_FULL + NW, T_FULL = W_EMPTY + NW, T_EMPTY = T_FULL + 2,
+           S_FULL = T_EMPTY + 2, S_EMPTY = S_FULL + 2, A_FULL = S_EMPTY + 2, A_EMPTY = A_FULL + NA,
+           A_STORED = A_EMPTY + NA, DD_FULL = A_STORED + NA, NBARS = DD_FULL + 1 };
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     uint32_t *tmem_slot = (uint32_t *)(bars + NBARS);
-    float *s_part = (float *)(bars + NBARS + 1);   // [EJ][128] log p partials of the warps of a quadrant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rt = blockIdx.x / p.gsplit, gs = blockIdx.x % p.gsplit;
@@ -110,17 +193,21 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
     }
     if (warp == 1 && lane == 0) {
         mbar_init(bar(D_FULL), 1);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NW; ++i) {
             mbar_init(bar(W_FULL + i), 1);
             mbar_init(bar(W_EMPTY + i), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(bar(T_FULL + i), 1);
             mbar_init(bar(T_EMPTY + i), EW);
             mbar_init(bar(S_FULL + i), 1);
             mbar_init(bar(S_EMPTY + i), EW);
         }
-        mbar_init(bar(A_FULL), EW);
-        mbar_init(bar(A_EMPTY), 1);
-        mbar_init(bar(A_STORED), 1);
+        for (int i = 0; i < NA; ++i) {
+            mbar_init(bar(A_FULL + i), EW);
+            mbar_init(bar(A_EMPTY + i), 1);
+            mbar_init(bar(A_STORED + i), 1);
+        }
         mbar_init(bar(DD_FULL), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -148,14 +235,16 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
                 const int st = n & 1;
                 const uint32_t ph = (n >> 1) & 1;
                 const int g0 = (tile0 + n) * FG;
-                mbar_wait(bar(W_EMPTY + st), ph ^ 1);
-                mbar_expect_tx(bar(W_FULL + st), P * FWBytes);
+                const int ws = n % NW;
+                mbar_wait(bar(W_EMPTY + ws), (uint32_t)((n / NW) & 1) ^ 1u);
+                FUSED_DBG(n, 9);
+                mbar_expect_tx(bar(W_FULL + ws), P * FWBytes);
 #pragma unroll
                 for (int h = 0; h < P; ++h) {
-                    const uint32_t dst = smem_u32(sW + (st * P + h) * FWBytes);
+                    const uint32_t dst = smem_u32(sW + (ws * P + h) * FWBytes);
                     const int wrow = (int)(h * p.head_stride) + g0;
-                    tma_load_2d(dst, &tmW, 0, wrow, bar(W_FULL + st));
-                    tma_load_2d(dst + FWBytes / 2, &tmW, 64, wrow, bar(W_FULL + st));
+                    tma_load_2d(dst, &tmW, 0, wrow, bar(W_FULL + ws));
+                    tma_load_2d(dst + FWBytes / 2, &tmW, 64, wrow, bar(W_FULL + ws));
                 }
                 mbar_wait(bar(T_EMPTY + st), ph ^ 1);
                 mbar_expect_tx(bar(T_FULL + st), FTBytes);
@@ -173,12 +262,14 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
             tc_fence_after();
             const uint32_t aD = smem_u32(sD);
             auto mma2 = [&](int n) {   // dd += da(n) . W(n)
-                const int st = n & 1;
-                mbar_wait(bar(A_FULL), (uint32_t)(n & 1));
+                const int st = n % NW;
+                const int ab = n % NA;
+                mbar_wait(bar(A_FULL + ab), (uint32_t)((n / NA) & 1));
+                FUSED_DBG(n, 1);
                 tc_fence_after();
 #pragma unroll
                 for (int h = 0; h < P; ++h) {
-                    const uint32_t aA = smem_u32(sA + h * FABytes);
+                    const uint32_t aA = smem_u32(sA + (ab * P + h) * FABytes);
                     const uint32_t aW = smem_u32(sW + (st * P + h) * FWBytes);
 #pragma unroll
                     for (int j = 0; j < FG / 16; ++j) {
@@ -187,18 +278,20 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
                         tc_mma_f16(tmem_DD, da, db, idesc2, (n > 0 || h > 0 || j > 0) ? 1u : 0u);
                     }
                 }
-                tc_commit(bar(A_EMPTY));
+                tc_commit(bar(A_EMPTY + ab));
                 tc_commit(bar(W_EMPTY + st));
             };
             for (int n = 0; n < ntile; ++n) {
                 const int st = n & 1;
                 const uint32_t ph = (n >> 1) & 1;
-                mbar_wait(bar(W_FULL + st), ph);
+                const int ws = n % NW;
+                mbar_wait(bar(W_FULL + ws), (uint32_t)((n / NW) & 1));
                 mbar_wait(bar(S_EMPTY + st), ph ^ 1);
+                FUSED_DBG(n, 0);
                 tc_fence_after();
 #pragma unroll
                 for (int h = 0; h < P; ++h) {
-                    const uint32_t aW = smem_u32(sW + (st * P + h) * FWBytes);
+                    const uint32_t aW = smem_u32(sW + (ws * P + h) * FWBytes);
                     const uint32_t dS = tmem_S + (st * P + h) * FG;
 #pragma unroll
                     for (int kk = 0; kk < FK / 16; ++kk) {
@@ -219,13 +312,17 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
         if (lane == 0) {
             for (int n = 0; n < ntile; ++n) {
                 const int g0 = (tile0 + n) * FG;
-                mbar_wait(bar(A_FULL), (uint32_t)(n & 1));
+                const int ab = n % NA;
+                mbar_wait(bar(A_FULL + ab), (uint32_t)((n / NA) & 1));
+                FUSED_DBG(n, 2);
 #pragma unroll
                 for (int h = 0; h < P; ++h)
-                    tma_store_2d(&tmDA, (int)(h * p.head_stride) + g0, row0, smem_u32(sA + h * FABytes));
+                    tma_store_2d(&tmDA, (int)(h * p.head_stride) + g0, row0,
+                                 smem_u32(sA + (ab * P + h) * FABytes));
                 tma_commit();
                 tma_wait_read<0>();
-                mbar_arrive(bar(A_STORED));
+                FUSED_DBG(n, 3);
+                mbar_arrive(bar(A_STORED + ab));
             }
             tma_wait_all();
         }
@@ -240,15 +337,21 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
         const int grow = row0 + row;
         const float gs_row = (grow < p.M ? (p.go ? p.go[grow] : p.go_scalar) : 0.f) * p.scale;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        float acc = 0.f;
+        const uint32_t rscr = smem_u32(sR + e * FRBytes);            // this warp's total_count chunk
+        const uint32_t a_row0 = smem_u32(sA) + (uint32_t)row * 128u;  // this row of da buffer 0, head 0
+        const bool fixups = Lik<KIND>::NB || p.has_const == 0;       // any x >= 2 special function left?
+        float accA = 0.f, accB = 0.f;      // log p of this row = accA - ln2 * accB
         for (int n = 0; n < ntile; ++n) {
             const int st = n & 1;
             const uint32_t ph = (n >> 1) & 1;
             const int g0 = (tile0 + n) * FG;
             mbar_wait(bar(S_FULL + st), ph);
             mbar_wait(bar(T_FULL + st), ph);
+            if (lane == 0 && (e == 0 || e == EW - 1)) FUSED_DBG(n, e == 0 ? 4 : 10);
             tc_fence_after();
-            const uint8_t *trow = sT + st * FTBytes + row * 128;
+            const uint32_t trow = smem_u32(sT + st * FTBytes) + (uint32_t)row * 128u;
+            const int ab = n % NA;
+            const uint32_t a_row = a_row0 + (uint32_t)(ab * P * FABytes);
             bool first_write = true;
 #pragma unroll 1
             for (int sub = 0; sub < 4; ++sub) {
@@ -258,48 +361,122 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
 #pragma unroll
                 for (int h = 0; h < P; ++h) tc_ld16(tmem_S + lane_addr + (st * P + h) * FG + gc, sv[h]);
                 const int c0 = gc >> 3;                         // 16-byte chunk index in the row
-                const uint4 t0 = *reinterpret_cast<const uint4 *>(trow + (((c0) ^ (row & 7)) << 4));
-                const uint4 t1 = *reinterpret_cast<const uint4 *>(trow + (((c0 + 1) ^ (row & 7)) << 4));
+                const uint32_t sw0 = (uint32_t)(((c0) ^ (row & 7)) << 4);
+                const uint32_t sw1 = (uint32_t)(((c0 + 1) ^ (row & 7)) << 4);
+                const uint4 t0 = lds_v4(trow + sw0);
+                const uint4 t1 = lds_v4(trow + sw1);
                 const uint32_t tw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
                 tc_wait_ld();
+                // is any clip of the reference active in this chunk? (fused_math.cuh)
+                float mlogit = 0.f, mlog = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+#pragma unroll
+                    for (int h = 0; h < P - 1; ++h) mlogit = fmaxf(mlogit, fabsf(__uint_as_float(sv[h][j])));
+                    mlog = fmaxf(mlog, fabsf(__uint_as_float(sv[P - 1][j])));
+                }
+                const bool slow = (mlogit > kFastLogitMax) || (mlog > kFastLogMax);
                 uint32_t packed[3][8];
+                uint32_t flags = 0;      // element 2i -> bit 14 - i, element 2i + 1 -> bit 30 - i: target >= 2
+                if (!slow) {
 #pragma unroll
-                for (int blk = 0; blk < 2; ++blk) {      // two blocks of 8 genes
-                    float x[8], av[3][8], gv[3][8];
+                    for (int blk = 0; blk < 2; ++blk) {      // two blocks of 8 genes
+                        // genes >= G only exist in the last tile; G % 8 == 0 keeps blocks uniform
+                        if ((g0 + gc + blk * 8) >= p.G) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t w = tw[blk * 4 + (j >> 1)];
-                        const uint16_t bits = (uint16_t)((j & 1) ? (w >> 16) : (w & 0xffffu));
-                        x[j] = p.t_is_half ? __half2float(__ushort_as_half(bits)) : (float)bits;
+                            for (int h = 0; h < P; ++h)
 #pragma unroll
-                        for (int h = 0; h < P; ++h) av[h][j] = __uint_as_float(sv[h][blk * 8 + j]);
+                                for (int j = 0; j < 4; ++j) packed[h][blk * 4 + j] = 0u;
+                            continue;
+                        }
+                        float x[8], av[3][8], gv[3][8], rr[8];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t w = tw[blk * 4 + i];
+                            fused_cvt2<T_HALF>(w, x[2 * i], x[2 * i + 1]);
+                            flags |= fused_flags2<T_HALF>(w) >> (blk * 4 + i);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+#pragma unroll
+                            for (int h = 0; h < P; ++h) av[h][j] = __uint_as_float(sv[h][blk * 8 + j]);
+                        fused_fast8<KIND>(x, av, gs_row, accA, accB, rr, gv);
+                        if (Lik<KIND>::NB) {
+                            // fp16 is ample for the x >= 2 corrections: their error is ~1e-3 x per
+                            // term with random sign, against a row sum of thousands
+                            sts_v4(rscr + (uint32_t)((blk * 32 + lane) * 16), pack_half2(rr[0], rr[1]),
+                                   pack_half2(rr[2], rr[3]), pack_half2(rr[4], rr[5]), pack_half2(rr[6], rr[7]));
+                        }
+#pragma unroll
+                        for (int h = 0; h < P; ++h)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                packed[h][blk * 4 + j] = pack_half2(gv[h][2 * j], gv[h][2 * j + 1]);
                     }
-                    float acc8 = 0.f;
-                    lik_group<KIND, true, 8>(x, av, p.has_const != 0, acc8, gv);
-                    // genes >= G only exist in the last tile; G % 8 == 0 keeps blocks uniform
-                    const bool valid = (g0 + gc + blk * 8) < p.G;
-                    acc += valid ? acc8 : 0.f;
-                    const float gsv = valid ? gs_row : 0.f;
+                } else {
+                    FusedSlowIn in;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) in.tw[i] = tw[i];
 #pragma unroll
                     for (int h = 0; h < P; ++h)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            packed[h][blk * 4 + j] = pack_half2(gv[h][2 * j] * gsv, gv[h][2 * j + 1] * gsv);
+                        for (int j = 0; j < 16; ++j) in.sv[h][j] = sv[h][j];
+                    const FusedSlowOut out = fused_slow_chunk<KIND, T_HALF>(in, gs_row, g0 + gc, p.G, p.has_const != 0);
+                    accA += out.acc;
+#pragma unroll
+                    for (int h = 0; h < P; ++h)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) packed[h][j] = out.packed[h][j];
                 }
-                if (first_write && n > 0) {
-                    // da(n-1) must have been consumed by MMA2 and read by its TMA store before
-                    // it is overwritten; waiting here (after the math) hides both latencies
-                    mbar_wait(bar(A_EMPTY), (uint32_t)((n - 1) & 1));
-                    mbar_wait(bar(A_STORED), (uint32_t)((n - 1) & 1));
+                if (first_write && n >= NA) {
+                    // the previous tile in this da buffer must have been consumed by MMA2 and read
+                    // by its TMA store before it is overwritten
+                    if (lane == 0 && e == 0) FUSED_DBG(n, 5);
+                    mbar_wait(bar(A_EMPTY + ab), (uint32_t)(((n - NA) / NA) & 1));
+                    if (lane == 0 && e == 0) FUSED_DBG(n, 6);
+                    mbar_wait(bar(A_STORED + ab), (uint32_t)(((n - NA) / NA) & 1));
+                    if (lane == 0 && e == 0) FUSED_DBG(n, 7);
                 }
                 first_write = false;
 #pragma unroll
                 for (int h = 0; h < P; ++h) {
-                    uint8_t *arow = sA + h * FABytes + row * 128;
-                    *reinterpret_cast<uint4 *>(arow + (((c0) ^ (row & 7)) << 4)) =
-                        make_uint4(packed[h][0], packed[h][1], packed[h][2], packed[h][3]);
-                    *reinterpret_cast<uint4 *>(arow + (((c0 + 1) ^ (row & 7)) << 4)) =
-                        make_uint4(packed[h][4], packed[h][5], packed[h][6], packed[h][7]);
+                    const uint32_t arow = a_row + (uint32_t)(h * FABytes);
+                    sts_v4(arow + sw0, packed[h][0], packed[h][1], packed[h][2], packed[h][3]);
+                    sts_v4(arow + sw1, packed[h][4], packed[h][5], packed[h][6], packed[h][7]);
+                }
+                // targets >= 2 (about 3 % of a single-cell matrix): lgamma / digamma differences,
+                // one trip per flagged element of this row; the fp16 gradient is patched in place
+                if (fixups) {
+                    // two flagged elements per trip: their (independent) latency chains overlap
+                    auto fix = [&](int b, bool on) {
+                        const int hi = b >> 4;
+                        const int j = 2 * ((hi ? 30 : 14) - b) + hi;       // element of the chunk
+                        const uint32_t off = ((j & 8) ? sw1 : sw0) + (uint32_t)((j & 7) << 1);
+                        const uint16_t bits = lds_u16(trow + off);
+                        const float xj = T_HALF ? __half2float(__ushort_as_half(bits)) : (float)bits;
+                        float extra = 0.f;
+                        if (Lik<KIND>::NB) {
+                            const float rj = __half2float(__ushort_as_half(
+                                lds_u16(rscr + (uint32_t)((((j >> 3) * 32 + lane) * 16) + ((j & 7) << 1)))));
+                            const uint32_t gp = a_row + (uint32_t)((P - 1) * FABytes) + off;
+                            const float g_old = __half2float(__ushort_as_half(lds_u16(gp)));
+                            float D, Pd;
+                            lgamma_diff_ge2(rj, xj, D, Pd);
+                            extra = D;
+                            if (on) sts_u16(gp, __half_as_ushort(__float2half_rn(fmaf(rj * Pd, gs_row, g_old))));
+                        }
+                        if (!p.has_const) extra -= lgammaf(1.f + xj);
+                        accA += on ? extra : 0.f;
+                    };
+                    while (flags) {
+                        const int b0 = 31 - __clz(flags);
+                        flags &= ~(1u << b0);
+                        const bool two = flags != 0;
+                        const int b1 = two ? 31 - __clz(flags) : b0;
+                        flags &= ~(1u << b1);
+                        fix(b0, true);
+                        fix(b1, two);
+                    }
                 }
             }
             // S(n) and t(n) are in registers / consumed: release them
@@ -311,15 +488,18 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
             }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(A_FULL));
+            if (lane == 0 && (e == 0 || e == EW - 1)) FUSED_DBG(n, e == 0 ? 8 : 11);
+            if (lane == 0) mbar_arrive(bar(A_FULL + ab));
         }
-        // ---- log p partial of this gene range: combine the two halves, fixed order ----
-        s_part[ej * 128 + row] = acc;
+        // ---- log p partial of this gene range: combine the warps of a quadrant, fixed order ----
+        // (the partials reuse the first 128 bytes of each warp's own total_count chunk)
+        __syncwarp();
+        sts_f32(rscr + (uint32_t)lane * 4u, fmaf(-kLn2, accB, accA));
         bar_sync_n(1, 32 * EW);
         if (ej == 0 && grow < p.M) {
             float tot = 0.f;
 #pragma unroll
-            for (int j = 0; j < EJ; ++j) tot += s_part[j * 128 + row];
+            for (int j = 0; j < EJ; ++j) tot += reinterpret_cast<const float *>(sR + (j * 4 + q) * FRBytes)[lane];
             p.logp_part[(int64_t)gs * p.part_stride + grow] = tot;
         }
         // ---- dd partial: TMEM -> staging smem (the t stages) -> TMA reduce-add ----
@@ -389,6 +569,8 @@ static inline int make_map_u16(CUtensorMap *map, const void *base, int64_t rows,
     return 0;
 }
 
+static long long *g_fused_dbg = nullptr;
+
 struct FusedPlan {
     int row_tiles, n_tiles, gsplit, tiles_per_cta;
 };
@@ -404,8 +586,8 @@ static FusedPlan fused_plan(int M, int G) {
     return f;
 }
 
-template <int KIND>
-static int launch_fused(const void *d16, const void *w16, const void *t16, int64_t ldt, int t_is_half, int t_rows,
+template <int KIND, bool T_HALF>
+static int launch_fused_t(const void *d16, const void *w16, const void *t16, int64_t ldt, int t_rows,
                         int M, int G,
                         int64_t head_stride, const float *go, float go_scalar, float scale, void *da16,
                         float *dd, int64_t lddd, int dd_cols, float *logp_part, const float *row_const,
@@ -428,18 +610,18 @@ static int launch_fused(const void *d16, const void *w16, const void *t16, int64
     p.go = go; p.go_scalar = go_scalar; p.scale = scale; p.inv_scale = 1.f / scale;
     p.logp_part = logp_part;
     p.has_const = row_const != nullptr;
-    p.t_is_half = t_is_half;
+    p.dbg = g_fused_dbg;
     constexpr int smem = fused_smem_bytes(P);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(heads_fused_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             smem);
+        cudaError_t e = cudaFuncSetAttribute(heads_fused_kernel<KIND, T_HALF>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         SCVAE_CHECK_ARG(e == cudaSuccess, "heads_fused: cannot set smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
     cudaError_t e = cudaMemsetAsync(dd, 0, (size_t)M * lddd * sizeof(float), s);
     SCVAE_CHECK_ARG(e == cudaSuccess, "heads_fused: memset failed: %s", cudaGetErrorString(e));
-    heads_fused_kernel<KIND><<<f.row_tiles * f.gsplit, fused_threads(P), smem, s>>>(tmD, tmW, tmT, tmDA, tmDD, p);
+    heads_fused_kernel<KIND, T_HALF><<<f.row_tiles * f.gsplit, fused_threads(P), smem, s>>>(tmD, tmW, tmT, tmDA, tmDD, p);
     SCVAE_CHECK_LAUNCH("heads_fused");
     fused_finish_kernel<<<(M + 255) / 256, 256, 0, s>>>(logp_part, p.part_stride, f.gsplit, M, row_const, t_rows,
                                                         logp);
@@ -447,9 +629,25 @@ static int launch_fused(const void *d16, const void *w16, const void *t16, int64
     return 0;
 }
 
+template <int KIND>
+static int launch_fused(const void *d16, const void *w16, const void *t16, int64_t ldt, int t_is_half, int t_rows,
+                        int M, int G, int64_t head_stride, const float *go, float go_scalar, float scale,
+                        void *da16, float *dd, int64_t lddd, int dd_cols, float *logp_part,
+                        const float *row_const, float *logp, cudaStream_t s) {
+    if (t_is_half)
+        return launch_fused_t<KIND, true>(d16, w16, t16, ldt, t_rows, M, G, head_stride, go, go_scalar, scale, da16,
+                                          dd, lddd, dd_cols, logp_part, row_const, logp, s);
+    return launch_fused_t<KIND, false>(d16, w16, t16, ldt, t_rows, M, G, head_stride, go, go_scalar, scale, da16, dd,
+                                       lddd, dd_cols, logp_part, row_const, logp, s);
+}
+
 }  // namespace scvae
 
 using namespace scvae;
+
+// development aid (not part of the public header): device buffer of 40 x 16 int64 that receives
+// the clock64 timeline of CTA 0 of subsequent launches; NULL switches it off
+extern "C" void scvae_heads_fused_debug(void *buf) { g_fused_dbg = (long long *)buf; }
 
 extern "C" int64_t scvae_heads_fused_workspace_floats(int M, int G) {
     if (M <= 0 || G <= 0) return 0;
