@@ -107,11 +107,14 @@ struct FusedParams {
     float *logp_part;
     long long *dbg;           // development aid: per-tile clock64 timeline of CTA 0 (NULL in production)
 };
+#ifdef SCVAE_FUSED_TIMELINE      // tools/fused_bench.py --timeline (build with -DSCVAE_FUSED_TIMELINE)
 #define FUSED_DBG(n, ev)                                                        \
     do {                                                                        \
         if (p.dbg && blockIdx.x == 0 && (n) < 40) p.dbg[(n) * 16 + (ev)] = clock64(); \
     } while (0)
-
+#else
+#define FUSED_DBG(n, ev) do { } while (0)
+#endif
 // A 16-gene chunk in which a clip of the reference is active (fused_math.cuh): exact masked math
 // of likelihood_math.cuh, out of line (rare; keeps the register budget of the fast path small).
 struct FusedSlowIn {
@@ -160,6 +163,7 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
     constexpr int P = Lik<KIND>::P;
     constexpr int EW = fused_epi_warps(P);       // epilogue warps
     constexpr int EJ = EW / 4;                   // epilogue warps per TMEM lane quadrant
+    static_assert(EJ == 1 || EJ == 2 || EJ == 4, "epilogue warps per quadrant must divide the 4 chunks of a tile");
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sD = smem;
@@ -354,8 +358,7 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
             const uint32_t a_row = a_row0 + (uint32_t)(ab * P * FABytes);
             bool first_write = true;
 #pragma unroll 1
-            for (int sub = 0; sub < 4; ++sub) {
-                if ((n * 4 + sub) % EJ != ej) continue;        // dealt round-robin over tiles
+            for (int sub = ej; sub < 4; sub += EJ) {           // EJ divides 4: same chunks every tile
                 const int gc = sub * 16;                       // first gene of this 16-gene chunk
                 uint32_t sv[3][16];
 #pragma unroll
@@ -447,35 +450,51 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
                 // targets >= 2 (about 3 % of a single-cell matrix): lgamma / digamma differences,
                 // one trip per flagged element of this row; the fp16 gradient is patched in place
                 if (fixups) {
-                    // two flagged elements per trip: their (independent) latency chains overlap
-                    auto fix = [&](int b, bool on) {
-                        const int hi = b >> 4;
-                        const int j = 2 * ((hi ? 30 : 14) - b) + hi;       // element of the chunk
-                        const uint32_t off = ((j & 8) ? sw1 : sw0) + (uint32_t)((j & 7) << 1);
-                        const uint16_t bits = lds_u16(trow + off);
-                        const float xj = T_HALF ? __half2float(__ushort_as_half(bits)) : (float)bits;
+                    // two flagged elements per trip, straight-line: the two latency chains overlap
+                    while (flags) {
+                        int b[2];
+                        b[0] = 31 - __clz(flags);
+                        flags &= ~(1u << b[0]);
+                        const bool two = flags != 0;
+                        b[1] = two ? 31 - __clz(flags) : b[0];
+                        flags &= ~(1u << b[1]);
+                        uint32_t off[2];
+                        float xj[2], rj[2], g_old[2], D[2], Pd[2];
+                        int jj[2];
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const int hi = b[k] >> 4;
+                            jj[k] = 2 * ((hi ? 30 : 14) - b[k]) + hi;      // element of the chunk
+                            off[k] = ((jj[k] & 8) ? sw1 : sw0) + (uint32_t)((jj[k] & 7) << 1);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const uint16_t bits = lds_u16(trow + off[k]);
+                            xj[k] = T_HALF ? __half2float(__ushort_as_half(bits)) : (float)bits;
+                            if (Lik<KIND>::NB) {
+                                rj[k] = __half2float(__ushort_as_half(lds_u16(
+                                    rscr + (uint32_t)((((jj[k] >> 3) * 32 + lane) * 16) + ((jj[k] & 7) << 1)))));
+                                g_old[k] = __half2float(
+                                    __ushort_as_half(lds_u16(a_row + (uint32_t)((P - 1) * FABytes) + off[k])));
+                            }
+                        }
                         float extra = 0.f;
                         if (Lik<KIND>::NB) {
-                            const float rj = __half2float(__ushort_as_half(
-                                lds_u16(rscr + (uint32_t)((((j >> 3) * 32 + lane) * 16) + ((j & 7) << 1)))));
-                            const uint32_t gp = a_row + (uint32_t)((P - 1) * FABytes) + off;
-                            const float g_old = __half2float(__ushort_as_half(lds_u16(gp)));
-                            float D, Pd;
-                            lgamma_diff_ge2(rj, xj, D, Pd);
-                            extra = D;
-                            if (on) sts_u16(gp, __half_as_ushort(__float2half_rn(fmaf(rj * Pd, gs_row, g_old))));
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) lgamma_diff_prod(rj[k], xj[k], D[k], Pd[k]);
+                            if (fmaxf(xj[0], xj[1]) > (float)kProdMax) {      // rare: large counts
+#pragma unroll
+                                for (int k = 0; k < 2; ++k) lgamma_diff_ge2(rj[k], xj[k], D[k], Pd[k]);
+                            }
+                            extra = D[0] + (two ? D[1] : 0.f);
+                            sts_u16(a_row + (uint32_t)((P - 1) * FABytes) + off[0],
+                                    __half_as_ushort(__float2half_rn(fmaf(rj[0] * Pd[0], gs_row, g_old[0]))));
+                            if (two)
+                                sts_u16(a_row + (uint32_t)((P - 1) * FABytes) + off[1],
+                                        __half_as_ushort(__float2half_rn(fmaf(rj[1] * Pd[1], gs_row, g_old[1]))));
                         }
-                        if (!p.has_const) extra -= lgammaf(1.f + xj);
-                        accA += on ? extra : 0.f;
-                    };
-                    while (flags) {
-                        const int b0 = 31 - __clz(flags);
-                        flags &= ~(1u << b0);
-                        const bool two = flags != 0;
-                        const int b1 = two ? 31 - __clz(flags) : b0;
-                        flags &= ~(1u << b1);
-                        fix(b0, true);
-                        fix(b1, two);
+                        if (!p.has_const) extra -= lgamma1p_ge2(xj[0]) + (two ? lgamma1p_ge2(xj[1]) : 0.f);
+                        accA += extra;
                     }
                 }
             }
