@@ -98,6 +98,10 @@ int scvae_gemm_f16(int layout, int M, int N, int K, const void *A, int64_t lda, 
                    int64_t ldb, float *C, int64_t ldc, int accumulate, float alpha,
                    void *workspace, int64_t workspace_bytes, void *stream);
 int64_t scvae_gemm_f16_workspace_bytes(int layout, int M, int N, int K);
+/* Bounds the persistent CTAs of the calling thread's subsequent tensor-core GEMM launches to
+ * `max_ctas` (0 = one per SM, the default); returns the previous bound.  A caller that runs a
+ * large HBM-bound product on a second stream uses it to leave SMs to the kernels it overlaps. */
+int scvae_gemm_sm_limit(int max_ctas);
 /* dst (rows, ldd) fp16 = scale * src (rows, lds) fp32 for the first `cols` columns, zero in
  * columns [cols, ldd): fp16 operand copies of fp32 master tensors. */
 int scvae_f32_to_f16(const float *src, int64_t lds, int64_t rows, int cols, void *dst,

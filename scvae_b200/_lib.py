@@ -39,6 +39,7 @@ SIGNATURES = {
     "scvae_gemm_f16": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64,
                                c_int, c_f32, c_ptr, c_i64, c_ptr]),
     "scvae_gemm_f16_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int]),
+    "scvae_gemm_sm_limit": (c_int, [c_int]),
     "scvae_f32_to_f16": (c_int, [c_ptr, c_i64, c_i64, c_int, c_ptr, c_i64, c_f32, c_ptr]),
     "scvae_bn_scratch_floats": (c_i64, [c_int, c_int, c_int]),
     "scvae_bn_act_fwd": (c_int, [c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int,

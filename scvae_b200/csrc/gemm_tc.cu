@@ -300,7 +300,11 @@ struct SplitPlan {
     int streamk, units_per_cta, grid;
 };
 
-static int num_sms() {
+// Upper bound on the persistent CTAs of subsequent tensor-core GEMM launches (0 = all SMs): lets
+// the caller leave SMs free for kernels it runs concurrently on another stream.
+static thread_local int g_sm_limit = 0;
+
+static int device_sms() {
     static int sms = 0;
     if (!sms) {
         int dev = 0, n = 0;
@@ -311,6 +315,10 @@ static int num_sms() {
             sms = 148;
     }
     return sms;
+}
+static int num_sms() {
+    const int n = device_sms();
+    return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 // Wave efficiency of `items` equal work items on `sms` persistent CTAs.
@@ -457,6 +465,12 @@ static int launch_gemm(const char *name, int layout, int M, int N, int K, const 
 }  // namespace scvae
 
 using namespace scvae;
+
+extern "C" int scvae_gemm_sm_limit(int max_ctas) {
+    const int prev = g_sm_limit;
+    g_sm_limit = max_ctas > 0 ? max_ctas : 0;
+    return prev;
+}
 
 extern "C" int64_t scvae_gemm_tf32_workspace_bytes(int layout, int M, int N, int K) {
     (void)layout;

@@ -111,6 +111,9 @@ class VAEEngine:
         self.world_size = 1
         self._all_reduce = None
         self._plans = {}
+        self._side = None                  # second stream: head weight gradients / shadow copies
+        self.overlap_streams = True
+        self.side_gemm_ctas = int(__import__("os").environ.get("SCVAE_SIDE_GEMM_CTAS", "116"))
 
         n = len(self.hidden_sizes)
         self.enc = []
@@ -350,6 +353,53 @@ class VAEEngine:
         p.d_encY = [zeros(B, round4(l.n_out)) for l in self.enc]
         p.bwd_ready = True
 
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
+    def _refresh_shadows(self, p, M):
+        """fp16 copies of the first encoder weight and of the head weights for this step.
+        They depend on the parameters only, so they run on the side stream beside the
+        densify / noise kernels that precede the first product; the main stream joins here."""
+        self._plan_fused(p, M)
+        main = torch.cuda.current_stream()
+        use_side = self.overlap_streams and getattr(p, "shadow_fork", None) is not None
+        if use_side:
+            side = self._side_stream()
+            side.wait_event(p.shadow_fork)
+            ctx = torch.cuda.stream(side)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            if self.enc:
+                l = self.enc[0]
+                if getattr(p, "W1_16", None) is None:
+                    p.W1_16 = torch.zeros(l.n_out, self._x16(p).shape[1], dtype=torch.float16,
+                                          device=self.device)
+                K.f32_to_f16(l.w, l.n_in + 1, p.W1_16)
+            l = self.head
+            for h in range(self.P):
+                K.f32_to_f16(l.w[h * self.Gn:(h + 1) * self.Gn], l.in_p,
+                             p.W16[h * self.Gh:h * self.Gh + self.Gn])
+            if use_side:
+                p.shadow_join.record(side)
+        if use_side:
+            main.wait_event(p.shadow_join)
+            p.shadow_fork = None
+
+    def fork_shadows(self, p):
+        """Call on the main stream BEFORE enqueueing the minibatch assembly of a training step:
+        marks the point after which the weight shadow copies may start on the side stream."""
+        if not self.overlap_streams:
+            return
+        if getattr(p, "shadow_join", None) is None:
+            p.shadow_join = torch.cuda.Event()
+            p.shadow_fork_ev = torch.cuda.Event()
+        p.shadow_fork_ev.record(torch.cuda.current_stream())
+        p.shadow_fork = p.shadow_fork_ev
+
     def _use_tc(self, M, N, Kd):
         """tcgen05 kernel for every product with a long reduction or a large tile count; the
         exact-fp32 FFMA kernel keeps the tiny ones (e.g. 100 x 100 x 101 at minibatch 100)."""
@@ -439,10 +489,7 @@ class VAEEngine:
         for i, l in enumerate(self.enc):
             if i == 0 and use16:
                 # (cells x genes) operand in fp16: half the HBM traffic of the tf32 path
-                if getattr(p, "W1_16", None) is None:
-                    p.W1_16 = torch.zeros(l.n_out, p.X16.shape[1], dtype=torch.float16,
-                                          device=self.device)
-                K.f32_to_f16(l.w, l.n_in + 1, p.W1_16)
+                self._refresh_shadows(p, M)
                 self._gemm16(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, p.X16, p.W1_16, p.encY[i])
             else:
                 self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, h, l.w, p.encY[i])
@@ -478,9 +525,8 @@ class VAEEngine:
             self._plan_backward(p)
             self._plan_fused(p, M)
             K.f32_to_f16(d, l.in_p, p.D16)
-            for h in range(self.P):
-                K.f32_to_f16(l.w[h * self.Gn:(h + 1) * self.Gn], l.in_p,
-                             p.W16[h * self.Gh:h * self.Gh + self.Gn])
+            if not self.enc:
+                self._refresh_shadows(p, M)
             p.fused_scale = 2.0 ** round(math.log2(max(S * B, 16) / 16.0))
             dd = p.d_decH[-1] if self.dec else p.dZ
             t16 = p.X16 if p.t16_is_x16 else p.T16
@@ -533,12 +579,39 @@ class VAEEngine:
         l = self.head
         d_in = p.decH[-1] if self.dec else p.Z
         dd_in = p.d_decH[-1] if self.dec else p.dZ
+        p.head_join = None
         if p.fused_done:
-            # dd came out of the fused kernel; dW = da^T d from the fp16 da (per head)
-            for h in range(self.P):
-                K.gemm_f16(K.GEMM_TN, self.Gn, l.in_p, M,
-                           p.dA16[:, h * self.Gh:h * self.Gh + self.Gn], p.D16,
-                           l.dw[h * self.Gn:(h + 1) * self.Gn], alpha=1.0 / p.fused_scale)
+            # dd came out of the fused kernel; dW = da^T d from the fp16 da (per head).  These
+            # two HBM-bound products (and, data-parallel, the all-reduce of their 2/3 of the
+            # gradient buffer) are independent of the rest of the backward chain: they run on
+            # the side stream beside the latency-bound decoder / encoder backward.
+            main = torch.cuda.current_stream()
+            if self.overlap_streams:
+                if getattr(p, "head_ev", None) is None:
+                    p.head_ev = (torch.cuda.Event(), torch.cuda.Event())
+                side = self._side_stream()
+                p.head_ev[0].record(main)
+                side.wait_event(p.head_ev[0])
+                ctx = torch.cuda.stream(side)
+            else:
+                import contextlib
+                ctx = contextlib.nullcontext()
+            with ctx:
+                # leave some SMs to the small kernels of the main stream
+                old = K.gemm_sm_limit(self.side_gemm_ctas) if self.overlap_streams else 0
+                for h in range(self.P):
+                    K.gemm_f16(K.GEMM_TN, self.Gn, l.in_p, M,
+                               p.dA16[:, h * self.Gh:h * self.Gh + self.Gn], p.D16,
+                               l.dw[h * self.Gn:(h + 1) * self.Gn], alpha=1.0 / p.fused_scale)
+                if self.overlap_streams:
+                    K.gemm_sm_limit(old)
+                if self.overlap_streams:
+                    if self._all_reduce is not None:
+                        off = self.store.offsets[l.name + "/W"][0]
+                        self._all_reduce(self.store.grad[off:])
+                        p.head_reduced_from = off
+                    p.head_ev[1].record(side)
+                    p.head_join = p.head_ev[1]
         else:
             # wgrad (bias gradient = the augmented ones column) and dgrad of the heads
             self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, M, p.dA, d_in, l.dw)
@@ -582,12 +655,19 @@ class VAEEngine:
                 self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.d_encY[i], h_in, l.dw)
             if i > 0:
                 self._gemm(p, K.GEMM_NN, B, l.n_in, l.n_out, p.d_encY[i], l.w, p.d_encH[i - 1])
+        self._reduce_upto = None
+        if p.head_join is not None:
+            torch.cuda.current_stream().wait_event(p.head_join)
+            if self._all_reduce is not None:
+                self._reduce_upto = p.head_reduced_from   # the tail is already summed
 
     def optimiser_step(self, learning_rate):
         """[all-reduce] -> clip to [-1, 1] -> TF Adam (VAE:2742-2759), one fused launch."""
         s = self.store
         if self._all_reduce is not None:
-            self._all_reduce(s.grad)
+            upto = getattr(self, "_reduce_upto", None)
+            self._all_reduce(s.grad if upto is None else s.grad[:upto])
+            self._reduce_upto = None
         K.adam_clip_step(s.param, s.grad, s.m, s.v, s.step, learning_rate, ADAM_BETA1,
                          ADAM_BETA2, ADAM_EPSILON, GRADIENT_CLIP, 1.0 / self.world_size)
         K.step_advance(s.step)

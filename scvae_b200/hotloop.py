@@ -126,6 +126,8 @@ class TrainLoop:
     # the captured body: everything that is identical from step to step
     def _body(self, src, lr, w):
         eng, p = self.engine, self.plan
+        if self.R == 1 and hasattr(eng, "fork_shadows"):
+            eng.fork_shadows(p)
         if isinstance(src, ResidentCSR):
             eng.set_batch_csr(p, src.indptr, src.indices, src.values, self.rows,
                               u16_ok=src.u16_ok, f16_exact=src.f16_exact, train16=self.R == 1)

@@ -111,6 +111,11 @@ def gemm_f16(layout, M, N, K, A, B, C, accumulate=False, alpha=1.0, workspace=No
                                   _stream()), "gemm_f16")
 
 
+def gemm_sm_limit(max_ctas):
+    """Bound the persistent CTAs of subsequent tensor-core GEMMs (0 = all SMs); returns the old bound."""
+    return int(_lib.load().scvae_gemm_sm_limit(int(max_ctas)))
+
+
 def gemm_f16_workspace_bytes(layout, M, N, K):
     return int(_lib.load().scvae_gemm_f16_workspace_bytes(layout, M, N, K))
 
