@@ -567,7 +567,7 @@ class VAEEngine:
         self._gemm(p, K.GEMM_NT, rows, l.n_out, l.n_in + 1, d, l.w, p.A[:rows])
 
     # ------------------------------------------------------------------ backward -----------
-    def backward(self, p, R, S, warm_up_weight=1.0, dA_ready=False):
+    def backward(self, p, R, S, warm_up_weight=1.0, dA_ready=False, defer_join=False):
         """Gradients of -lower_bound_weighted w.r.t. every parameter into the flat grad buffer."""
         self._plan_backward(p)
         B, M = p.B, p.M
@@ -656,27 +656,49 @@ class VAEEngine:
             if i > 0:
                 self._gemm(p, K.GEMM_NN, B, l.n_in, l.n_out, p.d_encY[i], l.w, p.d_encH[i - 1])
         self._reduce_upto = None
+        self._side_tail = None
         if p.head_join is not None:
-            torch.cuda.current_stream().wait_event(p.head_join)
+            off = self.store.offsets[self.head.name + "/W"][0]
             if self._all_reduce is not None:
-                self._reduce_upto = p.head_reduced_from   # the tail is already summed
+                self._reduce_upto = off                   # the tail is already summed (side stream)
+            if defer_join:
+                self._side_tail = (p, off)                # optimiser_step finishes the tail there
+            else:
+                torch.cuda.current_stream().wait_event(p.head_join)
+
+    def _adam(self, lo, hi, learning_rate):
+        s = self.store
+        K.adam_clip_step(s.param[lo:hi], s.grad[lo:hi], s.m[lo:hi], s.v[lo:hi], s.step,
+                         learning_rate, ADAM_BETA1, ADAM_BETA2, ADAM_EPSILON, GRADIENT_CLIP,
+                         1.0 / self.world_size)
 
     def optimiser_step(self, learning_rate):
-        """[all-reduce] -> clip to [-1, 1] -> TF Adam (VAE:2742-2759), one fused launch."""
+        """[all-reduce] -> clip to [-1, 1] -> TF Adam (VAE:2742-2759).  One fused launch over the
+        flat buffers; when the head gradients were produced on the side stream (train_step) the
+        head slice (2/3 of the parameters) is updated there, beside the rest of the backward."""
         s = self.store
+        tail = getattr(self, "_side_tail", None)
+        self._side_tail = None
+        upto = getattr(self, "_reduce_upto", None)
+        self._reduce_upto = None
+        if tail is not None:
+            p, off = tail
+            side = self._side_stream()
+            with torch.cuda.stream(side):
+                self._adam(off, s.total, learning_rate)
+                p.head_ev[1].record(side)
         if self._all_reduce is not None:
-            upto = getattr(self, "_reduce_upto", None)
             self._all_reduce(s.grad if upto is None else s.grad[:upto])
-            self._reduce_upto = None
-        K.adam_clip_step(s.param, s.grad, s.m, s.v, s.step, learning_rate, ADAM_BETA1,
-                         ADAM_BETA2, ADAM_EPSILON, GRADIENT_CLIP, 1.0 / self.world_size)
+        self._adam(0, s.total if tail is None else tail[1], learning_rate)
+        if tail is not None:
+            torch.cuda.current_stream().wait_event(tail[0].head_ev[1])
         K.step_advance(s.step)
 
     def train_step(self, p, R, S, learning_rate, warm_up_weight=1.0):
         """One ``session.run([optimiser, lower_bound])`` (VAE:1026-1029)."""
         if R == 1:
             self.forward(p, True, R, S, warm_up_weight, fused_backward=True)
-            self.backward(p, R, S, warm_up_weight, dA_ready=True)
+            self.backward(p, R, S, warm_up_weight, dA_ready=True, defer_join=True)
         else:
             self.forward(p, True, R, S, warm_up_weight, want_go=True)
             self.backward(p, R, S, warm_up_weight)
