@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--likelihood", default="negative binomial")
     ap.add_argument("--minibatch", type=int, default=4096, help="cells per step per GPU")
     ap.add_argument("--density", type=float, default=0.07)
+    ap.add_argument("--exchange", default=None, choices=["p2p", "nccl"],
+                    help="N > 1: fused peer-memory exchange + optimiser (default) or NCCL all-reduce")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -257,8 +259,12 @@ def run_b200(args):
     B = min(args.minibatch, args.cells)
     data = ResidentCSR(csr, dev)
     eng = VAEEngine(args.genes, args.latent, args.hidden, args.likelihood, device=dev, seed=0)
+    exchange = "none"
     if world > 1:
-        eng.set_data_parallel(world, lambda g: dist.all_reduce(g))
+        from scvae_b200 import distributed as D
+        D.attach(eng, exchange=args.exchange)
+        exchange = "p2p (fused reduce-scatter + Adam + all-gather over NVLink peer memory)" \
+            if eng._peer is not None else "nccl all-reduce"
     loop = TrainLoop(eng, B, seed=1 + rank, use_graph=not args.no_graph)
     n_batches = args.cells // B
     perm = torch.from_numpy(numpy.random.RandomState(2).permutation(args.cells)).to(dev)
@@ -438,6 +444,7 @@ def run_b200(args):
             "lower_bound_last_step": bound[0],
             "cuda_graph": bool(saved),
         }
+        line["config"]["gradient_exchange"] = exchange
         print(json.dumps(line), flush=True)
     if world > 1:
         # CUDA graphs that captured NCCL kernels must die before the communicator does; guard

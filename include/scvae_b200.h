@@ -215,6 +215,22 @@ int scvae_adam_clip_step(float *param, const float *grad, float *m, float *v, in
                          float epsilon, float clip, float grad_scale, void *stream);
 int scvae_step_advance(int64_t *step, void *stream);
 
+/* ---- e: data-parallel exchange fused with the optimiser ----------------------
+ * Replaces  all-reduce(grad) ; scvae_adam_clip_step(all parameters)  on W ranks of one NVLink
+ * domain by ONE kernel per rank: reduce-scatter of the flat gradient range over peer memory
+ * (P2P loads, fixed summation order), clip + TF-Adam on this rank's 1/W slice (only that slice
+ * of m / v is touched), all-gather of the updated parameters (P2P stores).  grad_ptrs /
+ * param_ptrs / flag_ptrs are HOST arrays of `world` peer-mapped device pointers to the start of
+ * the range in every rank's gradient / parameter buffer and to every rank's flag block (32
+ * zero-initialised uint32 per exchange channel).  ctl: 4 zero-initialised device uint32 owned
+ * by the channel ([2] != 0 after a peer timed out).  Two flag barriers per launch; no host
+ * synchronisation; CUDA-graph capturable.  n % 4 == 0. */
+int scvae_dp_reduce_adam(int world, int rank, const void *const *grad_ptrs,
+                         void *const *param_ptrs, void *const *flag_ptrs, float *m, float *v,
+                         int64_t n, const int64_t *step, float lr, float beta1, float beta2,
+                         float epsilon, float clip, float grad_scale, void *ctl, int max_ctas,
+                         void *stream);
+
 /* ---- a9/a10: Gaussian-mixture VAE pieces  (GMVAE:2788-3434) ------------------------------
  * The K cluster passes are K consecutive row groups of one tall matrix, rows ordered
  * (k, sample, cell); dense layers / batch norm (groups = K) / likelihood are shared with the VAE.

@@ -64,6 +64,8 @@ SIGNATURES = {
     "scvae_adam_clip_step": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_f32, c_f32,
                                      c_f32, c_f32, c_f32, c_f32, c_ptr]),
     "scvae_step_advance": (c_int, [c_ptr, c_ptr]),
+    "scvae_dp_reduce_adam": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr,
+                                     c_f32, c_f32, c_f32, c_f32, c_f32, c_f32, c_ptr, c_int, c_ptr]),
     "scvae_group_offset_fwd": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_i64,
                                        c_ptr]),
     "scvae_group_offset_bwd": (c_int, [c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_i64, c_ptr, c_i64,

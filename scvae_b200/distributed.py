@@ -77,10 +77,98 @@ def all_reduce_sum_(flat):
     return flat
 
 
-def attach(engine):
-    """Switch an engine to data-parallel mode if a process group is active."""
-    if is_active():
-        engine.set_data_parallel(world_size(), all_reduce_sum_)
+class PeerExchange:
+    """Gradient exchange over peer memory, fused with the optimiser (``scvae_dp_reduce_adam``).
+
+    The flat parameter and gradient buffers of the engine are moved into symmetric memory
+    (``torch.distributed._symmetric_memory``: every rank maps every peer's buffer over NVLink);
+    one kernel per rank and exchange channel then sums its 1/W slice of the gradient from all
+    peers, applies clip + Adam to that slice and stores the new parameters into every replica.
+    Only this rank's slice of the Adam slots is live; ``gather_slots`` rebuilds the full slots
+    (checkpoints).  NCCL remains the transport for set-up collectives and for the plain
+    all-reduce mode (``set_data_parallel(..., all_reduce)``)."""
+
+    CHANNELS = 2           # main stream / side stream of the step engine
+    FLAGS_PER_CHANNEL = 32
+
+    def __init__(self, engine, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        store, dev = engine.store, engine.device
+        n = store.total
+        self.param = symm_mem.empty(n, dtype=torch.float32, device=dev)
+        self.grad = symm_mem.empty(n, dtype=torch.float32, device=dev)
+        self.flags = symm_mem.empty(self.CHANNELS * self.FLAGS_PER_CHANNEL, dtype=torch.int32,
+                                    device=dev)
+        self.param.copy_(store.param)
+        self.grad.zero_()
+        self.flags.zero_()
+        self.h_param = symm_mem.rendezvous(self.param, group)
+        self.h_grad = symm_mem.rendezvous(self.grad, group)
+        self.h_flags = symm_mem.rendezvous(self.flags, group)
+        self.param_ptrs = [int(x) for x in self.h_param.buffer_ptrs]
+        self.grad_ptrs = [int(x) for x in self.h_grad.buffer_ptrs]
+        self.flag_ptrs = [int(x) for x in self.h_flags.buffer_ptrs]
+        self.ctl = torch.zeros(self.CHANNELS * 4, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)                    # every rank's buffers are initialised
+        engine.rebind_flat_buffers(self.param, self.grad)
+        self.engine = engine
+
+    def reduce_adam(self, lo, hi, learning_rate, channel, max_ctas=0):
+        """Exchange + optimiser update of the flat range [lo, hi) on the current stream."""
+        from . import kernels as K
+        from .engine import ADAM_BETA1, ADAM_BETA2, ADAM_EPSILON, GRADIENT_CLIP
+        s = self.engine.store
+        fo = channel * self.FLAGS_PER_CHANNEL * 4
+        K.dp_reduce_adam(self.world, self.rank, [p + 4 * lo for p in self.grad_ptrs],
+                         [p + 4 * lo for p in self.param_ptrs], [p + fo for p in self.flag_ptrs],
+                         s.m[lo:hi], s.v[lo:hi], hi - lo, s.step, learning_rate, ADAM_BETA1,
+                         ADAM_BETA2, ADAM_EPSILON, GRADIENT_CLIP, 1.0 / self.world,
+                         ctl=self.ctl[channel * 4:channel * 4 + 4], max_ctas=max_ctas)
+
+    def slice_bounds(self, lo, hi, rank_index):
+        """[a, b) of the flat range [lo, hi) owned by ``rank_index`` (as in the kernel)."""
+        n4 = (hi - lo) // 4
+        per = (n4 + self.world - 1) // self.world
+        a = min(rank_index * per, n4)
+        return lo + 4 * a, lo + 4 * min(a + per, n4)
+
+    def gather_slots(self, ranges):
+        """Full Adam slots on every rank (each rank owns one slice per exchanged range)."""
+        s = self.engine.store
+        for buf in (s.m, s.v):
+            full = torch.zeros_like(buf)
+            for lo, hi in ranges:
+                a, b = self.slice_bounds(lo, hi, self.rank)
+                full[a:b] = buf[a:b]
+            dist.all_reduce(full)
+            buf.copy_(full)
+
+    def timed_out(self):
+        return bool(self.ctl.view(self.CHANNELS, 4)[:, 2].any().item())
+
+
+def attach(engine, exchange=None):
+    """Switch an engine to data-parallel mode if a process group is active.  ``exchange``:
+    "p2p" (fused peer-memory exchange + optimiser), "nccl" (flat all-reduce, then the replicated
+    optimiser) or None = p2p when symmetric memory is available on a CUDA engine, else nccl."""
+    if not is_active():
+        return engine
+    exchange = exchange or os.environ.get("SCVAE_DP_EXCHANGE")
+    engine.set_data_parallel(world_size(), all_reduce_sum_)
+    want_p2p = exchange in (None, "p2p") and hasattr(engine, "set_peer_exchange") \
+        and torch.device(engine.device).type == "cuda" and dist.get_backend() == "nccl"
+    if want_p2p:
+        try:
+            engine.set_peer_exchange(PeerExchange(engine))
+        except Exception as exc:          # symmetric memory unavailable: NCCL all-reduce mode
+            if exchange == "p2p":
+                raise
+            if rank() == 0:
+                print("scvae_b200: peer-memory exchange unavailable ({}); using NCCL "
+                      "all-reduce".format(exc))
     return engine
 
 

@@ -138,17 +138,35 @@ class VAEEngine:
         store.allocate()
         self.store = store
         self.state = {}
+        self._peer = None                  # distributed.PeerExchange (fused exchange + optimiser)
+        for layer in self.enc + [self.post] + self.dec + [self.head]:
+            if layer.bn:
+                layer.moving_mean = torch.zeros(layer.n_out, dtype=torch.float32,
+                                                device=self.device)
+                layer.moving_var = torch.ones(layer.n_out, dtype=torch.float32,
+                                              device=self.device)
+        self._bind_views()
+        self.initialise(seed)
+
+    def _bind_views(self):
+        store = self.store
         for layer in self.enc + [self.post] + self.dec + [self.head]:
             layer.w = store.view(store.param, layer.name + "/W")
             layer.dw = store.view(store.grad, layer.name + "/W")
             if layer.bn:
                 layer.beta = store.view(store.param, layer.name + "/beta")
                 layer.dbeta = store.view(store.grad, layer.name + "/beta")
-                layer.moving_mean = torch.zeros(layer.n_out, dtype=torch.float32,
-                                                device=self.device)
-                layer.moving_var = torch.ones(layer.n_out, dtype=torch.float32,
-                                              device=self.device)
-        self.initialise(seed)
+
+    def rebind_flat_buffers(self, param, grad):
+        """Move the flat parameter / gradient buffers (e.g. into symmetric memory); the values
+        must already be in place.  Plans hold no views of them; captured graphs do and must be
+        re-captured (TrainLoop objects created before this call are stale)."""
+        assert param.numel() == self.store.total and grad.numel() == self.store.total
+        self.store.param, self.store.grad = param, grad
+        self._bind_views()
+
+    def set_peer_exchange(self, peer):
+        self._peer = peer
 
     # ------------------------------------------------------------------ parameters ---------
     def _tf_names(self):
@@ -227,7 +245,16 @@ class VAEEngine:
                 out[scope + "/BATCH_NORM/beta"] = layer.dbeta.cpu().clone()
         return out
 
+    def exchanged_ranges(self):
+        """Flat ranges exchanged separately by optimiser_step (peer mode owns a slice of each)."""
+        off = self.store.offsets[self.head.name + "/W"][0]
+        return [(0, off), (off, self.store.total)] if self.fused_heads and self.overlap_streams \
+            else [(0, self.store.total)]
+
     def state_dict(self):
+        if self._peer is not None and self.world_size > 1:
+            self._peer.gather_slots(self._last_ranges if getattr(self, "_last_ranges", None)
+                                    else self.exchanged_ranges())
         sd = {"param": self.store.param.cpu(), "m": self.store.m.cpu(), "v": self.store.v.cpu(),
               "step": self.store.step.cpu()}
         for layer in self.enc + self.dec:
@@ -606,7 +633,7 @@ class VAEEngine:
                 if self.overlap_streams:
                     K.gemm_sm_limit(old)
                 if self.overlap_streams:
-                    if self._all_reduce is not None:
+                    if self._all_reduce is not None and self._peer is None:
                         off = self.store.offsets[l.name + "/W"][0]
                         self._all_reduce(self.store.grad[off:])
                         p.head_reduced_from = off
@@ -659,7 +686,7 @@ class VAEEngine:
         self._side_tail = None
         if p.head_join is not None:
             off = self.store.offsets[self.head.name + "/W"][0]
-            if self._all_reduce is not None:
+            if self._all_reduce is not None and self._peer is None:
                 self._reduce_upto = off                   # the tail is already summed (side stream)
             if defer_join:
                 self._side_tail = (p, off)                # optimiser_step finishes the tail there
@@ -681,15 +708,25 @@ class VAEEngine:
         self._side_tail = None
         upto = getattr(self, "_reduce_upto", None)
         self._reduce_upto = None
+        peer = self._peer if self.world_size > 1 else None
         if tail is not None:
             p, off = tail
             side = self._side_stream()
             with torch.cuda.stream(side):
-                self._adam(off, s.total, learning_rate)
+                if peer is not None:        # exchange + Adam of the head slice in one kernel
+                    peer.reduce_adam(off, s.total, learning_rate, channel=1,
+                                     max_ctas=self.side_gemm_ctas // 2)
+                else:
+                    self._adam(off, s.total, learning_rate)
                 p.head_ev[1].record(side)
-        if self._all_reduce is not None:
-            self._all_reduce(s.grad if upto is None else s.grad[:upto])
-        self._adam(0, s.total if tail is None else tail[1], learning_rate)
+        hi = s.total if tail is None else tail[1]
+        self._last_ranges = [(0, hi)] + ([(hi, s.total)] if tail is not None else [])
+        if peer is not None:
+            peer.reduce_adam(0, hi, learning_rate, channel=0)
+        else:
+            if self._all_reduce is not None:
+                self._all_reduce(s.grad if upto is None else s.grad[:upto])
+            self._adam(0, hi, learning_rate)
         if tail is not None:
             torch.cuda.current_stream().wait_event(tail[0].head_ev[1])
         K.step_advance(s.step)

@@ -226,6 +226,21 @@ def adam_clip_step(param, grad, m, v, step, lr, beta1=0.9, beta2=0.999, epsilon=
                                         float(grad_scale), _stream()), "adam_clip_step")
 
 
+def dp_reduce_adam(world, rank, grad_ptrs, param_ptrs, flag_ptrs, m, v, n, step, lr, beta1=0.9,
+                   beta2=0.999, epsilon=1e-8, clip=1.0, grad_scale=1.0, ctl=None, max_ctas=0):
+    """Fused reduce-scatter -> clip + Adam -> all-gather over peer memory (dp_exchange.cu).
+    ``*_ptrs``: lists of ``world`` integer device addresses (peer-mapped), already offset to the
+    start of the exchanged range; m, v: local tensors starting at the same offset."""
+    import ctypes
+    _f32(m, v)
+    lib = _lib.load()
+    arr = ctypes.c_void_p * world
+    _lib.check(lib.scvae_dp_reduce_adam(world, rank, arr(*grad_ptrs), arr(*param_ptrs),
+                                        arr(*flag_ptrs), _p(m), _p(v), int(n), _p(step), float(lr),
+                                        beta1, beta2, epsilon, clip, float(grad_scale), _p(ctl),
+                                        int(max_ctas), _stream()), "dp_reduce_adam")
+
+
 def step_advance(step):
     lib = _lib.load()
     _lib.check(lib.scvae_step_advance(_p(step), _stream()), "step_advance")

@@ -143,3 +143,20 @@ def test_cli_train_and_evaluate_on_tsv(tmp_path):
                      "-M", models, "--split-data-set"]) == 0
     found = [f for _, _, files in os.walk(models) for f in files]
     assert "checkpoint" in found and any(f.startswith("model.ckpt-2") for f in found)
+
+
+def test_peer_exchange_matches_nccl_on_two_gpus():
+    """Fused peer-memory exchange + optimiser vs NCCL all-reduce + replicated Adam
+    (tools/dp_check.py under torchrun; needs two GPUs on the box)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                        "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+                        "29541", os.path.join(root, "tools", "dp_check.py")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "dp_check OK" in r.stdout, r.stdout[-3000:]
