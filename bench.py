@@ -381,10 +381,14 @@ def run_b200(args):
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": lik_bytes,
                 "launch_ms": lik_ms, "share_of_step": per_step_ms[top] / (elapsed_ms / args.steps),
+                "dram_traffic_frac_of_peak": (traffic / (lik_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "note": ("algorithmic bytes = SURVEY 8d per-(cell,gene) figure of the likelihood "
                          "stage (16-bit targets + P fp32 parameters + P fp32 gradients); the fused "
-                         "kernel keeps the parameters on chip, so its DRAM traffic is far lower "
-                         "and the kernel is FP32/SFU-issue bound" if top == "heads_fused_bwd" else
+                         "kernel keeps the parameters on chip, so its real DRAM traffic (`traffic`) is "
+                         "a third of that: frac is the rate an unfused HBM-bound implementation would "
+                         "have to stream at to match it (it can exceed 1), dram_traffic_frac_of_peak "
+                         "is the share of HBM peak the kernel really uses; its limiter is FP32/MUFU "
+                         "instruction issue (profiles/)" if top == "heads_fused_bwd" else
                          "HBM-bound streaming kernel"),
                 "eager_ms_per_step_by_kernel": {k: round(v, 4) for k, v in per_step_ms.items()}}
     _dbg("kernel timing done")
@@ -437,7 +441,7 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f16 tensor-core operands, f32 accumulate)",
             "data": "synthetic", "config": workload_config(args, B), "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "roofline": roofline, "cpu_baseline": cpu_base,

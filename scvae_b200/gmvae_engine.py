@@ -53,7 +53,7 @@ class GMVAEEngine(VAEEngine):
         self.head_buffer_bytes = int(head_buffer_bytes)
         self.Gn, self.Gp = round4(self.G), aug(self.G)
         self.world_size, self._all_reduce, self._plans = 1, None, {}
-        self._side, self.overlap_streams = None, False   # (VAE engine stream overlap: unused here)
+        self._side, self.overlap_streams, self._peer = None, False, None   # (VAE-engine-only features)
         self.unit_variance = False
         self.nL = 2 * self.L
 

@@ -518,6 +518,10 @@ class VariationalAutoencoder:
                 print("    {} set: {}.".format(subset.kind.capitalize(),
                                                self._result_string(result)))
 
+            # peer-exchange mode keeps one slice of the Adam slots per rank: rebuilding the full
+            # slots for the checkpoint is a collective, so every rank takes part
+            engine_state = engine.state_dict() \
+                if (is_main or getattr(engine, "_peer", None) is not None) else None
             if not is_main:
                 continue
             # early stopping (VAE:1385-1441)
@@ -542,7 +546,7 @@ class VariationalAutoencoder:
 
             # checkpoint: model.ckpt-<epoch> (VAE:1446-1450) and best model (VAE:1456-1474)
             write_checkpoint(log_directory, epoch + 1,
-                             {"engine": engine.state_dict(), "model": self.name,
+                             {"engine": engine_state, "model": self.name,
                               "epoch": epoch + 1})
             if validation_set and results["validation"]["lower_bound"] > lower_bound_valid_maximum:
                 lower_bound_valid_maximum = results["validation"]["lower_bound"]

@@ -402,6 +402,74 @@ def test_heads_fused_bwd(kind, M, G, H, tile):
     assert err <= 3e-3 * dd_ref.abs().max().item(), (kind, err, dd_ref.abs().max().item())
 
 
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("half_targets", [True, False])
+def test_heads_fused_bwd_clipped_heads_and_large_counts(kind, half_targets):
+    """Chunks in which a clip of the reference is active (log heads beyond +-10, logits below
+    log(tiny)) take the masked out-of-line path of the fused kernel; counts above the rising-
+    product range take the Stirling difference; fp16 and uint16 target encodings."""
+    from scvae_b200 import kernels as K
+    rng = numpy.random.RandomState(11)
+    P = len(O.LIKELIHOODS[kind])
+    M, G, H = 256, 512, 40
+    Gh = (G + 63) & ~63
+    dev = _dev()
+    d = numpy.abs(rng.randn(M, H)).astype(numpy.float32)
+    d_aug = numpy.concatenate([d, numpy.ones((M, 1), numpy.float32)], axis=1)
+    w = (rng.randn(P, G, H + 1) * (0.5 / math.sqrt(H))).astype(numpy.float32)
+    genes = numpy.arange(G)
+    w[P - 1, genes % 50 == 0, H] += 13.0       # log head clipped at +10
+    w[P - 1, genes % 50 == 1, H] -= 13.0       # ... and at -10
+    if P > 1:
+        w[0, genes % 50 == 2, H] -= 95.0       # logit below log(float32 tiny)
+    t = _counts(rng, M, G, 0.8)
+    t[:, genes % 7 == 3] *= 40.0               # counts far above the rising-product range
+    t = numpy.minimum(t, 2000.0).astype(numpy.float32)
+    go = (-(0.5 + rng.rand(M)) / M).astype(numpy.float32)
+    scale = 2.0 ** round(math.log2(M / 16.0))
+    d16 = torch.zeros(M, 128, dtype=torch.float16, device=dev)
+    d16[:, :H + 1] = torch.tensor(d_aug).half()
+    w16 = torch.zeros(P * Gh, 128, dtype=torch.float16, device=dev)
+    for h in range(P):
+        w16[h * Gh:h * Gh + G, :H + 1] = torch.tensor(w[h]).half()
+    if half_targets:
+        t16 = torch.zeros(M, Gh, dtype=torch.float16, device=dev)
+        t16[:, :G] = torch.tensor(t).half()
+    else:
+        t16 = torch.zeros(M, Gh, dtype=torch.int16, device=dev)
+        K.f32_to_u16(torch.tensor(t).to(dev), G, t16)
+    rc = torch.lgamma(1.0 + torch.tensor(t, dtype=torch.float64)).sum(dim=1).float().to(dev)
+    da16 = torch.zeros(M, P * Gh, dtype=torch.float16, device=dev)
+    dd = torch.zeros(M, 44, device=dev)
+    logp = torch.zeros(M, device=dev)
+    ws = torch.zeros(K.heads_fused_workspace_floats(M, G), device=dev)
+    K.heads_fused_bwd(K.LIKELIHOOD_KINDS[kind], d16, w16, Gh, t16, M, G, da16, dd, H, logp, ws,
+                      row_const=rc, go=torch.tensor(go).to(dev), scale=scale)
+    torch.cuda.synchronize()
+    d64 = d16[:, :H + 1].cpu().double()
+    w64 = torch.stack([w16[h * Gh:h * Gh + G, :H + 1].cpu().double() for h in range(P)])
+    a64 = [(d64 @ w64[h].t()).requires_grad_(True) for h in range(P)]
+    lp = _oracle_logp(kind, torch.tensor(t, dtype=torch.float64), a64).sum(dim=1)
+    (lp * torch.tensor(go, dtype=torch.float64)).sum().backward()
+    ref = lp.detach().numpy()
+    assert numpy.isfinite(ref).all()
+    assert numpy.abs(logp.cpu().numpy() - ref).max() <= 3e-5 * numpy.abs(ref).max() + 1e-4
+    got_da = da16.cpu().double() / scale
+    for h in range(P):
+        g = a64[h].grad
+        err = (got_da[:, h * Gh:h * Gh + G] - g).abs().max().item()
+        assert err <= 2e-3 * g.abs().max().item(), (kind, h, err)
+    dd_ref = sum(a64[h].grad @ w64[h] for h in range(P))[:, :H]
+    err = (dd[:, :H].cpu().double() - dd_ref).abs().max().item()
+    assert err <= 3e-3 * dd_ref.abs().max().item(), (kind, err)
+    # without the per-row constant the kernel adds -lgamma(1 + x) itself
+    logp2 = torch.zeros(M, device=dev)
+    K.heads_fused_bwd(K.LIKELIHOOD_KINDS[kind], d16, w16, Gh, t16, M, G, da16, dd, H, logp2, ws,
+                      row_const=None, go=torch.tensor(go).to(dev), scale=scale)
+    torch.cuda.synchronize()
+    assert numpy.abs(logp2.cpu().numpy() - ref).max() <= 3e-5 * numpy.abs(ref).max() + 1e-4
+
+
 def test_adam_clip_step():
     from scvae_b200 import kernels as K
     torch.manual_seed(2)
