@@ -346,12 +346,14 @@ def run_b200(args):
     for k in families:
         setattr(K, k, wrap(k))
     loop.use_graph = False
+    overlap_saved, eng.overlap_streams = eng.overlap_streams, False   # serial launches: clean per-kernel times
     n_eager = min(args.steps, 10)
     for i in range(n_eager):
         step(args.warmup + args.steps + i)
     torch.cuda.synchronize()
     for k in families:
         setattr(K, k, originals[k])
+    eng.overlap_streams = overlap_saved
     loop.use_graph = saved
     per_step_ms = {k: sum(s_.elapsed_time(e_) for s_, e_ in v) / n_eager for k, v in evs.items() if v}
     launches = {k: len(v) / n_eager for k, v in evs.items() if v}

@@ -106,7 +106,9 @@ csr_densify_kernel(const int64_t *__restrict__ indptr, const IdxT *__restrict__ 
 // 16-bit outputs only (the fused training path): the whole row is assembled in shared memory as
 // uint16 counts in ONE pass (zero, scatter, write), then written as fp16 (x16, augmented) and/or
 // uint16 (t16).  Dynamic shared memory: 2 * row_width bytes.
-template <typename IdxT, typename ValT>
+// X16_DIRECT (x16 only, the common case: counts <= 2048 serve as fp16 input AND targets): the row
+// is assembled as fp16 bit patterns, so the write-out is a plain 128-bit copy.
+template <typename IdxT, typename ValT, bool X16_DIRECT>
 __global__ void __launch_bounds__(256)
 csr_densify16_kernel(const int64_t *__restrict__ indptr, const IdxT *__restrict__ indices,
                      const ValT *__restrict__ values, const int64_t *__restrict__ rows, int G,
@@ -143,15 +145,22 @@ csr_densify16_kernel(const int64_t *__restrict__ indptr, const IdxT *__restrict_
         for (int k = 0; k < 4; ++k) {
             const int c = cc[k];
             const float v = vv[k];
-            if (c >= c_lo && c < c_hi && c < G) row16[c - c_lo] = (uint16_t)fminf(fmaxf(v, 0.f), 65535.f);
+            if (c >= c_lo && c < c_hi && c < G)
+                row16[c - c_lo] = X16_DIRECT ? __half_as_ushort(__float2half_rn(v))
+                                             : (uint16_t)fminf(fmaxf(v, 0.f), 65535.f);
             // the per-cell constant sum_g lgamma(1 + x) is accumulated by part 0 over the whole row
             if (row_const && blockIdx.y == 0 && c >= 0 && c < G && v > 0.f) acc += lgammaf(1.f + v);
         }
     }
+    if (X16_DIRECT && threadIdx.x == 0 && G >= c_lo && G < c_hi) row16[G - c_lo] = 0x3C00;   // ones column
     __syncthreads();
     for (int i = threadIdx.x; i < g8_hi - g8_lo; i += blockDim.x) {
         const int c = (g8_lo + i) << 3;
         const uint4 pk = row4[i];
+        if (X16_DIRECT) {
+            if (c < ldx16) *reinterpret_cast<uint4 *>(x16 + (int64_t)b * ldx16 + c) = pk;
+            continue;
+        }
         if (t16 && c < ldt16) *reinterpret_cast<uint4 *>(t16 + (int64_t)b * ldt16 + c) = pk;
         if (x16 && c < ldx16) {
             const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
@@ -191,12 +200,18 @@ static int launch_densify(const int64_t *indptr, const IdxT *indices, const ValT
         if (smem <= 200 * 1024) {
             static bool attr_set = false;
             if (!attr_set) {
-                cudaFuncSetAttribute(csr_densify16_kernel<IdxT, ValT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     200 * 1024);
+                cudaFuncSetAttribute(csr_densify16_kernel<IdxT, ValT, false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                cudaFuncSetAttribute(csr_densify16_kernel<IdxT, ValT, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
                 attr_set = true;
             }
-            csr_densify16_kernel<IdxT, ValT><<<dim3(B, parts), 256, smem, s>>>(
-                indptr, indices, values, rows, G, row_const, rebase, t16, ldt16, x16, ldx16, width8, part8);
+            if (x16 && !t16)
+                csr_densify16_kernel<IdxT, ValT, true><<<dim3(B, parts), 256, smem, s>>>(
+                    indptr, indices, values, rows, G, row_const, rebase, t16, ldt16, x16, ldx16, width8, part8);
+            else
+                csr_densify16_kernel<IdxT, ValT, false><<<dim3(B, parts), 256, smem, s>>>(
+                    indptr, indices, values, rows, G, row_const, rebase, t16, ldt16, x16, ldx16, width8, part8);
             SCVAE_CHECK_LAUNCH("csr_densify16");
             return 0;
         }
