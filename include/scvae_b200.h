@@ -68,6 +68,13 @@ int scvae_csr_densify(const int64_t *indptr, const int32_t *indices, const float
                       const int64_t *rows, int B, int G, float *x, int64_t ldx,
                       float *row_const, int rebase, void *t16, int64_t ldt16, void *x16,
                       int64_t ldx16, void *stream);
+/* The per-cell constant sum_g lgamma(1 + x) depends on the data only: computed ONCE for every
+ * row of a CSR matrix when it is loaded (out [n_rows]; values fp32, or uint16 when
+ * values_are_u16; absolute indptr), then gathered per minibatch (dst[b] = src[rows[b]], rows
+ * == NULL: src[b]) instead of evaluating lgamma in every minibatch assembly. */
+int scvae_csr_row_constants(const int64_t *indptr, const void *values, int values_are_u16,
+                            int64_t n_rows, float *out, void *stream);
+int scvae_gather_f32(const float *src, const int64_t *rows, int B, float *dst, void *stream);
 /* Same with a compact CSR (uint16 column indices, G <= 65536, and uint16 integer counts):
  * 4 bytes per non-zero instead of 8 -- the format the streaming path ships over PCIe. */
 int scvae_csr_densify_u16(const int64_t *indptr, const void *indices_u16, const void *values_u16,

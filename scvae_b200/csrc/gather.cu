@@ -41,7 +41,7 @@ csr_densify_kernel(const int64_t *__restrict__ indptr, const IdxT *__restrict__ 
             if (c >= c0 && c < c0 + kChunk && c < G) {
                 const float v = (float)values[i];
                 buf[c - c0] = v;
-                if (v > 0.f) acc += lgammaf(1.f + v);
+                if (row_const && v > 0.f) acc += lgammaf(1.f + v);
             }
         }
         if (G >= c0 && G < c0 + kChunk && threadIdx.x == 0) buf[G - c0] = 1.f;   // augmented ones column
@@ -222,6 +222,30 @@ static int launch_densify(const int64_t *indptr, const IdxT *indices, const ValT
     return 0;
 }
 
+// sum_g lgamma(1 + x) of every CSR row (one warp per row): a per-cell constant of the data set,
+// computed once when the matrix is loaded instead of in every minibatch assembly
+template <typename ValT>
+__global__ void __launch_bounds__(256)
+csr_row_constants_kernel(const int64_t *__restrict__ indptr, const ValT *__restrict__ values, int64_t n_rows,
+                         float *__restrict__ out) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    float acc = 0.f;
+    for (int64_t i = indptr[row] + lane; i < indptr[row + 1]; i += 32) {
+        const float v = (float)values[i];
+        if (v > 0.f) acc += lgammaf(1.f + v);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = acc;
+}
+
+__global__ void gather_f32_kernel(const float *__restrict__ src, const int64_t *__restrict__ rows, int B,
+                                  float *__restrict__ dst) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) dst[b] = src[rows ? rows[b] : b];
+}
+
 // dense fp32 counts -> u16 (clamped), zero padded to ldt16 columns
 __global__ void f32_to_u16_kernel(const float *__restrict__ x, int64_t ldx, int G, uint16_t *__restrict__ t16,
                                   int64_t ldt16) {
@@ -261,6 +285,31 @@ extern "C" int scvae_csr_densify_u16(const int64_t *indptr, const void *indices_
     return launch_densify<uint16_t, uint16_t>(indptr, (const uint16_t *)indices_u16, (const uint16_t *)values_u16,
                                               rows, B, G, x, ldx, row_const, rebase, (uint16_t *)t16, ldt16,
                                               (__half *)x16, ldx16, (cudaStream_t)stream);
+}
+
+extern "C" int scvae_csr_row_constants(const int64_t *indptr, const void *values, int values_are_u16,
+                                       int64_t n_rows, float *out, void *stream) {
+    using namespace scvae;
+    SCVAE_CHECK_ARG(indptr && values && out && n_rows >= 0, "csr_row_constants: bad arguments");
+    if (n_rows == 0) return 0;
+    const unsigned blocks = (unsigned)((n_rows + 7) / 8);
+    if (values_are_u16)
+        csr_row_constants_kernel<uint16_t><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+            indptr, (const uint16_t *)values, n_rows, out);
+    else
+        csr_row_constants_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(indptr, (const float *)values,
+                                                                                  n_rows, out);
+    SCVAE_CHECK_LAUNCH("csr_row_constants");
+    return 0;
+}
+
+extern "C" int scvae_gather_f32(const float *src, const int64_t *rows, int B, float *dst, void *stream) {
+    using namespace scvae;
+    SCVAE_CHECK_ARG(src && dst && B >= 0, "gather_f32: bad arguments");
+    if (B == 0) return 0;
+    gather_f32_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(src, rows, B, dst);
+    SCVAE_CHECK_LAUNCH("gather_f32");
+    return 0;
 }
 
 extern "C" int scvae_f32_to_u16(const float *x, int64_t ldx, int64_t rows, int G, void *t16, int64_t ldt16,

@@ -478,7 +478,7 @@ class VAEEngine:
             p.use_T = False
 
     def set_batch_csr(self, p, indptr, indices, values, rows=None, rebase=False, u16_ok=False,
-                      f16_exact=False, train16=False):
+                      f16_exact=False, train16=False, row_const_all=None):
         """Gather + densify B rows of a device-resident CSR matrix (a1).
         ``u16_ok``: counts are integers < 65536; ``f16_exact``: all counts <= 2048.
         ``train16``: the caller will run the fused 16-bit training step, so only the 16-bit
@@ -486,12 +486,16 @@ class VAEEngine:
         matrix is not written at all."""
         use16 = bool(train16 and u16_ok and self.fused_heads and self._fused_possible(p.M, p.B)
                      and p.RS == 1)
+        # sum_g lgamma(1 + x) per cell: gathered from the per-data-set table when there is one
+        rc_out = None if row_const_all is not None else p.row_const
         if use16:
             p.t16_is_x16 = bool(f16_exact)
-            K.csr_densify(indptr, indices, values, rows, self.G, None, p.row_const, rebase=rebase,
+            K.csr_densify(indptr, indices, values, rows, self.G, None, rc_out, rebase=rebase,
                           t16=None if f16_exact else self._t16(p), x16=self._x16(p))
         else:
-            K.csr_densify(indptr, indices, values, rows, self.G, p.X, p.row_const, rebase=rebase)
+            K.csr_densify(indptr, indices, values, rows, self.G, p.X, rc_out, rebase=rebase)
+        if row_const_all is not None:
+            K.gather_f32(row_const_all, rows, p.row_const)
         p.have_x = not use16
         p.have_row_const = True
         p.have_t16 = use16

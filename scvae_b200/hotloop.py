@@ -45,6 +45,9 @@ class ResidentCSR:
         self.nbytes = indptr.nbytes + indices.nbytes + data.nbytes
         self.u16_ok = _counts_fit_u16(data)
         self.f16_exact = bool(self.u16_ok and (data.size == 0 or data.max() <= 2048))
+        # per-cell constant of every count log-likelihood, once per data set
+        self.row_const = torch.zeros(shape[0], dtype=torch.float32, device=self.device)
+        K.csr_row_constants(self.indptr, self.values, self.row_const)
 
     @property
     def number_of_examples(self):
@@ -70,6 +73,12 @@ class StreamedCSR:
             self.indices = torch.from_numpy(indices).pin_memory()
             self.values = torch.from_numpy(data).pin_memory()
         self.bytes_per_nnz = 4 if self.compact else 8
+        # per-cell constant sum_g lgamma(1 + x), once per data set; 4 bytes per row on the wire
+        from scipy.special import gammaln
+        terms = gammaln(1.0 + data.astype(numpy.float64))
+        csum_t = numpy.concatenate([[0.0], numpy.cumsum(terms)])
+        self.row_const = torch.from_numpy(
+            (csum_t[indptr[1:]] - csum_t[indptr[:-1]]).astype(numpy.float32)).pin_memory()
         n = shape[0]
         row_nnz = numpy.diff(indptr)
         # worst-case slab of max_rows consecutive rows
@@ -88,6 +97,7 @@ class StreamedCSR:
                                        device=self.device),
                 "values": torch.empty(max(self.max_nnz, 1), dtype=self.values.dtype,
                                       device=self.device),
+                "row_const": torch.empty(max_rows, dtype=torch.float32, device=self.device),
                 "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "bytes": 0,
                 "u16_ok": self.u16_ok, "f16_exact": self.f16_exact,
             })
@@ -103,8 +113,9 @@ class StreamedCSR:
             s["indptr"][: i1 - i0 + 1].copy_(self.indptr[i0:i1 + 1], non_blocking=True)
             s["indices"][: hi - lo].copy_(self.indices[lo:hi], non_blocking=True)
             s["values"][: hi - lo].copy_(self.values[lo:hi], non_blocking=True)
+            s["row_const"][: i1 - i0].copy_(self.row_const[i0:i1], non_blocking=True)
             s["ready"].record(self.copy_stream)
-        s["bytes"] = (i1 - i0 + 1) * 8 + (hi - lo) * self.bytes_per_nnz
+        s["bytes"] = (i1 - i0 + 1) * 8 + (hi - lo) * self.bytes_per_nnz + (i1 - i0) * 4
         return s
 
 
@@ -130,11 +141,12 @@ class TrainLoop:
             eng.fork_shadows(p)
         if isinstance(src, ResidentCSR):
             eng.set_batch_csr(p, src.indptr, src.indices, src.values, self.rows,
-                              u16_ok=src.u16_ok, f16_exact=src.f16_exact, train16=self.R == 1)
+                              u16_ok=src.u16_ok, f16_exact=src.f16_exact, train16=self.R == 1,
+                              row_const_all=src.row_const)
         else:  # staging slot of a StreamedCSR
             eng.set_batch_csr(p, src["indptr"], src["indices"], src["values"], None, rebase=True,
                               u16_ok=src["u16_ok"], f16_exact=src["f16_exact"],
-                              train16=self.R == 1)
+                              train16=self.R == 1, row_const_all=src["row_const"])
         K.fill_normal(p.eps, self.seed, 0, eng.store.step)
         eng.train_step(p, self.R, self.S, lr, w)
 

@@ -65,6 +65,18 @@ def csr_densify(indptr, indices, values, rows, G, x, row_const=None, rebase=Fals
                "csr_densify")
 
 
+def csr_row_constants(indptr, values, out):
+    """out[r] = sum_g lgamma(1 + x[r, g]) for every CSR row (absolute indptr)."""
+    lib = _lib.load()
+    _lib.check(lib.scvae_csr_row_constants(_p(indptr), _p(values), int(values.dtype == torch.int16),
+                                           out.numel(), _p(out), _stream()), "csr_row_constants")
+
+
+def gather_f32(src, rows, dst):
+    lib = _lib.load()
+    _lib.check(lib.scvae_gather_f32(_p(src), _p(rows), dst.numel(), _p(dst), _stream()), "gather_f32")
+
+
 def f32_to_u16(x, G, t16):
     lib = _lib.load()
     _lib.check(lib.scvae_f32_to_u16(_p(x), _ld(x), x.shape[0], G, _p(t16), _ld(t16), _stream()),

@@ -525,6 +525,17 @@ def test_csr_densify():
     assert torch.all(x[:, G] == 1) and torch.all(x[:, G + 1:] == 0)
     exp = torch.lgamma(1.0 + torch.tensor(sel, dtype=torch.float64)).sum(1)
     assert torch.allclose(rc.cpu().double(), exp, rtol=1e-5, atol=1e-4)
+    # per-data-set table of the same constant + per-minibatch gather
+    table = torch.zeros(N, device=dev)
+    K.csr_row_constants(indptr, values, table)
+    exp_all = torch.lgamma(1.0 + torch.tensor(dense, dtype=torch.float64)).sum(1)
+    assert torch.allclose(table.cpu().double(), exp_all, rtol=1e-5, atol=1e-4)
+    table16 = torch.zeros(N, device=dev)
+    K.csr_row_constants(indptr, cv, table16)
+    assert torch.allclose(table16, table, rtol=1e-6, atol=1e-5)
+    got = torch.zeros(17, device=dev)
+    K.gather_f32(table, rows, got)
+    assert torch.equal(got, table[rows])
 
 
 @pytest.mark.parametrize("R,S", [(1, 1), (3, 2)])
