@@ -189,6 +189,12 @@ int scvae_likelihood_bwd(int kind, const float *t, int64_t ldt, int t_rows, cons
  *   da16 (M, P*head_stride) fp16 out; dd (M, lddd) fp32 out (first dd_cols columns);
  *   logp [M] out; workspace: scvae_heads_fused_workspace_floats(M, G) floats. */
 int64_t scvae_heads_fused_workspace_floats(int M, int G);
+/* Forward only (the per-epoch evaluation passes VAE:1092-1150 and `evaluate` when no per-gene
+ * moments are requested): a = d W^T and log p(t | a) summed over genes; nothing but logp [M]
+ * leaves the chip.  Same operand layouts as below. */
+int scvae_heads_fused_fwd(int kind, const void *d16, const void *w16, int64_t head_stride,
+                          const void *t16, int64_t ldt, int t_is_half, int t_rows, int M, int G,
+                          const float *row_const, float *logp, float *workspace, void *stream);
 int scvae_heads_fused_bwd(int kind, const void *d16, const void *w16, int64_t head_stride,
                           const void *t16, int64_t ldt, int t_is_half, int t_rows, int M, int G,
                           const float *row_const, const float *go, float go_scalar, float scale,

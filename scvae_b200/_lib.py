@@ -30,6 +30,8 @@ SIGNATURES = {
     "scvae_csr_row_constants": (c_int, [c_ptr, c_ptr, c_int, c_i64, c_ptr, c_ptr]),
     "scvae_gather_f32": (c_int, [c_ptr, c_ptr, c_int, c_ptr, c_ptr]),
     "scvae_heads_fused_workspace_floats": (c_i64, [c_int, c_int]),
+    "scvae_heads_fused_fwd": (c_int, [c_int, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_int, c_int, c_int, c_int,
+                                      c_ptr, c_ptr, c_ptr, c_ptr]),
     "scvae_heads_fused_bwd": (c_int, [c_int, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_int, c_int, c_int, c_int,
                                       c_ptr, c_ptr, c_f32, c_f32, c_ptr, c_ptr, c_i64, c_int, c_ptr,
                                       c_ptr, c_ptr]),

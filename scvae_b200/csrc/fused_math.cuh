@@ -181,4 +181,51 @@ __device__ __forceinline__ void fused_fast8(const float (&x)[8], const float (&a
     }
 }
 
+// Forward-only form of fused_fast8 (evaluation passes): log p only, no reciprocal.
+template <int KIND>
+__device__ __forceinline__ void fused_fwd8(const float (&x)[8], const float (&a)[3][8], float &accA, float &accB,
+                                           float (&r)[8]) {
+    using T = Lik<KIND>;
+    constexpr int iD = T::ZI ? 1 : 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float xj = x[j];
+        float l0, lpd;          // log p_d(0) and log p_d(x) of the wrapped distribution (natural log)
+        if (T::NB) {
+            const float ap = a[iD][j], ar = a[iD + 1][j];
+            const float t = fast_ex2(ap * kLog2e);
+            const float rj = fast_ex2(ar * kLog2e);
+            const float lg = fast_lg2(1.f + t);
+            const float xr = xj + rj;
+            const float one = xj == 1.f ? 1.f : 0.f;
+            r[j] = rj;
+            if (!T::ZI) {
+                accA = fmaf(xj, ap, accA);
+                accA = fmaf(one, ar, accA);
+                accB = fmaf(xr, lg, accB);
+                continue;
+            }
+            const float sp = lg * kLn2;
+            l0 = -rj * sp;
+            lpd = fmaf(one, ar, fmaf(xj, ap, -xr * sp));
+        } else {
+            const float al = a[iD][j];
+            const float lam = fast_ex2(al * kLog2e);
+            r[j] = 0.f;
+            if (!T::ZI) {
+                accA = fmaf(xj, al, accA) - lam;
+                continue;
+            }
+            l0 = -lam;
+            lpd = fmaf(xj, al, -lam);
+        }
+        const float api = a[0][j];
+        const float lgp = fast_lg2(1.f + fast_ex2(api * kLog2e));
+        const float lgu = fast_lg2(1.f + fast_ex2((l0 - api) * kLog2e));
+        const bool pos = xj > 0.f;
+        accA += pos ? lpd : api;
+        accB += pos ? lgp : lgp - lgu;
+    }
+}
+
 }  // namespace scvae

@@ -125,7 +125,7 @@ struct FusedSlowOut {
     uint32_t packed[3][8];
     float acc;
 };
-template <int KIND, bool T_HALF>
+template <int KIND, bool T_HALF, bool BWD>
 __device__ __noinline__ FusedSlowOut fused_slow_chunk(FusedSlowIn in, float gs_row, int g_first, int G,
                                                       bool has_const) {
     constexpr int P = Lik<KIND>::P;
@@ -141,9 +141,10 @@ __device__ __noinline__ FusedSlowOut fused_slow_chunk(FusedSlowIn in, float gs_r
 #pragma unroll
             for (int h = 0; h < P; ++h) av[h][j] = __uint_as_float(in.sv[h][blk * 8 + j]);
         float acc8 = 0.f;
-        lik_group<KIND, true, 8>(x, av, has_const, acc8, gv);
+        lik_group<KIND, BWD, 8>(x, av, has_const, acc8, gv);
         const bool valid = (g_first + blk * 8) < G;
         out.acc += valid ? acc8 : 0.f;
+        if (!BWD) continue;
         const float gsv = valid ? gs_row : 0.f;
 #pragma unroll
         for (int h = 0; h < P; ++h)
@@ -154,8 +155,9 @@ __device__ __noinline__ FusedSlowOut fused_slow_chunk(FusedSlowIn in, float gs_r
     return out;
 }
 
-// T_HALF: targets are fp16 (exact for counts <= 2048) instead of uint16
-template <int KIND, bool T_HALF>
+// T_HALF: targets are fp16 (exact for counts <= 2048) instead of uint16.  BWD = false: forward
+// only (evaluation passes): MMA1 + log p; no gradient, no da tile, no MMA2, no dd.
+template <int KIND, bool T_HALF, bool BWD>
 __global__ void __launch_bounds__(fused_threads(Lik<KIND>::P), 1)
 heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmDA,
@@ -306,14 +308,20 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
                     }
                 }
                 tc_commit(bar(S_FULL + st));
-                if (n > 0) mma2(n - 1);
+                if (BWD) {
+                    if (n > 0) mma2(n - 1);
+                } else {
+                    tc_commit(bar(W_EMPTY + ws));     // forward only: the weights are done with MMA1
+                }
             }
-            mma2(ntile - 1);
-            tc_commit(bar(DD_FULL));
+            if (BWD) {
+                mma2(ntile - 1);
+                tc_commit(bar(DD_FULL));
+            }
         }
     } else if (warp == 3) {
         // ===== da store warp: smem da tile -> HBM (fp16), releases the tile for the next epilogue
-        if (lane == 0) {
+        if (BWD && lane == 0) {
             for (int n = 0; n < ntile; ++n) {
                 const int g0 = (tile0 + n) * FG;
                 const int ab = n % NA;
@@ -403,18 +411,21 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
                         for (int j = 0; j < 8; ++j)
 #pragma unroll
                             for (int h = 0; h < P; ++h) av[h][j] = __uint_as_float(sv[h][blk * 8 + j]);
-                        fused_fast8<KIND>(x, av, gs_row, accA, accB, rr, gv);
+                        if (BWD) fused_fast8<KIND>(x, av, gs_row, accA, accB, rr, gv);
+                        else fused_fwd8<KIND>(x, av, accA, accB, rr);
                         if (Lik<KIND>::NB) {
                             // fp16 is ample for the x >= 2 corrections: their error is ~1e-3 x per
                             // term with random sign, against a row sum of thousands
                             sts_v4(rscr + (uint32_t)((blk * 32 + lane) * 16), pack_half2(rr[0], rr[1]),
                                    pack_half2(rr[2], rr[3]), pack_half2(rr[4], rr[5]), pack_half2(rr[6], rr[7]));
                         }
+                        if (BWD) {
 #pragma unroll
-                        for (int h = 0; h < P; ++h)
+                            for (int h = 0; h < P; ++h)
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                packed[h][blk * 4 + j] = pack_half2(gv[h][2 * j], gv[h][2 * j + 1]);
+                                for (int j = 0; j < 4; ++j)
+                                    packed[h][blk * 4 + j] = pack_half2(gv[h][2 * j], gv[h][2 * j + 1]);
+                        }
                     }
                 } else {
                     FusedSlowIn in;
@@ -424,14 +435,15 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
                     for (int h = 0; h < P; ++h)
 #pragma unroll
                         for (int j = 0; j < 16; ++j) in.sv[h][j] = sv[h][j];
-                    const FusedSlowOut out = fused_slow_chunk<KIND, T_HALF>(in, gs_row, g0 + gc, p.G, p.has_const != 0);
+                    const FusedSlowOut out =
+                        fused_slow_chunk<KIND, T_HALF, BWD>(in, gs_row, g0 + gc, p.G, p.has_const != 0);
                     accA += out.acc;
 #pragma unroll
                     for (int h = 0; h < P; ++h)
 #pragma unroll
                         for (int j = 0; j < 8; ++j) packed[h][j] = out.packed[h][j];
                 }
-                if (first_write && n >= NA) {
+                if (BWD && first_write && n >= NA) {
                     // the previous tile in this da buffer must have been consumed by MMA2 and read
                     // by its TMA store before it is overwritten
                     if (lane == 0 && e == 0) FUSED_DBG(n, 5);
@@ -441,11 +453,13 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
                     if (lane == 0 && e == 0) FUSED_DBG(n, 7);
                 }
                 first_write = false;
+                if (BWD) {
 #pragma unroll
-                for (int h = 0; h < P; ++h) {
-                    const uint32_t arow = a_row + (uint32_t)(h * FABytes);
-                    sts_v4(arow + sw0, packed[h][0], packed[h][1], packed[h][2], packed[h][3]);
-                    sts_v4(arow + sw1, packed[h][4], packed[h][5], packed[h][6], packed[h][7]);
+                    for (int h = 0; h < P; ++h) {
+                        const uint32_t arow = a_row + (uint32_t)(h * FABytes);
+                        sts_v4(arow + sw0, packed[h][0], packed[h][1], packed[h][2], packed[h][3]);
+                        sts_v4(arow + sw1, packed[h][4], packed[h][5], packed[h][6], packed[h][7]);
+                    }
                 }
                 // targets >= 2 (about 3 % of a single-cell matrix): lgamma / digamma differences,
                 // one trip per flagged element of this row; the fp16 gradient is patched in place
@@ -474,8 +488,9 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
                             if (Lik<KIND>::NB) {
                                 rj[k] = __half2float(__ushort_as_half(lds_u16(
                                     rscr + (uint32_t)((((jj[k] >> 3) * 32 + lane) * 16) + ((jj[k] & 7) << 1)))));
-                                g_old[k] = __half2float(
-                                    __ushort_as_half(lds_u16(a_row + (uint32_t)((P - 1) * FABytes) + off[k])));
+                                g_old[k] = BWD ? __half2float(__ushort_as_half(lds_u16(
+                                                     a_row + (uint32_t)((P - 1) * FABytes) + off[k])))
+                                               : 0.f;
                             }
                         }
                         float extra = 0.f;
@@ -487,9 +502,10 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
                                 for (int k = 0; k < 2; ++k) lgamma_diff_ge2(rj[k], xj[k], D[k], Pd[k]);
                             }
                             extra = D[0] + (two ? D[1] : 0.f);
+                            if (BWD)
                             sts_u16(a_row + (uint32_t)((P - 1) * FABytes) + off[0],
                                     __half_as_ushort(__float2half_rn(fmaf(rj[0] * Pd[0], gs_row, g_old[0]))));
-                            if (two)
+                            if (BWD && two)
                                 sts_u16(a_row + (uint32_t)((P - 1) * FABytes) + off[1],
                                         __half_as_ushort(__float2half_rn(fmaf(rj[1] * Pd[1], gs_row, g_old[1]))));
                         }
@@ -508,7 +524,7 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
             fence_async_smem();
             __syncwarp();
             if (lane == 0 && (e == 0 || e == EW - 1)) FUSED_DBG(n, e == 0 ? 8 : 11);
-            if (lane == 0) mbar_arrive(bar(A_FULL + ab));
+            if (BWD && lane == 0) mbar_arrive(bar(A_FULL + ab));
         }
         // ---- log p partial of this gene range: combine the warps of a quadrant, fixed order ----
         // (the partials reuse the first 128 bytes of each warp's own total_count chunk)
@@ -522,12 +538,12 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
             p.logp_part[(int64_t)gs * p.part_stride + grow] = tot;
         }
         // ---- dd partial: TMEM -> staging smem (the t stages) -> TMA reduce-add ----
-        mbar_wait(bar(DD_FULL), 0);
+        if (BWD) mbar_wait(bar(DD_FULL), 0);
         tc_fence_after();
         uint8_t *stage = sT + half * FTBytes;       // 128 rows x 32 fp32 columns
         const bool half_issuer = (lane == 0 && q == 0);
 #pragma unroll 1
-        for (int c = 0; c < 2 && ej < 2; ++c) {
+        for (int c = 0; BWD && c < 2 && ej < 2; ++c) {
             uint32_t v[32];
             tc_ld32(tmem_DD + lane_addr + half * 64 + c * 32, v);
             tc_wait_ld();
@@ -552,7 +568,7 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
                 tma_commit();
             }
         }
-        if (half_issuer && ej < 2) tma_wait_all();
+        if (BWD && half_issuer && ej < 2) tma_wait_all();
     }
 
     tc_fence_before();
@@ -605,7 +621,7 @@ static FusedPlan fused_plan(int M, int G) {
     return f;
 }
 
-template <int KIND, bool T_HALF>
+template <int KIND, bool T_HALF, bool BWD>
 static int launch_fused_t(const void *d16, const void *w16, const void *t16, int64_t ldt, int t_rows,
                         int M, int G,
                         int64_t head_stride, const float *go, float go_scalar, float scale, void *da16,
@@ -617,10 +633,15 @@ static int launch_fused_t(const void *d16, const void *w16, const void *t16, int
     if (make_map(&tmD, d16, M, FK, FK, 64, FM, CU_TENSOR_MAP_SWIZZLE_128B, 2)) return 1;
     if (make_map(&tmW, w16, (int64_t)P * head_stride, FK, FK, 64, FG, CU_TENSOR_MAP_SWIZZLE_128B, 2)) return 1;
     if (make_map_u16(&tmT, t16, t_rows, G, ldt, FG, FM)) return 1;
-    if (make_map(&tmDA, da16, M, (int64_t)P * head_stride, (int64_t)P * head_stride, FG, FM,
-                 CU_TENSOR_MAP_SWIZZLE_128B, 2))
-        return 1;
-    if (make_map(&tmDD, dd, M, dd_cols, lddd, 32, FM)) return 1;
+    if (BWD) {
+        if (make_map(&tmDA, da16, M, (int64_t)P * head_stride, (int64_t)P * head_stride, FG, FM,
+                     CU_TENSOR_MAP_SWIZZLE_128B, 2))
+            return 1;
+        if (make_map(&tmDD, dd, M, dd_cols, lddd, 32, FM)) return 1;
+    } else {
+        tmDA = tmD;      // unused by the forward-only kernel
+        tmDD = tmD;
+    }
     FusedParams p;
     p.M = M; p.G = G; p.t_rows = t_rows;
     p.tiles_per_cta = f.tiles_per_cta; p.n_tiles = f.n_tiles; p.gsplit = f.gsplit;
@@ -633,14 +654,16 @@ static int launch_fused_t(const void *d16, const void *w16, const void *t16, int
     constexpr int smem = fused_smem_bytes(P);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(heads_fused_kernel<KIND, T_HALF>,
+        cudaError_t e = cudaFuncSetAttribute(heads_fused_kernel<KIND, T_HALF, BWD>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         SCVAE_CHECK_ARG(e == cudaSuccess, "heads_fused: cannot set smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    cudaError_t e = cudaMemsetAsync(dd, 0, (size_t)M * lddd * sizeof(float), s);
-    SCVAE_CHECK_ARG(e == cudaSuccess, "heads_fused: memset failed: %s", cudaGetErrorString(e));
-    heads_fused_kernel<KIND, T_HALF><<<f.row_tiles * f.gsplit, fused_threads(P), smem, s>>>(tmD, tmW, tmT, tmDA, tmDD, p);
+    if (BWD) {
+        cudaError_t e = cudaMemsetAsync(dd, 0, (size_t)M * lddd * sizeof(float), s);
+        SCVAE_CHECK_ARG(e == cudaSuccess, "heads_fused: memset failed: %s", cudaGetErrorString(e));
+    }
+    heads_fused_kernel<KIND, T_HALF, BWD><<<f.row_tiles * f.gsplit, fused_threads(P), smem, s>>>(tmD, tmW, tmT, tmDA, tmDD, p);
     SCVAE_CHECK_LAUNCH("heads_fused");
     fused_finish_kernel<<<(M + 255) / 256, 256, 0, s>>>(logp_part, p.part_stride, f.gsplit, M, row_const, t_rows,
                                                         logp);
@@ -653,11 +676,17 @@ static int launch_fused(const void *d16, const void *w16, const void *t16, int64
                         int M, int G, int64_t head_stride, const float *go, float go_scalar, float scale,
                         void *da16, float *dd, int64_t lddd, int dd_cols, float *logp_part,
                         const float *row_const, float *logp, cudaStream_t s) {
-    if (t_is_half)
-        return launch_fused_t<KIND, true>(d16, w16, t16, ldt, t_rows, M, G, head_stride, go, go_scalar, scale, da16,
-                                          dd, lddd, dd_cols, logp_part, row_const, logp, s);
-    return launch_fused_t<KIND, false>(d16, w16, t16, ldt, t_rows, M, G, head_stride, go, go_scalar, scale, da16, dd,
-                                       lddd, dd_cols, logp_part, row_const, logp, s);
+    const bool bwd = da16 != nullptr;     // forward only when no gradient buffers are given
+#define FUSED_GO(TH, BW)                                                                                          \
+    return launch_fused_t<KIND, TH, BW>(d16, w16, t16, ldt, t_rows, M, G, head_stride, go, go_scalar, scale, da16, \
+                                        dd, lddd, dd_cols, logp_part, row_const, logp, s)
+    if (t_is_half) {
+        if (bwd) FUSED_GO(true, true);
+        FUSED_GO(true, false);
+    }
+    if (bwd) FUSED_GO(false, true);
+    FUSED_GO(false, false);
+#undef FUSED_GO
 }
 
 }  // namespace scvae
@@ -672,6 +701,31 @@ extern "C" int64_t scvae_heads_fused_workspace_floats(int M, int G) {
     if (M <= 0 || G <= 0) return 0;
     const FusedPlan f = fused_plan(M, G);
     return (int64_t)f.gsplit * f.row_tiles * FM;
+}
+
+extern "C" int scvae_heads_fused_fwd(int kind, const void *d16, const void *w16, int64_t head_stride,
+                                     const void *t16, int64_t ldt, int t_is_half, int t_rows, int M, int G,
+                                     const float *row_const, float *logp, float *workspace, void *stream) {
+    SCVAE_CHECK_ARG(d16 && w16 && t16 && logp && workspace, "heads_fused_fwd: NULL pointer");
+    SCVAE_CHECK_ARG(M > 0 && G > 0 && G % 8 == 0 && t_rows > 0, "heads_fused_fwd: bad shape (G must be a multiple of 8)");
+    SCVAE_CHECK_ARG(head_stride % 64 == 0 && head_stride >= G, "heads_fused_fwd: head_stride must be a multiple of 64");
+    SCVAE_CHECK_ARG(ldt % 8 == 0, "heads_fused_fwd: bad leading dimension");
+    SCVAE_CHECK_ARG(M == t_rows || t_rows % FM == 0,
+                    "heads_fused_fwd: targets must tile in multiples of 128 rows (t_rows=%d, M=%d)", t_rows, M);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (kind) {
+#define CASE(KK)                                                                                              \
+    case KK:                                                                                                  \
+        return launch_fused<KK>(d16, w16, t16, ldt, t_is_half, t_rows, M, G, head_stride, nullptr, 0.f, 1.f, nullptr, \
+                                nullptr, 0, 0, workspace, row_const, logp, s);
+        CASE(SCVAE_LIK_POISSON)
+        CASE(SCVAE_LIK_NB)
+        CASE(SCVAE_LIK_ZIP)
+        CASE(SCVAE_LIK_ZINB)
+#undef CASE
+    }
+    set_error("heads_fused_fwd: unknown kind %d", kind);
+    return 1;
 }
 
 extern "C" int scvae_heads_fused_bwd(int kind, const void *d16, const void *w16, int64_t head_stride,

@@ -339,16 +339,20 @@ class VAEEngine:
         return (self.fused_heads and self.head.n_in + 1 <= 128 and self.G % 8 == 0
                 and (M == B or B % 128 == 0))
 
-    def _plan_fused(self, p, M):
-        if p.fused_ready:
-            return
+    def _plan_fused(self, p, M, backward=True):
+        """Buffers of the fused heads kernel, sized for the plan's row count; the fp16 gradient
+        buffer (rows x P genes) only when a backward pass will follow."""
         dev = self.device
-        p.D16 = torch.zeros(M, 128, dtype=torch.float16, device=dev)
-        p.W16 = torch.zeros(self.P * self.Gh, 128, dtype=torch.float16, device=dev)
-        p.dA16 = torch.zeros(M, self.P * self.Gh, dtype=torch.float16, device=dev)
-        p.fused_ws = torch.zeros(K.heads_fused_workspace_floats(M, self.G), dtype=torch.float32,
-                                 device=dev)
-        p.fused_ready = True
+        rows = max(M, p.M)
+        if not p.fused_ready:
+            p.D16 = torch.zeros(rows, 128, dtype=torch.float16, device=dev)
+            p.W16 = torch.zeros(self.P * self.Gh, 128, dtype=torch.float16, device=dev)
+            p.fused_ws = torch.zeros(K.heads_fused_workspace_floats(rows, self.G),
+                                     dtype=torch.float32, device=dev)
+            p.dA16 = None
+            p.fused_ready = True
+        if backward and p.dA16 is None:
+            p.dA16 = torch.zeros(rows, self.P * self.Gh, dtype=torch.float16, device=dev)
 
     def _t16(self, p):
         if getattr(p, "T16", None) is None:
@@ -389,7 +393,7 @@ class VAEEngine:
         """fp16 copies of the first encoder weight and of the head weights for this step.
         They depend on the parameters only, so they run on the side stream beside the
         densify / noise kernels that precede the first product; the main stream joins here."""
-        self._plan_fused(p, M)
+        self._plan_fused(p, M, backward=False)
         main = torch.cuda.current_stream()
         use_side = self.overlap_streams and getattr(p, "shadow_fork", None) is not None
         if use_side:
@@ -484,8 +488,7 @@ class VAEEngine:
         ``train16``: the caller will run the fused 16-bit training step, so only the 16-bit
         copies are produced (fp16 input + uint16 targets when fp16 is not exact) and the fp32
         matrix is not written at all."""
-        use16 = bool(train16 and u16_ok and self.fused_heads and self._fused_possible(p.M, p.B)
-                     and p.RS == 1)
+        use16 = bool(train16 and u16_ok and self.fused_heads and self._fused_possible(p.M, p.B))
         # sum_g lgamma(1 + x) per cell: gathered from the per-data-set table when there is one
         rc_out = None if row_const_all is not None else p.row_const
         if use16:
@@ -503,7 +506,7 @@ class VAEEngine:
 
     # ------------------------------------------------------------------ forward ------------
     def forward(self, p, is_training, R, S, warm_up_weight=1.0, deterministic=False,
-                update_moving=None, want_go=False, fused_backward=False):
+                update_moving=None, want_go=False, fused_backward=False, keep_heads=True):
         """encoder -> posterior -> z -> decoder -> heads -> log-likelihood -> bound.
         With ``fused_backward`` (R == 1) the likelihood kernel also emits dA in the same pass."""
         B = p.B
@@ -511,8 +514,10 @@ class VAEEngine:
         M = RS * B
         if update_moving is None:
             update_moving = is_training
-        use16 = bool(fused_backward and p.have_t16 and not getattr(p, "use_T", False)
-                     and self._fused_possible(M, B))
+        # keep_heads=False: the caller needs log p only, not the (rows x P genes) head
+        # pre-activations (per-epoch evaluation passes): forward-only fused heads
+        use16 = bool((fused_backward or not keep_heads) and p.have_t16
+                     and not getattr(p, "use_T", False) and self._fused_possible(M, B))
         if not use16 and not getattr(p, "have_x", True):
             raise RuntimeError("this minibatch was densified for the fused 16-bit training step "
                                "only; call set_batch_csr without train16 for other passes")
@@ -550,6 +555,18 @@ class VAEEngine:
         rc = p.row_const if p.have_row_const else None
         weight = warm_up_weight * self.kl_weight
         p.fused_done = False
+        if use16 and not fused_backward:
+            # heads GEMM + likelihood in one kernel, nothing but log p leaves the chip
+            self._plan_fused(p, M, backward=False)
+            K.f32_to_f16(d, l.in_p, p.D16)
+            if not self.enc:
+                self._refresh_shadows(p, M)
+            t16 = p.X16 if p.t16_is_x16 else p.T16
+            K.heads_fused_fwd(self.kind, p.D16, p.W16, self.Gh, t16, M, self.G, p.logp,
+                              p.fused_ws, row_const=rc)
+            K.vae_bound(p.logp, p.kl_row, 1 if deterministic else R, 1 if deterministic else S,
+                        B, weight, p.bound, p.go if want_go else None)
+            return p
         if use16:
             # heads GEMM + likelihood + decoder gradient in one kernel; da stays fp16
             assert R == 1 and not deterministic

@@ -87,6 +87,15 @@ def heads_fused_workspace_floats(M, G):
     return int(_lib.load().scvae_heads_fused_workspace_floats(M, G))
 
 
+def heads_fused_fwd(kind, d16, w16, head_stride, t16, M, G, logp, workspace, row_const=None):
+    """Forward-only fused heads GEMM + likelihood (evaluation passes)."""
+    lib = _lib.load()
+    _lib.check(lib.scvae_heads_fused_fwd(kind, _p(d16), _p(w16), head_stride, _p(t16), _ld(t16),
+                                         int(t16.dtype == torch.float16), t16.shape[0], M, G,
+                                         _p(row_const), _p(logp), _p(workspace), _stream()),
+               "heads_fused_fwd")
+
+
 def heads_fused_bwd(kind, d16, w16, head_stride, t16, M, G, da16, dd, dd_cols, logp, workspace,
                     row_const=None, go=None, go_scalar=1.0, scale=1.0):
     """Fused heads GEMM + likelihood forward/backward + decoder-gradient GEMM.  ``t16`` is a

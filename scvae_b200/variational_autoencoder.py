@@ -316,7 +316,12 @@ class VariationalAutoencoder:
             rows = min(minibatch_size, n - i)
             plan = engine._plan(rows, R * S)
             idx = torch.arange(i, i + rows, dtype=torch.int64, device=dev)
-            engine.set_batch_csr(plan, data.indptr, data.indices, data.values, idx)
+            # no per-batch consumer of the head pre-activations: 16-bit minibatch + forward-only
+            # fused heads (when the shapes allow; otherwise this is the fp32 path as before)
+            lean = on_batch is None and targets is None
+            engine.set_batch_csr(plan, data.indptr, data.indices, data.values, idx,
+                                 u16_ok=data.u16_ok, f16_exact=data.f16_exact, train16=lean,
+                                 row_const_all=data.row_const)
             if targets is not None:
                 if plan.T is None:
                     plan.T = torch.zeros(rows, engine.Gp, dtype=torch.float32, device=dev)
@@ -325,7 +330,8 @@ class VariationalAutoencoder:
                 plan.use_T = True
             if not deterministic:
                 K.fill_normal(plan.eps, seed, b)
-            engine.forward(plan, False, R, S, 1.0, deterministic=deterministic)
+            engine.forward(plan, False, R, S, 1.0, deterministic=deterministic,
+                           keep_heads=not lean)
             log[b, :4].copy_(plan.bound)
             log[b, 4:].copy_(engine.kl_neurons(plan))
             q_z_mean[i:i + rows].copy_(plan.PH[:rows, :L])

@@ -400,6 +400,11 @@ def test_heads_fused_bwd(kind, M, G, H, tile):
             assert got_da[:, h * Gh + G:(h + 1) * Gh].abs().max().item() == 0
     err = (dd[:, :H].cpu().double() - dd_ref).abs().max().item()
     assert err <= 3e-3 * dd_ref.abs().max().item(), (kind, err, dd_ref.abs().max().item())
+    # forward-only variant (evaluation passes): same log p, nothing else written
+    logp_f = torch.zeros(M, device=dev)
+    K.heads_fused_fwd(K.LIKELIHOOD_KINDS[kind], d16, w16, Gh, t16, M, G, logp_f, ws, row_const=rc)
+    torch.cuda.synchronize()
+    assert numpy.abs(logp_f.cpu().numpy() - ref).max() <= 3e-5 * numpy.abs(ref).max() + 1e-4
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -468,6 +473,10 @@ def test_heads_fused_bwd_clipped_heads_and_large_counts(kind, half_targets):
                       row_const=None, go=torch.tensor(go).to(dev), scale=scale)
     torch.cuda.synchronize()
     assert numpy.abs(logp2.cpu().numpy() - ref).max() <= 3e-5 * numpy.abs(ref).max() + 1e-4
+    logp3 = torch.zeros(M, device=dev)
+    K.heads_fused_fwd(K.LIKELIHOOD_KINDS[kind], d16, w16, Gh, t16, M, G, logp3, ws, row_const=None)
+    torch.cuda.synchronize()
+    assert numpy.abs(logp3.cpu().numpy() - ref).max() <= 3e-5 * numpy.abs(ref).max() + 1e-4
 
 
 def test_adam_clip_step():

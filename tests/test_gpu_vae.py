@@ -146,3 +146,36 @@ def test_vae_csr_input_matches_dense():
     eng.forward(plan, True, R, S, 1.0, update_moving=False)
     torch.cuda.synchronize()
     assert numpy.allclose(plan.bound.cpu().numpy(), ref, rtol=2e-6)
+
+
+@pytest.mark.parametrize("R,S,deterministic", [(1, 1, False), (2, 2, False), (1, 1, True)])
+def test_vae_lean_evaluation_pass_matches_full_path(R, S, deterministic):
+    """Per-epoch evaluation passes: 16-bit minibatch + forward-only fused heads (keep_heads=False)
+    against the fp32 path that materialises the head pre-activations."""
+    import scipy.sparse
+    from scvae_b200.engine import VAEEngine
+    from scvae_b200.hotloop import ResidentCSR
+    G, L, H, B = 256, 8, [32], 128
+    dev = torch.device("cuda:0")
+    x, _ = O.synthetic_counts(B, G, n_types=3, seed=60, target_zero_fraction=0.85)
+    x = numpy.minimum(x, 300.0)
+    data = ResidentCSR(scipy.sparse.csr_matrix(x.astype(numpy.float32)), dev)
+    eng = VAEEngine(G, L, H, "negative binomial", device=dev, tensor_cores=True, seed=3)
+    plan = eng._plan(B, R * S)
+    idx = torch.arange(B, device=dev)
+    eng.sample_noise(plan, 5, 0)
+    results = []
+    for lean in (False, True):
+        eng.set_batch_csr(plan, data.indptr, data.indices, data.values, idx, u16_ok=data.u16_ok,
+                          f16_exact=data.f16_exact, train16=lean, row_const_all=data.row_const)
+        # batch statistics (an untrained model's moving averages do not normalise raw counts)
+        eng.forward(plan, True, R, S, 1.0, deterministic=deterministic, update_moving=False,
+                    keep_heads=not lean)
+        torch.cuda.synchronize()
+        results.append((plan.bound.cpu().numpy().copy(), plan.logp.cpu().numpy().copy()))
+    (b0, lp0), (b1, lp1) = results
+    assert plan.have_t16          # the lean pass really took the 16-bit / fused route
+    assert abs(b0[0] - b1[0]) <= 2e-3 * abs(b0[0])
+    assert abs(b0[2] - b1[2]) <= 2e-3 * abs(b0[2])
+    m = B if deterministic else R * S * B
+    assert numpy.abs(lp0[:m] - lp1[:m]).max() <= 3e-3 * numpy.abs(lp0[:m]).max()
