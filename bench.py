@@ -395,6 +395,35 @@ def run_b200(args):
                 "eager_ms_per_step_by_kernel": {k: round(v, 4) for k, v in per_step_ms.items()}}
     _dbg("kernel timing done")
 
+    # ---- forward-only evaluation pass (the reference runs one over the training set after every
+    # epoch, VAE:1092-1150): 16-bit minibatch + forward-only fused heads, eager launches
+    eval_pass = None
+    try:
+        n_eval = min(n_batches, 16)
+        plan = loop.plan
+
+        def eval_batch(b):
+            eng.set_batch_csr(plan, data.indptr, data.indices, data.values, perm[b * B:(b + 1) * B],
+                              u16_ok=data.u16_ok, f16_exact=data.f16_exact, train16=True,
+                              row_const_all=data.row_const)
+            K.fill_normal(plan.eps, 7, b)
+            eng.forward(plan, False, 1, 1, 1.0, keep_heads=False)
+
+        eval_batch(0)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for b in range(n_eval):
+            eval_batch(b)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / n_eval
+        eval_pass = {"value": B * world / (ms * 1e-3), "unit": UNIT, "ms_per_batch": ms,
+                     "what": "forward-only evaluation pass per GPU x n_gpus (not part of `value`)"}
+    except Exception as exc:      # informational only
+        eval_pass = {"error": str(exc)}
+    _dbg("evaluation pass timed")
+
     # ---- end to end: host CSR in pinned memory, per-step H2D of the row slab, D2H of ELBO ---
     e2e = None
     if not args.no_e2e:
@@ -459,6 +488,7 @@ def run_b200(args):
             "data": "synthetic", "config": workload_config(args, B), "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "roofline": roofline, "cpu_baseline": cpu_base,
+            "evaluation_pass": eval_pass,
             "lower_bound_last_step": bound[0],
             "cuda_graph": bool(saved),
         }

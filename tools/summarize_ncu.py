@@ -55,9 +55,14 @@ def launches(src, dst, title):
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             out.write("| `{}` | {} | {:.1f} | {:.1f} | {:.1f}% |\n".format(k, a[0], a[1], a[1] / a[0], 100 * a[1] / tot))
         out.write("\n## Launch sequence of the last training step\n\n| # | kernel | us | grid | block |\n|---|---|---:|---|---|\n")
-        # last step = launches after the last csr_densify
-        idx = max((i for i, o in enumerate(order) if "densify" in o[0]), default=0)
-        for i, o in enumerate(order[idx:]):
+        # last TRAINING step = the last csr_densify that is followed by the optimiser, up to the
+        # next csr_densify (evaluation passes have no optimiser launch)
+        starts = [i for i, o in enumerate(order) if "densify" in o[0]] + [len(order)]
+        idx, end = 0, len(order)
+        for a, b in zip(starts[:-1], starts[1:]):
+            if any("adam" in o[0] or "dp_reduce" in o[0] for o in order[a:b]):
+                idx, end = a, b
+        for i, o in enumerate(order[idx:end]):
             out.write("| {} | `{}` | {:.1f} | {} | {} |\n".format(i, o[0], o[1], o[2], o[3]))
 
 
