@@ -31,10 +31,9 @@ constexpr int FM = 128;        // cells per CTA
 constexpr int FG = 64;         // genes per tile
 constexpr int FK = 128;        // padded hidden width (fp16 elements)
 // 4 control warps + EW epilogue warps.  A tile has 16 (32-row x 16-gene) chunks and all epilogue
-// warps meet at the da tile once per tile, so EW must divide 16: 8 warps x 2 chunks
-// chunks each (2 per scheduler, 168 registers) or 16 warps x 1 chunk (4 per scheduler, 96
-// registers and 2 KB of total_count scratch each: P <= 2 only)
-__host__ __device__ constexpr int fused_epi_warps(int P) { return P <= 2 ? 16 : 8; }
+// warps meet at the da tile once per tile, so EW must divide 16: 16 warps x 1 chunk (4 per
+// scheduler, 96 registers, 1 KB of fp16 total_count scratch each) for every likelihood
+__host__ __device__ constexpr int fused_epi_warps(int P) { return 16; }
 __host__ __device__ constexpr int fused_threads(int P) { return 128 + 32 * fused_epi_warps(P); }
 // head-weight ring: a stage is held from its TMA load until MMA2 of its tile has finished, i.e.
 // for two tiles; a third stage takes the reload off the critical path (smem allows it for P <= 2)
