@@ -563,7 +563,9 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
             fence_async_smem();
             bar_sync_n(2 + half, 128);
             if (half_issuer) {
-                tma_reduce_add_2d(&tmDD, half * 64 + c * 32, row0, smem_u32(stage));
+                // partial of this gene range -> its own workspace slice; the finish kernel sums
+                // the slices in fixed order (deterministic, unlike a reduce-add into dd)
+                tma_store_2d(&tmDD, half * 64 + c * 32, gs * (int)p.part_stride + row0, smem_u32(stage));
                 tma_commit();
             }
         }
@@ -586,6 +588,25 @@ __global__ void fused_finish_kernel(const float *__restrict__ part, int64_t part
     float acc = 0.f;
     for (int s = 0; s < gsplit; ++s) acc += part[(int64_t)s * part_stride + m];
     logp[m] = acc - (row_const ? row_const[m % t_rows] : 0.f);
+}
+
+// dd[m][c] = sum_s part[s][m][c] (c < dd_cols), 0 for the padding columns [dd_cols, lddd)
+__global__ void fused_dd_finish_kernel(const float *__restrict__ part, int64_t part_stride, int gsplit, int M,
+                                       float *__restrict__ dd, int64_t lddd, int dd_cols) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (int)(i & 31) << 2;
+    const int64_t m = i >> 5;
+    if (m >= M || c >= lddd) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < gsplit; ++s) {
+        const float4 v = *reinterpret_cast<const float4 *>(part + ((int64_t)s * part_stride + m) * FK + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (c + 0 >= dd_cols) acc.x = 0.f;
+    if (c + 1 >= dd_cols) acc.y = 0.f;
+    if (c + 2 >= dd_cols) acc.z = 0.f;
+    if (c + 3 >= dd_cols) acc.w = 0.f;
+    *reinterpret_cast<float4 *>(dd + m * lddd + c) = acc;     // lddd % 4 == 0
 }
 
 static inline int make_map_u16(CUtensorMap *map, const void *base, int64_t rows, int64_t cols, int64_t ld,
@@ -636,7 +657,10 @@ static int launch_fused_t(const void *d16, const void *w16, const void *t16, int
         if (make_map(&tmDA, da16, M, (int64_t)P * head_stride, (int64_t)P * head_stride, FG, FM,
                      CU_TENSOR_MAP_SWIZZLE_128B, 2))
             return 1;
-        if (make_map(&tmDD, dd, M, dd_cols, lddd, 32, FM)) return 1;
+        // dd partials: one (rows_pad x 128) fp32 slice per gene range, behind the log p partials
+        if (make_map(&tmDD, logp_part + (int64_t)f.gsplit * f.row_tiles * FM, (int64_t)f.gsplit * f.row_tiles * FM,
+                     FK, FK, 32, FM))
+            return 1;
     } else {
         tmDA = tmD;      // unused by the forward-only kernel
         tmDD = tmD;
@@ -658,15 +682,17 @@ static int launch_fused_t(const void *d16, const void *w16, const void *t16, int
         SCVAE_CHECK_ARG(e == cudaSuccess, "heads_fused: cannot set smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    if (BWD) {
-        cudaError_t e = cudaMemsetAsync(dd, 0, (size_t)M * lddd * sizeof(float), s);
-        SCVAE_CHECK_ARG(e == cudaSuccess, "heads_fused: memset failed: %s", cudaGetErrorString(e));
-    }
     heads_fused_kernel<KIND, T_HALF, BWD><<<f.row_tiles * f.gsplit, fused_threads(P), smem, s>>>(tmD, tmW, tmT, tmDA, tmDD, p);
     SCVAE_CHECK_LAUNCH("heads_fused");
     fused_finish_kernel<<<(M + 255) / 256, 256, 0, s>>>(logp_part, p.part_stride, f.gsplit, M, row_const, t_rows,
                                                         logp);
     SCVAE_CHECK_LAUNCH("heads_fused_finish");
+    if (BWD) {
+        const int64_t items = (int64_t)M * 32;
+        fused_dd_finish_kernel<<<(unsigned)((items + 255) / 256), 256, 0, s>>>(
+            logp_part + (int64_t)f.gsplit * f.row_tiles * FM, p.part_stride, f.gsplit, M, dd, lddd, dd_cols);
+        SCVAE_CHECK_LAUNCH("heads_fused_dd_finish");
+    }
     return 0;
 }
 
@@ -699,7 +725,8 @@ extern "C" void scvae_heads_fused_debug(void *buf) { g_fused_dbg = (long long *)
 extern "C" int64_t scvae_heads_fused_workspace_floats(int M, int G) {
     if (M <= 0 || G <= 0) return 0;
     const FusedPlan f = fused_plan(M, G);
-    return (int64_t)f.gsplit * f.row_tiles * FM;
+    // per gene range: log p partials (rows_pad) + decoder-gradient partials (rows_pad x 128)
+    return (int64_t)f.gsplit * f.row_tiles * FM * (1 + FK);
 }
 
 extern "C" int scvae_heads_fused_fwd(int kind, const void *d16, const void *w16, int64_t head_stride,

@@ -179,3 +179,31 @@ def test_vae_lean_evaluation_pass_matches_full_path(R, S, deterministic):
     assert abs(b0[2] - b1[2]) <= 2e-3 * abs(b0[2])
     m = B if deterministic else R * S * B
     assert numpy.abs(lp0[:m] - lp1[:m]).max() <= 3e-3 * numpy.abs(lp0[:m]).max()
+
+
+def test_fused_training_step_is_bit_reproducible():
+    """Same parameters, data and noise -> bit-identical parameters after several steps: every
+    reduction on the training path has a fixed order (no atomics, no multi-contributor
+    reduce-adds)."""
+    import scipy.sparse
+    from scvae_b200.engine import VAEEngine
+    from scvae_b200.hotloop import ResidentCSR, TrainLoop
+    G, L, H, B, N = 1024, 8, [48], 256, 512
+    dev = torch.device("cuda:0")
+    x, _ = O.synthetic_counts(N, G, n_types=3, seed=61, target_zero_fraction=0.9)
+    x = numpy.minimum(x, 500.0)
+    csr = scipy.sparse.csr_matrix(x.astype(numpy.float32))
+    finals = []
+    for _ in range(2):
+        eng = VAEEngine(G, L, H, "negative binomial", device=dev, tensor_cores=True, seed=5)
+        loop = TrainLoop(eng, B, seed=3, use_graph=True)
+        data = ResidentCSR(csr, dev)
+        for i in range(4):
+            loop.rows.copy_(torch.arange(B, device=dev) + (i % 2) * B)
+            loop.step(data, 1e-3, 1.0)
+        torch.cuda.synchronize()
+        assert loop.plan.fused_done
+        finals.append((eng.store.param.clone(), eng.store.grad.clone(), loop.plan.bound.clone()))
+    assert torch.equal(finals[0][1], finals[1][1]), "gradients differ between identical runs"
+    assert torch.equal(finals[0][0], finals[1][0]), "parameters differ between identical runs"
+    assert torch.equal(finals[0][2], finals[1][2])
