@@ -159,6 +159,12 @@ int scvae_gaussian_latent_bwd(const float *ph, int64_t ldph, int B, int L, int R
                               const float *eps, int unit_variance, const float *dz,
                               int64_t lddz, float kl_coef, float *dph, int64_t lddph,
                               void *stream);
+/* Decoder-input extras (VAE:2400-2441: `tf.concat([z, one_hot(batch_indices), count_sum])`):
+ * for row m (cell b = m % B) of the latent sample matrix z (M, ldz) write the one-hot batch
+ * index (batch_index [B] as float, nullable, n_batches columns) and/or the normalised count sum
+ * (count_sum [B], nullable, one column) starting at column col0 (behind the ones column). */
+int scvae_decoder_features(float *z, int64_t ldz, int M, int B, int col0, const float *batch_index,
+                           int n_batches, const float *count_sum, void *stream);
 
 /* ---- a5: count log-likelihood + reduction over genes  (VAE:2583-2590, DU:206-305,
  * ZI:194-199) --------------------------------------------------------------------------

@@ -156,7 +156,37 @@ __global__ void fill_normal_kernel(float *__restrict__ out, int64_t n, uint64_t 
 
 }  // namespace scvae
 
+namespace scvae {
+// Decoder-input extras (VAE:2400-2441): one-hot batch index and/or normalised count sum of cell
+// b = m % B, written behind the augmented ones column of the latent sample matrix.
+__global__ void decoder_features_kernel(float *__restrict__ z, int64_t ldz, int M, int B, int col0,
+                                        const float *__restrict__ batch_index, int n_batches,
+                                        const float *__restrict__ count_sum) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int b = m % B;
+    float *zr = z + (int64_t)m * ldz + col0;
+    if (batch_index) {
+        const int k = (int)batch_index[b];
+        for (int c = 0; c < n_batches; ++c) zr[c] = (c == k) ? 1.f : 0.f;
+    }
+    if (count_sum) zr[batch_index ? n_batches : 0] = count_sum[b];
+}
+}  // namespace scvae
+
 using namespace scvae;
+
+extern "C" int scvae_decoder_features(float *z, int64_t ldz, int M, int B, int col0, const float *batch_index,
+                                      int n_batches, const float *count_sum, void *stream) {
+    SCVAE_CHECK_ARG(z && M > 0 && B > 0 && col0 >= 0, "decoder_features: bad arguments");
+    SCVAE_CHECK_ARG((!batch_index || n_batches > 0) && col0 + (batch_index ? n_batches : 0) + (count_sum ? 1 : 0) <= ldz,
+                    "decoder_features: the extra columns do not fit the row (ldz=%lld)", (long long)ldz);
+    if (!batch_index && !count_sum) return 0;
+    decoder_features_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(z, ldz, M, B, col0, batch_index,
+                                                                             n_batches, count_sum);
+    SCVAE_CHECK_LAUNCH("decoder_features");
+    return 0;
+}
 
 extern "C" int scvae_gaussian_latent_fwd(const float *ph, int64_t ldph, int B, int L, int RS,
                                          const float *eps, int unit_variance, int deterministic,

@@ -39,11 +39,15 @@ def aug(n):
 
 
 class _Layer:
-    """One dense layer: weight (n_out, in_p) with the bias in column n_in, optional BN."""
+    """One dense layer: weight (n_out, in_p) with the bias in column n_in, optional BN.
+    ``n_extra`` further input columns behind the bias column carry the decoder-input extras
+    (one-hot batch index, count sum; VAE:2400-2441): data, so no gradient flows into them."""
 
-    def __init__(self, name, n_in, n_out, bn):
+    def __init__(self, name, n_in, n_out, bn, n_extra=0):
         self.name, self.n_in, self.n_out, self.bn = name, n_in, n_out, bn
-        self.in_p = aug(n_in)
+        self.n_extra = n_extra
+        self.k_in = n_in + 1 + n_extra          # reduction length of the forward product
+        self.in_p = round4(self.k_in)
         self.w = self.dw = None          # views into the flat buffers
         self.beta = self.dbeta = None
         self.moving_mean = self.moving_var = None
@@ -86,7 +90,8 @@ class VAEEngine:
     def __init__(self, feature_size, latent_size, hidden_sizes=(100,),
                  reconstruction_distribution="poisson", latent_distribution="gaussian",
                  minibatch_normalisation=True, kl_weight=1.0, device="cuda", seed=0,
-                 tensor_cores=True, fused_heads=True):
+                 tensor_cores=True, fused_heads=True, number_of_batches=0, count_sum_feature=False,
+                 inference_architecture="MLP", generative_architecture="MLP"):
         if reconstruction_distribution not in K.LIKELIHOOD_KINDS:
             raise ValueError("reconstruction distribution `{}` is not supported by the "
                              "B200 hot path".format(reconstruction_distribution))
@@ -115,20 +120,33 @@ class VAEEngine:
         self.overlap_streams = True
         self.side_gemm_ctas = int(__import__("os").environ.get("SCVAE_SIDE_GEMM_CTAS", "116"))
 
+        for arch in (inference_architecture, generative_architecture):
+            if arch not in ("MLP", "LFM"):
+                raise ValueError("architectures are `MLP` or `LFM` (linear factor model)")
+        # LFM: no hidden layers on that side (VAE:2221-2239, :2443-2462)
+        self.lfm_inference = inference_architecture == "LFM"
+        self.lfm_generative = generative_architecture == "LFM"
+        # decoder-input extras concatenated to z (VAE:2400-2441)
+        self.number_of_batches = int(number_of_batches or 0)
+        self.count_sum_feature = bool(count_sum_feature)
+        self.n_extra = self.number_of_batches + (1 if self.count_sum_feature else 0)
         n = len(self.hidden_sizes)
         self.enc = []
         width = self.G
-        for i, h in enumerate(self.hidden_sizes):
+        for i, h in enumerate([] if self.lfm_inference else self.hidden_sizes):
             self.enc.append(_Layer("ENCODER/{}".format(i + 1), width, h, self.bn))
             width = h
         self.nL = self.L if self.unit_variance else 2 * self.L
         self.post = _Layer("POSTERIOR", width, self.nL, False)
         self.dec = []
         width = self.L
-        for i, h in enumerate(self.hidden_sizes[::-1]):
-            self.dec.append(_Layer("DECODER/{}".format(n - i), width, h, self.bn))
+        for i, h in enumerate([] if self.lfm_generative else self.hidden_sizes[::-1]):
+            self.dec.append(_Layer("DECODER/{}".format(n - i), width, h, self.bn,
+                                   n_extra=self.n_extra if i == 0 else 0))
             width = h
-        self.head = _Layer("X_TILDE", width, self.P * self.Gn, False)
+        self.head = _Layer("X_TILDE", width, self.P * self.Gn, False,
+                           n_extra=0 if self.dec else self.n_extra)
+        self.Zp = round4(self.L + 1 + self.n_extra)       # stored width of the latent samples
 
         store = ParameterStore(self.device)
         for layer in self.enc + [self.post] + self.dec + [self.head]:
@@ -192,7 +210,7 @@ class VAEEngine:
         gen = torch.Generator().manual_seed(int(seed))
         params = OrderedDict()
         for layer, rows, scope in self._tf_names():
-            fan_in, fan_out = layer.n_in, rows.stop - rows.start
+            fan_in, fan_out = layer.n_in + layer.n_extra, rows.stop - rows.start
             limit = math.sqrt(6.0 / (fan_in + fan_out))
             w = torch.rand((fan_in, fan_out), generator=gen, dtype=torch.float64)
             params[scope + "/DENSE/weights"] = ((2.0 * w - 1.0) * limit).float()
@@ -212,9 +230,11 @@ class VAEEngine:
         for layer, rows, scope in self._tf_names():
             w = params[scope + "/DENSE/weights"].to(self.device, torch.float32)
             b = params[scope + "/DENSE/biases"].to(self.device, torch.float32)
-            layer.w[rows, :layer.n_in] = w.t()
+            layer.w[rows, :layer.n_in] = w[:layer.n_in].t()
             layer.w[rows, layer.n_in] = b
             layer.w[rows, layer.n_in + 1:] = 0
+            if layer.n_extra:
+                layer.w[rows, layer.n_in + 1:layer.k_in] = w[layer.n_in:].t()
             if layer.bn:
                 for key, dst in (("beta", layer.beta), ("moving_mean", layer.moving_mean),
                                  ("moving_variance", layer.moving_var)):
@@ -224,10 +244,18 @@ class VAEEngine:
                     elif strict:
                         raise KeyError(name)
 
+    @staticmethod
+    def _tf_weight(buf, layer, rows):
+        """(in [+ extras], out) matrix in the reference layout from the stored (out, in_p) one."""
+        w = buf[rows, :layer.n_in]
+        if layer.n_extra:
+            w = torch.cat([w, buf[rows, layer.n_in + 1:layer.k_in]], dim=1)
+        return w.t().contiguous().cpu()
+
     def export_parameters(self):
         out = OrderedDict()
         for layer, rows, scope in self._tf_names():
-            out[scope + "/DENSE/weights"] = layer.w[rows, :layer.n_in].t().contiguous().cpu()
+            out[scope + "/DENSE/weights"] = self._tf_weight(layer.w, layer, rows)
             out[scope + "/DENSE/biases"] = layer.w[rows, layer.n_in].contiguous().cpu()
             if layer.bn:
                 out[scope + "/BATCH_NORM/beta"] = layer.beta.cpu().clone()
@@ -239,7 +267,7 @@ class VAEEngine:
         """Last computed raw gradients (before clipping) under the TF variable names."""
         out = OrderedDict()
         for layer, rows, scope in self._tf_names():
-            out[scope + "/DENSE/weights"] = layer.dw[rows, :layer.n_in].t().contiguous().cpu()
+            out[scope + "/DENSE/weights"] = self._tf_weight(layer.dw, layer, rows)
             out[scope + "/DENSE/biases"] = layer.dw[rows, layer.n_in].contiguous().cpu()
             if layer.bn:
                 out[scope + "/BATCH_NORM/beta"] = layer.dbeta.cpu().clone()
@@ -304,7 +332,9 @@ class VAEEngine:
         p.enc_rstd = [zeros(l.n_out) for l in self.enc]
         p.PH = zeros(B, round4(self.nL))
         p.eps = zeros(M, self.L)
-        p.Z = zeros(M, aug(self.L))
+        p.Z = zeros(M, self.Zp)
+        p.batch_index = zeros(B) if self.number_of_batches else None   # batch ids as floats
+        p.count_sum = zeros(B) if self.count_sum_feature else None
         p.kl_row = zeros(B)
         p.kl_elem = zeros(B, self.L)
         p.kl_neurons = zeros(self.L)
@@ -336,7 +366,7 @@ class VAEEngine:
     # ---- fused likelihood heads (heads_fused.cu) -------------------------------------------
     def _fused_possible(self, M, B):
         """n_in + 1 <= 128 hidden columns, genes a multiple of 8, targets tiling in 128 rows."""
-        return (self.fused_heads and self.head.n_in + 1 <= 128 and self.G % 8 == 0
+        return (self.fused_heads and self.head.k_in <= 128 and self.G % 8 == 0
                 and (M == B or B % 128 == 0))
 
     def _plan_fused(self, p, M, backward=True):
@@ -378,7 +408,7 @@ class VAEEngine:
         p.dA = zeros(M, self.P * self.Gn)
         p.d_decH = [zeros(M, aug(l.n_out)) for l in self.dec]
         p.d_decY = [zeros(M, round4(l.n_out)) for l in self.dec]
-        p.dZ = zeros(M, aug(self.L))
+        p.dZ = zeros(M, self.Zp)
         p.dPH = zeros(B, round4(self.nL))
         p.d_encH = [zeros(B, aug(l.n_out)) for l in self.enc]
         p.d_encY = [zeros(B, round4(l.n_out)) for l in self.enc]
@@ -493,13 +523,14 @@ class VAEEngine:
         rc_out = None if row_const_all is not None else p.row_const
         if use16:
             p.t16_is_x16 = bool(f16_exact)
-            K.csr_densify(indptr, indices, values, rows, self.G, None, rc_out, rebase=rebase,
-                          t16=None if f16_exact else self._t16(p), x16=self._x16(p))
+            # (LFM inference: the posterior heads read the fp32 minibatch directly)
+            K.csr_densify(indptr, indices, values, rows, self.G, None if self.enc else p.X, rc_out,
+                          rebase=rebase, t16=None if f16_exact else self._t16(p), x16=self._x16(p))
         else:
             K.csr_densify(indptr, indices, values, rows, self.G, p.X, rc_out, rebase=rebase)
         if row_const_all is not None:
             K.gather_f32(row_const_all, rows, p.row_const)
-        p.have_x = not use16
+        p.have_x = (not use16) or not self.enc
         p.have_row_const = True
         p.have_t16 = use16
         p.use_T = False
@@ -540,9 +571,10 @@ class VAEEngine:
         self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, h, l.w, p.PH)
         K.gaussian_latent_fwd(p.PH, B, self.L, RS, p.eps, p.Z, p.kl_row, p.kl_elem,
                               unit_variance=self.unit_variance, deterministic=deterministic)
+        self._decoder_features(p, M)
         d = p.Z
         for j, l in enumerate(self.dec):
-            self._gemm(p, K.GEMM_NT, M, l.n_out, l.n_in + 1, d, l.w, p.decY[j][:M])
+            self._gemm(p, K.GEMM_NT, M, l.n_out, l.k_in, d, l.w, p.decY[j][:M])
             if l.bn:
                 K.bn_act_fwd(p.decY[j][:M], l.n_out, l.beta, l.moving_mean, l.moving_var,
                              p.decH[j][:M], p.dec_mean[j], p.dec_rstd[j], p.bn_scratch,
@@ -584,7 +616,7 @@ class VAEEngine:
             K.vae_bound(p.logp, p.kl_row, R, S, B, weight, p.bound, None)
             p.fused_done = True
             return p
-        self._gemm(p, K.GEMM_NT, M, l.n_out, l.n_in + 1, d, l.w, p.A[:M])
+        self._gemm(p, K.GEMM_NT, M, l.n_out, l.k_in, d, l.w, p.A[:M])
         if fused_backward:
             assert R == 1 and not deterministic
             self._plan_backward(p)
@@ -597,13 +629,29 @@ class VAEEngine:
                         B, weight, p.bound, p.go if want_go else None)
         return p
 
+    def set_batch_features(self, p, batch_index=None, count_sum=None):
+        """Decoder-input extras of the current minibatch: batch ids ([B], any numeric dtype)
+        and/or normalised count sums ([B])."""
+        if self.number_of_batches:
+            p.batch_index.copy_(batch_index.reshape(-1))
+        if self.count_sum_feature:
+            p.count_sum.copy_(count_sum.reshape(-1))
+
+    def _decoder_features(self, p, M):
+        if self.n_extra:
+            K.decoder_features(p.Z, M, p.B, self.L + 1, p.batch_index, self.number_of_batches,
+                               p.count_sum)
+
     def decode(self, p, rows):
         """Decoder-only entry point (``session.run(p_x_mean, feed_dict={z: ...})``, VAE:1706-1721):
         p.Z[:rows, :L] holds the latent samples; runs decoder + heads with moving statistics."""
         K.act_fwd(p.Z[:rows], self.L, p.Z[:rows], relu=False)   # (re)write the augmented columns
+        if self.n_extra:
+            raise NotImplementedError("decoding free latent samples with batch correction or "
+                                      "count-sum features (as in the reference, VAE:1639-1649)")
         d = p.Z
         for j, l in enumerate(self.dec):
-            self._gemm(p, K.GEMM_NT, rows, l.n_out, l.n_in + 1, d, l.w, p.decY[j][:rows])
+            self._gemm(p, K.GEMM_NT, rows, l.n_out, l.k_in, d, l.w, p.decY[j][:rows])
             if l.bn:
                 K.bn_act_fwd(p.decY[j][:rows], l.n_out, l.beta, l.moving_mean, l.moving_var,
                              p.decH[j][:rows], p.dec_mean[j], p.dec_rstd[j], p.bn_scratch,
@@ -612,7 +660,7 @@ class VAEEngine:
                 K.act_fwd(p.decY[j][:rows], l.n_out, p.decH[j][:rows], relu=True)
             d = p.decH[j]
         l = self.head
-        self._gemm(p, K.GEMM_NT, rows, l.n_out, l.n_in + 1, d, l.w, p.A[:rows])
+        self._gemm(p, K.GEMM_NT, rows, l.n_out, l.k_in, d, l.w, p.A[:rows])
 
     # ------------------------------------------------------------------ backward -----------
     def backward(self, p, R, S, warm_up_weight=1.0, dA_ready=False, defer_join=False):

@@ -54,6 +54,8 @@ class GMVAEEngine(VAEEngine):
         self.Gn, self.Gp = round4(self.G), aug(self.G)
         self.world_size, self._all_reduce, self._plans = 1, None, {}
         self._side, self.overlap_streams, self._peer = None, False, None   # (VAE-engine-only features)
+        self.n_extra, self.number_of_batches, self.count_sum_feature = 0, 0, False
+        self.lfm_inference = self.lfm_generative = False
         self.unit_variance = False
         self.nL = 2 * self.L
 

@@ -48,6 +48,19 @@ class ResidentCSR:
         # per-cell constant of every count log-likelihood, once per data set
         self.row_const = torch.zeros(shape[0], dtype=torch.float32, device=self.device)
         K.csr_row_constants(self.indptr, self.values, self.row_const)
+        # optional per-cell decoder features (set by the model shell): batch ids as floats,
+        # normalised count sums
+        self.batch_index = None
+        self.count_sum_feature = None
+
+    def set_features(self, batch_indices=None, count_sum_feature=None):
+        if batch_indices is not None:
+            self.batch_index = torch.as_tensor(numpy.asarray(batch_indices).reshape(-1),
+                                               dtype=torch.float32).to(self.device)
+        if count_sum_feature is not None:
+            self.count_sum_feature = torch.as_tensor(
+                numpy.asarray(count_sum_feature).reshape(-1), dtype=torch.float32).to(self.device)
+        return self
 
     @property
     def number_of_examples(self):
@@ -147,6 +160,15 @@ class TrainLoop:
             eng.set_batch_csr(p, src["indptr"], src["indices"], src["values"], None, rebase=True,
                               u16_ok=src["u16_ok"], f16_exact=src["f16_exact"],
                               train16=self.R == 1, row_const_all=src["row_const"])
+        if getattr(eng, "n_extra", 0):
+            # decoder-input extras (batch correction / count-sum feature) of this minibatch
+            if not isinstance(src, ResidentCSR):
+                raise NotImplementedError("batch correction / count-sum features need a resident "
+                                          "data set")
+            if eng.number_of_batches:
+                K.gather_f32(src.batch_index, self.rows, p.batch_index)
+            if eng.count_sum_feature:
+                K.gather_f32(src.count_sum_feature, self.rows, p.count_sum)
         K.fill_normal(p.eps, self.seed, 0, eng.store.step)
         eng.train_step(p, self.R, self.S, lr, w)
 

@@ -195,6 +195,13 @@ def gaussian_latent_fwd(ph, B, L, RS, eps, z, kl_row, kl_elem=None, unit_varianc
                "gaussian_latent_fwd")
 
 
+def decoder_features(z, M, B, col0, batch_index=None, n_batches=0, count_sum=None):
+    """One-hot batch index / count-sum columns of the decoder input (behind the ones column)."""
+    lib = _lib.load()
+    _lib.check(lib.scvae_decoder_features(_p(z), _ld(z), M, B, col0, _p(batch_index), n_batches,
+                                          _p(count_sum), _stream()), "decoder_features")
+
+
 def gaussian_latent_bwd(ph, B, L, RS, eps, dz, kl_coef, dph, unit_variance=False):
     lib = _lib.load()
     _lib.check(lib.scvae_gaussian_latent_bwd(_p(ph), _ld(ph), B, L, RS, _p(eps),

@@ -138,14 +138,17 @@ class VariationalAutoencoder:
                 self.reconstruction_distribution_name))
         if self.k_max:
             problems.append("piecewise-categorical likelihoods (number_of_reconstruction_classes)")
-        if self.batch_correction:
-            problems.append("batch correction")
-        if self.use_count_sum_as_feature:
-            problems.append("count sums as a decoder feature")
+        if (self.batch_correction or self.use_count_sum_as_feature
+                or self.inference_architecture != "MLP"
+                or self.generative_architecture != "MLP") and self.type != "VAE":
+            problems.append("batch correction, count-sum features and LFM architectures for the "
+                            "GMVAE")
+        if self.inference_architecture not in ("MLP", "LFM") \
+                or self.generative_architecture not in ("MLP", "LFM"):
+            raise ValueError("The inference and generative architectures can only be a neural "
+                             "network (MLP) or a linear factor model (LFM).")
         if self.dropout_parts:
             problems.append("dropout")
-        if self.inference_architecture != "MLP" or self.generative_architecture != "MLP":
-            problems.append("non-MLP architectures")
         if self.parameterise_latent_posterior:
             problems.append("parameterised latent posteriors")
         if self.type == "VAE" and not self.analytical_kl_term:
@@ -263,7 +266,25 @@ class VariationalAutoencoder:
         return VAEEngine(self.feature_size, self.latent_size, self.hidden_sizes,
                          self.reconstruction_distribution_name, self.latent_distribution_name,
                          self.minibatch_normalisation, self.kl_weight_value,
-                         device=self._device, seed=self._seed, tensor_cores=self._tensor_cores)
+                         device=self._device, seed=self._seed, tensor_cores=self._tensor_cores,
+                         number_of_batches=self.number_of_batches if self.batch_correction else 0,
+                         count_sum_feature=bool(self.use_count_sum_as_feature),
+                         inference_architecture=self.inference_architecture,
+                         generative_architecture=self.generative_architecture)
+
+    def _attach_features(self, data, data_set):
+        """Per-cell decoder features of a data set (VAE:816-833): batch indices for batch
+        correction, the normalised count sum as a feature."""
+        batch_indices = count_sum = None
+        if self.batch_correction:
+            batch_indices = data_set.batch_indices
+            if batch_indices is None:
+                raise TypeError("No batch indices found in {} set.".format(data_set.kind))
+        if self.use_count_sum_as_feature:
+            count_sum = data_set.normalised_count_sum
+        if batch_indices is not None or count_sum is not None:
+            data.set_features(batch_indices, count_sum)
+        return data
 
     def _get_engine(self):
         if self._engine is None:
@@ -328,6 +349,11 @@ class VariationalAutoencoder:
                 K.csr_densify(targets.indptr, targets.indices, targets.values, idx, engine.G,
                               plan.T, plan.row_const)
                 plan.use_T = True
+            if getattr(engine, "n_extra", 0):
+                if engine.number_of_batches:
+                    K.gather_f32(data.batch_index, idx, plan.batch_index)
+                if engine.count_sum_feature:
+                    K.gather_f32(data.count_sum_feature, idx, plan.count_sum)
             if not deterministic:
                 K.fill_normal(plan.eps, seed, b)
             engine.forward(plan, False, R, S, 1.0, deterministic=deterministic,
@@ -417,6 +443,7 @@ class VariationalAutoencoder:
         n_train = training_set.number_of_examples
         minibatch_size = min(minibatch_size, n_train)
         data = ResidentCSR(scipy.sparse.csr_matrix(x_train, dtype=numpy.float32), engine.device)
+        self._attach_features(data, training_set)
         if t_train is not x_train:
             raise NotImplementedError("Separate preprocessed inputs are supported by evaluate() "
                                       "only; training expects x == t (no preprocessing).")
@@ -424,6 +451,7 @@ class VariationalAutoencoder:
             x_valid, t_valid = self._inputs(validation_set, self.reconstruction_distribution_name)
             valid_data = ResidentCSR(scipy.sparse.csr_matrix(x_valid, dtype=numpy.float32),
                                      engine.device)
+            self._attach_features(valid_data, validation_set)
 
         training_writer = SummaryWriter(os.path.join(log_directory, "training")) \
             if is_main else None
@@ -689,8 +717,10 @@ class VariationalAutoencoder:
                 stddev_of_p_x_mean[wanted] = stddev_of_mean[local].cpu().numpy()
 
         evaluating_time_start = time()
-        result = self._evaluate_pass(engine, x_csr, t_csr, minibatch_size, R, S,
-                                     deterministic=deterministic,
+        from .hotloop import ResidentCSR
+        x_data = self._attach_features(ResidentCSR(x_csr, engine.device), evaluation_set)
+        result = self._evaluate_pass(engine, x_data, x_data if t_csr is x_csr else t_csr,
+                                     minibatch_size, R, S, deterministic=deterministic,
                                      seed=kwargs.get("noise_seed", 7), on_batch=collect)
         if numpy.isnan(result["lower_bound"]):
             raise ArithmeticError("Aborting. The ELBO for the evaluation set became indefinite.")

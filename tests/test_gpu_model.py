@@ -160,3 +160,34 @@ def test_peer_exchange_matches_nccl_on_two_gpus():
                         "29541", os.path.join(root, "tools", "dp_check.py")],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "dp_check OK" in r.stdout, r.stdout[-3000:]
+
+
+def test_train_evaluate_with_batch_correction_count_sum_and_lfm(tmp_path):
+    """The `--batch-correction`, `--count-sum` and `--generative-architecture LFM` options of the
+    reference CLI through the model class (VAE:2400-2462)."""
+    from scvae_b200.data_set import DataSet
+    from scvae_b200.variational_autoencoder import VariationalAutoencoder
+    x, labels = O.synthetic_counts(240, 64, n_types=3, seed=8, target_zero_fraction=0.8)
+    x = numpy.minimum(x, 50.0)
+    batches = (numpy.arange(240) % 3).reshape(-1, 1)
+    full = DataSet("toy", values=scipy.sparse.csr_matrix(x), labels=labels.astype(str),
+                   batch_indices=batches, batch_names=["a", "b", "c"])
+    training, validation, test = full.split()
+    assert training.batch_indices is not None
+    for kwargs in (dict(batch_correction=True, number_of_batches=3, count_sum=True),
+                   dict(generative_architecture="LFM", batch_correction=True, number_of_batches=3)):
+        model = VariationalAutoencoder(
+            feature_size=64, latent_size=4, hidden_sizes=[32],
+            reconstruction_distribution="negative binomial", log_directory=str(tmp_path), seed=1,
+            **kwargs)
+        assert model.train(training, validation, number_of_epochs=3, minibatch_size=48,
+                           learning_rate=1e-2, shuffle_seed=0) == 0
+        from scvae_b200 import model_utilities as MU
+        curve = MU.load_learning_curves(model, "training")["lower_bound"]
+        assert len(curve) == 3 and numpy.isfinite(curve).all()
+        transformed, reconstructed, latent = model.evaluate(test, minibatch_size=64,
+                                                            output_versions="all")
+        assert reconstructed.values.shape == (test.number_of_examples, 64)
+        assert numpy.isfinite(reconstructed.values).all()
+        with pytest.raises(NotImplementedError):
+            model.sample(sample_size=5)

@@ -207,3 +207,89 @@ def test_fused_training_step_is_bit_reproducible():
     assert torch.equal(finals[0][1], finals[1][1]), "gradients differ between identical runs"
     assert torch.equal(finals[0][0], finals[1][0]), "parameters differ between identical runs"
     assert torch.equal(finals[0][2], finals[1][2])
+
+
+EXTRA_CASES = [
+    # name, G, L, hidden, likelihood, B, engine/oracle options
+    ("batch-correction", 96, 6, [32], "negative binomial", 48, dict(number_of_batches=3)),
+    ("count-sum-feature", 96, 6, [32], "poisson", 48, dict(count_sum_feature=True)),
+    ("both-two-layers", 104, 5, [40, 24], "zero-inflated negative binomial", 40,
+     dict(number_of_batches=4, count_sum_feature=True)),
+    ("lfm-generative", 96, 6, [32], "negative binomial", 48,
+     dict(generative_architecture="LFM", number_of_batches=2)),
+    ("lfm-inference", 96, 6, [32], "negative binomial", 48, dict(inference_architecture="LFM")),
+    ("lfm-both", 96, 6, [32], "poisson", 48,
+     dict(inference_architecture="LFM", generative_architecture="LFM", count_sum_feature=True)),
+]
+
+
+@pytest.mark.parametrize("case", EXTRA_CASES, ids=[c[0] for c in EXTRA_CASES])
+@pytest.mark.parametrize("tensor_cores", [False, True], ids=["fp32", "tc16"])
+def test_vae_decoder_extras_and_linear_factor_architectures(case, tensor_cores):
+    """Batch correction (one-hot batch index) and the count-sum feature concatenated to z
+    (VAE:2400-2441), LFM inference / generative architectures (VAE:2221-2239, :2443-2462):
+    forward, every gradient and one clip + Adam step against the oracle."""
+    from scvae_b200.engine import VAEEngine
+    name, G, L, hidden, lik, B, opts = case
+    cfg = O.VAEConfig(G, L, hidden, lik, "gaussian", 1, 1, True, True, kl_weight=1.0, **opts)
+    params = O.vae_init_params(cfg, seed=4, dtype=torch.float64)
+    gen = torch.Generator().manual_seed(12)
+    for k in params:
+        if k.endswith("biases") or k.endswith("beta"):
+            params[k] = torch.randn(params[k].shape, generator=gen, dtype=torch.float64) * 0.1
+        if cfg.inference_architecture == "LFM" and k.startswith("POSTERIOR") and k.endswith("weights"):
+            params[k] = params[k] * 0.05        # raw counts feed the posterior heads directly
+    x, _ = O.synthetic_counts(B, G, n_types=3, seed=6, target_zero_fraction=0.8)
+    x = numpy.minimum(x, 30.0)
+    x64 = torch.tensor(x, dtype=torch.float64)
+    eps = torch.randn(1, B, L, generator=gen, dtype=torch.float64)
+    feats = {}
+    if cfg.number_of_batches:
+        feats["batch_indices"] = torch.randint(0, cfg.number_of_batches, (B, 1), generator=gen)
+    if cfg.count_sum_feature:
+        cs = x64.sum(dim=1)
+        feats["count_sum_feature"] = ((cs - cs.min()) / (cs.max() - cs.min())).reshape(B, 1)
+    state = O.AdamState(params)
+    ref_params = {k: v.clone() for k, v in params.items()}
+    out, grads = O.train_step(cfg, ref_params, state, x64, x64, eps, 1e-3, **feats)
+
+    eng = VAEEngine(G, L, hidden, lik, "gaussian", True, device="cuda:0", tensor_cores=tensor_cores,
+                    **opts)
+    eng.import_parameters(params)
+    plan = eng._plan(B, 1)
+    eng.set_batch_dense(plan, torch.tensor(x).cuda())
+    eng.set_batch_features(plan, feats["batch_indices"].cuda() if "batch_indices" in feats else None,
+                           feats["count_sum_feature"].float().cuda() if "count_sum_feature" in feats
+                           else None)
+    plan.eps.copy_(eps.reshape(B, L).float())
+    if not tensor_cores:     # evaluation mode (moving statistics) with the extras, exact path
+        out_e = O.vae_forward(cfg, params, x64, x64, eps, is_training=False, **feats)
+        eng.forward(plan, False, 1, 1, 1.0)
+        torch.cuda.synchronize()
+        be = plan.bound.cpu().numpy()
+        assert abs(be[0] - out_e["lower_bound"].item()) <= 5e-5 * abs(out_e["lower_bound"].item())
+    bound = eng.train_step(plan, 1, 1, 1e-3).cpu().numpy()
+    torch.cuda.synchronize()
+    if tensor_cores:
+        assert plan.fused_done          # the 16-bit fused heads path handles the wider decoder input
+    tol = 5e-5 if not tensor_cores else 2e-3
+    assert abs(bound[0] - out["lower_bound"].item()) <= tol * abs(out["lower_bound"].item())
+    assert _rel(plan.PH[:, :L].cpu(), out["q_z_mean"]) <= tol
+    assert _rel(plan.logp.cpu(), out["log_p_x_given_z"].reshape(-1)) <= tol
+    got = eng.export_gradients()
+    gtol = 2e-4 if not tensor_cores else 1e-2
+    gmax = max(g.abs().max().item() for g in grads.values())
+    assert set(got) >= set(grads)
+    for k, g in grads.items():
+        assert got[k].shape == g.shape, (k, got[k].shape, g.shape)
+        err = (got[k].double() - g).abs().max().item()
+        assert err <= gtol * g.abs().max().item() + 1e-5 * gmax, (k, err)
+    new = eng.export_parameters()
+    noise = (1e-3 if not tensor_cores else 3e-2) * gmax
+    for k, v in ref_params.items():
+        if "moving" in k:
+            continue
+        diff = (new[k].double() - v).abs()
+        if k in grads:
+            diff = diff * (grads[k].abs() > noise)
+        assert diff.max().item() <= 1e-5 * max(v.abs().max().item(), 1.0) + (2e-3 if tensor_cores else 0), k
