@@ -264,7 +264,6 @@ extern "C" int scvae_csr_densify(const int64_t *indptr, const int32_t *indices, 
     SCVAE_CHECK_ARG(indptr && indices && values && (x || x16 || t16), "csr_densify: NULL pointer");
     SCVAE_CHECK_ARG(B >= 0 && G > 0 && (!x || ldx >= G), "csr_densify: bad shape (B=%d G=%d ldx=%lld)", B, G,
                     (long long)ldx);
-    SCVAE_CHECK_ARG(!x || (ldx % 4 == 0 && aligned16(x)) || true, "csr_densify: x layout");
     SCVAE_CHECK_ARG(!t16 || (ldt16 % 8 == 0 && ldt16 >= G && aligned16(t16)), "csr_densify: bad t16 layout");
     SCVAE_CHECK_ARG(!x16 || (ldx16 % 8 == 0 && ldx16 > G && aligned16(x16)), "csr_densify: bad x16 layout");
     if (B == 0) return 0;

@@ -167,8 +167,9 @@ def attach(engine, exchange=None):
             if exchange == "p2p":
                 raise
             if rank() == 0:
+                import sys
                 print("scvae_b200: peer-memory exchange unavailable ({}); using NCCL "
-                      "all-reduce".format(exc))
+                      "all-reduce".format(exc), file=sys.stderr)
     return engine
 
 
