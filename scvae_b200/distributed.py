@@ -77,6 +77,15 @@ def all_reduce_sum_(flat):
     return flat
 
 
+def peer_slice_bounds(lo, hi, rank_index, world):
+    """[a, b) of the flat range [lo, hi) whose reduction, Adam update and parameter broadcast
+    rank ``rank_index`` owns in ``scvae_dp_reduce_adam`` (128-bit granules, ceil-divided)."""
+    n4 = (hi - lo) // 4
+    per = (n4 + world - 1) // world
+    a = min(rank_index * per, n4)
+    return lo + 4 * a, lo + 4 * min(a + per, n4)
+
+
 class PeerExchange:
     """Gradient exchange over peer memory, fused with the optimiser (``scvae_dp_reduce_adam``).
 
@@ -130,10 +139,7 @@ class PeerExchange:
 
     def slice_bounds(self, lo, hi, rank_index):
         """[a, b) of the flat range [lo, hi) owned by ``rank_index`` (as in the kernel)."""
-        n4 = (hi - lo) // 4
-        per = (n4 + self.world - 1) // self.world
-        a = min(rank_index * per, n4)
-        return lo + 4 * a, lo + 4 * min(a + per, n4)
+        return peer_slice_bounds(lo, hi, rank_index, self.world)
 
     def gather_slots(self, ranges):
         """Full Adam slots on every rank (each rank owns one slice per exchanged range)."""

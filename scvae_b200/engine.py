@@ -524,13 +524,14 @@ class VAEEngine:
         if use16:
             p.t16_is_x16 = bool(f16_exact)
             # (LFM inference: the posterior heads read the fp32 minibatch directly)
-            K.csr_densify(indptr, indices, values, rows, self.G, None if self.enc else p.X, rc_out,
+            need_x = (not self.enc) or getattr(self, "_needs_fp32_x", False)
+            K.csr_densify(indptr, indices, values, rows, self.G, p.X if need_x else None, rc_out,
                           rebase=rebase, t16=None if f16_exact else self._t16(p), x16=self._x16(p))
         else:
             K.csr_densify(indptr, indices, values, rows, self.G, p.X, rc_out, rebase=rebase)
         if row_const_all is not None:
             K.gather_f32(row_const_all, rows, p.row_const)
-        p.have_x = (not use16) or not self.enc
+        p.have_x = (not use16) or (not self.enc) or getattr(self, "_needs_fp32_x", False)
         p.have_row_const = True
         p.have_t16 = use16
         p.use_T = False

@@ -48,7 +48,10 @@ class GMVAEEngine(VAEEngine):
         self.free_nats = float(proportion_of_free_nats_for_y_kl_divergence)
         self.device = torch.device(device)
         self.tensor_cores = bool(tensor_cores)
-        self.fused_heads = False               # the fused heads kernel is wired into the VAE only
+        # fused heads kernel for the K cluster passes of a training step (rows = clusters x
+        # samples x cells tile the B target rows: B % 128 == 0); the encoders read the fp32 minibatch
+        self.fused_heads = bool(tensor_cores)
+        self._needs_fp32_x = True
         self.Gh = (self.G + 63) & ~63
         self.head_buffer_bytes = int(head_buffer_bytes)
         self.Gn, self.Gp = round4(self.G), aug(self.G)
@@ -393,6 +396,16 @@ class GMVAEEngine(VAEEngine):
         tgt = p.T if p.use_T else p.X
         rc = p.row_const if p.have_row_const else None
         rows_per_k = RS * B
+        fused = bool(with_backward and p.have_t16 and not p.use_T
+                     and self._fused_possible(min(p.chunk, Kc) * rows_per_k, B))
+        if fused:
+            self._plan_fused_chunks(p)
+            l = self.head
+            for h in range(self.P):        # fp16 shadow of the head weights for this step
+                K.f32_to_f16(l.w[h * self.Gn:(h + 1) * self.Gn], l.in_p,
+                             p.W16[h * self.Gh:h * self.Gh + self.Gn])
+            p.fused_scale = 2.0 ** round(math.log2(max(RS * B, 16) / 16.0))
+        p.fused_done = fused
         for c0 in range(0, Kc, p.chunk):
             kc = min(p.chunk, Kc - c0)
             r0, rows = c0 * rows_per_k, kc * rows_per_k
@@ -403,6 +416,25 @@ class GMVAEEngine(VAEEngine):
                              is_training, update_moving, kc)
                 d = p.decH[j]
             l = self.head
+            if fused:
+                # heads GEMM + likelihood + gradient + head dgrad in one kernel (heads_fused.cu);
+                # row m of the chunk reads target row m % B, its upstream gradient is go[m]
+                K.f32_to_f16(d[:rows], l.in_p, p.D16[:rows])
+                dd = p.d_decH[-1] if self.dec else p.dZ[r0:r0 + rows]
+                t16 = p.X16 if p.t16_is_x16 else p.T16
+                K.heads_fused_bwd(self.kind, p.D16[:rows], p.W16, self.Gh, t16, rows, self.G,
+                                  p.dA16[:rows], dd[:rows], l.n_in, p.logp[r0:r0 + rows],
+                                  p.fused_ws, row_const=rc, go=p.go[r0:r0 + rows],
+                                  scale=p.fused_scale)
+                for h in range(self.P):
+                    K.gemm_f16(K.GEMM_TN, self.Gn, l.in_p, rows,
+                               p.dA16[:rows, h * self.Gh:h * self.Gh + self.Gn], p.D16[:rows],
+                               l.dw[h * self.Gn:(h + 1) * self.Gn], accumulate=c0 > 0,
+                               alpha=1.0 / p.fused_scale)
+                self._decoder_backward(p, r0, rows, kc, accumulate=c0 > 0, heads_done=True)
+                if getattr(p, "on_chunk", None) is not None:
+                    p.on_chunk(c0, kc, rows)
+                continue
             self._gemm(p, K.GEMM_NT, rows, l.n_out, l.n_in + 1, d, l.w, p.A[:rows])
             if with_backward:
                 K.likelihood_bwd(self.kind, tgt, p.A[:rows], self.Gn, rows, self.G, p.dA[:rows],
@@ -428,13 +460,27 @@ class GMVAEEngine(VAEEngine):
         # log_softmax of K learned logits (K floats: host-side glue of the shell)
         self.log_py = torch.log_softmax(self.py_logits.detach(), dim=0)
 
-    def _decoder_backward(self, p, r0, rows, kc, accumulate):
+    def _plan_fused_chunks(self, p):
+        """fp16 operand / gradient buffers of the fused heads kernel for one decoder chunk."""
+        if p.fused_ready:
+            return
+        dev = self.device
+        Mc = p.chunk * p.RS * p.B
+        p.D16 = torch.zeros(Mc, 128, dtype=torch.float16, device=dev)
+        p.W16 = torch.zeros(self.P * self.Gh, 128, dtype=torch.float16, device=dev)
+        p.dA16 = torch.zeros(Mc, self.P * self.Gh, dtype=torch.float16, device=dev)
+        p.fused_ws = torch.zeros(K.heads_fused_workspace_floats(Mc, self.G), dtype=torch.float32,
+                                 device=dev)
+        p.fused_ready = True
+
+    def _decoder_backward(self, p, r0, rows, kc, accumulate, heads_done=False):
         l = self.head
         d_in = p.decH[-1] if self.dec else p.Z[r0:r0 + rows]
         dd_in = p.d_decH[-1] if self.dec else p.dZ[r0:r0 + rows]
-        self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, rows, p.dA[:rows], d_in[:rows], l.dw,
-                   accumulate=accumulate)
-        self._gemm(p, K.GEMM_NN, rows, l.n_in, l.n_out, p.dA[:rows], l.w, dd_in[:rows])
+        if not heads_done:
+            self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, rows, p.dA[:rows], d_in[:rows], l.dw,
+                       accumulate=accumulate)
+            self._gemm(p, K.GEMM_NN, rows, l.n_in, l.n_out, p.dA[:rows], l.w, dd_in[:rows])
         for j in range(len(self.dec) - 1, -1, -1):
             l = self.dec[j]
             self._bn_bwd(p, l, p.d_decH[j][:rows], p.decY[j][:rows], p.decH[j][:rows],

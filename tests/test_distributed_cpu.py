@@ -66,3 +66,17 @@ def test_shard_bounds_cover_minibatch():
     assert spans == [(100, 116), (116, 132), (132, 148), (148, 164)]
     assert D.shard_bounds(0, 10, 1, 4) == (2, 4)     # remainder dropped: equal work per rank
     assert D.rank() == 0 and D.world_size() == 1 and not D.is_active()
+
+
+def test_peer_exchange_slices_partition_every_range():
+    """Ownership map of the fused peer exchange: the W slices of a flat range are disjoint,
+    ordered, 16-byte aligned and cover it exactly (also when W does not divide the range)."""
+    from scvae_b200.distributed import peer_slice_bounds
+    for lo, hi in ((0, 4), (0, 6060288), (2023424, 6060288), (16, 16 + 4 * 37), (8, 8)):
+        for world in (1, 2, 3, 4, 8, 16):
+            cursor = lo
+            for r in range(world):
+                a, b = peer_slice_bounds(lo, hi, r, world)
+                assert a == cursor and a <= b <= hi and (a - lo) % 4 == 0
+                cursor = b
+            assert cursor == hi

@@ -14,6 +14,10 @@ CASES = [
     ("zinb-chunked", 64, 4, 5, [20, 12], "zero-inflated negative binomial", 1, 2, 24, "uniform", 0.0, 60000),
     ("poisson-learn", 80, 3, 3, [16], "poisson", 2, 1, 32, "learn", 0.0, 4 << 30),
     ("nb-freenats", 72, 4, 6, [16], "negative binomial", 1, 1, 30, "uniform", 0.9, 4 << 30),
+    # minibatches of 128 rows: the tensor-core mode runs the cluster passes through the fused heads
+    ("nb-fused", 96, 5, 3, [24], "negative binomial", 1, 1, 128, "uniform", 0.0, 4 << 30),
+    ("zinb-fused-chunked", 64, 4, 4, [20], "zero-inflated negative binomial", 1, 2, 128, "uniform", 0.0,
+     800000),
 ]
 
 
@@ -45,7 +49,7 @@ def _setup(case, tensor_cores):
 def test_gmvae_forward_backward_step(case, tensor_cores):
     name, G, L, Kc, hidden, lik, R, S, B, prior, free_nats, hbb = case
     cfg, params, x, eps, eng, plan = _setup(case, tensor_cores)
-    if name == "zinb-chunked":
+    if "chunked" in name:
         assert plan.chunk < Kc
     w = 0.7
     tol = 5e-5 if not tensor_cores else 2e-3
@@ -54,6 +58,7 @@ def test_gmvae_forward_backward_step(case, tensor_cores):
     out, grads = O.train_step(cfg, ref, state, x, x, eps, 1e-3, warm_up_weight=w)
     bound = eng.train_step(plan, R, S, 1e-3, warm_up_weight=w).cpu().numpy()
     torch.cuda.synchronize()
+    assert plan.fused_done == (tensor_cores and "fused" in name)
     names = ["lower_bound", "lower_bound_weighted", "reconstruction_error", "kl_divergence_z",
              "kl_divergence_y"]
     for i, n in enumerate(names):
@@ -69,7 +74,10 @@ def test_gmvae_forward_backward_step(case, tensor_cores):
     gmax = max(g.abs().max().item() for g in grads.values())
     for k, g in grads.items():
         err = (got[k].double() - g).abs().max().item()
-        assert err <= gtol * g.abs().max().item() + 1e-5 * gmax, (k, err, g.abs().max().item())
+        # (absolute floor for the exactly-zero gradients of batch-normed biases: fp32 noise, or
+        # the fp16 operand rounding of the fused heads path)
+        floor = (1e-4 if plan.fused_done else 1e-5) * gmax
+        assert err <= gtol * g.abs().max().item() + floor, (k, err, g.abs().max().item())
     new = eng.export_parameters()
     noise = (1e-3 if not tensor_cores else 3e-2) * gmax
     for k, v in ref.items():
