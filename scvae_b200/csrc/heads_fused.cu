@@ -344,7 +344,6 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
         const int ej = e >> 2;                   // index among the EJ warps sharing this quadrant
         const int half = ej;                     // (dd epilogue: warps ej < 2 take 64 columns each)
         const int row = q * 32 + lane;
-        const bool issuer = (threadIdx.x == 128);
         const int grow = row0 + row;
         const float gs_row = (grow < p.M ? (p.go ? p.go[grow] : p.go_scalar) : 0.f) * p.scale;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;

@@ -1,6 +1,9 @@
 """Time / profile the fused heads kernel alone at the C2 shape (development aid).
 
-    python tools/fused_bench.py [B] [likelihood]
+    python tools/fused_bench.py [B] [likelihood] [--timeline]
+
+--timeline prints the clock64 timeline of CTA 0 (needs a library built with
+-DSCVAE_FUSED_TIMELINE, e.g. NVCC_FLAGS of scvae_b200/_build.py extended by hand).
     ncu --set full --import-source on --clock-control none -k regex:heads_fused_kernel -s 2 -c 1 \
         -o gpurun_out/fused python tools/fused_bench.py
 """
