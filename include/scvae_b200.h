@@ -183,6 +183,20 @@ int scvae_likelihood_bwd(int kind, const float *t, int64_t ldt, int t_rows, cons
                          float *da, int64_t ldda, int64_t dhead_stride, float *logp,
                          void *stream);
 
+/* Constrained Poisson (DU "constrained poisson", VAE:2492-2496): rate[m, g] = N[m % t_rows] *
+ * clip(softmax_g(a[m, :]), tiny, 1); count_sum [t_rows] is the cell's count sum N (fed by the
+ * reference as count_sum_parameter).  logp [M] (nullable) and/or da (M, ldda) = go[m] * d logp /
+ * d a (NULL: forward only); lse [M] (nullable) receives the row log-sum-exp for the moments.
+ * The moments entry gives p_x_mean / p_x_stddev / stddev_of_p_x_given_z_mean (VAE:2665-2713). */
+int scvae_constrained_poisson(const float *t, int64_t ldt, int t_rows, const float *a, int64_t lda,
+                              int M, int G, const float *count_sum, const float *row_const,
+                              const float *go, float go_scalar, float *da, int64_t ldda,
+                              float *logp, float *lse, void *stream);
+int scvae_constrained_poisson_moments(const float *a, int64_t lda, const float *lse,
+                                      const float *count_sum, int B, int G, int RS,
+                                      float *p_x_mean, float *p_x_stddev, float *stddev_of_mean,
+                                      int64_t ldo, void *stream);
+
 /* ---- a4 + a5 fused: likelihood heads without the (cells x P*genes) round trip ----------------
  * One kernel computes a = d W^T (tcgen05, fp16 operands), log p(t | a) summed over genes, its
  * gradient da and the decoder gradient dd = da W; only da (fp16, scaled by `scale`) is written

@@ -109,7 +109,10 @@ class VAEEngine:
         self.kl_weight = float(kl_weight)
         self.device = torch.device(device)
         self.tensor_cores = bool(tensor_cores)
-        self.fused_heads = bool(fused_heads) and self.tensor_cores
+        # constrained Poisson: softmax over the genes of a cell, N = count sum of the cell as a
+        # parameter (VAE:2492-2496) -- a row kernel of its own, never the fused heads
+        self.constrained = self.kind == K.CONSTRAINED_POISSON
+        self.fused_heads = bool(fused_heads) and self.tensor_cores and not self.constrained
         self.Gn = round4(self.G)
         self.Gp = aug(self.G)
         self.Gh = (self.G + 63) & ~63      # head stride of the fp16 buffers of the fused heads
@@ -333,6 +336,8 @@ class VAEEngine:
         p.PH = zeros(B, round4(self.nL))
         p.eps = zeros(M, self.L)
         p.Z = zeros(M, self.Zp)
+        p.count_sum_parameter = zeros(B) if self.constrained else None   # N of the constrained Poisson
+        p.lse = zeros(M) if self.constrained else None
         p.batch_index = zeros(B) if self.number_of_batches else None   # batch ids as floats
         p.count_sum = zeros(B) if self.count_sum_feature else None
         p.kl_row = zeros(B)
@@ -621,14 +626,29 @@ class VAEEngine:
         if fused_backward:
             assert R == 1 and not deterministic
             self._plan_backward(p)
-            K.likelihood_bwd(self.kind, tgt, p.A[:M], self.Gn, M, self.G, p.dA[:M], logp=p.logp,
-                             row_const=rc, go=None, go_scalar=-1.0 / (S * B))
+            self._likelihood(p, tgt, p.A[:M], M, rc, logp=p.logp, da=p.dA[:M],
+                             go_scalar=-1.0 / (S * B))
             K.vae_bound(p.logp, p.kl_row, R, S, B, weight, p.bound, None)
         else:
-            K.likelihood_fwd(self.kind, tgt, p.A[:M], self.Gn, M, self.G, p.logp, row_const=rc)
+            self._likelihood(p, tgt, p.A[:M], M, rc, logp=p.logp)
             K.vae_bound(p.logp, p.kl_row, 1 if deterministic else R, 1 if deterministic else S,
                         B, weight, p.bound, p.go if want_go else None)
         return p
+
+    def set_batch_count_sum_parameter(self, p, count_sum):
+        """N of the constrained Poisson for the current minibatch ([B] raw count sums)."""
+        p.count_sum_parameter.copy_(count_sum.reshape(-1))
+
+    def _likelihood(self, p, tgt, A, M, rc, logp=None, da=None, go=None, go_scalar=1.0):
+        """log p (+ gradient when ``da`` is given) of the M head rows in A (stand-alone kernels)."""
+        if self.constrained:
+            K.constrained_poisson(tgt, A, M, self.G, p.count_sum_parameter, logp=logp, row_const=rc,
+                                  go=go, go_scalar=go_scalar, da=da, lse=p.lse)
+        elif da is not None:
+            K.likelihood_bwd(self.kind, tgt, A, self.Gn, M, self.G, da, logp=logp, row_const=rc,
+                             go=go, go_scalar=go_scalar)
+        else:
+            K.likelihood_fwd(self.kind, tgt, A, self.Gn, M, self.G, logp, row_const=rc)
 
     def set_batch_features(self, p, batch_index=None, count_sum=None):
         """Decoder-input extras of the current minibatch: batch ids ([B], any numeric dtype)
@@ -671,8 +691,7 @@ class VAEEngine:
         tgt = p.T if getattr(p, "use_T", False) else p.X
         rc = p.row_const if p.have_row_const else None
         if not dA_ready:
-            K.likelihood_bwd(self.kind, tgt, p.A, self.Gn, M, self.G, p.dA, logp=None,
-                             row_const=rc, go=p.go)
+            self._likelihood(p, tgt, p.A, M, rc, logp=None, da=p.dA, go=p.go)
         l = self.head
         d_in = p.decH[-1] if self.dec else p.Z
         dd_in = p.d_decH[-1] if self.dec else p.dZ
@@ -827,6 +846,9 @@ class VAEEngine:
         RS = 1 if deterministic else R * S
         outs = [torch.empty(p.B, self.Gn, dtype=torch.float32, device=self.device)
                 for _ in range(3)]
+        if self.constrained:
+            K.constrained_poisson_moments(p.A, p.lse, p.count_sum_parameter, p.B, self.G, RS, *outs)
+            return [o[:, :self.G] for o in outs]
         K.likelihood_moments(self.kind, p.A, self.Gn, p.B, self.G, RS, 1, None, *outs)
         return [o[:, :self.G] for o in outs]
 

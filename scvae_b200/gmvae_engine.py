@@ -31,6 +31,8 @@ class GMVAEEngine(VAEEngine):
         if reconstruction_distribution not in K.LIKELIHOOD_KINDS:
             raise ValueError("reconstruction distribution `{}` is not supported by the "
                              "B200 hot path".format(reconstruction_distribution))
+        if reconstruction_distribution == "constrained poisson":
+            raise ValueError("the constrained Poisson is wired into the VAE engine only")
         if prior_probabilities_method not in ("uniform", "learn", "custom"):
             raise ValueError("unknown prior probabilities method `{}`".format(
                 prior_probabilities_method))

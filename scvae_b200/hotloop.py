@@ -52,8 +52,12 @@ class ResidentCSR:
         # normalised count sums
         self.batch_index = None
         self.count_sum_feature = None
+        self.count_sum_parameter = None     # raw count sums: N of the constrained Poisson
 
-    def set_features(self, batch_indices=None, count_sum_feature=None):
+    def set_features(self, batch_indices=None, count_sum_feature=None, count_sum_parameter=None):
+        if count_sum_parameter is not None:
+            self.count_sum_parameter = torch.as_tensor(
+                numpy.asarray(count_sum_parameter).reshape(-1), dtype=torch.float32).to(self.device)
         if batch_indices is not None:
             self.batch_index = torch.as_tensor(numpy.asarray(batch_indices).reshape(-1),
                                                dtype=torch.float32).to(self.device)
@@ -160,6 +164,11 @@ class TrainLoop:
             eng.set_batch_csr(p, src["indptr"], src["indices"], src["values"], None, rebase=True,
                               u16_ok=src["u16_ok"], f16_exact=src["f16_exact"],
                               train16=self.R == 1, row_const_all=src["row_const"])
+        if getattr(eng, "constrained", False):
+            if not isinstance(src, ResidentCSR) or src.count_sum_parameter is None:
+                raise NotImplementedError("the constrained Poisson needs a resident data set with "
+                                          "count sums (set_features(count_sum_parameter=...))")
+            K.gather_f32(src.count_sum_parameter, self.rows, p.count_sum_parameter)
         if getattr(eng, "n_extra", 0):
             # decoder-input extras (batch correction / count-sum feature) of this minibatch
             if not isinstance(src, ResidentCSR):

@@ -14,8 +14,11 @@ LIKELIHOOD_KINDS = {
     "negative binomial": 1,
     "zero-inflated poisson": 2,
     "zero-inflated negative binomial": 3,
+    "constrained poisson": 4,      # row kernel of its own (softmax over genes), not in the family
 }
+CONSTRAINED_POISSON = 4
 LIKELIHOOD_HEADS = {
+    "constrained poisson": ["lambda"],
     "poisson": ["log_lambda"],
     "negative binomial": ["p", "log_r"],
     "zero-inflated poisson": ["pi", "log_lambda"],
@@ -208,6 +211,25 @@ def gaussian_latent_bwd(ph, B, L, RS, eps, dz, kl_coef, dph, unit_variance=False
                                              int(unit_variance), _p(dz), _ld(dz), float(kl_coef),
                                              _p(dph), _ld(dph), _stream()),
                "gaussian_latent_bwd")
+
+
+def constrained_poisson(t, a, M, G, count_sum, logp=None, row_const=None, go=None, go_scalar=1.0,
+                        da=None, lse=None):
+    """Constrained Poisson log p (and gradient when ``da`` is given); rows of t tile over M."""
+    _f32(t, a)
+    lib = _lib.load()
+    _lib.check(lib.scvae_constrained_poisson(_p(t), _ld(t), t.shape[0], _p(a), _ld(a), M, G,
+                                             _p(count_sum), _p(row_const), _p(go), float(go_scalar),
+                                             _p(da), _ld(da) if da is not None else 0, _p(logp),
+                                             _p(lse), _stream()), "constrained_poisson")
+
+
+def constrained_poisson_moments(a, lse, count_sum, B, G, RS, p_x_mean, p_x_stddev, stddev_of_mean):
+    lib = _lib.load()
+    _lib.check(lib.scvae_constrained_poisson_moments(_p(a), _ld(a), _p(lse), _p(count_sum), B, G, RS,
+                                                     _p(p_x_mean), _p(p_x_stddev), _p(stddev_of_mean),
+                                                     _ld(p_x_mean), _stream()),
+               "constrained_poisson_moments")
 
 
 def likelihood_fwd(kind, t, a, head_stride, M, G, logp, row_const=None):

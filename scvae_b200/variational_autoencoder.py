@@ -147,6 +147,10 @@ class VariationalAutoencoder:
                 or self.generative_architecture not in ("MLP", "LFM"):
             raise ValueError("The inference and generative architectures can only be a neural "
                              "network (MLP) or a linear factor model (LFM).")
+        if self.use_count_sum_as_parameter and (
+                self.type != "VAE" or self.reconstruction_distribution_name != "constrained poisson"):
+            problems.append("count-sum-parameterised likelihoods other than the VAE's "
+                            "constrained Poisson")
         if self.dropout_parts:
             problems.append("dropout")
         if self.parameterise_latent_posterior:
@@ -282,8 +286,9 @@ class VariationalAutoencoder:
                 raise TypeError("No batch indices found in {} set.".format(data_set.kind))
         if self.use_count_sum_as_feature:
             count_sum = data_set.normalised_count_sum
-        if batch_indices is not None or count_sum is not None:
-            data.set_features(batch_indices, count_sum)
+        parameter = data_set.count_sum if self.use_count_sum_as_parameter else None
+        if batch_indices is not None or count_sum is not None or parameter is not None:
+            data.set_features(batch_indices, count_sum, parameter)
         return data
 
     def _get_engine(self):
@@ -349,6 +354,8 @@ class VariationalAutoencoder:
                 K.csr_densify(targets.indptr, targets.indices, targets.values, idx, engine.G,
                               plan.T, plan.row_const)
                 plan.use_T = True
+            if getattr(engine, "constrained", False):
+                K.gather_f32(data.count_sum_parameter, idx, plan.count_sum_parameter)
             if getattr(engine, "n_extra", 0):
                 if engine.number_of_batches:
                     K.gather_f32(data.batch_index, idx, plan.batch_index)

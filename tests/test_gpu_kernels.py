@@ -9,7 +9,7 @@ from oracle import scvae_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-KINDS = list(O.LIKELIHOODS)
+KINDS = [k for k in O.LIKELIHOODS if k != "constrained poisson"]   # (own row kernel, own test)
 
 
 def _dev():
@@ -579,3 +579,53 @@ def test_fill_normal_statistics():
     c = torch.zeros(1 << 20, device=dev)
     K.fill_normal(c, 7, 0)
     assert torch.equal(a, c)
+
+
+@pytest.mark.parametrize("G,tile", [(300, 1), (1000, 3), (37, 2)])
+def test_constrained_poisson_kernel(G, tile):
+    """Softmax-over-genes Poisson with the cell's count sum as parameter vs fp64 autograd."""
+    from scvae_b200 import kernels as K
+    rng = numpy.random.RandomState(4)
+    B = 6
+    M = B * tile
+    Gn = (G + 3) & ~3
+    t = _counts(rng, B, G, 0.7)
+    a = (rng.randn(M, Gn) * 2.0).astype(numpy.float32)
+    a[0, 5] = -120.0                                   # softmax output below float32 tiny: clipped
+    n = t.sum(axis=1) + rng.randint(0, 3, size=B)      # N need not equal the target's row sum
+    go = rng.randn(M).astype(numpy.float32)
+    t64 = torch.tensor(t, dtype=torch.float64).repeat(tile, 1)
+    n64 = torch.tensor(n, dtype=torch.float64).reshape(B, 1).repeat(tile, 1)
+    a64 = torch.tensor(a[:, :G], dtype=torch.float64, requires_grad=True)
+    theta = {"lambda": O._clip_head(a64, "lambda")}
+    lp = O.likelihood_log_prob("constrained poisson", t64, theta, n64).sum(dim=1)
+    (lp * torch.tensor(go, dtype=torch.float64)).sum().backward()
+    dev = _dev()
+    td = torch.zeros(B, Gn, device=dev)
+    td[:, :G] = torch.tensor(t)
+    ad = torch.tensor(a).to(dev)
+    nd = torch.tensor(n, dtype=torch.float32).to(dev)
+    logp = torch.zeros(M, device=dev)
+    lse = torch.zeros(M, device=dev)
+    da = torch.zeros(M, Gn, device=dev)
+    K.constrained_poisson(td, ad, M, G, nd, logp=logp, go=torch.tensor(go).to(dev), da=da, lse=lse)
+    torch.cuda.synchronize()
+    ref = lp.detach().numpy()
+    assert numpy.abs(logp.cpu().numpy() - ref).max() <= 3e-5 * numpy.abs(ref).max() + 1e-4
+    g_ref = a64.grad.numpy()
+    assert numpy.abs(da.cpu().numpy()[:, :G] - g_ref).max() <= 3e-5 * numpy.abs(g_ref).max() + 1e-5
+    assert torch.allclose(lse.cpu().double(), torch.logsumexp(a64.detach(), dim=1), rtol=1e-6, atol=1e-5)
+    # forward only, with the per-row constant
+    rc = torch.lgamma(1.0 + torch.tensor(t, dtype=torch.float64)).sum(dim=1).float().to(dev)
+    logp2 = torch.zeros(M, device=dev)
+    K.constrained_poisson(td, ad, M, G, nd, logp=logp2, row_const=rc)
+    torch.cuda.synchronize()
+    assert numpy.abs(logp2.cpu().numpy() - ref).max() <= 3e-5 * numpy.abs(ref).max() + 1e-4
+    # moments: mean = variance = N softmax(a), single sample
+    if tile == 1:
+        outs = [torch.zeros(B, Gn, device=dev) for _ in range(3)]
+        K.constrained_poisson_moments(ad, lse, nd, B, G, 1, *outs)
+        m_ref = (theta["lambda"] * n64).detach()
+        assert torch.allclose(outs[0][:, :G].cpu().double(), m_ref, rtol=1e-4, atol=1e-6)
+        assert torch.allclose(outs[1][:, :G].cpu().double(), m_ref.sqrt(), rtol=1e-4, atol=1e-6)
+        assert outs[2][:, :G].abs().max().item() <= 1e-4 * m_ref.max().item()   # one sample: sqrt of rounding

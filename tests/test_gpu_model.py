@@ -191,3 +191,23 @@ def test_train_evaluate_with_batch_correction_count_sum_and_lfm(tmp_path):
         assert numpy.isfinite(reconstructed.values).all()
         with pytest.raises(NotImplementedError):
             model.sample(sample_size=5)
+
+
+def test_train_evaluate_constrained_poisson(tmp_path):
+    """`-r "constrained poisson"`: softmax over genes, the cell's count sum as parameter N."""
+    from scvae_b200.variational_autoencoder import VariationalAutoencoder
+    from scvae_b200 import model_utilities as MU
+    full = _data(n=240, g=64, seed=9)
+    training, validation, test = full.split()
+    model = VariationalAutoencoder(
+        feature_size=64, latent_size=4, hidden_sizes=[32],
+        reconstruction_distribution="constrained poisson", log_directory=str(tmp_path), seed=1)
+    assert model.use_count_sum_as_parameter
+    assert model.train(training, validation, number_of_epochs=3, minibatch_size=48,
+                       learning_rate=1e-2, shuffle_seed=0) == 0
+    curve = MU.load_learning_curves(model, "training")["lower_bound"]
+    assert len(curve) == 3 and numpy.isfinite(curve).all()
+    transformed, reconstructed, latent = model.evaluate(test, minibatch_size=64, output_versions="all")
+    # the reconstruction of a constrained Poisson sums to the cell's count sum
+    sums = reconstructed.values.sum(axis=1)
+    assert numpy.allclose(sums, numpy.asarray(test.count_sum).reshape(-1), rtol=1e-3)

@@ -220,6 +220,9 @@ EXTRA_CASES = [
     ("lfm-inference", 96, 6, [32], "negative binomial", 48, dict(inference_architecture="LFM")),
     ("lfm-both", 96, 6, [32], "poisson", 48,
      dict(inference_architecture="LFM", generative_architecture="LFM", count_sum_feature=True)),
+    ("constrained-poisson", 96, 6, [32], "constrained poisson", 48, dict()),
+    ("constrained-poisson-extras", 100, 5, [24], "constrained poisson", 40,
+     dict(number_of_batches=2, count_sum_feature=True)),
 ]
 
 
@@ -249,6 +252,9 @@ def test_vae_decoder_extras_and_linear_factor_architectures(case, tensor_cores):
     if cfg.count_sum_feature:
         cs = x64.sum(dim=1)
         feats["count_sum_feature"] = ((cs - cs.min()) / (cs.max() - cs.min())).reshape(B, 1)
+    constrained = lik == "constrained poisson"
+    if constrained:
+        feats["count_sum"] = x64.sum(dim=1, keepdim=True)
     state = O.AdamState(params)
     ref_params = {k: v.clone() for k, v in params.items()}
     out, grads = O.train_step(cfg, ref_params, state, x64, x64, eps, 1e-3, **feats)
@@ -261,6 +267,8 @@ def test_vae_decoder_extras_and_linear_factor_architectures(case, tensor_cores):
     eng.set_batch_features(plan, feats["batch_indices"].cuda() if "batch_indices" in feats else None,
                            feats["count_sum_feature"].float().cuda() if "count_sum_feature" in feats
                            else None)
+    if constrained:
+        eng.set_batch_count_sum_parameter(plan, feats["count_sum"].float().cuda())
     plan.eps.copy_(eps.reshape(B, L).float())
     if not tensor_cores:     # evaluation mode (moving statistics) with the extras, exact path
         out_e = O.vae_forward(cfg, params, x64, x64, eps, is_training=False, **feats)
@@ -271,7 +279,9 @@ def test_vae_decoder_extras_and_linear_factor_architectures(case, tensor_cores):
     bound = eng.train_step(plan, 1, 1, 1e-3).cpu().numpy()
     torch.cuda.synchronize()
     if tensor_cores:
-        assert plan.fused_done          # the 16-bit fused heads path handles the wider decoder input
+        # the 16-bit fused heads path handles the wider decoder input (not the softmax-coupled
+        # constrained Poisson, which has its own row kernel)
+        assert plan.fused_done == (not constrained)
     tol = 5e-5 if not tensor_cores else 2e-3
     assert abs(bound[0] - out["lower_bound"].item()) <= tol * abs(out["lower_bound"].item())
     assert _rel(plan.PH[:, :L].cpu(), out["q_z_mean"]) <= tol
