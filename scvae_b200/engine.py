@@ -91,7 +91,8 @@ class VAEEngine:
                  reconstruction_distribution="poisson", latent_distribution="gaussian",
                  minibatch_normalisation=True, kl_weight=1.0, device="cuda", seed=0,
                  tensor_cores=True, fused_heads=True, number_of_batches=0, count_sum_feature=False,
-                 inference_architecture="MLP", generative_architecture="MLP"):
+                 inference_architecture="MLP", generative_architecture="MLP",
+                 number_of_reconstruction_classes=0):
         if reconstruction_distribution not in K.LIKELIHOOD_KINDS:
             raise ValueError("reconstruction distribution `{}` is not supported by the "
                              "B200 hot path".format(reconstruction_distribution))
@@ -112,7 +113,14 @@ class VAEEngine:
         # constrained Poisson: softmax over the genes of a cell, N = count sum of the cell as a
         # parameter (VAE:2492-2496) -- a row kernel of its own, never the fused heads
         self.constrained = self.kind == K.CONSTRAINED_POISSON
-        self.fused_heads = bool(fused_heads) and self.tensor_cores and not self.constrained
+        # piecewise-categorical likelihood (`-k`, CAT:210-274): k_max + 1 class-logit heads
+        # behind the P heads of the count distribution, a row kernel of its own
+        self.k_max = int(number_of_reconstruction_classes or 0)
+        if self.k_max and self.constrained:
+            raise ValueError("piecewise-categorical likelihoods wrap the Poisson / NB family")
+        self.PT = self.P + (self.k_max + 1 if self.k_max else 0)      # head blocks of width Gn
+        self.fused_heads = (bool(fused_heads) and self.tensor_cores and not self.constrained
+                            and not self.k_max)
         self.Gn = round4(self.G)
         self.Gp = aug(self.G)
         self.Gh = (self.G + 63) & ~63      # head stride of the fp16 buffers of the fused heads
@@ -147,7 +155,7 @@ class VAEEngine:
             self.dec.append(_Layer("DECODER/{}".format(n - i), width, h, self.bn,
                                    n_extra=self.n_extra if i == 0 else 0))
             width = h
-        self.head = _Layer("X_TILDE", width, self.P * self.Gn, False,
+        self.head = _Layer("X_TILDE", width, self.PT * self.Gn, False,
                            n_extra=0 if self.dec else self.n_extra)
         self.Zp = round4(self.L + 1 + self.n_extra)       # stored width of the latent samples
 
@@ -218,6 +226,12 @@ class VAEEngine:
             w = torch.rand((fan_in, fan_out), generator=gen, dtype=torch.float64)
             params[scope + "/DENSE/weights"] = ((2.0 * w - 1.0) * limit).float()
             params[scope + "/DENSE/biases"] = torch.zeros(fan_out)
+        if self.k_max:      # one FC of width G (k_max + 1) (VAE:2507-2518)
+            fan_in, fan_out = self.head.n_in + self.head.n_extra, self.G * (self.k_max + 1)
+            limit = math.sqrt(6.0 / (fan_in + fan_out))
+            w = torch.rand((fan_in, fan_out), generator=gen, dtype=torch.float64)
+            params["X_TILDE/P_K/DENSE/weights"] = ((2.0 * w - 1.0) * limit).float()
+            params["X_TILDE/P_K/DENSE/biases"] = torch.zeros(fan_out)
         self.import_parameters(params, strict=False)
         for buf in (self.store.grad, self.store.m, self.store.v):
             buf.zero_()
@@ -246,6 +260,36 @@ class VAEEngine:
                         dst.copy_(params[name].to(self.device, torch.float32))
                     elif strict:
                         raise KeyError(name)
+        if self.k_max:
+            # the reference's P_K variable is class-minor (column g (k_max + 1) + c, reshaped to
+            # (rows, G, k_max + 1)); the engine keeps one block of Gn rows per class
+            K1, layer = self.k_max + 1, self.head
+            w = params["X_TILDE/P_K/DENSE/weights"].to(self.device, torch.float32)
+            b = params["X_TILDE/P_K/DENSE/biases"].to(self.device, torch.float32)
+            for c in range(K1):
+                rows = self._pk_rows(c)
+                wc = w[:, c::K1]
+                layer.w[rows, :layer.n_in] = wc[:layer.n_in].t()
+                layer.w[rows, layer.n_in] = b[c::K1]
+                layer.w[rows, layer.n_in + 1:] = 0
+                if layer.n_extra:
+                    layer.w[rows, layer.n_in + 1:layer.k_in] = wc[layer.n_in:].t()
+
+    def _pk_rows(self, c):
+        return slice((self.P + c) * self.Gn, (self.P + c) * self.Gn + self.G)
+
+    def _export_pk(self, buf, out):
+        if not self.k_max:
+            return
+        K1, layer = self.k_max + 1, self.head
+        w = torch.zeros(layer.n_in + layer.n_extra, self.G * K1)
+        b = torch.zeros(self.G * K1)
+        for c in range(K1):
+            rows = self._pk_rows(c)
+            w[:, c::K1] = self._tf_weight(buf, layer, rows)
+            b[c::K1] = buf[rows, layer.n_in].cpu()
+        out["X_TILDE/P_K/DENSE/weights"] = w
+        out["X_TILDE/P_K/DENSE/biases"] = b
 
     @staticmethod
     def _tf_weight(buf, layer, rows):
@@ -264,6 +308,7 @@ class VAEEngine:
                 out[scope + "/BATCH_NORM/beta"] = layer.beta.cpu().clone()
                 out[scope + "/BATCH_NORM/moving_mean"] = layer.moving_mean.cpu().clone()
                 out[scope + "/BATCH_NORM/moving_variance"] = layer.moving_var.cpu().clone()
+        self._export_pk(self.head.w, out)
         return out
 
     def export_gradients(self):
@@ -274,6 +319,7 @@ class VAEEngine:
             out[scope + "/DENSE/biases"] = layer.dw[rows, layer.n_in].contiguous().cpu()
             if layer.bn:
                 out[scope + "/BATCH_NORM/beta"] = layer.dbeta.cpu().clone()
+        self._export_pk(self.head.dw, out)
         return out
 
     def exchanged_ranges(self):
@@ -347,7 +393,7 @@ class VAEEngine:
         p.decH = [zeros(M, aug(l.n_out)) for l in self.dec]
         p.dec_mean = [zeros(l.n_out) for l in self.dec]
         p.dec_rstd = [zeros(l.n_out) for l in self.dec]
-        p.A = zeros(M, self.P * self.Gn)
+        p.A = zeros(M, self.PT * self.Gn)
         p.logp = zeros(M)
         p.go = zeros(M)
         p.bound = zeros(4)
@@ -410,7 +456,7 @@ class VAEEngine:
             return torch.zeros(*shape, dtype=f32, device=dev)
 
         B, M = p.B, p.M
-        p.dA = zeros(M, self.P * self.Gn)
+        p.dA = zeros(M, self.PT * self.Gn)
         p.d_decH = [zeros(M, aug(l.n_out)) for l in self.dec]
         p.d_decY = [zeros(M, round4(l.n_out)) for l in self.dec]
         p.dZ = zeros(M, self.Zp)
@@ -641,7 +687,10 @@ class VAEEngine:
 
     def _likelihood(self, p, tgt, A, M, rc, logp=None, da=None, go=None, go_scalar=1.0):
         """log p (+ gradient when ``da`` is given) of the M head rows in A (stand-alone kernels)."""
-        if self.constrained:
+        if self.k_max:
+            K.piecewise_likelihood(self.kind, self.k_max, tgt, A, self.Gn, M, self.G, logp=logp,
+                                   go=go, go_scalar=go_scalar, da=da)
+        elif self.constrained:
             K.constrained_poisson(tgt, A, M, self.G, p.count_sum_parameter, logp=logp, row_const=rc,
                                   go=go, go_scalar=go_scalar, da=da, lse=p.lse)
         elif da is not None:
@@ -846,6 +895,9 @@ class VAEEngine:
         RS = 1 if deterministic else R * S
         outs = [torch.empty(p.B, self.Gn, dtype=torch.float32, device=self.device)
                 for _ in range(3)]
+        if self.k_max:
+            K.piecewise_moments(self.kind, self.k_max, p.A, self.Gn, p.B, self.G, RS, *outs)
+            return [o[:, :self.G] for o in outs]
         if self.constrained:
             K.constrained_poisson_moments(p.A, p.lse, p.count_sum_parameter, p.B, self.G, RS, *outs)
             return [o[:, :self.G] for o in outs]

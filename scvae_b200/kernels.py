@@ -213,6 +213,24 @@ def gaussian_latent_bwd(ph, B, L, RS, eps, dz, kl_coef, dph, unit_variance=False
                "gaussian_latent_bwd")
 
 
+def piecewise_likelihood(kind, k_max, t, a, head_stride, M, G, logp=None, go=None, go_scalar=1.0,
+                         da=None):
+    """Categorised count likelihood (`-k`): P heads of ``kind`` + k_max + 1 class-logit heads."""
+    _f32(t, a)
+    lib = _lib.load()
+    _lib.check(lib.scvae_piecewise_likelihood(kind, k_max, _p(t), _ld(t), t.shape[0], _p(a), _ld(a),
+                                              head_stride, M, G, _p(go), float(go_scalar), _p(da),
+                                              _ld(da) if da is not None else 0, head_stride,
+                                              _p(logp), _stream()), "piecewise_likelihood")
+
+
+def piecewise_moments(kind, k_max, a, head_stride, B, G, RS, p_x_mean, p_x_stddev, stddev_of_mean):
+    lib = _lib.load()
+    _lib.check(lib.scvae_piecewise_moments(kind, k_max, _p(a), _ld(a), head_stride, B, G, RS,
+                                           _p(p_x_mean), _p(p_x_stddev), _p(stddev_of_mean),
+                                           _ld(p_x_mean), _stream()), "piecewise_moments")
+
+
 def constrained_poisson(t, a, M, G, count_sum, logp=None, row_const=None, go=None, go_scalar=1.0,
                         da=None, lse=None):
     """Constrained Poisson log p (and gradient when ``da`` is given); rows of t tile over M."""

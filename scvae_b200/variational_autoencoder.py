@@ -5,8 +5,7 @@ Same constructor keywords, ``train`` / ``evaluate`` / ``sample`` signatures, ret
 log-directory layout, checkpoint naming and TensorBoard tags; the TensorFlow graph, session
 and saver underneath are replaced by ``scvae_b200.engine.VAEEngine`` (hand-written sm_100a
 kernels behind ``libscvae_b200.so``).  Options of the reference that are outside the hot-path
-scope of this round (piecewise-categorical likelihood ``-k``, batch correction,
-count-sum features, dropout, LFM architectures, the exotic likelihoods) raise
+scope of this round (dropout, the continuous likelihoods) raise
 ``NotImplementedError`` instead of silently degrading.
 """
 
@@ -136,8 +135,10 @@ class VariationalAutoencoder:
         if self.reconstruction_distribution_name not in LIKELIHOOD_KINDS:
             problems.append("reconstruction distribution `{}`".format(
                 self.reconstruction_distribution_name))
-        if self.k_max:
-            problems.append("piecewise-categorical likelihoods (number_of_reconstruction_classes)")
+        if self.k_max and (self.type != "VAE"
+                           or self.reconstruction_distribution_name == "constrained poisson"):
+            problems.append("piecewise-categorical likelihoods (number_of_reconstruction_classes) "
+                            "for the GMVAE / the constrained Poisson")
         if (self.batch_correction or self.use_count_sum_as_feature
                 or self.inference_architecture != "MLP"
                 or self.generative_architecture != "MLP") and self.type != "VAE":
@@ -274,7 +275,8 @@ class VariationalAutoencoder:
                          number_of_batches=self.number_of_batches if self.batch_correction else 0,
                          count_sum_feature=bool(self.use_count_sum_as_feature),
                          inference_architecture=self.inference_architecture,
-                         generative_architecture=self.generative_architecture)
+                         generative_architecture=self.generative_architecture,
+                         number_of_reconstruction_classes=self.k_max)
 
     def _attach_features(self, data, data_set):
         """Per-cell decoder features of a data set (VAE:816-833): batch indices for batch

@@ -629,3 +629,60 @@ def test_constrained_poisson_kernel(G, tile):
         assert torch.allclose(outs[0][:, :G].cpu().double(), m_ref, rtol=1e-4, atol=1e-6)
         assert torch.allclose(outs[1][:, :G].cpu().double(), m_ref.sqrt(), rtol=1e-4, atol=1e-6)
         assert outs[2][:, :G].abs().max().item() <= 1e-4 * m_ref.max().item()   # one sample: sqrt of rounding
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("k_max", [1, 3])
+def test_piecewise_categorical_likelihood(kind, k_max):
+    """`-k`: log softmax(c)[min(x, k)] + [x >= k] log p_kind(x - k) (CAT:249-262), gradients of
+    every head and the Categorised moments (CAT:210-247) vs the fp64 oracle."""
+    from scvae_b200 import kernels as K
+    rng = numpy.random.RandomState(6)
+    B, G, tile = 5, 120, 2
+    M = B * tile
+    heads = O.LIKELIHOODS[kind]
+    P, K1 = len(heads), k_max + 1
+    Gn = (G + 3) & ~3
+    t = _counts(rng, B, G, 0.6)
+    a = (rng.randn(M, P + K1, Gn) * 1.5).astype(numpy.float32)
+    go = rng.randn(M).astype(numpy.float32)
+    t64 = torch.tensor(t, dtype=torch.float64).repeat(tile, 1)
+    a64 = [torch.tensor(a[:, h, :G], dtype=torch.float64, requires_grad=True) for h in range(P + K1)]
+    theta = {h: O._clip_head(x, h) for h, x in zip(heads, a64[:P])}
+    cat = torch.log_softmax(torch.stack(a64[P:], dim=-1), dim=-1)            # (M, G, K1)
+    cls = torch.clamp(t64, 0, k_max).long()
+    cat_lp = torch.gather(cat, 2, cls.unsqueeze(-1)).squeeze(-1)
+    dist_lp = O.likelihood_log_prob(kind, torch.clamp(t64 - k_max, min=0.0), theta)
+    lp = torch.where(t64 < k_max, cat_lp, cat_lp + dist_lp).sum(dim=1)
+    (lp * torch.tensor(go, dtype=torch.float64)).sum().backward()
+    dev = _dev()
+    td = torch.zeros(B, Gn, device=dev)
+    td[:, :G] = torch.tensor(t)
+    ad = torch.tensor(a.reshape(M, (P + K1) * Gn)).to(dev)
+    logp = torch.zeros(M, device=dev)
+    da = torch.zeros(M, (P + K1) * Gn, device=dev)
+    kid = K.LIKELIHOOD_KINDS[kind]
+    K.piecewise_likelihood(kid, k_max, td, ad, Gn, M, G, logp=logp, go=torch.tensor(go).to(dev), da=da)
+    torch.cuda.synchronize()
+    ref = lp.detach().numpy()
+    assert numpy.abs(logp.cpu().numpy() - ref).max() <= 3e-5 * numpy.abs(ref).max() + 1e-4
+    got = da.cpu().numpy().reshape(M, P + K1, Gn)
+    for h in range(P + K1):
+        g_ref = a64[h].grad.numpy()
+        assert numpy.abs(got[:, h, :G] - g_ref).max() <= 3e-5 * numpy.abs(g_ref).max() + 1e-5, (kind, h)
+    logp_f = torch.zeros(M, device=dev)
+    K.piecewise_likelihood(kid, k_max, td, ad, Gn, M, G, logp=logp_f)
+    torch.cuda.synchronize()
+    assert torch.allclose(logp_f, logp, rtol=1e-6, atol=1e-5)
+    # moments of the first B rows (one sample)
+    m, v = O.likelihood_moments(kind, {h: x[:B].detach() for h, x in theta.items()})
+    probs = torch.exp(cat[:B].detach())
+    ks = torch.arange(k_max, dtype=torch.float64)
+    mean = (probs[..., :k_max] * ks).sum(-1) + probs[..., k_max] * (m + k_max)
+    second = (probs[..., :k_max] * ks * ks).sum(-1) + probs[..., k_max] * (2 * k_max * m + v + m * m + k_max ** 2)
+    outs = [torch.zeros(B, Gn, device=dev) for _ in range(3)]
+    K.piecewise_moments(kid, k_max, ad, Gn, B, G, 1, *outs)
+    torch.cuda.synchronize()
+    assert torch.allclose(outs[0][:, :G].cpu().double(), mean, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(outs[1][:, :G].cpu().double(), (second - mean * mean).clamp(min=0).sqrt(),
+                          rtol=2e-3, atol=1e-3)

@@ -211,3 +211,21 @@ def test_train_evaluate_constrained_poisson(tmp_path):
     # the reconstruction of a constrained Poisson sums to the cell's count sum
     sums = reconstructed.values.sum(axis=1)
     assert numpy.allclose(sums, numpy.asarray(test.count_sum).reshape(-1), rtol=1e-3)
+
+
+def test_train_evaluate_piecewise_categorical(tmp_path):
+    """`-k 2`: piecewise-categorical negative binomial through the model class."""
+    from scvae_b200.variational_autoencoder import VariationalAutoencoder
+    from scvae_b200 import model_utilities as MU
+    full = _data(n=240, g=64, seed=10)
+    training, validation, test = full.split()
+    model = VariationalAutoencoder(
+        feature_size=64, latent_size=4, hidden_sizes=[32], reconstruction_distribution="negative binomial",
+        number_of_reconstruction_classes=2, log_directory=str(tmp_path), seed=1)
+    assert "k_2" in model.name
+    assert model.train(training, validation, number_of_epochs=3, minibatch_size=48,
+                       learning_rate=1e-2, shuffle_seed=0) == 0
+    curve = MU.load_learning_curves(model, "training")["lower_bound"]
+    assert len(curve) == 3 and numpy.isfinite(curve).all()
+    transformed, reconstructed, latent = model.evaluate(test, minibatch_size=64, output_versions="all")
+    assert numpy.isfinite(reconstructed.values).all() and (reconstructed.values >= 0).all()

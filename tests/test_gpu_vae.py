@@ -223,6 +223,9 @@ EXTRA_CASES = [
     ("constrained-poisson", 96, 6, [32], "constrained poisson", 48, dict()),
     ("constrained-poisson-extras", 100, 5, [24], "constrained poisson", 40,
      dict(number_of_batches=2, count_sum_feature=True)),
+    ("piecewise-nb-k2", 96, 6, [32], "negative binomial", 48, dict(number_of_reconstruction_classes=2)),
+    ("piecewise-zip-k3-extras", 100, 5, [24], "zero-inflated poisson", 40,
+     dict(number_of_reconstruction_classes=3, number_of_batches=2)),
 ]
 
 
@@ -281,7 +284,7 @@ def test_vae_decoder_extras_and_linear_factor_architectures(case, tensor_cores):
     if tensor_cores:
         # the 16-bit fused heads path handles the wider decoder input (not the softmax-coupled
         # constrained Poisson, which has its own row kernel)
-        assert plan.fused_done == (not constrained)
+        assert plan.fused_done == (not constrained and not cfg.k_max)
     tol = 5e-5 if not tensor_cores else 2e-3
     assert abs(bound[0] - out["lower_bound"].item()) <= tol * abs(out["lower_bound"].item())
     assert _rel(plan.PH[:, :L].cpu(), out["q_z_mean"]) <= tol
