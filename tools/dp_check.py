@@ -75,12 +75,10 @@ def main():
         scale = a.abs().max().item()
         if rank == 0:
             print("dp_check {}: max |nccl - p2p| = {:.3e} (scale {:.3e})".format(k, err, scale))
-        # (the step is not bit-reproducible run to run: multi-contributor reduce-adds feed fp16
-        # roundings; noise-level gradient entries then move by up to lr under Adam)
-        if k != "param":
-            assert err <= 2e-3 * scale + 1e-9, (k, err, scale)
-    # after 6 steps only statistically: parameters whose gradient is pure rounding noise (biases
-    # feeding a batch norm) move by +-lr per step in any fp32 implementation
+        # the step is bit-reproducible and a two-rank sum is commutative: the two exchange modes
+        # agree exactly (observed: 0.0); a few ulp of slack for other NCCL reduction orders
+        assert err <= 1e-6 * scale + 1e-12, (k, err, scale)
+    # after 6 steps
     a, b = results["nccl"]["param6"], results["p2p"]["param6"]
     frac = ((a - b).abs() > 1e-4).float().mean().item()
     rel = abs(results["nccl"]["bound"] - results["p2p"]["bound"]) / abs(results["nccl"]["bound"])
