@@ -161,3 +161,43 @@ def test_synthetic_counts_shape_and_sparsity():
     assert x.shape == (500, 40) and x.dtype == numpy.float32 and labels.shape == (500,)
     assert numpy.array_equal(x, numpy.round(x)) and x.min() >= 0
     assert 0.8 < (x == 0).mean() < 0.99
+
+
+def test_constrained_poisson_matches_scipy():
+    """Poisson(rate = softmax(a) * N): log-pmf against scipy, moments = rate."""
+    import scipy.stats
+    rng = numpy.random.RandomState(3)
+    a = torch.tensor(rng.randn(5, 9), dtype=D)
+    n = torch.tensor(rng.randint(1, 60, size=(5, 1)), dtype=D)
+    x = torch.tensor(rng.poisson(3.0, size=(5, 9)), dtype=D)
+    theta = {"lambda": O._clip_head(a, "lambda")}
+    lp = O.likelihood_log_prob("constrained poisson", x, theta, n)
+    rate = (torch.softmax(a, dim=-1) * n).numpy()
+    assert numpy.allclose(lp.numpy(), scipy.stats.poisson.logpmf(x.numpy(), rate), rtol=1e-12, atol=1e-12)
+    m, v = O.likelihood_moments("constrained poisson", theta, n)
+    assert numpy.allclose(m.numpy(), rate) and numpy.allclose(v.numpy(), rate)
+    assert numpy.allclose(m.sum(dim=1).numpy(), n.reshape(-1).numpy())      # rates sum to N
+
+
+@pytest.mark.parametrize("kind", ["poisson", "negative binomial", "zero-inflated negative binomial"])
+@pytest.mark.parametrize("k_max", [1, 3])
+def test_piecewise_categorical_normalisation_and_moments(kind, k_max):
+    """Categorised (CAT:210-274): the pmf sums to one and its mean / variance equal the closed
+    forms, by direct summation over the support."""
+    rng = numpy.random.RandomState(5)
+    n = 6
+    heads = O.LIKELIHOODS[kind]
+    a = {h: torch.tensor(rng.randn(n) * 0.7, dtype=D) for h in heads}
+    theta = {h: O._clip_head(v, h) for h, v in a.items()}
+    cat = torch.log_softmax(torch.tensor(rng.randn(n, k_max + 1), dtype=D), dim=-1)
+    xs = torch.arange(0, 4000, dtype=D)
+    theta_b = {h: v.unsqueeze(-1) for h, v in theta.items()}
+    lp = O.piecewise_log_prob(kind, xs.unsqueeze(0).expand(n, -1), theta_b, cat.unsqueeze(1).expand(-1, len(xs), -1), k_max)
+    p = torch.exp(lp)
+    assert torch.allclose(p.sum(dim=1), torch.ones(n, dtype=D), atol=1e-9)
+    m, v = O.likelihood_moments(kind, theta)
+    mean, var = O.piecewise_moments(m, v, cat, k_max)
+    mean_direct = (p * xs).sum(dim=1)
+    var_direct = (p * xs * xs).sum(dim=1) - mean_direct ** 2
+    assert torch.allclose(mean, mean_direct, rtol=1e-8, atol=1e-9)
+    assert torch.allclose(var, var_direct, rtol=1e-7, atol=1e-8)
