@@ -21,7 +21,9 @@
 
 namespace scvae {
 
-constexpr float kFastLogitMax = 80.f;   // e^80 and 1/(1+e^80) are normal fp32 numbers
+// |logit| <= 40: e^40 (1 + e^40) still fits fp32, which lets the zero-inflated forms below share
+// one reciprocal between pi and the zero-count responsibility
+constexpr float kFastLogitMax = 40.f;
 constexpr float kFastLogMax = 10.f;     // the reference's clip of log_r / log_lambda
 
 // two 16-bit targets of one 32-bit word -> fp32 (u16 via the 2^23 mantissa trick: no I2F)
@@ -137,11 +139,13 @@ __device__ __forceinline__ void fused_fast8(const float (&x)[8], const float (&a
         } else {
             // zero inflation, pi = sigmoid(a_pi):
             //   x > 0: log p = lp_d - softplus(a_pi);  x == 0: softplus(l0 - a_pi) + a_pi - softplus(a_pi)
+            // With tp = e^{a_pi}, up = 1 + tp, e0 = e^{l0} = p_d(0), s = tp + e0:
+            //   pi = tp / up,  x == 0: log p = log(s / up), responsibility of the count part
+            //   wz = e0 / s;   x > 0: log p = lp_d + log(1 / up).
+            // One reciprocal (of s up) and one log2 serve both cases: 4 MUFU for the inflation.
             const float api = a[0][j];
             const float tp = fast_ex2(api * kLog2e);
             const float up = 1.f + tp;
-            const float lgp = fast_lg2(up);
-            const float pi = tp * fast_rcp(up);
             float l0, lpd, gd0, gd1 = 0.f;
             if (T::NB) {
                 const float ap = a[iD][j], ar = a[iD + 1][j];
@@ -165,14 +169,15 @@ __device__ __forceinline__ void fused_fast8(const float (&x)[8], const float (&a
                 gd0 = xj - lam;
                 r[j] = 0.f;
             }
-            const float uu = l0 - api;
-            const float tu = fast_ex2(uu * kLog2e);
-            const float u2 = 1.f + tu;
-            const float lgu = fast_lg2(u2);
-            const float wz = tu * fast_rcp(u2);
+            const float e0 = fast_ex2(l0 * kLog2e);
+            const float sz = tp + e0;
+            const float inv = fast_rcp(sz * up);
+            const float inv_up = inv * sz, inv_s = inv * up;
+            const float pi = tp * inv_up;
+            const float wz = e0 * inv_s;
             const bool pos = xj > 0.f;
-            accA += pos ? lpd : api;
-            accB += pos ? lgp : lgp - lgu;
+            accA += pos ? lpd : 0.f;
+            accB -= fast_lg2(pos ? inv_up : sz * inv_up);
             g[0][j] = ((pos ? 0.f : 1.f - wz) - pi) * gsv;
             const float w = pos ? gsv : wz * gsv;
             g[1][j] = gd0 * w;
