@@ -143,7 +143,9 @@ class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
             self.reconstruction_distribution_name, self.minibatch_normalisation,
             self.kl_weight_value, self.prior_probabilities_method, self.prior_probabilities,
             self.proportion_of_free_nats_for_y_kl_divergence, device=self._device,
-            seed=self._seed, tensor_cores=self._tensor_cores)
+            seed=self._seed, tensor_cores=self._tensor_cores,
+            number_of_batches=self.number_of_batches if self.batch_correction else 0,
+            count_sum_feature=bool(self.use_count_sum_as_feature))
 
     def _evaluate_pass(self, engine, x_csr, t_csr, minibatch_size, R, S, deterministic=False,
                        seed=0, on_batch=None):
@@ -171,6 +173,10 @@ class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
             plan = engine._plan(rows, R * S)
             idx = torch.arange(i, i + rows, dtype=torch.int64, device=dev)
             engine.set_batch_csr(plan, data.indptr, data.indices, data.values, idx)
+            if engine.number_of_batches:
+                K.gather_f32(data.batch_index, idx, plan.batch_index)
+            if engine.count_sum_feature:
+                K.gather_f32(data.count_sum_feature, idx, plan.count_sum)
             K.fill_normal(plan.eps, seed, b)
             engine.forward(plan, False, R, S, 1.0)
             log[b].copy_(plan.bound)

@@ -27,7 +27,8 @@ class GMVAEEngine(VAEEngine):
                  reconstruction_distribution="poisson", minibatch_normalisation=True, kl_weight=1.0,
                  prior_probabilities_method="uniform", prior_probabilities=None,
                  proportion_of_free_nats_for_y_kl_divergence=0.0, device="cuda", seed=0,
-                 tensor_cores=True, head_buffer_bytes=4 << 30):
+                 tensor_cores=True, head_buffer_bytes=4 << 30, number_of_batches=0,
+                 count_sum_feature=False):
         if reconstruction_distribution not in K.LIKELIHOOD_KINDS:
             raise ValueError("reconstruction distribution `{}` is not supported by the "
                              "B200 hot path".format(reconstruction_distribution))
@@ -59,8 +60,13 @@ class GMVAEEngine(VAEEngine):
         self.Gn, self.Gp = round4(self.G), aug(self.G)
         self.world_size, self._all_reduce, self._plans = 1, None, {}
         self._side, self.overlap_streams, self._peer = None, False, None   # (VAE-engine-only features)
-        self.n_extra, self.number_of_batches, self.count_sum_feature = 0, 0, False
+        # decoder-input extras concatenated to every z_k (GMVAE:3097-3132), as in the VAE engine
+        self.number_of_batches = int(number_of_batches or 0)
+        self.count_sum_feature = bool(count_sum_feature)
+        self.n_extra = self.number_of_batches + (1 if self.count_sum_feature else 0)
+        self.Zp = round4(int(latent_size) + 1 + self.n_extra)
         self.lfm_inference = self.lfm_generative = False
+        self.constrained, self.k_max = False, 0
         self.unit_variance = False
         self.nL = 2 * self.L
 
@@ -77,7 +83,8 @@ class GMVAEEngine(VAEEngine):
         self.qz_head = _Layer("Z/Q/SOFTPLUS_GAUSSIAN", width, 2 * self.L, False)
         self.dec, width = [], self.L
         for i, h in enumerate(self.hidden_sizes[::-1]):
-            self.dec.append(_Layer("X/DECODER/LAYER_{}".format(i + 1), width, h, self.bn))
+            self.dec.append(_Layer("X/DECODER/LAYER_{}".format(i + 1), width, h, self.bn,
+                                   n_extra=self.n_extra if i == 0 else 0))
             width = h
         self.head = _Layer("X/DISTRIBUTION", width, self.P * self.Gn, False)
         self.enc = self.qy_enc + self.qz_enc          # every batch-normed encoder layer
@@ -164,7 +171,7 @@ class GMVAEEngine(VAEEngine):
                     params["Z/P/SOFTPLUS_GAUSSIAN/{}/DENSE/weights".format(name)] = xavier(self.K, self.L)
                     params["Z/P/SOFTPLUS_GAUSSIAN/{}/DENSE/biases".format(name)] = torch.zeros(self.L)
         for layer, rows, scope, _ in self._tf_tail():
-            params[scope + "/DENSE/weights"] = xavier(layer.n_in, rows.stop - rows.start)
+            params[scope + "/DENSE/weights"] = xavier(layer.n_in + layer.n_extra, rows.stop - rows.start)
             params[scope + "/DENSE/biases"] = torch.zeros(rows.stop - rows.start)
         self.import_parameters(params, strict=False)
         for buf in (self.store.grad, self.store.m, self.store.v):
@@ -184,9 +191,11 @@ class GMVAEEngine(VAEEngine):
                 self.qz_wy[:, :layer.n_out] = w[self.G:]
                 self.qz_wy[:, layer.n_out:] = 0
                 w = w[:self.G]
-            layer.w[rows, :layer.n_in] = w.t()
+            layer.w[rows, :layer.n_in] = w[:layer.n_in].t()
             layer.w[rows, layer.n_in] = b
             layer.w[rows, layer.n_in + 1:] = 0
+            if layer.n_extra:      # rows [n_in, n_in + extras) of the TF weight: batch one-hot, count sum
+                layer.w[rows, layer.n_in + 1:layer.k_in] = w[layer.n_in:].t()
             if layer.bn:
                 for key, dst in (("beta", layer.beta), ("moving_mean", layer.moving_mean),
                                  ("moving_variance", layer.moving_var)):
@@ -210,7 +219,7 @@ class GMVAEEngine(VAEEngine):
             out["Y/P/LOGITS"] = (self.d_py_logits if grads else self.py_logits).cpu().clone()
 
         def dense(layer, rows, scope):
-            w = pick(layer)[rows, :layer.n_in].t().contiguous().cpu()
+            w = self._tf_weight(pick(layer), layer, rows)
             if scope == "Z/Q/ENCODER/LAYER_1":
                 wy = (self.d_qz_wy if grads else self.qz_wy)[:, :layer.n_out].cpu()
                 w = torch.cat([w, wy], dim=0)
@@ -278,7 +287,9 @@ class GMVAEEngine(VAEEngine):
         p.QH = zeros(KB, round4(2 * L))
         p.PZ = zeros(Kc, 2 * L)
         p.eps = zeros(M, L)
-        p.Z = zeros(M, aug(L))
+        p.Z = zeros(M, self.Zp)
+        p.batch_index = zeros(B) if self.number_of_batches else None
+        p.count_sum = zeros(B) if self.count_sum_feature else None
         p.klz = zeros(M)
         p.kl_elem = None
         p.go, p.coef, p.logp = zeros(M), zeros(M), zeros(M)
@@ -322,7 +333,7 @@ class GMVAEEngine(VAEEngine):
         p.dA = zeros(Mc, self.P * self.Gn)
         p.d_decH = [zeros(Mc, aug(l.n_out)) for l in self.dec]
         p.d_decY = [zeros(Mc, round4(l.n_out)) for l in self.dec]
-        p.dZ = zeros(M, aug(L))
+        p.dZ = zeros(M, self.Zp)
         p.dQH = zeros(KB, round4(2 * L))
         p.dPZ = zeros(Kc, 2 * L)
         p.d_qzH = [zeros(KB, aug(l.n_out)) for l in self.qz_enc]
@@ -393,6 +404,7 @@ class GMVAEEngine(VAEEngine):
         # --- p(z|y=k) = FC(e_k) ---------------------------------------------------------------
         K.group_offset_fwd(self.pz_b, self.pz_w, Kc, 1, 2 * L, p.PZ)
         K.gmvae_latent_fwd(p.QH, p.PZ, Kc, B, L, RS, p.eps, p.Z, p.klz, p.kl_elem)
+        self._decoder_features(p, p.M)
         K.gmvae_row_coefficients(p.y, Kc, RS, B, weight, p.go, p.coef)
         # --- p(x|z_k): decoder + heads + likelihood, cluster chunk by cluster chunk -----------
         tgt = p.T if p.use_T else p.X
@@ -413,7 +425,7 @@ class GMVAEEngine(VAEEngine):
             r0, rows = c0 * rows_per_k, kc * rows_per_k
             d = p.Z[r0:r0 + rows]
             for j, l in enumerate(self.dec):
-                self._gemm(p, K.GEMM_NT, rows, l.n_out, l.n_in + 1, d, l.w, p.decY[j][:rows])
+                self._gemm(p, K.GEMM_NT, rows, l.n_out, l.k_in, d, l.w, p.decY[j][:rows])
                 self._bn_fwd(p, l, p.decY[j][:rows], p.decH[j][:rows], p.dec_mean[j], p.dec_rstd[j],
                              is_training, update_moving, kc)
                 d = p.decH[j]

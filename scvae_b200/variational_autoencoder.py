@@ -139,11 +139,9 @@ class VariationalAutoencoder:
                            or self.reconstruction_distribution_name == "constrained poisson"):
             problems.append("piecewise-categorical likelihoods (number_of_reconstruction_classes) "
                             "for the GMVAE / the constrained Poisson")
-        if (self.batch_correction or self.use_count_sum_as_feature
-                or self.inference_architecture != "MLP"
-                or self.generative_architecture != "MLP") and self.type != "VAE":
-            problems.append("batch correction, count-sum features and LFM architectures for the "
-                            "GMVAE")
+        if (self.inference_architecture != "MLP" or self.generative_architecture != "MLP") \
+                and self.type != "VAE":
+            problems.append("LFM architectures for the GMVAE")
         if self.inference_architecture not in ("MLP", "LFM") \
                 or self.generative_architecture not in ("MLP", "LFM"):
             raise ValueError("The inference and generative architectures can only be a neural "

@@ -110,3 +110,51 @@ def test_gmvae_evaluate_mode():
     assert (m[0].cpu().double() - out["p_x_mean"]).abs().max().item() <= 1e-4 * scale
     assert (m[1].cpu().double() - out["p_x_stddev"]).abs().max().item() <= 1e-4 * out["p_x_stddev"].abs().max().item()
     assert (m[2].cpu().double() - out["stddev_of_p_x_given_z_mean"]).abs().max().item() <= 1e-4 * scale
+
+
+@pytest.mark.parametrize("tensor_cores", [False, True], ids=["fp32", "tc"])
+@pytest.mark.parametrize("B", [40, 128])
+def test_gmvae_batch_correction_and_count_sum_feature(tensor_cores, B):
+    """Decoder-input extras concatenated to every z_k (GMVAE:3097-3132): forward, gradients and
+    one optimiser step against the oracle (B = 128 also takes the fused heads path)."""
+    from scvae_b200.gmvae_engine import GMVAEEngine
+    G, L, Kc, hidden, lik = 96, 4, 3, [24], "negative binomial"
+    opts = dict(number_of_batches=3, count_sum_feature=True)
+    cfg = O.GMVAEConfig(G, L, Kc, hidden, lik, 1, 1, True, kl_weight=1.0, **opts)
+    params = O.gmvae_init_params(cfg, seed=4, dtype=torch.float64)
+    gen = torch.Generator().manual_seed(7)
+    for k in params:
+        if k.endswith("biases") or k.endswith("beta"):
+            params[k] = torch.randn(params[k].shape, generator=gen, dtype=torch.float64) * 0.2
+    x, _ = O.synthetic_counts(B, G, n_types=3, seed=9, target_zero_fraction=0.8)
+    x = numpy.minimum(x, 100.0)
+    x64 = torch.tensor(x, dtype=torch.float64)
+    eps = torch.randn(Kc, 1, B, L, generator=gen, dtype=torch.float64)
+    batch = torch.randint(0, 3, (B, 1), generator=gen)
+    cs = x64.sum(dim=1)
+    cs = ((cs - cs.min()) / (cs.max() - cs.min())).reshape(B, 1)
+    feats = dict(batch_indices=batch, count_sum_feature=cs)
+    state = O.AdamState(params)
+    ref = {k: v.clone() for k, v in params.items()}
+    out, grads = O.train_step(cfg, ref, state, x64, x64, eps, 1e-3, **feats)
+    eng = GMVAEEngine(G, L, Kc, hidden, lik, True, 1.0, "uniform", None, 0.0, device="cuda:0",
+                      tensor_cores=tensor_cores, **opts)
+    eng.import_parameters(params)
+    plan = eng._plan(B, 1)
+    eng.set_batch_dense(plan, torch.tensor(x).cuda())
+    eng.set_batch_features(plan, batch.cuda(), cs.float().cuda())
+    plan.eps.copy_(eps.reshape(-1, L).float())
+    bound = eng.train_step(plan, 1, 1, 1e-3).cpu().numpy()
+    torch.cuda.synchronize()
+    assert plan.fused_done == (tensor_cores and B % 128 == 0)
+    tol = 5e-5 if not tensor_cores else 2e-3
+    for i, n in enumerate(["lower_bound", "lower_bound_weighted", "reconstruction_error"]):
+        assert abs(bound[i] - out[n].item()) <= tol * abs(out[n].item()) + 1e-5, (n, bound[i], out[n].item())
+    got = eng.export_gradients()
+    gtol = 3e-4 if not tensor_cores else 1e-2
+    gmax = max(g.abs().max().item() for g in grads.values())
+    floor = (1e-4 if plan.fused_done else 1e-5) * gmax
+    for k, g in grads.items():
+        assert got[k].shape == g.shape, (k, got[k].shape, g.shape)
+        err = (got[k].double() - g).abs().max().item()
+        assert err <= gtol * g.abs().max().item() + floor, (k, err, g.abs().max().item())

@@ -229,3 +229,25 @@ def test_train_evaluate_piecewise_categorical(tmp_path):
     assert len(curve) == 3 and numpy.isfinite(curve).all()
     transformed, reconstructed, latent = model.evaluate(test, minibatch_size=64, output_versions="all")
     assert numpy.isfinite(reconstructed.values).all() and (reconstructed.values >= 0).all()
+
+
+def test_gmvae_train_evaluate_with_batch_correction_and_count_sum(tmp_path):
+    from scvae_b200.data_set import DataSet
+    from scvae_b200.gaussian_mixture_variational_autoencoder import (
+        GaussianMixtureVariationalAutoencoder)
+    from scvae_b200 import model_utilities as MU
+    x, labels = O.synthetic_counts(240, 48, n_types=3, seed=12, target_zero_fraction=0.8)
+    x = numpy.minimum(x, 50.0)
+    full = DataSet("toy", values=scipy.sparse.csr_matrix(x), labels=labels.astype(str),
+                   batch_indices=(numpy.arange(240) % 2).reshape(-1, 1), batch_names=["a", "b"])
+    training, validation, test = full.split()
+    model = GaussianMixtureVariationalAutoencoder(
+        feature_size=48, latent_size=3, hidden_sizes=[24], number_of_latent_clusters=3,
+        reconstruction_distribution="negative binomial", batch_correction=True,
+        number_of_batches=2, count_sum=True, log_directory=str(tmp_path), seed=2)
+    assert model.train(training, validation, number_of_epochs=2, minibatch_size=48,
+                       learning_rate=5e-3, shuffle_seed=0) == 0
+    curve = MU.load_learning_curves(model, "training")["lower_bound"]
+    assert len(curve) == 2 and numpy.isfinite(curve).all()
+    transformed, reconstructed, latent = model.evaluate(test, minibatch_size=64, output_versions="all")
+    assert numpy.isfinite(reconstructed.values).all()
