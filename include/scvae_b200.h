@@ -187,14 +187,17 @@ int scvae_likelihood_bwd(int kind, const float *t, int64_t ldt, int t_rows, cons
  * VAE:2507-2532): log p(x) = log softmax(c)[min(x, k_max)] + [x >= k_max] log p_kind(x - k_max).
  * a (M, lda): the P heads of `kind` followed by the k_max + 1 class-logit heads (class-major),
  * all `head_stride` columns apart; da (nullable: forward only) has the same layout.  The
- * moments entry implements Categorised.mean / .variance (CAT:210-247) under VAE:2665-2713. */
+ * moments entry implements Categorised.mean / .variance (CAT:210-247) under VAE:2665-2713, for
+ * the GMVAE (K > 1, rows ordered (k, sample, cell), y = q(y|x) [B, K]) marginalised over the
+ * clusters as scvae_likelihood_moments. */
 int scvae_piecewise_likelihood(int kind, int k_max, const float *t, int64_t ldt, int t_rows,
                                const float *a, int64_t lda, int64_t head_stride, int M, int G,
                                const float *go, float go_scalar, float *da, int64_t ldda,
                                int64_t dhead_stride, float *logp, void *stream);
 int scvae_piecewise_moments(int kind, int k_max, const float *a, int64_t lda, int64_t head_stride,
-                            int B, int G, int RS, float *p_x_mean, float *p_x_stddev,
-                            float *stddev_of_mean, int64_t ldo, void *stream);
+                            int B, int G, int RS, int K, const float *y, int64_t ldy,
+                            float *p_x_mean, float *p_x_stddev, float *stddev_of_mean,
+                            int64_t ldo, void *stream);
 
 /* Constrained Poisson (DU "constrained poisson", VAE:2492-2496): rate[m, g] = N[m % t_rows] *
  * clip(softmax_g(a[m, :]), tiny, 1); count_sum [t_rows] is the cell's count sum N (fed by the

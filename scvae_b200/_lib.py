@@ -67,8 +67,8 @@ SIGNATURES = {
     "scvae_decoder_features": (c_int, [c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_int, c_ptr, c_ptr]),
     "scvae_piecewise_likelihood": (c_int, [c_int, c_int, c_ptr, c_i64, c_int, c_ptr, c_i64, c_i64, c_int,
                                            c_int, c_ptr, c_f32, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
-    "scvae_piecewise_moments": (c_int, [c_int, c_int, c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_ptr,
-                                        c_ptr, c_ptr, c_i64, c_ptr]),
+    "scvae_piecewise_moments": (c_int, [c_int, c_int, c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_int,
+                                        c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "scvae_constrained_poisson": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr,
                                           c_ptr, c_f32, c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     "scvae_constrained_poisson_moments": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr,

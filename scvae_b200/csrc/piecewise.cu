@@ -86,20 +86,23 @@ __device__ __forceinline__ void dist_moments(const float (&a)[3], float &m, floa
     }
 }
 
-// Categorised mean / variance (CAT:210-247) averaged over the RS samples as VAE:2665-2713
+// Categorised mean / variance (CAT:210-247) averaged over the RS samples as VAE:2665-2713 and,
+// for the GMVAE (K > 1, y = q(y|x) [B, K]), marginalised over the clusters with the y-weighted
+// per-cluster mean of GMVAE:3312-3386 (as moments_kernel in likelihood.cu).  Rows of a are
+// ordered (k, sample, cell).
 template <int KIND>
 __global__ void piecewise_moments_kernel(const float *__restrict__ a, int64_t lda, int64_t head_stride, int B, int G,
-                                         int RS, int k_max, float *__restrict__ p_x_mean,
-                                         float *__restrict__ p_x_stddev, float *__restrict__ stddev_of_mean,
-                                         int64_t ldo) {
+                                         int RS, int K, const float *__restrict__ y, int64_t ldy, int k_max,
+                                         float *__restrict__ p_x_mean, float *__restrict__ p_x_stddev,
+                                         float *__restrict__ stddev_of_mean, int64_t ldo) {
     constexpr int P = Lik<KIND>::P;
     const int g = blockIdx.y * blockDim.x + threadIdx.x;
     const int b = blockIdx.x;
     if (g >= G) return;
     const int K1 = k_max + 1;
     const float kf = (float)k_max, inv = 1.f / (float)RS;
-    auto moments = [&](int s, float &mean, float &var) {
-        const float *ap = a + ((int64_t)s * B + b) * lda + g;
+    auto moments = [&](int row, float &mean, float &var) {
+        const float *ap = a + ((int64_t)row * B + b) * lda + g;
         float c[kMaxClasses], mx = -INFINITY, se = 0.f;
         for (int k = 0; k < K1; ++k) {
             c[k] = ap[(int64_t)(P + k) * head_stride];
@@ -119,24 +122,31 @@ __global__ void piecewise_moments_kernel(const float *__restrict__ a, int64_t ld
         mean = m1 + pK * (dm + kf);
         var = m2 + pK * (2.f * kf * dm + dv + dm * dm + kf * kf) - mean * mean;
     };
-    float ms = 0.f, vs = 0.f;
-    for (int s = 0; s < RS; ++s) {
-        float m, v;
-        moments(s, m, v);
-        ms += m;
-        vs += v;
-    }
-    const float mean = ms * inv;
-    float dev = 0.f;
-    for (int s = 0; s < RS; ++s) {
-        float m, v;
-        moments(s, m, v);
-        dev += (m - mean) * (m - mean);
+    float mean_tot = 0.f, var_of_mean = 0.f, mean_of_var = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const float w = y ? y[(int64_t)b * ldy + k] : 1.f;
+        float ms = 0.f, vs = 0.f;
+        for (int s = 0; s < RS; ++s) {
+            float m, v;
+            moments(k * RS + s, m, v);
+            ms += m;
+            vs += v;
+        }
+        const float pm = ms * inv * w;
+        float dev = 0.f;
+        for (int s = 0; s < RS; ++s) {
+            float m, v;
+            moments(k * RS + s, m, v);
+            dev += (m - pm) * (m - pm);
+        }
+        mean_tot += pm;
+        var_of_mean += dev * inv * w;
+        mean_of_var += vs * inv * w;
     }
     const int64_t o = (int64_t)b * ldo + g;
-    if (p_x_mean) p_x_mean[o] = mean;
-    if (p_x_stddev) p_x_stddev[o] = sqrtf(dev * inv + vs * inv);
-    if (stddev_of_mean) stddev_of_mean[o] = sqrtf(dev * inv);
+    if (p_x_mean) p_x_mean[o] = mean_tot;
+    if (p_x_stddev) p_x_stddev[o] = sqrtf(var_of_mean + mean_of_var);
+    if (stddev_of_mean) stddev_of_mean[o] = sqrtf(var_of_mean);
 }
 
 }  // namespace scvae
@@ -176,17 +186,18 @@ extern "C" int scvae_piecewise_likelihood(int kind, int k_max, const float *t, i
 }
 
 extern "C" int scvae_piecewise_moments(int kind, int k_max, const float *a, int64_t lda, int64_t head_stride, int B,
-                                       int G, int RS, float *p_x_mean, float *p_x_stddev, float *stddev_of_mean,
-                                       int64_t ldo, void *stream) {
-    SCVAE_CHECK_ARG(a && B > 0 && G > 0 && RS > 0, "piecewise_moments: bad arguments");
+                                       int G, int RS, int K, const float *y, int64_t ldy, float *p_x_mean,
+                                       float *p_x_stddev, float *stddev_of_mean, int64_t ldo, void *stream) {
+    SCVAE_CHECK_ARG(a && B > 0 && G > 0 && RS > 0 && K > 0, "piecewise_moments: bad arguments");
+    SCVAE_CHECK_ARG(K == 1 || y, "piecewise_moments: K > 1 needs cluster weights y");
     SCVAE_CHECK_ARG(k_max >= 1 && k_max + 1 <= kMaxClasses, "piecewise_moments: k_max out of range");
     dim3 grid(B, (G + 255) / 256);
     cudaStream_t s = (cudaStream_t)stream;
     switch (kind) {
 #define CASE(KK)                                                                                          \
     case KK:                                                                                              \
-        piecewise_moments_kernel<KK><<<grid, 256, 0, s>>>(a, lda, head_stride, B, G, RS, k_max, p_x_mean, \
-                                                          p_x_stddev, stddev_of_mean, ldo);               \
+        piecewise_moments_kernel<KK><<<grid, 256, 0, s>>>(a, lda, head_stride, B, G, RS, K, y, ldy, k_max, \
+                                                          p_x_mean, p_x_stddev, stddev_of_mean, ldo);     \
         break;
         CASE(SCVAE_LIK_POISSON)
         CASE(SCVAE_LIK_NB)

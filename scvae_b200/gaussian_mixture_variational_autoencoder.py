@@ -145,7 +145,8 @@ class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
             self.proportion_of_free_nats_for_y_kl_divergence, device=self._device,
             seed=self._seed, tensor_cores=self._tensor_cores,
             number_of_batches=self.number_of_batches if self.batch_correction else 0,
-            count_sum_feature=bool(self.use_count_sum_as_feature))
+            count_sum_feature=bool(self.use_count_sum_as_feature),
+            number_of_reconstruction_classes=self.k_max)
 
     def _evaluate_pass(self, engine, x_csr, t_csr, minibatch_size, R, S, deterministic=False,
                        seed=0, on_batch=None):

@@ -23,12 +23,14 @@ from .engine import (ADAM_BETA1, ADAM_BETA2, ADAM_EPSILON, GRADIENT_CLIP, Parame
 
 
 class GMVAEEngine(VAEEngine):
+    PK_SCOPE = "X/DISTRIBUTION/P_K"
+
     def __init__(self, feature_size, latent_size, number_of_latent_clusters, hidden_sizes=(100,),
                  reconstruction_distribution="poisson", minibatch_normalisation=True, kl_weight=1.0,
                  prior_probabilities_method="uniform", prior_probabilities=None,
                  proportion_of_free_nats_for_y_kl_divergence=0.0, device="cuda", seed=0,
                  tensor_cores=True, head_buffer_bytes=4 << 30, number_of_batches=0,
-                 count_sum_feature=False):
+                 count_sum_feature=False, number_of_reconstruction_classes=0):
         if reconstruction_distribution not in K.LIKELIHOOD_KINDS:
             raise ValueError("reconstruction distribution `{}` is not supported by the "
                              "B200 hot path".format(reconstruction_distribution))
@@ -66,7 +68,13 @@ class GMVAEEngine(VAEEngine):
         self.n_extra = self.number_of_batches + (1 if self.count_sum_feature else 0)
         self.Zp = round4(int(latent_size) + 1 + self.n_extra)
         self.lfm_inference = self.lfm_generative = False
-        self.constrained, self.k_max = False, 0
+        self.constrained = False
+        # piecewise-categorical likelihood (`-k`, head P_K GMVAE:3192-3218): k_max + 1 class-logit
+        # head blocks behind the P heads; its own row kernel, never the fused heads
+        self.k_max = int(number_of_reconstruction_classes or 0)
+        self.PT = self.P + (self.k_max + 1 if self.k_max else 0)
+        if self.k_max:
+            self.fused_heads = False
         self.unit_variance = False
         self.nL = 2 * self.L
 
@@ -86,7 +94,7 @@ class GMVAEEngine(VAEEngine):
             self.dec.append(_Layer("X/DECODER/LAYER_{}".format(i + 1), width, h, self.bn,
                                    n_extra=self.n_extra if i == 0 else 0))
             width = h
-        self.head = _Layer("X/DISTRIBUTION", width, self.P * self.Gn, False)
+        self.head = _Layer("X/DISTRIBUTION", width, self.PT * self.Gn, False)
         self.enc = self.qy_enc + self.qz_enc          # every batch-normed encoder layer
         self._dense = self.qy_enc + [self.qy_logits] + self.qz_enc + [self.qz_head] + self.dec + \
             [self.head]
@@ -173,6 +181,10 @@ class GMVAEEngine(VAEEngine):
         for layer, rows, scope, _ in self._tf_tail():
             params[scope + "/DENSE/weights"] = xavier(layer.n_in + layer.n_extra, rows.stop - rows.start)
             params[scope + "/DENSE/biases"] = torch.zeros(rows.stop - rows.start)
+        if self.k_max:
+            fan_out = self.G * (self.k_max + 1)
+            params[self.PK_SCOPE + "/DENSE/weights"] = xavier(self.head.n_in, fan_out)
+            params[self.PK_SCOPE + "/DENSE/biases"] = torch.zeros(fan_out)
         self.import_parameters(params, strict=False)
         for buf in (self.store.grad, self.store.m, self.store.v):
             buf.zero_()
@@ -204,6 +216,15 @@ class GMVAEEngine(VAEEngine):
                         dst.copy_(params[name].to(dev, torch.float32))
                     elif strict:
                         raise KeyError(name)
+        if self.k_max:      # class-minor P_K variable -> one block of Gn rows per class
+            K1, layer = self.k_max + 1, self.head
+            w = params[self.PK_SCOPE + "/DENSE/weights"].to(dev, torch.float32)
+            b = params[self.PK_SCOPE + "/DENSE/biases"].to(dev, torch.float32)
+            for c in range(K1):
+                rows = self._pk_rows(c)
+                layer.w[rows, :layer.n_in] = w[:, c::K1].t()
+                layer.w[rows, layer.n_in] = b[c::K1]
+                layer.w[rows, layer.n_in + 1:] = 0
         for j, name in enumerate(("MEAN", "SOFTPLUS_SCALE")):
             cols = slice(j * self.L, (j + 1) * self.L)
             scope = "Z/P/SOFTPLUS_GAUSSIAN/" + name
@@ -240,6 +261,11 @@ class GMVAEEngine(VAEEngine):
             out[scope + "/DENSE/biases"] = (self.d_pz_b if grads else self.pz_b)[0, cols].cpu().clone()
         for layer, rows, scope, _ in self._tf_tail():
             dense(layer, rows, scope)
+        if self.k_max:
+            pk = OrderedDict()
+            self._export_pk(pick(self.head), pk)
+            out[self.PK_SCOPE + "/DENSE/weights"] = pk["X_TILDE/P_K/DENSE/weights"]
+            out[self.PK_SCOPE + "/DENSE/biases"] = pk["X_TILDE/P_K/DENSE/biases"]
         return out
 
     def export_parameters(self):
@@ -257,7 +283,7 @@ class GMVAEEngine(VAEEngine):
         Kc, L = self.K, self.L
         KB, M = Kc * B, Kc * RS * B
         # clusters per decoder chunk: bound the two (rows, P*Gn) head buffers
-        per_cluster = RS * B * self.P * self.Gn * 4 * 2
+        per_cluster = RS * B * self.PT * self.Gn * 4 * 2
         chunk = max(1, min(Kc, self.head_buffer_bytes // max(per_cluster, 1)))
         p = type("Plan", (), {})()
         p.B, p.RS, p.M, p.KB, p.chunk = B, RS, M, KB, chunk
@@ -298,7 +324,7 @@ class GMVAEEngine(VAEEngine):
         p.decH = [zeros(Mc, aug(l.n_out)) for l in self.dec]
         p.dec_mean = [zeros(chunk * l.n_out) for l in self.dec]
         p.dec_rstd = [zeros(chunk * l.n_out) for l in self.dec]
-        p.A = zeros(Mc, self.P * self.Gn)
+        p.A = zeros(Mc, self.PT * self.Gn)
         p.bound = zeros(6)
         p.ll_mean, p.klz_mean = zeros(Kc, B), zeros(Kc, B)
         p.z_mean = zeros(B, L)
@@ -330,7 +356,7 @@ class GMVAEEngine(VAEEngine):
 
         B, KB, M, Kc, L = p.B, p.KB, p.M, self.K, self.L
         Mc = p.chunk * p.RS * B
-        p.dA = zeros(Mc, self.P * self.Gn)
+        p.dA = zeros(Mc, self.PT * self.Gn)
         p.d_decH = [zeros(Mc, aug(l.n_out)) for l in self.dec]
         p.d_decY = [zeros(Mc, round4(l.n_out)) for l in self.dec]
         p.dZ = zeros(M, self.Zp)
@@ -451,12 +477,11 @@ class GMVAEEngine(VAEEngine):
                 continue
             self._gemm(p, K.GEMM_NT, rows, l.n_out, l.n_in + 1, d, l.w, p.A[:rows])
             if with_backward:
-                K.likelihood_bwd(self.kind, tgt, p.A[:rows], self.Gn, rows, self.G, p.dA[:rows],
-                                 logp=p.logp[r0:r0 + rows], row_const=rc, go=p.go[r0:r0 + rows])
+                self._likelihood(p, tgt, p.A[:rows], rows, rc, logp=p.logp[r0:r0 + rows],
+                                 da=p.dA[:rows], go=p.go[r0:r0 + rows])
                 self._decoder_backward(p, r0, rows, kc, accumulate=c0 > 0)
             else:
-                K.likelihood_fwd(self.kind, tgt, p.A[:rows], self.Gn, rows, self.G,
-                                 p.logp[r0:r0 + rows], row_const=rc)
+                self._likelihood(p, tgt, p.A[:rows], rows, rc, logp=p.logp[r0:r0 + rows])
             if getattr(p, "on_chunk", None) is not None:
                 p.on_chunk(c0, kc, rows)
         thr = 0.0
@@ -562,10 +587,14 @@ class GMVAEEngine(VAEEngine):
                              "size or raise head_buffer_bytes")
         outs = [torch.empty(p.B, self.Gn, dtype=torch.float32, device=self.device)
                 for _ in range(3)]
+        if self.k_max:
+            K.piecewise_moments(self.kind, self.k_max, p.A, self.Gn, p.B, self.G, p.RS, *outs,
+                                K_=self.K, y=p.y)
+            return [o[:, :self.G] for o in outs]
         K.likelihood_moments(self.kind, p.A, self.Gn, p.B, self.G, p.RS, self.K, p.y, *outs)
         return [o[:, :self.G] for o in outs]
 
     def max_single_chunk_minibatch(self, RS):
         """Largest minibatch whose K cluster passes fit the head buffers in one chunk."""
-        per_cell = self.K * RS * self.P * self.Gn * 4 * 2
+        per_cell = self.K * RS * self.PT * self.Gn * 4 * 2
         return max(1, self.head_buffer_bytes // per_cell)

@@ -224,11 +224,13 @@ def piecewise_likelihood(kind, k_max, t, a, head_stride, M, G, logp=None, go=Non
                                               _p(logp), _stream()), "piecewise_likelihood")
 
 
-def piecewise_moments(kind, k_max, a, head_stride, B, G, RS, p_x_mean, p_x_stddev, stddev_of_mean):
+def piecewise_moments(kind, k_max, a, head_stride, B, G, RS, p_x_mean, p_x_stddev, stddev_of_mean,
+                      K_=1, y=None):
     lib = _lib.load()
-    _lib.check(lib.scvae_piecewise_moments(kind, k_max, _p(a), _ld(a), head_stride, B, G, RS,
-                                           _p(p_x_mean), _p(p_x_stddev), _p(stddev_of_mean),
-                                           _ld(p_x_mean), _stream()), "piecewise_moments")
+    _lib.check(lib.scvae_piecewise_moments(kind, k_max, _p(a), _ld(a), head_stride, B, G, RS, K_,
+                                           _p(y), _ld(y) if y is not None else 0, _p(p_x_mean),
+                                           _p(p_x_stddev), _p(stddev_of_mean), _ld(p_x_mean),
+                                           _stream()), "piecewise_moments")
 
 
 def constrained_poisson(t, a, M, G, count_sum, logp=None, row_const=None, go=None, go_scalar=1.0,

@@ -135,10 +135,9 @@ class VariationalAutoencoder:
         if self.reconstruction_distribution_name not in LIKELIHOOD_KINDS:
             problems.append("reconstruction distribution `{}`".format(
                 self.reconstruction_distribution_name))
-        if self.k_max and (self.type != "VAE"
-                           or self.reconstruction_distribution_name == "constrained poisson"):
+        if self.k_max and self.reconstruction_distribution_name == "constrained poisson":
             problems.append("piecewise-categorical likelihoods (number_of_reconstruction_classes) "
-                            "for the GMVAE / the constrained Poisson")
+                            "around the constrained Poisson")
         if (self.inference_architecture != "MLP" or self.generative_architecture != "MLP") \
                 and self.type != "VAE":
             problems.append("LFM architectures for the GMVAE")

@@ -158,3 +158,48 @@ def test_gmvae_batch_correction_and_count_sum_feature(tensor_cores, B):
         assert got[k].shape == g.shape, (k, got[k].shape, g.shape)
         err = (got[k].double() - g).abs().max().item()
         assert err <= gtol * g.abs().max().item() + floor, (k, err, g.abs().max().item())
+
+
+@pytest.mark.parametrize("lik", ["negative binomial", "zero-inflated poisson"])
+def test_gmvae_piecewise_categorical(lik):
+    """`-k` for the GMVAE (head P_K, GMVAE:3192-3220): step parity and the y-marginalised moments."""
+    from scvae_b200.gmvae_engine import GMVAEEngine
+    G, L, Kc, hidden, B, k_max = 80, 4, 3, [20], 36, 2
+    cfg = O.GMVAEConfig(G, L, Kc, hidden, lik, 1, 2, True, kl_weight=1.0,
+                        number_of_reconstruction_classes=k_max)
+    params = O.gmvae_init_params(cfg, seed=5, dtype=torch.float64)
+    gen = torch.Generator().manual_seed(8)
+    for k in params:
+        if k.endswith("biases") or k.endswith("beta"):
+            params[k] = torch.randn(params[k].shape, generator=gen, dtype=torch.float64) * 0.2
+    x, _ = O.synthetic_counts(B, G, n_types=3, seed=10, target_zero_fraction=0.7)
+    x = numpy.minimum(x, 60.0)
+    x64 = torch.tensor(x, dtype=torch.float64)
+    eps = torch.randn(Kc, 2, B, L, generator=gen, dtype=torch.float64)
+    state = O.AdamState(params)
+    ref = {k: v.clone() for k, v in params.items()}
+    out_m = O.gmvae_forward(cfg, params, x64, x64, eps, is_training=True, moments=True)
+    out, grads = O.train_step(cfg, ref, state, x64, x64, eps, 1e-3)
+    eng = GMVAEEngine(G, L, Kc, hidden, lik, True, 1.0, "uniform", None, 0.0, device="cuda:0",
+                      tensor_cores=False, number_of_reconstruction_classes=k_max)
+    eng.import_parameters(params)
+    plan = eng._plan(B, 2)
+    eng.set_batch_dense(plan, torch.tensor(x).cuda())
+    plan.eps.copy_(eps.reshape(-1, L).float())
+    eng.forward(plan, True, 1, 2, 1.0, update_moving=False)
+    m = eng.moments(plan, 1, 2)
+    torch.cuda.synchronize()
+    scale = out_m["p_x_mean"].abs().max().item()
+    assert (m[0].cpu().double() - out_m["p_x_mean"]).abs().max().item() <= 1e-4 * scale
+    sd_scale = out_m["p_x_stddev"].abs().max().item()
+    assert (m[1].cpu().double() - out_m["p_x_stddev"]).abs().max().item() <= 2e-4 * sd_scale
+    bound = eng.train_step(plan, 1, 2, 1e-3).cpu().numpy()
+    torch.cuda.synchronize()
+    for i, n in enumerate(["lower_bound", "lower_bound_weighted", "reconstruction_error"]):
+        assert abs(bound[i] - out[n].item()) <= 5e-5 * abs(out[n].item()) + 1e-5, (n, bound[i], out[n].item())
+    got = eng.export_gradients()
+    gmax = max(g.abs().max().item() for g in grads.values())
+    for k, g in grads.items():
+        assert got[k].shape == g.shape, (k, got[k].shape, g.shape)
+        err = (got[k].double() - g).abs().max().item()
+        assert err <= 3e-4 * g.abs().max().item() + 1e-5 * gmax, (k, err, g.abs().max().item())
