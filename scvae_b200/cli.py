@@ -36,6 +36,12 @@ def _setup_model(data_set, arguments):
         reconstruction_distribution=arguments.reconstruction_distribution,
         number_of_reconstruction_classes=arguments.number_of_reconstruction_classes,
         minibatch_normalisation=arguments.minibatch_normalisation,
+        inference_architecture=arguments.inference_architecture,
+        generative_architecture=arguments.generative_architecture,
+        batch_correction=arguments.batch_correction,
+        number_of_batches=(data_set.number_of_batches if arguments.batch_correction else None),
+        count_sum=arguments.count_sum,
+        dropout_keep_probabilities=arguments.dropout_keep_probabilities,
         number_of_warm_up_epochs=arguments.number_of_warm_up_epochs,
         kl_weight=arguments.kl_weight, log_directory=arguments.models_directory)
     model_type = arguments.model_type.upper()
@@ -127,6 +133,13 @@ def _parser():
                          default=m["minibatch_normalisation"])
         sub.add_argument("--no-minibatch-normalisation", dest="minibatch_normalisation",
                          action="store_false")
+        sub.add_argument("--inference-architecture", default=m["inference_architecture"])
+        sub.add_argument("--generative-architecture", default=m["generative_architecture"])
+        sub.add_argument("--batch-correction", "--bc", action="store_true",
+                         default=m["batch_correction"])
+        sub.add_argument("--count-sum", action="store_true", default=m["count_sum"])
+        sub.add_argument("--dropout-keep-probabilities", type=float, nargs="+",
+                         default=m["dropout_keep_probabilities"])
         sub.add_argument("--minibatch-size", "-B", type=int, default=m["minibatch_size"])
         sub.add_argument("--run-id", default=m["run_id"])
         sub.add_argument("--models-directory", "-M", default=m["directory"])

@@ -46,6 +46,15 @@ class DataSet:
         if values is not None:
             self.update(values=values)
 
+    @property
+    def number_of_batches(self):
+        """Number of distinct batches (DataSet.number_of_batches of the reference, DS:309-316)."""
+        if self.batch_names is not None:
+            return len(self.batch_names)
+        if self.batch_indices is None:
+            return None
+        return int(numpy.asarray(self.batch_indices).max()) + 1
+
     def update(self, values=None, **_):
         if values is not None:
             if not scipy.sparse.issparse(values):
