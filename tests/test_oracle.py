@@ -201,3 +201,41 @@ def test_piecewise_categorical_normalisation_and_moments(kind, k_max):
     var_direct = (p * xs * xs).sum(dim=1) - mean_direct ** 2
     assert torch.allclose(mean, mean_direct, rtol=1e-8, atol=1e-9)
     assert torch.allclose(var, var_direct, rtol=1e-7, atol=1e-8)
+
+
+def test_dropout_sites_and_gradients():
+    """Dropout restated for the next build step (MU:45-50; independent masks per head,
+    VAE:2286,2487): identity in evaluation, inverted scaling in training, autograd vs finite
+    differences with the masks held fixed."""
+    cfg = O.VAEConfig(12, 3, [6, 5], "negative binomial", dropout_keep_probabilities=[0.8, 0.7, 0.9])
+    params = O.vae_init_params(cfg, 2, D)
+    x = torch.tensor(O.synthetic_counts(5, 12, seed=3)[0], dtype=D).clamp(max=30)
+    eps = torch.randn(1, 5, 3, generator=torch.Generator().manual_seed(0), dtype=D)
+    drop = {"generator": torch.Generator().manual_seed(4)}
+    out = O.vae_forward(cfg, params, x, x, eps, True, dropout=drop)
+    sites = set(drop["masks"])
+    assert sites == {"ENCODER/1", "ENCODER/2", "POSTERIOR/MU", "POSTERIOR/LOG_SIGMA", "DECODER/2",
+                     "DECODER/1", "X_TILDE/P", "X_TILDE/LOG_R"}
+    assert drop["masks"]["ENCODER/1"].shape == x.shape            # keep_x on the input counts
+    assert not torch.equal(drop["masks"]["X_TILDE/P"], drop["masks"]["X_TILDE/LOG_R"])
+    # evaluation mode and all-ones masks are the un-dropped graph (up to the 1 / keep scaling)
+    plain = O.vae_forward(cfg, params, x, x, eps, False)["lower_bound"]
+    assert torch.equal(O.vae_forward(cfg, params, x, x, eps, False, dropout=drop)["lower_bound"], plain)
+    assert not torch.equal(out["lower_bound"], O.vae_forward(cfg, params, x, x, eps, True)["lower_bound"])
+    # gradients with the masks fixed
+    names = O.trainable_names(params)
+    leaves = {k: params[k].clone().requires_grad_(True) for k in names}
+    local = {k: leaves.get(k, v) for k, v in params.items()}
+    loss = -O.vae_forward(cfg, local, x, x, eps, True, dropout=drop)["lower_bound_weighted"]
+    grads = dict(zip(names, torch.autograd.grad(loss, [leaves[k] for k in names])))
+    rng = numpy.random.RandomState(1)
+    for name in names:
+        flat = params[name].reshape(-1)
+        idx = int(rng.randint(flat.numel()))
+        vals = []
+        for sgn in (+1, -1):
+            p2 = {k: v.clone() for k, v in params.items()}
+            p2[name].reshape(-1)[idx] += sgn * 1e-6
+            vals.append(-O.vae_forward(cfg, p2, x, x, eps, True, dropout=drop)["lower_bound_weighted"].item())
+        fd = (vals[0] - vals[1]) / 2e-6
+        assert abs(fd - grads[name].reshape(-1)[idx].item()) <= 1e-5 * max(1.0, abs(fd)), name
