@@ -11,8 +11,11 @@ stand-in modules for the missing imports.  Fixtures:
   development_data_set.npz   the reference's deterministic synthetic data set
                              (``_create_development_data_set``, loaders.py:942-1022,
                              RandomState(60)): values (10000 x 25), labels.
-  split_indices.npz          ``split_data_set`` default/random split indices for N=1000
-                             (processing.py:336-493, RandomState(42)).
+  normalise_string.npz       ``scvae.utilities.normalise_string`` on distribution / data names.
+  model_utilities.json       the pure-Python helpers of ``scvae/models/utilities.py`` that the CLI
+                             and the model classes call (MU:140-176, :591-613, :647-658,
+                             :755-898, :973-990) and ``format_duration`` of ``scvae/utilities.py``:
+                             inputs -> outputs (or the exception type raised).
 """
 
 import hashlib
@@ -51,6 +54,88 @@ def import_reference_modules():
     return utilities, loaders
 
 
+def import_reference_model_utilities():
+    """scvae/models/utilities.py with stand-ins for TensorFlow (only its graph helpers use it)."""
+    tf = types.ModuleType("tensorflow")
+    tf.reduce_mean = None
+    contrib = types.ModuleType("tensorflow.contrib")
+    layers = types.ModuleType("tensorflow.contrib.layers")
+    layers.fully_connected = layers.batch_norm = layers.dropout = None
+    sys.modules.update({"tensorflow": tf, "tensorflow.contrib": contrib,
+                        "tensorflow.contrib.layers": layers})
+    models_pkg = types.ModuleType("scvae.models")
+    models_pkg.__path__ = [os.path.join(REFERENCE, "scvae", "models")]
+    sys.modules["scvae.models"] = models_pkg
+    return _load_by_path("scvae.models.utilities",
+                         os.path.join(REFERENCE, "scvae", "models", "utilities.py"))
+
+
+def _record(function, *args, **kwargs):
+    try:
+        value = function(*args, **kwargs)
+        if isinstance(value, tuple):
+            value = list(value)
+        return {"args": list(args), "kwargs": kwargs, "result": value}
+    except Exception as exc:            # the type is part of the contract (SURVEY 8b "Errors")
+        return {"args": list(args), "kwargs": kwargs, "raises": type(exc).__name__}
+
+
+def model_utilities_golden(utilities):
+    import json
+    MU = import_reference_model_utilities()
+    nan = float("nan")
+    records = {
+        "parse_numbers_of_samples": [_record(MU.parse_numbers_of_samples, a) for a in
+                                     (1, [5], [5, 2], {"training": 3, "evaluation": 7}, [1, 2, 3])],
+        "parse_model_versions": [_record(MU.parse_model_versions, a) for a in
+                                 ("all", ["all"], "best_model", ["end_of_training", "early_stopping"],
+                                  ["e", "b"], "nonsense")],
+        "early_stopping_status": [_record(MU.early_stopping_status, a, b) for a, b in
+                                  (([-10, -9, -9.5, -9.6, -9.7], 2), ([-10, -9, -8], 10),
+                                   ([-5, -6, -7, -8], 3), ([-5.0], 10), ([-3, -2, -2.5], 1))],
+        "check_run_id": [_record(MU.check_run_id, a) for a in
+                         ("Run_1", "2019-run", "bad id!", "a/b", "")],
+        "validate_model_parameters": [
+            _record(MU.validate_model_parameters, **kw) for kw in (
+                dict(reconstruction_distribution="negative binomial", number_of_reconstruction_classes=3,
+                     model_type="VAE", latent_distribution="gaussian", parameterise_latent_posterior=False),
+                dict(reconstruction_distribution="zero-inflated poisson", number_of_reconstruction_classes=2,
+                     model_type="VAE", latent_distribution="gaussian", parameterise_latent_posterior=False),
+                dict(reconstruction_distribution="constrained poisson", number_of_reconstruction_classes=2,
+                     model_type="VAE", latent_distribution="gaussian", parameterise_latent_posterior=False),
+                dict(reconstruction_distribution="bernoulli", number_of_reconstruction_classes=1,
+                     model_type="VAE", latent_distribution="gaussian", parameterise_latent_posterior=False),
+                dict(reconstruction_distribution="poisson", number_of_reconstruction_classes=0,
+                     model_type="GMVAE", latent_distribution="gaussian mixture",
+                     parameterise_latent_posterior=False),
+                dict(reconstruction_distribution="poisson", number_of_reconstruction_classes=0,
+                     model_type="VAE", latent_distribution="gaussian mixture",
+                     parameterise_latent_posterior=True),
+            )],
+        "build_training_string": [_record(MU.build_training_string, *a) for a in
+                                  (("model", 0, 10, "training set"), ("model for run r", 3, 10, "training set"),
+                                   ("model", 10, 10, "training set"), ("model", 12, 10, "full set"))],
+        "format_duration": [_record(utilities.format_duration, a) for a in
+                            (0.0004, 0.5, 3.2, 75, 3700, 90000)],
+    }
+
+    def clean(o):
+        if isinstance(o, float) and o != o:
+            return "nan"
+        if isinstance(o, dict):
+            return {k: clean(v) for k, v in o.items()}
+        if isinstance(o, (list, tuple)):
+            return [clean(v) for v in o]
+        if isinstance(o, (numpy.bool_, bool)):
+            return bool(o)
+        if isinstance(o, numpy.generic):
+            return o.item()
+        return o
+    with open(os.path.join(OUT, "model_utilities.json"), "w") as handle:
+        json.dump(clean(records), handle, indent=1, sort_keys=True)
+    print("model utilities:", {k: len(v) for k, v in records.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     utilities, loaders = import_reference_modules()
@@ -72,6 +157,7 @@ def main():
                 inputs=numpy.array(samples), outputs=numpy.array(
                     [utilities.normalise_string(s) for s in samples]))
     print("normalise_string:", [utilities.normalise_string(s) for s in samples])
+    model_utilities_golden(utilities)
 
 
 if __name__ == "__main__":

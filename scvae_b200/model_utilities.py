@@ -472,5 +472,11 @@ def build_training_string(model_string, epoch_start, number_of_epochs, data_stri
     if epoch_start < number_of_epochs:
         return "Continue training {} for {} additionally epochs (up to {} epochs) on {}.".format(
             model_string, number_of_epochs - epoch_start, number_of_epochs, data_string)
-    return "{} has already been trained for {} epochs on {}.".format(
-        model_string[0].upper() + model_string[1:], epoch_start, data_string)
+    subject = model_string[0].upper() + model_string[1:]
+    if epoch_start == number_of_epochs:
+        return "{} has already been trained for {} epochs on {}.".format(
+            subject, number_of_epochs, data_string)
+    # trained beyond the requested number of epochs (MU:163-171)
+    return ("{} has already been trained for more than {} epochs on {}. "
+            "Loading model trained for {} epochs.").format(
+                subject, number_of_epochs, data_string, epoch_start)
