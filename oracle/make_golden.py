@@ -16,6 +16,13 @@ stand-in modules for the missing imports.  Fixtures:
                              and the model classes call (MU:140-176, :591-613, :647-658,
                              :755-898, :973-990) and ``format_duration`` of ``scvae/utilities.py``:
                              inputs -> outputs (or the exception type raised).
+  model_names.json           ``name`` / ``description`` / ``log_directory()`` of the reference's
+                             ``VariationalAutoencoder`` (VAE:412-608) and
+                             ``GaussianMixtureVariationalAutoencoder`` (GMVAE:441-640) classes for
+                             a sweep of constructor options: the on-disk naming contract.  The
+                             classes are imported with mock TensorFlow / TFP packages and their
+                             three graph-building methods replaced by no-ops (run as
+                             ``make_golden.py names`` in a fresh interpreter).
 """
 
 import hashlib
@@ -136,8 +143,128 @@ def model_utilities_golden(utilities):
     print("model utilities:", {k: len(v) for k, v in records.items()})
 
 
+class _MockModule(types.ModuleType):
+    """Package whose attributes are mocks; ``Distribution`` is a real class (it is subclassed)."""
+    __path__ = []
+
+    def __getattr__(self, key):
+        from unittest import mock
+        if key.startswith("__"):
+            raise AttributeError(key)
+        value = (type(key, (object,), {"__init__": lambda self, *a, **kw: None})
+                 if key == "Distribution" else mock.MagicMock(name=self.__name__ + "." + key))
+        setattr(self, key, value)
+        return value
+
+
+class _MockFinder:
+    """Serves any (sub)module of the packages the reference imports but this image lacks."""
+    ROOTS = ("tensorflow", "tensorflow_probability", "loompy", "tables", "matplotlib", "seaborn",
+             "mpl_toolkits")
+
+    def find_spec(self, name, path=None, target=None):
+        import importlib.machinery
+        if name.split(".")[0] in self.ROOTS or name.startswith("scvae.analyses"):
+            return importlib.machinery.ModuleSpec(name, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        return _MockModule(spec.name)
+
+    def exec_module(self, module):
+        pass
+
+
+MODEL_NAME_CASES = [
+    ("VAE", dict()),
+    ("VAE", dict(latent_size=50, hidden_sizes=[100], reconstruction_distribution="negative binomial")),
+    ("VAE", dict(latent_size=8, hidden_sizes=[64, 32], reconstruction_distribution="poisson",
+                 number_of_reconstruction_classes=3, batch_correction=True, number_of_batches=2,
+                 count_sum=True)),
+    ("VAE", dict(reconstruction_distribution="zero-inflated negative binomial",
+                 minibatch_normalisation=False, number_of_warm_up_epochs=20)),
+    ("VAE", dict(reconstruction_distribution="constrained poisson", kl_weight=0.5)),
+    ("VAE", dict(reconstruction_distribution="zero-inflated poisson",
+                 number_of_monte_carlo_samples={"training": 3, "evaluation": 7},
+                 number_of_importance_samples={"training": 2, "evaluation": 5})),
+    ("VAE", dict(reconstruction_distribution="negative binomial", dropout_keep_probabilities=[0.8, 0.9])),
+    ("VAE", dict(reconstruction_distribution="negative binomial", inference_architecture="LFM",
+                 latent_size=2, hidden_sizes=[])),
+    ("VAE", dict(reconstruction_distribution="negative binomial", inference_architecture="MLP",
+                 generative_architecture="LFM")),
+    ("VAE", dict(latent_distribution="gaussian mixture", number_of_latent_clusters=4,
+                 analytical_kl_term=False)),
+    ("VAE", dict(latent_distribution="gaussian", analytical_kl_term=False, count_sum_feature=True)),
+    ("VAE", dict(reconstruction_distribution="poisson", count_sum_feature=True, count_sum=True,
+                 batch_correction=True, number_of_batches=3)),
+    ("GMVAE", dict()),
+    ("GMVAE", dict(latent_size=50, hidden_sizes=[100, 100], number_of_latent_clusters=9,
+                   reconstruction_distribution="zero-inflated negative binomial")),
+    ("GMVAE", dict(latent_distribution="full-covariance gaussian mixture", number_of_latent_clusters=3)),
+    ("GMVAE", dict(number_of_latent_clusters=5, prior_probabilities_method="uniform",
+                   reconstruction_distribution="negative binomial", number_of_reconstruction_classes=4,
+                   number_of_warm_up_epochs=10, kl_weight=2)),
+    ("GMVAE", dict(number_of_latent_clusters=5, proportion_of_free_nats_for_y_kl_divergence=0.8,
+                   minibatch_normalisation=False, batch_correction=True, number_of_batches=2)),
+    ("GMVAE", dict(number_of_latent_clusters=2, number_of_monte_carlo_samples=[4, 2],
+                   number_of_importance_samples=3, dropout_keep_probabilities=[0.5],
+                   count_sum_feature=True)),
+]
+
+LOG_DIRECTORY_CASES = [
+    dict(), dict(run_id="r1"), dict(run_id="r1", early_stopping=True),
+    dict(run_id="r1", best_model=True), dict(base="other", early_stopping=True),
+]
+
+
+def model_names_golden():
+    """Names, descriptions and log directories from the reference's own model classes."""
+    import importlib
+    import json
+    sys.meta_path.insert(0, _MockFinder())
+    resources = types.ModuleType("importlib_resources")
+    resources.open_text = lambda package, name: open(
+        os.path.join(REFERENCE, package.replace(".", os.sep), name))
+    sys.modules["importlib_resources"] = resources
+    for name, directory in (("scvae", "scvae"), ("scvae.data", "scvae/data")):
+        package = types.ModuleType(name)
+        package.__path__ = [os.path.join(REFERENCE, directory)]
+        sys.modules[name] = package
+    data_set = types.ModuleType("scvae.data.data_set")
+    data_set.DataSet = object
+    sys.modules["scvae.data.data_set"] = data_set
+    classes = {
+        "VAE": importlib.import_module(
+            "scvae.models.variational_autoencoder").VariationalAutoencoder,
+        "GMVAE": importlib.import_module(
+            "scvae.models.gaussian_mixture_variational_autoencoder"
+        ).GaussianMixtureVariationalAutoencoder,
+    }
+    for cls in classes.values():
+        for method in ("_setup_model_graph", "_setup_loss_function", "_setup_optimiser"):
+            setattr(cls, method, lambda self: None)
+    records = []
+    for kind, kwargs in MODEL_NAME_CASES:
+        record = {"model": kind, "kwargs": kwargs}
+        try:
+            model = classes[kind](feature_size=100, log_directory="log", **kwargs)
+            record["name"] = model.name
+            record["description"] = model.description
+            record["log_directories"] = [
+                {"kwargs": kw, "result": model.log_directory(**kw)} for kw in LOG_DIRECTORY_CASES]
+        except Exception as exc:
+            record["raises"] = type(exc).__name__
+        records.append(record)
+    with open(os.path.join(OUT, "model_names.json"), "w") as handle:
+        json.dump(records, handle, indent=1, sort_keys=True)
+    print("model names:", len(records), "records,",
+          sum("raises" in r for r in records), "raising")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["names"]:
+        return model_names_golden()
     utilities, loaders = import_reference_modules()
     dd = loaders._create_development_data_set()
     values = dd["values"]
@@ -158,6 +285,8 @@ def main():
                     [utilities.normalise_string(s) for s in samples]))
     print("normalise_string:", [utilities.normalise_string(s) for s in samples])
     model_utilities_golden(utilities)
+    import subprocess
+    subprocess.run([sys.executable, os.path.abspath(__file__), "names"], check=True)
 
 
 if __name__ == "__main__":

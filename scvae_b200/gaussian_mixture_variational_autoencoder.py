@@ -126,14 +126,22 @@ class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
             minor.append("fn_{}".format(self.proportion_of_free_nats_for_y_kl_divergence))
         return os.path.join(self.type, "-".join(latent), "-".join(minor))
 
-    @property
-    def description(self):
-        text = super().description
-        extra = ["prior probabilities: " + self.prior_probabilities_method]
+    _description_hides_single_samples = True
+    _description_kl_weight_label = "KL weight"
+    _description_mentions_analytical_kl = False
+
+    def _description_latent(self):
+        lines = []
+        if "mixture" in self.latent_distribution_name:
+            lines.append("latent clusters: {}".format(self.number_of_latent_clusters))
+            lines.append("prior probabilities: " + self.prior_probabilities_method)
+        return lines
+
+    def _description_training_terms(self):
         if self.proportion_of_free_nats_for_y_kl_divergence:
-            extra.append("proportion of free nats for y KL divergence: {}".format(
-                self.proportion_of_free_nats_for_y_kl_divergence))
-        return text + "\n    " + "\n    ".join(extra)
+            return ["proportion of free nats for y KL divergence: {}".format(
+                self.proportion_of_free_nats_for_y_kl_divergence)]
+        return []
 
     # ------------------------------------------------------------------------------------------
     def _build_engine(self):

@@ -197,33 +197,60 @@ class VariationalAutoencoder:
 
     @property
     def description(self):
+        """Model summary printed by the CLI; wording and order follow VAE:471-553 (and, through
+        the ``_description_*`` hooks, GMVAE:505-592), typos included ("KL weigth")."""
         lines = ["Model setup:", "type: {}".format(self.type),
                  "feature size: {}".format(self.feature_size),
                  "latent size: {}".format(self.latent_size),
                  "hidden sizes: {}".format(", ".join(map(str, self.hidden_sizes))),
                  "latent distribution: " + self.latent_distribution_name]
-        if "mixture" in self.latent_distribution_name:
-            lines.append("latent clusters: {}".format(self.number_of_latent_clusters))
+        lines += self._description_latent()
         lines.append("reconstruction distribution: " + self.reconstruction_distribution_name)
+        if self.k_max > 0:
+            lines.append("reconstruction classes: {} (including 0s)".format(self.k_max))
         for label, numbers in (("Monte Carlo samples", self.number_of_monte_carlo_samples),
                                ("importance samples", self.number_of_importance_samples)):
+            if self._description_hides_single_samples and max(numbers.values()) <= 1:
+                continue
             text = "{}: {}".format(label, numbers["training"])
             if numbers["evaluation"] != numbers["training"]:
                 text += " (training), {} (evaluation)".format(numbers["evaluation"])
             lines.append(text)
         if self.kl_weight_value != 1:
-            lines.append("KL weigth: {}".format(self.kl_weight_value))
-        if self.analytical_kl_term:
+            lines.append("{}: {}".format(self._description_kl_weight_label, self.kl_weight_value))
+        if self._description_mentions_analytical_kl and self.analytical_kl_term:
             lines.append("using analytical KL term")
         if self.minibatch_normalisation:
             lines.append("using batch normalisation for minibatches")
+        if self.batch_correction:
+            lines.append("with batch correction")
         if self.number_of_warm_up_epochs:
             lines.append("using linear warm-up weighting for the first {} epochs".format(
                 self.number_of_warm_up_epochs))
+        lines += self._description_training_terms()
+        if self.dropout_parts:
+            lines.append("dropout keep probability: {}".format(", ".join(self.dropout_parts)))
+        if self.use_count_sum_as_feature:
+            lines.append("using count sums")
         if self.early_stopping_rounds:
             lines.append("early stopping: after {} epoch with no improvements".format(
                 self.early_stopping_rounds))
         return "\n    ".join(lines)
+
+    _description_hides_single_samples = False
+    _description_kl_weight_label = "KL weigth"
+    _description_mentions_analytical_kl = True
+
+    def _description_latent(self):
+        lines = []
+        if "mixture" in self.latent_distribution_name:
+            lines.append("latent clusters: {}".format(self.number_of_latent_clusters))
+        if self.parameterise_latent_posterior:
+            lines.append("using parameterisation of latent posterior parameters")
+        return lines
+
+    def _description_training_terms(self):
+        return []
 
     @property
     def parameters(self):
