@@ -1,0 +1,176 @@
+"""The oracle against golden vectors produced by the REFERENCE'S OWN graph code.
+
+``tests/golden/reference_graph_*.npz`` were recorded by ``oracle/make_golden_graph.py``: the
+reference's ``VariationalAutoencoder`` / ``GaussianMixtureVariationalAutoencoder`` classes
+(VAE:2219-2770, GMVAE:2788-3470, MU:38-137, DU:30-306, ZI:180-199, CAT:210-274), imported
+unmodified from /root/reference and executed over an eager stand-in for the TF-1.x / TFP-0.7
+primitives (``oracle/tf1_standin.py``), in fp64.  They pin the oracle's graph composition --
+variable names, layer / head order, clips, tiling over (R, S, B), zero-inflated and
+piecewise-categorical formulas, KL / ELBO aggregation, moments, clip + Adam, batch-norm update
+order -- to the reference's code; TF's own primitive arithmetic stays restated (see the
+stand-in's docstring).  Nothing here reads /root/reference.
+"""
+import glob
+import json
+import os
+from collections import OrderedDict
+
+import numpy
+import pytest
+import torch
+
+from oracle import scvae_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[len("reference_graph_"):-len(".npz")]
+               for p in glob.glob(os.path.join(GOLDEN, "reference_graph_*.npz")))
+D = torch.float64
+RTOL, ATOL = 1e-9, 1e-10      # fp64 oracle against fp64 golden vectors
+
+
+def load_case(name):
+    data = numpy.load(os.path.join(GOLDEN, "reference_graph_{}.npz".format(name)))
+    meta = json.loads(str(data["meta"]))
+    groups = {}
+    for key in data.files:
+        if key == "meta":
+            continue
+        head, _, rest = key.partition("/")
+        if head == "in":
+            head, _, rest = rest.partition("/")
+            head = "in_" + head
+        groups.setdefault(head, OrderedDict())[rest] = data[key]
+    return meta, groups
+
+
+def oracle_config(meta):
+    kw = dict(meta["kwargs"])
+    common = dict(
+        feature_size=24, latent_size=kw["latent_size"], hidden_sizes=kw["hidden_sizes"],
+        reconstruction_distribution=kw["reconstruction_distribution"],
+        number_of_importance_samples=meta["R"], number_of_monte_carlo_samples=meta["S"],
+        minibatch_normalisation=kw.get("minibatch_normalisation", True),
+        kl_weight=kw.get("kl_weight", 1.0),
+        number_of_batches=kw.get("number_of_batches", 0) if kw.get("batch_correction") else 0,
+        count_sum_feature=kw.get("count_sum", False),
+        number_of_reconstruction_classes=kw.get("number_of_reconstruction_classes", 0))
+    if meta["model"] == "GMVAE":
+        return O.GMVAEConfig(
+            number_of_latent_clusters=kw["number_of_latent_clusters"],
+            prior_probabilities_method=kw.get("prior_probabilities_method", "uniform"),
+            prior_probabilities=kw.get("prior_probabilities"),
+            proportion_of_free_nats_for_y_kl_divergence=kw.get(
+                "proportion_of_free_nats_for_y_kl_divergence", 0.0), **common)
+    return O.VAEConfig(
+        latent_distribution=kw.get("latent_distribution", "gaussian"),
+        # VAE:186-192: analytic KL by default only for the plain gaussian latent distribution
+        analytical_kl_term=kw.get("analytical_kl_term",
+                                  kw.get("latent_distribution", "gaussian") == "gaussian"),
+        inference_architecture=kw.get("inference_architecture", "MLP"),
+        generative_architecture=kw.get("generative_architecture", "MLP"),
+        dropout_keep_probabilities=kw.get("dropout_keep_probabilities"), **common)
+
+
+def oracle_inputs(meta, groups):
+    """(params in the reference's creation order, x, eps, feature kwargs, dropout masks)."""
+    params = OrderedDict((name, torch.as_tensor(groups["in_var"][name], dtype=D))
+                         for name, _, _ in meta["variables"])
+    feeds = groups["in_feed"]
+    x = torch.as_tensor(feeds["X"], dtype=D)
+    eps = [torch.as_tensor(v, dtype=D) for v in groups.get("in_eps", {}).values()]
+    kw = meta["kwargs"]
+    features = {}
+    if kw.get("batch_correction"):
+        features["batch_indices"] = torch.as_tensor(feeds["batch_indices"])
+    if kw.get("count_sum"):
+        features["count_sum_feature"] = torch.as_tensor(feeds["count_sum_feature"], dtype=D)
+    if meta["model"] == "GMVAE":
+        eps = torch.stack(eps)                       # (K, R*S, B, L)
+    else:
+        eps = eps[0] if eps else None                # (R*S, B, L)
+        if kw["reconstruction_distribution"] == "constrained poisson":
+            features["count_sum"] = torch.as_tensor(feeds["count_sum"], dtype=D)
+        masks = {site: torch.as_tensor(m, dtype=D)
+                 for site, m in groups.get("in_dropout", {}).items()}
+        if masks:
+            features["dropout"] = {"masks": masks}
+    return params, x, eps, features
+
+
+def close(got, want, what, rtol=RTOL, atol=ATOL):
+    got = got.detach().numpy() if torch.is_tensor(got) else numpy.asarray(got)
+    want = numpy.asarray(want)
+    assert got.size == want.size, "{}: {} vs {}".format(what, got.shape, want.shape)
+    got = got.reshape(want.shape)
+    scale = max(1.0, float(numpy.abs(want).max())) if want.size else 1.0
+    error = numpy.abs(got - want)
+    assert numpy.all(error <= atol * scale + rtol * numpy.abs(want)), \
+        "{}: max |diff| {:.3e} (scale {:.3e})".format(what, float(error.max()), scale)
+
+
+def test_golden_cases_present():
+    assert len(CASES) >= 25
+    assert sum(c.startswith("gmvae") for c in CASES) >= 8
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_variable_layout_matches_reference_graph(name):
+    """Variable names, shapes, trainability and creation order of the reference's graph."""
+    meta, groups = load_case(name)
+    cfg = oracle_config(meta)
+    init = O.gmvae_init_params if meta["model"] == "GMVAE" else O.vae_init_params
+    params = init(cfg, seed=0, dtype=D)
+    assert [(k, list(v.shape)) for k, v in params.items()] == \
+        [(n, s) for n, s, _ in meta["variables"]]
+    assert O.trainable_names(params) == [n for n, _, t in meta["variables"] if t]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_graph(name):
+    meta, groups = load_case(name)
+    cfg = oracle_config(meta)
+    params, x, eps, features = oracle_inputs(meta, groups)
+    feeds = groups["in_feed"]
+    warm_up = float(feeds["warm_up_weight"])
+    forward = O.gmvae_forward if meta["model"] == "GMVAE" else O.vae_forward
+    extra = {} if meta["model"] == "GMVAE" else {
+        "use_deterministic_z": meta["use_deterministic_z"]}
+    out = forward(cfg, params, x, x, eps, is_training=meta["is_training"],
+                  warm_up_weight=warm_up, moments=True, **extra, **features)
+    for key, want in groups["out"].items():
+        close(out[key], want, name + " " + key)
+
+    if not meta["is_training"]:
+        return
+    # one optimiser step: raw gradients, batch-norm moving statistics, clip + Adam
+    state = O.AdamState(params)
+    if meta["adam_step"]:
+        state.step = meta["adam_step"]
+        for key in state.m:
+            state.m[key] = torch.as_tensor(groups["in_adam_m"][key], dtype=D)
+            state.v[key] = torch.as_tensor(groups["in_adam_v"][key], dtype=D)
+    _, grads = O.train_step(cfg, params, state, x, x, eps,
+                            float(feeds["learning_rate"]), warm_up_weight=warm_up, **features)
+    assert set(groups["grad"]) == set(state.m)
+    for key, want in groups["grad"].items():
+        got = grads[key] if grads[key] is not None else torch.zeros_like(params[key])
+        close(got, want, name + " grad " + key, rtol=1e-8, atol=1e-9)
+    assert set(groups["new"]) == {k for k in params
+                                  if k in state.m or k.endswith(("moving_mean",
+                                                                 "moving_variance"))}
+    for key, want in groups["new"].items():
+        close(params[key], want, name + " new " + key)
+
+
+def test_reference_sample_and_update_order():
+    """Order of the reference's sampling ops and batch-norm update ops (K-fold reuse)."""
+    meta, _ = load_case("gmvae_nb_train")
+    K = meta["kwargs"]["number_of_latent_clusters"]
+    assert [c[0] for c in meta["sample_calls"]] == ["Categorical"] + ["Normal"] * (2 * K)
+    # q(y|x) encoder once, then per k the q(z|x,y) encoder, then per k the decoder
+    assert meta["bn_update_order"] == (["Y/CATEGORICAL/ENCODER/LAYER_1/BATCH_NORM"]
+                                       + ["Z/Q/ENCODER/LAYER_1/BATCH_NORM"] * K
+                                       + ["X/DECODER/LAYER_1/BATCH_NORM"] * K)
+    meta, _ = load_case("vae_nb_dropout_train")
+    assert meta["dropout_sites"] == ["ENCODER/1", "POSTERIOR/MU", "POSTERIOR/LOG_SIGMA",
+                                     "DECODER/1", "X_TILDE/P", "X_TILDE/LOG_R"]
