@@ -104,9 +104,13 @@ CASES = [
                                                batch_correction=True, number_of_batches=3,
                                                count_sum=True), dict()),
     ("vae_nb_lfm_inference_train", "VAE", dict(reconstruction_distribution="negative binomial",
-                                                inference_architecture="LFM"), dict()),
+                                                inference_architecture="LFM"),
+     # raw counts feed the posterior heads directly: small counts, small head weights
+     dict(small_counts=True, scale={"POSTERIOR": 0.05})),
     ("vae_nb_lfm_generative_train", "VAE", dict(reconstruction_distribution="negative binomial",
-                                                 generative_architecture="LFM"), dict()),
+                                                 generative_architecture="LFM"),
+     # z feeds the likelihood heads directly: keep sigma = exp(log_sigma) moderate
+     dict(scale={"POSTERIOR": 0.3})),
     ("vae_nb_sampled_kl_train", "VAE", dict(reconstruction_distribution="negative binomial",
                                              analytical_kl_term=False), dict(R=2, S=2)),
     ("vae_nb_unit_variance_train", "VAE", dict(reconstruction_distribution="negative binomial",
@@ -114,6 +118,12 @@ CASES = [
      dict()),
     ("vae_nb_dropout_train", "VAE", dict(reconstruction_distribution="negative binomial",
                                           dropout_keep_probabilities=[0.8, 0.9, 0.7]), dict()),
+    # large head weights: log_lambda / log_r reach their +-10 clips, log_sigma its +-3 clips
+    # (zero gradient through a clipped unit)
+    ("vae_poisson_clipped_train", "VAE", dict(reconstruction_distribution="poisson"),
+     dict(scale={"X_TILDE": 12.0, "POSTERIOR/LOG_SIGMA": 12.0})),
+    ("vae_nb_clipped_train", "VAE", dict(reconstruction_distribution="negative binomial"),
+     dict(scale={"X_TILDE/LOG_R": 15.0, "POSTERIOR/LOG_SIGMA": 12.0})),
     ("gmvae_nb_train", "GMVAE", dict(reconstruction_distribution="negative binomial",
                                       number_of_latent_clusters=3), dict()),
     ("gmvae_nb_eval", "GMVAE", dict(reconstruction_distribution="negative binomial",
@@ -186,7 +196,7 @@ def run_case(classes, name, model, kwargs, options, seed):
     R, S = options.get("R", 1), options.get("S", 1)
     is_training = options.get("is_training", True)
     deterministic = options.get("use_deterministic_z", False)
-    x = counts(rng, B, G, options.get("gentle", False))
+    x = counts(rng, B, G, options.get("gentle", False) or options.get("small_counts", False))
     feeds = {
         "X": x, "T": x, "learning_rate": 1e-3,
         "warm_up_weight": options.get("warm_up_weight", 1.0),
@@ -201,11 +211,17 @@ def run_case(classes, name, model, kwargs, options, seed):
     variables = randomised_variables(rng, layout)
     if options.get("gentle"):
         variables = {k: (0.3 * v if k.endswith("/weights") else v) for k, v in variables.items()}
+    for prefix, factor in options.get("scale", {}).items():
+        variables = {k: (factor * v if k.startswith(prefix) and k.endswith("/weights") else v)
+                     for k, v in variables.items()}
+    K = kwargs.get("number_of_latent_clusters", 1) if model == "GMVAE" else 1
+    n_noise = 0 if deterministic else K
+    noise = [rng.standard_normal(size=(R * S, B, kwargs["latent_size"])) for _ in range(n_noise)]
     if not is_training and kwargs.get("minibatch_normalisation", True):
         # moving statistics of a trained model track the activations: take them from the batch
         # statistics of a training-mode pass (slightly perturbed), not from thin air
-        tf1_standin.STATE.reset(feeds=dict(feeds, is_training=True, use_deterministic_z=False),
-                                initial=variables, seed=seed)
+        tf1_standin.STATE.reset(feeds=dict(feeds, is_training=True), initial=variables,
+                                noise=[n.copy() for n in noise], seed=seed)
         cls(feature_size=G, log_directory="log", **kwargs)
         for path, stats in tf1_standin.STATE.batch_statistics.items():
             mean = sum(m for m, _ in stats).numpy() / len(stats)
@@ -222,10 +238,6 @@ def run_case(classes, name, model, kwargs, options, seed):
                 slots_v[vname] = 1e-4 * rng.uniform(0.1, 1.0, size=shape)
         initial.update({"__adam_m__": slots_m, "__adam_v__": slots_v,
                         "__adam_step__": adam_step})
-    K = kwargs.get("number_of_latent_clusters", 1) if model == "GMVAE" else 1
-    n_noise = 0 if deterministic else K
-    noise = [rng.standard_normal(size=(R * S, B, kwargs["latent_size"])) for _ in range(n_noise)]
-
     # dropout: discover the sites (scopes) with generated masks, then re-run with them injected
     tf1_standin.STATE.reset(feeds=feeds, initial=initial, noise=[n.copy() for n in noise],
                             seed=seed)
