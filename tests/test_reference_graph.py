@@ -174,3 +174,69 @@ def test_reference_sample_and_update_order():
     meta, _ = load_case("vae_nb_dropout_train")
     assert meta["dropout_sites"] == ["ENCODER/1", "POSTERIOR/MU", "POSTERIOR/LOG_SIGMA",
                                      "DECODER/1", "X_TILDE/P", "X_TILDE/LOG_R"]
+
+
+def test_standin_primitives_match_scipy():
+    """The TFP closed forms restated in ``oracle/tf1_standin.py`` (the part of the golden vectors
+    that is NOT the reference's own code) against scipy, independently of the oracle."""
+    import scipy.stats
+    from oracle import tf1_standin as T
+    T.STATE.reset()
+    x = torch.arange(0, 70, dtype=D)
+    for rate in (0.05, 1.3, 17.0):
+        got = T.Poisson(rate=torch.tensor(rate, dtype=D)).log_prob(x).numpy()
+        assert numpy.allclose(got, scipy.stats.poisson.logpmf(x.numpy(), rate), rtol=1e-12,
+                              atol=1e-12)
+    for r in (0.2, 1.0, 9.5):
+        for p in (0.03, 0.5, 0.97):
+            nb = T.NegativeBinomial(total_count=torch.tensor(r, dtype=D),
+                                    probs=torch.tensor(p, dtype=D))
+            ref = scipy.stats.nbinom(r, 1.0 - p)      # tfp probs = 1 - scipy p
+            assert numpy.allclose(nb.log_prob(x).numpy(), ref.logpmf(x.numpy()), rtol=1e-10,
+                                  atol=1e-10)
+            assert numpy.isclose(nb.mean().item(), ref.mean(), rtol=1e-12)
+            assert numpy.isclose(nb.variance().item(), ref.var(), rtol=1e-12)
+    a = T.Normal(torch.tensor([0.3, -1.2], dtype=D), torch.tensor([0.7, 2.0], dtype=D))
+    b = T.Normal(torch.tensor([0.0, 0.5], dtype=D), torch.tensor([1.0, 0.4], dtype=D))
+    z = torch.tensor([0.1, 0.9], dtype=D)
+    assert numpy.allclose(a.log_prob(z).numpy(), scipy.stats.norm.logpdf(z.numpy(), [0.3, -1.2],
+                                                                         [0.7, 2.0]))
+    grid = torch.linspace(-40, 40, 400001, dtype=D).unsqueeze(-1)
+    numeric = (torch.exp(a.log_prob(grid)) * (a.log_prob(grid) - b.log_prob(grid))).sum(0) * (
+        grid[1, 0] - grid[0, 0])
+    assert numpy.allclose(T.kl_divergence(a, b).numpy(), numeric.numpy(), rtol=1e-8)
+    logits = torch.tensor([[0.2, -1.0, 3.0], [0.0, 0.0, 0.0]], dtype=D)
+    cat = T.Categorical(logits=logits)
+    probs = torch.softmax(logits, -1).numpy()
+    assert numpy.allclose(cat.entropy().numpy(), [scipy.stats.entropy(p) for p in probs])
+    assert numpy.allclose(cat.log_prob(torch.tensor([2, 1])).numpy(),
+                          numpy.log([probs[0, 2], probs[1, 1]]))
+    other = T.Categorical(logits=torch.tensor([[1.0, 1.0, -2.0]], dtype=D))
+    q = torch.softmax(other.logits, -1).numpy()[0]
+    assert numpy.allclose(T.kl_divergence(cat, other).numpy(),
+                          [scipy.stats.entropy(p, q) for p in probs])
+
+
+def test_standin_layers_follow_tf_contrib_semantics():
+    """fully_connected / batch_norm / dropout / Adam of the stand-in on hand-computed cases."""
+    from oracle import tf1_standin as T
+    x = numpy.array([[1.0, 2.0], [3.0, 6.0], [5.0, 1.0]])
+    T.STATE.reset(initial={"L/DENSE/weights": numpy.array([[1.0, 0.0], [0.0, 2.0]]),
+                           "L/DENSE/biases": numpy.array([0.5, -1.0])})
+    with T.variable_scope("L"):
+        y = T.fully_connected(torch.as_tensor(x), 2, scope="DENSE")
+        assert numpy.allclose(y.detach().numpy(), x * [1.0, 2.0] + [0.5, -1.0])
+        out = T.batch_norm(y, is_training=True, scope="BATCH_NORM")
+    mean, var = y.detach().numpy().mean(0), y.detach().numpy().var(0)
+    assert numpy.allclose(out.detach().numpy(), (y.detach().numpy() - mean) / numpy.sqrt(var + 1e-3))
+    new_mean = T.STATE.updates["L/BATCH_NORM/moving_mean"].numpy()
+    new_var = T.STATE.updates["L/BATCH_NORM/moving_variance"].numpy()
+    assert numpy.allclose(new_mean, 0.001 * mean)                       # 0 - (0 - mean)(1 - .999)
+    assert numpy.allclose(new_var, 1.0 - 0.001 * (1.0 - var * 3 / 2))   # Bessel-corrected
+    # Adam, first step from zero slots: theta - lr * g / (|g| + eps * sqrt(1 - b2)) ~ lr sign(g)
+    w = T.STATE.variables["L/DENSE/weights"]
+    opt = T.AdamOptimizer(0.01)
+    pairs = opt.compute_gradients((w * torch.tensor([[2.0, -3.0], [0.5, 0.0]])).sum())
+    opt.apply_gradients([(T.clip_by_value(g, -1.0, 1.0), v) for g, v in pairs])
+    step = w.detach().numpy() - T.STATE.updates["L/DENSE/weights"].numpy()
+    assert numpy.allclose(step, 0.01 * numpy.array([[1.0, -1.0], [1.0, 0.0]]), atol=1e-8)
