@@ -159,6 +159,21 @@ int scvae_gaussian_latent_bwd(const float *ph, int64_t ldph, int B, int L, int R
                               const float *eps, int unit_variance, const float *dz,
                               int64_t lddz, float kl_coef, float *dph, int64_t lddph,
                               void *stream);
+/* Sampled (non-analytical) KL term (VAE:2628-2640; the default of every VAE latent distribution
+ * except `gaussian`, VAE:186-192): kl_rows[RS*B] (sample-major) = sum_l [log q(z|x) - log p(z)]
+ * at z = mu + sigma eps, = sum_l (z^2/2 - eps^2/2 - log_sigma); kl_elem (nullable, (B, L)
+ * contiguous) = the per-neuron terms averaged over the RS samples (column mean =
+ * kl_divergence_neurons, VAE:2643-2646).  deterministic != 0: eps = 0, RS treated as 1. */
+int scvae_gaussian_sampled_kl(const float *ph, int64_t ldph, int B, int L, int RS,
+                              const float *eps, int unit_variance, int deterministic,
+                              float *kl_rows, float *kl_elem, void *stream);
+/* Backward of the sample and the sampled KL together.  c_m = d loss / d kl_rows[m] is
+ * -weight * go[m] (go [RS*B] from scvae_vae_bound_rows) or, when go is NULL (R == 1),
+ * coef_scalar = weight / (S B).  dph as in scvae_gaussian_latent_bwd. */
+int scvae_gaussian_sampled_kl_bwd(const float *ph, int64_t ldph, int B, int L, int RS,
+                                  const float *eps, int unit_variance, const float *dz,
+                                  int64_t lddz, const float *go, float weight, float coef_scalar,
+                                  float *dph, int64_t lddph, void *stream);
 /* Decoder-input extras (VAE:2400-2441: `tf.concat([z, one_hot(batch_indices), count_sum])`):
  * for row m (cell b = m % B) of the latent sample matrix z (M, ldz) write the one-hot batch
  * index (batch_index [B] as float, nullable, n_batches columns) and/or the normalised count sum
@@ -253,6 +268,11 @@ int scvae_likelihood_moments(int kind, const float *a, int64_t lda, int64_t head
  * / d logp = -softmax_r(logp - w kl)/(S B).  weight = warm_up_weight * kl_weight. */
 int scvae_vae_bound(const float *logp, const float *kl_row, int R, int S, int B,
                     float weight, float *out, float *go, void *stream);
+
+/* The same bound with one KL value per (r, s, b) row (sampled KL, VAE:2656, :2715-2734):
+ * kl_rows[R*S*B]; out[3] = mean over all rows (= sum_l kl_divergence_neurons). */
+int scvae_vae_bound_rows(const float *logp, const float *kl_rows, int R, int S, int B,
+                         float weight, float *out, float *go, void *stream);
 
 /* ---- a8: optimiser  (VAE:2736-2770) elementwise clip to [-clip, clip] + TF Adam -------
  * One fused pass over the flat parameter buffer.  `step` [device, int64] is read (t =

@@ -123,6 +123,136 @@ vae_bound_kernel(const float *__restrict__ logp, const float *__restrict__ kl_ro
     }
 }
 
+// ---- sampled (non-analytical) KL term (VAE:2628-2640): kl[r,s,b,l] = log q(z|x) - log p(z) at
+// the drawn z = mu + sigma eps, i.e. 0.5 z^2 - 0.5 eps^2 - log_sigma (the 2 pi terms cancel).
+// The default of every VAE latent distribution except the plain `gaussian` (VAE:186-192).
+// One warp per cell.  kl_rows[RS*B] (sample-major, like logp) = sum_l; kl_elem (nullable, (B, L))
+// = mean over the RS samples, so that its column mean is kl_divergence_neurons (VAE:2643-2646).
+__global__ void __launch_bounds__(32 * kRowsPerBlock)
+gaussian_sampled_kl_kernel(const float *__restrict__ ph, int64_t ldph, int B, int L, int RS,
+                           const float *__restrict__ eps, int unit_variance, int deterministic,
+                           float *__restrict__ kl_rows, float *__restrict__ kl_elem) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const float *pr = ph + (int64_t)b * ldph;
+    const int nrep = deterministic ? 1 : RS;
+    for (int s = 0; s < nrep; ++s) {
+        const int64_t m = (int64_t)s * B + b;
+        float acc = 0.f;
+        for (int l = lane; l < L; l += 32) {
+            const float mu = pr[l];
+            const float ls = unit_variance ? 0.f : fminf(fmaxf(pr[L + l], -3.f), 3.f);
+            const float e = deterministic ? 0.f : eps[m * L + l];
+            const float zv = mu + __expf(ls) * e;
+            acc += 0.5f * zv * zv - 0.5f * e * e - ls;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) kl_rows[m] = acc;
+    }
+    if (kl_elem) {
+        const float inv = 1.f / (float)nrep;
+        for (int l = lane; l < L; l += 32) {
+            const float mu = pr[l];
+            const float ls = unit_variance ? 0.f : fminf(fmaxf(pr[L + l], -3.f), 3.f);
+            const float sigma = __expf(ls);
+            float acc = 0.f;
+            for (int s = 0; s < nrep; ++s) {
+                const float e = deterministic ? 0.f : eps[((int64_t)s * B + b) * L + l];
+                const float zv = mu + sigma * e;
+                acc += 0.5f * zv * zv - 0.5f * e * e - ls;
+            }
+            kl_elem[(int64_t)b * L + l] = acc * inv;
+        }
+    }
+}
+
+// Backward of the reparameterised sample AND the sampled KL: with c_m = d loss / d kl_rows[m]
+// (= -weight * go[m]; weight / (S B) when R == 1), z = mu + sigma eps:
+//   d kl_m / d mu = z,   d kl_m / d log_sigma = z sigma eps - 1.
+__global__ void __launch_bounds__(32 * kRowsPerBlock)
+gaussian_sampled_kl_bwd_kernel(const float *__restrict__ ph, int64_t ldph, int B, int L, int RS,
+                               const float *__restrict__ eps, int unit_variance,
+                               const float *__restrict__ dz, int64_t lddz,
+                               const float *__restrict__ go, float weight, float coef_scalar,
+                               float *__restrict__ dph, int64_t lddph) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const float *pr = ph + (int64_t)b * ldph;
+    float *dr = dph + (int64_t)b * lddph;
+    for (int l = lane; l < L; l += 32) {
+        const float mu = pr[l];
+        const float raw = unit_variance ? 0.f : pr[L + l];
+        const float ls = fminf(fmaxf(raw, -3.f), 3.f);
+        const float sigma = __expf(ls);
+        float dmu = 0.f, dls = 0.f;
+        for (int s = 0; s < RS; ++s) {
+            const int64_t m = (int64_t)s * B + b;
+            const float e = eps[m * L + l];
+            const float c = go ? -weight * go[m] : coef_scalar;
+            const float zv = mu + sigma * e;
+            const float d = dz[m * lddz + l] + c * zv;      // total gradient w.r.t. z
+            dmu += d;
+            dls += d * sigma * e - c;
+        }
+        dr[l] = dmu;
+        if (!unit_variance) {
+            const float mask = (raw < -3.f || raw > 3.f) ? 0.f : 1.f;
+            dr[L + l] = dls * mask;
+        }
+    }
+}
+
+// vae_bound_kernel with one KL value per (r, s, b) row (sampled KL).  out[3] = mean over all
+// rows = sum_l kl_divergence_neurons[l] (VAE:2643-2652).
+__global__ void __launch_bounds__(1024)
+vae_bound_rows_kernel(const float *__restrict__ logp, const float *__restrict__ kl_rows, int R,
+                      int S, int B, float weight, float *__restrict__ out,
+                      float *__restrict__ go) {
+    __shared__ float red[32];
+    const int SB = S * B;
+    const float inv_sb = 1.f / (float)SB;
+    float s_lb = 0.f, s_lbw = 0.f, s_lp = 0.f, s_kl = 0.f;
+    for (int i = threadIdx.x; i < SB; i += blockDim.x) {
+        float mx = -INFINITY, mxw = -INFINITY;
+        for (int r = 0; r < R; ++r) {
+            const float lp = logp[(int64_t)r * SB + i];
+            const float kl = kl_rows[(int64_t)r * SB + i];
+            mx = fmaxf(mx, lp - kl);
+            mxw = fmaxf(mxw, lp - weight * kl);
+            s_lp += lp;
+            s_kl += kl;
+        }
+        float se = 0.f, sew = 0.f;
+        for (int r = 0; r < R; ++r) {
+            const float lp = logp[(int64_t)r * SB + i];
+            const float kl = kl_rows[(int64_t)r * SB + i];
+            se += expf(lp - kl - mx);
+            sew += expf(lp - weight * kl - mxw);
+        }
+        s_lb += logf(se / (float)R) + mx;
+        s_lbw += logf(sew / (float)R) + mxw;
+        if (go) {
+            for (int r = 0; r < R; ++r) {
+                const float lp = logp[(int64_t)r * SB + i];
+                const float kl = kl_rows[(int64_t)r * SB + i];
+                go[(int64_t)r * SB + i] = -expf(lp - weight * kl - mxw) / sew * inv_sb;
+            }
+        }
+    }
+    const float lb = block_sum(s_lb, red);
+    const float lbw = block_sum(s_lbw, red);
+    const float lp = block_sum(s_lp, red);
+    const float kl = block_sum(s_kl, red);
+    if (threadIdx.x == 0) {
+        out[0] = lb * inv_sb;
+        out[1] = lbw * inv_sb;
+        out[2] = lp * inv_sb / (float)R;
+        out[3] = kl * inv_sb / (float)R;
+    }
+}
+
 __global__ void col_mean_kernel(const float *__restrict__ x, int64_t ldx, int rows, int cols,
                                 float *__restrict__ out) {
     // one block of 32 x 8 threads per 32 columns; deterministic tree
@@ -222,6 +352,44 @@ extern "C" int scvae_vae_bound(const float *logp, const float *kl_row, int R, in
     const int threads = (S * B >= 1024) ? 1024 : 256;
     vae_bound_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(logp, kl_row, R, S, B, weight, out, go);
     SCVAE_CHECK_LAUNCH("vae_bound");
+    return 0;
+}
+
+extern "C" int scvae_gaussian_sampled_kl(const float *ph, int64_t ldph, int B, int L, int RS,
+                                         const float *eps, int unit_variance, int deterministic,
+                                         float *kl_rows, float *kl_elem, void *stream) {
+    SCVAE_CHECK_ARG(ph && kl_rows && B > 0 && L > 0 && RS > 0, "gaussian_sampled_kl: bad arguments");
+    SCVAE_CHECK_ARG(deterministic || eps, "gaussian_sampled_kl: eps is NULL");
+    SCVAE_CHECK_ARG(ldph >= (unit_variance ? L : 2 * L), "gaussian_sampled_kl: bad ld");
+    const int blocks = (B + kRowsPerBlock - 1) / kRowsPerBlock;
+    gaussian_sampled_kl_kernel<<<blocks, 32 * kRowsPerBlock, 0, (cudaStream_t)stream>>>(
+        ph, ldph, B, L, RS, eps, unit_variance, deterministic, kl_rows, kl_elem);
+    SCVAE_CHECK_LAUNCH("gaussian_sampled_kl");
+    return 0;
+}
+
+extern "C" int scvae_gaussian_sampled_kl_bwd(const float *ph, int64_t ldph, int B, int L, int RS,
+                                             const float *eps, int unit_variance, const float *dz,
+                                             int64_t lddz, const float *go, float weight,
+                                             float coef_scalar, float *dph, int64_t lddph,
+                                             void *stream) {
+    SCVAE_CHECK_ARG(ph && eps && dz && dph && B > 0 && L > 0 && RS > 0,
+                    "gaussian_sampled_kl_bwd: bad arguments");
+    const int blocks = (B + kRowsPerBlock - 1) / kRowsPerBlock;
+    gaussian_sampled_kl_bwd_kernel<<<blocks, 32 * kRowsPerBlock, 0, (cudaStream_t)stream>>>(
+        ph, ldph, B, L, RS, eps, unit_variance, dz, lddz, go, weight, coef_scalar, dph, lddph);
+    SCVAE_CHECK_LAUNCH("gaussian_sampled_kl_bwd");
+    return 0;
+}
+
+extern "C" int scvae_vae_bound_rows(const float *logp, const float *kl_rows, int R, int S, int B,
+                                    float weight, float *out, float *go, void *stream) {
+    SCVAE_CHECK_ARG(logp && kl_rows && out && R > 0 && S > 0 && B > 0,
+                    "vae_bound_rows: bad arguments");
+    const int threads = (S * B >= 1024) ? 1024 : 256;
+    vae_bound_rows_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(logp, kl_rows, R, S, B, weight,
+                                                                   out, go);
+    SCVAE_CHECK_LAUNCH("vae_bound_rows");
     return 0;
 }
 

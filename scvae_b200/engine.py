@@ -92,7 +92,7 @@ class VAEEngine:
                  minibatch_normalisation=True, kl_weight=1.0, device="cuda", seed=0,
                  tensor_cores=True, fused_heads=True, number_of_batches=0, count_sum_feature=False,
                  inference_architecture="MLP", generative_architecture="MLP",
-                 number_of_reconstruction_classes=0):
+                 number_of_reconstruction_classes=0, analytical_kl_term=True):
         if reconstruction_distribution not in K.LIKELIHOOD_KINDS:
             raise ValueError("reconstruction distribution `{}` is not supported by the "
                              "B200 hot path".format(reconstruction_distribution))
@@ -106,6 +106,9 @@ class VAEEngine:
         self.heads = K.LIKELIHOOD_HEADS[reconstruction_distribution]
         self.P = len(self.heads)
         self.unit_variance = latent_distribution == "unit-variance gaussian"
+        # sampled KL term, log q(z|x) - log p(z) at the drawn z (VAE:2628-2640), instead of the
+        # closed form (VAE:2624-2627); one KL value per (sample, cell) row
+        self.sampled_kl = not bool(analytical_kl_term)
         self.bn = bool(minibatch_normalisation)
         self.kl_weight = float(kl_weight)
         self.device = torch.device(device)
@@ -387,6 +390,7 @@ class VAEEngine:
         p.batch_index = zeros(B) if self.number_of_batches else None   # batch ids as floats
         p.count_sum = zeros(B) if self.count_sum_feature else None
         p.kl_row = zeros(B)
+        p.kl_rows = zeros(M) if self.sampled_kl else None
         p.kl_elem = zeros(B, self.L)
         p.kl_neurons = zeros(self.L)
         p.decY = [zeros(M, round4(l.n_out)) for l in self.dec]
@@ -648,8 +652,7 @@ class VAEEngine:
             t16 = p.X16 if p.t16_is_x16 else p.T16
             K.heads_fused_fwd(self.kind, p.D16, p.W16, self.Gh, t16, M, self.G, p.logp,
                               p.fused_ws, row_const=rc)
-            K.vae_bound(p.logp, p.kl_row, 1 if deterministic else R, 1 if deterministic else S,
-                        B, weight, p.bound, p.go if want_go else None)
+            self._bound(p, R, S, weight, p.go if want_go else None, deterministic)
             return p
         if use16:
             # heads GEMM + likelihood + decoder gradient in one kernel; da stays fp16
@@ -665,7 +668,7 @@ class VAEEngine:
             K.heads_fused_bwd(self.kind, p.D16, p.W16, self.Gh, t16, M, self.G, p.dA16, dd,
                               l.n_in, p.logp, p.fused_ws, row_const=rc, go=None,
                               go_scalar=-1.0 / (S * B), scale=p.fused_scale)
-            K.vae_bound(p.logp, p.kl_row, R, S, B, weight, p.bound, None)
+            self._bound(p, R, S, weight)
             p.fused_done = True
             return p
         self._gemm(p, K.GEMM_NT, M, l.n_out, l.k_in, d, l.w, p.A[:M])
@@ -674,12 +677,22 @@ class VAEEngine:
             self._plan_backward(p)
             self._likelihood(p, tgt, p.A[:M], M, rc, logp=p.logp, da=p.dA[:M],
                              go_scalar=-1.0 / (S * B))
-            K.vae_bound(p.logp, p.kl_row, R, S, B, weight, p.bound, None)
+            self._bound(p, R, S, weight)
         else:
             self._likelihood(p, tgt, p.A[:M], M, rc, logp=p.logp)
-            K.vae_bound(p.logp, p.kl_row, 1 if deterministic else R, 1 if deterministic else S,
-                        B, weight, p.bound, p.go if want_go else None)
+            self._bound(p, R, S, weight, p.go if want_go else None, deterministic)
         return p
+
+    def _bound(self, p, R, S, weight, go=None, deterministic=False):
+        """ELBO terms (+ d loss / d log p) from the per-row log-likelihoods and the KL term."""
+        if deterministic:
+            R = S = 1
+        if self.sampled_kl:
+            K.gaussian_sampled_kl(p.PH, p.B, self.L, R * S, p.eps, p.kl_rows, p.kl_elem,
+                                  unit_variance=self.unit_variance, deterministic=deterministic)
+            K.vae_bound_rows(p.logp, p.kl_rows, R, S, p.B, weight, p.bound, go)
+        else:
+            K.vae_bound(p.logp, p.kl_row, R, S, p.B, weight, p.bound, go)
 
     def set_batch_count_sum_parameter(self, p, count_sum):
         """N of the constrained Poisson for the current minibatch ([B] raw count sums)."""
@@ -792,9 +805,16 @@ class VAEEngine:
             dd_in = p.d_decH[j - 1] if j > 0 else p.dZ
             self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, M, p.d_decY[j], d_in, l.dw)
             self._gemm(p, K.GEMM_NN, M, l.n_in, l.n_out, p.d_decY[j], l.w, dd_in)
-        kl_coef = warm_up_weight * self.kl_weight / B
-        K.gaussian_latent_bwd(p.PH, B, self.L, p.RS, p.eps, p.dZ, kl_coef, p.dPH,
-                              unit_variance=self.unit_variance)
+        if self.sampled_kl:
+            weight = warm_up_weight * self.kl_weight
+            # R == 1: d loss / d log p = -1/(S B) for every row, so d loss / d KL = weight/(S B)
+            K.gaussian_sampled_kl_bwd(p.PH, B, self.L, p.RS, p.eps, p.dZ,
+                                      p.go if R > 1 else None, weight, weight / (S * B), p.dPH,
+                                      unit_variance=self.unit_variance)
+        else:
+            kl_coef = warm_up_weight * self.kl_weight / B
+            K.gaussian_latent_bwd(p.PH, B, self.L, p.RS, p.eps, p.dZ, kl_coef, p.dPH,
+                                  unit_variance=self.unit_variance)
         l = self.post
         h_in = p.encH[-1] if self.enc else p.X
         self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.dPH, h_in, l.dw)

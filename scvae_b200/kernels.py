@@ -213,6 +213,30 @@ def gaussian_latent_bwd(ph, B, L, RS, eps, dz, kl_coef, dph, unit_variance=False
                "gaussian_latent_bwd")
 
 
+def gaussian_sampled_kl(ph, B, L, RS, eps, kl_rows, kl_elem=None, unit_variance=False,
+                        deterministic=False):
+    """Sampled KL term per (sample, cell) row (VAE:2628-2640)."""
+    lib = _lib.load()
+    _lib.check(lib.scvae_gaussian_sampled_kl(_p(ph), _ld(ph), B, L, RS, _p(eps),
+                                             int(unit_variance), int(deterministic), _p(kl_rows),
+                                             _p(kl_elem), _stream()), "gaussian_sampled_kl")
+
+
+def gaussian_sampled_kl_bwd(ph, B, L, RS, eps, dz, go, weight, coef_scalar, dph,
+                            unit_variance=False):
+    lib = _lib.load()
+    _lib.check(lib.scvae_gaussian_sampled_kl_bwd(_p(ph), _ld(ph), B, L, RS, _p(eps),
+                                                 int(unit_variance), _p(dz), _ld(dz), _p(go),
+                                                 float(weight), float(coef_scalar), _p(dph),
+                                                 _ld(dph), _stream()), "gaussian_sampled_kl_bwd")
+
+
+def vae_bound_rows(logp, kl_rows, R, S, B, weight, out, go=None):
+    lib = _lib.load()
+    _lib.check(lib.scvae_vae_bound_rows(_p(logp), _p(kl_rows), R, S, B, float(weight), _p(out),
+                                        _p(go), _stream()), "vae_bound_rows")
+
+
 def piecewise_likelihood(kind, k_max, t, a, head_stride, M, G, logp=None, go=None, go_scalar=1.0,
                          da=None):
     """Categorised count likelihood (`-k`): P heads of ``kind`` + k_max + 1 class-logit heads."""

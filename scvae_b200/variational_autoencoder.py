@@ -153,8 +153,6 @@ class VariationalAutoencoder:
             problems.append("dropout")
         if self.parameterise_latent_posterior:
             problems.append("parameterised latent posteriors")
-        if self.type == "VAE" and not self.analytical_kl_term:
-            problems.append("the sampled (non-analytical) KL term")
         if problems:
             raise NotImplementedError(
                 "Not on the B200 hot path yet (SURVEY §8 f3): " + "; ".join(problems) + ".")
@@ -300,7 +298,8 @@ class VariationalAutoencoder:
                          count_sum_feature=bool(self.use_count_sum_as_feature),
                          inference_architecture=self.inference_architecture,
                          generative_architecture=self.generative_architecture,
-                         number_of_reconstruction_classes=self.k_max)
+                         number_of_reconstruction_classes=self.k_max,
+                         analytical_kl_term=self.analytical_kl_term)
 
     def _attach_features(self, data, data_set):
         """Per-cell decoder features of a data set (VAE:816-833): batch indices for batch
