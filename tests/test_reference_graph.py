@@ -46,7 +46,7 @@ def load_case(name):
 def oracle_config(meta):
     kw = dict(meta["kwargs"])
     common = dict(
-        feature_size=24, latent_size=kw["latent_size"], hidden_sizes=kw["hidden_sizes"],
+        feature_size=meta["G"], latent_size=kw["latent_size"], hidden_sizes=kw["hidden_sizes"],
         reconstruction_distribution=kw["reconstruction_distribution"],
         number_of_importance_samples=meta["R"], number_of_monte_carlo_samples=meta["S"],
         minibatch_normalisation=kw.get("minibatch_normalisation", True),
@@ -158,8 +158,16 @@ def test_oracle_matches_reference_graph(name):
     assert set(groups["new"]) == {k for k in params
                                   if k in state.m or k.endswith(("moving_mean",
                                                                  "moving_variance"))}
+    gmax = max(float(numpy.abs(g).max()) for g in groups["grad"].values())
     for key, want in groups["new"].items():
-        close(params[key], want, name + " new " + key)
+        got = params[key]
+        if key in groups["grad"]:
+            # a bias in front of a batch norm has an exactly-zero gradient; what either side
+            # computes instead is rounding noise (~1e-16 gmax) that Adam's g / (|g| + 1e-8)
+            # turns into a visible step -- leave those entries out
+            live = torch.as_tensor(numpy.abs(groups["grad"][key]) > 1e-10 * gmax)
+            got = torch.where(live, got, torch.as_tensor(want, dtype=D))
+        close(got, want, name + " new " + key)
 
 
 def test_reference_sample_and_update_order():

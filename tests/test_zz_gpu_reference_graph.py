@@ -17,12 +17,11 @@ from test_reference_graph import load_case
 pytestmark = pytest.mark.gpu
 
 TOL = 2e-4
-G = 24
 
-VAE_TRAIN = ["vae_poisson_train", "vae_nb_train", "vae_zip_train", "vae_zinb_train",
+VAE_TRAIN = ["vae_c1_poisson_train", "vae_poisson_train", "vae_nb_train", "vae_zip_train", "vae_zinb_train",
              "vae_nb_train_iw_warmup", "vae_nb_no_bn_train", "vae_constrained_poisson_train",
              "vae_nb_k3_train", "vae_nb_bc_count_sum_train", "vae_nb_lfm_generative_train"]
-VAE_EVAL = ["vae_nb_eval", "vae_nb_eval_deterministic", "vae_zinb_eval_iw", "vae_poisson_k2_eval"]
+VAE_EVAL = ["vae_c1_poisson_eval", "vae_nb_eval", "vae_nb_eval_deterministic", "vae_zinb_eval_iw", "vae_poisson_k2_eval"]
 # (combinations no oracle-based GPU suite covers -- custom prior probabilities, a GMVAE without
 # batch norm -- come last)
 GMVAE_TRAIN = ["gmvae_nb_train", "gmvae_zinb_train_mc", "gmvae_poisson_learn_train",
@@ -56,7 +55,7 @@ def _vae(name):
     RS = 1 if meta["use_deterministic_z"] else R * S
     L = kw["latent_size"]
     eng = VAEEngine(
-        G, L, kw["hidden_sizes"], kw["reconstruction_distribution"],
+        meta["G"], L, kw["hidden_sizes"], kw["reconstruction_distribution"],
         kw.get("latent_distribution", "gaussian"), kw.get("minibatch_normalisation", True),
         kl_weight=kw.get("kl_weight", 1.0), device="cuda:0", tensor_cores=False,
         number_of_batches=kw.get("number_of_batches", 0) if kw.get("batch_correction") else 0,
@@ -154,7 +153,7 @@ def _gmvae(name):
     R, S = meta["R"], meta["S"]
     L, K = kw["latent_size"], kw["number_of_latent_clusters"]
     eng = GMVAEEngine(
-        G, L, K, kw["hidden_sizes"], kw["reconstruction_distribution"],
+        meta["G"], L, K, kw["hidden_sizes"], kw["reconstruction_distribution"],
         kw.get("minibatch_normalisation", True), kw.get("kl_weight", 1.0),
         kw.get("prior_probabilities_method", "uniform"), kw.get("prior_probabilities"),
         kw.get("proportion_of_free_nats_for_y_kl_divergence", 0.0), device="cuda:0",
@@ -208,6 +207,55 @@ def test_gmvae_evaluation_matches_reference_graph(name):
     assert _rel(z_mean.cpu(), out["z_mean"]) <= TOL
     assert _rel(moments[0].cpu(), out["p_x_mean"]) <= 5e-4
     assert _rel(moments[1].cpu(), out["p_x_stddev"]) <= 5e-4
+
+
+@pytest.mark.parametrize("R,S,unit_variance", [(1, 1, False), (3, 2, False), (2, 1, True)])
+def test_sampled_kl_kernels_match_their_cpu_restatement(R, S, unit_variance):
+    """scvae_gaussian_sampled_kl / scvae_vae_bound_rows / scvae_gaussian_sampled_kl_bwd against
+    the loop-for-loop numpy restatement of tests/test_sampled_kl_math.py (which is itself held
+    to autograd and to the reference-graph golden cases on the CPU)."""
+    from scvae_b200 import kernels as K
+    from test_sampled_kl_math import bound_rows, sampled_kl_bwd, sampled_kl_rows
+    B, L, RS, weight = 37, 5, R * S, 0.6
+    gen = torch.Generator().manual_seed(3)
+    nL = L if unit_variance else 2 * L
+    ph = torch.randn(B, nL, generator=gen)
+    if not unit_variance:
+        ph[:, L:] *= 2.5                        # some log_sigma beyond the +-3 clip
+    eps = torch.randn(RS * B, L, generator=gen)
+    logp = torch.randn(RS * B, generator=gen) * 5 - 100
+    dz = torch.randn(RS * B, L + 3, generator=gen)          # padded leading dimension
+    dev = "cuda:0"
+    ph_d = torch.zeros(B, nL + 2, device=dev)
+    ph_d[:, :nL] = ph.to(dev)
+    kl_rows = torch.zeros(RS * B, device=dev)
+    kl_elem = torch.zeros(B, L, device=dev)
+    K.gaussian_sampled_kl(ph_d, B, L, RS, eps.to(dev), kl_rows, kl_elem,
+                          unit_variance=unit_variance)
+    ref_rows, ref_elem = sampled_kl_rows(ph.double().numpy(), eps.double().numpy(), B, L, RS,
+                                         unit_variance)
+    assert numpy.abs(kl_rows.cpu().numpy() - ref_rows).max() <= 2e-5 * numpy.abs(ref_rows).max()
+    assert numpy.abs(kl_elem.cpu().numpy() - ref_elem).max() <= 2e-5 * numpy.abs(ref_elem).max()
+    out = torch.zeros(4, device=dev)
+    go = torch.zeros(RS * B, device=dev)
+    K.vae_bound_rows(logp.to(dev), kl_rows, R, S, B, weight, out, go)
+    ref_out, ref_go = bound_rows(logp.double().numpy(), ref_rows, R, S, B, weight)
+    assert numpy.abs(out.cpu().numpy() - ref_out).max() <= 2e-5 * numpy.abs(ref_out).max()
+    assert numpy.abs(go.cpu().numpy() - ref_go).max() <= 1e-4 * numpy.abs(ref_go).max()
+    dph = torch.zeros(B, nL + 2, device=dev)
+    K.gaussian_sampled_kl_bwd(ph_d, B, L, RS, eps.to(dev), dz.to(dev), go, weight, 0.0, dph,
+                              unit_variance=unit_variance)
+    ref_dph = sampled_kl_bwd(ph.double().numpy(), eps.double().numpy(),
+                             dz[:, :L].double().numpy(), go.cpu().double().numpy(), weight, 0.0,
+                             B, L, RS, unit_variance)
+    assert numpy.abs(dph[:, :nL].cpu().numpy() - ref_dph).max() <= 5e-5 * numpy.abs(ref_dph).max()
+    # deterministic z: eps = 0, one sample
+    K.gaussian_sampled_kl(ph_d, B, L, RS, None, kl_rows, None, unit_variance=unit_variance,
+                          deterministic=True)
+    det_rows, _ = sampled_kl_rows(ph.double().numpy(), None, B, L, RS, unit_variance,
+                                  deterministic=True)
+    assert numpy.abs(kl_rows[:B].cpu().numpy() - det_rows).max() <= \
+        2e-5 * numpy.abs(det_rows).max()
 
 
 # The sampled (non-analytical) KL term (VAE:2628-2640; kernels scvae_gaussian_sampled_kl,
