@@ -264,3 +264,30 @@ def test_sampled_kl_kernels_match_their_cpu_restatement(R, S, unit_variance):
 @pytest.mark.parametrize("name", ["vae_nb_sampled_kl_train", "vae_nb_unit_variance_train"])
 def test_vae_sampled_kl_training_step_matches_reference_graph(name):
     test_vae_training_step_matches_reference_graph(name)
+
+
+def test_train_evaluate_unit_variance_gaussian_with_its_default_sampled_kl(tmp_path):
+    """`-q "unit-variance gaussian"` end to end through the model class: the reference's default
+    for it is the sampled KL (VAE:186-192), which used to be refused.  The ELBO must improve and
+    the per-neuron KL estimates must be logged."""
+    import scipy.sparse
+    from oracle import scvae_oracle as O
+    from scvae_b200 import model_utilities as MU
+    from scvae_b200.data_set import DataSet
+    from scvae_b200.variational_autoencoder import VariationalAutoencoder
+    x, labels = O.synthetic_counts(300, 60, n_types=3, seed=3, target_zero_fraction=0.8)
+    full = DataSet("toy", values=scipy.sparse.csr_matrix(numpy.minimum(x, 50.0)),
+                   labels=labels.astype(str))
+    training, validation, test = full.split()
+    model = VariationalAutoencoder(
+        feature_size=60, latent_size=4, hidden_sizes=[32],
+        reconstruction_distribution="negative binomial",
+        latent_distribution="unit-variance gaussian", log_directory=str(tmp_path), seed=1)
+    assert model.analytical_kl_term is False
+    assert model.train(training, validation, number_of_epochs=4, minibatch_size=50,
+                       learning_rate=1e-2, shuffle_seed=0) == 0
+    curve = MU.load_learning_curves(model, "training")["lower_bound"]
+    assert len(curve) == 4 and numpy.isfinite(curve).all() and curve[-1] > curve[0]
+    assert MU.load_kl_divergences(model, "training").shape == (4, 4)
+    reconstructed = model.evaluate(test, minibatch_size=64, output_versions="reconstructed")
+    assert numpy.isfinite(reconstructed.values).all()
