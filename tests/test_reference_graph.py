@@ -248,3 +248,31 @@ def test_standin_layers_follow_tf_contrib_semantics():
     opt.apply_gradients([(T.clip_by_value(g, -1.0, 1.0), v) for g, v in pairs])
     step = w.detach().numpy() - T.STATE.updates["L/DENSE/weights"].numpy()
     assert numpy.allclose(step, 0.01 * numpy.array([[1.0, -1.0], [1.0, 0.0]]), atol=1e-8)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fixtures_are_reachable_in_fp32(name):
+    """The fixtures are fp64; the CUDA engines compute in fp32 and are held to them at 2e-4
+    (tests/test_zz_gpu_reference_graph.py).  The oracle run in fp32 must land well inside that,
+    otherwise a fixture sits in an ill-conditioned corner (saturated sigmoids, values on a clip
+    boundary) and says nothing about an fp32 implementation."""
+    if "clipped" in name:
+        pytest.skip("drives the heads onto their clips on purpose (fp64 comparison only)")
+    meta, groups = load_case(name)
+    cfg = oracle_config(meta)
+    params, x, eps, features = oracle_inputs(meta, groups)
+    f32 = lambda v: v.float() if torch.is_tensor(v) and v.is_floating_point() else v  # noqa: E731
+    params = OrderedDict((k, f32(v)) for k, v in params.items())
+    features = {k: ({"masks": {s: f32(m) for s, m in v["masks"].items()}} if k == "dropout"
+                    else f32(v)) for k, v in features.items()}
+    forward = O.gmvae_forward if meta["model"] == "GMVAE" else O.vae_forward
+    extra = {} if meta["model"] == "GMVAE" else {
+        "use_deterministic_z": meta["use_deterministic_z"]}
+    out = forward(cfg, params, x.float(), x.float(), f32(eps), is_training=meta["is_training"],
+                  warm_up_weight=float(groups["in_feed"]["warm_up_weight"]), moments=True,
+                  **extra, **features)
+    for key, want in groups["out"].items():
+        got = out[key].detach().double().numpy().reshape(-1)
+        want = want.reshape(-1)
+        scale = max(float(numpy.abs(want).max()), 0.05)
+        assert numpy.abs(got - want).max() <= 5e-5 * scale, (key, numpy.abs(got - want).max(), scale)
