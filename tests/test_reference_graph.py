@@ -276,3 +276,49 @@ def test_fixtures_are_reachable_in_fp32(name):
         want = want.reshape(-1)
         scale = max(float(numpy.abs(want).max()), 0.05)
         assert numpy.abs(got - want).max() <= 5e-5 * scale, (key, numpy.abs(got - want).max(), scale)
+
+
+def _engine_for(meta, device="cpu"):
+    kw = meta["kwargs"]
+    extras = dict(
+        number_of_batches=kw.get("number_of_batches", 0) if kw.get("batch_correction") else 0,
+        count_sum_feature=kw.get("count_sum", False),
+        number_of_reconstruction_classes=kw.get("number_of_reconstruction_classes", 0))
+    if meta["model"] == "GMVAE":
+        from scvae_b200.gmvae_engine import GMVAEEngine
+        return GMVAEEngine(
+            meta["G"], kw["latent_size"], kw["number_of_latent_clusters"], kw["hidden_sizes"],
+            kw["reconstruction_distribution"], kw.get("minibatch_normalisation", True),
+            kw.get("kl_weight", 1.0), kw.get("prior_probabilities_method", "uniform"),
+            kw.get("prior_probabilities"),
+            kw.get("proportion_of_free_nats_for_y_kl_divergence", 0.0), device=device,
+            tensor_cores=False, **extras)
+    from scvae_b200.engine import VAEEngine
+    return VAEEngine(
+        meta["G"], kw["latent_size"], kw["hidden_sizes"], kw["reconstruction_distribution"],
+        kw.get("latent_distribution", "gaussian"), kw.get("minibatch_normalisation", True),
+        kl_weight=kw.get("kl_weight", 1.0), device=device, tensor_cores=False,
+        inference_architecture=kw.get("inference_architecture", "MLP"),
+        generative_architecture=kw.get("generative_architecture", "MLP"), **extras)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_engine_parameter_layout_round_trips_reference_variables(name):
+    """Host logic of the product, no kernels involved: the engines' flat parameter store
+    (transposed, bias-augmented, head-concatenated, class-major P_K, split one-hot rows) must
+    take the reference's variables by their TF names and give back exactly the same names,
+    shapes and values (fp32)."""
+    meta, groups = load_case(name)
+    engine = _engine_for(meta)
+    variables = OrderedDict((n, torch.as_tensor(groups["in_var"][n], dtype=torch.float32))
+                            for n, _, _ in meta["variables"])
+    engine.import_parameters(variables)
+    exported = engine.export_parameters()
+    assert sorted(exported) == sorted(variables)
+    for key, value in variables.items():
+        assert tuple(exported[key].shape) == tuple(value.shape), key
+        assert torch.equal(exported[key].float().cpu(), value), key
+    gradients = engine.export_gradients()
+    assert sorted(gradients) == sorted(n for n, _, t in meta["variables"] if t)
+    for key, value in gradients.items():
+        assert tuple(value.shape) == tuple(variables[key].shape), key
