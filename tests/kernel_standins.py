@@ -1,0 +1,344 @@
+"""CPU stand-ins for the kernel wrappers of ``scvae_b200.kernels`` -- TEST INFRASTRUCTURE.
+
+Each function has the signature of the wrapper it replaces and the semantics documented for the
+entry point in ``include/scvae_b200.h`` (operand layouts, augmented ones columns, leading
+dimensions, in-place outputs), restated with PyTorch-CPU ops in fp32 storage.  They exist so
+that the HOST logic of the engines -- buffer layout, launch order, which gradient lands where,
+the optimiser wiring -- can be exercised by ``-m "not gpu"`` tests against the golden vectors
+recorded from the reference's graph code (``tests/test_engine_host_logic.py``).  They are never
+imported by the product: without the CUDA library and a device every product entry point raises.
+Only the exact-fp32 VAE path is covered (no tensor-core / fused-heads / CSR kernels).
+"""
+import math
+
+import numpy
+import torch
+
+from oracle import scvae_oracle as O
+from scvae_b200 import kernels as RealK
+from test_sampled_kl_math import bound_rows, sampled_kl_bwd, sampled_kl_rows
+
+# constants and pure host helpers are the real ones
+GEMM_NT, GEMM_NN, GEMM_TN = RealK.GEMM_NT, RealK.GEMM_NN, RealK.GEMM_TN
+LIKELIHOOD_KINDS = RealK.LIKELIHOOD_KINDS
+LIKELIHOOD_HEADS = RealK.LIKELIHOOD_HEADS
+CONSTRAINED_POISSON = RealK.CONSTRAINED_POISSON
+_KIND_NAMES = {v: k for k, v in LIKELIHOOD_KINDS.items()}
+BN_EPSILON, BN_DECAY = 1e-3, 0.999
+
+launches = []        # names of the stand-ins called, in order (the launch sequence of a step)
+
+
+def _log(name):
+    launches.append(name)
+
+
+def _view(t, rows, cols):
+    """(rows, cols) window at the tensor's base pointer with its leading dimension -- the
+    kernels see only (pointer, ld), not the declared shape."""
+    if t.dim() == 1:
+        return t.as_strided((rows, cols), (cols, 1), t.storage_offset())
+    return t.as_strided((rows, cols), (t.stride(0), 1), t.storage_offset())
+
+
+def bn_scratch_floats(M, H, groups):
+    return 1
+
+
+def gemm_workspace_bytes(layout, M, N, K):
+    return 0
+
+
+def gemm(layout, M, N, K, A, B, C, accumulate=False, tensor_cores=True, workspace=None):
+    _log("gemm")
+    assert not tensor_cores
+    if layout == GEMM_NT:
+        c = _view(A, M, K).double() @ _view(B, N, K).double().t()
+    elif layout == GEMM_NN:
+        c = _view(A, M, K).double() @ _view(B, K, N).double()
+    else:
+        c = _view(A, K, M).double().t() @ _view(B, K, N).double()
+    out = _view(C, M, N)
+    out.copy_((c + out.double()) if accumulate else c)
+
+
+def _augment(out, H):
+    if out.shape[1] > H:
+        out[:, H] = 1.0
+        out[:, H + 1:] = 0.0
+
+
+def act_fwd(y, H, out, relu=True):
+    _log("act_fwd")
+    v = y[:, :H].clone()
+    out[:, :H] = torch.relu(v) if relu else v
+    _augment(out, H)
+
+
+def act_bwd(dout, out, H, dy, relu=True):
+    _log("act_bwd")
+    g = dout[:, :H]
+    dy[:, :H] = g * (out[:, :H] > 0) if relu else g
+
+
+def bn_act_fwd(y, H, beta, moving_mean, moving_var, out, save_mean, save_rstd, scratch,
+               training=True, update_moving=True, relu=True, groups=1):
+    _log("bn_act_fwd")
+    M = y.shape[0]
+    n = M // groups
+    v = y[:, :H].double().reshape(groups, n, H)
+    if training:
+        mean = v.mean(dim=1)
+        var = ((v - mean.unsqueeze(1)) ** 2).mean(dim=1)
+        rstd = 1.0 / torch.sqrt(var + BN_EPSILON)
+        save_mean[:groups * H] = mean.reshape(-1)
+        save_rstd[:groups * H] = rstd.reshape(-1)
+        if update_moving:
+            for g in range(groups):
+                moving_mean -= ((1.0 - BN_DECAY) * (moving_mean.double() - mean[g])).float()
+                unbiased = var[g] * (n / max(n - 1, 1))
+                moving_var -= ((1.0 - BN_DECAY) * (moving_var.double() - unbiased)).float()
+    else:
+        mean = moving_mean.double().expand(groups, H)
+        rstd = (1.0 / torch.sqrt(moving_var.double() + BN_EPSILON)).expand(groups, H)
+    r = (v - mean.unsqueeze(1)) * rstd.unsqueeze(1) + beta.double()
+    if relu:
+        r = torch.relu(r)
+    out[:, :H] = r.reshape(M, H)
+    _augment(out, H)
+
+
+def bn_act_bwd(dout, y, out, H, save_mean, save_rstd, dy, dbeta, scratch, relu=True, groups=1,
+               accumulate_dbeta=False):
+    _log("bn_act_bwd")
+    M = y.shape[0]
+    n = M // groups
+    g = dout[:, :H].double()
+    if relu:
+        g = g * (out[:, :H] > 0)
+    g = g.reshape(groups, n, H)
+    mean = save_mean[:groups * H].double().reshape(groups, 1, H)
+    rstd = save_rstd[:groups * H].double().reshape(groups, 1, H)
+    xhat = (y[:, :H].double().reshape(groups, n, H) - mean) * rstd
+    total = g.sum(dim=(0, 1))
+    dbeta[:H] = (dbeta[:H].double() + total) if accumulate_dbeta else total
+    d = rstd * (g - g.mean(dim=1, keepdim=True) - xhat * (g * xhat).mean(dim=1, keepdim=True))
+    dy[:, :H] = d.reshape(M, H)
+
+
+def gaussian_latent_fwd(ph, B, L, RS, eps, z, kl_row, kl_elem=None, unit_variance=False,
+                        deterministic=False):
+    _log("gaussian_latent_fwd")
+    mu = ph[:B, :L].double()
+    ls = torch.zeros_like(mu) if unit_variance else torch.clamp(ph[:B, L:2 * L].double(), -3, 3)
+    sigma = torch.exp(ls)
+    k = 0.5 * mu * mu + 0.5 * (sigma * sigma - 1.0) - ls
+    if kl_elem is not None:
+        kl_elem.reshape(-1)[:B * L] = k.reshape(-1)
+    if kl_row is not None:
+        kl_row[:B] = k.sum(dim=1)
+    nrep = 1 if deterministic else RS
+    for s in range(nrep):
+        rows = slice(s * B, (s + 1) * B)
+        z[rows, :L] = mu if deterministic else mu + sigma * eps[rows, :L].double()
+        z[rows, L] = 1.0
+        z[rows, L + 1:] = 0.0
+
+
+def gaussian_latent_bwd(ph, B, L, RS, eps, dz, kl_coef, dph, unit_variance=False):
+    _log("gaussian_latent_bwd")
+    mu = ph[:B, :L].double()
+    raw = torch.zeros_like(mu) if unit_variance else ph[:B, L:2 * L].double()
+    sigma = torch.exp(torch.clamp(raw, -3, 3))
+    d = dz[:RS * B, :L].double().reshape(RS, B, L)
+    e = eps[:RS * B, :L].double().reshape(RS, B, L)
+    dph[:B, :L] = d.sum(dim=0) + kl_coef * mu
+    if not unit_variance:
+        mask = ((raw >= -3) & (raw <= 3)).double()
+        dph[:B, L:2 * L] = ((d * e).sum(dim=0) * sigma + kl_coef * (sigma * sigma - 1.0)) * mask
+
+
+def gaussian_sampled_kl(ph, B, L, RS, eps, kl_rows, kl_elem=None, unit_variance=False,
+                        deterministic=False):
+    _log("gaussian_sampled_kl")
+    nL = L if unit_variance else 2 * L
+    rows, elem = sampled_kl_rows(ph[:B, :nL].double().numpy(),
+                                 None if eps is None else eps.double().numpy(), B, L, RS,
+                                 unit_variance, deterministic)
+    kl_rows[:rows.size] = torch.as_tensor(rows)
+    if kl_elem is not None:
+        kl_elem.reshape(-1)[:B * L] = torch.as_tensor(elem).reshape(-1)
+
+
+def gaussian_sampled_kl_bwd(ph, B, L, RS, eps, dz, go, weight, coef_scalar, dph,
+                            unit_variance=False):
+    _log("gaussian_sampled_kl_bwd")
+    nL = L if unit_variance else 2 * L
+    d = sampled_kl_bwd(ph[:B, :nL].double().numpy(), eps.double().numpy(),
+                       dz[:RS * B, :L].double().numpy(),
+                       None if go is None else go.double().numpy(), weight, coef_scalar, B, L,
+                       RS, unit_variance)
+    dph[:B, :nL] = torch.as_tensor(d)
+
+
+def vae_bound_rows(logp, kl_rows, R, S, B, weight, out, go=None):
+    _log("vae_bound_rows")
+    o, g = bound_rows(logp.double().numpy(), kl_rows.double().numpy(), R, S, B, weight)
+    out[:4] = torch.as_tensor(o)
+    if go is not None:
+        go[:R * S * B] = torch.as_tensor(g)
+
+
+def vae_bound(logp, kl_row, R, S, B, weight, out, go=None):
+    _log("vae_bound")
+    rows = numpy.tile(kl_row[:B].double().numpy(), R * S)
+    o, g = bound_rows(logp.double().numpy(), rows, R, S, B, weight)
+    out[:4] = torch.as_tensor(o)
+    if go is not None:
+        go[:R * S * B] = torch.as_tensor(g)
+
+
+def decoder_features(z, M, B, col0, batch_index=None, n_batches=0, count_sum=None):
+    _log("decoder_features")
+    for m in range(M):
+        b = m % B
+        col = col0
+        if batch_index is not None and n_batches:
+            z[m, col:col + n_batches] = 0.0
+            z[m, col + int(batch_index[b])] = 1.0
+            col += n_batches
+        if count_sum is not None:
+            z[m, col] = count_sum[b]
+
+
+def _theta(kind, a, head_stride, M, G):
+    name = _KIND_NAMES[kind]
+    heads = LIKELIHOOD_HEADS[name]
+    return name, {head: O._clip_head(a[:M, h * head_stride:h * head_stride + G], head)
+                  for h, head in enumerate(heads)}
+
+
+def _targets(t, M, G):
+    rows = torch.arange(M) % t.shape[0]
+    return t[rows, :G].double()
+
+
+def _rows_log_prob(kind, t, a, head_stride, M, G, k_max=0, count_sum=None):
+    name, theta = _theta(kind, a, head_stride, M, G)
+    x = _targets(t, M, G)
+    n = None
+    if count_sum is not None:
+        n = count_sum.double()[torch.arange(M) % t.shape[0]].reshape(M, 1)
+    if k_max:
+        P = len(theta)
+        logits = torch.stack([a[:M, (P + c) * head_stride:(P + c) * head_stride + G]
+                              for c in range(k_max + 1)], dim=-1)
+        log_p = O.piecewise_log_prob(name, x, theta, torch.log_softmax(logits, dim=-1), k_max, n)
+    else:
+        log_p = O.likelihood_log_prob(name, x, theta, n)
+    return log_p.sum(dim=-1)
+
+
+def _fwd_bwd(kind, t, a, head_stride, M, G, logp, da, go, go_scalar, k_max=0, count_sum=None):
+    leaf = a.double().detach().clone().requires_grad_(da is not None)
+    rows = _rows_log_prob(kind, t, leaf, head_stride, M, G, k_max, count_sum)
+    if logp is not None:
+        logp[:M] = rows.detach()
+    if da is not None:
+        upstream = go[:M].double() if go is not None else torch.full((M,), float(go_scalar),
+                                                                     dtype=torch.float64)
+        grad, = torch.autograd.grad(rows, leaf, grad_outputs=upstream)
+        da[:M] = grad[:M, :da.shape[1]]
+
+
+def likelihood_fwd(kind, t, a, head_stride, M, G, logp, row_const=None):
+    _log("likelihood_fwd")
+    _fwd_bwd(kind, t, a, head_stride, M, G, logp, None, None, 1.0)
+
+
+def likelihood_bwd(kind, t, a, head_stride, M, G, da, logp=None, row_const=None, go=None,
+                   go_scalar=1.0):
+    _log("likelihood_bwd")
+    _fwd_bwd(kind, t, a, head_stride, M, G, logp, da, go, go_scalar)
+
+
+def piecewise_likelihood(kind, k_max, t, a, head_stride, M, G, logp=None, go=None, go_scalar=1.0,
+                         da=None):
+    _log("piecewise_likelihood")
+    _fwd_bwd(kind, t, a, head_stride, M, G, logp, da, go, go_scalar, k_max=k_max)
+
+
+def constrained_poisson(t, a, M, G, count_sum, logp=None, row_const=None, go=None, go_scalar=1.0,
+                        da=None, lse=None):
+    _log("constrained_poisson")
+    _fwd_bwd(CONSTRAINED_POISSON, t, a, 0, M, G, logp, da, go, go_scalar, count_sum=count_sum)
+    if lse is not None:
+        lse[:M] = torch.logsumexp(a[:M, :G].double(), dim=1)
+
+
+def _write_moments(m, v, B, G, RS, outs):
+    m = m.reshape(RS, B, G)
+    v = v.reshape(RS, B, G)
+    mean = m.mean(dim=0)
+    var_of_mean = ((m - mean) ** 2).mean(dim=0)
+    for out, value in zip(outs, (mean, torch.sqrt(var_of_mean + v.mean(dim=0)),
+                                 torch.sqrt(var_of_mean))):
+        if out is not None:
+            out[:B, :G] = value
+
+
+def likelihood_moments(kind, a, head_stride, B, G, RS, K, y, p_x_mean, p_x_stddev,
+                       stddev_of_mean):
+    _log("likelihood_moments")
+    assert K == 1 and y is None
+    name, theta = _theta(kind, a.double(), head_stride, RS * B, G)
+    m, v = O.likelihood_moments(name, theta)
+    _write_moments(m, v, B, G, RS, (p_x_mean, p_x_stddev, stddev_of_mean))
+
+
+def piecewise_moments(kind, k_max, a, head_stride, B, G, RS, p_x_mean, p_x_stddev, stddev_of_mean,
+                      K=1, y=None):
+    _log("piecewise_moments")
+    a = a.double()
+    name, theta = _theta(kind, a, head_stride, RS * B, G)
+    P = len(theta)
+    logits = torch.stack([a[:RS * B, (P + c) * head_stride:(P + c) * head_stride + G]
+                          for c in range(k_max + 1)], dim=-1)
+    m, v = O.likelihood_moments(name, theta)
+    m, v = O.piecewise_moments(m, v, torch.log_softmax(logits, dim=-1), k_max)
+    _write_moments(m, v, B, G, RS, (p_x_mean, p_x_stddev, stddev_of_mean))
+
+
+def constrained_poisson_moments(a, lse, count_sum, B, G, RS, p_x_mean, p_x_stddev,
+                                stddev_of_mean):
+    _log("constrained_poisson_moments")
+    theta = {"lambda": O._clip_head(a[:RS * B, :G].double(), "lambda")}
+    n = count_sum.double()[torch.arange(RS * B) % B].reshape(-1, 1)
+    m, v = O.likelihood_moments("constrained poisson", theta, n)
+    _write_moments(m, v, B, G, RS, (p_x_mean, p_x_stddev, stddev_of_mean))
+
+
+def col_mean(x, rows, cols, out):
+    _log("col_mean")
+    out[:cols] = x[:rows, :cols].double().mean(dim=0)
+
+
+def adam_clip_step(param, grad, m, v, step, lr, beta1=0.9, beta2=0.999, epsilon=1e-8, clip=1.0,
+                   grad_scale=1.0):
+    _log("adam_clip_step")
+    t = int(step.item()) + 1
+    g = torch.clamp(grad.double() * grad_scale, -clip, clip)
+    m.copy_(beta1 * m.double() + (1.0 - beta1) * g)
+    v.copy_(beta2 * v.double() + (1.0 - beta2) * g * g)
+    lr_t = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+    param.copy_(param.double() - lr_t * m.double() / (torch.sqrt(v.double()) + epsilon))
+
+
+def step_advance(step):
+    _log("step_advance")
+    step += 1
+
+
+def fill_normal(out, seed, offset=0, offset_dev=None):
+    _log("fill_normal")
+    out.copy_(torch.randn(out.shape, generator=torch.Generator().manual_seed(int(seed))))

@@ -1,0 +1,54 @@
+"""Host logic of the VAE engine on the CPU: buffer layout, launch sequence, gradient routing and
+optimiser wiring of ``scvae_b200.engine.VAEEngine`` with every kernel wrapper replaced by its CPU
+stand-in (``tests/kernel_standins.py``), held to the golden vectors recorded from the reference's
+own graph code.  The very same test bodies run against the real kernels on the GPU
+(``tests/test_zz_gpu_reference_graph.py``); here they prove that what surrounds the kernels --
+and only that -- reproduces the reference.  The product itself has no CPU path: the stand-ins
+are injected by monkeypatching inside this test module only.
+"""
+import pytest
+import torch
+
+import kernel_standins
+import test_zz_gpu_reference_graph as Z
+
+
+@pytest.fixture
+def engine_on_cpu(monkeypatch):
+    import scvae_b200.engine as E
+    monkeypatch.setattr(E, "K", kernel_standins)
+    original = E.VAEEngine.__init__
+
+    def init(self, *args, **kwargs):
+        kwargs["device"] = "cpu"
+        original(self, *args, **kwargs)
+
+    monkeypatch.setattr(E.VAEEngine, "__init__", init)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    del kernel_standins.launches[:]
+    return kernel_standins.launches
+
+
+@pytest.mark.parametrize("name", Z.VAE_TRAIN + ["vae_nb_sampled_kl_train",
+                                                "vae_nb_unit_variance_train"])
+def test_vae_engine_training_step_host_logic(engine_on_cpu, name):
+    Z.test_vae_training_step_matches_reference_graph(name)
+    launches = engine_on_cpu
+    assert launches[-1] == "step_advance" and launches.count("adam_clip_step") == 1
+    sampled = name in ("vae_nb_sampled_kl_train", "vae_nb_unit_variance_train")
+    assert ("gaussian_sampled_kl_bwd" in launches) == sampled
+    assert ("gaussian_latent_bwd" in launches) == (not sampled)
+    assert ("vae_bound_rows" in launches) == sampled
+
+
+@pytest.mark.parametrize("name", Z.VAE_EVAL)
+def test_vae_engine_evaluation_host_logic(engine_on_cpu, name):
+    Z.test_vae_evaluation_matches_reference_graph(name)
+    assert "adam_clip_step" not in engine_on_cpu
+
+
+def test_product_kernels_module_is_untouched_outside_the_fixture():
+    import scvae_b200.engine as E
+    import scvae_b200.kernels as K
+    assert E.K is K
