@@ -7,7 +7,8 @@ that the HOST logic of the engines -- buffer layout, launch order, which gradien
 the optimiser wiring -- can be exercised by ``-m "not gpu"`` tests against the golden vectors
 recorded from the reference's graph code (``tests/test_engine_host_logic.py``).  They are never
 imported by the product: without the CUDA library and a device every product entry point raises.
-Only the exact-fp32 VAE path is covered (no tensor-core / fused-heads / CSR kernels).
+Only the exact-fp32 paths of the VAE and GMVAE engines are covered (no tensor-core, fused-heads,
+CSR or data-parallel kernels).
 """
 import math
 
@@ -342,3 +343,161 @@ def step_advance(step):
 def fill_normal(out, seed, offset=0, offset_dev=None):
     _log("fill_normal")
     out.copy_(torch.randn(out.shape, generator=torch.Generator().manual_seed(int(seed))))
+
+
+# ---- Gaussian-mixture VAE pieces (include/scvae_b200.h, "a9/a10") ------------------------------
+F32_HALF_MAX = O.F32_HALF_MAX
+
+
+def group_offset_fwd(x, t, K_, B, H, y):
+    _log("group_offset_fwd")
+    for k in range(K_):
+        y[k * B:(k + 1) * B, :H] = x[:B, :H] + t[k, :H]
+
+
+def group_offset_bwd(dy, K_, B, H, dx=None, dt=None, accumulate_dt=False):
+    _log("group_offset_bwd")
+    d = dy[:K_ * B, :H].double().reshape(K_, B, H)
+    if dx is not None:
+        dx[:B, :H] = d.sum(dim=0)
+    if dt is not None:
+        total = d.sum(dim=1)
+        dt[:K_, :H] = (dt[:K_, :H].double() + total) if accumulate_dt else total
+
+
+def softmax_fwd(logits, B, K_, y, logy):
+    _log("softmax_fwd")
+    lp = torch.log_softmax(logits[:B, :K_].double(), dim=-1)
+    logy.reshape(-1)[:B * K_] = lp.reshape(-1)
+    y.reshape(-1)[:B * K_] = torch.exp(lp).reshape(-1)
+
+
+def _gmvae_latent(qh, pz, K_, B, L, RS, eps):
+    """z (K, RS, B, L), per-element KL terms (K, RS, B, L) from [mean | s] heads."""
+    q = torch.clamp(qh[:K_ * B, :2 * L], -F32_HALF_MAX, F32_HALF_MAX).reshape(K_, 1, B, 2 * L)
+    pr = torch.clamp(pz[:K_, :2 * L], -F32_HALF_MAX, F32_HALF_MAX).reshape(K_, 1, 1, 2 * L)
+    q_mean, q_scale = q[..., :L], torch.sqrt(torch.nn.functional.softplus(q[..., L:]))
+    p_mean, p_scale = pr[..., :L], torch.sqrt(torch.nn.functional.softplus(pr[..., L:]))
+    z = q_mean + q_scale * eps.double().reshape(K_, RS, B, L)
+    kl = O._normal_log_prob(z, q_mean, q_scale) - O._normal_log_prob(z, p_mean, p_scale)
+    return z, kl
+
+
+def gmvae_latent_fwd(qh, pz, K_, B, L, RS, eps, z, klz, kl_elem=None):
+    _log("gmvae_latent_fwd")
+    zz, kl = _gmvae_latent(qh.double(), pz.double(), K_, B, L, RS, eps)
+    M = K_ * RS * B
+    z[:M, :L] = zz.reshape(M, L)
+    z[:M, L] = 1.0
+    z[:M, L + 1:] = 0.0
+    klz[:M] = kl.sum(dim=-1).reshape(M)
+    if kl_elem is not None:
+        kl_elem.reshape(-1)[:M * L] = kl.reshape(-1)
+
+
+def gmvae_latent_bwd(qh, pz, K_, B, L, RS, eps, dz, coef, dqh, dpz):
+    _log("gmvae_latent_bwd")
+    M = K_ * RS * B
+    q_leaf = qh[:K_ * B, :2 * L].double().detach().clone().requires_grad_(True)
+    p_leaf = pz[:K_, :2 * L].double().detach().clone().requires_grad_(True)
+    zz, kl = _gmvae_latent(q_leaf, p_leaf, K_, B, L, RS, eps)
+    total = (dz[:M, :L].double() * zz.reshape(M, L)).sum() + \
+        (coef[:M].double() * kl.sum(dim=-1).reshape(M)).sum()
+    gq, gp = torch.autograd.grad(total, [q_leaf, p_leaf])
+    dqh[:K_ * B, :2 * L] = gq
+    dpz[:K_, :2 * L] = gp
+
+
+def gmvae_row_coefficients(y, K_, RS, B, weight, go, coef):
+    _log("gmvae_row_coefficients")
+    w = (y.reshape(-1)[:B * K_].double().reshape(B, K_).t() / (B * RS))     # (K, B)
+    rows = w.unsqueeze(1).expand(K_, RS, B).reshape(-1)
+    go[:K_ * RS * B] = -rows
+    coef[:K_ * RS * B] = weight * rows
+
+
+def gmvae_bound(y, logy, logp, klz, log_py, K_, RS, B, weight, free_nats_threshold, uniform_prior,
+                out, dlogits, dpy_logits, ll_mean, klz_mean):
+    _log("gmvae_bound")
+    logits = logy.reshape(-1)[:B * K_].double().reshape(B, K_).detach().clone().requires_grad_(True)
+    prior = log_py[:K_].double().detach().clone().requires_grad_(True)
+    lq = torch.log_softmax(logits, dim=-1)
+    q = torch.exp(lq)
+    lpy = torch.log_softmax(prior, dim=-1)
+    ll = logp[:K_ * RS * B].double().reshape(K_, RS, B).mean(dim=1)         # (K, B)
+    kz = klz[:K_ * RS * B].double().reshape(K_, RS, B).mean(dim=1)
+    ll_mean.reshape(-1)[:K_ * B] = ll.reshape(-1)
+    klz_mean.reshape(-1)[:K_ * B] = kz.reshape(-1)
+    reconstruction = (q.t() * ll).sum(dim=0).mean()
+    kl_z = (q.t() * kz).sum(dim=0).mean()
+    if uniform_prior:
+        kl_y = (math.log(K_) + (q * lq).sum(dim=-1)).mean()
+    else:
+        kl_y = (q * (lq - lpy)).sum(dim=-1).mean()
+    if free_nats_threshold:
+        threshold = torch.tensor(float(free_nats_threshold), dtype=torch.float64)
+        kl_y_mod = torch.where(kl_y > threshold, kl_y, threshold)
+    else:
+        kl_y_mod = kl_y
+    weighted = reconstruction - weight * (kl_z + kl_y_mod)
+    values = [reconstruction - kl_z - kl_y, weighted, reconstruction, kl_z, kl_y, kl_y_mod]
+    out[:6] = torch.stack([v.detach() for v in values])
+    if dlogits is not None or dpy_logits is not None:
+        g_logits, g_prior = torch.autograd.grad(-weighted, [logits, prior], allow_unused=True)
+        if dlogits is not None:
+            dlogits.reshape(-1)[:B * K_] = g_logits.reshape(-1)
+        if dpy_logits is not None:
+            dpy_logits[:K_] = g_prior if g_prior is not None else 0.0
+
+
+def gmvae_z_mean(qh, y, K_, B, L, z_mean):
+    _log("gmvae_z_mean")
+    mean = qh[:K_ * B, :L].double().reshape(K_, B, L)
+    w = y.reshape(-1)[:B * K_].double().reshape(B, K_).t().unsqueeze(-1)
+    z_mean.reshape(-1)[:B * L] = (mean * w).sum(dim=0).reshape(-1)
+
+
+def _write_mixture_moments(m, v, y, K_, B, G, RS, outs):
+    """GMVAE:3312-3386 with the y-weighted per-cluster mean of quirk Q7."""
+    m = m.reshape(K_, RS, B, G)
+    v = v.reshape(K_, RS, B, G)
+    w = y.reshape(-1)[:B * K_].double().reshape(B, K_).t().unsqueeze(-1)      # (K, B, 1)
+    means = m.mean(dim=1) * w
+    mean_of_var = (v.mean(dim=1) * w).sum(dim=0)
+    var_of_mean = (((m - means.unsqueeze(1)) ** 2).mean(dim=1) * w).sum(dim=0)
+    for out, value in zip(outs, (means.sum(dim=0), torch.sqrt(mean_of_var + var_of_mean),
+                                 torch.sqrt(var_of_mean))):
+        if out is not None:
+            out[:B, :G] = value
+
+
+_vae_likelihood_moments = likelihood_moments
+_vae_piecewise_moments = piecewise_moments
+
+
+def likelihood_moments(kind, a, head_stride, B, G, RS, K, y, p_x_mean, p_x_stddev,  # noqa: F811
+                       stddev_of_mean):
+    if K == 1 and y is None:
+        return _vae_likelihood_moments(kind, a, head_stride, B, G, RS, K, y, p_x_mean,
+                                       p_x_stddev, stddev_of_mean)
+    _log("likelihood_moments")
+    name, theta = _theta(kind, a.double(), head_stride, K * RS * B, G)
+    m, v = O.likelihood_moments(name, theta)
+    _write_mixture_moments(m, v, y, K, B, G, RS, (p_x_mean, p_x_stddev, stddev_of_mean))
+
+
+def piecewise_moments(kind, k_max, a, head_stride, B, G, RS, p_x_mean, p_x_stddev,  # noqa: F811
+                      stddev_of_mean, K_=1, y=None):
+    if K_ == 1 and y is None:
+        return _vae_piecewise_moments(kind, k_max, a, head_stride, B, G, RS, p_x_mean,
+                                      p_x_stddev, stddev_of_mean)
+    _log("piecewise_moments")
+    a = a.double()
+    rows = K_ * RS * B
+    name, theta = _theta(kind, a, head_stride, rows, G)
+    P = len(theta)
+    logits = torch.stack([a[:rows, (P + c) * head_stride:(P + c) * head_stride + G]
+                          for c in range(k_max + 1)], dim=-1)
+    m, v = O.likelihood_moments(name, theta)
+    m, v = O.piecewise_moments(m, v, torch.log_softmax(logits, dim=-1), k_max)
+    _write_mixture_moments(m, v, y, K_, B, G, RS, (p_x_mean, p_x_stddev, stddev_of_mean))

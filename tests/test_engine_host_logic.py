@@ -24,6 +24,15 @@ def engine_on_cpu(monkeypatch):
         original(self, *args, **kwargs)
 
     monkeypatch.setattr(E.VAEEngine, "__init__", init)
+    import scvae_b200.gmvae_engine as GE
+    monkeypatch.setattr(GE, "K", kernel_standins)
+    gm_original = GE.GMVAEEngine.__init__
+
+    def gm_init(self, *args, **kwargs):
+        kwargs["device"] = "cpu"
+        gm_original(self, *args, **kwargs)
+
+    monkeypatch.setattr(GE.GMVAEEngine, "__init__", gm_init)
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     del kernel_standins.launches[:]
@@ -48,7 +57,20 @@ def test_vae_engine_evaluation_host_logic(engine_on_cpu, name):
     assert "adam_clip_step" not in engine_on_cpu
 
 
+@pytest.mark.parametrize("name", Z.GMVAE_TRAIN)
+def test_gmvae_engine_training_step_host_logic(engine_on_cpu, name):
+    Z.test_gmvae_training_step_matches_reference_graph(name)
+    assert engine_on_cpu.count("gmvae_bound") == 1
+
+
+@pytest.mark.parametrize("name", Z.GMVAE_EVAL)
+def test_gmvae_engine_evaluation_host_logic(engine_on_cpu, name):
+    Z.test_gmvae_evaluation_matches_reference_graph(name)
+    assert "adam_clip_step" not in engine_on_cpu
+
+
 def test_product_kernels_module_is_untouched_outside_the_fixture():
     import scvae_b200.engine as E
+    import scvae_b200.gmvae_engine as GE
     import scvae_b200.kernels as K
-    assert E.K is K
+    assert E.K is K and GE.K is K
