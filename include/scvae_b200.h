@@ -114,6 +114,21 @@ int scvae_gemm_sm_limit(int max_ctas);
 int scvae_f32_to_f16(const float *src, int64_t lds, int64_t rows, int cols, void *dst,
                      int64_t ldd, float scale, void *stream);
 
+/* ---- f3: dropout on the input of a dense layer  (MU:45-50; one mask per site, VAE:2286,
+ * :2487, :2516) ------------------------------------------------------------------------------
+ * Inverted dropout on a bias-augmented operand: out = x * [noise < threshold] / keep on the
+ * logical columns [0, n), which skip the physical column `skip_col` (the ones column when
+ * decoder extras follow it; skip_col == n when it lies behind the masked range); every other
+ * of the `width` stored columns is copied.  noise (rows, n) contiguous: standard-normal draws
+ * (scvae_fill_normal) with threshold = the normal quantile of `keep`, or injected values.
+ * Backward: dx (+)= dsrc * mask / keep on the masked columns (dsrc NULL: in place). */
+int scvae_dropout_fwd(const float *x, int64_t ldx, int rows, int n, int skip_col,
+                      const float *noise, float threshold, float keep, float *out, int64_t ldo,
+                      int width, void *stream);
+int scvae_dropout_bwd(float *dx, int64_t lddx, int rows, int n, int skip_col, const float *noise,
+                      float threshold, float keep, const float *dsrc, int64_t ldds,
+                      int accumulate, void *stream);
+
 /* ---- a2: batch normalisation + ReLU  (MU:62-74; tf.contrib batch_norm center=True,
  * scale=False, epsilon 1e-3, decay 0.999) ---------------------------------------------
  * y (M, ldy) pre-activations, H logical columns; rows form `groups` consecutive groups of

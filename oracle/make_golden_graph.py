@@ -129,6 +129,14 @@ CASES = [
      dict()),
     ("vae_nb_dropout_train", "VAE", dict(reconstruction_distribution="negative binomial",
                                           dropout_keep_probabilities=[0.8, 0.9, 0.7]), dict()),
+    ("vae_zinb_dropout_deep_train", "VAE",
+     dict(reconstruction_distribution="zero-inflated negative binomial", hidden_sizes=[8, 5],
+          batch_correction=True, number_of_batches=3, count_sum=True,
+          dropout_keep_probabilities=[0.8, 0.9, 0.7]), dict(R=1, S=2)),
+    ("vae_poisson_k2_dropout_train", "VAE",
+     dict(reconstruction_distribution="poisson", number_of_reconstruction_classes=2,
+          latent_distribution="unit-variance gaussian", analytical_kl_term=True,
+          dropout_keep_probabilities=0.75), dict(R=2, S=1)),
     # large head weights: log_lambda / log_r reach their +-10 clips, log_sigma its +-3 clips
     # (zero gradient through a clipped unit)
     ("vae_poisson_clipped_train", "VAE", dict(reconstruction_distribution="poisson"),

@@ -64,6 +64,10 @@ SIGNATURES = {
                                               c_ptr]),
     "scvae_vae_bound_rows": (c_int, [c_ptr, c_ptr, c_int, c_int, c_int, c_f32, c_ptr, c_ptr,
                                      c_ptr]),
+    "scvae_dropout_fwd": (c_int, [c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_f32, c_f32, c_ptr,
+                                  c_i64, c_int, c_ptr]),
+    "scvae_dropout_bwd": (c_int, [c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_f32, c_f32, c_ptr,
+                                  c_i64, c_int, c_ptr]),
     "scvae_likelihood_fwd": (c_int, [c_int, c_ptr, c_i64, c_int, c_ptr, c_i64, c_i64, c_int,
                                      c_int, c_ptr, c_ptr, c_ptr]),
     "scvae_likelihood_bwd": (c_int, [c_int, c_ptr, c_i64, c_int, c_ptr, c_i64, c_i64, c_int,

@@ -92,7 +92,8 @@ class VAEEngine:
                  minibatch_normalisation=True, kl_weight=1.0, device="cuda", seed=0,
                  tensor_cores=True, fused_heads=True, number_of_batches=0, count_sum_feature=False,
                  inference_architecture="MLP", generative_architecture="MLP",
-                 number_of_reconstruction_classes=0, analytical_kl_term=True):
+                 number_of_reconstruction_classes=0, analytical_kl_term=True,
+                 dropout_keep_probabilities=None):
         if reconstruction_distribution not in K.LIKELIHOOD_KINDS:
             raise ValueError("reconstruction distribution `{}` is not supported by the "
                              "B200 hot path".format(reconstruction_distribution))
@@ -109,6 +110,17 @@ class VAEEngine:
         # sampled KL term, log q(z|x) - log p(z) at the drawn z (VAE:2628-2640), instead of the
         # closed form (VAE:2624-2627); one KL value per (sample, cell) row
         self.sampled_kl = not bool(analytical_kl_term)
+        # dropout keep probabilities [hidden, x, z] (VAE:246-269; a scalar means hidden only);
+        # False / None / 0 / 1 switch a kind off (MU:45-46)
+        keep = dropout_keep_probabilities
+        if isinstance(keep, (list, tuple)):
+            keep = list(keep) + [False] * (3 - len(keep))
+        else:
+            keep = [keep, False, False]
+        self.keep_h, self.keep_x, self.keep_z = [
+            float(k) if (k and k != 1) else None for k in keep[:3]]
+        self.dropout_active = any(k is not None for k in (self.keep_h, self.keep_x, self.keep_z))
+        self.dropout_seed = int(seed) + 104729
         self.bn = bool(minibatch_normalisation)
         self.kl_weight = float(kl_weight)
         self.device = torch.device(device)
@@ -391,6 +403,9 @@ class VAEEngine:
         p.count_sum = zeros(B) if self.count_sum_feature else None
         p.kl_row = zeros(B)
         p.kl_rows = zeros(M) if self.sampled_kl else None
+        p.drop = {}                      # dropout sites: noise, dropped operand copy
+        p.drop_on = False
+        p.drop_injected = False          # tests: noise tensors set by hand, not drawn
         p.kl_elem = zeros(B, self.L)
         p.kl_neurons = zeros(self.L)
         p.decY = [zeros(M, round4(l.n_out)) for l in self.dec]
@@ -603,7 +618,8 @@ class VAEEngine:
             update_moving = is_training
         # keep_heads=False: the caller needs log p only, not the (rows x P genes) head
         # pre-activations (per-epoch evaluation passes): forward-only fused heads
-        use16 = bool((fused_backward or not keep_heads) and p.have_t16
+        drop = p.drop_on = bool(self.dropout_active and is_training)
+        use16 = bool((fused_backward or not keep_heads) and p.have_t16 and not drop
                      and not getattr(p, "use_T", False) and self._fused_possible(M, B))
         if not use16 and not getattr(p, "have_x", True):
             raise RuntimeError("this minibatch was densified for the fused 16-bit training step "
@@ -615,7 +631,9 @@ class VAEEngine:
                 self._refresh_shadows(p, M)
                 self._gemm16(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, p.X16, p.W1_16, p.encY[i])
             else:
-                self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, h, l.w, p.encY[i])
+                keep = (self.keep_x if i == 0 else self.keep_h) if drop else None
+                src = self._drop_site(p, l.name, h, B, l.n_in, l.n_in, keep).copy if keep else h
+                self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, src, l.w, p.encY[i])
             if l.bn:
                 K.bn_act_fwd(p.encY[i], l.n_out, l.beta, l.moving_mean, l.moving_var, p.encH[i],
                              p.enc_mean[i], p.enc_rstd[i], p.bn_scratch, training=is_training,
@@ -624,13 +642,25 @@ class VAEEngine:
                 K.act_fwd(p.encY[i], l.n_out, p.encH[i], relu=True)
             h = p.encH[i]
         l = self.post
-        self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, h, l.w, p.PH)
+        if drop and self.keep_h:
+            # one mask per posterior parameter over the same activation (VAE:2280-2289)
+            L = self.L
+            for part, site in enumerate(["POSTERIOR/MU"] + (
+                    [] if self.unit_variance else ["POSTERIOR/LOG_SIGMA"])):
+                st = self._drop_site(p, site, h, B, l.n_in, l.n_in, self.keep_h)
+                K.gemm(K.GEMM_NT, B, L, l.n_in + 1, st.copy, l.w[part * L:(part + 1) * L],
+                       p.PH[:, part * L:(part + 1) * L], tensor_cores=False)
+        else:
+            self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, h, l.w, p.PH)
         K.gaussian_latent_fwd(p.PH, B, self.L, RS, p.eps, p.Z, p.kl_row, p.kl_elem,
                               unit_variance=self.unit_variance, deterministic=deterministic)
         self._decoder_features(p, M)
         d = p.Z
         for j, l in enumerate(self.dec):
-            self._gemm(p, K.GEMM_NT, M, l.n_out, l.k_in, d, l.w, p.decY[j][:M])
+            keep = (self.keep_z if j == 0 else self.keep_h) if drop else None
+            src = self._drop_site(p, l.name, d, M, l.n_in + l.n_extra, l.n_in,
+                                  keep).copy if keep else d
+            self._gemm(p, K.GEMM_NT, M, l.n_out, l.k_in, src, l.w, p.decY[j][:M])
             if l.bn:
                 K.bn_act_fwd(p.decY[j][:M], l.n_out, l.beta, l.moving_mean, l.moving_var,
                              p.decH[j][:M], p.dec_mean[j], p.dec_rstd[j], p.bn_scratch,
@@ -671,7 +701,13 @@ class VAEEngine:
             self._bound(p, R, S, weight)
             p.fused_done = True
             return p
-        self._gemm(p, K.GEMM_NT, M, l.n_out, l.k_in, d, l.w, p.A[:M])
+        if drop and self.keep_h:
+            for r0, nr, site in self._head_blocks():
+                st = self._drop_site(p, site, d, M, l.n_in + l.n_extra, l.n_in, self.keep_h)
+                K.gemm(K.GEMM_NT, M, nr, l.k_in, st.copy, l.w[r0:r0 + nr], p.A[:M, r0:r0 + nr],
+                       tensor_cores=False)
+        else:
+            self._gemm(p, K.GEMM_NT, M, l.n_out, l.k_in, d, l.w, p.A[:M])
         if fused_backward:
             assert R == 1 and not deterministic
             self._plan_backward(p)
@@ -682,6 +718,53 @@ class VAEEngine:
             self._likelihood(p, tgt, p.A[:M], M, rc, logp=p.logp)
             self._bound(p, R, S, weight, p.go if want_go else None, deterministic)
         return p
+
+    # ---- dropout (MU:45-50): one mask per site, the dropped copy feeds the site's product ------
+    def _drop_site(self, p, site, src, rows, n, skip_col, keep):
+        """Draw (unless injected) the site's mask and write the dropped copy of ``src``."""
+        st = p.drop.get(site)
+        if st is None:
+            import statistics
+            st = p.drop[site] = type("DropSite", (), {})()
+            st.index = len(p.drop)
+            st.rows, st.n, st.skip, st.keep = rows, n, skip_col, keep
+            st.threshold = statistics.NormalDist().inv_cdf(keep)
+            st.noise = torch.zeros(rows, n, dtype=torch.float32, device=self.device)
+            st.copy = torch.zeros(rows, src.shape[1], dtype=torch.float32, device=self.device)
+        if p.drop_injected:
+            # keep (1) -> far below, drop (0) -> far above any threshold
+            st.noise.copy_((0.5 - p.drop_masks[site].to(self.device, torch.float32)) * 2e9)
+        else:
+            K.fill_normal(st.noise, self.dropout_seed + 7919 * st.index, 0, self.store.step)
+        K.dropout_fwd(src, rows, n, skip_col, st.noise, st.threshold, keep, st.copy,
+                      src.shape[1])
+        return st
+
+    def inject_dropout_masks(self, p, masks):
+        """Parity tests: 0/1 keep masks by site name (rows x masked columns) instead of draws."""
+        p.drop_injected = masks is not None
+        p.drop_masks = masks
+
+    def _drop_bwd(self, st, dx, dsrc=None, accumulate=False):
+        K.dropout_bwd(dx, st.rows, st.n, st.skip, st.noise, st.threshold, st.keep, dsrc=dsrc,
+                      accumulate=accumulate)
+
+    def _head_blocks(self):
+        """(first row, rows, site) of every likelihood head in the stacked head weight: each
+        head is a dense layer of its own in the reference, with its own dropout mask."""
+        blocks = [(h * self.Gn, self.Gn, "X_TILDE/" + head.upper())
+                  for h, head in enumerate(self.heads)]
+        if self.k_max:
+            blocks.append((self.P * self.Gn, (self.k_max + 1) * self.Gn, "X_TILDE/P_K"))
+        return blocks
+
+    def _drop_tmp(self, p, rows, cols):
+        key = "_drop_tmp_{}".format(rows)
+        buf = getattr(p, key, None)
+        if buf is None or buf.shape[1] < cols:
+            buf = torch.zeros(rows, round4(cols), dtype=torch.float32, device=self.device)
+            setattr(p, key, buf)
+        return buf
 
     def _bound(self, p, R, S, weight, go=None, deterministic=False):
         """ELBO terms (+ d loss / d log p) from the per-row log-likelihoods and the KL term."""
@@ -790,6 +873,17 @@ class VAEEngine:
                         p.head_reduced_from = off
                     p.head_ev[1].record(side)
                     p.head_join = p.head_ev[1]
+        elif p.drop_on and self.keep_h:
+            # per head: dW from the head's own dropped operand; the input gradients of the
+            # heads meet in dd through their masks
+            tmp = self._drop_tmp(p, M, l.in_p)
+            for b, (r0, nr, site) in enumerate(self._head_blocks()):
+                st = p.drop[site]
+                K.gemm(K.GEMM_TN, nr, l.in_p, M, p.dA[:, r0:r0 + nr], st.copy, l.dw[r0:r0 + nr],
+                       tensor_cores=False)
+                K.gemm(K.GEMM_NN, M, l.n_in, nr, p.dA[:, r0:r0 + nr], l.w[r0:r0 + nr], tmp,
+                       tensor_cores=False)
+                self._drop_bwd(st, dd_in, dsrc=tmp, accumulate=b > 0)
         else:
             # wgrad (bias gradient = the augmented ones column) and dgrad of the heads
             self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, M, p.dA, d_in, l.dw)
@@ -803,8 +897,13 @@ class VAEEngine:
                 K.act_bwd(p.d_decH[j], p.decH[j], l.n_out, p.d_decY[j], relu=True)
             d_in = p.decH[j - 1] if j > 0 else p.Z
             dd_in = p.d_decH[j - 1] if j > 0 else p.dZ
+            st = p.drop.get(l.name) if p.drop_on else None
+            if st is not None:
+                d_in = st.copy
             self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, M, p.d_decY[j], d_in, l.dw)
             self._gemm(p, K.GEMM_NN, M, l.n_in, l.n_out, p.d_decY[j], l.w, dd_in)
+            if st is not None:
+                self._drop_bwd(st, dd_in)       # gradient w.r.t. the un-dropped input, in place
         if self.sampled_kl:
             weight = warm_up_weight * self.kl_weight
             # R == 1: d loss / d log p = -1/(S B) for every row, so d loss / d KL = weight/(S B)
@@ -817,9 +916,23 @@ class VAEEngine:
                                   unit_variance=self.unit_variance)
         l = self.post
         h_in = p.encH[-1] if self.enc else p.X
-        self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.dPH, h_in, l.dw)
-        if self.enc:
-            self._gemm(p, K.GEMM_NN, B, l.n_in, l.n_out, p.dPH, l.w, p.d_encH[-1])
+        if p.drop_on and self.keep_h:
+            L = self.L
+            tmp = self._drop_tmp(p, B, l.in_p) if self.enc else None
+            for part, site in enumerate(["POSTERIOR/MU"] + (
+                    [] if self.unit_variance else ["POSTERIOR/LOG_SIGMA"])):
+                st = p.drop[site]
+                rows, cols = slice(part * L, (part + 1) * L), slice(part * L, (part + 1) * L)
+                K.gemm(K.GEMM_TN, L, l.in_p, B, p.dPH[:, cols], st.copy, l.dw[rows],
+                       tensor_cores=False)
+                if self.enc:
+                    K.gemm(K.GEMM_NN, B, l.n_in, L, p.dPH[:, cols], l.w[rows], tmp,
+                           tensor_cores=False)
+                    self._drop_bwd(st, p.d_encH[-1], dsrc=tmp, accumulate=part > 0)
+        else:
+            self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.dPH, h_in, l.dw)
+            if self.enc:
+                self._gemm(p, K.GEMM_NN, B, l.n_in, l.n_out, p.dPH, l.w, p.d_encH[-1])
         for i in range(len(self.enc) - 1, -1, -1):
             l = self.enc[i]
             if l.bn:
@@ -828,6 +941,9 @@ class VAEEngine:
             else:
                 K.act_bwd(p.d_encH[i], p.encH[i], l.n_out, p.d_encY[i], relu=True)
             h_in = p.encH[i - 1] if i > 0 else p.X
+            st = p.drop.get(l.name) if p.drop_on else None
+            if st is not None:
+                h_in = st.copy
             if i == 0 and p.fused_done:
                 # dW1 = dY1^T X with the fp16 minibatch (dY1 scaled into fp16 range)
                 if getattr(p, "dY1_16", None) is None:
@@ -840,6 +956,8 @@ class VAEEngine:
                 self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.d_encY[i], h_in, l.dw)
             if i > 0:
                 self._gemm(p, K.GEMM_NN, B, l.n_in, l.n_out, p.d_encY[i], l.w, p.d_encH[i - 1])
+                if st is not None:
+                    self._drop_bwd(st, p.d_encH[i - 1])
         self._reduce_upto = None
         self._side_tail = None
         if p.head_join is not None:

@@ -213,6 +213,23 @@ def gaussian_latent_bwd(ph, B, L, RS, eps, dz, kl_coef, dph, unit_variance=False
                "gaussian_latent_bwd")
 
 
+def dropout_fwd(x, rows, n, skip_col, noise, threshold, keep, out, width):
+    """out = x * [noise < threshold] / keep on the logical columns [0, n) (skipping the physical
+    column ``skip_col``), other stored columns copied (MU:45-50)."""
+    lib = _lib.load()
+    _lib.check(lib.scvae_dropout_fwd(_p(x), _ld(x), rows, n, skip_col, _p(noise), float(threshold),
+                                     float(keep), _p(out), _ld(out), width, _stream()),
+               "dropout_fwd")
+
+
+def dropout_bwd(dx, rows, n, skip_col, noise, threshold, keep, dsrc=None, accumulate=False):
+    lib = _lib.load()
+    _lib.check(lib.scvae_dropout_bwd(_p(dx), _ld(dx), rows, n, skip_col, _p(noise),
+                                     float(threshold), float(keep), _p(dsrc),
+                                     _ld(dsrc) if dsrc is not None else 0, int(accumulate),
+                                     _stream()), "dropout_bwd")
+
+
 def gaussian_sampled_kl(ph, B, L, RS, eps, kl_rows, kl_elem=None, unit_variance=False,
                         deterministic=False):
     """Sampled KL term per (sample, cell) row (VAE:2628-2640)."""

@@ -5,7 +5,7 @@ Same constructor keywords, ``train`` / ``evaluate`` / ``sample`` signatures, ret
 log-directory layout, checkpoint naming and TensorBoard tags; the TensorFlow graph, session
 and saver underneath are replaced by ``scvae_b200.engine.VAEEngine`` (hand-written sm_100a
 kernels behind ``libscvae_b200.so``).  Options of the reference that are outside the hot-path
-scope of this round (dropout, the continuous likelihoods) raise
+scope of this round (the continuous likelihoods, dropout for the GMVAE) raise
 ``NotImplementedError`` instead of silently degrading.
 """
 
@@ -149,8 +149,8 @@ class VariationalAutoencoder:
                 self.type != "VAE" or self.reconstruction_distribution_name != "constrained poisson"):
             problems.append("count-sum-parameterised likelihoods other than the VAE's "
                             "constrained Poisson")
-        if self.dropout_parts:
-            problems.append("dropout")
+        if self.dropout_parts and self.type != "VAE":
+            problems.append("dropout for the GMVAE")
         if self.parameterise_latent_posterior:
             problems.append("parameterised latent posteriors")
         if problems:
@@ -299,7 +299,8 @@ class VariationalAutoencoder:
                          inference_architecture=self.inference_architecture,
                          generative_architecture=self.generative_architecture,
                          number_of_reconstruction_classes=self.k_max,
-                         analytical_kl_term=self.analytical_kl_term)
+                         analytical_kl_term=self.analytical_kl_term,
+                         dropout_keep_probabilities=self.dropout_keep_probabilities)
 
     def _attach_features(self, data, data_set):
         """Per-cell decoder features of a data set (VAE:816-833): batch indices for batch

@@ -127,6 +127,27 @@ def bn_act_bwd(dout, y, out, H, save_mean, save_rstd, dy, dbeta, scratch, relu=T
     dy[:, :H] = d.reshape(M, H)
 
 
+def _physical(n, skip_col):
+    return [c if c < skip_col else c + 1 for c in range(n)]
+
+
+def dropout_fwd(x, rows, n, skip_col, noise, threshold, keep, out, width):
+    _log("dropout_fwd")
+    out[:rows, :width] = x[:rows, :width]
+    cols = _physical(n, skip_col)
+    mask = (noise[:rows, :n] < threshold).float()
+    out[:rows, cols] = x[:rows, cols] * mask / keep
+
+
+def dropout_bwd(dx, rows, n, skip_col, noise, threshold, keep, dsrc=None, accumulate=False):
+    _log("dropout_bwd")
+    cols = _physical(n, skip_col)
+    mask = (noise[:rows, :n] < threshold).float()
+    source = dx if dsrc is None else dsrc
+    g = source[:rows, cols] * mask / keep
+    dx[:rows, cols] = dx[:rows, cols] + g if (accumulate and dsrc is not None) else g
+
+
 def gaussian_latent_fwd(ph, B, L, RS, eps, z, kl_row, kl_elem=None, unit_variance=False,
                         deterministic=False):
     _log("gaussian_latent_fwd")

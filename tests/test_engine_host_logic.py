@@ -51,6 +51,24 @@ def test_vae_engine_training_step_host_logic(engine_on_cpu, name):
     assert ("vae_bound_rows" in launches) == sampled
 
 
+@pytest.mark.parametrize("name", Z.DROPOUT_CASES[1:])
+def test_vae_engine_dropout_host_logic_more_sites(engine_on_cpu, name):
+    Z.test_vae_dropout_training_step_matches_reference_graph(name)
+    assert "fill_normal" not in engine_on_cpu
+
+
+def test_vae_engine_dropout_host_logic(engine_on_cpu):
+    """Dropout with the masks the reference-graph run recorded: six sites, one product per
+    posterior parameter and per likelihood head, masked gradient routing."""
+    Z.test_vae_dropout_training_step_matches_reference_graph(Z.DROPOUT_CASES[0])
+    launches = engine_on_cpu
+    assert launches.count("dropout_fwd") == 6       # ENCODER/1, MU, LOG_SIGMA, DECODER/1, P, LOG_R
+    # two heads into d(decoder output), DECODER/1 in place, two posterior heads into d(encoder
+    # output); ENCODER/1 masks the data itself (no input gradient)
+    assert launches.count("dropout_bwd") == 5
+    assert "fill_normal" not in launches            # masks injected, nothing drawn
+
+
 @pytest.mark.parametrize("name", Z.VAE_EVAL)
 def test_vae_engine_evaluation_host_logic(engine_on_cpu, name):
     Z.test_vae_evaluation_matches_reference_graph(name)

@@ -38,9 +38,12 @@ def test_option_validation_mirrors_the_scope():
                                reconstruction_distribution="zero-inflated poisson",
                                number_of_reconstruction_classes=2)
     # still outside: loud, never silently degraded
+    VariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
+                           dropout_keep_probabilities=[0.9])          # VAE: built
     with pytest.raises(NotImplementedError):
-        VariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
-                               dropout_keep_probabilities=[0.9])
+        GaussianMixtureVariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
+                                              number_of_latent_clusters=3,
+                                              dropout_keep_probabilities=[0.9])
     with pytest.raises(NotImplementedError):
         GaussianMixtureVariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
                                               number_of_latent_clusters=3,

@@ -65,11 +65,15 @@ def _vae(name):
         number_of_reconstruction_classes=kw.get("number_of_reconstruction_classes", 0),
         # VAE:186-192: the closed-form KL is the default for the plain gaussian only
         analytical_kl_term=kw.get("analytical_kl_term",
-                                  kw.get("latent_distribution", "gaussian") == "gaussian"))
+                                  kw.get("latent_distribution", "gaussian") == "gaussian"),
+        dropout_keep_probabilities=kw.get("dropout_keep_probabilities"))
     eng.import_parameters(_params(meta, groups))
     feeds = groups["in_feed"]
     B = feeds["X"].shape[0]
     plan = eng._plan(B, R * S)
+    if "in_dropout" in groups:           # the recorded per-site keep masks instead of draws
+        eng.inject_dropout_masks(plan, {site: torch.tensor(mask, dtype=torch.float32)
+                                        for site, mask in groups["in_dropout"].items()})
     eng.set_batch_dense(plan, torch.tensor(feeds["X"], dtype=torch.float32).cuda())
     if kw.get("batch_correction") or kw.get("count_sum"):
         eng.set_batch_features(
@@ -266,6 +270,45 @@ def test_vae_sampled_kl_training_step_matches_reference_graph(name):
     test_vae_training_step_matches_reference_graph(name)
 
 
+def test_dropout_kernels_match_their_cpu_restatement():
+    """scvae_dropout_fwd / scvae_dropout_bwd against tests/kernel_standins.py (whose versions
+    carry the engine through the reference-graph dropout case on the CPU)."""
+    import kernel_standins as C
+    from scvae_b200 import kernels as K
+    gen = torch.Generator().manual_seed(9)
+    rows, n, skip, width, keep = 37, 11, 7, 16, 0.8
+    x = torch.randn(rows, width, generator=gen)
+    noise = torch.randn(rows, n, generator=gen)
+    d = torch.randn(rows, width, generator=gen)
+    acc = torch.randn(rows, width, generator=gen)
+    thr = 0.8416212335729143
+    for skip_col in (skip, n):
+        want = torch.zeros(rows, width)
+        C.dropout_fwd(x, rows, n, skip_col, noise, thr, keep, want, width)
+        got = torch.zeros(rows, width, device="cuda:0")
+        K.dropout_fwd(x.cuda(), rows, n, skip_col, noise.cuda(), thr, keep, got, width)
+        assert torch.allclose(got.cpu(), want, rtol=1e-6, atol=0)
+        for dsrc, accumulate in ((None, False), (d, False), (d, True)):
+            want = acc.clone()
+            C.dropout_bwd(want, rows, n, skip_col, noise, thr, keep, dsrc=dsrc,
+                          accumulate=accumulate)
+            got = acc.clone().cuda()
+            K.dropout_bwd(got, rows, n, skip_col, noise.cuda(), thr, keep,
+                          dsrc=None if dsrc is None else dsrc.cuda(), accumulate=accumulate)
+            assert torch.allclose(got.cpu(), want, rtol=1e-6, atol=1e-7)
+
+
+DROPOUT_CASES = ["vae_nb_dropout_train", "vae_zinb_dropout_deep_train",
+                 "vae_poisson_k2_dropout_train"]
+
+
+@pytest.mark.parametrize("name", DROPOUT_CASES)
+def test_vae_dropout_training_step_matches_reference_graph(name):
+    """Dropout with the recorded masks (VAE:246-269, MU:45-50): all three site kinds; two hidden
+    layers with decoder extras and three heads; hidden-only with the P_K head."""
+    test_vae_training_step_matches_reference_graph(name)
+
+
 def test_train_evaluate_unit_variance_gaussian_with_its_default_sampled_kl(tmp_path):
     """`-q "unit-variance gaussian"` end to end through the model class: the reference's default
     for it is the sampled KL (VAE:186-192), which used to be refused.  The ELBO must improve and
@@ -291,3 +334,31 @@ def test_train_evaluate_unit_variance_gaussian_with_its_default_sampled_kl(tmp_p
     assert MU.load_kl_divergences(model, "training").shape == (4, 4)
     reconstructed = model.evaluate(test, minibatch_size=64, output_versions="reconstructed")
     assert numpy.isfinite(reconstructed.values).all()
+
+
+def test_train_evaluate_with_dropout(tmp_path):
+    """`--dropout-keep-probabilities 0.8 0.9 0.7` end to end through the model class (masks drawn
+    on the device inside the captured step, no dropout in the evaluation passes)."""
+    import scipy.sparse
+    from oracle import scvae_oracle as O
+    from scvae_b200 import model_utilities as MU
+    from scvae_b200.data_set import DataSet
+    from scvae_b200.variational_autoencoder import VariationalAutoencoder
+    x, labels = O.synthetic_counts(300, 60, n_types=3, seed=3, target_zero_fraction=0.8)
+    full = DataSet("toy", values=scipy.sparse.csr_matrix(numpy.minimum(x, 50.0)),
+                   labels=labels.astype(str))
+    training, validation, test = full.split()
+    model = VariationalAutoencoder(
+        feature_size=60, latent_size=4, hidden_sizes=[32, 16],
+        reconstruction_distribution="negative binomial",
+        dropout_keep_probabilities=[0.8, 0.9, 0.7], log_directory=str(tmp_path), seed=1)
+    assert "dropout_0.8_0.9_0.7" in model.name
+    assert model.train(training, validation, number_of_epochs=4, minibatch_size=50,
+                       learning_rate=1e-2, shuffle_seed=0) == 0
+    curve = MU.load_learning_curves(model, "training")["lower_bound"]
+    assert len(curve) == 4 and numpy.isfinite(curve).all() and curve[-1] > curve[0]
+    reconstructed = model.evaluate(test, minibatch_size=64, output_versions="reconstructed")
+    assert numpy.isfinite(reconstructed.values).all()
+    # evaluation is deterministic given the noise seed: no dropout outside training
+    again = model.evaluate(test, minibatch_size=64, output_versions="reconstructed")
+    assert numpy.array_equal(reconstructed.values, again.values)
