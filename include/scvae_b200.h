@@ -365,8 +365,9 @@ int scvae_gmvae_z_mean(const float *qh, int64_t ldq, const float *y, int K, int 
 int scvae_col_mean(const float *x, int64_t ldx, int rows, int cols, float *out,
                    void *stream);
 /* Philox-4x32-10 standard-normal fill (tf.random_normal stand-in, VAE:2363).  The Philox
- * offset is `offset + *offset_dev` (offset_dev nullable, device int64: normally the optimiser
- * step counter, which keeps the launch CUDA-graph capturable). */
+ * offset is `4 * (offset + *offset_dev)` outputs, i.e. one Philox block per unit, so calls with
+ * different offsets draw from disjoint blocks (offset_dev nullable, device int64: normally the
+ * optimiser step counter, which keeps the launch CUDA-graph capturable). */
 int scvae_fill_normal(float *out, int64_t n, uint64_t seed, uint64_t offset,
                       const int64_t *offset_dev, void *stream);
 

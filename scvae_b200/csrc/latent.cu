@@ -278,7 +278,10 @@ __global__ void fill_normal_kernel(float *__restrict__ out, int64_t n, uint64_t 
     if (base >= n) return;
     curandStatePhilox4_32_10_t st;
     if (offset_dev) offset += (uint64_t)(*offset_dev);
-    curand_init(seed, (unsigned long long)tid, offset, &st);
+    // curand offsets count single 32-bit outputs and one call consumes a Philox block of four:
+    // four outputs per unit of `offset`, so that consecutive offsets (steps, minibatches) draw
+    // from disjoint blocks instead of overlapping ones
+    curand_init(seed, (unsigned long long)tid, 4ull * offset, &st);
     const float4 v = curand_normal4(&st);
     const float vv[4] = {v.x, v.y, v.z, v.w};
     for (int j = 0; j < 4 && base + j < n; ++j) out[base + j] = vv[j];

@@ -362,3 +362,22 @@ def test_train_evaluate_with_dropout(tmp_path):
     # evaluation is deterministic given the noise seed: no dropout outside training
     again = model.evaluate(test, minibatch_size=64, output_versions="reconstructed")
     assert numpy.allclose(reconstructed.values, again.values, rtol=1e-5, atol=1e-6)
+
+
+def test_fill_normal_offsets_draw_from_disjoint_blocks():
+    """Consecutive offsets (optimiser steps, minibatches) must give independent noise: one
+    Philox block of four outputs per unit of offset, no shared uniforms between calls."""
+    from scvae_b200 import kernels as K
+    n = 1 << 20
+    a = torch.zeros(n, device="cuda:0")
+    b = torch.zeros(n, device="cuda:0")
+    K.fill_normal(a, 7, 0)
+    K.fill_normal(b, 7, 1)
+    for shift in range(-3, 4):
+        x, y = (a[shift:], b[:n - shift]) if shift >= 0 else (a[:n + shift], b[-shift:])
+        corr = torch.corrcoef(torch.stack([x, y]))[0, 1].item()
+        assert abs(corr) < 0.01, (shift, corr)
+    step = torch.tensor([1], dtype=torch.int64, device="cuda:0")
+    c = torch.zeros(n, device="cuda:0")
+    K.fill_normal(c, 7, 0, step)
+    assert torch.equal(b, c)            # host and device offsets add
