@@ -206,6 +206,9 @@ MODEL_NAME_CASES = [
                    number_of_warm_up_epochs=10, kl_weight=2)),
     ("GMVAE", dict(number_of_latent_clusters=5, proportion_of_free_nats_for_y_kl_divergence=0.8,
                    minibatch_normalisation=False, batch_correction=True, number_of_batches=2)),
+    # the reference's GMVAE has no LFM form: it takes these keywords and ignores them
+    ("GMVAE", dict(number_of_latent_clusters=3, inference_architecture="LFM",
+                   generative_architecture="LFM")),
     ("GMVAE", dict(number_of_latent_clusters=2, number_of_monte_carlo_samples=[4, 2],
                    number_of_importance_samples=3, dropout_keep_probabilities=[0.5],
                    count_sum_feature=True)),
