@@ -729,13 +729,17 @@ class VAEEngine:
             st.index = len(p.drop)
             st.rows, st.n, st.skip, st.keep = rows, n, skip_col, keep
             st.threshold = statistics.NormalDist().inv_cdf(keep)
+            # independent streams per site and, data-parallel, per rank (the shards differ)
+            rank = torch.distributed.get_rank() if (
+                torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
+            st.seed = self.dropout_seed + 7919 * st.index + 15485863 * rank
             st.noise = torch.zeros(rows, n, dtype=torch.float32, device=self.device)
             st.copy = torch.zeros(rows, src.shape[1], dtype=torch.float32, device=self.device)
         if p.drop_injected:
             # keep (1) -> far below, drop (0) -> far above any threshold
             st.noise.copy_((0.5 - p.drop_masks[site].to(self.device, torch.float32)) * 2e9)
         else:
-            K.fill_normal(st.noise, self.dropout_seed + 7919 * st.index, 0, self.store.step)
+            K.fill_normal(st.noise, st.seed, 0, self.store.step)
         K.dropout_fwd(src, rows, n, skip_col, st.noise, st.threshold, keep, st.copy,
                       src.shape[1])
         return st

@@ -92,3 +92,38 @@ def test_product_kernels_module_is_untouched_outside_the_fixture():
     import scvae_b200.gmvae_engine as GE
     import scvae_b200.kernels as K
     assert E.K is K and GE.K is K
+
+
+def test_vae_engine_draws_its_own_dropout_masks(engine_on_cpu):
+    """Without injected masks every site draws its own noise each step (one generator call per
+    site, keyed by site and optimiser step); evaluation passes do not drop anything."""
+    import numpy
+    from scvae_b200.engine import VAEEngine
+    from oracle import scvae_oracle as O
+    G, L, B = 40, 3, 64
+    eng = VAEEngine(G, L, [16, 8], "negative binomial", tensor_cores=False,
+                    dropout_keep_probabilities=[0.8, 0.9, 0.7])
+    x, _ = O.synthetic_counts(B, G, n_types=3, seed=4, target_zero_fraction=0.8)
+    plan = eng._plan(B, 1)
+    eng.set_batch_dense(plan, torch.tensor(numpy.minimum(x, 30.0), dtype=torch.float32))
+    plan.eps.normal_(generator=torch.Generator().manual_seed(0))
+    bound = eng.train_step(plan, 1, 1, 1e-3)
+    assert torch.isfinite(bound).all()
+    launches = list(engine_on_cpu)
+    sites = ["ENCODER/1", "ENCODER/2", "POSTERIOR/MU", "POSTERIOR/LOG_SIGMA", "DECODER/2",
+             "DECODER/1", "X_TILDE/P", "X_TILDE/LOG_R"]
+    assert list(plan.drop) == sites
+    assert launches.count("fill_normal") == len(sites) == launches.count("dropout_fwd")
+    assert len({st.seed for st in plan.drop.values()}) == len(sites)
+    for site, keep in (("ENCODER/1", 0.9), ("ENCODER/2", 0.8), ("DECODER/2", 0.7)):
+        st = plan.drop[site]
+        kept = (st.noise < st.threshold).float().mean().item()
+        assert abs(kept - keep) < 4 * (keep * (1 - keep) / st.noise.numel()) ** 0.5, (site, kept)
+    # the dropped copy: kept entries scaled by 1 / keep, the ones column intact
+    st = plan.drop["ENCODER/1"]
+    mask = (st.noise < st.threshold).float()
+    assert torch.allclose(st.copy[:, :G], plan.X[:, :G] * mask / 0.9)
+    assert torch.equal(st.copy[:, G], torch.ones(B))
+    del engine_on_cpu[:]
+    eng.forward(plan, False, 1, 1, 1.0)
+    assert "dropout_fwd" not in engine_on_cpu and "fill_normal" not in engine_on_cpu
