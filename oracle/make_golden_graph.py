@@ -93,6 +93,16 @@ CASES = [
      dict(is_training=False)),
     ("vae_nb_eval_deterministic", "VAE", dict(reconstruction_distribution="negative binomial"),
      dict(is_training=False, use_deterministic_z=True)),
+    # training steps WITHOUT sampling noise (z = q_z_mean while is_training): nothing random is
+    # left in the graph, so a machine with TensorFlow 1.15 can replay these through the real
+    # reference and pin the TF / TFP primitives too (oracle/check_with_tensorflow.py)
+    ("vae_nb_train_deterministic", "VAE", dict(reconstruction_distribution="negative binomial"),
+     dict(use_deterministic_z=True)),
+    ("vae_zinb_train_deterministic", "VAE",
+     dict(reconstruction_distribution="zero-inflated negative binomial", hidden_sizes=[8, 5]),
+     dict(use_deterministic_z=True)),
+    ("vae_poisson_eval_deterministic", "VAE", dict(reconstruction_distribution="poisson"),
+     dict(is_training=False, use_deterministic_z=True)),
     ("vae_zip_train", "VAE", dict(reconstruction_distribution="zero-inflated poisson"), dict()),
     ("vae_zinb_train", "VAE", dict(reconstruction_distribution="zero-inflated negative binomial",
                                    hidden_sizes=[8, 5]), dict()),

@@ -150,7 +150,8 @@ def test_oracle_matches_reference_graph(name):
             state.m[key] = torch.as_tensor(groups["in_adam_m"][key], dtype=D)
             state.v[key] = torch.as_tensor(groups["in_adam_v"][key], dtype=D)
     _, grads = O.train_step(cfg, params, state, x, x, eps,
-                            float(feeds["learning_rate"]), warm_up_weight=warm_up, **features)
+                            float(feeds["learning_rate"]), warm_up_weight=warm_up, **extra,
+                            **features)
     assert set(groups["grad"]) == set(state.m)
     for key, want in groups["grad"].items():
         got = grads[key] if grads[key] is not None else torch.zeros_like(params[key])
