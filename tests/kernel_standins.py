@@ -245,7 +245,52 @@ def _targets(t, M, G):
     return t[rows, :G].double()
 
 
+LOGIT_FLOOR = -87.33654475      # log(float32 tiny): sigmoid heads are clipped to [tiny, 1]
+
+
+def _safe_log_prob(name, x, heads):
+    """Count log-pmf from the head PRE-activations, as the kernels evaluate it (DESIGN §2,
+    "known deviations": the sigmoid pre-activation is the NB / ZI logit): identical to the
+    oracle's formulas wherever those are finite, and finite where sigmoid(a) rounds to one."""
+    logsig = torch.nn.functional.logsigmoid
+    if "poisson" in name:
+        ll = torch.clamp(heads["log_lambda"], -10.0, 10.0)
+        lp = x * ll - torch.lgamma(1.0 + x) - torch.exp(ll)
+    else:
+        a = torch.clamp(heads["p"], min=LOGIT_FLOOR)
+        r = torch.exp(torch.clamp(heads["log_r"], -10.0, 10.0))
+        lp = (torch.lgamma(x + r) - torch.lgamma(1.0 + x) - torch.lgamma(r)
+              + r * logsig(-a) + x * logsig(a))
+    if name.startswith("zero-inflated"):
+        b = torch.clamp(heads["pi"], min=LOGIT_FLOOR)
+        lp = torch.where(x > 0, logsig(-b) + lp, torch.logaddexp(logsig(b), logsig(-b) + lp))
+    return lp
+
+
+def _safe_moments(name, heads):
+    if "poisson" in name:
+        mean = var = torch.exp(torch.clamp(heads["log_lambda"], -10.0, 10.0))
+    else:
+        a = torch.clamp(heads["p"], min=LOGIT_FLOOR)
+        mean = torch.exp(torch.clamp(heads["log_r"], -10.0, 10.0)) * torch.exp(a)
+        var = mean * (1.0 + torch.exp(a))
+    if name.startswith("zero-inflated"):
+        keep = torch.sigmoid(-torch.clamp(heads["pi"], min=LOGIT_FLOOR))      # 1 - pi
+        zi_mean = keep * mean
+        return zi_mean, keep * (var + mean * mean) - zi_mean * zi_mean
+    return mean, var
+
+
+def _heads(kind, a, head_stride, M, G):
+    name = _KIND_NAMES[kind]
+    return name, {head: a[:M, h * head_stride:h * head_stride + G]
+                  for h, head in enumerate(LIKELIHOOD_HEADS[name])}
+
+
 def _rows_log_prob(kind, t, a, head_stride, M, G, k_max=0, count_sum=None):
+    if not k_max and count_sum is None:
+        name, heads = _heads(kind, a, head_stride, M, G)
+        return _safe_log_prob(name, _targets(t, M, G), heads).sum(dim=-1)
     name, theta = _theta(kind, a, head_stride, M, G)
     x = _targets(t, M, G)
     n = None
@@ -313,8 +358,8 @@ def likelihood_moments(kind, a, head_stride, B, G, RS, K, y, p_x_mean, p_x_stdde
                        stddev_of_mean):
     _log("likelihood_moments")
     assert K == 1 and y is None
-    name, theta = _theta(kind, a.double(), head_stride, RS * B, G)
-    m, v = O.likelihood_moments(name, theta)
+    name, heads = _heads(kind, a.double(), head_stride, RS * B, G)
+    m, v = _safe_moments(name, heads)
     _write_moments(m, v, B, G, RS, (p_x_mean, p_x_stddev, stddev_of_mean))
 
 
@@ -502,8 +547,8 @@ def likelihood_moments(kind, a, head_stride, B, G, RS, K, y, p_x_mean, p_x_stdde
         return _vae_likelihood_moments(kind, a, head_stride, B, G, RS, K, y, p_x_mean,
                                        p_x_stddev, stddev_of_mean)
     _log("likelihood_moments")
-    name, theta = _theta(kind, a.double(), head_stride, K * RS * B, G)
-    m, v = O.likelihood_moments(name, theta)
+    name, heads = _heads(kind, a.double(), head_stride, K * RS * B, G)
+    m, v = _safe_moments(name, heads)
     _write_mixture_moments(m, v, y, K, B, G, RS, (p_x_mean, p_x_stddev, stddev_of_mean))
 
 
@@ -522,3 +567,33 @@ def piecewise_moments(kind, k_max, a, head_stride, B, G, RS, p_x_mean, p_x_stdde
     m, v = O.likelihood_moments(name, theta)
     m, v = O.piecewise_moments(m, v, torch.log_softmax(logits, dim=-1), k_max)
     _write_mixture_moments(m, v, y, K_, B, G, RS, (p_x_mean, p_x_stddev, stddev_of_mean))
+
+
+# ---- minibatch assembly (a1) -------------------------------------------------------------------
+def csr_row_constants(indptr, values, out):
+    _log("csr_row_constants")
+    v = torch.lgamma(1.0 + values.double())
+    csum = torch.cat([torch.zeros(1, dtype=torch.float64), torch.cumsum(v, dim=0)])
+    out[:] = csum[indptr[1:].long()] - csum[indptr[:-1].long()]
+
+
+def gather_f32(src, rows, dst):
+    _log("gather_f32")
+    n = dst.numel()
+    dst.reshape(-1)[:] = src[:n] if rows is None else src[rows[:n].long()]
+
+
+def csr_densify(indptr, indices, values, rows, G, x, row_const=None, rebase=False, t16=None,
+                x16=None):
+    _log("csr_densify")
+    assert x is not None and t16 is None and x16 is None, "fp32 minibatch only"
+    B = x.shape[0]
+    base = int(indptr[0]) if rebase else 0
+    x[:, :G] = 0.0
+    for b in range(B):
+        r = b if rows is None else int(rows[b])
+        lo, hi = int(indptr[r]) - base, int(indptr[r + 1]) - base
+        x[b, indices[lo:hi].long()] = values[lo:hi].float()
+    _augment(x, G)
+    if row_const is not None:
+        row_const[:B] = torch.lgamma(1.0 + x[:, :G].double()).sum(dim=1)
