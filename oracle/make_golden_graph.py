@@ -134,6 +134,12 @@ CASES = [
      dict(scale={"POSTERIOR": 0.3})),
     ("vae_nb_sampled_kl_train", "VAE", dict(reconstruction_distribution="negative binomial",
                                              analytical_kl_term=False), dict(R=2, S=2)),
+    ("vae_nb_sampled_kl_eval_deterministic", "VAE",
+     dict(reconstruction_distribution="negative binomial", analytical_kl_term=False),
+     dict(is_training=False, use_deterministic_z=True)),
+    ("vae_nb_sampled_kl_eval_iw", "VAE",
+     dict(reconstruction_distribution="negative binomial", analytical_kl_term=False,
+          latent_distribution="unit-variance gaussian"), dict(is_training=False, R=3, S=2)),
     ("vae_nb_unit_variance_train", "VAE", dict(reconstruction_distribution="negative binomial",
                                                 latent_distribution="unit-variance gaussian"),
      dict()),

@@ -75,6 +75,13 @@ def test_vae_engine_evaluation_host_logic(engine_on_cpu, name):
     assert "adam_clip_step" not in engine_on_cpu
 
 
+@pytest.mark.parametrize("name", ["vae_nb_sampled_kl_eval_deterministic",
+                                  "vae_nb_sampled_kl_eval_iw"])
+def test_vae_engine_sampled_kl_evaluation_host_logic(engine_on_cpu, name):
+    Z.test_vae_sampled_kl_evaluation_matches_reference_graph(name)
+    assert "gaussian_sampled_kl" in engine_on_cpu and "vae_bound" not in engine_on_cpu
+
+
 @pytest.mark.parametrize("name", Z.GMVAE_TRAIN)
 def test_gmvae_engine_training_step_host_logic(engine_on_cpu, name):
     Z.test_gmvae_training_step_matches_reference_graph(name)

@@ -286,6 +286,12 @@ def test_vae_sampled_kl_training_step_matches_reference_graph(name):
     test_vae_training_step_matches_reference_graph(name)
 
 
+@pytest.mark.parametrize("name", ["vae_nb_sampled_kl_eval_deterministic",
+                                  "vae_nb_sampled_kl_eval_iw"])
+def test_vae_sampled_kl_evaluation_matches_reference_graph(name):
+    test_vae_evaluation_matches_reference_graph(name)
+
+
 def test_dropout_kernels_match_their_cpu_restatement():
     """scvae_dropout_fwd / scvae_dropout_bwd against tests/kernel_standins.py (whose versions
     carry the engine through the reference-graph dropout case on the CPU)."""
