@@ -242,6 +242,14 @@ int scvae_constrained_poisson_moments(const float *a, int64_t lda, const float *
                                       const float *count_sum, int B, int G, int RS,
                                       float *p_x_mean, float *p_x_stddev, float *stddev_of_mean,
                                       int64_t ldo, void *stream);
+/* GMVAE form (GMVAE:3170-3176, :3312-3386): a has K*RS*B rows ordered (k, sample, cell), lse one
+ * entry per row, y (B, ldy) = q(y|x); moments marginalised over the clusters as in
+ * scvae_likelihood_moments. */
+int scvae_constrained_poisson_mixture_moments(const float *a, int64_t lda, const float *lse,
+                                              const float *count_sum, int B, int G, int RS, int K,
+                                              const float *y, int64_t ldy, float *p_x_mean,
+                                              float *p_x_stddev, float *stddev_of_mean,
+                                              int64_t ldo, void *stream);
 
 /* ---- a4 + a5 fused: likelihood heads without the (cells x P*genes) round trip ----------------
  * One kernel computes a = d W^T (tcgen05, fp16 operands), log p(t | a) summed over genes, its

@@ -181,6 +181,12 @@ CASES = [
     ("gmvae_nb_bc_count_sum_train", "GMVAE",
      dict(reconstruction_distribution="negative binomial", number_of_latent_clusters=2,
           batch_correction=True, number_of_batches=2, count_sum=True), dict()),
+    ("gmvae_constrained_poisson_train", "GMVAE",
+     dict(reconstruction_distribution="constrained poisson", number_of_latent_clusters=3),
+     dict(R=1, S=2)),
+    ("gmvae_constrained_poisson_eval", "GMVAE",
+     dict(reconstruction_distribution="constrained poisson", number_of_latent_clusters=3),
+     dict(is_training=False, R=2, S=1)),
     ("gmvae_nb_no_bn_eval", "GMVAE", dict(reconstruction_distribution="negative binomial",
                                            number_of_latent_clusters=3,
                                            minibatch_normalisation=False),

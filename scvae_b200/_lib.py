@@ -82,6 +82,9 @@ SIGNATURES = {
                                         c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "scvae_constrained_poisson": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr,
                                           c_ptr, c_f32, c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
+    "scvae_constrained_poisson_mixture_moments": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_int, c_int,
+                                                          c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr,
+                                                          c_ptr, c_i64, c_ptr]),
     "scvae_constrained_poisson_moments": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr,
                                                   c_ptr, c_ptr, c_i64, c_ptr]),
     "scvae_vae_bound": (c_int, [c_ptr, c_ptr, c_int, c_int, c_int, c_f32, c_ptr, c_ptr, c_ptr]),

@@ -107,6 +107,42 @@ __global__ void constrained_poisson_moments_kernel(const float *__restrict__ a, 
     if (stddev_of_mean) stddev_of_mean[o] = sqrtf(dev * inv);
 }
 
+// The same moments marginalised over the K clusters of the GMVAE (GMVAE:3312-3386, with the
+// y-weighted per-cluster mean of quirk Q7): rows ordered (k, sample, cell), y = q(y|x) (B, ldy).
+__global__ void constrained_poisson_mixture_moments_kernel(
+    const float *__restrict__ a, int64_t lda, const float *__restrict__ lse,
+    const float *__restrict__ count_sum, int B, int G, int RS, int K, const float *__restrict__ y,
+    int64_t ldy, float *__restrict__ p_x_mean, float *__restrict__ p_x_stddev,
+    float *__restrict__ stddev_of_mean, int64_t ldo) {
+    const int g = blockIdx.y * blockDim.x + threadIdx.x;
+    const int b = blockIdx.x;
+    if (g >= G) return;
+    const float N = count_sum[b], inv = 1.f / (float)RS;
+    float mean_total = 0.f, mean_of_var = 0.f, var_of_mean = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const float w = y[(int64_t)b * ldy + k];
+        float ms = 0.f;
+        for (int s = 0; s < RS; ++s) {
+            const int64_t m = ((int64_t)k * RS + s) * B + b;
+            ms += N * __expf(fmaxf(a[m * lda + g] - lse[m], kLogTiny));
+        }
+        const float c = w * ms * inv;          // y-weighted mean of E[x|z_k] over the samples
+        float dev = 0.f;
+        for (int s = 0; s < RS; ++s) {
+            const int64_t m = ((int64_t)k * RS + s) * B + b;
+            const float r = N * __expf(fmaxf(a[m * lda + g] - lse[m], kLogTiny));
+            dev += (r - c) * (r - c);
+        }
+        mean_total += c;
+        mean_of_var += c;                      // Poisson: Var[x|z] = E[x|z]
+        var_of_mean += w * dev * inv;
+    }
+    const int64_t o = (int64_t)b * ldo + g;
+    if (p_x_mean) p_x_mean[o] = mean_total;
+    if (p_x_stddev) p_x_stddev[o] = sqrtf(mean_of_var + var_of_mean);
+    if (stddev_of_mean) stddev_of_mean[o] = sqrtf(var_of_mean);
+}
+
 }  // namespace scvae
 
 using namespace scvae;
@@ -138,5 +174,18 @@ extern "C" int scvae_constrained_poisson_moments(const float *a, int64_t lda, co
                                                                                p_x_mean, p_x_stddev,
                                                                                stddev_of_mean, ldo);
     SCVAE_CHECK_LAUNCH("constrained_poisson_moments");
+    return 0;
+}
+
+extern "C" int scvae_constrained_poisson_mixture_moments(
+    const float *a, int64_t lda, const float *lse, const float *count_sum, int B, int G, int RS,
+    int K, const float *y, int64_t ldy, float *p_x_mean, float *p_x_stddev, float *stddev_of_mean,
+    int64_t ldo, void *stream) {
+    SCVAE_CHECK_ARG(a && lse && count_sum && y && B > 0 && G > 0 && RS > 0 && K > 0 && ldy >= K,
+                    "constrained_poisson_mixture_moments: bad arguments");
+    dim3 grid(B, (G + 255) / 256);
+    constrained_poisson_mixture_moments_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        a, lda, lse, count_sum, B, G, RS, K, y, ldy, p_x_mean, p_x_stddev, stddev_of_mean, ldo);
+    SCVAE_CHECK_LAUNCH("constrained_poisson_mixture_moments");
     return 0;
 }

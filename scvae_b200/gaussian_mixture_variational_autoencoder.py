@@ -186,6 +186,8 @@ class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
                 K.gather_f32(data.batch_index, idx, plan.batch_index)
             if engine.count_sum_feature:
                 K.gather_f32(data.count_sum_feature, idx, plan.count_sum)
+            if engine.constrained:
+                K.gather_f32(data.count_sum_parameter, idx, plan.count_sum_parameter)
             K.fill_normal(plan.eps, seed, b)
             engine.forward(plan, False, R, S, 1.0)
             log[b].copy_(plan.bound)

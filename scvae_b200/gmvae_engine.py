@@ -34,8 +34,6 @@ class GMVAEEngine(VAEEngine):
         if reconstruction_distribution not in K.LIKELIHOOD_KINDS:
             raise ValueError("reconstruction distribution `{}` is not supported by the "
                              "B200 hot path".format(reconstruction_distribution))
-        if reconstruction_distribution == "constrained poisson":
-            raise ValueError("the constrained Poisson is wired into the VAE engine only")
         if prior_probabilities_method not in ("uniform", "learn", "custom"):
             raise ValueError("unknown prior probabilities method `{}`".format(
                 prior_probabilities_method))
@@ -68,7 +66,9 @@ class GMVAEEngine(VAEEngine):
         self.n_extra = self.number_of_batches + (1 if self.count_sum_feature else 0)
         self.Zp = round4(int(latent_size) + 1 + self.n_extra)
         self.lfm_inference = self.lfm_generative = False
-        self.constrained = False
+        # constrained Poisson (rate = N softmax_g(a), N = the cell's count sum fed as
+        # count_sum_parameter, GMVAE:419-429, :3170-3176): its own row kernel, never the fused heads
+        self.constrained = self.kind == K.CONSTRAINED_POISSON
         # piecewise-categorical likelihood (`-k`, head P_K GMVAE:3192-3218): k_max + 1 class-logit
         # head blocks behind the P heads; its own row kernel, never the fused heads
         self.k_max = int(number_of_reconstruction_classes or 0)
@@ -318,6 +318,11 @@ class GMVAEEngine(VAEEngine):
         p.count_sum = zeros(B) if self.count_sum_feature else None
         p.klz = zeros(M)
         p.kl_elem = None
+        # constrained Poisson: N of the cells, row log-sum-exps of all K*RS*B rows (each decoder
+        # chunk writes its slice through the view p.lse)
+        p.count_sum_parameter = zeros(B) if self.constrained else None
+        p.lse_all = zeros(M) if self.constrained else None
+        p.lse = None
         p.go, p.coef, p.logp = zeros(M), zeros(M), zeros(M)
         # decoder chunk buffers
         p.decY = [zeros(Mc, round4(l.n_out)) for l in self.dec]
@@ -449,6 +454,8 @@ class GMVAEEngine(VAEEngine):
         for c0 in range(0, Kc, p.chunk):
             kc = min(p.chunk, Kc - c0)
             r0, rows = c0 * rows_per_k, kc * rows_per_k
+            if self.constrained:
+                p.lse = p.lse_all[r0:r0 + rows]
             d = p.Z[r0:r0 + rows]
             for j, l in enumerate(self.dec):
                 self._gemm(p, K.GEMM_NT, rows, l.n_out, l.k_in, d, l.w, p.decY[j][:rows])
@@ -590,6 +597,10 @@ class GMVAEEngine(VAEEngine):
         if self.k_max:
             K.piecewise_moments(self.kind, self.k_max, p.A, self.Gn, p.B, self.G, p.RS, *outs,
                                 K_=self.K, y=p.y)
+            return [o[:, :self.G] for o in outs]
+        if self.constrained:
+            K.constrained_poisson_mixture_moments(p.A, p.lse_all, p.count_sum_parameter, p.B,
+                                                  self.G, p.RS, self.K, p.y, *outs)
             return [o[:, :self.G] for o in outs]
         K.likelihood_moments(self.kind, p.A, self.Gn, p.B, self.G, p.RS, self.K, p.y, *outs)
         return [o[:, :self.G] for o in outs]

@@ -293,6 +293,16 @@ def constrained_poisson_moments(a, lse, count_sum, B, G, RS, p_x_mean, p_x_stdde
                "constrained_poisson_moments")
 
 
+def constrained_poisson_mixture_moments(a, lse, count_sum, B, G, RS, K_, y, p_x_mean, p_x_stddev,
+                                        stddev_of_mean):
+    """GMVAE: the constrained-Poisson moments marginalised over the K clusters."""
+    lib = _lib.load()
+    _lib.check(lib.scvae_constrained_poisson_mixture_moments(
+        _p(a), _ld(a), _p(lse), _p(count_sum), B, G, RS, K_, _p(y), _ld(y), _p(p_x_mean),
+        _p(p_x_stddev), _p(stddev_of_mean), _ld(p_x_mean), _stream()),
+        "constrained_poisson_mixture_moments")
+
+
 def likelihood_fwd(kind, t, a, head_stride, M, G, logp, row_const=None):
     _f32(t, a, logp)
     lib = _lib.load()

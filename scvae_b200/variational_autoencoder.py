@@ -147,10 +147,10 @@ class VariationalAutoencoder:
                 or self.generative_architecture not in ("MLP", "LFM"):
             raise ValueError("The inference and generative architectures can only be a neural "
                              "network (MLP) or a linear factor model (LFM).")
-        if self.use_count_sum_as_parameter and (
-                self.type != "VAE" or self.reconstruction_distribution_name != "constrained poisson"):
-            problems.append("count-sum-parameterised likelihoods other than the VAE's "
-                            "constrained Poisson")
+        if self.use_count_sum_as_parameter \
+                and self.reconstruction_distribution_name != "constrained poisson":
+            problems.append("count-sum-parameterised likelihoods other than the constrained "
+                            "Poisson")
         if self.dropout_parts and self.type != "VAE":
             problems.append("dropout for the GMVAE")
         if self.parameterise_latent_posterior:

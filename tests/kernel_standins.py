@@ -597,3 +597,12 @@ def csr_densify(indptr, indices, values, rows, G, x, row_const=None, rebase=Fals
     _augment(x, G)
     if row_const is not None:
         row_const[:B] = torch.lgamma(1.0 + x[:, :G].double()).sum(dim=1)
+
+
+def constrained_poisson_mixture_moments(a, lse, count_sum, B, G, RS, K_, y, p_x_mean, p_x_stddev,
+                                        stddev_of_mean):
+    _log("constrained_poisson_mixture_moments")
+    rows = K_ * RS * B
+    rate = count_sum.double()[torch.arange(rows) % B].reshape(-1, 1) * torch.exp(torch.clamp(
+        a[:rows, :G].double() - lse[:rows].double().reshape(-1, 1), min=math.log(O.TINY)))
+    _write_mixture_moments(rate, rate, y, K_, B, G, RS, (p_x_mean, p_x_stddev, stddev_of_mean))

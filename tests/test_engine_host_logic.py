@@ -94,6 +94,12 @@ def test_gmvae_engine_evaluation_host_logic(engine_on_cpu, name):
     assert "adam_clip_step" not in engine_on_cpu
 
 
+def test_gmvae_engine_constrained_poisson_host_logic(engine_on_cpu):
+    Z.test_gmvae_constrained_poisson_matches_reference_graph()
+    assert "constrained_poisson_mixture_moments" in engine_on_cpu
+    assert "likelihood_fwd" not in engine_on_cpu and "likelihood_bwd" not in engine_on_cpu
+
+
 def test_product_kernels_module_is_untouched_outside_the_fixture():
     import scvae_b200.engine as E
     import scvae_b200.gmvae_engine as GE

@@ -44,10 +44,9 @@ def test_option_validation_mirrors_the_scope():
         GaussianMixtureVariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
                                               number_of_latent_clusters=3,
                                               dropout_keep_probabilities=[0.9])
-    with pytest.raises(NotImplementedError):
-        GaussianMixtureVariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
-                                              number_of_latent_clusters=3,
-                                              reconstruction_distribution="constrained poisson")
+    GaussianMixtureVariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
+                                          number_of_latent_clusters=3,
+                                          reconstruction_distribution="constrained poisson")
     with pytest.raises(NotImplementedError):
         VariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
                                reconstruction_distribution="gamma")

@@ -40,6 +40,7 @@ PRELUDE = r"""
 struct Dim3 { int x, y, z; };
 static Dim3 blockIdx, threadIdx, blockDim;
 constexpr int kRowsPerBlock = 4;
+constexpr float kLogTiny = -87.33654475f;
 // reductions across threads: pass 0 records, pass 1 answers
 static int g_pass = 0;
 static std::map<long long, std::vector<float>> g_table;   // (block, unit, call) -> contributions
@@ -102,6 +103,13 @@ void emu_sampled_kl_bwd(const float *ph, int64_t ldph, int B, int L, int RS, con
         gaussian_sampled_kl_bwd_kernel(ph, ldph, B, L, RS, eps, uv, dz, lddz, go, weight, coef,
                                        dph, lddph); }, 1);
 }
+void emu_mixture_moments(const float *a, int64_t lda, const float *lse, const float *count_sum,
+                         int B, int G, int RS, int K, const float *y, int64_t ldy, float *mean,
+                         float *stddev, float *stddev_of_mean, int64_t ldo) {
+    launch(B, (G + 255) / 256, 256, [&] {
+        constrained_poisson_mixture_moments_kernel(a, lda, lse, count_sum, B, G, RS, K, y, ldy,
+                                                   mean, stddev, stddev_of_mean, ldo); }, 1);
+}
 void emu_bound_rows(const float *logp, const float *kl_rows, int R, int S, int B, float weight,
                     float *out, float *go) {
     launch(1, 1, (S * B >= 1024) ? 1024 : 256, [&] {
@@ -132,7 +140,9 @@ def emulated(tmp_path_factory):
         _kernel(dropout, "dropout_fwd_kernel"), _kernel(dropout, "dropout_bwd_kernel"),
         _kernel(latent, "gaussian_sampled_kl_kernel"),
         _kernel(latent, "gaussian_sampled_kl_bwd_kernel"),
-        _kernel(latent, "vae_bound_rows_kernel")]) + ENTRY
+        _kernel(latent, "vae_bound_rows_kernel"),
+        _kernel(open(os.path.join(CSRC, "constrained_poisson.cu")).read(),
+                "constrained_poisson_mixture_moments_kernel")]) + ENTRY
     directory = tmp_path_factory.mktemp("emu")
     path = os.path.join(str(directory), "emu.cpp")
     with open(path, "w") as handle:
@@ -217,3 +227,24 @@ def test_sampled_kl_kernel_sources(emulated, R, S, unit_variance):
                              coef, B, L, RS, bool(unit_variance))
         assert numpy.abs(dph[:, :nL].numpy() - ref).max() <= 1e-5 * numpy.abs(ref).max()
         assert float(dph[:, nL:].abs().max()) == 0.0         # nothing written past the heads
+
+
+def test_constrained_poisson_mixture_moments_kernel_source(emulated):
+    gen = torch.Generator().manual_seed(5)
+    B, G, RS, K = 7, 300, 2, 3
+    rows = K * RS * B
+    a = torch.randn(rows, G + 4, generator=gen) * 2
+    lse = torch.logsumexp(a[:, :G].double(), dim=1).float()
+    count_sum = torch.rand(B, generator=gen) * 500 + 20
+    y = torch.softmax(torch.randn(B, K + 1, generator=gen), dim=-1)       # padded leading dimension
+    y[:, :K] = torch.softmax(torch.randn(B, K, generator=gen), dim=-1)
+    outs = [torch.zeros(B, G + 4) for _ in range(3)]
+    emulated.emu_mixture_moments(ptr(a), L64(G + 4), ptr(lse), ptr(count_sum), I(B), I(G), I(RS),
+                                 I(K), ptr(y), L64(K + 1), ptr(outs[0]), ptr(outs[1]),
+                                 ptr(outs[2]), L64(G + 4))
+    want = [torch.zeros(B, G) for _ in range(3)]
+    C.constrained_poisson_mixture_moments(a, lse, count_sum, B, G, RS, K,
+                                          y[:, :K].contiguous(), *want)
+    for got, ref in zip(outs, want):
+        assert torch.allclose(got[:, :G], ref, rtol=2e-5, atol=1e-6)
+        assert float(got[:, G:].abs().max()) == 0.0

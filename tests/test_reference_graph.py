@@ -86,6 +86,8 @@ def oracle_inputs(meta, groups):
         features["count_sum_feature"] = torch.as_tensor(feeds["count_sum_feature"], dtype=D)
     if meta["model"] == "GMVAE":
         eps = torch.stack(eps)                       # (K, R*S, B, L)
+        if kw["reconstruction_distribution"] == "constrained poisson":
+            features["count_sum"] = torch.as_tensor(feeds["count_sum"], dtype=D)
     else:
         eps = eps[0] if eps else None                # (R*S, B, L)
         if kw["reconstruction_distribution"] == "constrained poisson":

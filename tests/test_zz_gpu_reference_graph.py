@@ -192,6 +192,9 @@ def _gmvae(name):
             torch.tensor(feeds["batch_indices"]).cuda() if kw.get("batch_correction") else None,
             torch.tensor(feeds["count_sum_feature"], dtype=torch.float32).cuda()
             if kw.get("count_sum") else None)
+    if kw["reconstruction_distribution"] == "constrained poisson":
+        eng.set_batch_count_sum_parameter(
+            plan, torch.tensor(feeds["count_sum"], dtype=torch.float32).cuda())
     eps = numpy.stack([groups["in_eps"][str(k)] for k in range(K)])      # (K, R*S, B, L)
     plan.eps.copy_(torch.tensor(eps, dtype=torch.float32).reshape(-1, L))
     return meta, groups, eng, plan, R, S, L, K
@@ -403,3 +406,38 @@ def test_fill_normal_offsets_draw_from_disjoint_blocks():
     c = torch.zeros(n, device="cuda:0")
     K.fill_normal(c, 7, 0, step)
     assert torch.equal(b, c)            # host and device offsets add
+
+
+# The constrained Poisson for the GMVAE (GMVAE:419-429, :3170-3176): the VAE's row kernel over
+# the K cluster passes, moments marginalised over the clusters by
+# scvae_constrained_poisson_mixture_moments (written without a device as well).
+def test_gmvae_constrained_poisson_matches_reference_graph():
+    test_gmvae_training_step_matches_reference_graph("gmvae_constrained_poisson_train")
+    test_gmvae_evaluation_matches_reference_graph("gmvae_constrained_poisson_eval")
+
+
+def test_gmvae_train_evaluate_constrained_poisson(tmp_path):
+    """`-m GMVAE -r "constrained poisson"`: count sums reach the engine through the data set's
+    features in training, the per-epoch passes and `evaluate`."""
+    import scipy.sparse
+    from oracle import scvae_oracle as O
+    from scvae_b200 import model_utilities as MU
+    from scvae_b200.data_set import DataSet
+    from scvae_b200.gaussian_mixture_variational_autoencoder import (
+        GaussianMixtureVariationalAutoencoder)
+    x, labels = O.synthetic_counts(240, 64, n_types=3, seed=9, target_zero_fraction=0.8)
+    full = DataSet("toy", values=scipy.sparse.csr_matrix(numpy.minimum(x, 50.0)),
+                   labels=labels.astype(str))
+    training, validation, test = full.split()
+    model = GaussianMixtureVariationalAutoencoder(
+        feature_size=64, latent_size=4, hidden_sizes=[32], number_of_latent_clusters=3,
+        reconstruction_distribution="constrained poisson", log_directory=str(tmp_path), seed=1)
+    assert model.train(training, validation, number_of_epochs=3, minibatch_size=48,
+                       learning_rate=1e-2, shuffle_seed=0) == 0
+    curve = MU.load_learning_curves(model, "training")["lower_bound"]
+    assert len(curve) == 3 and numpy.isfinite(curve).all()
+    reconstructed = model.evaluate(test, minibatch_size=64, output_versions="reconstructed")
+    assert reconstructed.values.shape == (test.number_of_examples, 64)
+    assert numpy.isfinite(reconstructed.values).all()
+    # the constrained Poisson spreads each cell's count sum over the genes
+    assert numpy.allclose(reconstructed.values.sum(axis=1), test.count_sum.reshape(-1), rtol=1e-3)
