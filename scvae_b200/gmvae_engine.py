@@ -73,7 +73,7 @@ class GMVAEEngine(VAEEngine):
         # head blocks behind the P heads; its own row kernel, never the fused heads
         self.k_max = int(number_of_reconstruction_classes or 0)
         self.PT = self.P + (self.k_max + 1 if self.k_max else 0)
-        if self.k_max:
+        if self.k_max or self.constrained:
             self.fused_heads = False
         self.unit_variance = False
         self.nL = 2 * self.L
