@@ -134,8 +134,11 @@ class VAEEngine:
         if self.k_max and self.constrained:
             raise ValueError("piecewise-categorical likelihoods wrap the Poisson / NB family")
         self.PT = self.P + (self.k_max + 1 if self.k_max else 0)      # head blocks of width Gn
+        # (dropout: every head multiplies its own dropped copy of the decoder output, so neither
+        # the fused heads kernel -- one shared operand -- nor the 16-bit-only minibatch assembly
+        # that feeds it applies)
         self.fused_heads = (bool(fused_heads) and self.tensor_cores and not self.constrained
-                            and not self.k_max)
+                            and not self.k_max and not self.dropout_active)
         self.Gn = round4(self.G)
         self.Gp = aug(self.G)
         self.Gh = (self.G + 63) & ~63      # head stride of the fp16 buffers of the fused heads

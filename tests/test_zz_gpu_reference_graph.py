@@ -337,18 +337,19 @@ def test_vae_dropout_training_step_matches_reference_graph(name):
 def test_train_evaluate_unit_variance_gaussian_with_its_default_sampled_kl(tmp_path):
     """`-q "unit-variance gaussian"` end to end through the model class: the reference's default
     for it is the sampled KL (VAE:186-192), which used to be refused.  The ELBO must improve and
-    the per-neuron KL estimates must be logged."""
+    the per-neuron KL estimates must be logged.  (64 genes: on the device the training steps take
+    the default fused 16-bit heads path, whose decoder gradient feeds the sampled-KL backward.)"""
     import scipy.sparse
     from oracle import scvae_oracle as O
     from scvae_b200 import model_utilities as MU
     from scvae_b200.data_set import DataSet
     from scvae_b200.variational_autoencoder import VariationalAutoencoder
-    x, labels = O.synthetic_counts(300, 60, n_types=3, seed=3, target_zero_fraction=0.8)
+    x, labels = O.synthetic_counts(300, 64, n_types=3, seed=3, target_zero_fraction=0.8)
     full = DataSet("toy", values=scipy.sparse.csr_matrix(numpy.minimum(x, 50.0)),
                    labels=labels.astype(str))
     training, validation, test = full.split()
     model = VariationalAutoencoder(
-        feature_size=60, latent_size=4, hidden_sizes=[32],
+        feature_size=64, latent_size=4, hidden_sizes=[32],
         reconstruction_distribution="negative binomial",
         latent_distribution="unit-variance gaussian", log_directory=str(tmp_path), seed=1)
     assert model.analytical_kl_term is False
@@ -363,18 +364,19 @@ def test_train_evaluate_unit_variance_gaussian_with_its_default_sampled_kl(tmp_p
 
 def test_train_evaluate_with_dropout(tmp_path):
     """`--dropout-keep-probabilities 0.8 0.9 0.7` end to end through the model class (masks drawn
-    on the device inside the captured step, no dropout in the evaluation passes)."""
+    on the device inside the captured step, no dropout in the evaluation passes).  64 genes: the
+    shape would qualify for the fused 16-bit heads path, which a dropout model must not take."""
     import scipy.sparse
     from oracle import scvae_oracle as O
     from scvae_b200 import model_utilities as MU
     from scvae_b200.data_set import DataSet
     from scvae_b200.variational_autoencoder import VariationalAutoencoder
-    x, labels = O.synthetic_counts(300, 60, n_types=3, seed=3, target_zero_fraction=0.8)
+    x, labels = O.synthetic_counts(300, 64, n_types=3, seed=3, target_zero_fraction=0.8)
     full = DataSet("toy", values=scipy.sparse.csr_matrix(numpy.minimum(x, 50.0)),
                    labels=labels.astype(str))
     training, validation, test = full.split()
     model = VariationalAutoencoder(
-        feature_size=60, latent_size=4, hidden_sizes=[32, 16],
+        feature_size=64, latent_size=4, hidden_sizes=[32, 16],
         reconstruction_distribution="negative binomial",
         dropout_keep_probabilities=[0.8, 0.9, 0.7], log_directory=str(tmp_path), seed=1)
     assert "dropout_0.8_0.9_0.7" in model.name
