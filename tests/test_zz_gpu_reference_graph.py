@@ -410,6 +410,25 @@ def test_fill_normal_offsets_draw_from_disjoint_blocks():
     assert torch.equal(b, c)            # host and device offsets add
 
 
+def test_constrained_poisson_mixture_moments_kernel_matches_its_cpu_restatement():
+    import kernel_standins as C
+    from scvae_b200 import kernels as K
+    gen = torch.Generator().manual_seed(5)
+    B, G, RS, Kc = 7, 300, 2, 3
+    rows = Kc * RS * B
+    a = torch.randn(rows, G + 4, generator=gen) * 2
+    lse = torch.logsumexp(a[:, :G].double(), dim=1).float()
+    count_sum = torch.rand(B, generator=gen) * 500 + 20
+    y = torch.softmax(torch.randn(B, Kc, generator=gen), dim=-1)
+    want = [torch.zeros(B, G) for _ in range(3)]
+    C.constrained_poisson_mixture_moments(a, lse, count_sum, B, G, RS, Kc, y, *want)
+    got = [torch.zeros(B, G + 4, device="cuda:0") for _ in range(3)]
+    K.constrained_poisson_mixture_moments(a.cuda(), lse.cuda(), count_sum.cuda(), B, G, RS, Kc,
+                                          y.cuda(), *got)
+    for g, w in zip(got, want):
+        assert torch.allclose(g[:, :G].cpu(), w, rtol=5e-5, atol=1e-5)
+
+
 # The constrained Poisson for the GMVAE (GMVAE:419-429, :3170-3176): the VAE's row kernel over
 # the K cluster passes, moments marginalised over the clusters by
 # scvae_constrained_poisson_mixture_moments (written without a device as well).
@@ -443,22 +462,3 @@ def test_gmvae_train_evaluate_constrained_poisson(tmp_path):
     assert numpy.isfinite(reconstructed.values).all()
     # the constrained Poisson spreads each cell's count sum over the genes
     assert numpy.allclose(reconstructed.values.sum(axis=1), test.count_sum.reshape(-1), rtol=1e-3)
-
-
-def test_constrained_poisson_mixture_moments_kernel_matches_its_cpu_restatement():
-    import kernel_standins as C
-    from scvae_b200 import kernels as K
-    gen = torch.Generator().manual_seed(5)
-    B, G, RS, Kc = 7, 300, 2, 3
-    rows = Kc * RS * B
-    a = torch.randn(rows, G + 4, generator=gen) * 2
-    lse = torch.logsumexp(a[:, :G].double(), dim=1).float()
-    count_sum = torch.rand(B, generator=gen) * 500 + 20
-    y = torch.softmax(torch.randn(B, Kc, generator=gen), dim=-1)
-    want = [torch.zeros(B, G) for _ in range(3)]
-    C.constrained_poisson_mixture_moments(a, lse, count_sum, B, G, RS, Kc, y, *want)
-    got = [torch.zeros(B, G + 4, device="cuda:0") for _ in range(3)]
-    K.constrained_poisson_mixture_moments(a.cuda(), lse.cuda(), count_sum.cuda(), B, G, RS, Kc,
-                                          y.cuda(), *got)
-    for g, w in zip(got, want):
-        assert torch.allclose(g[:, :G].cpu(), w, rtol=5e-5, atol=1e-5)
