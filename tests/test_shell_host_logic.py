@@ -87,3 +87,10 @@ def test_gmvae_constrained_poisson_through_the_model_class_on_cpu(shell_on_cpu, 
     import test_zz_gpu_reference_graph as Z
     Z.test_gmvae_train_evaluate_constrained_poisson(tmp_path)
     assert "constrained_poisson_mixture_moments" in shell_on_cpu
+
+
+def test_cli_train_and_evaluate_on_tsv_on_cpu(shell_on_cpu, tmp_path):
+    """BASELINE configs[0] in miniature (TSV -> `scvae train` -> `scvae evaluate`) through the
+    command-line front end."""
+    G.test_cli_train_and_evaluate_on_tsv(tmp_path)
+    assert "adam_clip_step" in shell_on_cpu
