@@ -76,6 +76,7 @@ class _State:
         self.generator = torch.Generator().manual_seed(seed)
         self.sample_calls = []
         self.batch_statistics = defaultdict(list)
+        self.dropout_visits = {}
 
 
 STATE = _State()
@@ -464,6 +465,12 @@ def dropout(inputs, keep_prob=0.5, is_training=True, **_):
     if not bool(is_training):
         return inputs
     site = _scope_path()
+    # a scope visited again (the GMVAE builds its layers once per cluster with reuse=True) is a
+    # NEW dropout op with its own mask in TensorFlow: key the later visits `site#1`, `site#2`, ...
+    visit = STATE.dropout_visits.get(site, 0)
+    STATE.dropout_visits[site] = visit + 1
+    if visit:
+        site = "{}#{}".format(site, visit)
     if site in STATE.dropout_masks:
         mask = _t(STATE.dropout_masks[site], STATE.dtype)
     else:
