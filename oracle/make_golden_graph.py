@@ -181,6 +181,11 @@ CASES = [
     ("gmvae_nb_bc_count_sum_train", "GMVAE",
      dict(reconstruction_distribution="negative binomial", number_of_latent_clusters=2,
           batch_correction=True, number_of_batches=2, count_sum=True), dict()),
+    # every build of a shared layer is a dropout op of its own (one mask per cluster), and the
+    # GMVAE takes a fourth keep probability for the one-hot input of the p(z|y) heads
+    ("gmvae_nb_dropout_train", "GMVAE",
+     dict(reconstruction_distribution="negative binomial", number_of_latent_clusters=3,
+          hidden_sizes=[8, 5], dropout_keep_probabilities=[0.8, 0.9, 0.7, 0.6]), dict(R=1, S=2)),
     ("gmvae_constrained_poisson_train", "GMVAE",
      dict(reconstruction_distribution="constrained poisson", number_of_latent_clusters=3),
      dict(R=1, S=2)),

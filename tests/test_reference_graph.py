@@ -60,7 +60,8 @@ def oracle_config(meta):
             prior_probabilities_method=kw.get("prior_probabilities_method", "uniform"),
             prior_probabilities=kw.get("prior_probabilities"),
             proportion_of_free_nats_for_y_kl_divergence=kw.get(
-                "proportion_of_free_nats_for_y_kl_divergence", 0.0), **common)
+                "proportion_of_free_nats_for_y_kl_divergence", 0.0),
+            dropout_keep_probabilities=kw.get("dropout_keep_probabilities"), **common)
     return O.VAEConfig(
         latent_distribution=kw.get("latent_distribution", "gaussian"),
         # VAE:186-192: analytic KL by default only for the plain gaussian latent distribution
@@ -88,6 +89,9 @@ def oracle_inputs(meta, groups):
         eps = torch.stack(eps)                       # (K, R*S, B, L)
         if kw["reconstruction_distribution"] == "constrained poisson":
             features["count_sum"] = torch.as_tensor(feeds["count_sum"], dtype=D)
+        if "in_dropout" in groups:
+            features["dropout"] = {"masks": {site: torch.as_tensor(m, dtype=D)
+                                             for site, m in groups["in_dropout"].items()}}
     else:
         eps = eps[0] if eps else None                # (R*S, B, L)
         if kw["reconstruction_distribution"] == "constrained poisson":
@@ -185,6 +189,27 @@ def test_reference_sample_and_update_order():
     meta, _ = load_case("vae_nb_dropout_train")
     assert meta["dropout_sites"] == ["ENCODER/1", "POSTERIOR/MU", "POSTERIOR/LOG_SIGMA",
                                      "DECODER/1", "X_TILDE/P", "X_TILDE/LOG_R"]
+    # GMVAE: every build of a shared layer (one per cluster) is a dropout op of its own, the
+    # one-hot input of the p(z|y) heads is dropped too (fourth keep probability)
+    meta, groups = load_case("gmvae_nb_dropout_train")
+    K, B, G = 3, meta["B"], meta["G"]
+    sites = meta["dropout_sites"]
+    assert sites[:3] == ["Y/CATEGORICAL/ENCODER/LAYER_1", "Y/CATEGORICAL/ENCODER/LAYER_2",
+                         "Y/CATEGORICAL/LOGITS"]
+    per_cluster = ["Z/Q/ENCODER/LAYER_1", "Z/Q/ENCODER/LAYER_2", "Z/Q/SOFTPLUS_GAUSSIAN/MEAN",
+                   "Z/Q/SOFTPLUS_GAUSSIAN/SOFTPLUS_SCALE", "Z/P/SOFTPLUS_GAUSSIAN/MEAN",
+                   "Z/P/SOFTPLUS_GAUSSIAN/SOFTPLUS_SCALE"]
+    decoder = ["X/DECODER/LAYER_1", "X/DECODER/LAYER_2", "X/DISTRIBUTION/P",
+               "X/DISTRIBUTION/LOG_R"]
+    expected = list(sites[:3])
+    for group in (per_cluster, decoder):
+        for k in range(K):
+            expected += [s if k == 0 else "{}#{}".format(s, k) for s in group]
+    assert sites == expected and len(sites) == 3 + K * 10
+    masks = groups["in_dropout"]
+    assert masks["Z/Q/ENCODER/LAYER_1#2"].shape == (B, G + K)          # [x, e_k] together
+    assert masks["Z/P/SOFTPLUS_GAUSSIAN/MEAN#1"].shape == (1, K)         # the one-hot y itself
+    assert masks["X/DECODER/LAYER_1"].shape == (meta["R"] * meta["S"] * B, 3)
 
 
 def test_standin_primitives_match_scipy():
