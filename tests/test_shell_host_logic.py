@@ -41,6 +41,16 @@ def shell_on_cpu(monkeypatch):
     on_cpu(H.TrainLoop, use_graph=False)
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+
+    def on_host(factory):
+        def build(*args, **kwargs):
+            if str(kwargs.get("device", "")).startswith("cuda"):
+                kwargs["device"] = "cpu"
+            return factory(*args, **kwargs)
+        return build
+
+    monkeypatch.setattr(torch, "zeros", on_host(torch.zeros))       # scratch tensors of the tests
+    monkeypatch.setattr(torch, "tensor", on_host(torch.tensor))
     del kernel_standins.launches[:]
     return kernel_standins.launches
 
@@ -94,3 +104,10 @@ def test_cli_train_and_evaluate_on_tsv_on_cpu(shell_on_cpu, tmp_path):
     command-line front end."""
     G.test_cli_train_and_evaluate_on_tsv(tmp_path)
     assert "adam_clip_step" in shell_on_cpu
+
+
+def test_one_epoch_matches_oracle_on_cpu(shell_on_cpu, tmp_path):
+    """train() for one epoch == the oracle's steps on the same permutation and noise: minibatch
+    order, learning rate, warm-up weight and step counting of the training loop."""
+    G.test_one_epoch_matches_oracle(tmp_path)
+    assert shell_on_cpu.count("adam_clip_step") == 2
