@@ -140,3 +140,69 @@ def test_vae_engine_draws_its_own_dropout_masks(engine_on_cpu):
     del engine_on_cpu[:]
     eng.forward(plan, False, 1, 1, 1.0)
     assert "dropout_fwd" not in engine_on_cpu and "fill_normal" not in engine_on_cpu
+
+
+@pytest.mark.parametrize("seed,G,L,hidden,lik,R,S,B,extras,k_max", [
+    (0, 37, 5, [7, 5], "zero-inflated negative binomial", 1, 1, 9, dict(number_of_batches=3), 0),
+    (1, 41, 2, [6], "negative binomial", 2, 1, 5, dict(count_sum_feature=True), 2),
+    (2, 30, 3, [9, 4, 6], "poisson", 1, 3, 7, dict(number_of_batches=2, count_sum_feature=True), 0),
+    (3, 26, 4, [5], "zero-inflated poisson", 1, 1, 11, dict(generative_architecture="LFM"), 0),
+])
+def test_vae_engine_dropout_odd_shapes_against_the_oracle(engine_on_cpu, seed, G, L, hidden, lik,
+                                                          R, S, B, extras, k_max):
+    """Dropout wiring at sizes that are not multiples of four (padded leading dimensions, the
+    ones column between z and the decoder extras, head blocks behind the P_K block), against
+    the oracle with the same injected masks: ELBO, every gradient, the clip + Adam step."""
+    import numpy
+    from oracle import scvae_oracle as O
+    from scvae_b200.engine import VAEEngine
+    keep = [0.8, 0.9, 0.7]
+    cfg = O.VAEConfig(G, L, hidden, lik, "gaussian", R, S, True, True, kl_weight=0.9,
+                      number_of_reconstruction_classes=k_max, dropout_keep_probabilities=keep,
+                      **extras)
+    params = O.vae_init_params(cfg, seed=seed, dtype=torch.float64)
+    gen = torch.Generator().manual_seed(100 + seed)
+    for k in params:
+        if k.endswith("biases") or k.endswith("beta"):
+            params[k] = torch.randn(params[k].shape, generator=gen, dtype=torch.float64) * 0.1
+    x = torch.tensor(numpy.minimum(O.synthetic_counts(B, G, n_types=3, seed=seed)[0], 20.0),
+                     dtype=torch.float64)
+    eps = torch.randn(R * S, B, L, generator=gen, dtype=torch.float64)
+    feats = {}
+    if cfg.number_of_batches:
+        feats["batch_indices"] = torch.randint(0, cfg.number_of_batches, (B, 1), generator=gen)
+    if cfg.count_sum_feature:
+        feats["count_sum_feature"] = torch.rand(B, 1, generator=gen, dtype=torch.float64)
+    dropout = {"generator": torch.Generator().manual_seed(7 + seed)}      # masks drawn once ...
+    state = O.AdamState(params)
+    reference = {k: v.clone() for k, v in params.items()}
+    out, grads = O.train_step(cfg, reference, state, x, x, eps, 1e-3, warm_up_weight=0.6,
+                              dropout=dropout, **feats)
+    eng = VAEEngine(G, L, hidden, lik, "gaussian", True, kl_weight=0.9, tensor_cores=False,
+                    number_of_reconstruction_classes=k_max, dropout_keep_probabilities=keep,
+                    **extras)
+    eng.import_parameters(params)
+    plan = eng._plan(B, R * S)
+    eng.set_batch_dense(plan, x.float())
+    eng.set_batch_features(plan, feats.get("batch_indices"),
+                           feats["count_sum_feature"].float() if "count_sum_feature" in feats
+                           else None)
+    plan.eps.copy_(eps.reshape(R * S * B, L).float())
+    eng.inject_dropout_masks(plan, dropout["masks"])                      # ... and shared
+    bound = eng.train_step(plan, R, S, 1e-3, warm_up_weight=0.6)
+    assert sorted(plan.drop) == sorted(dropout["masks"])
+    assert abs(bound[0].item() - out["lower_bound"].item()) <= 5e-5 * abs(out["lower_bound"].item())
+    got = eng.export_gradients()
+    gmax = max(g.abs().max().item() for g in grads.values() if g is not None)
+    for key, g in grads.items():
+        g = g if g is not None else torch.zeros_like(params[key])
+        error = (got[key].double() - g).abs().max().item()
+        assert error <= 2e-4 * g.abs().max().item() + 1e-5 * gmax, (key, error)
+    new = eng.export_parameters()
+    for key, value in reference.items():
+        if "moving" in key:
+            continue
+        difference = (new[key].double() - value).abs()
+        if key in grads and grads[key] is not None:
+            difference = difference * (grads[key].abs() > 1e-3 * gmax)
+        assert difference.max().item() <= 1e-5 * max(value.abs().max().item(), 1.0), key
