@@ -206,3 +206,52 @@ def test_vae_engine_dropout_odd_shapes_against_the_oracle(engine_on_cpu, seed, G
         if key in grads and grads[key] is not None:
             difference = difference * (grads[key].abs() > 1e-3 * gmax)
         assert difference.max().item() <= 1e-5 * max(value.abs().max().item(), 1.0), key
+
+
+@pytest.mark.parametrize("head_buffer_bytes", [4 << 30, 20000])
+def test_gmvae_engine_constrained_poisson_chunked_against_the_oracle(engine_on_cpu,
+                                                                     head_buffer_bytes):
+    """Constrained Poisson through the cluster-chunked decoder (each chunk writes its slice of
+    the row log-sum-exps) at sizes that are not multiples of four."""
+    import numpy
+    from oracle import scvae_oracle as O
+    from scvae_b200.gmvae_engine import GMVAEEngine
+    G, L, Kc, hidden, B, R, S = 37, 3, 4, [7, 5], 9, 1, 2
+    cfg = O.GMVAEConfig(G, L, Kc, hidden, "constrained poisson", R, S, True, kl_weight=0.8)
+    params = O.gmvae_init_params(cfg, seed=3, dtype=torch.float64)
+    gen = torch.Generator().manual_seed(4)
+    for k in params:
+        if k.endswith("biases") or k.endswith("beta"):
+            params[k] = torch.randn(params[k].shape, generator=gen, dtype=torch.float64) * 0.2
+    x = torch.tensor(numpy.minimum(O.synthetic_counts(B, G, n_types=3, seed=5)[0], 40.0),
+                     dtype=torch.float64)
+    eps = torch.randn(Kc, R * S, B, L, generator=gen, dtype=torch.float64)
+    count_sum = x.sum(dim=1, keepdim=True)
+    state = O.AdamState(params)
+    reference = {k: v.clone() for k, v in params.items()}
+    out, grads = O.train_step(cfg, reference, state, x, x, eps, 1e-3, warm_up_weight=0.7,
+                              count_sum=count_sum)
+    eng = GMVAEEngine(G, L, Kc, hidden, "constrained poisson", True, 0.8, "uniform", None, 0.0,
+                      tensor_cores=False, head_buffer_bytes=head_buffer_bytes)
+    eng.import_parameters(params)
+    plan = eng._plan(B, R * S)
+    assert (plan.chunk < Kc) == (head_buffer_bytes < 1 << 20)
+    eng.set_batch_dense(plan, x.float())
+    eng.set_batch_count_sum_parameter(plan, count_sum.float())
+    plan.eps.copy_(eps.reshape(-1, L).float())
+    bound = eng.train_step(plan, R, S, 1e-3, warm_up_weight=0.7)
+    for i, key in enumerate(["lower_bound", "lower_bound_weighted", "reconstruction_error"]):
+        assert abs(bound[i].item() - out[key].item()) <= 5e-5 * abs(out[key].item()), key
+    # every row's log-sum-exp landed in its slot, whatever the chunking
+    a_rows = torch.logsumexp(plan.A[:plan.chunk * R * S * B, :G].double(), dim=1)
+    first = plan.chunk * R * S * B
+    last_chunk_rows = (Kc - (Kc - 1) // plan.chunk * plan.chunk) * R * S * B
+    assert torch.allclose(plan.lse_all[-last_chunk_rows:].double(), a_rows[:last_chunk_rows],
+                          rtol=1e-5) or plan.chunk == Kc
+    if plan.chunk == Kc:
+        assert torch.allclose(plan.lse_all.double(), a_rows[:first], rtol=1e-5)
+    got = eng.export_gradients()
+    gmax = max(g.abs().max().item() for g in grads.values())
+    for key, g in grads.items():
+        error = (got[key].double() - g).abs().max().item()
+        assert error <= 3e-4 * g.abs().max().item() + 1e-5 * gmax, (key, error)
