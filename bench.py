@@ -35,8 +35,8 @@ UNIT = "cells/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=int, default=68000)
     ap.add_argument("--genes", type=int, default=20000)
@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true",
+                    help="skip the untimed oracle check of one timed-path minibatch")
     return ap.parse_args()
 
 
@@ -110,12 +112,18 @@ class ClockSampler:
         self.index = index
         self.samples = []
         self.proc = None
+        self.marks = []
+
+    def mark(self):
+        """Bracket the timed region: samples between the first and the last mark are reported
+        (the sampler itself starts before the warm-up, so short regions still see samples)."""
+        self.marks.append(time.perf_counter())
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "20"],
+                 "--format=csv,noheader,nounits", "-lms", "5"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -124,7 +132,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -137,7 +145,15 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        picked = self.samples
+        if len(self.marks) >= 2:
+            # a sample describes the interval before it was printed: keep those printed inside the
+            # timed region or right behind it; fall back to the samples under load (warm-up
+            # included) when the region was shorter than one sampling period
+            lo, hi = self.marks[0], self.marks[-1] + 0.006
+            inside = [s for s in self.samples if lo <= s[0] <= hi]
+            picked = inside if inside else [s for s in self.samples if s[0] <= hi][-4:]
+        for _, s in picked:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 6:
                 continue
@@ -228,6 +244,46 @@ def workload_config(args, minibatch):
 
 
 # ---------------------------------------------------------------------------------------------
+# parity of the benchmarked path against the oracle (checker only, outside every timed region)
+# ---------------------------------------------------------------------------------------------
+def parity_check(args, eng, loop, data, csr, rows):
+    """Replays the captured training step (the object the timed region replays) on ``rows`` and
+    compares ELBO / reconstruction error / KL / per-cell log p / per-cell latent means with
+    ``oracle.train_step`` (fp64) on the same rows, variables and reparameterisation noise.
+    With N > 1 ranks the step includes the gradient exchange; the quantities compared are this
+    rank's forward results, which do not depend on it."""
+    from oracle import scvae_oracle as O
+    B, L = rows.numel(), args.latent
+    before = {k: v.double() for k, v in eng.export_parameters().items()}
+    loop.rows.copy_(rows)
+    bound = loop.step(data, 1e-4, 1.0)
+    torch.cuda.synchronize()
+    plan = loop.plan
+    bound = bound.cpu().numpy().astype(numpy.float64)
+    eps = plan.eps.cpu().double().reshape(1, B, L)
+    x = torch.from_numpy(csr[rows.cpu().numpy()].toarray()).double()
+    cfg = O.VAEConfig(args.genes, L, args.hidden, args.likelihood)
+    torch.set_num_threads(os.cpu_count() or 1)
+    out = O.vae_forward(cfg, before, x, x, eps, is_training=True)
+    names = ["lower_bound", "lower_bound_weighted", "reconstruction_error", "kl_divergence"]
+    rel = {n: abs(bound[i] - out[n].item()) / abs(out[n].item()) for i, n in enumerate(names)}
+    lp_ref = out["log_p_x_given_z"].reshape(-1)
+    lp_rel = ((plan.logp.cpu().double() - lp_ref).abs().max() / lp_ref.abs().max()).item()
+    mu_ref = out["q_z_mean"]
+    mu_rel = ((plan.PH[:, :L].cpu().double() - mu_ref).abs().max() / mu_ref.abs().max()).item()
+    tol = 1e-3
+    return {"checked": "one CUDA-graph replay of the timed training step vs oracle.vae_forward "
+                       "(fp64) on the same {} rows, variables and noise".format(B),
+            "elbo_gpu": bound[0], "elbo_oracle": out["lower_bound"].item(),
+            "rel_err": {"elbo": rel["lower_bound"], "enre": rel["reconstruction_error"],
+                        "kl": rel["kl_divergence"], "per_cell_log_p_max": lp_rel,
+                        "per_cell_latent_mean_max": mu_rel},
+            "tolerance": tol,
+            "pass": bool(max(rel.values()) <= tol and lp_rel <= tol and mu_rel <= tol),
+            "fused_16bit_path": bool(plan.fused_done)}
+
+
+# ---------------------------------------------------------------------------------------------
 # this repository's arm
 # ---------------------------------------------------------------------------------------------
 def _dbg(msg):
@@ -292,19 +348,21 @@ def run_b200(args):
     launches_per_step = lib.scvae_launch_count() - l0
     loop.use_graph = saved
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         step(i)
     sync_all()
     _dbg("warm-up done")
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
         step(args.warmup + i)
     e1.record()
     sync_all()
+    sampler.mark()
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = e0.elapsed_time(e1)
     t = torch.tensor([elapsed_ms], device=dev)
@@ -475,6 +533,18 @@ def run_b200(args):
                        "-> train step -> D2H of the bound (async to pinned memory, read by the "
                        "host one step later)"}
 
+    # ---- parity of the timed path (untimed): one more replay of the SAME captured step on the
+    # rows of the first timed minibatch, checked against the oracle on those rows / weights / noise
+    parity = None
+    if rank == 0 and not args.no_parity:
+        try:
+            parity = parity_check(args, eng, loop, data, csr, perm[args.warmup % n_batches * B:
+                                                                   (args.warmup % n_batches + 1) * B])
+        except Exception as exc:      # reported, never silently dropped
+            parity = {"error": repr(exc)}
+    if world > 1:
+        dist.barrier()
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sub = csr[:min(args.cells, 16384)]
@@ -492,7 +562,8 @@ def run_b200(args):
             "lower_bound_last_step": bound[0],
             "cuda_graph": bool(saved),
         }
-        line["config"]["gradient_exchange"] = exchange
+        line["gradient_exchange"] = exchange     # (not in `config`: both arms name one workload)
+        line["parity"] = parity
         print(json.dumps(line), flush=True)
     if world > 1:
         # CUDA graphs that captured NCCL kernels must die before the communicator does; guard

@@ -362,7 +362,7 @@ int scvae_gmvae_row_coefficients(const float *y, int K, int RS, int B, float wei
  * outputs (sample means, not y-weighted). */
 int scvae_gmvae_bound(const float *y, const float *logy, const float *logp, const float *klz,
                       const float *log_py, int K, int RS, int B, float weight,
-                      float free_nats_threshold, int uniform_prior, float *out, float *dlogits,
+                      float free_nats_proportion, int uniform_prior, float *out, float *dlogits,
                       float *dpy_logits, float *ll_mean, float *klz_mean, void *stream);
 /* z_mean[b] = sum_k y[b,k] mean_k[b]  (GMVAE:2896-2899); z_mean (B, L) contiguous. */
 int scvae_gmvae_z_mean(const float *qh, int64_t ldq, const float *y, int K, int B, int L,

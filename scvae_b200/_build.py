@@ -57,10 +57,24 @@ def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into ``libscvae_b200.so``; returns its path."""
     if not force and not _stale():
         return LIB_PATH
+    # one builder at a time: under torchrun every rank may find the library stale at once
+    import fcntl
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():      # another process built it while we waited
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libscvae_b200.so")
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", "obj-{}".format(os.getpid()))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
@@ -76,7 +90,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed for {}:\n{}".format(src, out))
         if verbose and out:
             print(out)
-    tmp = LIB_PATH + ".tmp"
+    tmp = "{}.{}.tmp".format(LIB_PATH, os.getpid())
     cmd = [nvcc, "-shared", "-cudart", "static", "-o", tmp] + objs
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
@@ -84,6 +98,7 @@ def build(force=False, verbose=False):
     os.replace(tmp, LIB_PATH)
     with open(HASH_PATH, "w") as fh:
         fh.write(source_hash())
+    shutil.rmtree(objdir, ignore_errors=True)
     return LIB_PATH
 
 

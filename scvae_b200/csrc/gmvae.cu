@@ -196,7 +196,7 @@ gmvae_latent_bwd_p_kernel(const float *__restrict__ qh, int64_t ldq, const float
 __global__ void __launch_bounds__(256)
 gmvae_bound_kernel(const float *__restrict__ y, const float *__restrict__ logy, const float *__restrict__ logp,
                    const float *__restrict__ klz, const float *__restrict__ log_py, int K, int RS, int B,
-                   float weight, float free_nats_threshold, int uniform_prior, float *__restrict__ out,
+                   float weight, float free_nats_proportion, int uniform_prior, float *__restrict__ out,
                    float *__restrict__ dlogits, float *__restrict__ dpy_logits, float *__restrict__ ll_mean,
                    float *__restrict__ klz_mean) {
     __shared__ float red[32];
@@ -226,6 +226,13 @@ gmvae_bound_kernel(const float *__restrict__ y, const float *__restrict__ logy, 
     const float re = block_sum(s_re, red) * inv_b;
     const float kz = block_sum(s_klz, red) * inv_b;
     const float ky = block_sum(s_kly, red) * inv_b;
+    // threshold = proportion * H[p(y)] (GMVAE:3260-3261), from the prior on the device: a learnt
+    // prior changes every step and the step is replayed from a CUDA graph
+    float free_nats_threshold = 0.f, prior_entropy = 0.f;
+    if (free_nats_proportion > 0.f) {
+        for (int k = 0; k < K; ++k) prior_entropy -= expf(log_py[k]) * log_py[k];
+        free_nats_threshold = free_nats_proportion * prior_entropy;
+    }
     const bool use_kly = !(free_nats_threshold > 0.f) || ky > free_nats_threshold;
     const float ky_mod = use_kly ? ky : free_nats_threshold;
     if (threadIdx.x == 0) {
@@ -262,7 +269,11 @@ gmvae_bound_kernel(const float *__restrict__ y, const float *__restrict__ logy, 
         for (int k = threadIdx.x; k < K; k += blockDim.x) {
             float ym = 0.f;
             for (int b = 0; b < B; ++b) ym += y[(int64_t)b * K + k];
-            dpy_logits[k] = wy * (expf(log_py[k]) - ym * inv_b);
+            float g = wy * (expf(log_py[k]) - ym * inv_b);
+            // below the threshold the loss holds weight * proportion * H[p(y)] instead of KL_y, and
+            // a learnt prior receives its gradient: dH / d logit_k = -p_k (log p_k + H)
+            if (s_use_kly == 0.f) g = -weight * free_nats_proportion * expf(log_py[k]) * (log_py[k] + prior_entropy);
+            dpy_logits[k] = g;
         }
     }
 }
@@ -368,12 +379,12 @@ extern "C" int scvae_gmvae_row_coefficients(const float *y, int K, int RS, int B
 
 extern "C" int scvae_gmvae_bound(const float *y, const float *logy, const float *logp, const float *klz,
                                  const float *log_py, int K, int RS, int B, float weight,
-                                 float free_nats_threshold, int uniform_prior, float *out, float *dlogits,
+                                 float free_nats_proportion, int uniform_prior, float *out, float *dlogits,
                                  float *dpy_logits, float *ll_mean, float *klz_mean, void *stream) {
     SCVAE_CHECK_ARG(y && logy && logp && klz && log_py && out && ll_mean && klz_mean,
                     "gmvae_bound: NULL pointer");
     gmvae_bound_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(y, logy, logp, klz, log_py, K, RS, B, weight,
-                                                            free_nats_threshold, uniform_prior, out, dlogits,
+                                                            free_nats_proportion, uniform_prior, out, dlogits,
                                                             dpy_logits, ll_mean, klz_mean);
     SCVAE_CHECK_LAUNCH("gmvae_bound");
     return 0;

@@ -179,6 +179,20 @@ def attach(engine, exchange=None):
     return engine
 
 
+def raise_if_exchange_failed(engine):
+    """Checked once per epoch, before the checkpoint: ``scvae_dp_reduce_adam`` bounds its flag
+    waits and records an expired one in its control block instead of hanging the GPU."""
+    peer = getattr(engine, "_peer", None)
+    if peer is None or not is_active():
+        return
+    failed = torch.tensor([1 if peer.timed_out() else 0], dtype=torch.int32, device=engine.device)
+    dist.all_reduce(failed, op=dist.ReduceOp.MAX)      # every rank raises, none is left waiting
+    if int(failed.item()):
+        raise RuntimeError("scvae_b200: the peer-memory gradient exchange timed out on at least "
+                           "one rank during this epoch (a rank stalled beyond the bounded flag "
+                           "wait); replicas may have diverged -- aborting before the checkpoint")
+
+
 def broadcast_parameters(engine):
     """Make replicas bit-identical at start (rank 0's parameters, optimiser slots and step)."""
     if not is_active():

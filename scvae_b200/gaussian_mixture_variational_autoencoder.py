@@ -308,6 +308,10 @@ class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
             sample_size = defaults["models"]["sample_size"]
         if minibatch_size is None:
             minibatch_size = defaults["models"]["minibatch_size"]
+        if self.batch_correction or self.use_count_sum_as_parameter or self.use_count_sum_as_feature:
+            # a free sample has no batch index / count sum to feed (as for the VAE, VAE:1639-1649)
+            raise NotImplementedError("Sampling with batch correction or count sums is not "
+                                      "implemented (as in the reference).")
         engine, _, _ = self._load_for_inference(run_id, use_early_stopping_model, use_best_model,
                                                 "sample from")
         L, G, Kc = self.latent_size, self.feature_size, self.number_of_latent_clusters
@@ -332,7 +336,12 @@ class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
             VAEEngine.decode(engine, plan, rows)       # decoder only, moving statistics, 1 group
             outs = [torch.empty(rows, engine.Gn, dtype=torch.float32, device=engine.device)
                     for _ in range(3)]
-            K.likelihood_moments(engine.kind, plan.A[:rows], engine.Gn, rows, G, 1, 1, None, *outs)
+            if engine.k_max:       # mean of the Categorised distribution (P_K class heads, CAT:210-247)
+                K.piecewise_moments(engine.kind, engine.k_max, plan.A[:rows], engine.Gn, rows, G, 1,
+                                    *outs)
+            else:
+                K.likelihood_moments(engine.kind, plan.A[:rows], engine.Gn, rows, G, 1, 1, None,
+                                     *outs)
             x[i:i + rows] = outs[0][:, :G].cpu().numpy()
         names = numpy.array(["example {}".format(i + 1) for i in range(sample_size)])
         y = numpy.eye(Kc, dtype=numpy.float32)[clusters]

@@ -491,11 +491,10 @@ class GMVAEEngine(VAEEngine):
                 self._likelihood(p, tgt, p.A[:rows], rows, rc, logp=p.logp[r0:r0 + rows])
             if getattr(p, "on_chunk", None) is not None:
                 p.on_chunk(c0, kc, rows)
-        thr = 0.0
-        if self.free_nats:
-            # threshold = proportion * H[p(y)] (GMVAE:3260-3261)
-            thr = self.free_nats * float(-(torch.exp(self.log_py) * self.log_py).sum())
-        K.gmvae_bound(p.y, p.logy, p.logp, p.klz, self.log_py, Kc, RS, B, weight, thr,
+        # free nats: the kernel forms threshold = proportion * H[p(y)] (GMVAE:3260-3261) from
+        # log_py on the device -- no host read inside a captured step, and a learnt prior's
+        # threshold follows the prior
+        K.gmvae_bound(p.y, p.logy, p.logp, p.klz, self.log_py, Kc, RS, B, weight, self.free_nats,
                       self.prior_method == "uniform", p.bound,
                       p.dlogits_c if with_backward else None,
                       self.d_py_logits if (with_backward and self.prior_method == "learn") else None,

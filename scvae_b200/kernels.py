@@ -419,11 +419,11 @@ def gmvae_row_coefficients(y, K_, RS, B, weight, go, coef):
                                                 _stream()), "gmvae_row_coefficients")
 
 
-def gmvae_bound(y, logy, logp, klz, log_py, K_, RS, B, weight, free_nats_threshold, uniform_prior,
+def gmvae_bound(y, logy, logp, klz, log_py, K_, RS, B, weight, free_nats_proportion, uniform_prior,
                 out, dlogits, dpy_logits, ll_mean, klz_mean):
     lib = _lib.load()
     _lib.check(lib.scvae_gmvae_bound(_p(y), _p(logy), _p(logp), _p(klz), _p(log_py), K_, RS, B,
-                                     float(weight), float(free_nats_threshold), int(uniform_prior),
+                                     float(weight), float(free_nats_proportion), int(uniform_prior),
                                      _p(out), _p(dlogits), _p(dpy_logits), _p(ll_mean),
                                      _p(klz_mean), _stream()), "gmvae_bound")
 

@@ -202,7 +202,7 @@ def write_checkpoint(directory, epoch, payload, keep=1):
 def read_checkpoint(state):
     import torch
     return torch.load(state.model_checkpoint_path + CHECKPOINT_SUFFIX, map_location="cpu",
-                      weights_only=False)
+                      weights_only=True)      # plain tensors / str / int only: nothing executable
 
 
 def copy_model_directory(checkpoint_state, destination):

@@ -549,13 +549,18 @@ class VariationalAutoencoder:
                     if rows == 0:
                         continue
                 if rows not in loops:
-                    loops[rows] = TrainLoop(engine, rows, R, S, seed=noise_seed,
+                    # (independent reparameterisation noise per rank: the shards hold different cells)
+                    loops[rows] = TrainLoop(engine, rows, R, S, seed=noise_seed + 7919 * rank,
                                             use_graph=use_graph)
                 loop = loops[rows]
                 loop.rows.copy_(shuffled[i:i + rows])
                 bound = loop.step(data, learning_rate, warm_up_weight)
                 step_bounds[s, :bound.numel()].copy_(bound)
             bounds = step_bounds.cpu().numpy()
+            # a peer-memory exchange whose flag wait ran out (a rank stalled for seconds) has
+            # summed stale gradients: the replicas are no longer identical and nothing computed
+            # since may reach a checkpoint
+            D.raise_if_exchange_failed(engine)
             if numpy.isnan(bounds[:, 0]).any():
                 raise ArithmeticError("Aborting. The ELBO became indefinite during training.")
             epoch_duration = time() - epoch_time_start

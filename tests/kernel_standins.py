@@ -482,7 +482,7 @@ def gmvae_row_coefficients(y, K_, RS, B, weight, go, coef):
     coef[:K_ * RS * B] = weight * rows
 
 
-def gmvae_bound(y, logy, logp, klz, log_py, K_, RS, B, weight, free_nats_threshold, uniform_prior,
+def gmvae_bound(y, logy, logp, klz, log_py, K_, RS, B, weight, free_nats_proportion, uniform_prior,
                 out, dlogits, dpy_logits, ll_mean, klz_mean):
     _log("gmvae_bound")
     logits = logy.reshape(-1)[:B * K_].double().reshape(B, K_).detach().clone().requires_grad_(True)
@@ -500,8 +500,9 @@ def gmvae_bound(y, logy, logp, klz, log_py, K_, RS, B, weight, free_nats_thresho
         kl_y = (math.log(K_) + (q * lq).sum(dim=-1)).mean()
     else:
         kl_y = (q * (lq - lpy)).sum(dim=-1).mean()
-    if free_nats_threshold:
-        threshold = torch.tensor(float(free_nats_threshold), dtype=torch.float64)
+    if free_nats_proportion:
+        # H[p(y)] of the prior; differentiable for a learnt prior (GMVAE:3258-3261)
+        threshold = float(free_nats_proportion) * (-(torch.exp(lpy) * lpy).sum())
         kl_y_mod = torch.where(kl_y > threshold, kl_y, threshold)
     else:
         kl_y_mod = kl_y

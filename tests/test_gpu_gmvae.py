@@ -53,6 +53,7 @@ def test_gmvae_forward_backward_step(case, tensor_cores):
         assert plan.chunk < Kc
     w = 0.7
     tol = 5e-5 if not tensor_cores else 2e-3
+    etol = 5e-5 if not tensor_cores else 1e-3      # ELBO terms: the north-star bound
     state = O.AdamState(params)
     ref = {k: v.clone() for k, v in params.items()}
     out, grads = O.train_step(cfg, ref, state, x, x, eps, 1e-3, warm_up_weight=w)
@@ -62,7 +63,7 @@ def test_gmvae_forward_backward_step(case, tensor_cores):
     names = ["lower_bound", "lower_bound_weighted", "reconstruction_error", "kl_divergence_z",
              "kl_divergence_y"]
     for i, n in enumerate(names):
-        assert abs(bound[i] - out[n].item()) <= tol * abs(out[n].item()) + 1e-5, (n, bound[i], out[n].item())
+        assert abs(bound[i] - out[n].item()) <= etol * abs(out[n].item()) + 1e-5, (n, bound[i], out[n].item())
     assert (plan.logits[:, :Kc].cpu().double() - out["q_y_logits"]).abs().max().item() <= \
         tol * out["q_y_logits"].abs().max().item() + 1e-5
     lp_ref = out["log_p_x_given_z"].reshape(-1)
@@ -147,7 +148,7 @@ def test_gmvae_batch_correction_and_count_sum_feature(tensor_cores, B):
     bound = eng.train_step(plan, 1, 1, 1e-3).cpu().numpy()
     torch.cuda.synchronize()
     assert plan.fused_done == (tensor_cores and B % 128 == 0)
-    tol = 5e-5 if not tensor_cores else 2e-3
+    tol = 5e-5 if not tensor_cores else 1e-3
     for i, n in enumerate(["lower_bound", "lower_bound_weighted", "reconstruction_error"]):
         assert abs(bound[i] - out[n].item()) <= tol * abs(out[n].item()) + 1e-5, (n, bound[i], out[n].item())
     got = eng.export_gradients()

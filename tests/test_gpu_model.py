@@ -251,3 +251,25 @@ def test_gmvae_train_evaluate_with_batch_correction_and_count_sum(tmp_path):
     assert len(curve) == 2 and numpy.isfinite(curve).all()
     transformed, reconstructed, latent = model.evaluate(test, minibatch_size=64, output_versions="all")
     assert numpy.isfinite(reconstructed.values).all()
+
+
+@pytest.mark.parametrize("prior", ["uniform", "learn"])
+def test_gmvae_trains_with_free_nats_under_graph_capture(tmp_path, prior):
+    """Free nats for KL_y (GMVAE:3258-3261, :3391-3398) with the training step replayed from a
+    CUDA graph: the threshold proportion * H[p(y)] is formed on the device (no host read inside
+    the captured step) and follows a learnt prior from step to step."""
+    from scvae_b200.gaussian_mixture_variational_autoencoder import (
+        GaussianMixtureVariationalAutoencoder)
+    from scvae_b200 import model_utilities as MU
+    full = _data(n=240, g=40, seed=4)
+    training, validation, _ = full.split()
+    model = GaussianMixtureVariationalAutoencoder(
+        feature_size=40, latent_size=3, hidden_sizes=[24], number_of_latent_clusters=4,
+        reconstruction_distribution="negative binomial", prior_probabilities_method=prior,
+        proportion_of_free_nats_for_y_kl_divergence=0.8, log_directory=str(tmp_path), seed=2)
+    assert model.train(training, validation, number_of_epochs=3, minibatch_size=48,
+                       learning_rate=5e-3, shuffle_seed=0, use_cuda_graph=True) == 0
+    curves = MU.load_learning_curves(model, ["training", "validation"])
+    assert len(curves["training"]["lower_bound"]) == 3
+    assert numpy.isfinite(curves["training"]["lower_bound"]).all()
+    assert curves["training"]["lower_bound"][-1] > curves["training"]["lower_bound"][0]

@@ -67,7 +67,8 @@ def test_vae_forward_backward_step(case, tensor_cores):
     name, G, L, hidden, lik, R, S, B, bn, latent = case
     cfg, params, x, eps, eng, plan = _setup(case, tensor_cores)
     w = 0.6
-    tol = 5e-5 if not tensor_cores else 2e-3   # tf32 operands: 2^-10 truncation per product
+    tol = 5e-5 if not tensor_cores else 2e-3   # per-cell tensors; tf32 operands: 2^-10 truncation per product
+    etol = 5e-5 if not tensor_cores else 1e-3  # ELBO terms: the north-star bound on every path
     state = O.AdamState(params)
     ref_params = {k: v.clone() for k, v in params.items()}
     out, grads = O.train_step(cfg, ref_params, state, x, x, eps, 1e-3, warm_up_weight=w)
@@ -76,10 +77,10 @@ def test_vae_forward_backward_step(case, tensor_cores):
     torch.cuda.synchronize()
     bound = bound.cpu().numpy()
     # ELBO / reconstruction error / KL within 1e-3 relative (BASELINE north_star), much tighter here
-    assert abs(bound[0] - out["lower_bound"].item()) <= tol * abs(out["lower_bound"].item())
-    assert abs(bound[1] - out["lower_bound_weighted"].item()) <= tol * abs(out["lower_bound_weighted"].item())
-    assert abs(bound[2] - out["reconstruction_error"].item()) <= tol * abs(out["reconstruction_error"].item())
-    assert abs(bound[3] - out["kl_divergence"].item()) <= tol * abs(out["kl_divergence"].item()) + 1e-6
+    assert abs(bound[0] - out["lower_bound"].item()) <= etol * abs(out["lower_bound"].item())
+    assert abs(bound[1] - out["lower_bound_weighted"].item()) <= etol * abs(out["lower_bound_weighted"].item())
+    assert abs(bound[2] - out["reconstruction_error"].item()) <= etol * abs(out["reconstruction_error"].item())
+    assert abs(bound[3] - out["kl_divergence"].item()) <= etol * abs(out["kl_divergence"].item()) + 1e-6
     # per-cell latent means and log-likelihoods
     assert _rel(plan.PH[:, :L].cpu(), out["q_z_mean"]) <= tol
     assert _rel(plan.logp.cpu(), out["log_p_x_given_z"].reshape(-1)) <= tol
@@ -175,8 +176,8 @@ def test_vae_lean_evaluation_pass_matches_full_path(R, S, deterministic):
         results.append((plan.bound.cpu().numpy().copy(), plan.logp.cpu().numpy().copy()))
     (b0, lp0), (b1, lp1) = results
     assert plan.have_t16          # the lean pass really took the 16-bit / fused route
-    assert abs(b0[0] - b1[0]) <= 2e-3 * abs(b0[0])
-    assert abs(b0[2] - b1[2]) <= 2e-3 * abs(b0[2])
+    assert abs(b0[0] - b1[0]) <= 1e-3 * abs(b0[0])
+    assert abs(b0[2] - b1[2]) <= 1e-3 * abs(b0[2])
     m = B if deterministic else R * S * B
     assert numpy.abs(lp0[:m] - lp1[:m]).max() <= 3e-3 * numpy.abs(lp0[:m]).max()
 
@@ -286,7 +287,8 @@ def test_vae_decoder_extras_and_linear_factor_architectures(case, tensor_cores):
         # constrained Poisson, which has its own row kernel)
         assert plan.fused_done == (not constrained and not cfg.k_max)
     tol = 5e-5 if not tensor_cores else 2e-3
-    assert abs(bound[0] - out["lower_bound"].item()) <= tol * abs(out["lower_bound"].item())
+    etol = 5e-5 if not tensor_cores else 1e-3
+    assert abs(bound[0] - out["lower_bound"].item()) <= etol * abs(out["lower_bound"].item())
     assert _rel(plan.PH[:, :L].cpu(), out["q_z_mean"]) <= tol
     assert _rel(plan.logp.cpu(), out["log_p_x_given_z"].reshape(-1)) <= tol
     got = eng.export_gradients()

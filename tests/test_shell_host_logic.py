@@ -111,3 +111,9 @@ def test_one_epoch_matches_oracle_on_cpu(shell_on_cpu, tmp_path):
     order, learning rate, warm-up weight and step counting of the training loop."""
     G.test_one_epoch_matches_oracle(tmp_path)
     assert shell_on_cpu.count("adam_clip_step") == 2
+
+
+@pytest.mark.parametrize("prior", ["uniform", "learn"])
+def test_gmvae_free_nats_on_cpu(shell_on_cpu, tmp_path, prior):
+    G.test_gmvae_trains_with_free_nats_under_graph_capture(tmp_path, prior)
+    assert "gmvae_bound" in shell_on_cpu
