@@ -105,6 +105,20 @@ int scvae_gemm_f16(int layout, int M, int N, int K, const void *A, int64_t lda, 
                    int64_t ldb, float *C, int64_t ldc, int accumulate, float alpha,
                    void *workspace, int64_t workspace_bytes, void *stream);
 int64_t scvae_gemm_f16_workspace_bytes(int layout, int M, int N, int K);
+/* fp16 product with one operand given as TWO fp16 matrices, X being the rounding remainder of the
+ * fp32 original (scvae_f32_to_f16_split): which = 1: C = alpha (A + X) B, which = 2: C = alpha A (B + X);
+ * X has the shape and layout of the operand it completes.  Both halves accumulate into the same
+ * TMEM tile, so the product carries ~22 mantissa bits of that operand at fp16 HBM traffic for the
+ * other one.  Used for the first encoder layer (weights split: its activations then match the
+ * reference's fp32 `fully_connected`, MU:53-59, to ~1e-6) and its weight gradient (dY split: the
+ * batch-norm backward makes that sum cancel heavily, so 11 bits are not enough). */
+int scvae_gemm_f16_split(int layout, int M, int N, int K, const void *A, int64_t lda, const void *B,
+                         int64_t ldb, const void *X, int64_t ldx, int which, float *C, int64_t ldc,
+                         int accumulate, float alpha, void *workspace, int64_t workspace_bytes,
+                         void *stream);
+/* hi = fp16(scale * src), lo = fp16(scale * src - hi); zero padded to ldd columns (ldd % 8 == 0). */
+int scvae_f32_to_f16_split(const float *src, int64_t lds, int64_t rows, int cols, void *hi, void *lo,
+                           int64_t ldd, float scale, void *stream);
 /* Bounds the persistent CTAs of the calling thread's subsequent tensor-core GEMM launches to
  * `max_ctas` (0 = one per SM, the default); returns the previous bound.  A caller that runs a
  * large HBM-bound product on a second stream uses it to leave SMs to the kernels it overlaps. */
@@ -301,10 +315,30 @@ int scvae_vae_bound_rows(const float *logp, const float *kl_rows, int R, int S, 
  * One fused pass over the flat parameter buffer.  `step` [device, int64] is read (t =
  * *step + 1) for the bias correction lr_t = lr sqrt(1-b2^t)/(1-b1^t); the caller advances
  * it with scvae_step_advance (kept separate so the pair is CUDA-graph capturable).
- * grad_scale multiplies the gradient before clipping (data-parallel mean). */
+ * grad_scale multiplies the gradient before clipping (data-parallel mean).
+ * scalars (nullable, device {learning rate factor, warm-up weight}): lr is multiplied by
+ * scalars[0], so a captured step serves any learning rate.
+ * shadows (nullable, [host], n_shadows <= SCVAE_MAX_SHADOWS): blocks of the parameter range whose
+ * fp16 operand copies (+ rounding remainders, see scvae_gemm_f16_split) are rewritten in the same
+ * pass: flat offsets [lo, hi) relative to `param` hold rows of src_ld floats; row r goes to row
+ * (r / src_block_rows) * dst_block_rows + r % src_block_rows of the (.., dst_ld) half matrix,
+ * columns < cols copied, the rest of a touched 4-column group zeroed.
+ * advance_counter (nullable, device int, zero-initialised) / advance_total: *step += 1 once the
+ * last of `advance_total` CTAs sharing the counter finishes (scvae_adam_clip_ctas(n) CTAs per
+ * launch) -- replaces scvae_step_advance when every optimiser launch of a step takes part. */
+#define SCVAE_MAX_SHADOWS 4
+typedef struct scvae_shadow {
+    int64_t lo, hi, src_ld, dst_ld;
+    int64_t src_block_rows, dst_block_rows;
+    void *hi16, *lo16;
+    int cols, reserved;
+} scvae_shadow;
 int scvae_adam_clip_step(float *param, const float *grad, float *m, float *v, int64_t n,
-                         const int64_t *step, float lr, float beta1, float beta2,
-                         float epsilon, float clip, float grad_scale, void *stream);
+                         int64_t *step, float lr, float beta1, float beta2,
+                         float epsilon, float clip, float grad_scale, const float *scalars,
+                         const scvae_shadow *shadows /* [host] */, int n_shadows,
+                         int *advance_counter, int advance_total, void *stream);
+int scvae_adam_clip_ctas(int64_t n);
 int scvae_step_advance(int64_t *step, void *stream);
 
 /* ---- e: data-parallel exchange fused with the optimiser ----------------------
@@ -316,12 +350,12 @@ int scvae_step_advance(int64_t *step, void *stream);
  * the range in every rank's gradient / parameter buffer and to every rank's flag block (32
  * zero-initialised uint32 per exchange channel).  ctl: 4 zero-initialised device uint32 owned
  * by the channel ([2] != 0 after a peer timed out).  Two flag barriers per launch; no host
- * synchronisation; CUDA-graph capturable.  n % 4 == 0. */
+ * synchronisation; CUDA-graph capturable.  n % 4 == 0.  scalars: as in scvae_adam_clip_step. */
 int scvae_dp_reduce_adam(int world, int rank, const void *const *grad_ptrs,
                          void *const *param_ptrs, void *const *flag_ptrs, float *m, float *v,
                          int64_t n, const int64_t *step, float lr, float beta1, float beta2,
-                         float epsilon, float clip, float grad_scale, void *ctl, int max_ctas,
-                         void *stream);
+                         float epsilon, float clip, float grad_scale, const float *scalars, void *ctl,
+                         int max_ctas, void *stream);
 
 /* ---- a9/a10: Gaussian-mixture VAE pieces  (GMVAE:2788-3434) ------------------------------
  * The K cluster passes are K consecutive row groups of one tall matrix, rows ordered
@@ -367,6 +401,67 @@ int scvae_gmvae_bound(const float *y, const float *logy, const float *logp, cons
 /* z_mean[b] = sum_k y[b,k] mean_k[b]  (GMVAE:2896-2899); z_mean (B, L) contiguous. */
 int scvae_gmvae_z_mean(const float *qh, int64_t ldq, const float *y, int K, int B, int L,
                        float *z_mean, void *stream);
+
+/* ---- a2 + a3 + a6 fused: the (cells x ~100) middle of a VAE training step --------------------
+ * Everything between the two gene-axis products of a step -- per `dense_layer` (MU:53-74) the
+ * FC with batch norm and ReLU behind it, the posterior heads with clip / reparameterised sample /
+ * analytic KL behind them (VAE:2280-2369, :2624-2627), the decoder layers -- as ONE persistent
+ * kernel per direction: a CTA owns <= 64 cells, keeps their activations in shared memory and runs
+ * every small product in exact fp32 with its normalisation / activation / sample as the epilogue;
+ * batch statistics and weight-gradient partials cross CTAs through `workspace` and a grid barrier
+ * and are folded in a fixed order (deterministic).  Requirements: hidden widths < 128, latent
+ * size <= 128, one sample per cell (R = S = 1), B <= 64 * (number of SMs).
+ *
+ * scvae_vae_mid_fwd:  enc[0].y partials (the tensor-core product x W1^T, `y1_nsplit` split-K
+ *   slices `y1_slice` floats apart, scaled by y1_alpha) -> ... -> d16, the fp16 augmented operand
+ *   of scvae_heads_fused_*.  Writes every layer's pre-activations `y` and batch statistics
+ *   `mean` / `rstd` (training), ph = [mu | raw log_sigma], z (augmented, with the decoder-input
+ *   extras of VAE:2400-2441), kl_row, optionally kl_elem, and the noise when generate_eps (same
+ *   Philox stream as scvae_fill_normal(seed, offset + *offset_dev)).
+ * scvae_vae_mid_bwd:  dd_parts / logp_parts = the gene-range partials of scvae_heads_fused_bwd's
+ *   workspace -> logp (with the first-order correction for the fp16 rounding of d16), bound[4] =
+ *   {lower_bound, lower_bound_weighted, reconstruction_error, kl_divergence} (VAE:2715-2734, R = 1),
+ *   dw / dbeta of every layer but the first encoder layer, and dy1_16 (+ dy1_16_lo, nullable: the
+ *   rounding remainder, see scvae_gemm_f16_split) = fp16(dy1_scale * dY1) for that layer's
+ *   weight-gradient product.  kl weight = kl_weight * scalars[1] (scalars nullable,
+ *   device: {learning rate, warm-up weight}).
+ * A barrier wait that exceeds ~2 s sets *error (device int) instead of hanging. */
+#define SCVAE_MID_MAX_LAYERS 4
+typedef struct scvae_mid_layer {
+    const float *w;        /* (n_out, ldw): bias in column n_in, decoder-input extras behind it */
+    float *dw;             /* gradient of w (backward) */
+    const float *beta;     /* batch-norm offset [n_out]; NULL = no batch norm */
+    float *dbeta;
+    float *moving_mean, *moving_var;
+    float *mean, *rstd;    /* batch statistics [n_out]: written forward, read backward */
+    float *y;              /* pre-activations (B, ldy): written forward, read backward */
+    int64_t ldw, ldy;
+    int n_in, k_in, n_out; /* k_in = n_in + 1 + extras = reduction length of the forward product */
+    int reserved;
+} scvae_mid_layer;
+typedef struct scvae_mid_desc {
+    int B, L, n_enc, n_dec;
+    int training, update_moving, deterministic, rows_per_cta;
+    scvae_mid_layer enc[SCVAE_MID_MAX_LAYERS], post, dec[SCVAE_MID_MAX_LAYERS];
+    const float *y1_parts; int64_t y1_ld, y1_slice; int y1_nsplit; float y1_alpha;
+    float *ph; int64_t ldph;
+    float *eps; int generate_eps; int reserved0; uint64_t seed, offset; const int64_t *offset_dev;
+    float *z; int64_t ldz;
+    float *kl_row, *kl_elem;
+    const float *batch_index; const float *count_sum; int n_batches; int reserved1;
+    void *d16; int64_t ldd16;
+    float *h_last; int64_t ldh_last;           /* optional fp32 copy of the last decoder activation */
+    /* backward */
+    const float *dd_parts; int64_t dd_ld, dd_slice; int dd_nsplit; int logp_nsplit;
+    const float *logp_parts; int64_t logp_slice; const float *row_const;
+    float *logp; float *bound;
+    void *dy1_16; void *dy1_16_lo; int64_t lddy1; float *dy1; int64_t lddy1_f32;
+    float go_scalar, dy1_scale, kl_weight; int reserved2; const float *scalars;
+    float *workspace; int64_t workspace_floats; uint32_t *barrier; int *error;
+} scvae_mid_desc;
+int64_t scvae_vae_mid_workspace_floats(const scvae_mid_desc *desc /* [host] */);
+int scvae_vae_mid_fwd(const scvae_mid_desc *desc /* [host] */, void *stream);
+int scvae_vae_mid_bwd(const scvae_mid_desc *desc /* [host] */, void *stream);
 
 /* ---- small helpers used by the shells ------------------------------------------------- */
 /* out[c] = (1/rows) * sum_r x[r, c]  (kl_divergence_neurons, VAE:2643-2646). */

@@ -60,14 +60,15 @@ template <int WORLD, int U>
 __global__ void __launch_bounds__(256)
 dp_reduce_adam_kernel(DpPeers peers, int world_rt, int rank, float *__restrict__ m, float *__restrict__ v, int64_t n,
                       const int64_t *__restrict__ step, float lr, float beta1, float beta2, float eps, float clip,
-                      float gscale, uint32_t *ctl) {
+                      float gscale, const float *__restrict__ scalars, uint32_t *ctl) {
     const int world = WORLD > 0 ? WORLD : world_rt;
     __shared__ float s_lr_t;
     __shared__ uint32_t s_seq;
     __shared__ int s_last;
     if (threadIdx.x == 0) {
         const double t = (double)(*step + 1);
-        s_lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t)));
+        const double lr_eff = (double)lr * (scalars ? (double)scalars[0] : 1.0);
+        s_lr_t = (float)(lr_eff * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t)));
         s_seq = ctl[0] + 1u;
     }
     __syncthreads();
@@ -172,7 +173,7 @@ dp_reduce_adam_kernel(DpPeers peers, int world_rt, int rank, float *__restrict__
 extern "C" int scvae_dp_reduce_adam(int world, int rank, const void *const *grad_ptrs, void *const *param_ptrs,
                                     void *const *flag_ptrs, float *m, float *v, int64_t n, const int64_t *step,
                                     float lr, float beta1, float beta2, float epsilon, float clip, float grad_scale,
-                                    void *ctl, int max_ctas, void *stream) {
+                                    const float *scalars, void *ctl, int max_ctas, void *stream) {
     using namespace scvae;
     SCVAE_CHECK_ARG(world >= 1 && world <= kDpMaxWorld && rank >= 0 && rank < world,
                     "dp_reduce_adam: world %d / rank %d out of range (max %d ranks)", world, rank, kDpMaxWorld);
@@ -197,7 +198,7 @@ extern "C" int scvae_dp_reduce_adam(int world, int rank, const void *const *grad
     if (blocks < 1) blocks = 1;
 #define DP_LAUNCH(W, UU)                                                                                      \
     dp_reduce_adam_kernel<W, UU><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(                               \
-        peers, world, rank, m, v, n, step, lr, beta1, beta2, epsilon, clip, grad_scale, (uint32_t *)ctl)
+        peers, world, rank, m, v, n, step, lr, beta1, beta2, epsilon, clip, grad_scale, scalars, (uint32_t *)ctl)
     switch (world) {
         case 2: DP_LAUNCH(2, 8); break;
         case 4: DP_LAUNCH(4, 4); break;

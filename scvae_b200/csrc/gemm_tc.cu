@@ -23,7 +23,12 @@ constexpr int kStages = 5;
 constexpr int kTileBytes = BM * BK * 4;          // 16 KB per operand per stage
 constexpr int kStageBytes = 2 * kTileBytes;
 constexpr int kEpiBytes = BM * 32 * 4;           // 128 rows x 32 fp32 columns
+// dual mode (a second, low-order copy of one operand accumulated into the same tile): three tiles
+// per stage, four stages
+constexpr int kDualStages = 4;
+constexpr int kDualStageBytes = 3 * kTileBytes;
 constexpr int kSmemBytes = kStages * kStageBytes + 2 * kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kSmemBytesDual = kDualStages * kDualStageBytes + 2 * kEpiBytes + 1024 + 256;
 constexpr int kTmemCols = 2 * BN;                // double-buffered fp32 accumulator
 constexpr int kThreads = 256;
 
@@ -36,6 +41,8 @@ struct GemmParams {
     float alpha;              // accumulator scale applied in the epilogue
     int streamk;              // 1: CTAs own equal contiguous ranges of (tile, k-block) units
     int units_per_cta, total_units;
+    int dual;                 // 0: C = A B;  1: C = (A + X) B;  2: C = A (B + X)   (X: the low-order half
+                              // of an fp32 operand split into two fp16 matrices, same shape and major)
 };
 
 // One unit of work of a CTA: k-blocks [kb0, kb1) of output tile (tm, tn).
@@ -84,13 +91,18 @@ struct WorkIter {
 
 // F16: operands are fp16 (kind::f16, 64-element k-blocks, plain 128B swizzle for both majors);
 // otherwise fp32 consumed as tf32 (32-element k-blocks, 32-byte-atom swizzle for MN-major).
-template <bool F16, bool A_MN, bool B_MN>
+// DUAL (compile time, so that no tcgen05.mma sits under a run-time predicate): 0: C = A B;
+// 1: C = (A + X) B;  2: C = A (B + X).
+template <bool F16, bool A_MN, bool B_MN, int DUAL = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX,
+                 const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *epi = smem + kStages * kStageBytes;
+    constexpr int nstages = DUAL ? kDualStages : kStages;
+    constexpr int stage_bytes = DUAL ? kDualStageBytes : kStageBytes;
+    uint8_t *epi = smem + nstages * stage_bytes;
     uint64_t *bars = (uint64_t *)(epi + 2 * kEpiBytes);
     // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem base address
     const uint32_t bar_full = smem_u32(bars);
@@ -113,6 +125,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+        if (DUAL) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kStages; ++i) {
@@ -147,10 +160,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int tm = sg.tm, tn = sg.tn, kb0 = sg.kb0, kb1 = sg.kb1;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                    const uint32_t sa = smem_u32(smem + stage * stage_bytes);
                     const uint32_t sb = sa + kTileBytes;
+                    const uint32_t sx = sb + kTileBytes;
                     const uint32_t full = bar_full + 8 * stage;
-                    mbar_expect_tx(full, kStageBytes);
+                    mbar_expect_tx(full, stage_bytes);
+                    if (DUAL == 1) {
+                        if (A_MN) {
+#pragma unroll
+                            for (int j = 0; j < MN_BOXES; ++j)
+                                tma_load_2d(sx + j * MN_BOX_BYTES, &tmX, tm * BM + MN_BOX * j, kb * BKE, full);
+                        } else {
+                            tma_load_2d(sx, &tmX, kb * BKE, tm * BM, full);
+                        }
+                    } else if (DUAL == 2) {
+                        if (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < MN_BOXES; ++j)
+                                tma_load_2d(sx + j * MN_BOX_BYTES, &tmX, tn * BN + MN_BOX * j, kb * BKE, full);
+                        } else {
+                            tma_load_2d(sx, &tmX, kb * BKE, tn * BN, full);
+                        }
+                    }
                     if (A_MN) {
 #pragma unroll
                         for (int j = 0; j < MN_BOXES; ++j)
@@ -165,7 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     } else {
                         tma_load_2d(sb, &tmB, kb * BKE, tn * BN, full);
                     }
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -192,8 +223,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                    const uint32_t sa = smem_u32(smem + stage * stage_bytes);
                     const uint32_t sb = sa + kTileBytes;
+                    const uint32_t sx = sb + kTileBytes;
                     const uint64_t da = A_MN ? make_desc(sa, p.mn_lbo, p.mn_sbo, MN_LAYOUT) : make_desc(sa, 16, 1024, 2);
                     const uint64_t db = B_MN ? make_desc(sb, p.mn_lbo, p.mn_sbo, MN_LAYOUT) : make_desc(sb, 16, 1024, 2);
                     // per UMMA K step: K-major +32 B inside the swizzle row; MN-major +UK k-rows
@@ -206,8 +238,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         else
                             tc_mma_tf32(tmem_d, da + k * sta, db + k * stb, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
+                    if constexpr (F16 && DUAL != 0) {
+                        // low-order half of the split operand into the same accumulator
+                        const uint64_t dx = (DUAL == 1 ? A_MN : B_MN) ? make_desc(sx, p.mn_lbo, p.mn_sbo, MN_LAYOUT)
+                                                                      : make_desc(sx, 16, 1024, 2);
+                        const uint64_t a2 = DUAL == 1 ? dx : da, b2 = DUAL == 1 ? db : dx;
+#pragma unroll
+                        for (int k = 0; k < BKE / UK; ++k) tc_mma_f16(tmem_d, a2 + k * sta, b2 + k * stb, idesc, 1u);
+                    }
                     tc_commit(bar_empty + 8 * stage);  // frees the smem slot once the MMAs retire
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(bar_tfull + 8 * acc);        // accumulator complete
             }
@@ -376,7 +416,8 @@ static int64_t workspace_bytes(int M, int N, int K, int bke) {
 template <bool F16>
 static int launch_gemm(const char *name, int layout, int M, int N, int K, const void *A, int64_t lda, const void *B,
                        int64_t ldb, float *C, int64_t ldc, int accumulate, float alpha, void *workspace,
-                       int64_t workspace_bytes_given, cudaStream_t s) {
+                       int64_t workspace_bytes_given, cudaStream_t s, const void *X = nullptr, int64_t ldx = 0,
+                       int dual = 0) {
     constexpr int EB = F16 ? 2 : 4;
     constexpr int BKE = 128 / EB;
     constexpr int LDM = 16 / EB;   // leading dimensions must be multiples of 16 bytes
@@ -393,8 +434,10 @@ static int launch_gemm(const char *name, int layout, int M, int N, int K, const 
             sp.kb_per_split = sp.nkb;
         }
     }
-    CUtensorMap tmA, tmB, tmC;
+    CUtensorMap tmA, tmB, tmC, tmX;
     const bool a_mn = (layout == SCVAE_GEMM_TN), b_mn = (layout != SCVAE_GEMM_NT);
+    SCVAE_CHECK_ARG(dual == 0 || (F16 && X && (dual == 1 || dual == 2) && aligned16(X) && ldx % LDM == 0),
+                    "%s: bad split operand", name);
     // K-major operand (rows = M or N, cols = K): box BKE (K) x 128 (rows), SWIZZLE_128B.
     // MN-major operand (rows = K, cols = M or N): boxes of 128 bytes (MN) x BKE (K rows); fp32
     // needs the 32-byte-atom swizzle (Swizzle<2,5,2>, atom = 128 B of MN x 4 K rows).
@@ -403,6 +446,15 @@ static int launch_gemm(const char *name, int layout, int M, int N, int K, const 
     else      { if (make_map(&tmA, A, M, K, lda, BKE, 128, CU_TENSOR_MAP_SWIZZLE_128B, EB)) return 1; }
     if (b_mn) { if (make_map(&tmB, B, K, N, ldb, 128 / EB, BKE, mn_sw, EB)) return 1; }
     else      { if (make_map(&tmB, B, N, K, ldb, BKE, 128, CU_TENSOR_MAP_SWIZZLE_128B, EB)) return 1; }
+    if (dual == 1) {
+        if (a_mn) { if (make_map(&tmX, X, K, M, ldx, 128 / EB, BKE, mn_sw, EB)) return 1; }
+        else      { if (make_map(&tmX, X, M, K, ldx, BKE, 128, CU_TENSOR_MAP_SWIZZLE_128B, EB)) return 1; }
+    } else if (dual == 2) {
+        if (b_mn) { if (make_map(&tmX, X, K, N, ldx, 128 / EB, BKE, mn_sw, EB)) return 1; }
+        else      { if (make_map(&tmX, X, N, K, ldx, BKE, 128, CU_TENSOR_MAP_SWIZZLE_128B, EB)) return 1; }
+    } else {
+        tmX = tmA;
+    }
     if (sp.nsplit > 1) {
         if (make_map(&tmC, (const float *)workspace, (int64_t)sp.nsplit * ws_rows, N, ldw, 32, 128)) return 1;
     } else {
@@ -419,6 +471,7 @@ static int launch_gemm(const char *name, int layout, int M, int N, int K, const 
     if (const char *e = getenv("SCVAE_TC_MN_LBO")) p.mn_lbo = (uint32_t)atoi(e);
     if (const char *e = getenv("SCVAE_TC_MN_SBO")) p.mn_sbo = (uint32_t)atoi(e);
 
+    p.dual = dual;
     p.streamk = sp.streamk;
     p.units_per_cta = sp.units_per_cta;
     p.total_units = sp.tiles_m * sp.tiles_n * sp.nkb;
@@ -432,23 +485,33 @@ static int launch_gemm(const char *name, int layout, int M, int N, int K, const 
         cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), s);
         SCVAE_CHECK_ARG(e == cudaSuccess, "%s: memset failed: %s", name, cudaGetErrorString(e));
     }
-#define LAUNCH(AM, BMN)                                                                                     \
+#define LAUNCH(AM, BMN, DU)                                                                                 \
     do {                                                                                                    \
+        constexpr int smem_bytes = (DU) ? kSmemBytesDual : kSmemBytes;                                      \
         static bool attr_set = false;                                                                       \
         if (!attr_set) {                                                                                    \
-            cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<F16, AM, BMN>,                              \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);  \
+            cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<F16, AM, BMN, DU>,                          \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);  \
             SCVAE_CHECK_ARG(e == cudaSuccess, "%s: cannot set smem attribute: %s", name,                    \
                             cudaGetErrorString(e));                                                         \
             attr_set = true;                                                                                \
         }                                                                                                   \
-        gemm_tc_kernel<F16, AM, BMN><<<grid, kThreads, kSmemBytes, s>>>(tmA, tmB, tmC, p);                  \
+        gemm_tc_kernel<F16, AM, BMN, DU><<<grid, kThreads, smem_bytes, s>>>(tmA, tmB, tmC, tmX, p);         \
     } while (0)
-    switch (layout) {
-        case SCVAE_GEMM_NT: LAUNCH(false, false); break;
-        case SCVAE_GEMM_NN: LAUNCH(false, true); break;
-        case SCVAE_GEMM_TN: LAUNCH(true, true); break;
-        default: set_error("%s: unknown layout %d", name, layout); return 1;
+    if (dual == 0) {
+        switch (layout) {
+            case SCVAE_GEMM_NT: LAUNCH(false, false, 0); break;
+            case SCVAE_GEMM_NN: LAUNCH(false, true, 0); break;
+            case SCVAE_GEMM_TN: LAUNCH(true, true, 0); break;
+            default: set_error("%s: unknown layout %d", name, layout); return 1;
+        }
+    } else if (F16 && dual == 2 && layout == SCVAE_GEMM_NT) {
+        LAUNCH(false, false, 2);          // forward with split weights
+    } else if (F16 && dual == 1 && layout == SCVAE_GEMM_TN) {
+        LAUNCH(true, true, 1);            // weight gradient with split output gradient
+    } else {
+        set_error("%s: split operands are built for NT (which = 2) and TN (which = 1)", name);
+        return 1;
     }
 #undef LAUNCH
     SCVAE_CHECK_LAUNCH(name);
@@ -470,6 +533,14 @@ extern "C" int scvae_gemm_sm_limit(int max_ctas) {
     const int prev = g_sm_limit;
     g_sm_limit = max_ctas > 0 ? max_ctas : 0;
     return prev;
+}
+
+extern "C" int scvae_gemm_f16_split(int layout, int M, int N, int K, const void *A, int64_t lda, const void *B,
+                                    int64_t ldb, const void *X, int64_t ldx, int which, float *C, int64_t ldc,
+                                    int accumulate, float alpha, void *workspace, int64_t workspace_bytes,
+                                    void *stream) {
+    return launch_gemm<true>("gemm_f16_split", layout, M, N, K, A, lda, B, ldb, C, ldc, accumulate, alpha, workspace,
+                             workspace_bytes, (cudaStream_t)stream, X, ldx, which);
 }
 
 extern "C" int64_t scvae_gemm_tf32_workspace_bytes(int layout, int M, int N, int K) {

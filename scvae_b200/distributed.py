@@ -125,7 +125,7 @@ class PeerExchange:
         engine.rebind_flat_buffers(self.param, self.grad)
         self.engine = engine
 
-    def reduce_adam(self, lo, hi, learning_rate, channel, max_ctas=0):
+    def reduce_adam(self, lo, hi, learning_rate, channel, max_ctas=0, scalars=None):
         """Exchange + optimiser update of the flat range [lo, hi) on the current stream."""
         from . import kernels as K
         from .engine import ADAM_BETA1, ADAM_BETA2, ADAM_EPSILON, GRADIENT_CLIP
@@ -135,7 +135,8 @@ class PeerExchange:
                          [p + 4 * lo for p in self.param_ptrs], [p + fo for p in self.flag_ptrs],
                          s.m[lo:hi], s.v[lo:hi], hi - lo, s.step, learning_rate, ADAM_BETA1,
                          ADAM_BETA2, ADAM_EPSILON, GRADIENT_CLIP, 1.0 / self.world,
-                         ctl=self.ctl[channel * 4:channel * 4 + 4], max_ctas=max_ctas)
+                         ctl=self.ctl[channel * 4:channel * 4 + 4], max_ctas=max_ctas,
+                         scalars=scalars)
 
     def slice_bounds(self, lo, hi, rank_index):
         """[a, b) of the flat range [lo, hi) owned by ``rank_index`` (as in the kernel)."""
@@ -198,6 +199,8 @@ def broadcast_parameters(engine):
     if not is_active():
         return
     s = engine.store
+    if hasattr(engine, "invalidate_shadows"):
+        engine.invalidate_shadows()
     for buf in (s.param, s.m, s.v, s.step):
         dist.broadcast(buf, src=0)
     for layer in getattr(engine, "bn_layers", lambda: [])():

@@ -148,6 +148,10 @@ class VAEEngine:
         self._side = None                  # second stream: head weight gradients / shadow copies
         self.overlap_streams = True
         self.side_gemm_ctas = int(__import__("os").environ.get("SCVAE_SIDE_GEMM_CTAS", "116"))
+        # the (cells x ~100) middle of a 16-bit training / lean evaluation step as one persistent
+        # kernel per direction (csrc/mid_layers.cu) instead of ~20 small launches
+        self.mid_fused = __import__("os").environ.get("SCVAE_MID_FUSED", "1") != "0"
+        self.mid_bwd_ctas = int(__import__("os").environ.get("SCVAE_MID_BWD_CTAS", "0"))   # 0: all SMs
 
         for arch in (inference_architecture, generative_architecture):
             if arch not in ("MLP", "LFM"):
@@ -186,6 +190,10 @@ class VAEEngine:
         self.store = store
         self.state = {}
         self._peer = None                  # distributed.PeerExchange (fused exchange + optimiser)
+        # {learning rate, warm-up weight} of the current step on the device: kernels of a captured
+        # step read them here, so one CUDA graph serves every epoch of a warm-up schedule
+        self.scalars = torch.tensor([0.0, 1.0], dtype=torch.float32, device=self.device)
+        self._scalars_host = (None, None)
         for layer in self.enc + [self.post] + self.dec + [self.head]:
             if layer.bn:
                 layer.moving_mean = torch.zeros(layer.n_out, dtype=torch.float32,
@@ -209,6 +217,7 @@ class VAEEngine:
         must already be in place.  Plans hold no views of them; captured graphs do and must be
         re-captured (TrainLoop objects created before this call are stale)."""
         assert param.numel() == self.store.total and grad.numel() == self.store.total
+        self._shadow_valid = False
         self.store.param, self.store.grad = param, grad
         self._bind_views()
 
@@ -262,6 +271,7 @@ class VAEEngine:
 
     def import_parameters(self, params, strict=True):
         """Load variables given by their TF names in the reference layout (weights (in,out))."""
+        self._shadow_valid = False
         for layer, rows, scope in self._tf_names():
             w = params[scope + "/DENSE/weights"].to(self.device, torch.float32)
             b = params[scope + "/DENSE/biases"].to(self.device, torch.float32)
@@ -359,6 +369,7 @@ class VAEEngine:
         return sd
 
     def load_state_dict(self, sd):
+        self._shadow_valid = False
         self.store.param.copy_(sd["param"])
         self.store.m.copy_(sd["m"])
         self.store.v.copy_(sd["v"])
@@ -449,7 +460,7 @@ class VAEEngine:
         rows = max(M, p.M)
         if not p.fused_ready:
             p.D16 = torch.zeros(rows, 128, dtype=torch.float16, device=dev)
-            p.W16 = torch.zeros(self.P * self.Gh, 128, dtype=torch.float16, device=dev)
+            self._shadow_buffers(p)
             p.fused_ws = torch.zeros(K.heads_fused_workspace_floats(rows, self.G),
                                      dtype=torch.float32, device=dev)
             p.dA16 = None
@@ -492,11 +503,54 @@ class VAEEngine:
             self._side = torch.cuda.Stream(device=self.device)
         return self._side
 
+    def _shadow_buffers(self, p):
+        """fp16 operand copies of the gene-axis weights.  They depend on the parameters only, so
+        the ENGINE owns them (plans alias them): head weights W16, first encoder weight as fp16 +
+        rounding remainder (scvae_gemm_f16_split)."""
+        if getattr(self, "W16", None) is None:
+            dev = self.device
+            self.W16 = torch.zeros(self.P * self.Gh, 128, dtype=torch.float16, device=dev)
+            self.W1_16 = self.W1_16_lo = None
+            if self.enc:
+                self.W1_16 = torch.zeros(self.enc[0].n_out, (self.G + 8) & ~7, dtype=torch.float16,
+                                         device=dev)
+                self.W1_16_lo = torch.zeros_like(self.W1_16)
+            self._shadow_valid = False
+        p.W16, p.W1_16, p.W1_16_lo = self.W16, self.W1_16, self.W1_16_lo
+
+    def invalidate_shadows(self):
+        """The parameters changed behind the optimiser kernel's back (import, restore, broadcast)."""
+        self._shadow_valid = False
+
+    def _adam_shadows(self, lo, hi):
+        """scvae_shadow descriptors of the shadowed blocks inside the flat range [lo, hi): the
+        optimiser kernel rewrites the fp16 copies in the pass that updates the masters."""
+        if getattr(self, "W16", None) is None:
+            return []
+        out = []
+        if self.enc:
+            l = self.enc[0]
+            off = self.store.offsets[l.name + "/W"][0]
+            if lo <= off and off + l.n_out * l.in_p <= hi:
+                out.append(K.shadow(off - lo, off - lo + l.n_out * l.in_p, l.in_p, l.n_in + 1,
+                                    self.W1_16, self.W1_16_lo))
+        l = self.head
+        off = self.store.offsets[l.name + "/W"][0]
+        if lo <= off and off + self.P * self.Gn * l.in_p <= hi:
+            out.append(K.shadow(off - lo, off - lo + self.P * self.Gn * l.in_p, l.in_p, l.in_p,
+                                self.W16, None, src_block_rows=self.Gn, dst_block_rows=self.Gh))
+        return out
+
     def _refresh_shadows(self, p, M):
-        """fp16 copies of the first encoder weight and of the head weights for this step.
+        """fp16 copies of the first encoder weight and of the head weights for this step -- only
+        when the last optimiser step did not already rewrite them (scvae_adam_clip_step shadows).
         They depend on the parameters only, so they run on the side stream beside the
         densify / noise kernels that precede the first product; the main stream joins here."""
         self._plan_fused(p, M, backward=False)
+        if self._shadow_valid:
+            p.shadow_fork = None
+            return
+        self._shadow_valid = True
         main = torch.cuda.current_stream()
         use_side = self.overlap_streams and getattr(p, "shadow_fork", None) is not None
         if use_side:
@@ -509,10 +563,9 @@ class VAEEngine:
         with ctx:
             if self.enc:
                 l = self.enc[0]
-                if getattr(p, "W1_16", None) is None:
-                    p.W1_16 = torch.zeros(l.n_out, self._x16(p).shape[1], dtype=torch.float16,
-                                          device=self.device)
-                K.f32_to_f16(l.w, l.n_in + 1, p.W1_16)
+                # weights as fp16 + their fp16 rounding remainder: the counts are exact in fp16,
+                # so x W1^T keeps ~22 bits of the fp32 weights (scvae_gemm_f16_split)
+                K.f32_to_f16_split(l.w, l.n_in + 1, p.W1_16, p.W1_16_lo)
             l = self.head
             for h in range(self.P):
                 K.f32_to_f16(l.w[h * self.Gn:(h + 1) * self.Gn], l.in_p,
@@ -560,6 +613,118 @@ class VAEEngine:
                 p.ws_bytes = need
             ws = p.workspace
         K.gemm_f16(layout, M, N, Kd, A, Bm, C, accumulate=accumulate, alpha=alpha, workspace=ws)
+
+    # ---- fused middle (mid_layers.cu) -------------------------------------------------------
+    def _mid_possible(self, p, M, drop):
+        """Hidden widths < 128, latent size <= 128 (padded latent row <= 128), one sample per cell,
+        Gaussian posterior with the analytic KL, no dropout, cells <= 64 per SM."""
+        if not (self.mid_fused and self.tensor_cores and M == p.B and self.enc and self.dec
+                and not drop and not self.unit_variance and not self.sampled_kl):
+            return False
+        if len(self.enc) > 4 or len(self.dec) > 4 or self.Zp > 128 or self.post.in_p > 128:
+            return False
+        if any(l.n_out >= 128 or (i > 0 and l.in_p > 128) for i, l in enumerate(self.enc)):
+            return False
+        if any(l.n_out >= 128 or l.in_p > 128 for l in self.dec):
+            return False
+        return p.B <= 64 * self._sm_count()
+
+    def _sm_count(self):
+        if getattr(self, "_sms", None) is None:
+            self._sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        return self._sms
+
+    def _mid_rows(self, B, ctas):
+        """Cells per CTA (a multiple of 4, <= 64) so that at most ``ctas`` CTAs cover B cells."""
+        rows = max(4, -(-B // max(ctas, 1)))
+        return min(64, (rows + 3) & ~3)
+
+    def _mid_desc(self, p, backward):
+        """The descriptor of vae_mid_fwd / vae_mid_bwd for this plan (all pointers are static)."""
+        key = "_mid_bwd" if backward else "_mid_fwd"
+        d = getattr(p, key, None)
+        if d is not None:
+            return d
+        dev, B, L = self.device, p.B, self.L
+        if getattr(p, "mid_bar", None) is None:
+            p.mid_bar = torch.zeros(4, dtype=torch.int32, device=dev)
+            p.mid_err = torch.zeros(4, dtype=torch.int32, device=dev)
+            p.mid_ws = None
+        self._plan_fused(p, p.M, backward=backward)
+        d = K.mid_desc()
+        d.B, d.L, d.n_enc, d.n_dec = B, L, len(self.enc), len(self.dec)
+        sms = self._sm_count()
+        d.rows_per_cta = self._mid_rows(B, min(sms, self.mid_bwd_ctas) if (
+            backward and self.mid_bwd_ctas > 0) else sms)
+        for i, l in enumerate(self.enc):
+            d.enc[i] = K.mid_layer(
+                w=l.w if i else None, dw=l.dw if i else None, beta=l.beta if l.bn else None,
+                dbeta=l.dbeta if l.bn else None, moving_mean=l.moving_mean, moving_var=l.moving_var,
+                mean=p.enc_mean[i], rstd=p.enc_rstd[i], y=p.encY[i], n_in=l.n_in, k_in=l.k_in,
+                n_out=l.n_out)
+        l = self.post
+        d.post = K.mid_layer(w=l.w, dw=l.dw, n_in=l.n_in, k_in=l.k_in, n_out=l.n_out)
+        for j, l in enumerate(self.dec):
+            d.dec[j] = K.mid_layer(
+                w=l.w, dw=l.dw, beta=l.beta if l.bn else None, dbeta=l.dbeta if l.bn else None,
+                moving_mean=l.moving_mean, moving_var=l.moving_var, mean=p.dec_mean[j],
+                rstd=p.dec_rstd[j], y=p.decY[j], n_in=l.n_in, k_in=l.k_in, n_out=l.n_out)
+        d.ph, d.ldph = p.PH.data_ptr(), p.PH.stride(0)
+        d.eps = p.eps.data_ptr()
+        d.z, d.ldz = p.Z.data_ptr(), p.Z.stride(0)
+        d.kl_row, d.kl_elem = p.kl_row.data_ptr(), p.kl_elem.data_ptr()
+        if self.number_of_batches:
+            d.batch_index, d.n_batches = p.batch_index.data_ptr(), self.number_of_batches
+        if self.count_sum_feature:
+            d.count_sum = p.count_sum.data_ptr()
+        d.d16, d.ldd16 = p.D16.data_ptr(), p.D16.stride(0)
+        d.kl_weight = self.kl_weight
+        d.scalars = self.scalars.data_ptr()
+        d.barrier, d.error = p.mid_bar.data_ptr(), p.mid_err.data_ptr()
+        if backward:
+            self._plan_backward(p)
+            self._dy1_16(p)
+            d.logp, d.bound = p.logp.data_ptr(), p.bound.data_ptr()
+            d.dy1_16, d.lddy1 = p.dY1_16.data_ptr(), p.dY1_16.stride(0)
+            d.dy1_16_lo = p.dY1_16_lo.data_ptr()
+        setattr(p, key, d)
+        need = K.vae_mid_workspace_floats(d)
+        if p.mid_ws is None or p.mid_ws.numel() < need:
+            p.mid_ws = torch.zeros(need, dtype=torch.float32, device=dev)
+        for other in ("_mid_fwd", "_mid_bwd"):        # (both share the workspace)
+            o = getattr(p, other, None)
+            if o is not None:
+                o.workspace, o.workspace_floats = p.mid_ws.data_ptr(), p.mid_ws.numel()
+        return d
+
+    def step_on_device_scalars(self, p, R, S, u16_ok):
+        """True when a training step on this plan takes the 16-bit path with the fused middle: its
+        kernels read the warm-up weight (and draw the noise) on the device, so ONE captured graph
+        serves every epoch of a warm-up schedule."""
+        M = R * S * p.B
+        return bool(R == 1 and u16_ok and self.fused_heads and self._fused_possible(M, p.B)
+                    and self._mid_possible(p, M, bool(self.dropout_active)))
+
+    def mid_error(self, p):
+        """True when a grid barrier of the fused middle timed out (results invalid)."""
+        return getattr(p, "mid_err", None) is not None and bool(p.mid_err[0].item())
+
+    def _gemm16_split(self, p, layout, M, N, Kd, A, Bm, X, which, C, alpha=1.0):
+        need = K.gemm_f16_workspace_bytes(layout, M, N, Kd)
+        ws = None
+        if need > 0:
+            if p.ws_bytes < need:
+                p.workspace = torch.empty(need // 4, dtype=torch.float32, device=self.device)
+                p.ws_bytes = need
+            ws = p.workspace
+        K.gemm_f16_split(layout, M, N, Kd, A, Bm, X, which, C, alpha=alpha, workspace=ws)
+
+    def _dy1_16(self, p):
+        if getattr(p, "dY1_16", None) is None:
+            p.dY1_16 = torch.zeros(p.B, (self.enc[0].n_out + 7) & ~7, dtype=torch.float16,
+                                   device=self.device)
+            p.dY1_16_lo = torch.zeros_like(p.dY1_16)
+        return p.dY1_16
 
     # ------------------------------------------------------------------ inputs -------------
     def set_batch_dense(self, p, x, t=None):
@@ -627,12 +792,35 @@ class VAEEngine:
         if not use16 and not getattr(p, "have_x", True):
             raise RuntimeError("this minibatch was densified for the fused 16-bit training step "
                                "only; call set_batch_csr without train16 for other passes")
+        p.mid_done = False
+        mid = bool(use16 and self._mid_possible(p, M, drop))
+        if mid:
+            # first encoder product on the tensor cores, everything up to the fp16 operand of the
+            # fused heads in ONE persistent kernel (batch norm / ReLU / sample / KL as epilogues)
+            l = self.enc[0]
+            self._refresh_shadows(p, M)
+            self._gemm16_split(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, p.X16, p.W1_16, p.W1_16_lo, 2,
+                               p.encY[0])
+            md = self._mid_desc(p, backward=False)
+            md.training, md.update_moving = int(bool(is_training)), int(bool(update_moving))
+            md.deterministic = int(bool(deterministic))
+            md.y1_parts, md.y1_ld = p.encY[0].data_ptr(), p.encY[0].stride(0)
+            md.y1_slice, md.y1_nsplit, md.y1_alpha = 0, 1, 1.0
+            src = getattr(p, "eps_source", None)
+            if src is not None and not deterministic:
+                # the noise is drawn inside the kernel (same Philox stream as scvae_fill_normal)
+                md.generate_eps, md.seed, md.offset = 1, int(src[0]), 0
+                md.offset_dev = src[1].data_ptr()
+            else:
+                md.generate_eps, md.offset_dev = 0, None
+            K.vae_mid_fwd(md)
         h, h_cols = p.X, self.G
-        for i, l in enumerate(self.enc):
+        for i, l in enumerate([] if mid else self.enc):
             if i == 0 and use16:
                 # (cells x genes) operand in fp16: half the HBM traffic of the tf32 path
                 self._refresh_shadows(p, M)
-                self._gemm16(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, p.X16, p.W1_16, p.encY[i])
+                self._gemm16_split(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, p.X16, p.W1_16,
+                                   p.W1_16_lo, 2, p.encY[i])
             else:
                 keep = (self.keep_x if i == 0 else self.keep_h) if drop else None
                 src = self._drop_site(p, l.name, h, B, l.n_in, l.n_in, keep).copy if keep else h
@@ -645,7 +833,9 @@ class VAEEngine:
                 K.act_fwd(p.encY[i], l.n_out, p.encH[i], relu=True)
             h = p.encH[i]
         l = self.post
-        if drop and self.keep_h:
+        if mid:
+            pass
+        elif drop and self.keep_h:
             # one mask per posterior parameter over the same activation (VAE:2280-2289)
             L = self.L
             for part, site in enumerate(["POSTERIOR/MU"] + (
@@ -655,11 +845,12 @@ class VAEEngine:
                        p.PH[:, part * L:(part + 1) * L], tensor_cores=False)
         else:
             self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, h, l.w, p.PH)
-        K.gaussian_latent_fwd(p.PH, B, self.L, RS, p.eps, p.Z, p.kl_row, p.kl_elem,
-                              unit_variance=self.unit_variance, deterministic=deterministic)
-        self._decoder_features(p, M)
+        if not mid:
+            K.gaussian_latent_fwd(p.PH, B, self.L, RS, p.eps, p.Z, p.kl_row, p.kl_elem,
+                                  unit_variance=self.unit_variance, deterministic=deterministic)
+            self._decoder_features(p, M)
         d = p.Z
-        for j, l in enumerate(self.dec):
+        for j, l in enumerate([] if mid else self.dec):
             keep = (self.keep_z if j == 0 else self.keep_h) if drop else None
             src = self._drop_site(p, l.name, d, M, l.n_in + l.n_extra, l.n_in,
                                   keep).copy if keep else d
@@ -679,7 +870,8 @@ class VAEEngine:
         if use16 and not fused_backward:
             # heads GEMM + likelihood in one kernel, nothing but log p leaves the chip
             self._plan_fused(p, M, backward=False)
-            K.f32_to_f16(d, l.in_p, p.D16)
+            if not mid:
+                K.f32_to_f16(d, l.in_p, p.D16)
             if not self.enc:
                 self._refresh_shadows(p, M)
             t16 = p.X16 if p.t16_is_x16 else p.T16
@@ -692,7 +884,8 @@ class VAEEngine:
             assert R == 1 and not deterministic
             self._plan_backward(p)
             self._plan_fused(p, M)
-            K.f32_to_f16(d, l.in_p, p.D16)
+            if not mid:
+                K.f32_to_f16(d, l.in_p, p.D16)
             if not self.enc:
                 self._refresh_shadows(p, M)
             p.fused_scale = 2.0 ** round(math.log2(max(S * B, 16) / 16.0))
@@ -701,7 +894,10 @@ class VAEEngine:
             K.heads_fused_bwd(self.kind, p.D16, p.W16, self.Gh, t16, M, self.G, p.dA16, dd,
                               l.n_in, p.logp, p.fused_ws, row_const=rc, go=None,
                               go_scalar=-1.0 / (S * B), scale=p.fused_scale)
-            self._bound(p, R, S, weight)
+            if mid:
+                p.mid_done = True      # the bound comes out of vae_mid_bwd (backward())
+            else:
+                self._bound(p, R, S, weight)
             p.fused_done = True
             return p
         if drop and self.keep_h:
@@ -848,6 +1044,22 @@ class VAEEngine:
         d_in = p.decH[-1] if self.dec else p.Z
         dd_in = p.d_decH[-1] if self.dec else p.dZ
         p.head_join = None
+        mid = getattr(p, "mid_done", False)
+        if mid:
+            # decoder -> sample / KL -> posterior -> encoder backward, log p finish and the bound in
+            # ONE persistent kernel.  It runs BEFORE the head weight-gradient GEMMs are forked to
+            # the side stream: its grid barriers need all of its CTAs resident, and persistent GEMM
+            # CTAs holding most SMs would make it wait for them.
+            md = self._mid_desc(p, backward=True)
+            dd = p.d_decH[-1]
+            md.dd_parts, md.dd_ld, md.dd_slice, md.dd_nsplit = dd.data_ptr(), dd.stride(0), 0, 1
+            md.logp_parts, md.logp_slice, md.logp_nsplit = p.logp.data_ptr(), 0, 1
+            md.row_const = None
+            md.go_scalar = -1.0 / (S * B)
+            md.dy1_scale = p.fused_scale
+            md.deterministic = 0
+            self.set_step_scalars(None, warm_up_weight)
+            K.vae_mid_bwd(md)
         if p.fused_done:
             # dd came out of the fused kernel; dW = da^T d from the fp16 da (per head).  These
             # two HBM-bound products (and, data-parallel, the all-reduce of their 2/3 of the
@@ -895,6 +1107,14 @@ class VAEEngine:
             # wgrad (bias gradient = the augmented ones column) and dgrad of the heads
             self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, M, p.dA, d_in, l.dw)
             self._gemm(p, K.GEMM_NN, M, l.n_in, l.n_out, p.dA, l.w, dd_in)
+        if mid:
+            # the first layer's weight gradient on the tensor cores
+            l = self.enc[0]
+            # (dY1 as fp16 + remainder: the batch-norm backward makes this sum cancel heavily)
+            self._gemm16_split(p, K.GEMM_TN, l.n_out, l.in_p, B, p.dY1_16, p.X16, p.dY1_16_lo, 1, l.dw,
+                               alpha=1.0 / p.fused_scale)
+            self._finish_backward(p, defer_join)
+            return
         for j in range(len(self.dec) - 1, -1, -1):
             l = self.dec[j]
             if l.bn:
@@ -953,18 +1173,33 @@ class VAEEngine:
                 h_in = st.copy
             if i == 0 and p.fused_done:
                 # dW1 = dY1^T X with the fp16 minibatch (dY1 scaled into fp16 range)
-                if getattr(p, "dY1_16", None) is None:
-                    p.dY1_16 = torch.zeros(B, (l.n_out + 7) & ~7, dtype=torch.float16,
-                                           device=self.device)
-                K.f32_to_f16(p.d_encY[0], l.n_out, p.dY1_16, scale=p.fused_scale)
-                self._gemm16(p, K.GEMM_TN, l.n_out, l.in_p, B, p.dY1_16, p.X16, l.dw,
-                             alpha=1.0 / p.fused_scale)
+                self._dy1_16(p)
+                K.f32_to_f16_split(p.d_encY[0], l.n_out, p.dY1_16, p.dY1_16_lo, scale=p.fused_scale)
+                self._gemm16_split(p, K.GEMM_TN, l.n_out, l.in_p, B, p.dY1_16, p.X16, p.dY1_16_lo, 1,
+                                   l.dw, alpha=1.0 / p.fused_scale)
             else:
                 self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.d_encY[i], h_in, l.dw)
             if i > 0:
                 self._gemm(p, K.GEMM_NN, B, l.n_in, l.n_out, p.d_encY[i], l.w, p.d_encH[i - 1])
                 if st is not None:
                     self._drop_bwd(st, p.d_encH[i - 1])
+        self._finish_backward(p, defer_join)
+
+    def set_step_scalars(self, learning_rate=None, warm_up_weight=None):
+        """Update {learning rate, warm-up weight} on the device when they changed (outside a
+        captured step: TrainLoop calls this before the replay)."""
+        lr0, w0 = self._scalars_host
+        lr = lr0 if learning_rate is None else float(learning_rate)
+        w = w0 if warm_up_weight is None else float(warm_up_weight)
+        if (lr, w) != (lr0, w0):
+            if self.device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("step scalars changed inside a captured step: set them with "
+                                   "set_step_scalars() before the capture / replay")
+            self.scalars.copy_(torch.tensor([0.0 if lr is None else lr, 1.0 if w is None else w],
+                                            dtype=torch.float32))
+            self._scalars_host = (lr, w)
+
+    def _finish_backward(self, p, defer_join):
         self._reduce_upto = None
         self._side_tail = None
         if p.head_join is not None:
@@ -976,43 +1211,61 @@ class VAEEngine:
             else:
                 torch.cuda.current_stream().wait_event(p.head_join)
 
-    def _adam(self, lo, hi, learning_rate):
+    def _adam(self, lo, hi, advance=None):
+        """clip + Adam on the flat range; the learning rate comes from the device scalars.  On one
+        GPU the kernel also rewrites the fp16 weight shadows and (advance = (counter, total CTAs))
+        advances the step counter once the last optimiser CTA of the step is done."""
         s = self.store
+        shadows = self._adam_shadows(lo, hi) if self.world_size == 1 else None
         K.adam_clip_step(s.param[lo:hi], s.grad[lo:hi], s.m[lo:hi], s.v[lo:hi], s.step,
-                         learning_rate, ADAM_BETA1, ADAM_BETA2, ADAM_EPSILON, GRADIENT_CLIP,
-                         1.0 / self.world_size)
+                         1.0, ADAM_BETA1, ADAM_BETA2, ADAM_EPSILON, GRADIENT_CLIP,
+                         1.0 / self.world_size, scalars=self.scalars, shadows=shadows,
+                         advance_counter=advance[0] if advance else None,
+                         advance_total=advance[1] if advance else 0)
 
     def optimiser_step(self, learning_rate):
         """[all-reduce] -> clip to [-1, 1] -> TF Adam (VAE:2742-2759).  One fused launch over the
         flat buffers; when the head gradients were produced on the side stream (train_step) the
         head slice (2/3 of the parameters) is updated there, beside the rest of the backward."""
         s = self.store
+        self.set_step_scalars(learning_rate, None)
         tail = getattr(self, "_side_tail", None)
         self._side_tail = None
         upto = getattr(self, "_reduce_upto", None)
         self._reduce_upto = None
         peer = self._peer if self.world_size > 1 else None
+        hi = s.total if tail is None else tail[1]
+        # one GPU: the optimiser launches advance the step counter themselves (last CTA done)
+        advance = None
+        if peer is None and self._all_reduce is None:
+            if getattr(self, "_adam_counter", None) is None:
+                self._adam_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+            total = K.adam_clip_ctas(hi) + (K.adam_clip_ctas(s.total - hi) if tail is not None else 0)
+            advance = (self._adam_counter, total)
         if tail is not None:
             p, off = tail
             side = self._side_stream()
             with torch.cuda.stream(side):
                 if peer is not None:        # exchange + Adam of the head slice in one kernel
-                    peer.reduce_adam(off, s.total, learning_rate, channel=1,
-                                     max_ctas=self.side_gemm_ctas // 2)
+                    peer.reduce_adam(off, s.total, 1.0, channel=1,
+                                     max_ctas=self.side_gemm_ctas // 2, scalars=self.scalars)
                 else:
-                    self._adam(off, s.total, learning_rate)
+                    self._adam(off, s.total, advance)
                 p.head_ev[1].record(side)
-        hi = s.total if tail is None else tail[1]
         self._last_ranges = [(0, hi)] + ([(hi, s.total)] if tail is not None else [])
         if peer is not None:
-            peer.reduce_adam(0, hi, learning_rate, channel=0)
+            peer.reduce_adam(0, hi, 1.0, channel=0, scalars=self.scalars)
         else:
             if self._all_reduce is not None:
                 self._all_reduce(s.grad if upto is None else s.grad[:upto])
-            self._adam(0, hi, learning_rate)
+            self._adam(0, hi, advance)
         if tail is not None:
             torch.cuda.current_stream().wait_event(tail[0].head_ev[1])
-        K.step_advance(s.step)
+        if advance is None:
+            K.step_advance(s.step)
+        # the optimiser kernel rewrote the fp16 weight shadows only on the single-GPU path
+        if getattr(self, "W16", None) is not None:
+            self._shadow_valid = self.world_size == 1
 
     def train_step(self, p, R, S, learning_rate, warm_up_weight=1.0):
         """One ``session.run([optimiser, lower_bound])`` (VAE:1026-1029)."""

@@ -60,6 +60,9 @@ class GMVAEEngine(VAEEngine):
         self.Gn, self.Gp = round4(self.G), aug(self.G)
         self.world_size, self._all_reduce, self._plans = 1, None, {}
         self._side, self.overlap_streams, self._peer = None, False, None   # (VAE-engine-only features)
+        self.scalars = torch.tensor([0.0, 1.0], dtype=torch.float32, device=self.device)
+        self._scalars_host = (None, None)
+        self.mid_fused = False
         # decoder-input extras concatenated to every z_k (GMVAE:3097-3132), as in the VAE engine
         self.number_of_batches = int(number_of_batches or 0)
         self.count_sum_feature = bool(count_sum_feature)

@@ -178,12 +178,29 @@ class TrainLoop:
                 K.gather_f32(src.batch_index, self.rows, p.batch_index)
             if eng.count_sum_feature:
                 K.gather_f32(src.count_sum_feature, self.rows, p.count_sum)
-        K.fill_normal(p.eps, self.seed, 0, eng.store.step)
+        if self._device_scalars(src):
+            p.eps_source = (self.seed, eng.store.step)      # drawn inside vae_mid_fwd
+        else:
+            p.eps_source = None
+            K.fill_normal(p.eps, self.seed, 0, eng.store.step)
         eng.train_step(p, self.R, self.S, lr, w)
+        p.eps_source = None
+
+    def _device_scalars(self, src):
+        """The step reads learning rate, warm-up weight and noise offset on the device."""
+        eng = self.engine
+        u16_ok = src.u16_ok if isinstance(src, ResidentCSR) else src["u16_ok"]
+        fn = getattr(eng, "step_on_device_scalars", None)
+        return bool(fn is not None and fn(self.plan, self.R, self.S, u16_ok))
 
     def step(self, src, lr, warm_up_weight=1.0):
         """Run one optimiser step on the minibatch described by ``src`` (+ ``self.rows``)."""
-        key = (id(src), float(lr), float(warm_up_weight))
+        eng = self.engine
+        if hasattr(eng, "set_step_scalars"):
+            eng.set_step_scalars(lr, warm_up_weight)       # read on the device by the step's kernels
+        # the learning rate always comes from the device; the warm-up weight too on the fused path,
+        # so one graph per minibatch source serves a whole warm-up schedule
+        key = (id(src), None if self._device_scalars(src) else float(warm_up_weight))
         if not self.use_graph:
             self._body(src, lr, warm_up_weight)
             return self.plan.bound
@@ -206,6 +223,8 @@ class TrainLoop:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._body(src, lr, warm_up_weight)
+                if hasattr(eng, "invalidate_shadows"):
+                    eng.invalidate_shadows()         # the snapshot restores the masters only
                 eng.store.param.copy_(snap[0])
                 eng.store.m.copy_(snap[1])
                 eng.store.v.copy_(snap[2])
@@ -215,5 +234,10 @@ class TrainLoop:
                     l.moving_var.copy_(mv)
                 graphs[key] = (g, src)   # keep src alive: its buffers are baked into the graph
             self._graph, self._graph_key = graphs[key][0], key
+        if getattr(eng, "_shadow_valid", True) is False and getattr(eng, "W16", None) is not None \
+                and getattr(eng, "world_size", 1) == 1:
+            # the captured step holds no shadow refresh (the optimiser kernel keeps the fp16 weight
+            # copies current): bring them up to date after an outside change of the parameters
+            eng._refresh_shadows(self.plan, self.plan.M)
         self._graph.replay()
         return self.plan.bound

@@ -126,6 +126,21 @@ def gemm(layout, M, N, K, A, B, C, accumulate=False, tensor_cores=True, workspac
                                       _ld(C), int(accumulate), _stream()), "gemm_f32")
 
 
+def gemm_f16_split(layout, M, N, K, A, B, X, which, C, accumulate=False, alpha=1.0, workspace=None):
+    """fp16 product with operand ``which`` (1 = A, 2 = B) completed by its rounding remainder X."""
+    lib = _lib.load()
+    ws_bytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
+    _lib.check(lib.scvae_gemm_f16_split(layout, M, N, K, _p(A), _ld(A), _p(B), _ld(B), _p(X), _ld(X),
+                                        int(which), _p(C), _ld(C), int(accumulate), float(alpha),
+                                        _p(workspace), ws_bytes, _stream()), "gemm_f16_split")
+
+
+def f32_to_f16_split(src, cols, hi, lo, scale=1.0):
+    lib = _lib.load()
+    _lib.check(lib.scvae_f32_to_f16_split(_p(src), _ld(src), src.shape[0], cols, _p(hi), _p(lo),
+                                          _ld(hi), float(scale), _stream()), "f32_to_f16_split")
+
+
 def gemm_f16(layout, M, N, K, A, B, C, accumulate=False, alpha=1.0, workspace=None):
     """fp16 operands (torch.float16 2-D row-major views), fp32 output."""
     lib = _lib.load()
@@ -338,17 +353,38 @@ def vae_bound(logp, kl_row, R, S, B, weight, out, go=None):
                                    _p(go), _stream()), "vae_bound")
 
 
+def shadow(lo, hi, src_ld, cols, hi16, lo16=None, src_block_rows=1 << 40, dst_block_rows=1 << 40):
+    """``scvae_shadow``: the fp32 block at flat offsets [lo, hi) (rows of src_ld floats) mirrored
+    into the half matrix ``hi16`` (+ remainder ``lo16``)."""
+    s = _lib.Shadow()
+    s.lo, s.hi, s.src_ld, s.dst_ld = int(lo), int(hi), int(src_ld), _ld(hi16)
+    s.src_block_rows, s.dst_block_rows = int(src_block_rows), int(dst_block_rows)
+    s.hi16, s.lo16, s.cols = _p(hi16), _p(lo16), int(cols)
+    return s
+
+
+def adam_clip_ctas(n):
+    return int(_lib.load().scvae_adam_clip_ctas(int(n)))
+
+
 def adam_clip_step(param, grad, m, v, step, lr, beta1=0.9, beta2=0.999, epsilon=1e-8, clip=1.0,
-                   grad_scale=1.0):
+                   grad_scale=1.0, scalars=None, shadows=None, advance_counter=None, advance_total=0):
     _f32(param, grad, m, v)
     lib = _lib.load()
+    arr, n_sh = None, 0
+    if shadows:
+        n_sh = len(shadows)
+        arr = (_lib.Shadow * n_sh)(*shadows)
     _lib.check(lib.scvae_adam_clip_step(_p(param), _p(grad), _p(m), _p(v), param.numel(),
                                         _p(step), float(lr), beta1, beta2, epsilon, clip,
-                                        float(grad_scale), _stream()), "adam_clip_step")
+                                        float(grad_scale), _p(scalars), arr, n_sh,
+                                        _p(advance_counter), int(advance_total), _stream()),
+               "adam_clip_step")
 
 
 def dp_reduce_adam(world, rank, grad_ptrs, param_ptrs, flag_ptrs, m, v, n, step, lr, beta1=0.9,
-                   beta2=0.999, epsilon=1e-8, clip=1.0, grad_scale=1.0, ctl=None, max_ctas=0):
+                   beta2=0.999, epsilon=1e-8, clip=1.0, grad_scale=1.0, ctl=None, max_ctas=0,
+                   scalars=None):
     """Fused reduce-scatter -> clip + Adam -> all-gather over peer memory (dp_exchange.cu).
     ``*_ptrs``: lists of ``world`` integer device addresses (peer-mapped), already offset to the
     start of the exchanged range; m, v: local tensors starting at the same offset."""
@@ -358,8 +394,8 @@ def dp_reduce_adam(world, rank, grad_ptrs, param_ptrs, flag_ptrs, m, v, n, step,
     arr = ctypes.c_void_p * world
     _lib.check(lib.scvae_dp_reduce_adam(world, rank, arr(*grad_ptrs), arr(*param_ptrs),
                                         arr(*flag_ptrs), _p(m), _p(v), int(n), _p(step), float(lr),
-                                        beta1, beta2, epsilon, clip, float(grad_scale), _p(ctl),
-                                        int(max_ctas), _stream()), "dp_reduce_adam")
+                                        beta1, beta2, epsilon, clip, float(grad_scale), _p(scalars),
+                                        _p(ctl), int(max_ctas), _stream()), "dp_reduce_adam")
 
 
 def step_advance(step):
@@ -432,3 +468,37 @@ def gmvae_z_mean(qh, y, K_, B, L, z_mean):
     lib = _lib.load()
     _lib.check(lib.scvae_gmvae_z_mean(_p(qh), _ld(qh), _p(y), K_, B, L, _p(z_mean), _stream()),
                "gmvae_z_mean")
+
+
+# ---- fused middle of the VAE step (csrc/mid_layers.cu) -------------------------------------------
+def mid_layer(w=None, dw=None, beta=None, dbeta=None, moving_mean=None, moving_var=None, mean=None,
+              rstd=None, y=None, n_in=0, k_in=0, n_out=0):
+    """``scvae_mid_layer`` from tensors (2-D row-major ``w`` / ``dw`` / ``y``)."""
+    l = _lib.MidLayer()
+    for name, t in (("w", w), ("dw", dw), ("beta", beta), ("dbeta", dbeta),
+                    ("moving_mean", moving_mean), ("moving_var", moving_var), ("mean", mean),
+                    ("rstd", rstd), ("y", y)):
+        setattr(l, name, _p(t))
+    l.ldw = _ld(w) if w is not None else 0
+    l.ldy = _ld(y) if y is not None else 0
+    l.n_in, l.k_in, l.n_out = int(n_in), int(k_in), int(n_out)
+    return l
+
+
+def mid_desc():
+    return _lib.MidDesc()
+
+
+def vae_mid_workspace_floats(desc):
+    import ctypes
+    return int(_lib.load().scvae_vae_mid_workspace_floats(ctypes.byref(desc)))
+
+
+def vae_mid_fwd(desc):
+    import ctypes
+    _lib.check(_lib.load().scvae_vae_mid_fwd(ctypes.byref(desc), _stream()), "vae_mid_fwd")
+
+
+def vae_mid_bwd(desc):
+    import ctypes
+    _lib.check(_lib.load().scvae_vae_mid_bwd(ctypes.byref(desc), _stream()), "vae_mid_bwd")

@@ -390,15 +390,27 @@ def col_mean(x, rows, cols, out):
     out[:cols] = x[:rows, :cols].double().mean(dim=0)
 
 
+def adam_clip_ctas(n):
+    return max(1, min((int(n) + 255) // 256, 148 * 16))
+
+
 def adam_clip_step(param, grad, m, v, step, lr, beta1=0.9, beta2=0.999, epsilon=1e-8, clip=1.0,
-                   grad_scale=1.0):
+                   grad_scale=1.0, scalars=None, shadows=None, advance_counter=None, advance_total=0):
     _log("adam_clip_step")
+    assert not shadows, "fp16 shadows belong to the tensor-core path"
+    if scalars is not None:
+        lr = lr * float(scalars[0])
     t = int(step.item()) + 1
     g = torch.clamp(grad.double() * grad_scale, -clip, clip)
     m.copy_(beta1 * m.double() + (1.0 - beta1) * g)
     v.copy_(beta2 * v.double() + (1.0 - beta2) * g * g)
     lr_t = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
     param.copy_(param.double() - lr_t * m.double() / (torch.sqrt(v.double()) + epsilon))
+    if advance_counter is not None:      # the last CTA of the launches sharing the counter advances
+        advance_counter += adam_clip_ctas(param.numel())
+        if int(advance_counter.item()) >= advance_total:
+            step += 1
+            advance_counter.zero_()
 
 
 def step_advance(step):

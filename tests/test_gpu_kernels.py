@@ -498,6 +498,55 @@ def test_adam_clip_step():
     assert torch.allclose(pd.cpu().double(), params["w/weights"], atol=1e-6, rtol=1e-5)
 
 
+def test_adam_clip_step_device_scalars_shadows_and_step_advance():
+    """The optimiser kernel with the learning rate on the device, fp16 weight shadows (a plain
+    block with rounding remainder and a head-style block with padded row groups) rewritten in the
+    same pass, and the step counter advanced by the last CTA of two launches sharing a counter."""
+    from scvae_b200 import kernels as K
+    torch.manual_seed(3)
+    dev = _dev()
+    rows1, ld1, cols1 = 20, 204, 201            # "first encoder weight": (20, 204), 201 valid columns
+    gn, gh, heads, ld2 = 36, 64, 2, 24          # "head weights": 2 blocks of 36 rows -> 64-row blocks
+    n1, n2 = rows1 * ld1, heads * gn * ld2
+    n = n1 + 8 + n2                             # 8 unshadowed floats in between
+    p = torch.randn(n)
+    params = {"w/weights": p.clone().double()}
+    state = O.AdamState(params)
+    pd, m, v = p.to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    step = torch.zeros(1, dtype=torch.int64, device=dev)
+    scalars = torch.tensor([2.0, 1.0], device=dev)
+    counter = torch.zeros(1, dtype=torch.int32, device=dev)
+    hi1 = torch.full((rows1, 208), 9.0, dtype=torch.float16, device=dev)
+    lo1 = torch.full((rows1, 208), 9.0, dtype=torch.float16, device=dev)
+    hi2 = torch.zeros(heads * gh, 128, dtype=torch.float16, device=dev)
+    cut = n1 + 8                                # second launch: the head block, on its own range
+    total = K.adam_clip_ctas(cut) + K.adam_clip_ctas(n - cut)
+    for it in range(3):
+        g = torch.randn(n) * (3.0 if it % 2 else 1e-3)
+        O.adam_clip_step(params, {"w/weights": g.double()}, state, 2e-3)
+        gd = g.to(dev)
+        K.adam_clip_step(pd[:cut], gd[:cut], m[:cut], v[:cut], step, 1e-3, scalars=scalars,
+                         shadows=[K.shadow(0, n1, ld1, cols1, hi1, lo1)], advance_counter=counter,
+                         advance_total=total)
+        assert int(step.item()) == it           # not advanced before the last launch of the step
+        K.adam_clip_step(pd[cut:], gd[cut:], m[cut:], v[cut:], step, 1e-3, scalars=scalars,
+                         shadows=[K.shadow(0, n2, ld2, ld2, hi2, None, src_block_rows=gn,
+                                           dst_block_rows=gh)], advance_counter=counter,
+                         advance_total=total)
+        assert int(step.item()) == it + 1 and int(counter.item()) == 0
+    assert torch.allclose(pd.cpu().double(), params["w/weights"], atol=1e-6, rtol=1e-5)
+    w1 = pd[:n1].view(rows1, ld1)
+    assert torch.equal(hi1[:, :cols1], w1[:, :cols1].half())
+    rec = hi1[:, :cols1].float() + lo1[:, :cols1].float()
+    assert (rec - w1[:, :cols1]).abs().max().item() <= 3e-7 * w1.abs().max().item()
+    assert torch.all(hi1[:, cols1:ld1] == 0) and torch.all(hi1[:, ld1:] == 9.0)
+    w2 = pd[cut:].view(heads, gn, ld2)
+    for h in range(heads):
+        assert torch.equal(hi2[h * gh:h * gh + gn, :ld2], w2[h].half())
+        assert torch.all(hi2[h * gh + gn:(h + 1) * gh] == 0)
+    assert torch.all(hi2[:, ld2:] == 0)
+
+
 def test_csr_densify():
     import scipy.sparse
     from scvae_b200 import kernels as K
@@ -686,3 +735,41 @@ def test_piecewise_categorical_likelihood(kind, k_max):
     assert torch.allclose(outs[0][:, :G].cpu().double(), mean, rtol=1e-4, atol=1e-5)
     assert torch.allclose(outs[1][:, :G].cpu().double(), (second - mean * mean).clamp(min=0).sqrt(),
                           rtol=2e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("layout,which,M,N,Kd", [(0, 2, 512, 100, 5000), (2, 1, 100, 5004, 1024),
+                                                  (0, 2, 4096, 100, 20001), (2, 1, 100, 20004, 4096)])
+def test_gemm_f16_split_operand(layout, which, M, N, Kd):
+    """One fp32 operand as fp16 + its fp16 rounding remainder (scvae_gemm_f16_split): the product
+    carries ~22 bits of that operand -- first encoder layer (weights split, NT) and its weight
+    gradient (dY split, TN, both operands MN-major, stream-K)."""
+    from scvae_b200 import kernels as K
+    gen = torch.Generator().manual_seed(layout * 7 + N)
+    A, B = _gemm_operands(layout, M, N, Kd, gen)
+    dev = _dev()
+    # the exact operand holds small integers (counts), the split one arbitrary fp32 values
+    exact, split = (A, B) if which == 2 else (B, A)
+    exact = torch.floor(exact.abs() * 3.0)
+
+    def pad16(t):
+        ld = (t.shape[1] + 7) & ~7
+        return torch.zeros(t.shape[0], ld, dtype=torch.float16, device=dev), ld
+    e16, _ = pad16(exact)
+    e16[:, :exact.shape[1]] = exact.half()
+    hi, _ = pad16(split)
+    lo = torch.zeros_like(hi)
+    src = torch.zeros(split.shape[0], (split.shape[1] + 3) & ~3, device=dev)
+    src[:, :split.shape[1]] = split.float()
+    K.f32_to_f16_split(src, split.shape[1], hi, lo, scale=4.0)
+    torch.cuda.synchronize()
+    rec = (hi.float() + lo.float())[:, :split.shape[1]].cpu().double() / 4.0
+    assert (rec - split.float().double()).abs().max().item() <= 2e-7 * split.abs().max().item()
+    A16, B16, X = (e16, hi, lo) if which == 2 else (hi, e16, lo)
+    Ad, Bd = (exact.double(), split.float().double()) if which == 2 else (split.float().double(), exact.double())
+    ref = _gemm_ref(layout, Ad, Bd)
+    C = torch.full((M, (N + 3) & ~3), 3.0, device=dev)
+    ws = torch.empty(max(K.gemm_f16_workspace_bytes(layout, M, N, Kd) // 4, 1), device=dev)
+    K.gemm_f16_split(layout, M, N, Kd, A16, B16, X, which, C, alpha=0.25, workspace=ws)
+    torch.cuda.synchronize()
+    err = (C[:, :N].cpu().double() - ref).abs().max().item()
+    assert err <= 1e-5 * ref.abs().max().item() + 1e-6 * math.sqrt(Kd), (layout, which, err, ref.abs().max().item())

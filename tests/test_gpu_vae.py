@@ -308,3 +308,95 @@ def test_vae_decoder_extras_and_linear_factor_architectures(case, tensor_cores):
         if k in grads:
             diff = diff * (grads[k].abs() > noise)
         assert diff.max().item() <= 1e-5 * max(v.abs().max().item(), 1.0) + (2e-3 if tensor_cores else 0), k
+
+
+MID_CASES = [
+    # name, G, L, hidden, likelihood, B, bn, engine/oracle options
+    ("one-layer", 256, 10, [64], "negative binomial", 128, True, {}),
+    ("ragged-slabs", 256, 10, [100], "poisson", 333, True, {}),
+    ("two-layers", 512, 7, [48, 24], "zero-inflated negative binomial", 200, True, {}),
+    ("three-layers-wide-latent", 256, 100, [96, 64, 127], "negative binomial", 150, True, {}),
+    ("no-batch-norm", 256, 6, [40], "zero-inflated poisson", 96, False, {}),
+    ("batch-correction-count-sum", 256, 6, [32, 16], "negative binomial", 130, True,
+     dict(number_of_batches=3, count_sum_feature=True)),
+    ("reference-default-minibatch", 1000, 10, [100], "negative binomial", 100, True, {}),
+]
+
+
+@pytest.mark.parametrize("case", MID_CASES, ids=[c[0] for c in MID_CASES])
+def test_fused_middle_training_step_matches_oracle(case):
+    """The 16-bit training step with the persistent middle kernels (vae_mid_fwd / vae_mid_bwd:
+    batch norm, ReLU, posterior clip + sample + KL fused behind exact-fp32 products) against the
+    oracle: bound terms, per-cell tensors, raw gradients, variables after clip + Adam."""
+    from scvae_b200.engine import VAEEngine
+    name, G, L, hidden, lik, B, bn, opts = case
+    cfg = O.VAEConfig(G, L, hidden, lik, "gaussian", 1, 1, bn, True, kl_weight=0.7, **opts)
+    params = O.vae_init_params(cfg, seed=3, dtype=torch.float64)
+    gen = torch.Generator().manual_seed(11)
+    for k in params:
+        if k.endswith("biases") or k.endswith("beta"):
+            params[k] = torch.randn(params[k].shape, generator=gen, dtype=torch.float64) * 0.1
+        if not bn and k.endswith("weights"):
+            params[k] = params[k] * 0.3
+    x, _ = O.synthetic_counts(B, G, n_types=3, seed=5, target_zero_fraction=0.8)
+    x = numpy.minimum(x, 500.0 if bn else 6.0)
+    eps = torch.randn(1, B, L, generator=gen, dtype=torch.float64)
+    features = {}
+    if opts.get("number_of_batches"):
+        features["batch_indices"] = torch.randint(0, opts["number_of_batches"], (B, 1), generator=gen)
+    if opts.get("count_sum_feature"):
+        cs = torch.tensor(x.sum(axis=1, keepdims=True), dtype=torch.float64)
+        features["count_sum_feature"] = cs / cs.max()
+    x64 = torch.tensor(x, dtype=torch.float64)
+    if bn:  # plausible moving statistics: the batch statistics of this batch, perturbed
+        upd = []
+        O.vae_forward(cfg, params, x64, x64, eps, True, bn_updates=upd, **features)
+        for scope, mean, var in upd:
+            params[scope + "/BATCH_NORM/moving_mean"] = mean[0] * 0.9
+            params[scope + "/BATCH_NORM/moving_variance"] = var[0] * 1.1
+    eng = VAEEngine(G, L, hidden, lik, "gaussian", bn, kl_weight=0.7, device="cuda:0",
+                    tensor_cores=True, **opts)
+    eng.import_parameters(params)
+    plan = eng._plan(B, 1)
+    eng.set_batch_dense(plan, torch.tensor(x).cuda())
+    if features:
+        eng.set_batch_features(
+            plan, features["batch_indices"].float().cuda() if "batch_indices" in features else None,
+            features["count_sum_feature"].float().cuda() if "count_sum_feature" in features else None)
+    plan.eps.copy_(eps.reshape(B, L).float())
+    w = 0.6
+    state = O.AdamState(params)
+    ref = {k: v.clone() for k, v in params.items()}
+    out, grads = O.train_step(cfg, ref, state, x64, x64, eps, 1e-3, warm_up_weight=w, **features)
+    bound = eng.train_step(plan, 1, 1, 1e-3, warm_up_weight=w).cpu().numpy()
+    torch.cuda.synchronize()
+    assert plan.fused_done and plan.mid_done, "the fused middle was not taken"
+    assert not eng.mid_error(plan)
+    for i, key in enumerate(["lower_bound", "lower_bound_weighted", "reconstruction_error",
+                             "kl_divergence"]):
+        r = out[key].item()
+        assert abs(bound[i] - r) <= 2e-4 * abs(r) + 1e-6, (key, bound[i], r)
+    # the middle is exact fp32: only the fp16 rounding of the first layer's weights reaches mu
+    assert _rel(plan.PH[:, :L].cpu(), out["q_z_mean"]) <= 5e-4
+    assert _rel(plan.logp.cpu(), out["log_p_x_given_z"].reshape(-1)) <= 2e-4
+    got = eng.export_gradients()
+    gmax = max(g.abs().max().item() for g in grads.values())
+    for k, g in grads.items():
+        err = (got[k].double() - g).abs().max().item()
+        assert err <= 1e-2 * g.abs().max().item() + 1e-4 * gmax, (k, err, g.abs().max().item())
+    new = eng.export_parameters()
+    noise = 3e-2 * gmax
+    for k, v in ref.items():
+        diff = (new[k].double() - v).abs()
+        if k in grads:
+            diff = diff * (grads[k].abs() > noise)
+        rtol = 1e-4 if "moving" in k else 1e-5
+        assert diff.max().item() <= rtol * max(v.abs().max().item(), 1.0), (k, diff.max().item())
+    # lean evaluation pass (moving statistics, forward-only heads) through the same middle kernel
+    ev = O.vae_forward(cfg, ref, x64, x64, eps, is_training=False, **features)
+    eng.forward(plan, False, 1, 1, 1.0, keep_heads=False)
+    torch.cuda.synchronize()
+    b = plan.bound.cpu().numpy()
+    assert abs(b[0] - ev["lower_bound"].item()) <= 1e-3 * abs(ev["lower_bound"].item())
+    assert abs(b[3] - ev["kl_divergence"].item()) <= 1e-3 * abs(ev["kl_divergence"].item()) + 1e-6
+    assert _rel(eng.kl_neurons(plan).cpu(), ev["kl_divergence_neurons"]) <= 1e-3
