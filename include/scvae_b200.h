@@ -458,6 +458,7 @@ typedef struct scvae_mid_desc {
     void *dy1_16; void *dy1_16_lo; int64_t lddy1; float *dy1; int64_t lddy1_f32;
     float go_scalar, dy1_scale, kl_weight; int reserved2; const float *scalars;
     float *workspace; int64_t workspace_floats; uint32_t *barrier; int *error;
+    long long *timeline;    /* development aid (nullable): [CTA][32] %globaltimer stamps of the phases */
 } scvae_mid_desc;
 int64_t scvae_vae_mid_workspace_floats(const scvae_mid_desc *desc /* [host] */);
 int scvae_vae_mid_fwd(const scvae_mid_desc *desc /* [host] */, void *stream);

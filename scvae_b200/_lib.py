@@ -55,7 +55,7 @@ class MidDesc(ctypes.Structure):
                 ("go_scalar", c_f32), ("dy1_scale", c_f32), ("kl_weight", c_f32),
                 ("reserved2", c_int), ("scalars", _c_fp),
                 ("workspace", _c_fp), ("workspace_floats", c_i64), ("barrier", _c_fp),
-                ("error", _c_fp)]
+                ("error", _c_fp), ("timeline", _c_fp)]
 
 
 class Shadow(ctypes.Structure):

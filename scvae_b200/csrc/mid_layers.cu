@@ -38,8 +38,8 @@ constexpr int kMidThreads = 256;
 constexpr int kMidCols = 128;       // widest activation held in shared memory
 constexpr int kMidRows = 64;        // most cells per CTA
 constexpr int kMidWP = 132;         // row pitch of the staged weight tile: 4 mod 32 (conflict-free 128-bit rows)
-constexpr int kMidWIt = kMidCols * (kMidCols / 4) / kMidThreads;   // most float4 of a weight tile per thread (16)
 constexpr int kMidSlots = 2 * SCVAE_MID_MAX_LAYERS;                // batch-normed layers (encoder + decoder)
+constexpr int kMidFoldIt = 20;                                      // CTAs per warp in a fold: grid <= 160
 constexpr long long kMidSpinLimit = 4000000000ll;   // ~2 s of clock64 ticks: bounded barrier wait
 
 typedef scvae_mid_layer MidLayer;
@@ -94,86 +94,105 @@ __device__ __forceinline__ void mid_grid_sync(unsigned *bar, int *err) {
     __syncthreads();
 }
 
+// development aid: phase time stamps (ns) of every CTA, written only when d.timeline is given
+__device__ __forceinline__ void mid_stamp(const MidDesc &d, int k) {
+    if (d.timeline && threadIdx.x == 0 && k < 32) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        d.timeline[(int64_t)blockIdx.x * 32 + k] = (long long)t;
+    }
+}
+
 __device__ __forceinline__ int mid_rows_of(int cta, int rows_per_cta, int B) {
     const int lo = cta * rows_per_cta;
     return max(0, min(rows_per_cta, B - lo));
 }
 
-// ---- batched slab access: one global round trip per slab -------------------------------------------
-// element i of a slab of `ncol` columns: column i % ncol of cell i / ncol (lanes along the column
-// index: coalesced global access).  SLAB_IT (a constexpr of the enclosing function) bounds the
-// elements per thread: 128 columns x pitch / 256 threads.
-#define MID_SLAB(total, ncol, v, LOAD)                                            \
-    float v[SLAB_IT];                                                             \
-    _Pragma("unroll") for (int it_ = 0; it_ < SLAB_IT; ++it_) {                   \
-        const int i = threadIdx.x + it_ * kMidThreads;                            \
-        const int col = i % (ncol), r = i / (ncol);                               \
-        (void)col; (void)r;                                                       \
-        v[it_] = (i < (total)) ? (LOAD) : 0.f;                                    \
-    }
-#define MID_SLAB_FOR(total, ncol, v, BODY)                                        \
-    _Pragma("unroll") for (int it_ = 0; it_ < SLAB_IT; ++it_) {                   \
-        const int i = threadIdx.x + it_ * kMidThreads;                            \
-        if (i < (total)) {                                                        \
-            const int col = i % (ncol), r = i / (ncol);                           \
-            const float x = v[it_];                                               \
-            (void)col; (void)r; (void)x;                                          \
-            BODY                                                                  \
-        }                                                                         \
-    }
+// ---- compact code first ------------------------------------------------------------------------------
+// These kernels run every phase ONCE: straight-line, fully unrolled code is fetched from memory at a
+// few bytes per cycle (the first version spent 60 % of its cycles in `no instruction` stalls), so
+// everything below is rolled loops over a division-free 2-D index space, shared helper functions
+// (not inlined), and asynchronous copies (cp.async) for every global -> shared transfer: all of a
+// phase's loads are in flight together without holding registers, and they can be issued ahead of a
+// grid barrier or another phase's arithmetic.
 template <int TM>
 struct MidTraits {
-    static constexpr int kSlabIt = kMidCols * (TM == 4 ? 36 : 68) / kMidThreads;   // 18 or 34
+    static constexpr int kSpan = TM * 8;          // rows covered by a product tile: 32 or 64
 };
 
-// ---- weight staging: sw[n][k] = W[row0 + n][k], n < N, k < round4(Kc), zeros beyond Kc ----------------
-// issue (loads into registers) and commit (stores to shared memory) are separate so that the loads can
-// be in flight across a barrier or another phase's arithmetic.
-struct WRegs {
-    float4 v[kMidWIt];
-};
-__device__ __forceinline__ void stage_w_issue(WRegs &w, const float *__restrict__ W, int64_t ldw, int row0, int N, int Kc) {
-    const int K4 = (Kc + 3) >> 2;
-#pragma unroll
-    for (int it = 0; it < kMidWIt; ++it) {
-        const int i = threadIdx.x + it * kMidThreads;
-        if (i < N * K4) {
-            const int n = i / K4, k = (i % K4) << 2;
-            w.v[it] = __ldg(reinterpret_cast<const float4 *>(W + (int64_t)(row0 + n) * ldw + k));   // ldw % 4 == 0
+__device__ __forceinline__ uint32_t mid_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// 4-byte asynchronous copy; !valid writes zero without touching global memory
+__device__ __forceinline__ void cp_async4(float *dst, const float *src, bool valid) {
+    const int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(mid_smem_u32(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float *dst, const float *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(mid_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// dst[col][r] <- src[r0 + r][col] for col < ncol, r < span; zero for cells beyond this CTA's.
+// Lanes run along the column index (coalesced global reads), warps along the cells.
+__device__ __noinline__ void slab_copy_async(const MidCtx &c, float *dst, const float *__restrict__ src, int64_t ld,
+                                             int ncol, int span) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < span; r += kMidThreads / 32) {
+        const bool valid = r < c.nr;
+        const float *row = src + (int64_t)(c.r0 + (valid ? r : 0)) * ld;
+        for (int col = lane; col < ncol; col += 32) cp_async4(dst + col * c.RP + r, row + col, valid);
+    }
+}
+// dst[col][r] = alpha * sum_s src_s[r0 + r][col] (s < nsplit slices, `slice` floats apart), fixed order
+__device__ __noinline__ void slab_sum(const MidCtx &c, float *dst, const float *__restrict__ src, int64_t ld, int ncol,
+                                      int span, int nsplit, int64_t slice, float alpha) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < span; r += kMidThreads / 32) {
+        const bool valid = r < c.nr;
+        const float *row = src + (int64_t)(c.r0 + (valid ? r : 0)) * ld;
+        for (int col = lane; col < ncol; col += 32) {
+            float v = 0.f;
+            if (valid) {
+#pragma unroll 4
+                for (int s = 0; s < nsplit; ++s) v += __ldcg(row + (int64_t)s * slice + col);
+            }
+            dst[col * c.RP + r] = v * alpha;
         }
     }
 }
-__device__ __forceinline__ void stage_w_commit(const MidCtx &c, const WRegs &w, int N, int Kc) {
-    const int K4 = (Kc + 3) >> 2;
-#pragma unroll
-    for (int it = 0; it < kMidWIt; ++it) {
-        const int i = threadIdx.x + it * kMidThreads;
-        if (i < N * K4) {
-            const int n = i / K4, k = (i % K4) << 2;
-            float4 v = w.v[it];
-            if (k + 1 >= Kc) v.y = 0.f;
-            if (k + 2 >= Kc) v.z = 0.f;
-            if (k + 3 >= Kc) v.w = 0.f;
-            *reinterpret_cast<float4 *>(c.sw + n * kMidWP + k) = v;
-        }
-    }
-}
-__device__ __forceinline__ void stage_w(const MidCtx &c, const float *__restrict__ W, int64_t ldw, int row0, int N, int Kc) {
-    WRegs w;
-    stage_w_issue(w, W, ldw, row0, N, Kc);
-    stage_w_commit(c, w, N, Kc);
+// HBM[r0 + r][col] <- src[col][r] (row-major copy of a shared activation, valid cells only)
+__device__ __noinline__ void slab_store(const MidCtx &c, const float *src, float *__restrict__ dst, int64_t ld, int ncol) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < c.nr; r += kMidThreads / 32)
+        for (int col = lane; col < ncol; col += 32) dst[(int64_t)(c.r0 + r) * ld + col] = src[col * c.RP + r];
 }
 
-// ---- forward product tile: acc[i][j] = sum_k A[k][ty TM + i] * sw[tx + 32 j][k] ---------------------
-// (weights in their natural (out, in) layout; the 8 lanes of a 128-bit phase read 8 consecutive rows of
-// sw, 4 mod 32 floats apart: conflict free).  A must be finite (zero) on the rows [K, round4(K)).
+// ---- weight staging: sw[n][k] = W[row0 + n][k], n < N, k < round4(Kc) (natural layout, async) ---------
+// (columns beyond the reduction length are zero in the stored weights -- forward -- or unused -- dgrad)
+__device__ __noinline__ void stage_w_async(const MidCtx &c, const float *__restrict__ W, int64_t ldw, int row0, int N, int Kc) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K4 = (Kc + 3) >> 2;
+    for (int n = warp; n < N; n += kMidThreads / 32)
+        for (int k4 = lane; k4 < K4; k4 += 32)
+            cp_async16(c.sw + n * kMidWP + 4 * k4, W + (int64_t)(row0 + n) * ldw + 4 * k4);   // ldw % 4 == 0
+}
+
+// ---- forward product: C[n][r] = sum_k A[k][r] * sw[n][k], n < N; optional HBM copy Y[r0 + r][n] -------
+// thread (ty = warp, tx = lane): rows ty TM + i, columns tx + 32 j.  The 8 lanes of a 128-bit phase
+// read 8 consecutive rows of sw, 4 mod 32 floats apart: conflict free.  A must be finite (zero) on
+// the rows [K, round4(K)).
 template <int TM>
-__device__ __forceinline__ void mm_fwd(const float *__restrict__ A, int RP, const float *__restrict__ sw, int K, int N,
-                                       float (&acc)[TM][4]) {
+__device__ __noinline__ void mid_product(const MidCtx &c, const float *__restrict__ A, int K, float *__restrict__ C, int N,
+                                         float *__restrict__ Y, int64_t ldy) {
     const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
     const float *a = A + ty * TM;
+    const float *sw = c.sw;
     const int K4 = (K + 3) & ~3;
-#pragma unroll 2
+    float acc[TM][4];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
     for (int k = 0; k < K4; k += 4) {
         float4 wv[4];
 #pragma unroll
@@ -185,7 +204,7 @@ __device__ __forceinline__ void mm_fwd(const float *__restrict__ A, int RP, cons
             float av[TM];
 #pragma unroll
             for (int i = 0; i < TM; i += 4) {
-                const float4 t = *reinterpret_cast<const float4 *>(a + (k + kk) * RP + i);
+                const float4 t = *reinterpret_cast<const float4 *>(a + (k + kk) * c.RP + i);
                 av[i] = t.x; av[i + 1] = t.y; av[i + 2] = t.z; av[i + 3] = t.w;
             }
 #pragma unroll
@@ -196,13 +215,6 @@ __device__ __forceinline__ void mm_fwd(const float *__restrict__ A, int RP, cons
             }
         }
     }
-}
-// acc -> C[n][r] (shared, column-major) and, when Y is given, -> Y[r0 + r][n] (HBM, row-major);
-// column n of thread (ty, tx), slot j is tx + 32 j.
-template <int TM>
-__device__ __forceinline__ void mm_fwd_store(const MidCtx &c, float *__restrict__ C, int N, const float (&acc)[TM][4],
-                                             float *__restrict__ Y, int64_t ldy) {
-    const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int n = tx + 32 * j;
@@ -219,50 +231,54 @@ __device__ __forceinline__ void mm_fwd_store(const MidCtx &c, float *__restrict_
         }
     }
 }
-// C[n][r] = sum_k A[k][r] W[n][k] for the staged weights (shared -> shared [+ HBM]).
-template <int TM>
-__device__ __forceinline__ void mid_product(const MidCtx &c, const float *A, int K, float *C, int N, float *Y, int64_t ldy) {
-    float acc[TM][4] = {};
-    mm_fwd<TM>(A, c.RP, c.sw, K, N, acc);
-    mm_fwd_store<TM>(c, C, N, acc, Y, ldy);
-}
 
-// ---- dgrad product tile: acc[i][j] += sum_n G[n][ty TM + i] * sw[n][tx 4 + j] -----------------------
+// ---- dgrad product: Out[k][r] (+)= sum_{n < Nred} G[n][r] * sw[n][k], k < Kout -------------------------
+// thread (ty, tx): rows ty TM + i, columns tx 4 + j.  first: overwrite, else accumulate into Out.
 template <int TM>
-__device__ __forceinline__ void mm_dgrad(const float *__restrict__ G, int RP, const float *__restrict__ sw, int Nred,
-                                         float (&acc)[TM][4]) {
+__device__ __noinline__ void mid_dgrad_tile(const MidCtx &c, const float *__restrict__ G, int Nred, float *__restrict__ Out,
+                                            int Kout, bool first) {
     const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
     const float *a = G + ty * TM;
-    const float *w = sw + tx * 4;
-#pragma unroll 4
-    for (int n = 0; n < Nred; ++n) {
-        const float4 wv = *reinterpret_cast<const float4 *>(w + n * kMidWP);
-        float av[TM];
+    const float *w = c.sw + tx * 4;
+    float acc[TM][4];
 #pragma unroll
-        for (int i = 0; i < TM; i += 4) {
-            const float4 t = *reinterpret_cast<const float4 *>(a + n * RP + i);
-            av[i] = t.x; av[i + 1] = t.y; av[i + 2] = t.z; av[i + 3] = t.w;
-        }
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-            acc[i][0] = fmaf(av[i], wv.x, acc[i][0]);
-            acc[i][1] = fmaf(av[i], wv.y, acc[i][1]);
-            acc[i][2] = fmaf(av[i], wv.z, acc[i][2]);
-            acc[i][3] = fmaf(av[i], wv.w, acc[i][3]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    if (tx * 4 < Kout) {
+#pragma unroll 2
+        for (int n = 0; n < Nred; ++n) {
+            const float4 wv = *reinterpret_cast<const float4 *>(w + n * kMidWP);
+            float av[TM];
+#pragma unroll
+            for (int i = 0; i < TM; i += 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(a + n * c.RP + i);
+                av[i] = t.x; av[i + 1] = t.y; av[i + 2] = t.z; av[i + 3] = t.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i) {
+                acc[i][0] = fmaf(av[i], wv.x, acc[i][0]);
+                acc[i][1] = fmaf(av[i], wv.y, acc[i][1]);
+                acc[i][2] = fmaf(av[i], wv.z, acc[i][2]);
+                acc[i][3] = fmaf(av[i], wv.w, acc[i][3]);
+            }
         }
     }
-}
-template <int TM>
-__device__ __forceinline__ void mm_dgrad_store(const MidCtx &c, float *__restrict__ C, int Kout, const float (&acc)[TM][4]) {
-    const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+    __syncthreads();            // every thread is done reading G before Out (which may alias it) is written
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int k = tx * 4 + j;
         if (k < Kout) {
 #pragma unroll
-            for (int i = 0; i < TM; i += 4)
-                *reinterpret_cast<float4 *>(C + k * c.RP + ty * TM + i) =
-                    make_float4(acc[i][j], acc[i + 1][j], acc[i + 2][j], acc[i + 3][j]);
+            for (int i = 0; i < TM; i += 4) {
+                float4 *dst = reinterpret_cast<float4 *>(Out + k * c.RP + ty * TM + i);
+                float4 v = make_float4(acc[i][j], acc[i + 1][j], acc[i + 2][j], acc[i + 3][j]);
+                if (!first) {
+                    const float4 o = *dst;
+                    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                }
+                *dst = v;
+            }
         }
     }
 }
@@ -270,118 +286,151 @@ __device__ __forceinline__ void mm_dgrad_store(const MidCtx &c, float *__restric
 // ---- weight-gradient partial of this CTA: out[n][k] = sum_{r < nr} G[n][r] * I[k][r] ----------
 // thread (ty, tx) of a 16 x 16 grid owns n = ty + 16 i, k = tx + 16 j.  out: (N, Kp) row-major
 // in the workspace (Kp = padded input width = leading dimension of the weight).
-__device__ __noinline__ void mid_wgrad(const MidCtx &c, const float *__restrict__ G, int N, const float *__restrict__ I,
-                                       int Kp, float *__restrict__ out) {
+template <int NJ>
+__device__ __noinline__ void mid_wgrad_t(const MidCtx &c, const float *__restrict__ G, int N, const float *__restrict__ I,
+                                         int Kp, float *__restrict__ out) {
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     const int ni = (N - ty + 15) >> 4, kj = (Kp - tx + 15) >> 4;    // valid i / j counts
-    float acc[8][8];
+    float acc[8][NJ];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
     for (int r = 0; r < c.nr4; r += 4) {
-        float4 g[8], x[8];
+        float4 g[8], x[NJ];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             g[i] = i < ni ? *reinterpret_cast<const float4 *>(G + (ty + 16 * i) * c.RP + r) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < NJ; ++j)
             x[j] = j < kj ? *reinterpret_cast<const float4 *>(I + (tx + 16 * j) * c.RP + r) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < NJ; ++j)
                 acc[i][j] = fmaf(g[i].x, x[j].x, fmaf(g[i].y, x[j].y, fmaf(g[i].z, x[j].z, fmaf(g[i].w, x[j].w, acc[i][j]))));
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < NJ; ++j)
             if (i < ni && j < kj) out[(int64_t)(ty + 16 * i) * Kp + tx + 16 * j] = acc[i][j];
 }
-
-__device__ __forceinline__ void zero_cols(const MidCtx &c, float *dst, int col0, int col1) {
-    for (int i = col0 * c.RP + threadIdx.x; i < col1 * c.RP; i += kMidThreads) dst[i] = 0.f;
+__device__ __forceinline__ void mid_wgrad(const MidCtx &c, const float *G, int N, const float *I, int Kp, float *out) {
+    if (Kp <= 64) mid_wgrad_t<4>(c, G, N, I, Kp, out);      // narrow inputs (the latent sample): half the tile
+    else mid_wgrad_t<8>(c, G, N, I, Kp, out);
 }
+
 // augmented ones column (valid cells only) at `col`, zero columns behind it up to `col_end`
-__device__ __forceinline__ void set_aug_cols(const MidCtx &c, float *dst, int col, int col_end) {
-    for (int i = col * c.RP + threadIdx.x; i < col_end * c.RP; i += kMidThreads)
-        dst[i] = (i < (col + 1) * c.RP && i - col * c.RP < c.nr) ? 1.f : 0.f;
-}
-
-__device__ __forceinline__ void chan_merge2(float &cnt, float &mu, float &m2, float nb, float mb, float qb) {
-    const float tot = cnt + nb;
-    if (tot > 0.f) {
-        const float delta = mb - mu;
-        const float f = nb / tot;
-        mu += delta * f;
-        m2 += qb + delta * delta * (cnt * f);
-        cnt = tot;
-    }
+__device__ __noinline__ void set_aug_cols(const MidCtx &c, float *dst, int col, int col_end, int span) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int cc = col + warp; cc < col_end; cc += kMidThreads / 32)
+        for (int r = lane; r < span; r += 32) dst[cc * c.RP + r] = (cc == col && r < c.nr) ? 1.f : 0.f;
 }
 
 // Per-CTA partial statistics of Y[c][r] (columns < N over this CTA's cells): (mean, M2) -> workspace.
-__device__ __forceinline__ void mid_bn_partial(const MidCtx &c, const float *Y, int N, float *ws_stat) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int col = warp; col < N; col += kMidThreads / 32) {
-        float s = 0.f;
-        for (int r = lane; r < c.nr; r += 32) s += Y[col * c.RP + r];
-        s = warp_sum(s);
-        const float mean = c.nr > 0 ? s / (float)c.nr : 0.f;
-        float q = 0.f;
-        for (int r = lane; r < c.nr; r += 32) {
-            const float dv = Y[col * c.RP + r] - mean;
-            q += dv * dv;
-        }
-        q = warp_sum(q);
-        if (lane == 0) {
-            ws_stat[((int64_t)blockIdx.x * 2 + 0) * kMidCols + col] = mean;
-            ws_stat[((int64_t)blockIdx.x * 2 + 1) * kMidCols + col] = q;
+// One thread per (column, half of the cells); the two halves meet in shared memory in fixed order.
+__device__ __noinline__ void mid_bn_partial(const MidCtx &c, const float *Y, int N, float *ws_stat) {
+    // one pass: sums of (y - pivot) and (y - pivot)^2 with the column's first cell as the pivot (a
+    // value within the spread of the data, so neither sum cancels): mean = pivot + s1 / n,
+    // M2 = s2 - s1^2 / n
+    const int col = threadIdx.x & (kMidCols - 1), half = threadIdx.x >> 7;
+    const int h0 = half ? (c.nr >> 1) : 0, h1 = half ? c.nr : (c.nr >> 1);
+    float *x = c.stat + 4 * kMidCols;        // [2 halves][2][128]
+    float s1 = 0.f, s2 = 0.f;
+    const float pivot = col < N ? Y[col * c.RP] : 0.f;
+    if (col < N) {
+#pragma unroll 4
+        for (int r = h0; r < h1; ++r) {
+            const float dv = Y[col * c.RP + r] - pivot;
+            s1 += dv;
+            s2 = fmaf(dv, dv, s2);
         }
     }
+    x[(half * 2 + 0) * kMidCols + col] = s1;
+    x[(half * 2 + 1) * kMidCols + col] = s2;
+    __syncthreads();
+    if (half == 0 && col < N) {
+        const float t1 = x[col] + x[2 * kMidCols + col], t2 = x[kMidCols + col] + x[3 * kMidCols + col];
+        const float inv_n = c.nr > 0 ? 1.f / (float)c.nr : 0.f;
+        ws_stat[((int64_t)blockIdx.x * 2 + 0) * kMidCols + col] = pivot + t1 * inv_n;
+        ws_stat[((int64_t)blockIdx.x * 2 + 1) * kMidCols + col] = fmaxf(t2 - t1 * t1 * inv_n, 0.f);
+    }
 }
-// Every CTA folds all partials in the same fixed order: warp w takes the CTAs k = w mod 8 (4 columns
-// per lane, their loads independent and batched: the fold costs ~2 L2 round trips, not one per
-// partial), then the 8 per-warp results in warp order.  `scratch`: [8 warps][3][128] floats of idle
-// shared memory.  Result: s_mean / s_rstd [N]; CTA 0 writes the saved statistics and moving averages.
-__device__ __forceinline__ void mid_bn_fold(const MidCtx &c, const MidDesc &d, const MidLayer &l, const float *ws_stat,
-                                            float *scratch, float *s_mean, float *s_rstd) {
+// Every CTA folds all partials in the same fixed order.  With n_k cells, mean m_k and M2 q_k per CTA:
+//   mean = sum n_k m_k / B,   M2 = sum q_k + sum n_k (m_k - mean)^2     (exact, no cancellation),
+// each as plain sums: warp w takes the CTAs k = w mod 8 for 4 columns per lane, then the 8 per-warp
+// sums are added in warp order.  `scratch`: [8 warps][128] floats of idle shared memory.  Result:
+// s_mean / s_rstd [N]; CTA 0 writes the saved statistics and the moving averages.
+__device__ __noinline__ void mid_bn_fold(const MidCtx &c, const MidDesc &d, const MidLayer &l, const float *ws_stat,
+                                         float *scratch, float *s_mean, float *s_rstd) {
     const int N = l.n_out;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x;
-    float cnt[4] = {0.f, 0.f, 0.f, 0.f}, mu[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 10
-    for (int k = warp; k < G; k += kMidThreads / 32) {
-        const float nb = (float)mid_rows_of(k, d.rows_per_cta, d.B);
-        float mb[4], qb[4];
+    const float inv_b = 1.f / (float)d.B;
+    // (all loads of a pass are issued before the first use: the fold costs two L2 round trips)
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float mb[kMidFoldIt][4];
+#pragma unroll
+    for (int it = 0; it < kMidFoldIt; ++it) {
+        const int k = warp + it * (kMidThreads / 32);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int col = lane + 32 * q;
-            mb[q] = col < N ? __ldcg(ws_stat + ((int64_t)k * 2 + 0) * kMidCols + col) : 0.f;
-            qb[q] = col < N ? __ldcg(ws_stat + ((int64_t)k * 2 + 1) * kMidCols + col) : 0.f;
+            mb[it][q] = (k < G && col < N) ? __ldcg(ws_stat + ((int64_t)k * 2 + 0) * kMidCols + col) : 0.f;
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) chan_merge2(cnt[q], mu[q], m2[q], nb, mb[q], qb[q]);
     }
-    float *x = scratch;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        x[(warp * 3 + 0) * kMidCols + lane + 32 * q] = cnt[q];
-        x[(warp * 3 + 1) * kMidCols + lane + 32 * q] = mu[q];
-        x[(warp * 3 + 2) * kMidCols + lane + 32 * q] = m2[q];
+    for (int it = 0; it < kMidFoldIt; ++it) {
+        const int k = warp + it * (kMidThreads / 32);
+        const float nb = (float)mid_rows_of(k, d.rows_per_cta, d.B);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = fmaf(nb, mb[it][q], acc[q]);
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) scratch[warp * kMidCols + lane + 32 * q] = acc[q];
+    __syncthreads();
+    if (threadIdx.x < kMidCols) {
+        float m = 0.f;
+        for (int w = 0; w < kMidThreads / 32; ++w) m += scratch[w * kMidCols + threadIdx.x];
+        s_mean[threadIdx.x] = m * inv_b;
+    }
+    __syncthreads();
+    float qb[kMidFoldIt][4];
+#pragma unroll
+    for (int it = 0; it < kMidFoldIt; ++it) {
+        const int k = warp + it * (kMidThreads / 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int col = lane + 32 * q;
+            qb[it][q] = (k < G && col < N) ? __ldcg(ws_stat + ((int64_t)k * 2 + 1) * kMidCols + col) : 0.f;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = 0.f;
+#pragma unroll
+    for (int it = 0; it < kMidFoldIt; ++it) {
+        const int k = warp + it * (kMidThreads / 32);
+        const float nb = (float)mid_rows_of(k, d.rows_per_cta, d.B);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float dm = mb[it][q] - s_mean[lane + 32 * q];
+            acc[q] += qb[it][q] + nb * dm * dm;          // (nb == 0 beyond the grid)
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) scratch[warp * kMidCols + lane + 32 * q] = acc[q];
     __syncthreads();
     const int col = threadIdx.x;
     if (col < N) {
-        float cn = 0.f, mean_all = 0.f, q_all = 0.f;
-        for (int w = 0; w < kMidThreads / 32; ++w)
-            chan_merge2(cn, mean_all, q_all, x[(w * 3 + 0) * kMidCols + col], x[(w * 3 + 1) * kMidCols + col],
-                        x[(w * 3 + 2) * kMidCols + col]);
-        const float var = cn > 0.f ? q_all / cn : 0.f;
+        float q_all = 0.f;
+        for (int w = 0; w < kMidThreads / 32; ++w) q_all += scratch[w * kMidCols + col];
+        const float var = q_all * inv_b;
         const float rstd = rsqrtf(var + kBnEps);
-        s_mean[col] = mean_all;
         s_rstd[col] = rstd;
         if (blockIdx.x == 0) {
+            const float mean_all = s_mean[col];
             l.mean[col] = mean_all;
             l.rstd[col] = rstd;
             if (d.update_moving) {      // Bessel-corrected variance (tf fused batch norm)
@@ -394,17 +443,31 @@ __device__ __forceinline__ void mid_bn_fold(const MidCtx &c, const MidDesc &d, c
     __syncthreads();
 }
 
-__device__ __forceinline__ void mid_setup(MidCtx &c, const MidDesc &d, float *smem) {
-    const int rows = d.rows_per_cta;
-    c.RP = mid_pitch(rows);
-    for (int b = 0; b < 4; ++b) c.act[b] = smem + b * kMidCols * c.RP;
-    c.sw = c.act[3] + kMidCols * c.RP;
-    c.stat = c.sw + kMidCols * kMidWP;
-    c.bnv = c.stat + 8 * kMidCols;
-    c.red = c.bnv + kMidSlots * 3 * kMidCols;
-    c.r0 = blockIdx.x * rows;
-    c.nr = mid_rows_of(blockIdx.x, rows, d.B);
-    c.nr4 = (c.nr + 3) & ~3;
+// The descriptor (1.3 KB of kernel parameters) and the context are copied into SHARED memory once per
+// CTA: the helper functions take them by reference, and a reference to a kernel parameter would make
+// every thread spill the whole structure to local memory at kernel entry (53 MB of traffic per launch).
+struct MidShared {
+    MidDesc d;
+    MidCtx c;
+};
+__device__ __forceinline__ void mid_setup(MidShared &sh, const MidDesc &param, float *smem) {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(&param);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.d);
+    for (int i = threadIdx.x; i < (int)(sizeof(MidDesc) / 4); i += kMidThreads) dst[i] = src[i];
+    if (threadIdx.x == 0) {
+        MidCtx &c = sh.c;
+        const int rows = param.rows_per_cta;
+        c.RP = mid_pitch(rows);
+        for (int b = 0; b < 4; ++b) c.act[b] = smem + b * kMidCols * c.RP;
+        c.sw = c.act[3] + kMidCols * c.RP;
+        c.stat = c.sw + kMidCols * kMidWP;
+        c.bnv = c.stat + 8 * kMidCols;
+        c.red = c.bnv + kMidSlots * 3 * kMidCols;
+        c.r0 = blockIdx.x * rows;
+        c.nr = mid_rows_of(blockIdx.x, rows, param.B);
+        c.nr4 = (c.nr + 3) & ~3;
+    }
+    __syncthreads();
 }
 
 // workspace map (floats): [BN slots][grid][2][128] | [grid][4] bound partials | dW partials
@@ -424,25 +487,47 @@ __device__ __forceinline__ float *bnv_beta(const MidCtx &c, int s) { return c.bn
 // Normalisation vectors of every layer -> shared memory.  mode 0: beta only (training forward: the
 // batch statistics follow from the folds), 1: + moving statistics (evaluation), 2: + saved batch
 // statistics (backward).  Layers without batch norm get (0, 1, 0): the identity.
-__device__ __forceinline__ void mid_load_bnv(const MidCtx &c, const MidDesc &d, int mode) {
+__device__ __noinline__ void mid_load_bnv(const MidCtx &c, const MidDesc &d, int mode) {
     const int nl = d.n_enc + d.n_dec;
-    for (int i = threadIdx.x; i < nl * kMidCols; i += kMidThreads) {
-        const int s = i / kMidCols, col = i % kMidCols;
+    for (int s = 0; s < nl; ++s) {
         const MidLayer &l = s < d.n_enc ? d.enc[s] : d.dec[s - d.n_enc];
-        float mean = 0.f, rstd = 1.f, beta = 0.f;
-        if (l.beta && col < l.n_out) {
-            beta = l.beta[col];
-            if (mode == 1) {
-                mean = l.moving_mean[col];
-                rstd = rsqrtf(l.moving_var[col] + kBnEps);
-            } else if (mode == 2) {
-                mean = l.mean[col];
-                rstd = l.rstd[col];
+        for (int col = threadIdx.x; col < kMidCols; col += kMidThreads) {
+            float mean = 0.f, rstd = 1.f, beta = 0.f;
+            if (l.beta && col < l.n_out) {
+                beta = l.beta[col];
+                if (mode == 1) {
+                    mean = l.moving_mean[col];
+                    rstd = rsqrtf(l.moving_var[col] + kBnEps);
+                } else if (mode == 2) {
+                    mean = l.mean[col];
+                    rstd = l.rstd[col];
+                }
             }
+            bnv_mean(c, s)[col] = mean;
+            bnv_rstd(c, s)[col] = rstd;
+            bnv_beta(c, s)[col] = beta;
         }
-        bnv_mean(c, s)[col] = mean;
-        bnv_rstd(c, s)[col] = rstd;
-        bnv_beta(c, s)[col] = beta;
+    }
+}
+
+// H[c][r] = relu((Y[c][r] - mean) rstd + beta) for valid cells, 0 otherwise; X (nullable) = xhat.
+// (lanes along the cells: conflict-free shared-memory access)
+__device__ __noinline__ void mid_normalise(const MidCtx &c, int slot, int N, int span, const float *Y, float *X, float *H) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float *m = bnv_mean(c, slot), *rs = bnv_rstd(c, slot), *bt = bnv_beta(c, slot);
+#pragma unroll 4
+    for (int col = warp; col < N; col += kMidThreads / 32) {
+        const float mean = m[col], rstd = rs[col], beta = bt[col];
+        for (int r = lane; r < span; r += 32) {
+            const int i = col * c.RP + r;
+            float xh = 0.f, h = 0.f;
+            if (r < c.nr) {
+                xh = (Y[i] - mean) * rstd;
+                h = fmaxf(xh + beta, 0.f);
+            }
+            if (X) X[i] = xh;
+            if (H) H[i] = h;
+        }
     }
 }
 
@@ -451,34 +536,34 @@ __device__ __forceinline__ void mid_load_bnv(const MidCtx &c, const MidDesc &d, 
 // =============================================================================================
 // One layer's normalisation + ReLU on Y (shared) -> H (shared), batch statistics through the grid
 // barrier (H doubles as the scratch of the fold: it is written only afterwards).
-__device__ __forceinline__ void mid_fwd_bn_relu(const MidCtx &c, const MidDesc &d, const MidLayer &l, int slot,
-                                                const float *Y, float *H, bool training, int aug_end) {
+__device__ __noinline__ void mid_fwd_bn_relu(const MidCtx &c, const MidDesc &d, const MidLayer &l, int slot, const float *Y,
+                                             float *H, bool training, int span) {
     const int N = l.n_out;
-    float *s_mean = bnv_mean(c, slot), *s_rstd = bnv_rstd(c, slot), *s_beta = bnv_beta(c, slot);
     if (l.beta && training) {
         mid_bn_partial(c, Y, N, ws_stat_slot(d, slot));
+        mid_stamp(d, slot == 0 ? 2 : 10);
         mid_grid_sync(d.barrier, d.error);
-        mid_bn_fold(c, d, l, ws_stat_slot(d, slot), H, s_mean, s_rstd);
+        mid_stamp(d, slot == 0 ? 3 : 11);
+        mid_bn_fold(c, d, l, ws_stat_slot(d, slot), H, bnv_mean(c, slot), bnv_rstd(c, slot));
+        mid_stamp(d, slot == 0 ? 4 : 12);
     }
-    for (int i = threadIdx.x; i < N * c.RP; i += kMidThreads) {
-        const int col = i / c.RP, r = i - col * c.RP;
-        float v = 0.f;
-        if (r < c.nr) v = fmaxf((Y[i] - s_mean[col]) * s_rstd[col] + s_beta[col], 0.f);
-        H[i] = v;
-    }
-    set_aug_cols(c, H, N, aug_end);
+    mid_normalise(c, slot, N, span, Y, nullptr, H);
+    set_aug_cols(c, H, N, (N + 1 + 3) & ~3, span);
 }
 
 template <int TM>
-__global__ void __launch_bounds__(kMidThreads, 1) vae_mid_fwd_kernel(const MidDesc d) {
-    constexpr int SLAB_IT = MidTraits<TM>::kSlabIt;
+__global__ void __launch_bounds__(kMidThreads, 1) vae_mid_fwd_kernel(const __grid_constant__ MidDesc param) {
+    constexpr int SPAN = MidTraits<TM>::kSpan;
     extern __shared__ __align__(16) float mid_smem[];
-    MidCtx c;
-    mid_setup(c, d, mid_smem);
+    __shared__ MidShared sh;
+    mid_setup(sh, param, mid_smem);
+    const MidDesc &d = sh.d;
+    const MidCtx &c = sh.c;
     const bool training = d.training != 0;
     const int L = d.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *E = c.act[3];       // noise slab [l][r]
+    mid_stamp(d, 0);
 
     // ---- prologue: every load that depends on no other CTA, in ONE round trip ------------------------
     // first-layer pre-activations (the tensor-core product's split-K partials, folded in fixed order:
@@ -486,66 +571,59 @@ __global__ void __launch_bounds__(kMidThreads, 1) vae_mid_fwd_kernel(const MidDe
     // weights of the first product of this kernel.
     const MidLayer &l0 = d.enc[0];
     const int N0 = l0.n_out;
+    // posterior heads: one product for [mu | log_sigma] when both fit the 128-column tile
+    const int post_parts = (2 * L <= kMidCols) ? 1 : 2;
+    const int NP = post_parts == 1 ? 2 * L : L;
     const MidLayer &first = d.n_enc > 1 ? d.enc[1] : d.post;
-    const int firstN = d.n_enc > 1 ? first.n_out : L;
-    WRegs wr;
-    stage_w_issue(wr, first.w, first.ldw, 0, firstN, first.k_in);
-    mid_load_bnv(c, d, training ? 0 : 1);
+    const int firstN = d.n_enc > 1 ? first.n_out : NP;
+    stage_w_async(c, first.w, first.ldw, 0, firstN, first.k_in);
     const bool use_eps = !d.deterministic;
+    if (use_eps && !d.generate_eps) slab_copy_async(c, E, d.eps, L, L, SPAN);
+    if (d.y1_nsplit == 1 && d.y1_alpha == 1.f) slab_copy_async(c, c.act[1], d.y1_parts, d.y1_ld, N0, SPAN);
+    else slab_sum(c, c.act[1], d.y1_parts, d.y1_ld, N0, SPAN, d.y1_nsplit, d.y1_slice, d.y1_alpha);
+    mid_load_bnv(c, d, training ? 0 : 1);
     if (use_eps && d.generate_eps) {
         uint64_t offset = d.offset;
         if (d.offset_dev) offset += (uint64_t)(*d.offset_dev);
-        const int64_t e0 = (int64_t)c.r0 * L, e1 = (int64_t)(c.r0 + c.nr) * L;
-        for (int64_t q = (e0 >> 2) + threadIdx.x; q * 4 < e1; q += kMidThreads) {
+        const int64_t e0 = (int64_t)c.r0 * L;
+        const int n_el = c.nr * L;                    // elements of this CTA's cells
+        const int lead = (int)(e0 & 3);               // offset of the first one inside its Philox quad
+        for (int q = threadIdx.x; q * 4 < n_el + lead; q += kMidThreads) {
             curandStatePhilox4_32_10_t st;            // same stream as scvae_fill_normal
-            curand_init(d.seed, (unsigned long long)q, 4ull * offset, &st);
+            curand_init(d.seed, (unsigned long long)((e0 >> 2) + q), 4ull * offset, &st);
             const float4 v = curand_normal4(&st);
             const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int64_t e = q * 4 + j;
-                if (e >= e0 && e < e1) {
-                    d.eps[e] = vv[j];
-                    E[(int)((e - e0) % L) * c.RP + (int)((e - e0) / L)] = vv[j];
+                const int e = q * 4 + j - lead;       // element index relative to the CTA's first
+                if (e >= 0 && e < n_el) {
+                    const int r = e / L;
+                    d.eps[e0 + e] = vv[j];
+                    E[(e - r * L) * c.RP + r] = vv[j];
                 }
             }
         }
     }
-    {
-        float *Y = c.act[1];
-        const int total = N0 * c.RP;
-        const int etotal = (use_eps && !d.generate_eps) ? L * c.RP : 0;
-        MID_SLAB(etotal, L, ev, (r < c.nr ? d.eps[(int64_t)(c.r0 + r) * L + col] : 0.f))
-        // (split-K partials: one batch per slice, summed in slice order)
-        MID_SLAB(total, N0, y, (r < c.nr ? __ldcg(d.y1_parts + (int64_t)(c.r0 + r) * d.y1_ld + col) : 0.f))
-        for (int s = 1; s < d.y1_nsplit; ++s) {
-            MID_SLAB(total, N0, part,
-                     (r < c.nr ? __ldcg(d.y1_parts + (int64_t)s * d.y1_slice + (int64_t)(c.r0 + r) * d.y1_ld + col) : 0.f))
-#pragma unroll
-            for (int it = 0; it < SLAB_IT; ++it) y[it] += part[it];
-        }
-        MID_SLAB_FOR(total, N0, y, {
-            const float val = x * d.y1_alpha;
-            if (r < c.nr && l0.y) l0.y[(int64_t)(c.r0 + r) * l0.ldy + col] = val;
-            Y[col * c.RP + r] = val;
-        })
-        MID_SLAB_FOR(etotal, L, ev, { E[col * c.RP + r] = x; })
-    }
-    stage_w_commit(c, wr, firstN, first.k_in);
+    cp_async_wait();
     __syncthreads();
+    if (l0.y && d.y1_parts != l0.y) slab_store(c, c.act[1], l0.y, l0.ldy, N0);
+    mid_stamp(d, 1);
 
     int cur = 0;          // buffer holding the current activation H
-    mid_fwd_bn_relu(c, d, l0, 0, c.act[1], c.act[0], training, ((N0 + 1 + 3) & ~3));
+    mid_fwd_bn_relu(c, d, l0, 0, c.act[1], c.act[0], training, SPAN);
     __syncthreads();
+    mid_stamp(d, 5);
     for (int i = 1; i < d.n_enc; ++i) {
         const MidLayer &l = d.enc[i];
         const int yb = (cur + 1) % 3, hb = (cur + 2) % 3;
         if (i > 1) {
-            stage_w(c, l.w, l.ldw, 0, l.n_out, l.k_in);
+            stage_w_async(c, l.w, l.ldw, 0, l.n_out, l.k_in);
+            cp_async_wait();
             __syncthreads();
         }
         mid_product<TM>(c, c.act[cur], l.k_in, c.act[yb], l.n_out, l.y, l.ldy);
         __syncthreads();
-        mid_fwd_bn_relu(c, d, l, i, c.act[yb], c.act[hb], training, ((l.n_out + 1 + 3) & ~3));
+        mid_fwd_bn_relu(c, d, l, i, c.act[yb], c.act[hb], training, SPAN);
         cur = hb;
         __syncthreads();
     }
@@ -553,194 +631,185 @@ __global__ void __launch_bounds__(kMidThreads, 1) vae_mid_fwd_kernel(const MidDe
     const int mb = (cur + 1) % 3, lb = (cur + 2) % 3;
     {
         const MidLayer &l = d.post;
-        for (int part = 0; part < 2; ++part) {
+        for (int part = 0; part < post_parts; ++part) {
             if (part > 0 || d.n_enc > 1) {
-                stage_w(c, l.w, l.ldw, part * L, L, l.k_in);
+                stage_w_async(c, l.w, l.ldw, part * L, NP, l.k_in);
+                cp_async_wait();
                 __syncthreads();
             }
-            mid_product<TM>(c, c.act[cur], l.k_in, c.act[part ? lb : mb], L, nullptr, 0);
+            mid_product<TM>(c, c.act[cur], l.k_in, c.act[part ? lb : mb], NP, nullptr, 0);
             __syncthreads();
         }
     }
+    mid_stamp(d, 6);
     // the decoder's first weights travel while the sample is formed
     const MidLayer &dl0 = d.dec[0];
-    stage_w_issue(wr, dl0.w, dl0.ldw, 0, dl0.n_out, dl0.k_in);
-    // ---- sample and KL (VAE:2353-2369, :2624-2627), one element per thread and pass ----------------
+    stage_w_async(c, dl0.w, dl0.ldw, 0, dl0.n_out, dl0.k_in);
+    // ---- sample and KL (VAE:2353-2369, :2624-2627) ----------------------------------------------------
     {
-        float *sMu = c.act[mb], *sLs = c.act[lb], *sZ = c.act[cur];
+        float *sMu = c.act[mb], *sLs = post_parts == 1 ? c.act[mb] + L * c.RP : c.act[lb], *sZ = c.act[cur];
         const int Kzp = (dl0.k_in + 3) & ~3;
-        for (int i = threadIdx.x; i < L * c.RP; i += kMidThreads) {
-            const int l = i / c.RP, r = i - l * c.RP;
-            float zv = 0.f, k = 0.f;
-            if (r < c.nr) {
-                const int64_t row = c.r0 + r;
-                const float mu = sMu[i];
-                const float raw = sLs[i];
-                const float ls = fminf(fmaxf(raw, -3.f), 3.f);
-                const float sigma = __expf(ls);
-                // tfp kl_divergence(Normal(mu, sigma), Normal(0, 1))
-                k = 0.5f * mu * mu + 0.5f * (sigma * sigma - 1.f) - ls;
-                zv = d.deterministic ? mu : mu + sigma * E[i];
-                if (d.kl_elem) d.kl_elem[row * L + l] = k;
-                // HBM copies for the backward pass / the shells: [mu | raw log_sigma], z
-                d.ph[row * d.ldph + l] = mu;
-                d.ph[row * d.ldph + L + l] = raw;
-                d.z[row * d.ldz + l] = zv;
-            }
-            sZ[i] = zv;
-            sLs[i] = k;           // (log_sigma is consumed: its buffer now holds the KL terms)
-        }
-        // augmented column, decoder-input extras (VAE:2400-2441), zero padding
-        for (int i = threadIdx.x; i < (Kzp - L) * c.RP; i += kMidThreads) {
-            const int col = L + i / c.RP, r = i % c.RP;
-            float v = 0.f;
-            if (r < c.nr) {
-                const int64_t row = c.r0 + r;
-                if (col == L) v = 1.f;
-                else if (d.batch_index && col - (L + 1) < d.n_batches)
-                    v = ((int)d.batch_index[row] == col - (L + 1)) ? 1.f : 0.f;
-                else if (d.count_sum && col == L + 1 + (d.batch_index ? d.n_batches : 0))
-                    v = d.count_sum[row];
-                if (col < d.ldz) d.z[row * d.ldz + col] = v;
-            }
-            sZ[col * c.RP + r] = v;
-        }
-        __syncthreads();
-        for (int r = warp; r < c.nr; r += kMidThreads / 32) {      // per-cell KL, fixed order
+        // lanes along the latent dimension: coalesced HBM copies of [mu | raw log_sigma] and z
+        for (int r = warp; r < SPAN; r += kMidThreads / 32) {
+            const bool valid = r < c.nr;
+            const int64_t row = c.r0 + r;
             float kl = 0.f;
-            for (int l = lane; l < L; l += 32) kl += sLs[l * c.RP + r];
+            for (int l = lane; l < L; l += 32) {
+                const int i = l * c.RP + r;
+                float zv = 0.f;
+                if (valid) {
+                    const float mu = sMu[i];
+                    const float raw = sLs[i];
+                    const float ls = fminf(fmaxf(raw, -3.f), 3.f);
+                    const float sigma = __expf(ls);
+                    // tfp kl_divergence(Normal(mu, sigma), Normal(0, 1))
+                    const float k = 0.5f * mu * mu + 0.5f * (sigma * sigma - 1.f) - ls;
+                    kl += k;
+                    zv = d.deterministic ? mu : mu + sigma * E[i];
+                    if (d.kl_elem) d.kl_elem[row * L + l] = k;
+                    d.ph[row * d.ldph + l] = mu;
+                    d.ph[row * d.ldph + L + l] = raw;
+                    d.z[row * d.ldz + l] = zv;
+                }
+                sZ[i] = zv;
+            }
+            // augmented column, decoder-input extras (VAE:2400-2441), zero padding
+            for (int col = L + lane; col < Kzp; col += 32) {
+                float v = 0.f;
+                if (valid) {
+                    if (col == L) v = 1.f;
+                    else if (d.batch_index && col - (L + 1) < d.n_batches)
+                        v = ((int)d.batch_index[row] == col - (L + 1)) ? 1.f : 0.f;
+                    else if (d.count_sum && col == L + 1 + (d.batch_index ? d.n_batches : 0))
+                        v = d.count_sum[row];
+                    if (col < d.ldz) d.z[row * d.ldz + col] = v;
+                }
+                sZ[col * c.RP + r] = v;
+            }
             kl = warp_sum(kl);
-            if (lane == 0 && d.kl_row) d.kl_row[c.r0 + r] = kl;
+            if (valid && lane == 0 && d.kl_row) d.kl_row[row] = kl;
         }
     }
-    stage_w_commit(c, wr, dl0.n_out, dl0.k_in);
+    cp_async_wait();
     __syncthreads();
+    mid_stamp(d, 7);
     // ---- decoder layers ---------------------------------------------------------------------------
     for (int j = 0; j < d.n_dec; ++j) {
         const MidLayer &l = d.dec[j];
         const int yb = (cur + 1) % 3, hb = (cur + 2) % 3;
         if (j > 0) {
-            stage_w(c, l.w, l.ldw, 0, l.n_out, l.k_in);
+            stage_w_async(c, l.w, l.ldw, 0, l.n_out, l.k_in);
+            cp_async_wait();
             __syncthreads();
         }
         mid_product<TM>(c, c.act[cur], l.k_in, c.act[yb], l.n_out, l.y, l.ldy);
         __syncthreads();
-        mid_fwd_bn_relu(c, d, l, d.n_enc + j, c.act[yb], c.act[hb], training, ((l.n_out + 1 + 3) & ~3));
+        mid_fwd_bn_relu(c, d, l, d.n_enc + j, c.act[yb], c.act[hb], training, SPAN);
         cur = hb;
         __syncthreads();
     }
+    mid_stamp(d, 13);
     // ---- operand of the fused likelihood heads: fp16, augmented, zero padded to ldd16 columns ----
     {
         const int N = d.dec[d.n_dec - 1].n_out;
         const float *H = c.act[cur];
         const int groups = (int)(d.ldd16 >> 3);
         __half *out = reinterpret_cast<__half *>(d.d16);
-        for (int i = threadIdx.x; i < c.nr * groups; i += kMidThreads) {
-            const int r = i / groups, c0 = (i % groups) << 3;
-            __align__(16) __half h[8];
+        for (int r = warp; r < c.nr; r += kMidThreads / 32) {
+            for (int g = lane; g < groups; g += 32) {
+                const int c0 = g << 3;
+                __align__(16) __half h[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) h[j] = __float2half_rn((c0 + j <= N) ? H[(c0 + j) * c.RP + r] : 0.f);   // column N = 1
-            *reinterpret_cast<uint4 *>(out + (int64_t)(c.r0 + r) * d.ldd16 + c0) = *reinterpret_cast<const uint4 *>(h);
-        }
-        if (d.h_last) {
-            float *hl = d.h_last;
-            for (int i = threadIdx.x; i < c.nr * (int)d.ldh_last; i += kMidThreads) {
-                const int r = i / (int)d.ldh_last, col = i % (int)d.ldh_last;
-                hl[(int64_t)(c.r0 + r) * d.ldh_last + col] = col <= N ? H[col * c.RP + r] : 0.f;
+                for (int j = 0; j < 8; ++j) h[j] = __float2half_rn((c0 + j <= N) ? H[(c0 + j) * c.RP + r] : 0.f);   // column N = 1
+                *reinterpret_cast<uint4 *>(out + (int64_t)(c.r0 + r) * d.ldd16 + c0) = *reinterpret_cast<const uint4 *>(h);
             }
         }
+        if (d.h_last) slab_store(c, H, d.h_last, d.ldh_last, N + 1);
     }
+    mid_stamp(d, 14);
 }
 
 // =============================================================================================
 // backward
 // =============================================================================================
-// Batched load of a layer's stored pre-activations -> X[c][r] = xhat (normalised) and / or
-// H[c][r] = relu(xhat + beta), with the layer's (mean, rstd, beta) from shared-memory slot `s`.
-template <int TM>
-__device__ __forceinline__ void mid_recompute(const MidCtx &c, const MidLayer &l, int s, float *X, float *H) {
-    constexpr int SLAB_IT = MidTraits<TM>::kSlabIt;
-    const int N = l.n_out;
-    const int total = N * c.RP;
-    const float *m = bnv_mean(c, s), *rs = bnv_rstd(c, s), *bt = bnv_beta(c, s);
-    MID_SLAB(total, N, y, (r < c.nr ? l.y[(int64_t)(c.r0 + r) * l.ldy + col] : 0.f))
-    MID_SLAB_FOR(total, N, y, {
-        float xh = 0.f;
-        float h = 0.f;
-        if (r < c.nr) {
-            xh = (x - m[col]) * rs[col];
-            h = fmaxf(xh + bt[col], 0.f);
-        }
-        if (X) X[col * c.RP + r] = xh;
-        if (H) H[col * c.RP + r] = h;
-    })
-}
-
 // In place on Gd[c][r] (d loss / d activation): ReLU mask, batch-norm backward.  X holds xhat.
 // dy = rstd (g - s1/B - xhat s2/B);  dbeta = s1  (s1 = sum g, s2 = sum g xhat over ALL cells).
 // `scratch`: [8 warps][2][128] floats of idle shared memory.
-__device__ __forceinline__ void mid_bn_relu_bwd(const MidCtx &c, const MidDesc &d, const MidLayer &l, int s, float *Gd,
-                                                const float *X, float *ws_stat, float *scratch) {
+__device__ __noinline__ void mid_bn_relu_bwd(const MidCtx &c, const MidDesc &d, const MidLayer &l, int s, int span, float *Gd,
+                                             const float *X, float *ws_stat, float *scratch) {
     const int N = l.n_out;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float *rs = bnv_rstd(c, s), *bt = bnv_beta(c, s);
     // g = dH * [H > 0], H = relu(xhat + beta)
-    for (int i = threadIdx.x; i < N * c.RP; i += kMidThreads) {
-        const int col = i / c.RP, r = i - col * c.RP;
-        float g = 0.f;
-        if (r < c.nr && X[i] + bt[col] > 0.f) g = Gd[i];
-        Gd[i] = g;
+#pragma unroll 4
+    for (int col = warp; col < N; col += kMidThreads / 32) {
+        const float beta = bt[col];
+        for (int r = lane; r < span; r += 32) {
+            const int i = col * c.RP + r;
+            Gd[i] = (r < c.nr && X[i] + beta > 0.f) ? Gd[i] : 0.f;
+        }
     }
     __syncthreads();
     if (!l.beta) return;
-    for (int col = warp; col < N; col += kMidThreads / 32) {
+    {
+        // per-CTA column sums: one thread per (column, half of the cells)
+        const int col = threadIdx.x & (kMidCols - 1), half = threadIdx.x >> 7;
+        const int h0 = half ? (c.nr >> 1) : 0, h1 = half ? c.nr : (c.nr >> 1);
         float s1 = 0.f, s2 = 0.f;
-        for (int r = lane; r < c.nr; r += 32) {
-            const float g = Gd[col * c.RP + r];
-            s1 += g;
-            s2 += g * X[col * c.RP + r];
+        if (col < N) {
+#pragma unroll 4
+            for (int r = h0; r < h1; ++r) {
+                const float g = Gd[col * c.RP + r];
+                s1 += g;
+                s2 = fmaf(g, X[col * c.RP + r], s2);
+            }
         }
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
-        if (lane == 0) {
-            ws_stat[((int64_t)blockIdx.x * 2 + 0) * kMidCols + col] = s1;
-            ws_stat[((int64_t)blockIdx.x * 2 + 1) * kMidCols + col] = s2;
+        float *x = c.stat + 4 * kMidCols;        // [2 halves][2][128]
+        x[(half * 2 + 0) * kMidCols + col] = s1;
+        x[(half * 2 + 1) * kMidCols + col] = s2;
+        __syncthreads();
+        if (half == 0 && col < N) {
+            ws_stat[((int64_t)blockIdx.x * 2 + 0) * kMidCols + col] = x[col] + x[2 * kMidCols + col];
+            ws_stat[((int64_t)blockIdx.x * 2 + 1) * kMidCols + col] = x[kMidCols + col] + x[3 * kMidCols + col];
         }
     }
     mid_grid_sync(d.barrier, d.error);
     float *t1 = c.stat, *t2 = c.stat + kMidCols;
     {
-        // fixed-order fold, loads batched as in the forward statistics
+        // fixed-order fold of the CTA partials: warp w takes the CTAs k = w mod 8
         const int G = gridDim.x;
         float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 10
-        for (int k = warp; k < G; k += kMidThreads / 32) {
-            float v1[4], v2[4];
+        float v1[kMidFoldIt][4], v2[kMidFoldIt][4];
+#pragma unroll
+        for (int it = 0; it < kMidFoldIt; ++it) {          // every load in flight before the first add
+            const int k = warp + it * (kMidThreads / 32);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int col = lane + 32 * q;
-                v1[q] = col < N ? __ldcg(ws_stat + ((int64_t)k * 2 + 0) * kMidCols + col) : 0.f;
-                v2[q] = col < N ? __ldcg(ws_stat + ((int64_t)k * 2 + 1) * kMidCols + col) : 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                a1[q] += v1[q];
-                a2[q] += v2[q];
+                const bool ok = k < G && col < N;
+                v1[it][q] = ok ? __ldcg(ws_stat + ((int64_t)k * 2 + 0) * kMidCols + col) : 0.f;
+                v2[it][q] = ok ? __ldcg(ws_stat + ((int64_t)k * 2 + 1) * kMidCols + col) : 0.f;
             }
         }
-        float *x = scratch;
+#pragma unroll
+        for (int it = 0; it < kMidFoldIt; ++it)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                a1[q] += v1[it][q];
+                a2[q] += v2[it][q];
+            }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            x[(warp * 2 + 0) * kMidCols + lane + 32 * q] = a1[q];
-            x[(warp * 2 + 1) * kMidCols + lane + 32 * q] = a2[q];
+            scratch[(warp * 2 + 0) * kMidCols + lane + 32 * q] = a1[q];
+            scratch[(warp * 2 + 1) * kMidCols + lane + 32 * q] = a2[q];
         }
         __syncthreads();
         const int col = threadIdx.x;
         if (col < N) {
             float s1 = 0.f, s2 = 0.f;
             for (int w = 0; w < kMidThreads / 32; ++w) {
-                s1 += x[(w * 2 + 0) * kMidCols + col];
-                s2 += x[(w * 2 + 1) * kMidCols + col];
+                s1 += scratch[(w * 2 + 0) * kMidCols + col];
+                s2 += scratch[(w * 2 + 1) * kMidCols + col];
             }
             t1[col] = s1;
             t2[col] = s2;
@@ -749,41 +818,25 @@ __device__ __forceinline__ void mid_bn_relu_bwd(const MidCtx &c, const MidDesc &
     }
     __syncthreads();
     const float inv_b = 1.f / (float)d.B;
-    for (int i = threadIdx.x; i < N * c.RP; i += kMidThreads) {
-        const int col = i / c.RP, r = i - col * c.RP;
-        float v = 0.f;
-        if (r < c.nr) v = rs[col] * (Gd[i] - t1[col] * inv_b - X[i] * t2[col] * inv_b);
-        Gd[i] = v;
+#pragma unroll 4
+    for (int col = warp; col < N; col += kMidThreads / 32) {
+        const float rstd = rs[col], m1 = t1[col] * inv_b, m2 = t2[col] * inv_b;
+        for (int r = lane; r < span; r += 32) {
+            const int i = col * c.RP + r;
+            Gd[i] = r < c.nr ? rstd * (Gd[i] - m1 - X[i] * m2) : 0.f;
+        }
     }
     __syncthreads();
 }
 
-// dIn[k][r] = sum_n G[n][r] W[row0 + n][k], k < n_in, accumulated over `parts` row blocks of W.
-// `pre`: the weights of part 0, issued by the caller (in flight across the work before this call).
 template <int TM>
-__device__ __forceinline__ void mid_dgrad(const MidCtx &c, const MidLayer &l, const float *G0, const float *G1,
-                                          int rows_per_part, int parts, float *Out, const WRegs &pre) {
-    float acc[TM][4] = {};
-    for (int p = 0; p < parts; ++p) {
-        if (p == 0) {
-            stage_w_commit(c, pre, rows_per_part, l.n_in);
-        } else {
-            __syncthreads();
-            stage_w(c, l.w, l.ldw, p * rows_per_part, rows_per_part, l.n_in);
-        }
-        __syncthreads();
-        mm_dgrad<TM>(p ? G1 : G0, c.RP, c.sw, rows_per_part, acc);
-    }
-    __syncthreads();            // every thread is done reading G before Out (which may alias) is written
-    mm_dgrad_store<TM>(c, Out, l.n_in, acc);
-}
-
-template <int TM>
-__global__ void __launch_bounds__(kMidThreads, 1) vae_mid_bwd_kernel(const MidDesc d) {
-    constexpr int SLAB_IT = MidTraits<TM>::kSlabIt;
+__global__ void __launch_bounds__(kMidThreads, 1) vae_mid_bwd_kernel(const __grid_constant__ MidDesc param) {
+    constexpr int SPAN = MidTraits<TM>::kSpan;
     extern __shared__ __align__(16) float mid_smem[];
-    MidCtx c;
-    mid_setup(c, d, mid_smem);
+    __shared__ MidShared sh;
+    mid_setup(sh, param, mid_smem);
+    const MidDesc &d = sh.d;
+    const MidCtx &c = sh.c;
     const int L = d.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float weight = d.kl_weight;
@@ -804,12 +857,16 @@ __global__ void __launch_bounds__(kMidThreads, 1) vae_mid_bwd_kernel(const MidDe
     const MidLayer &last = d.dec[d.n_dec - 1];
     const int s_last = d.n_enc + d.n_dec - 1;
     float *Gd = c.act[0], *X = c.act[1], *T = c.act[2], *F = c.act[3];
-    WRegs wr;
-    mid_load_bnv(c, d, 2);
+    mid_stamp(d, 0);
     {
         const int N = last.n_out;
-        const int total = N * c.RP;
-        const __half *d16 = reinterpret_cast<const __half *>(d.d16);
+        if (d.dd_nsplit == 1) slab_copy_async(c, Gd, d.dd_parts, d.dd_ld, N, SPAN);
+        else slab_sum(c, Gd, d.dd_parts, d.dd_ld, N, SPAN, d.dd_nsplit, d.dd_slice, 1.f);
+        slab_copy_async(c, X, last.y, last.ldy, N, SPAN);
+        // the fp16 operand the heads saw, as 32-bit words (pairs of halves): T[w][r]
+        slab_copy_async(c, T, reinterpret_cast<const float *>(d.d16), d.ldd16 >> 1, (N + 1) >> 1, SPAN);
+        stage_w_async(c, last.w, last.ldw, 0, last.n_out, last.n_in);      // dgrad weights of the last decoder layer
+        mid_load_bnv(c, d, 2);
         // per-cell scalars: threads 0..nr-1
         float lp = 0.f, klr = 0.f;
         if ((int)threadIdx.x < c.nr) {
@@ -818,40 +875,29 @@ __global__ void __launch_bounds__(kMidThreads, 1) vae_mid_bwd_kernel(const MidDe
             if (d.row_const) lp -= d.row_const[row];
             klr = d.kl_row[row];
         }
-        MID_SLAB(total, N, y, (r < c.nr ? last.y[(int64_t)(c.r0 + r) * last.ldy + col] : 0.f))
-        MID_SLAB(total, N, h16, (r < c.nr ? __half2float(d16[(int64_t)(c.r0 + r) * d.ldd16 + col]) : 0.f))
-        MID_SLAB(total, N, g, (r < c.nr ? __ldcg(d.dd_parts + (int64_t)(c.r0 + r) * d.dd_ld + col) : 0.f))
-        for (int s = 1; s < d.dd_nsplit; ++s) {
-            MID_SLAB(total, N, part,
-                     (r < c.nr ? __ldcg(d.dd_parts + (int64_t)s * d.dd_slice + (int64_t)(c.r0 + r) * d.dd_ld + col) : 0.f))
-#pragma unroll
-            for (int it = 0; it < SLAB_IT; ++it) g[it] += part[it];
-        }
-        __syncthreads();         // the normalisation vectors are in shared memory
-        const float *m = bnv_mean(c, s_last), *rs = bnv_rstd(c, s_last), *bt = bnv_beta(c, s_last);
-#pragma unroll
-        for (int it = 0; it < SLAB_IT; ++it) {
-            const int i = threadIdx.x + it * kMidThreads;
-            if (i < total) {
-                const int col = i % N, r = i / N;
-                float xh = 0.f, corr = 0.f;
-                if (r < c.nr) {
-                    xh = (y[it] - m[col]) * rs[col];
-                    const float h = fmaxf(xh + bt[col], 0.f);      // fp32 activation the heads saw in fp16
-                    corr = (h - h16[it]) * g[it];
-                }
-                Gd[col * c.RP + r] = g[it];
-                X[col * c.RP + r] = xh;
-                T[col * c.RP + r] = corr;
-            }
-        }
+        cp_async_wait();
         __syncthreads();
+        // X: y -> xhat; per-cell correction sum_h (h - h16) dd_h, lanes along the columns (coalesced d16)
+        const float *m = bnv_mean(c, s_last), *rs = bnv_rstd(c, s_last), *bt = bnv_beta(c, s_last);
         const float inv_go = 1.f / d.go_scalar;
-        for (int r = warp; r < c.nr; r += kMidThreads / 32) {
+        for (int r = warp; r < SPAN; r += kMidThreads / 32) {
+            const bool valid = r < c.nr;
             float corr = 0.f;
-            for (int col = lane; col < N; col += 32) corr += T[col * c.RP + r];
+#pragma unroll 4
+            for (int col = lane; col < N; col += 32) {
+                const int i = col * c.RP + r;
+                float xh = 0.f;
+                if (valid) {
+                    xh = (X[i] - m[col]) * rs[col];
+                    const float h = fmaxf(xh + bt[col], 0.f);      // fp32 activation the heads saw in fp16
+                    const float word = T[(col >> 1) * c.RP + r];
+                    const __half2 h2 = *reinterpret_cast<const __half2 *>(&word);
+                    corr = fmaf(h - ((col & 1) ? __high2float(h2) : __low2float(h2)), Gd[i], corr);
+                }
+                X[i] = xh;
+            }
             corr = warp_sum(corr) * inv_go;
-            if (lane == 0) c.stat[2 * kMidCols + r] = corr;
+            if (lane == 0 && valid) c.stat[2 * kMidCols + r] = corr;
         }
         __syncthreads();
         float lp_sum = 0.f, kl_sum = 0.f;
@@ -878,35 +924,43 @@ __global__ void __launch_bounds__(kMidThreads, 1) vae_mid_bwd_kernel(const MidDe
             ws_bound(d)[blockIdx.x * 4 + 0] = a;
             ws_bound(d)[blockIdx.x * 4 + 1] = b;
         }
-        __syncthreads();
     }
+    mid_stamp(d, 1);
     // ---- decoder layers, last to first -------------------------------------------------------------
-    // invariant at the top: Gd = d loss / d activation of layer j, X = its xhat; T, F free
+    // invariant at the top: Gd = d loss / d activation of layer j, X = its xhat, sw = its dgrad weights
+    // (in flight or landed); T, F free
     for (int j = d.n_dec - 1; j >= 0; --j) {
         const MidLayer &l = d.dec[j];
         const int s = d.n_enc + j;
-        // issued ahead of the barrier inside the batch-norm backward: the layer's dgrad weights and
-        // its input -- the previous decoder activation (recomputed, with its xhat for the next
-        // iteration) or the latent sample
+        // issued ahead of the barrier inside the batch-norm backward: the layer's input -- the
+        // previous decoder activation (its stored pre-activations) or the latent sample
         float *In = T, *Xprev = F;
         const int Kp = (int)l.ldw;
-        stage_w_issue(wr, l.w, l.ldw, 0, l.n_out, l.n_in);
         if (j > 0) {
-            mid_recompute<TM>(c, d.dec[j - 1], s - 1, Xprev, In);
-            set_aug_cols(c, In, d.dec[j - 1].n_out, Kp);
+            slab_copy_async(c, Xprev, d.dec[j - 1].y, d.dec[j - 1].ldy, d.dec[j - 1].n_out, SPAN);
         } else {
             const int zc = min(Kp, (int)d.ldz);
-            const int total = zc * c.RP;
-            MID_SLAB(total, zc, zv, (r < c.nr ? d.z[(int64_t)(c.r0 + r) * d.ldz + col] : 0.f))
-            MID_SLAB_FOR(total, zc, zv, { In[col * c.RP + r] = x; })
-            if (zc < Kp) zero_cols(c, In, zc, Kp);
+            slab_copy_async(c, In, d.z, d.ldz, zc, SPAN);
+            if (zc < Kp) set_aug_cols(c, In, Kp, Kp, SPAN);      // (never: ldz == Kp)
         }
-        mid_bn_relu_bwd(c, d, l, s, Gd, X, ws_stat_slot(d, slot++), c.sw);
+        mid_stamp(d, 2);
+        mid_bn_relu_bwd(c, d, l, s, SPAN, Gd, X, ws_stat_slot(d, slot++), j > 0 ? T : F);
+        mid_stamp(d, 3);
+        cp_async_wait();
+        __syncthreads();
+        if (j > 0) {
+            mid_normalise(c, s - 1, d.dec[j - 1].n_out, SPAN, Xprev, Xprev, In);
+            set_aug_cols(c, In, d.dec[j - 1].n_out, Kp, SPAN);
+            __syncthreads();
+        }
         mid_wgrad(c, Gd, l.n_out, In, Kp, dw_part(dw_ws, l));
-        __syncthreads();
+        mid_stamp(d, 4);
         float *Out = X;      // xhat of this layer is dead: the dgrad output takes its buffer
-        mid_dgrad<TM>(c, l, Gd, Gd, l.n_out, 1, Out, wr);
+        mid_dgrad_tile<TM>(c, Gd, l.n_out, Out, l.n_in, true);
         __syncthreads();
+        mid_stamp(d, 5);
+        // the next product's dgrad weights travel during the next phase
+        if (j > 0) stage_w_async(c, d.dec[j - 1].w, d.dec[j - 1].ldw, 0, d.dec[j - 1].n_out, d.dec[j - 1].n_in);
         // rotate: Gd <- Out, X <- Xprev, free: old Gd (-> F), In (T stays T)
         float *oldG = Gd;
         Gd = Out;
@@ -915,49 +969,63 @@ __global__ void __launch_bounds__(kMidThreads, 1) vae_mid_bwd_kernel(const MidDe
     }
     // ---- sample / KL backward (VAE:2353-2369 and the analytic KL): Gd = dZ[l][r] -----------------
     // dmu = dz + c mu;  dlog_sigma = (dz eps sigma + c (sigma^2 - 1)) [|raw| <= 3];  c = weight / B
-    float *Gmu = Gd, *Gls = X;
+    const int post_parts = (2 * L <= kMidCols) ? 1 : 2;
+    const int NP = post_parts == 1 ? 2 * L : L;
+    float *Gmu = Gd, *Gls = post_parts == 1 ? Gd + L * c.RP : X;     // (one buffer when both halves fit)
     const MidLayer &pl = d.post;
     const MidLayer &prev = d.enc[d.n_enc - 1];
-    stage_w_issue(wr, pl.w, pl.ldw, 0, L, pl.n_in);
-    {
-        const int total = L * c.RP;
-        MID_SLAB(total, L, mu, (r < c.nr ? d.ph[(int64_t)(c.r0 + r) * d.ldph + col] : 0.f))
-        MID_SLAB(total, L, raw, (r < c.nr ? d.ph[(int64_t)(c.r0 + r) * d.ldph + L + col] : 0.f))
-        MID_SLAB(total, L, ep, ((r < c.nr && !d.deterministic) ? d.eps[(int64_t)(c.r0 + r) * L + col] : 0.f))
-#pragma unroll
-        for (int it = 0; it < SLAB_IT; ++it) {
-            const int i = threadIdx.x + it * kMidThreads;
-            if (i < total) {
-                const int col = i % L, r = i / L;
-                float gm = 0.f, gl = 0.f;
-                if (r < c.nr) {
-                    const float ls = fminf(fmaxf(raw[it], -3.f), 3.f);
-                    const float sigma = __expf(ls);
-                    const float dz = Gd[col * c.RP + r];
-                    gm = dz + kl_coef * mu[it];
-                    const float mask = (raw[it] < -3.f || raw[it] > 3.f) ? 0.f : 1.f;
-                    gl = (dz * ep[it] * sigma + kl_coef * (sigma * sigma - 1.f)) * mask;
-                }
-                Gmu[col * c.RP + r] = gm;      // (the element this thread just read)
-                Gls[col * c.RP + r] = gl;
+    stage_w_async(c, pl.w, pl.ldw, 0, NP, pl.n_in);
+    slab_copy_async(c, F, prev.y, prev.ldy, prev.n_out, SPAN);       // pre-activations of the last encoder layer
+#pragma unroll 4
+    for (int r = warp; r < SPAN; r += kMidThreads / 32) {        // (unrolled: several cells' loads in flight)
+        const bool valid = r < c.nr;
+        const int64_t row = c.r0 + r;
+        for (int l = lane; l < L; l += 32) {
+            const int i = l * c.RP + r;
+            float gm = 0.f, gl = 0.f;
+            if (valid) {
+                const float mu = d.ph[row * d.ldph + l];
+                const float raw = d.ph[row * d.ldph + L + l];
+                const float e = d.deterministic ? 0.f : d.eps[row * L + l];
+                const float ls = fminf(fmaxf(raw, -3.f), 3.f);
+                const float sigma = __expf(ls);
+                const float dz = Gd[i];
+                gm = dz + kl_coef * mu;
+                const float mask = (raw < -3.f || raw > 3.f) ? 0.f : 1.f;
+                gl = (dz * e * sigma + kl_coef * (sigma * sigma - 1.f)) * mask;
             }
+            Gmu[i] = gm;      // (the element this thread just read)
+            Gls[i] = gl;
         }
     }
+    mid_stamp(d, 6);
     // ---- posterior heads: wgrad of both halves, dgrad summed over them ----------------------------
     {
         float *In = T;
         const int Kp = (int)pl.ldw;
-        mid_recompute<TM>(c, prev, d.n_enc - 1, F, In);      // F = xhat of the last encoder layer (kept)
-        set_aug_cols(c, In, prev.n_out, Kp);
+        cp_async_wait();
         __syncthreads();
+        mid_normalise(c, d.n_enc - 1, prev.n_out, SPAN, F, F, In);      // F = xhat of the last encoder layer (kept)
+        set_aug_cols(c, In, prev.n_out, Kp, SPAN);
+        __syncthreads();
+        mid_stamp(d, 7);
         float *mine = dw_part(dw_ws, pl);
-        mid_wgrad(c, Gmu, L, In, Kp, mine);
-        mid_wgrad(c, Gls, L, In, Kp, mine + (int64_t)L * Kp);
+        mid_wgrad(c, Gmu, NP, In, Kp, mine);
+        if (post_parts == 2) mid_wgrad(c, Gls, L, In, Kp, mine + (int64_t)L * Kp);
         __syncthreads();
-        mid_dgrad<TM>(c, pl, Gmu, Gls, L, 2, In, wr);           // d loss / d H of the last encoder layer
+        mid_stamp(d, 8);
+        mid_dgrad_tile<TM>(c, Gmu, NP, In, pl.n_in, true);          // d loss / d H of the last encoder layer
         __syncthreads();
-        // Gd <- In (T's buffer); X <- F (xhat); free: Gmu's and Gls's buffers
-        float *f0 = Gmu, *f1 = Gls;
+        if (post_parts == 2) {
+            stage_w_async(c, pl.w, pl.ldw, L, L, pl.n_in);
+            cp_async_wait();
+            __syncthreads();
+            mid_dgrad_tile<TM>(c, Gls, L, In, pl.n_in, false);
+            __syncthreads();
+        }
+        mid_stamp(d, 9);
+        // Gd <- In (T's buffer); X <- F (xhat); free: Gmu's buffer and X's old one
+        float *f0 = Gd, *f1 = X;
         Gd = In;
         X = F;
         T = f0;
@@ -969,50 +1037,53 @@ __global__ void __launch_bounds__(kMidThreads, 1) vae_mid_bwd_kernel(const MidDe
         float *In = T, *Xprev = F;
         const int Kp = (int)l.ldw;
         if (i > 0) {
-            stage_w_issue(wr, l.w, l.ldw, 0, l.n_out, l.n_in);
-            mid_recompute<TM>(c, d.enc[i - 1], i - 1, Xprev, In);
-            set_aug_cols(c, In, d.enc[i - 1].n_out, Kp);
+            stage_w_async(c, l.w, l.ldw, 0, l.n_out, l.n_in);
+            slab_copy_async(c, Xprev, d.enc[i - 1].y, d.enc[i - 1].ldy, d.enc[i - 1].n_out, SPAN);
         }
-        mid_bn_relu_bwd(c, d, l, i, Gd, X, ws_stat_slot(d, slot++), c.sw);
+        mid_bn_relu_bwd(c, d, l, i, SPAN, Gd, X, ws_stat_slot(d, slot++), i > 0 ? In : T);
         if (i == 0) break;
-        mid_wgrad(c, Gd, l.n_out, In, Kp, dw_part(dw_ws, l));
+        cp_async_wait();
         __syncthreads();
+        mid_normalise(c, i - 1, d.enc[i - 1].n_out, SPAN, Xprev, Xprev, In);
+        set_aug_cols(c, In, d.enc[i - 1].n_out, Kp, SPAN);
+        __syncthreads();
+        mid_wgrad(c, Gd, l.n_out, In, Kp, dw_part(dw_ws, l));
         float *Out = X;
-        mid_dgrad<TM>(c, l, Gd, Gd, l.n_out, 1, Out, wr);
+        mid_dgrad_tile<TM>(c, Gd, l.n_out, Out, l.n_in, true);
         __syncthreads();
         float *oldG = Gd;
         Gd = Out;
         X = Xprev;
         F = oldG;
     }
+    mid_stamp(d, 10);
     // dY1 (B, H1) -> fp16 + rounding remainder, scaled into range, zero padded: operand of dW1 = dY1^T X
     {
         const int N = d.enc[0].n_out;
         const int groups = (int)(d.lddy1 >> 3);
         __half *out = reinterpret_cast<__half *>(d.dy1_16);
         __half *out_lo = reinterpret_cast<__half *>(d.dy1_16_lo);
-        for (int i = threadIdx.x; i < c.nr * groups; i += kMidThreads) {
-            const int r = i / groups, c0 = (i % groups) << 3;
-            __align__(16) __half h[8], lo[8];
+        for (int r = warp; r < c.nr; r += kMidThreads / 32) {
+            for (int g = lane; g < groups; g += 32) {
+                const int c0 = g << 3;
+                __align__(16) __half h[8], lo[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float v = (c0 + j < N) ? Gd[(c0 + j) * c.RP + r] * d.dy1_scale : 0.f;
-                h[j] = __float2half_rn(v);
-                lo[j] = __float2half_rn(v - __half2float(h[j]));     // rounding remainder
-            }
-            *reinterpret_cast<uint4 *>(out + (int64_t)(c.r0 + r) * d.lddy1 + c0) = *reinterpret_cast<const uint4 *>(h);
-            if (out_lo)
-                *reinterpret_cast<uint4 *>(out_lo + (int64_t)(c.r0 + r) * d.lddy1 + c0) = *reinterpret_cast<const uint4 *>(lo);
-        }
-        if (d.dy1) {
-            for (int i = threadIdx.x; i < c.nr * N; i += kMidThreads) {
-                const int r = i / N, col = i % N;
-                d.dy1[(int64_t)(c.r0 + r) * d.lddy1_f32 + col] = Gd[col * c.RP + r];
+                for (int j = 0; j < 8; ++j) {
+                    const float v = (c0 + j < N) ? Gd[(c0 + j) * c.RP + r] * d.dy1_scale : 0.f;
+                    h[j] = __float2half_rn(v);
+                    lo[j] = __float2half_rn(v - __half2float(h[j]));     // rounding remainder
+                }
+                *reinterpret_cast<uint4 *>(out + (int64_t)(c.r0 + r) * d.lddy1 + c0) = *reinterpret_cast<const uint4 *>(h);
+                if (out_lo)
+                    *reinterpret_cast<uint4 *>(out_lo + (int64_t)(c.r0 + r) * d.lddy1 + c0) = *reinterpret_cast<const uint4 *>(lo);
             }
         }
+        if (d.dy1) slab_store(c, Gd, d.dy1, d.lddy1_f32, N);
     }
     // ---- all partials are in the workspace: fold them in fixed order --------------------------------
+    mid_stamp(d, 11);
     mid_grid_sync(d.barrier, d.error);
+    mid_stamp(d, 12);
     {
         float *cursor = ws_dw_base(d);
         const int G = gridDim.x;
@@ -1020,15 +1091,8 @@ __global__ void __launch_bounds__(kMidThreads, 1) vae_mid_bwd_kernel(const MidDe
             const int64_t n = (int64_t)l.n_out * l.ldw;
             for (int64_t e = (int64_t)blockIdx.x * kMidThreads + threadIdx.x; e < n; e += (int64_t)gridDim.x * kMidThreads) {
                 float s = 0.f;
-                int k = 0;
-                for (; k + 16 <= G; k += 16) {        // 16 loads in flight, summed in CTA order
-                    float v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __ldcg(cursor + (int64_t)(k + j) * n + e);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) s += v[j];
-                }
-                for (; k < G; ++k) s += __ldcg(cursor + (int64_t)k * n + e);
+#pragma unroll 8
+                for (int k = 0; k < G; ++k) s += __ldcg(cursor + (int64_t)k * n + e);      // CTA order
                 l.dw[e] = s;
             }
             cursor += (int64_t)gridDim.x * n;
@@ -1036,27 +1100,38 @@ __global__ void __launch_bounds__(kMidThreads, 1) vae_mid_bwd_kernel(const MidDe
         for (int j = d.n_dec - 1; j >= 0; --j) reduce(d.dec[j]);
         reduce(d.post);
         for (int i = d.n_enc - 1; i >= 1; --i) reduce(d.enc[i]);
-        if (blockIdx.x == 0) {
+        if (blockIdx.x == gridDim.x - 1) {       // (the last CTA has the fewest cells: least other work)
             for (int k = threadIdx.x; k < G; k += kMidThreads) {
                 c.stat[k] = __ldcg(ws_bound(d) + k * 4 + 0);
                 c.stat[kMidThreads + k] = __ldcg(ws_bound(d) + k * 4 + 1);
             }
             __syncthreads();
-        }
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            // lower bound (R = 1): mean_b(log p - KL); weighted; ENRE; KL (VAE:2715-2734)
+            // fixed order: lane l sums the CTAs l, l + 32, ...; lane 0 then adds the lanes in order
             float lp = 0.f, kl = 0.f;
-            for (int k = 0; k < G; ++k) {
-                lp += c.stat[k];
-                kl += c.stat[kMidThreads + k];
+            if (warp == 0) {
+                for (int k = lane; k < G; k += 32) {
+                    lp += c.stat[k];
+                    kl += c.stat[kMidThreads + k];
+                }
+                float lps = 0.f, kls = 0.f;
+                for (int src = 0; src < 32; ++src) {
+                    lps += __shfl_sync(0xffffffffu, lp, src);
+                    kls += __shfl_sync(0xffffffffu, kl, src);
+                }
+                lp = lps;
+                kl = kls;
             }
-            const float inv_b = 1.f / (float)d.B;
-            d.bound[0] = (lp - kl) * inv_b;
-            d.bound[1] = (lp - weight * kl) * inv_b;
-            d.bound[2] = lp * inv_b;
-            d.bound[3] = kl * inv_b;
+            if (threadIdx.x == 0) {
+                // lower bound (R = 1): mean_b(log p - KL); weighted; ENRE; KL (VAE:2715-2734)
+                const float inv_b = 1.f / (float)d.B;
+                d.bound[0] = (lp - kl) * inv_b;
+                d.bound[1] = (lp - weight * kl) * inv_b;
+                d.bound[2] = lp * inv_b;
+                d.bound[3] = kl * inv_b;
+            }
         }
     }
+    mid_stamp(d, 13);
 }
 
 static int mid_check(const MidDesc *d, const char *name, bool bwd) {
@@ -1128,8 +1203,9 @@ static int mid_launch(const char *name, const MidDesc *d, cudaStream_t s) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = mid_grid(d);
-    SCVAE_CHECK_ARG(grid <= sms, "%s: %d cells need %d CTAs of %d cells, the device has %d SMs (grid barrier)", name, d->B,
-                    grid, d->rows_per_cta, sms);
+    SCVAE_CHECK_ARG(grid <= sms && grid <= kMidFoldIt * (kMidThreads / 32),
+                    "%s: %d cells need %d CTAs of %d cells, the device has %d SMs (grid barrier)", name, d->B, grid,
+                    d->rows_per_cta, sms);
     SCVAE_CHECK_ARG(d->workspace_floats >= mid_workspace_floats_impl(d), "%s: workspace too small", name);
     return d->rows_per_cta <= 32 ? mid_launch_t<BWD, 4>(name, d, grid, s) : mid_launch_t<BWD, 8>(name, d, grid, s);
 }

@@ -18,11 +18,13 @@ __device__ __forceinline__ void write_shadows(const AdamShadows &sh, int64_t i, 
     for (int k = 0; k < sh.n; ++k) {
         const scvae_shadow &s = sh.s[k];
         if (i < s.lo || i >= s.hi) continue;
-        const int64_t rel = i - s.lo;
-        const int64_t r = rel / s.src_ld;
-        const int c = (int)(rel - r * s.src_ld);
+        // (a shadowed block holds < 2^32 floats: 32-bit divisions, the kernel stays memory-bound)
+        const uint32_t rel = (uint32_t)(i - s.lo);
+        const uint32_t r = rel / (uint32_t)s.src_ld;
+        const int c = (int)(rel - r * (uint32_t)s.src_ld);
         if (c >= s.dst_ld) continue;                    // (src_ld, dst_ld % 4 == 0: all four or none)
-        const int64_t row = (r / s.src_block_rows) * s.dst_block_rows + (r % s.src_block_rows);
+        const uint32_t blk = s.src_block_rows > r ? 0u : r / (uint32_t)s.src_block_rows;
+        const int64_t row = (int64_t)blk * s.dst_block_rows + (r - blk * (uint32_t)s.src_block_rows);
         const float x[4] = {p4.x, p4.y, p4.z, p4.w};
         __align__(8) __half h[4], l[4];
 #pragma unroll
@@ -184,6 +186,7 @@ extern "C" int scvae_adam_clip_step(float *param, const float *grad, float *m, f
     for (int k = 0; k < n_shadows; ++k) {
         const scvae_shadow &s = shadows[k];
         SCVAE_CHECK_ARG(s.hi16 && s.lo % 4 == 0 && s.hi % 4 == 0 && s.src_ld % 4 == 0 && s.dst_ld % 4 == 0 &&
+                            s.hi - s.lo < (int64_t)1 << 32 && s.src_ld < (int64_t)1 << 31 &&
                             s.src_block_rows > 0 && s.dst_block_rows > 0 && aligned16(param) &&
                             (reinterpret_cast<uintptr_t>(s.hi16) & 7u) == 0,
                         "adam_clip_step: bad shadow %d", k);

@@ -151,7 +151,9 @@ class VAEEngine:
         # the (cells x ~100) middle of a 16-bit training / lean evaluation step as one persistent
         # kernel per direction (csrc/mid_layers.cu) instead of ~20 small launches
         self.mid_fused = __import__("os").environ.get("SCVAE_MID_FUSED", "1") != "0"
-        self.mid_bwd_ctas = int(__import__("os").environ.get("SCVAE_MID_BWD_CTAS", "0"))   # 0: all SMs
+        # CTAs of the backward middle kernel when it shares the SMs with the side-stream GEMMs
+        # (0: never share, run it first on all SMs)
+        self.mid_bwd_ctas = int(__import__("os").environ.get("SCVAE_MID_BWD_CTAS", "64"))
 
         for arch in (inference_architecture, generative_architecture):
             if arch not in ("MLP", "LFM"):
@@ -634,6 +636,15 @@ class VAEEngine:
             self._sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         return self._sms
 
+    def _mid_bwd_grid(self, p):
+        """CTAs of the backward middle kernel when it runs beside the side-stream GEMMs (0: it
+        does not fit beside them: more than half of the SMs)."""
+        if not (self.mid_bwd_ctas > 0 and self.overlap_streams):
+            return 0
+        rows = self._mid_rows(p.B, min(self._sm_count(), self.mid_bwd_ctas))
+        grid = -(-p.B // rows)
+        return grid if grid <= self._sm_count() // 2 else 0
+
     def _mid_rows(self, B, ctas):
         """Cells per CTA (a multiple of 4, <= 64) so that at most ``ctas`` CTAs cover B cells."""
         rows = max(4, -(-B // max(ctas, 1)))
@@ -655,7 +666,7 @@ class VAEEngine:
         d.B, d.L, d.n_enc, d.n_dec = B, L, len(self.enc), len(self.dec)
         sms = self._sm_count()
         d.rows_per_cta = self._mid_rows(B, min(sms, self.mid_bwd_ctas) if (
-            backward and self.mid_bwd_ctas > 0) else sms)
+            backward and self.mid_bwd_ctas > 0 and self.overlap_streams) else sms)
         for i, l in enumerate(self.enc):
             d.enc[i] = K.mid_layer(
                 w=l.w if i else None, dw=l.dw if i else None, beta=l.beta if l.bn else None,
@@ -681,6 +692,10 @@ class VAEEngine:
         d.kl_weight = self.kl_weight
         d.scalars = self.scalars.data_ptr()
         d.barrier, d.error = p.mid_bar.data_ptr(), p.mid_err.data_ptr()
+        if __import__("os").environ.get("SCVAE_MID_TIMELINE"):       # development aid
+            tl = torch.zeros(160 * 32, dtype=torch.int64, device=dev)
+            setattr(p, key + "_timeline", tl)
+            d.timeline = tl.data_ptr()
         if backward:
             self._plan_backward(p)
             self._dy1_16(p)
@@ -1045,11 +1060,10 @@ class VAEEngine:
         dd_in = p.d_decH[-1] if self.dec else p.dZ
         p.head_join = None
         mid = getattr(p, "mid_done", False)
-        if mid:
+
+        def mid_backward():
             # decoder -> sample / KL -> posterior -> encoder backward, log p finish and the bound in
-            # ONE persistent kernel.  It runs BEFORE the head weight-gradient GEMMs are forked to
-            # the side stream: its grid barriers need all of its CTAs resident, and persistent GEMM
-            # CTAs holding most SMs would make it wait for them.
+            # ONE persistent kernel
             md = self._mid_desc(p, backward=True)
             dd = p.d_decH[-1]
             md.dd_parts, md.dd_ld, md.dd_slice, md.dd_nsplit = dd.data_ptr(), dd.stride(0), 0, 1
@@ -1060,6 +1074,15 @@ class VAEEngine:
             md.deterministic = 0
             self.set_step_scalars(None, warm_up_weight)
             K.vae_mid_bwd(md)
+
+        # The kernel's grid barriers need all of its CTAs resident.  Beside the persistent head
+        # weight-gradient GEMMs of the side stream that holds when the two share the SMs by
+        # construction (GEMM CTAs capped at #SMs - mid CTAs, one CTA per SM each); otherwise the
+        # kernel runs first.
+        share = bool(mid and p.fused_done and self.overlap_streams and self._mid_bwd_grid(p) > 0)
+        side_ctas = self._sm_count() - self._mid_bwd_grid(p) if share else self.side_gemm_ctas
+        if mid and not share:
+            mid_backward()
         if p.fused_done:
             # dd came out of the fused kernel; dW = da^T d from the fp16 da (per head).  These
             # two HBM-bound products (and, data-parallel, the all-reduce of their 2/3 of the
@@ -1078,7 +1101,7 @@ class VAEEngine:
                 ctx = contextlib.nullcontext()
             with ctx:
                 # leave some SMs to the small kernels of the main stream
-                old = K.gemm_sm_limit(self.side_gemm_ctas) if self.overlap_streams else 0
+                old = K.gemm_sm_limit(side_ctas) if self.overlap_streams else 0
                 for h in range(self.P):
                     K.gemm_f16(K.GEMM_TN, self.Gn, l.in_p, M,
                                p.dA16[:, h * self.Gh:h * self.Gh + self.Gn], p.D16,
@@ -1108,6 +1131,8 @@ class VAEEngine:
             self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, M, p.dA, d_in, l.dw)
             self._gemm(p, K.GEMM_NN, M, l.n_in, l.n_out, p.dA, l.w, dd_in)
         if mid:
+            if share:
+                mid_backward()
             # the first layer's weight gradient on the tensor cores
             l = self.enc[0]
             # (dY1 as fp16 + remainder: the batch-norm backward makes this sum cancel heavily)
