@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the C3 / C4 shaped extra configurations (BASELINE.json configs[2..3])")
     ap.add_argument("--no-parity", action="store_true",
                     help="skip the untimed oracle check of one timed-path minibatch")
     return ap.parse_args()
@@ -281,6 +283,132 @@ def parity_check(args, eng, loop, data, csr, rows):
             "tolerance": tol,
             "pass": bool(max(rel.values()) <= tol and lp_rel <= tol and mu_rel <= tol),
             "fused_16bit_path": bool(plan.fused_done)}
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[2] and configs[3] at their stated shapes (not the headline metric): a short
+# timed run each, with the same oracle check as the headline configuration
+# ---------------------------------------------------------------------------------------------
+def _time_steps(step, steps, warmup):
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def _timed_kernels(K, names, run, repeats):
+    """Per-call CUDA-event time of the named C-ABI wrappers over `repeats` eager runs."""
+    evs = {k: [] for k in names}
+    originals = {k: getattr(K, k) for k in names}
+
+    def wrap(name):
+        def timed(*a, **kw):
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            originals[name](*a, **kw)
+            e_.record()
+            evs[name].append((s_, e_))
+        return timed
+    for k in names:
+        setattr(K, k, wrap(k))
+    try:
+        for i in range(repeats):
+            run(i)
+        torch.cuda.synchronize()
+    finally:
+        for k in names:
+            setattr(K, k, originals[k])
+    return {k: sum(s_.elapsed_time(e_) for s_, e_ in v) / repeats for k, v in evs.items() if v}
+
+
+def extra_configs(dev):
+    """C3 shape: VAE, zero-inflated NB, 28 000 genes, latent 100 (a 32 768-cell shard of the 1.3 M
+    cells: a step touches one minibatch, so the per-step work is that of the full matrix);
+    C4 shape: GMVAE, K = 20 clusters, 20 000 genes, NB, latent 50.  Each: cells/s of CUDA-graph
+    replayed training steps, the dominant kernel, and the oracle check of one replayed step."""
+    from oracle import scvae_oracle as O
+    from scvae_b200 import kernels as K
+    from scvae_b200.engine import VAEEngine
+    from scvae_b200.gmvae_engine import GMVAEEngine
+    from scvae_b200.hotloop import ResidentCSR, TrainLoop
+    out = []
+    heavy = ["heads_fused_bwd", "gemm_f16", "gemm_f16_split", "gemm", "csr_densify", "adam_clip_step",
+             "vae_mid_fwd", "vae_mid_bwd", "likelihood_bwd"]
+
+    def one(name, make_engine, cfg, forward, n_cells, G, L, B, parity_B, steps, bound_names):
+        csr = make_csr(n_cells, G, 0.07, seed=61, device=dev)
+        data = ResidentCSR(csr, dev)
+        eng = make_engine()
+        loop = TrainLoop(eng, B, seed=5, use_graph=True)
+        n_batches = n_cells // B
+        perm = torch.from_numpy(numpy.random.RandomState(3).permutation(n_cells)).to(dev)
+
+        def step(i):
+            b = i % n_batches
+            loop.rows.copy_(perm[b * B:(b + 1) * B])
+            return loop.step(data, 1e-4, 1.0)
+        ms = _time_steps(step, steps, 3)
+        loop.use_graph = False
+        overlap, eng.overlap_streams = eng.overlap_streams, False
+        per = _timed_kernels(K, heavy, step, 3)
+        eng.overlap_streams = overlap
+        loop.use_graph = True
+        top = max(per, key=per.get)
+        entry = {"workload": name, "minibatch": B, "steps": steps, "ms_per_step": ms,
+                 "value": B / (ms * 1e-3), "unit": UNIT,
+                 "dominant_kernel": {"entry_point": top, "ms_per_step": round(per[top], 4),
+                                     "share_of_step": round(per[top] / ms, 3)},
+                 "eager_ms_per_step_by_kernel": {k: round(v, 4) for k, v in per.items()}}
+        # oracle check of one replayed step on a smaller minibatch of the same data and model
+        ploop = TrainLoop(eng, parity_B, seed=9, use_graph=True)
+        rows = perm[:parity_B]
+        ploop.rows.copy_(rows)
+        before = {k: v.double() for k, v in eng.export_parameters().items()}
+        bound = ploop.step(data, 1e-4, 1.0)
+        torch.cuda.synchronize()
+        bound = bound.cpu().numpy().astype(numpy.float64)
+        plan = ploop.plan
+        x = torch.from_numpy(csr[rows.cpu().numpy()].toarray()).double()
+        eps = plan.eps.cpu().double()
+        ref = forward(cfg, before, x, eps, parity_B)
+        rel = {n: abs(bound[i] - ref[n].item()) / (abs(ref[n].item()) + 1e-30)
+               for i, n in enumerate(bound_names)}
+        lp_ref = ref["log_p_x_given_z"].reshape(-1)
+        lp_rel = ((plan.logp.cpu().double()[:lp_ref.numel()] - lp_ref).abs().max()
+                  / lp_ref.abs().max()).item()
+        entry["parity"] = {"minibatch": parity_B, "rel_err": dict(rel, per_cell_log_p_max=lp_rel),
+                           "tolerance": 1e-3,
+                           "pass": bool(max(rel.values()) <= 1e-3 and lp_rel <= 1e-3),
+                           "fused_16bit_path": bool(plan.fused_done)}
+        out.append(entry)
+        del loop, ploop, eng, data
+        torch.cuda.empty_cache()
+
+    G3, L3 = 28000, 100
+    lik3 = "zero-inflated negative binomial"
+    cfg3 = O.VAEConfig(G3, L3, [100], lik3)
+    one("C3 shape: VAE, 1.3M x 28000 genes synthetic (32768-cell shard resident), zero-inflated "
+        "negative binomial, latent 100, hidden [100], R=S=1",
+        lambda: VAEEngine(G3, L3, [100], lik3, device=dev, seed=0), cfg3,
+        lambda cfg, prm, x, eps, b: O.vae_forward(cfg, prm, x, x, eps.reshape(1, b, L3), is_training=True),
+        32768, G3, L3, 4096, 1024, 30,
+        ["lower_bound", "lower_bound_weighted", "reconstruction_error", "kl_divergence"])
+    G4, L4, K4 = 20000, 50, 20
+    cfg4 = O.GMVAEConfig(G4, L4, K4, [100], "negative binomial", 1, 1, True)
+    one("C4 shape: GMVAE, K=20 clusters, 68000 x 20000 genes synthetic (16384-cell shard resident), "
+        "negative binomial, latent 50, hidden [100], R=S=1",
+        lambda: GMVAEEngine(G4, L4, K4, [100], "negative binomial", device=dev, seed=0), cfg4,
+        lambda cfg, prm, x, eps, b: O.gmvae_forward(cfg, prm, x, x, eps.reshape(K4, 1, b, L4), is_training=True),
+        16384, G4, L4, 1024, 128, 10,
+        ["lower_bound", "lower_bound_weighted", "reconstruction_error", "kl_divergence_z",
+         "kl_divergence_y"])
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -545,6 +673,14 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
 
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        # free the headline configuration's buffers first
+        try:
+            extra = extra_configs(dev)
+        except Exception as exc:
+            extra = {"error": repr(exc)}
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sub = csr[:min(args.cells, 16384)]
@@ -564,6 +700,7 @@ def run_b200(args):
         }
         line["gradient_exchange"] = exchange     # (not in `config`: both arms name one workload)
         line["parity"] = parity
+        line["extra_configs"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         # CUDA graphs that captured NCCL kernels must die before the communicator does; guard

@@ -153,7 +153,7 @@ class VAEEngine:
         self.mid_fused = __import__("os").environ.get("SCVAE_MID_FUSED", "1") != "0"
         # CTAs of the backward middle kernel when it shares the SMs with the side-stream GEMMs
         # (0: never share, run it first on all SMs)
-        self.mid_bwd_ctas = int(__import__("os").environ.get("SCVAE_MID_BWD_CTAS", "64"))
+        self.mid_bwd_ctas = int(__import__("os").environ.get("SCVAE_MID_BWD_CTAS", "74"))
 
         for arch in (inference_architecture, generative_architecture):
             if arch not in ("MLP", "LFM"):
@@ -590,9 +590,11 @@ class VAEEngine:
         p.shadow_fork = p.shadow_fork_ev
 
     def _use_tc(self, M, N, Kd):
-        """tcgen05 kernel for every product with a long reduction or a large tile count; the
-        exact-fp32 FFMA kernel keeps the tiny ones (e.g. 100 x 100 x 101 at minibatch 100)."""
-        return self.tensor_cores and (Kd >= 256 or M * N * Kd >= (1 << 22))
+        """tcgen05 kernel for every product with a long reduction or a very large output; the
+        exact-fp32 FFMA kernel keeps the hidden-layer-sized ones."""
+        # (kind::tf32 truncates its fp32 operands -- a -5e-4 relative bias per product that batch norm
+        # does not remove behind the posterior heads -- so the small products stay exact)
+        return self.tensor_cores and (Kd >= 512 or M * N * Kd >= (1 << 28))
 
     def _gemm(self, p, layout, M, N, Kd, A, Bm, C, accumulate=False):
         tc = self._use_tc(M, N, Kd)
@@ -750,7 +752,7 @@ class VAEEngine:
         p.have_x = True
         if self.fused_heads and (t is None or t is x):
             # 16-bit copies are exact only for integer counts below 65536 (fp16: <= 2048)
-            if bool(((x == x.round()) & (x >= 0) & (x <= 65535)).all()):
+            if bool(((x == x.round()) & (x >= 0) & (x <= 65504)).all()):
                 p.t16_is_x16 = bool((x <= 2048).all())
                 K.f32_to_f16(p.X, self.G + 1, self._x16(p))
                 if not p.t16_is_x16:

@@ -395,6 +395,41 @@ class GMVAEEngine(VAEEngine):
         else:
             K.act_bwd(dH, H, layer.n_out, dY, relu=True)
 
+    # ---- gene-axis products of the two encoders --------------------------------------------------
+    # With the 16-bit minibatch at hand (integer counts) they run as fp16 products with the weight
+    # (forward) resp. the output gradient (weight gradient) split into fp16 + rounding remainder
+    # (scvae_gemm_f16_split): exact counts x ~22-bit weights, half the HBM traffic of the tf32
+    # product and none of its truncation bias.
+    def _x_product(self, p, l, out):
+        B = p.B
+        if self.tensor_cores and p.have_t16:
+            key = "_w16_" + l.name
+            bufs = getattr(p, key, None)
+            if bufs is None:
+                hi = torch.zeros(l.n_out, (self.G + 8) & ~7, dtype=torch.float16, device=self.device)
+                bufs = (hi, torch.zeros_like(hi))
+                setattr(p, key, bufs)
+            K.f32_to_f16_split(l.w, l.n_in + 1, bufs[0], bufs[1])
+            self._gemm16_split(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, p.X16, bufs[0], bufs[1], 2, out)
+        else:
+            self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, p.X, l.w, out)
+
+    def _x_wgrad(self, p, l, dY):
+        B = p.B
+        if self.tensor_cores and p.have_t16:
+            key = "_dy16_" + l.name
+            bufs = getattr(p, key, None)
+            if bufs is None:
+                hi = torch.zeros(B, (l.n_out + 7) & ~7, dtype=torch.float16, device=self.device)
+                bufs = (hi, torch.zeros_like(hi))
+                setattr(p, key, bufs)
+            scale = 2.0 ** round(math.log2(max(p.RS * B, 16) / 16.0))
+            K.f32_to_f16_split(dY, l.n_out, bufs[0], bufs[1], scale=scale)
+            self._gemm16_split(p, K.GEMM_TN, l.n_out, l.in_p, B, bufs[0], p.X16, bufs[1], 1, l.dw,
+                               alpha=1.0 / scale)
+        else:
+            self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, dY, p.X, l.dw)
+
     # ------------------------------------------------------------------ forward ------------
     def forward(self, p, is_training, R, S, warm_up_weight=1.0, update_moving=None,
                 with_backward=False, deterministic=False):
@@ -413,7 +448,10 @@ class GMVAEEngine(VAEEngine):
         # --- q(y|x) ---------------------------------------------------------------------------
         h = p.X
         for i, l in enumerate(self.qy_enc):
-            self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, h, l.w, p.qyY[i])
+            if i == 0:
+                self._x_product(p, l, p.qyY[i])
+            else:
+                self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, h, l.w, p.qyY[i])
             self._bn_fwd(p, l, p.qyY[i], p.qyH[i], p.qy_mean[i], p.qy_rstd[i], is_training,
                          update_moving, 1)
             h = p.qyH[i]
@@ -424,7 +462,7 @@ class GMVAEEngine(VAEEngine):
             self._refresh_log_py()
         # --- q(z|x, y=k) for all k ----------------------------------------------------------
         l = self.qz_enc[0]
-        self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, p.X, l.w, p.XW)
+        self._x_product(p, l, p.XW)
         K.group_offset_fwd(p.XW, self.qz_wy, Kc, B, l.n_out, p.qzY[0])
         self._bn_fwd(p, l, p.qzY[0], p.qzH[0], p.qz_mean[0], p.qz_rstd[0], is_training,
                      update_moving, Kc)
@@ -560,7 +598,7 @@ class GMVAEEngine(VAEEngine):
                 self._gemm(p, K.GEMM_NN, KB, l.n_in, l.n_out, p.d_qzY[i], l.w, p.d_qzH[i - 1])
             else:
                 K.group_offset_bwd(p.d_qzY[0], Kc, B, l.n_out, dx=p.dXW, dt=self.d_qz_wy)
-                self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.dXW, p.X, l.dw)
+                self._x_wgrad(p, l, p.dXW)
         # q(y|x) encoder
         p.dlogits[:, :Kc].copy_(p.dlogits_c)
         l = self.qy_logits
@@ -570,8 +608,10 @@ class GMVAEEngine(VAEEngine):
             l = self.qy_enc[i]
             self._bn_bwd(p, l, p.d_qyH[i], p.qyY[i], p.qyH[i], p.qy_mean[i], p.qy_rstd[i],
                          p.d_qyY[i], 1, False)
-            h_in = p.qyH[i - 1] if i > 0 else p.X
-            self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.d_qyY[i], h_in, l.dw)
+            if i > 0:
+                self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.d_qyY[i], p.qyH[i - 1], l.dw)
+            else:
+                self._x_wgrad(p, l, p.d_qyY[i])
             if i > 0:
                 self._gemm(p, K.GEMM_NN, B, l.n_in, l.n_out, p.d_qyY[i], l.w, p.d_qyH[i - 1])
 

@@ -28,7 +28,7 @@ def _as_csr_arrays(matrix):
 
 def _counts_fit_u16(data):
     """Integer counts below 65536: the 16-bit target copy of the fused heads is exact."""
-    return bool(data.size == 0 or (data.min() >= 0 and data.max() <= 65535
+    return bool(data.size == 0 or (data.min() >= 0 and data.max() <= 65504
                                    and numpy.array_equal(data, numpy.floor(data))))
 
 
