@@ -41,6 +41,16 @@ extern "C" {
 #define SCVAE_LIK_ZIP     2 /* heads: pi, log_lambda       DU:247-264, ZI:180-199 */
 #define SCVAE_LIK_ZINB    3 /* heads: pi, p, log_r         DU:283-305, ZI:180-199 */
 
+/* Continuous / binary reconstruction distributions (DU:31-73, :125-245): their own row kernels
+ * (scvae_continuous_likelihood / scvae_continuous_moments). */
+#define SCVAE_LIK_GAUSSIAN          8  /* heads: mu, log_sigma                 DU:31-50 */
+#define SCVAE_LIK_SOFTPLUS_GAUSSIAN 9  /* heads: mean, softplus_scale          DU:52-73 ("modified gaussian") */
+#define SCVAE_LIK_LOG_NORMAL       10  /* heads: mean, variance                DU:125-140 */
+#define SCVAE_LIK_GAMMA            11  /* heads: concentration, rate           DU:166-180 */
+#define SCVAE_LIK_BERNOULLI        12  /* heads: logits                        DU:193-204 */
+#define SCVAE_LIK_LOMAX            13  /* heads: log_concentration, log_scale  DU:230-245, lomax.py:177-247 */
+#define SCVAE_LIK_EMG              14  /* heads: location, scale, rate         DU:142-164, exponentially_modified_normal.py:196-234 */
+
 /* GEMM operand layouts. C is always (M, N) row-major. */
 #define SCVAE_GEMM_NT 0 /* A (M,K) row-major, B (N,K) row-major : forward  Y = A W^T       */
 #define SCVAE_GEMM_NN 1 /* A (M,K) row-major, B (K,N) row-major : dgrad    dA = dY W       */
@@ -264,6 +274,24 @@ int scvae_constrained_poisson_mixture_moments(const float *a, int64_t lda, const
                                               const float *y, int64_t ldy, float *p_x_mean,
                                               float *p_x_stddev, float *stddev_of_mean,
                                               int64_t ldo, void *stream);
+
+/* ---- f3: continuous / binary reconstruction distributions -----------------------------------------
+ * log p(t | a) summed over the genes of every (sample, cell) row and, when `da` is given, the
+ * gradient go * d log p / d a, for kind = SCVAE_LIK_GAUSSIAN .. SCVAE_LIK_EMG.  `a` holds the P head
+ * PRE-activations (head h at column h * head_stride); the kernel applies the head's activation and
+ * clip (VAE:2466-2489: theta = clip(act(a), lo + tiny, hi - tiny), zero gradient outside the clip)
+ * and the closed forms of TFP 0.7 Normal / LogNormal / Gamma / Bernoulli and of the reference's
+ * Lomax / ExponentiallyModifiedNormal classes.  Targets tile over the rows (row m reads target row
+ * m % t_rows).  scvae_continuous_moments: p_x_mean / p_x_stddev / stddev_of_p_x_given_z_mean as
+ * scvae_likelihood_moments (Lomax: nan / inf where a moment does not exist, allow_nan_stats). */
+int scvae_continuous_num_heads(int kind);
+int scvae_continuous_likelihood(int kind, const float *t, int64_t ldt, int t_rows, const float *a,
+                                int64_t lda, int64_t head_stride, int M, int G, const float *go,
+                                float go_scalar, float *da, int64_t ldda, int64_t dhead_stride,
+                                float *logp, void *stream);
+int scvae_continuous_moments(int kind, const float *a, int64_t lda, int64_t head_stride, int B, int G,
+                             int RS, int K, const float *y, int64_t ldy, float *p_x_mean,
+                             float *p_x_stddev, float *stddev_of_mean, int64_t ldo, void *stream);
 
 /* ---- a4 + a5 fused: likelihood heads without the (cells x P*genes) round trip ----------------
  * One kernel computes a = d W^T (tcgen05, fp16 operands), log p(t | a) summed over genes, its

@@ -127,6 +127,11 @@ SIGNATURES = {
                                      c_ptr]),
     "scvae_likelihood_moments": (c_int, [c_int, c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_int,
                                          c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "scvae_continuous_num_heads": (c_int, [c_int]),
+    "scvae_continuous_likelihood": (c_int, [c_int, c_ptr, c_i64, c_int, c_ptr, c_i64, c_i64, c_int,
+                                            c_int, c_ptr, c_f32, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
+    "scvae_continuous_moments": (c_int, [c_int, c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_int,
+                                         c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "scvae_decoder_features": (c_int, [c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_int, c_ptr, c_ptr]),
     "scvae_piecewise_likelihood": (c_int, [c_int, c_int, c_ptr, c_i64, c_int, c_ptr, c_i64, c_i64, c_int,
                                            c_int, c_ptr, c_f32, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),

@@ -128,17 +128,19 @@ class VAEEngine:
         # constrained Poisson: softmax over the genes of a cell, N = count sum of the cell as a
         # parameter (VAE:2492-2496) -- a row kernel of its own, never the fused heads
         self.constrained = self.kind == K.CONSTRAINED_POISSON
+        # continuous / binary reconstruction distributions: row kernels of their own
+        self.continuous = self.kind in K.CONTINUOUS_KINDS
         # piecewise-categorical likelihood (`-k`, CAT:210-274): k_max + 1 class-logit heads
         # behind the P heads of the count distribution, a row kernel of its own
         self.k_max = int(number_of_reconstruction_classes or 0)
-        if self.k_max and self.constrained:
+        if self.k_max and (self.constrained or self.continuous):
             raise ValueError("piecewise-categorical likelihoods wrap the Poisson / NB family")
         self.PT = self.P + (self.k_max + 1 if self.k_max else 0)      # head blocks of width Gn
         # (dropout: every head multiplies its own dropped copy of the decoder output, so neither
         # the fused heads kernel -- one shared operand -- nor the 16-bit-only minibatch assembly
         # that feeds it applies)
         self.fused_heads = (bool(fused_heads) and self.tensor_cores and not self.constrained
-                            and not self.k_max and not self.dropout_active)
+                            and not self.continuous and not self.k_max and not self.dropout_active)
         self.Gn = round4(self.G)
         self.Gp = aug(self.G)
         self.Gh = (self.G + 63) & ~63      # head stride of the fp16 buffers of the fused heads
@@ -1009,6 +1011,9 @@ class VAEEngine:
         elif self.constrained:
             K.constrained_poisson(tgt, A, M, self.G, p.count_sum_parameter, logp=logp, row_const=rc,
                                   go=go, go_scalar=go_scalar, da=da, lse=p.lse)
+        elif self.continuous:
+            K.continuous_likelihood(self.kind, tgt, A, self.Gn, M, self.G, logp=logp, go=go,
+                                    go_scalar=go_scalar, da=da)
         elif da is not None:
             K.likelihood_bwd(self.kind, tgt, A, self.Gn, M, self.G, da, logp=logp, row_const=rc,
                              go=go, go_scalar=go_scalar)
@@ -1325,6 +1330,9 @@ class VAEEngine:
             return [o[:, :self.G] for o in outs]
         if self.constrained:
             K.constrained_poisson_moments(p.A, p.lse, p.count_sum_parameter, p.B, self.G, RS, *outs)
+            return [o[:, :self.G] for o in outs]
+        if self.continuous:
+            K.continuous_moments(self.kind, p.A, self.Gn, p.B, self.G, RS, 1, None, *outs)
             return [o[:, :self.G] for o in outs]
         K.likelihood_moments(self.kind, p.A, self.Gn, p.B, self.G, RS, 1, None, *outs)
         return [o[:, :self.G] for o in outs]

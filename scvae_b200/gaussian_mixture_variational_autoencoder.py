@@ -339,6 +339,9 @@ class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
             if engine.k_max:       # mean of the Categorised distribution (P_K class heads, CAT:210-247)
                 K.piecewise_moments(engine.kind, engine.k_max, plan.A[:rows], engine.Gn, rows, G, 1,
                                     *outs)
+            elif engine.continuous:
+                K.continuous_moments(engine.kind, plan.A[:rows], engine.Gn, rows, G, 1, 1, None,
+                                     *outs)
             else:
                 K.likelihood_moments(engine.kind, plan.A[:rows], engine.Gn, rows, G, 1, 1, None,
                                      *outs)

@@ -72,11 +72,14 @@ class GMVAEEngine(VAEEngine):
         # constrained Poisson (rate = N softmax_g(a), N = the cell's count sum fed as
         # count_sum_parameter, GMVAE:419-429, :3170-3176): its own row kernel, never the fused heads
         self.constrained = self.kind == K.CONSTRAINED_POISSON
+        self.continuous = self.kind in K.CONTINUOUS_KINDS      # row kernels of csrc/continuous.cu
         # piecewise-categorical likelihood (`-k`, head P_K GMVAE:3192-3218): k_max + 1 class-logit
         # head blocks behind the P heads; its own row kernel, never the fused heads
         self.k_max = int(number_of_reconstruction_classes or 0)
         self.PT = self.P + (self.k_max + 1 if self.k_max else 0)
-        if self.k_max or self.constrained:
+        if self.k_max and self.continuous:
+            raise ValueError("piecewise-categorical likelihoods wrap the Poisson / NB family")
+        if self.k_max or self.constrained or self.continuous:
             self.fused_heads = False
         self.unit_variance = False
         self.nL = 2 * self.L
@@ -643,6 +646,9 @@ class GMVAEEngine(VAEEngine):
         if self.constrained:
             K.constrained_poisson_mixture_moments(p.A, p.lse_all, p.count_sum_parameter, p.B,
                                                   self.G, p.RS, self.K, p.y, *outs)
+            return [o[:, :self.G] for o in outs]
+        if self.continuous:
+            K.continuous_moments(self.kind, p.A, self.Gn, p.B, self.G, p.RS, self.K, p.y, *outs)
             return [o[:, :self.G] for o in outs]
         K.likelihood_moments(self.kind, p.A, self.Gn, p.B, self.G, p.RS, self.K, p.y, *outs)
         return [o[:, :self.G] for o in outs]

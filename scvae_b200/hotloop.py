@@ -50,6 +50,7 @@ class ResidentCSR:
         K.csr_row_constants(self.indptr, self.values, self.row_const)
         # optional per-cell decoder features (set by the model shell): batch ids as floats,
         # normalised count sums
+        self.targets = None                 # ResidentCSR of likelihood targets when they differ from x
         self.batch_index = None
         self.count_sum_feature = None
         self.count_sum_parameter = None     # raw count sums: N of the constrained Poisson
@@ -164,6 +165,14 @@ class TrainLoop:
             eng.set_batch_csr(p, src["indptr"], src["indices"], src["values"], None, rebase=True,
                               u16_ok=src["u16_ok"], f16_exact=src["f16_exact"],
                               train16=self.R == 1, row_const_all=src["row_const"])
+        targets = getattr(src, "targets", None) if isinstance(src, ResidentCSR) else None
+        if targets is not None:
+            # likelihood targets that differ from the network input (binarised values of the
+            # Bernoulli likelihood, VAE:854-857): a second resident matrix, same rows
+            if p.T is None:
+                p.T = torch.zeros(p.B, eng.Gp, dtype=torch.float32, device=eng.device)
+            K.csr_densify(targets.indptr, targets.indices, targets.values, self.rows, eng.G, p.T, None)
+            p.use_T = True
         if getattr(eng, "constrained", False):
             if not isinstance(src, ResidentCSR) or src.count_sum_parameter is None:
                 raise NotImplementedError("the constrained Poisson needs a resident data set with "

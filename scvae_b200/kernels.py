@@ -15,14 +15,32 @@ LIKELIHOOD_KINDS = {
     "zero-inflated poisson": 2,
     "zero-inflated negative binomial": 3,
     "constrained poisson": 4,      # row kernel of its own (softmax over genes), not in the family
+    # continuous / binary reconstruction distributions (csrc/continuous.cu)
+    "gaussian": 8,
+    "softplus gaussian": 9,
+    "modified gaussian": 9,        # DU:306: an alias
+    "log-normal": 10,
+    "gamma": 11,
+    "bernoulli": 12,
+    "lomax": 13,
+    "exponentially_modified_gaussian": 14,
 }
 CONSTRAINED_POISSON = 4
+CONTINUOUS_KINDS = frozenset(range(8, 15))
 LIKELIHOOD_HEADS = {
     "constrained poisson": ["lambda"],
     "poisson": ["log_lambda"],
     "negative binomial": ["p", "log_r"],
     "zero-inflated poisson": ["pi", "log_lambda"],
     "zero-inflated negative binomial": ["pi", "p", "log_r"],
+    "gaussian": ["mu", "log_sigma"],
+    "softplus gaussian": ["mean", "softplus_scale"],
+    "modified gaussian": ["mean", "softplus_scale"],
+    "log-normal": ["mean", "variance"],
+    "gamma": ["concentration", "rate"],
+    "bernoulli": ["logits"],
+    "lomax": ["log_concentration", "log_scale"],
+    "exponentially_modified_gaussian": ["location", "scale", "rate"],
 }
 GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
 
@@ -109,6 +127,24 @@ def heads_fused_bwd(kind, d16, w16, head_stride, t16, M, G, da16, dd, dd_cols, l
                                          float(go_scalar), float(scale), _p(da16), _p(dd), _ld(dd),
                                          dd_cols, _p(logp), _p(workspace), _stream()),
                "heads_fused_bwd")
+
+
+def continuous_likelihood(kind, t, a, head_stride, M, G, logp=None, go=None, go_scalar=1.0, da=None):
+    """log p (and, with ``da``, its gradient) of a continuous / binary reconstruction distribution."""
+    _f32(t, a)
+    lib = _lib.load()
+    _lib.check(lib.scvae_continuous_likelihood(kind, _p(t), _ld(t), t.shape[0], _p(a), _ld(a),
+                                               head_stride, M, G, _p(go), float(go_scalar), _p(da),
+                                               _ld(da) if da is not None else 0, head_stride,
+                                               _p(logp), _stream()), "continuous_likelihood")
+
+
+def continuous_moments(kind, a, head_stride, B, G, RS, K_, y, p_x_mean, p_x_stddev, stddev_of_mean):
+    lib = _lib.load()
+    _lib.check(lib.scvae_continuous_moments(kind, _p(a), _ld(a), head_stride, B, G, RS, K_, _p(y),
+                                            _ld(y) if y is not None else 0, _p(p_x_mean),
+                                            _p(p_x_stddev), _p(stddev_of_mean), _ld(p_x_mean),
+                                            _stream()), "continuous_moments")
 
 
 def gemm(layout, M, N, K, A, B, C, accumulate=False, tensor_cores=True, workspace=None):

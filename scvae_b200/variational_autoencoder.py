@@ -28,9 +28,12 @@ from .model_utilities import (
 
 RECONSTRUCTION_DISTRIBUTIONS = [
     "poisson", "negative binomial", "zero-inflated poisson", "zero-inflated negative binomial",
-    # known to the reference, not on the B200 hot path yet:
-    "bernoulli", "constrained poisson", "lomax", "gaussian", "log-normal", "gamma",
-    "exponentially_modified_gaussian", "categorical", "multinomial",
+    "constrained poisson",
+    # continuous / binary distributions (DU:31-73, :125-245; csrc/continuous.cu)
+    "bernoulli", "lomax", "gaussian", "softplus gaussian", "modified gaussian", "log-normal", "gamma",
+    "exponentially_modified_gaussian",
+    # known to the reference, not on the B200 hot path (a categorical / multinomial over genes):
+    "categorical", "multinomial",
 ]
 VAE_LATENT_DISTRIBUTIONS = ["gaussian", "unit-variance gaussian"]
 
@@ -480,13 +483,20 @@ class VariationalAutoencoder:
         data = ResidentCSR(scipy.sparse.csr_matrix(x_train, dtype=numpy.float32), engine.device)
         self._attach_features(data, training_set)
         if t_train is not x_train:
-            raise NotImplementedError("Separate preprocessed inputs are supported by evaluate() "
-                                      "only; training expects x == t (no preprocessing).")
+            # targets other than the network input (binarised values for the Bernoulli likelihood,
+            # raw counts behind preprocessed inputs; VAE:849-861): a second resident matrix
+            data.targets = ResidentCSR(scipy.sparse.csr_matrix(t_train, dtype=numpy.float32),
+                                       engine.device)
+            data.u16_ok = False             # (the 16-bit fused path reads x as its own target)
         if validation_set:
             x_valid, t_valid = self._inputs(validation_set, self.reconstruction_distribution_name)
             valid_data = ResidentCSR(scipy.sparse.csr_matrix(x_valid, dtype=numpy.float32),
                                      engine.device)
             self._attach_features(valid_data, validation_set)
+            if t_valid is not x_valid:
+                valid_data.targets = ResidentCSR(scipy.sparse.csr_matrix(t_valid, dtype=numpy.float32),
+                                                 engine.device)
+                valid_data.u16_ok = False
 
         training_writer = SummaryWriter(os.path.join(log_directory, "training")) \
             if is_main else None
@@ -568,12 +578,12 @@ class VariationalAutoencoder:
                 epoch + 1, format_duration(epoch_duration), n_train / max(epoch_duration, 1e-9)))
 
             # evaluation passes with the *training* sample counts (VAE:1103-1106, 1262-1265)
-            results = {"training": self._evaluate_pass(engine, data, None, minibatch_size, R, S,
-                                                       seed=noise_seed + 1000 + epoch)}
+            results = {"training": self._evaluate_pass(engine, data, data.targets, minibatch_size, R,
+                                                       S, seed=noise_seed + 1000 + epoch)}
             if validation_set:
                 results["validation"] = self._evaluate_pass(
-                    engine, valid_data, None, min(minibatch_size, valid_data.shape[0]), R, S,
-                    seed=noise_seed + 2000 + epoch)
+                    engine, valid_data, valid_data.targets,
+                    min(minibatch_size, valid_data.shape[0]), R, S, seed=noise_seed + 2000 + epoch)
             for kind, result in results.items():
                 if numpy.isnan(result["lower_bound"]):
                     raise ArithmeticError("Aborting. The ELBO for the {} set became indefinite."

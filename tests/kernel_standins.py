@@ -24,6 +24,7 @@ GEMM_NT, GEMM_NN, GEMM_TN = RealK.GEMM_NT, RealK.GEMM_NN, RealK.GEMM_TN
 LIKELIHOOD_KINDS = RealK.LIKELIHOOD_KINDS
 LIKELIHOOD_HEADS = RealK.LIKELIHOOD_HEADS
 CONSTRAINED_POISSON = RealK.CONSTRAINED_POISSON
+CONTINUOUS_KINDS = RealK.CONTINUOUS_KINDS
 _KIND_NAMES = {v: k for k, v in LIKELIHOOD_KINDS.items()}
 BN_EPSILON, BN_DECAY = 1e-3, 0.999
 
@@ -341,6 +342,31 @@ def constrained_poisson(t, a, M, G, count_sum, logp=None, row_const=None, go=Non
     _fwd_bwd(CONSTRAINED_POISSON, t, a, 0, M, G, logp, da, go, go_scalar, count_sum=count_sum)
     if lse is not None:
         lse[:M] = torch.logsumexp(a[:M, :G].double(), dim=1)
+
+
+def continuous_likelihood(kind, t, a, head_stride, M, G, logp=None, go=None, go_scalar=1.0, da=None):
+    """csrc/continuous.cu: activation + clip of the heads, closed-form log density, gradient."""
+    _log("continuous_likelihood")
+    leaf = a.double().detach().clone().requires_grad_(da is not None)
+    name, theta = _theta(kind, leaf, head_stride, M, G)
+    rows = O.continuous_log_prob(name, _targets(t, M, G), theta).sum(dim=-1)
+    if logp is not None:
+        logp[:M] = rows.detach()
+    if da is not None:
+        upstream = go[:M].double() if go is not None else torch.full((M,), float(go_scalar),
+                                                                     dtype=torch.float64)
+        grad, = torch.autograd.grad(rows, leaf, grad_outputs=upstream)
+        da[:M] = grad[:M, :da.shape[1]]
+
+
+def continuous_moments(kind, a, head_stride, B, G, RS, K_, y, p_x_mean, p_x_stddev, stddev_of_mean):
+    _log("continuous_moments")
+    name, theta = _theta(kind, a.double(), head_stride, K_ * RS * B, G)
+    m, v = O.continuous_moments(name, theta)
+    if K_ == 1 and y is None:
+        _write_moments(m, v, B, G, RS, (p_x_mean, p_x_stddev, stddev_of_mean))
+    else:
+        _write_mixture_moments(m, v, y, K_, B, G, RS, (p_x_mean, p_x_stddev, stddev_of_mean))
 
 
 def _write_moments(m, v, B, G, RS, outs):

@@ -773,3 +773,77 @@ def test_gemm_f16_split_operand(layout, which, M, N, Kd):
     torch.cuda.synchronize()
     err = (C[:, :N].cpu().double() - ref).abs().max().item()
     assert err <= 1e-5 * ref.abs().max().item() + 1e-6 * math.sqrt(Kd), (layout, which, err, ref.abs().max().item())
+
+
+CONTINUOUS = ["gaussian", "softplus gaussian", "log-normal", "gamma", "bernoulli", "lomax",
+              "exponentially_modified_gaussian"]
+
+
+@pytest.mark.parametrize("kind", CONTINUOUS)
+@pytest.mark.parametrize("M,G,tile", [(37, 203, 1), (64, 2052, 2)])
+def test_continuous_likelihood_fwd_bwd_and_moments(kind, M, G, tile):
+    """csrc/continuous.cu against the oracle (fp64): log p per row, gradient w.r.t. the head
+    pre-activations (activation, clip and density in one), moments."""
+    from scvae_b200 import kernels as K
+    rng = numpy.random.RandomState(5)
+    heads = O.LIKELIHOODS[kind]
+    P = len(heads)
+    B = M // tile if M % tile == 0 else M
+    tile = M // B
+    Gn = (G + 3) & ~3
+    a = (rng.randn(M, P, G) * 1.5).astype(numpy.float32)
+    if kind == "gaussian":
+        a[:, 1, ::17] = 4.0            # log_sigma beyond its clip
+    if kind == "lomax":
+        a[:, 0, ::19] = 11.0           # log_concentration beyond its clip
+    if kind == "bernoulli":
+        t = (rng.rand(B, G) < 0.3).astype(numpy.float32)
+    elif kind in ("gaussian", "softplus gaussian", "exponentially_modified_gaussian"):
+        t = (rng.randn(B, G) * 3).astype(numpy.float32)
+    else:
+        t = (rng.gamma(2.0, 1.5, (B, G)) + 0.05).astype(numpy.float32)
+    go = (-(0.5 + rng.rand(M)) / M).astype(numpy.float32)
+    dev = _dev()
+    A = torch.zeros(M, P * Gn, device=dev)
+    for h in range(P):
+        A[:, h * Gn:h * Gn + G] = torch.tensor(a[:, h])
+    T = torch.zeros(B, Gn, device=dev)
+    T[:, :G] = torch.tensor(t)
+    logp = torch.zeros(M, device=dev)
+    dA = torch.zeros(M, P * Gn, device=dev)
+    K.continuous_likelihood(K.LIKELIHOOD_KINDS[kind], T, A, Gn, M, G, logp=logp,
+                            go=torch.tensor(go).to(dev), da=dA)
+    logp_f = torch.zeros(M, device=dev)
+    K.continuous_likelihood(K.LIKELIHOOD_KINDS[kind], T, A, Gn, M, G, logp=logp_f)
+    torch.cuda.synchronize()
+    pre = [torch.tensor(a[:, h], dtype=torch.float64).requires_grad_(True) for h in range(P)]
+    theta = {head: O._clip_head(pre[h], head) for h, head in enumerate(heads)}
+    x64 = torch.tensor(t, dtype=torch.float64).repeat(tile, 1)
+    lp = O.continuous_log_prob(kind, x64, theta).sum(dim=1)
+    (lp * torch.tensor(go, dtype=torch.float64)).sum().backward()
+    ref = lp.detach().numpy()
+    assert numpy.isfinite(ref).all()
+    tol = 2e-5 if kind != "exponentially_modified_gaussian" else 2e-4     # erfc in fp32
+    assert numpy.abs(logp.cpu().numpy() - ref).max() <= tol * numpy.abs(ref).max() + 1e-3
+    assert torch.equal(logp, logp_f)
+    for h in range(P):
+        g = pre[h].grad
+        err = (dA[:, h * Gn:h * Gn + G].cpu().double() - g).abs().max().item()
+        assert err <= 5e-4 * g.abs().max().item() + 1e-9, (kind, heads[h], err, g.abs().max().item())
+    # moments (RS = tile samples per cell)
+    outs = [torch.zeros(B, Gn, device=dev) for _ in range(3)]
+    K.continuous_moments(K.LIKELIHOOD_KINDS[kind], A, Gn, B, G, tile, 1, None, *outs)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        m, v = O.continuous_moments(kind, theta)
+    m = m.reshape(tile, B, G)
+    v = v.reshape(tile, B, G)
+    mean = m.mean(dim=0)
+    vom = ((m - mean) ** 2).mean(dim=0)
+    want = [mean, torch.sqrt(vom + v.mean(dim=0)), torch.sqrt(vom)]
+    for got, w in zip(outs, want):
+        got = got[:, :G].cpu().double()
+        ok = torch.isfinite(w)
+        assert torch.equal(torch.isfinite(got), ok)            # nan / inf where a Lomax moment does not exist
+        scale = w[ok].abs().max().item() if ok.any() else 1.0
+        assert (got[ok] - w[ok]).abs().max().item() <= 2e-4 * scale + 1e-6

@@ -273,3 +273,33 @@ def test_gmvae_trains_with_free_nats_under_graph_capture(tmp_path, prior):
     assert len(curves["training"]["lower_bound"]) == 3
     assert numpy.isfinite(curves["training"]["lower_bound"]).all()
     assert curves["training"]["lower_bound"][-1] > curves["training"]["lower_bound"][0]
+
+
+@pytest.mark.parametrize("likelihood", ["gaussian", "softplus gaussian", "log-normal", "gamma", "bernoulli",
+                                        "lomax", "exponentially_modified_gaussian"])
+def test_train_evaluate_with_continuous_likelihoods(tmp_path, likelihood):
+    """`-r` choices outside the count family: train, evaluate, reconstruct, with the
+    Bernoulli likelihood reading the binarised values as its targets (VAE:854-857)."""
+    from scvae_b200.data_set import DataSet
+    from scvae_b200.variational_autoencoder import VariationalAutoencoder
+    from scvae_b200 import model_utilities as MU
+    x, labels = O.synthetic_counts(240, 40, n_types=3, seed=4, target_zero_fraction=0.5)
+    x = numpy.minimum(x, 30.0)
+    if likelihood in ("log-normal", "gamma"):
+        x = x + 1.0                      # strictly positive support
+    binarised = scipy.sparse.csr_matrix((x > 0).astype(numpy.float32)) if likelihood == "bernoulli" else None
+    full = DataSet("toy", values=scipy.sparse.csr_matrix(x), labels=labels.astype(str),
+                   binarised_values=binarised)
+    training, validation, test = full.split()
+    model = VariationalAutoencoder(
+        feature_size=40, latent_size=3, hidden_sizes=[24], reconstruction_distribution=likelihood,
+        log_directory=str(tmp_path), seed=2)
+    assert model.train(training, validation, number_of_epochs=3, minibatch_size=48,
+                       learning_rate=2e-3, shuffle_seed=0) == 0
+    curves = MU.load_learning_curves(model, ["training", "validation"])
+    lb = curves["training"]["lower_bound"]
+    assert len(lb) == 3 and numpy.isfinite(lb).all() and lb[-1] > lb[0]
+    transformed, reconstructed, latent = model.evaluate(test, minibatch_size=32)
+    assert reconstructed.values.shape == (test.number_of_examples, 40)
+    if likelihood != "lomax":            # (the Lomax mean does not exist for concentration <= 1: nan)
+        assert numpy.isfinite(reconstructed.values).all()

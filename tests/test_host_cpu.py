@@ -47,9 +47,14 @@ def test_option_validation_mirrors_the_scope():
     GaussianMixtureVariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
                                           number_of_latent_clusters=3,
                                           reconstruction_distribution="constrained poisson")
+    # the continuous / binary reconstruction distributions are built (csrc/continuous.cu)
+    for name in ("gamma", "gaussian", "modified gaussian", "log-normal", "bernoulli", "lomax",
+                 "exponentially_modified_gaussian"):
+        VariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
+                               reconstruction_distribution=name)
     with pytest.raises(NotImplementedError):
         VariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
-                               reconstruction_distribution="gamma")
+                               reconstruction_distribution="multinomial")
     with pytest.raises(TypeError):
         VariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
                                batch_correction=True)          # number of batches missing

@@ -93,6 +93,8 @@ def test_vae_autograd_matches_finite_differences(kind):
     cfg = O.VAEConfig(12, 3, [5], kind, number_of_importance_samples=2, number_of_monte_carlo_samples=2)
     params = O.vae_init_params(cfg, 2, D)
     x = torch.tensor(O.synthetic_counts(4, 12, seed=3)[0], dtype=D).clamp(max=30)
+    if kind in ("log-normal", "gamma"):
+        x = x + 0.5          # strictly positive support
     eps = torch.randn(4, 4, 3, generator=torch.Generator().manual_seed(0), dtype=D)
     state = O.AdamState(params)
     base = {k: v.clone() for k, v in params.items()}

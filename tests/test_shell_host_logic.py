@@ -117,3 +117,10 @@ def test_one_epoch_matches_oracle_on_cpu(shell_on_cpu, tmp_path):
 def test_gmvae_free_nats_on_cpu(shell_on_cpu, tmp_path, prior):
     G.test_gmvae_trains_with_free_nats_under_graph_capture(tmp_path, prior)
     assert "gmvae_bound" in shell_on_cpu
+
+
+@pytest.mark.parametrize("likelihood", ["gaussian", "log-normal", "gamma", "bernoulli", "lomax",
+                                        "exponentially_modified_gaussian"])
+def test_continuous_likelihoods_through_the_model_class_on_cpu(shell_on_cpu, tmp_path, likelihood):
+    G.test_train_evaluate_with_continuous_likelihoods(tmp_path, likelihood)
+    assert "continuous_likelihood" in shell_on_cpu and "continuous_moments" in shell_on_cpu
