@@ -91,6 +91,16 @@ int scvae_csr_densify_u16(const int64_t *indptr, const void *indices_u16, const 
                           const int64_t *rows, int B, int G, float *x, int64_t ldx,
                           float *row_const, int rebase, void *t16, int64_t ldt16, void *x16,
                           int64_t ldx16, void *stream);
+/* Streamed form of the same gather: the B rows of a minibatch arrive as ONE packed slab (a single
+ * host -> device copy per step, ~2 bytes per non-zero):
+ *   int32 rowptr[B + 1] at offset 0 (entry offsets relative to the slab's first entry),
+ *   float row_const[B] at off_const, uint8 blocks[B][ceil(G / 255)] at off_blocks (non-zeros of the
+ *   row per block of 255 genes: a count fits one byte), uint8 entries[nnz][1 + value_bytes] at
+ *   off_entries (gene index within its block, then the count as uint8 or little-endian uint16).
+ * Outputs as the 16-bit outputs of scvae_csr_densify; row_const (nullable) receives the slab's copy. */
+int scvae_csr_densify_packed(const void *slab, int64_t off_const, int64_t off_blocks,
+                             int64_t off_entries, int value_bytes, int B, int G, float *row_const,
+                             void *t16, int64_t ldt16, void *x16, int64_t ldx16, void *stream);
 /* Dense fp32 counts -> uint16 (clamped), zero padded to ldt16 columns. */
 int scvae_f32_to_u16(const float *x, int64_t ldx, int64_t rows, int G, void *t16, int64_t ldt16,
                      void *stream);

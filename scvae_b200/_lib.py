@@ -75,6 +75,8 @@ SIGNATURES = {
                                   c_int, c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
     "scvae_csr_densify_u16": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_i64, c_ptr,
                                       c_int, c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
+    "scvae_csr_densify_packed": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_ptr, c_ptr,
+                                         c_i64, c_ptr, c_i64, c_ptr]),
     "scvae_f32_to_u16": (c_int, [c_ptr, c_i64, c_i64, c_int, c_ptr, c_i64, c_ptr]),
     "scvae_csr_row_constants": (c_int, [c_ptr, c_ptr, c_int, c_i64, c_ptr, c_ptr]),
     "scvae_gather_f32": (c_int, [c_ptr, c_ptr, c_int, c_ptr, c_ptr]),

@@ -137,6 +137,121 @@ class StreamedCSR:
         return s
 
 
+class PackedStream:
+    """The count matrix stays in HOST memory; every step's rows travel as ONE packed slab (see
+    ``scvae_csr_densify_packed``: ~2 bytes per non-zero, a single host -> device copy per step)
+    into one of two device staging buffers on a copy stream while the previous step computes.
+
+    ``pack_epoch(order)`` lays the epoch out slab by slab in pinned memory (row order = the
+    epoch's permutation); ``fetch(slot, k)`` enqueues the copy of slab k.  For matrices beyond
+    HBM, and the host-to-device leg of `bench.py`'s end-to-end number."""
+
+    BLOCK = 255          # genes per block: a block's non-zero count fits one byte
+
+    def __init__(self, matrix, device, minibatch_size):
+        indptr, indices, data, shape = _as_csr_arrays(matrix)
+        if not (_counts_fit_u16(data) and shape[1] <= 65535):
+            raise ValueError("the packed stream carries integer counts <= 65504 of <= 65535 genes")
+        self.shape = shape
+        self.device = torch.device(device)
+        self.B = int(minibatch_size)
+        self.indptr, self.indices = indptr, indices
+        self.values = data.astype(numpy.uint16)
+        self.value_bytes = 1 if (data.size == 0 or data.max() <= 255) else 2
+        self.u16_ok = True
+        self.f16_exact = bool(data.size == 0 or data.max() <= 2048)
+        self.nblk = -(-shape[1] // self.BLOCK)
+        from scipy.special import gammaln
+        csum = numpy.concatenate([[0.0], numpy.cumsum(gammaln(1.0 + data.astype(numpy.float64)))])
+        self.row_const = (csum[indptr[1:]] - csum[indptr[:-1]]).astype(numpy.float32)
+        self._copy_stream = None
+        self.slabs, self.buf, self.slots = [], None, None
+        self.pack_seconds = 0.0
+
+    @property
+    def copy_stream(self):
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        return self._copy_stream
+
+    @property
+    def number_of_examples(self):
+        return self.shape[0]
+
+    def slab_layout(self, rows):
+        """(off_const, off_blocks, off_entries) of a slab of ``rows`` rows."""
+        off_const = 4 * (rows + 1)
+        off_blocks = off_const + 4 * rows
+        return off_const, off_blocks, off_blocks + rows * self.nblk
+
+    def pack_epoch(self, order=None):
+        """Lay out the rows ``order`` (default: data order) as slabs of ``B`` rows in pinned memory."""
+        import time
+        t0 = time.perf_counter()
+        n, B, eb = self.shape[0], self.B, 1 + self.value_bytes
+        order = numpy.arange(n) if order is None else numpy.asarray(order, dtype=numpy.int64)
+        starts, lens = self.indptr[order], numpy.diff(self.indptr)[order]
+        total = int(lens.sum())
+        first = numpy.concatenate([[0], numpy.cumsum(lens)])            # entry offsets in epoch order
+        src = numpy.repeat(starts - first[:-1], lens) + numpy.arange(total)
+        cols = self.indices[src]
+        blk = cols // self.BLOCK
+        ent = numpy.empty((total, eb), dtype=numpy.uint8)
+        ent[:, 0] = cols - blk * self.BLOCK
+        vals = self.values[src]
+        ent[:, 1] = vals & 255
+        if self.value_bytes == 2:
+            ent[:, 2] = vals >> 8
+        row_of = numpy.repeat(numpy.arange(order.size), lens)
+        blocks = numpy.bincount(row_of * self.nblk + blk, minlength=order.size * self.nblk).astype(
+            numpy.uint8).reshape(order.size, self.nblk)
+        # slab-major byte buffer
+        bounds = [(i, min(i + B, order.size)) for i in range(0, order.size, B)]
+        sizes = []
+        for i0, i1 in bounds:
+            rows = i1 - i0
+            sizes.append((self.slab_layout(rows)[2] + int(first[i1] - first[i0]) * eb + 15) & ~15)
+        offsets = numpy.concatenate([[0], numpy.cumsum(sizes)])
+        if self.buf is None or self.buf.numel() < int(offsets[-1]):
+            self.buf = torch.empty(int(offsets[-1]), dtype=torch.uint8)
+            if self.device.type == "cuda":
+                self.buf = self.buf.pin_memory()
+        host = self.buf.numpy()
+        self.slabs = []
+        for k, (i0, i1) in enumerate(bounds):
+            rows, o = i1 - i0, int(offsets[k])
+            oc, ob, oe = self.slab_layout(rows)
+            e0, e1 = int(first[i0]), int(first[i1])
+            host[o:o + 4 * (rows + 1)].view(numpy.int32)[:] = (first[i0:i1 + 1] - e0).astype(numpy.int32)
+            host[o + oc:o + oc + 4 * rows].view(numpy.float32)[:] = self.row_const[order[i0:i1]]
+            host[o + ob:o + oe] = blocks[i0:i1].reshape(-1)
+            host[o + oe:o + oe + (e1 - e0) * eb] = ent[e0:e1].reshape(-1)
+            self.slabs.append({"offset": o, "bytes": oe + (e1 - e0) * eb, "rows": rows})
+        need = (int(1.25 * max(sizes)) + 15) & ~15 if sizes else 16      # (slack: later epochs' orders differ)
+        if self.device.type == "cuda" and (self.slots is None or self.slots[0]["buf"].numel() < need):
+            self.slots = []
+            for _ in range(2):
+                slot = {"packed": True, "buf": torch.empty(need, dtype=torch.uint8, device=self.device),
+                        "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "bytes": 0, "rows": 0,
+                        "value_bytes": self.value_bytes, "u16_ok": True, "f16_exact": self.f16_exact,
+                        "stream": self}
+                slot["free"].record()
+                self.slots.append(slot)
+        self.pack_seconds = time.perf_counter() - t0
+        return len(self.slabs)
+
+    def fetch(self, slot_id, k):
+        """Enqueue the host -> device copy of slab ``k`` into staging slot ``slot_id``."""
+        slab, slot = self.slabs[k], self.slots[slot_id]
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(slot["free"])
+            slot["buf"][:slab["bytes"]].copy_(self.buf[slab["offset"]:slab["offset"] + slab["bytes"]],
+                                              non_blocking=True)
+            slot["ready"].record(self.copy_stream)
+        slot["bytes"], slot["rows"] = slab["bytes"], slab["rows"]
+        return slot
+
+
 class TrainLoop:
     """One (engine, minibatch size) training loop with a CUDA-graph-captured step."""
 
@@ -161,6 +276,9 @@ class TrainLoop:
             eng.set_batch_csr(p, src.indptr, src.indices, src.values, self.rows,
                               u16_ok=src.u16_ok, f16_exact=src.f16_exact, train16=self.R == 1,
                               row_const_all=src.row_const)
+        elif src.get("packed"):      # staging slot of a PackedStream: one slab = this minibatch
+            eng.set_batch_packed(p, src["buf"], src["stream"].slab_layout(self.B), src["value_bytes"],
+                                 f16_exact=src["f16_exact"])
         else:  # staging slot of a StreamedCSR
             eng.set_batch_csr(p, src["indptr"], src["indices"], src["values"], None, rebase=True,
                               u16_ok=src["u16_ok"], f16_exact=src["f16_exact"],

@@ -86,6 +86,17 @@ def csr_densify(indptr, indices, values, rows, G, x, row_const=None, rebase=Fals
                "csr_densify")
 
 
+def csr_densify_packed(slab, off_const, off_blocks, off_entries, value_bytes, B, G, row_const=None,
+                       t16=None, x16=None):
+    """Packed row slab (uint8 device tensor, see include/scvae_b200.h) -> 16-bit minibatch."""
+    lib = _lib.load()
+    _lib.check(lib.scvae_csr_densify_packed(_p(slab), int(off_const), int(off_blocks), int(off_entries),
+                                            int(value_bytes), B, G, _p(row_const), _p(t16),
+                                            _ld(t16) if t16 is not None else 0, _p(x16),
+                                            _ld(x16) if x16 is not None else 0, _stream()),
+               "csr_densify_packed")
+
+
 def csr_row_constants(indptr, values, out):
     """out[r] = sum_g lgamma(1 + x[r, g]) for every CSR row (absolute indptr)."""
     lib = _lib.load()

@@ -359,10 +359,20 @@ class VariationalAutoencoder:
         import torch
         from .hotloop import ResidentCSR
         from . import kernels as K
+        from .hotloop import PackedStream
         n = x_csr.shape[0]
         L = self.latent_size
         dev = engine.device
-        data = x_csr if isinstance(x_csr, ResidentCSR) else ResidentCSR(x_csr, dev)
+        packed = x_csr if isinstance(x_csr, PackedStream) else None
+        if packed is not None:
+            # host-resident matrix: the rows stream through in data order as packed slabs
+            if on_batch is not None or (t_csr is not None and t_csr is not x_csr):
+                raise NotImplementedError("host-resident data feeds the lean evaluation passes only")
+            if packed.B != minibatch_size or not packed.slabs:
+                packed.B = int(minibatch_size)
+                packed.pack_epoch(None)
+        data = packed if packed is not None else (
+            x_csr if isinstance(x_csr, ResidentCSR) else ResidentCSR(x_csr, dev))
         targets = None
         if t_csr is not None and t_csr is not x_csr:
             targets = t_csr if isinstance(t_csr, ResidentCSR) else ResidentCSR(t_csr, dev)
@@ -376,9 +386,16 @@ class VariationalAutoencoder:
             # no per-batch consumer of the head pre-activations: 16-bit minibatch + forward-only
             # fused heads (when the shapes allow; otherwise this is the fp32 path as before)
             lean = on_batch is None and targets is None
-            engine.set_batch_csr(plan, data.indptr, data.indices, data.values, idx,
-                                 u16_ok=data.u16_ok, f16_exact=data.f16_exact, train16=lean,
-                                 row_const_all=data.row_const)
+            if packed is not None:
+                slot = packed.fetch(b % 2, b)
+                torch.cuda.current_stream().wait_event(slot["ready"])
+                engine.set_batch_packed(plan, slot["buf"], packed.slab_layout(rows),
+                                        packed.value_bytes, f16_exact=packed.f16_exact)
+                slot["free"].record(torch.cuda.current_stream())
+            else:
+                engine.set_batch_csr(plan, data.indptr, data.indices, data.values, idx,
+                                     u16_ok=data.u16_ok, f16_exact=data.f16_exact, train16=lean,
+                                     row_const_all=data.row_const)
             if targets is not None:
                 if plan.T is None:
                     plan.T = torch.zeros(rows, engine.Gp, dtype=torch.float32, device=dev)
@@ -480,8 +497,23 @@ class VariationalAutoencoder:
         x_train, t_train = self._inputs(training_set, self.reconstruction_distribution_name)
         n_train = training_set.number_of_examples
         minibatch_size = min(minibatch_size, n_train)
-        data = ResidentCSR(scipy.sparse.csr_matrix(x_train, dtype=numpy.float32), engine.device)
-        self._attach_features(data, training_set)
+        # data_residency="host": the count matrix stays in (pinned) host memory and every step's rows
+        # travel as one packed slab (hotloop.PackedStream) -- for matrices beyond HBM
+        host_resident = kwargs.get("data_residency", "device") == "host"
+        stream = eval_stream = None
+        if host_resident:
+            from .hotloop import PackedStream
+            if t_train is not x_train or getattr(engine, "n_extra", 0) or getattr(engine, "constrained", False):
+                raise NotImplementedError("host-resident training data: counts only (no separate "
+                                          "targets, batch correction or count-sum inputs)")
+            csr_train = scipy.sparse.csr_matrix(x_train, dtype=numpy.float32)
+            per_rank = minibatch_size // world if world > 1 else minibatch_size
+            stream = PackedStream(csr_train, engine.device, per_rank)
+            eval_stream = PackedStream(csr_train, engine.device, minibatch_size)
+            data = eval_stream
+        else:
+            data = ResidentCSR(scipy.sparse.csr_matrix(x_train, dtype=numpy.float32), engine.device)
+            self._attach_features(data, training_set)
         if t_train is not x_train:
             # targets other than the network input (binarised values for the Bernoulli likelihood,
             # raw counts behind preprocessed inputs; VAE:849-861): a second resident matrix
@@ -551,7 +583,31 @@ class VariationalAutoencoder:
                     engine.device)
             n_steps = -(-n_train // minibatch_size)
             step_bounds = torch.zeros(n_steps, 8, dtype=torch.float32, device=engine.device)
-            for s, i in enumerate(range(0, n_train, minibatch_size)):
+            if stream is not None:
+                # this rank's rows of every global minibatch, in step order, as packed slabs
+                order_host = shuffled.cpu().numpy()
+                pieces = []
+                for i in range(0, n_train, minibatch_size):
+                    rows = min(minibatch_size, n_train - i)
+                    lo, hi = D.shard_bounds(i, rows, rank, world) if world > 1 else (i, i + rows)
+                    pieces.append(order_host[lo:hi])
+                order_rank = numpy.concatenate(pieces)
+                stream.pack_epoch(order_rank)       # (uneven last steps only without ranks)
+                compute = torch.cuda.current_stream()
+                pending = stream.fetch(0, 0)
+                for s in range(len(stream.slabs)):
+                    slot = pending
+                    if s + 1 < len(stream.slabs):
+                        pending = stream.fetch((s + 1) % 2, s + 1)
+                    rows = slot["rows"]
+                    if rows not in loops:
+                        loops[rows] = TrainLoop(engine, rows, R, S, seed=noise_seed + 7919 * rank,
+                                                use_graph=use_graph)
+                    compute.wait_event(slot["ready"])
+                    bound = loops[rows].step(slot, learning_rate, warm_up_weight)
+                    slot["free"].record(compute)
+                    step_bounds[s, :bound.numel()].copy_(bound)
+            for s, i in enumerate(range(0, n_train, minibatch_size) if stream is None else []):
                 rows = min(minibatch_size, n_train - i)
                 if world > 1:   # this rank's slice of the global minibatch
                     i, hi = D.shard_bounds(i, rows, rank, world)
@@ -578,8 +634,9 @@ class VariationalAutoencoder:
                 epoch + 1, format_duration(epoch_duration), n_train / max(epoch_duration, 1e-9)))
 
             # evaluation passes with the *training* sample counts (VAE:1103-1106, 1262-1265)
-            results = {"training": self._evaluate_pass(engine, data, data.targets, minibatch_size, R,
-                                                       S, seed=noise_seed + 1000 + epoch)}
+            results = {"training": self._evaluate_pass(engine, data, getattr(data, "targets", None),
+                                                       minibatch_size, R, S,
+                                                       seed=noise_seed + 1000 + epoch)}
             if validation_set:
                 results["validation"] = self._evaluate_pass(
                     engine, valid_data, valid_data.targets,

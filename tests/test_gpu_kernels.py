@@ -848,3 +848,46 @@ def test_continuous_likelihood_fwd_bwd_and_moments(kind, M, G, tile):
         scale = w[ok].abs().max().item() if ok.any() else 1.0
         # (fp32 with fast exponentials; the Lomax variance spans ten orders of magnitude)
         assert (got[ok] - w[ok]).abs().max().item() <= 1e-3 * scale + 1e-6
+
+
+@pytest.mark.parametrize("cap,direct", [(200.0, True), (3000.0, False), (60000.0, False)])
+def test_csr_densify_packed_matches_csr_densify(cap, direct):
+    """The streamed wire format (packed row slabs, scvae_csr_densify_packed) against the CSR form:
+    identical 16-bit minibatch and per-cell constants, one- and two-byte counts, a ragged last slab."""
+    import scipy.sparse
+    from scvae_b200 import kernels as K
+    from scvae_b200.hotloop import PackedStream
+    rng = numpy.random.RandomState(1)
+    N, G, B = 300, 1000, 128
+    dense = numpy.minimum(_counts(rng, N, G, 0.85) * (1 + 50 * (rng.rand(N, G) < 0.01)), cap).astype(numpy.float32)
+    dense[7] = 0
+    csr = scipy.sparse.csr_matrix(dense)
+    dev = _dev()
+    stream = PackedStream(csr, dev, B)
+    assert stream.value_bytes == (1 if cap <= 255 else 2)
+    order = rng.permutation(N)
+    stream.pack_epoch(order)
+    indptr = torch.tensor(csr.indptr.astype(numpy.int64)).to(dev)
+    indices = torch.tensor(csr.indices.astype(numpy.int32)).to(dev)
+    values = torch.tensor(csr.data.astype(numpy.float32)).to(dev)
+    ld16 = (G + 8) & ~7
+    for k, slab in enumerate(stream.slabs):
+        rows = slab["rows"]
+        slot = stream.fetch(k % 2, k)
+        torch.cuda.current_stream().wait_event(slot["ready"])
+        x16 = torch.full((rows, ld16), 3.0, dtype=torch.float16, device=dev)
+        t16 = None if direct else torch.full((rows, (G + 7) & ~7), 7, dtype=torch.int16, device=dev)
+        rc = torch.zeros(rows, device=dev)
+        K.csr_densify_packed(slot["buf"], *stream.slab_layout(rows), stream.value_bytes, rows, G,
+                             row_const=rc, t16=t16, x16=x16)
+        slot["free"].record()
+        idx = torch.tensor(order[k * B:k * B + rows].astype(numpy.int64)).to(dev)
+        x16_ref = torch.full((rows, ld16), 5.0, dtype=torch.float16, device=dev)
+        t16_ref = None if direct else torch.full((rows, (G + 7) & ~7), 9, dtype=torch.int16, device=dev)
+        rc_ref = torch.zeros(rows, device=dev)
+        K.csr_densify(indptr, indices, values, idx, G, None, rc_ref, t16=t16_ref, x16=x16_ref)
+        torch.cuda.synchronize()
+        assert torch.equal(x16, x16_ref)
+        if not direct:
+            assert torch.equal(t16, t16_ref)
+        assert torch.allclose(rc, rc_ref, rtol=2e-6, atol=1e-5)

@@ -303,3 +303,24 @@ def test_train_evaluate_with_continuous_likelihoods(tmp_path, likelihood):
     assert reconstructed.values.shape == (test.number_of_examples, 40)
     if likelihood != "lomax":            # (the Lomax mean does not exist for concentration <= 1: nan)
         assert numpy.isfinite(reconstructed.values).all()
+
+
+def test_training_from_host_resident_data_matches_device_resident(tmp_path):
+    """train(..., data_residency="host"): the matrix stays in host memory and streams as packed
+    slabs (hotloop.PackedStream); same permutation, noise and updates as the resident path."""
+    from scvae_b200.variational_autoencoder import VariationalAutoencoder
+    from scvae_b200 import model_utilities as MU
+    full = _data(n=600, g=256, seed=6)
+    training, validation, _ = full.split()
+    curves = {}
+    for residency in ("device", "host"):
+        model = VariationalAutoencoder(
+            feature_size=256, latent_size=5, hidden_sizes=[32], reconstruction_distribution="negative binomial",
+            log_directory=str(tmp_path / residency), seed=3)
+        assert model.train(training, None, number_of_epochs=3, minibatch_size=128, learning_rate=3e-3,
+                           shuffle_seed=5, data_residency=residency) == 0
+        curves[residency] = MU.load_learning_curves(model, ["training", "validation"])["training"]
+    for key in ("lower_bound", "reconstruction_error", "kl_divergence"):
+        a, b = numpy.asarray(curves["device"][key]), numpy.asarray(curves["host"][key])
+        assert numpy.allclose(a, b, rtol=2e-4), (key, a, b)
+    assert curves["host"]["lower_bound"][-1] > curves["host"]["lower_bound"][0]

@@ -131,7 +131,7 @@ STEP_CASES = [
 ]
 
 
-@pytest.mark.parametrize("source", ["resident", "streamed"])
+@pytest.mark.parametrize("source", ["resident", "streamed", "packed"])
 @pytest.mark.parametrize("case", STEP_CASES, ids=[c[0] for c in STEP_CASES])
 def test_train_loop_step_at_baseline_shape(case, source):
     """`TrainLoop.step` (CUDA-graph replay of densify -> noise -> forward -> backward -> clip +
@@ -162,6 +162,14 @@ def test_train_loop_step_at_baseline_shape(case, source):
         loop.rows.copy_(rows)
         src = data
         rows_host = rows.cpu().numpy()
+    elif source == "packed":
+        from scvae_b200.hotloop import PackedStream
+        stream = PackedStream(csr, dev, B)
+        order = rng.permutation(N)
+        stream.pack_epoch(order)
+        src = stream.fetch(1, 1)                        # the second slab of the epoch
+        torch.cuda.current_stream().wait_event(src["ready"])
+        rows_host = order[B:2 * B]
     else:
         stream = StreamedCSR(csr, dev, B)
         src = stream.fetch(0, B // 2, B // 2 + B)       # a slab that does not start at row 0

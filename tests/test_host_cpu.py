@@ -58,3 +58,45 @@ def test_option_validation_mirrors_the_scope():
     with pytest.raises(TypeError):
         VariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
                                batch_correction=True)          # number of batches missing
+
+
+def test_packed_stream_slabs_decode_to_the_rows_of_the_matrix():
+    """Host logic of the streamed wire format (scvae_csr_densify_packed): every slab of an epoch,
+    decoded with numpy exactly as the kernel reads it, reproduces its rows in epoch order."""
+    import numpy
+    import scipy.sparse
+    from scvae_b200.hotloop import PackedStream
+    rng = numpy.random.RandomState(0)
+    n, G, B = 37, 700, 8
+    dense = ((rng.rand(n, G) < 0.1) * rng.randint(1, 400, size=(n, G))).astype(numpy.float32)
+    dense[3] = 0                      # an empty row
+    dense[5, :] = 7                   # a full row: every block holds 255 entries
+    stream = PackedStream(scipy.sparse.csr_matrix(dense), "cpu", B)
+    assert stream.value_bytes == 2 and stream.nblk == 3
+    order = rng.permutation(n)
+    assert stream.pack_epoch(order) == 5
+    host = stream.buf.numpy()
+    eb = 1 + stream.value_bytes
+    seen = 0
+    for k, slab in enumerate(stream.slabs):
+        rows = slab["rows"]
+        oc, ob, oe = stream.slab_layout(rows)
+        base = host[slab["offset"]:slab["offset"] + slab["bytes"]]
+        rowptr = base[:4 * (rows + 1)].view(numpy.int32)
+        consts = base[oc:oc + 4 * rows].view(numpy.float32)
+        blocks = base[ob:oe].reshape(rows, stream.nblk)
+        ent = base[oe:].reshape(-1, eb)
+        for r in range(rows):
+            out = numpy.zeros(G, numpy.float32)
+            e = ent[rowptr[r]:rowptr[r + 1]]
+            assert blocks[r].sum() == len(e)
+            blk = numpy.repeat(numpy.arange(stream.nblk), blocks[r])
+            out[blk * 255 + e[:, 0]] = e[:, 1].astype(numpy.int32) | (e[:, 2].astype(numpy.int32) << 8)
+            want = dense[order[k * B + r]]
+            assert numpy.array_equal(out, want)
+            assert abs(consts[r] - stream.row_const[order[k * B + r]]) == 0
+            seen += 1
+    assert seen == n
+    # 2 bytes per non-zero when the counts fit one byte
+    small = PackedStream(scipy.sparse.csr_matrix(numpy.minimum(dense, 200.0)), "cpu", B)
+    assert small.value_bytes == 1
