@@ -197,6 +197,10 @@ class VAEEngine:
         # {learning rate, warm-up weight} of the current step on the device: kernels of a captured
         # step read them here, so one CUDA graph serves every epoch of a warm-up schedule
         self.scalars = torch.tensor([0.0, 1.0], dtype=torch.float32, device=self.device)
+        # CTA counter of the optimiser launches of one step (scvae_adam_clip_step advance_counter).
+        # Created here, not lazily: its first use is on the side stream, which does not wait for
+        # a fill enqueued on the main stream
+        self._adam_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._scalars_host = (None, None)
         for layer in self.enc + [self.post] + self.dec + [self.head]:
             if layer.bn:
@@ -1284,8 +1288,6 @@ class VAEEngine:
         # one GPU: the optimiser launches advance the step counter themselves (last CTA done)
         advance = None
         if peer is None and self._all_reduce is None:
-            if getattr(self, "_adam_counter", None) is None:
-                self._adam_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
             total = K.adam_clip_ctas(hi) + (K.adam_clip_ctas(s.total - hi) if tail is not None else 0)
             advance = (self._adam_counter, total)
         if tail is not None:

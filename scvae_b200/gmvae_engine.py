@@ -61,6 +61,7 @@ class GMVAEEngine(VAEEngine):
         self.world_size, self._all_reduce, self._plans = 1, None, {}
         self._side, self.overlap_streams, self._peer = None, False, None   # (VAE-engine-only features)
         self.scalars = torch.tensor([0.0, 1.0], dtype=torch.float32, device=self.device)
+        self._adam_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._scalars_host = (None, None)
         self.mid_fused = False
         self.dropout_active = False
