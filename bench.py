@@ -327,6 +327,41 @@ def _timed_kernels(K, names, run, repeats):
     return {k: sum(s_.elapsed_time(e_) for s_, e_ in v) / repeats for k, v in evs.items() if v}
 
 
+def evaluate_reconstruction(args, dev, csr):
+    """f2 (VAE:1939-2052): one `evaluate` pass with the reconstruction at the C2 shape, on a
+    16 384-cell shard (a 1.3 GB fp32 result in pinned memory): forward with the evaluation-mode
+    graph, moments kernel straight into the staging buffers of hotloop.ReconstructionSink, D2H of
+    p_x_mean behind the next minibatch.  cells/s INCLUDING the device -> host copy."""
+    from scvae_b200.variational_autoencoder import VariationalAutoencoder
+    from scvae_b200.hotloop import ResidentCSR
+    n = min(16384, csr.shape[0])
+    sub = csr[:n]
+    B = min(args.minibatch, n)
+    model = VariationalAutoencoder(feature_size=args.genes, latent_size=args.latent,
+                                   hidden_sizes=list(args.hidden), reconstruction_distribution=args.likelihood,
+                                   log_directory="/tmp/scvae_b200_bench_log", seed=0)
+    engine = model._get_engine()
+    data = ResidentCSR(sub, dev)
+    out = {}
+    for dtype in ("float32", "float16"):
+        best = None
+        for rep in range(2):                 # the first pass allocates plans and pins the result
+            collect, sink, _, _ = model._reconstruction_collector(engine, n, B, 1, 1, True, [], dtype)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            model._evaluate_pass(engine, data, data, B, 1, 1, deterministic=True, on_batch=collect)
+            values = sink.finish()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        out[dtype] = {"cells_per_s": n / best, "seconds": best,
+                      "d2h_bytes": int(sink.bytes_copied), "d2h_gb_per_s": sink.bytes_copied / best / 1e9,
+                      "finite": bool(numpy.isfinite(values[::97]).all())}
+    out["what"] = ("VariationalAutoencoder._evaluate_pass + ReconstructionSink on {} cells x {} genes, "
+                   "minibatch {}, wall clock of the whole pass incl. the D2H of p_x_mean "
+                   "(second pass; the first allocates)").format(n, args.genes, B)
+    return out
+
+
 def extra_configs(dev):
     """C3 shape: VAE, zero-inflated NB, 28 000 genes, latent 100 (a 32 768-cell shard of the 1.3 M
     cells: a step touches one minibatch, so the per-step work is that of the full matrix);
@@ -684,12 +719,17 @@ def run_b200(args):
         dist.barrier()
 
     extra = None
+    evaluate_block = None
     if rank == 0 and world == 1 and not args.no_extra:
         # free the headline configuration's buffers first
         try:
             extra = extra_configs(dev)
         except Exception as exc:
             extra = {"error": repr(exc)}
+        try:
+            evaluate_block = evaluate_reconstruction(args, dev, csr)
+        except Exception as exc:
+            evaluate_block = {"error": repr(exc)}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -711,6 +751,7 @@ def run_b200(args):
         line["gradient_exchange"] = exchange     # (not in `config`: both arms name one workload)
         line["parity"] = parity
         line["extra_configs"] = extra
+        line["evaluate_reconstruction"] = evaluate_block
         print(json.dumps(line), flush=True)
     if world > 1:
         # CUDA graphs that captured NCCL kernels must die before the communicator does; guard

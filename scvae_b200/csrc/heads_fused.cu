@@ -579,33 +579,66 @@ heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constan
     }
 }
 
-// logp[m] = sum_s part[s][m] - row_const[m % t_rows]
-__global__ void fused_finish_kernel(const float *__restrict__ part, int64_t part_stride, int gsplit, int M,
-                                    const float *__restrict__ row_const, int t_rows, float *__restrict__ logp) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= M) return;
-    float acc = 0.f;
-    for (int s = 0; s < gsplit; ++s) acc += part[(int64_t)s * part_stride + m];
-    logp[m] = acc - (row_const ? row_const[m % t_rows] : 0.f);
-}
-
-// dd[m][c] = sum_s part[s][m][c] (c < dd_cols), 0 for the padding columns [dd_cols, lddd)
-__global__ void fused_dd_finish_kernel(const float *__restrict__ part, int64_t part_stride, int gsplit, int M,
-                                       float *__restrict__ dd, int64_t lddd, int dd_cols) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int c = (int)(i & 31) << 2;
-    const int64_t m = i >> 5;
-    if (m >= M || c >= lddd) return;
+// One CTA per cell m: logp[m] = sum_s part[s][m] - row_const[m % t_rows], and (backward)
+// dd[m][c] = sum_s dd_part[s][m][c] for c < dd_cols, 0 for the padding columns [dd_cols, lddd).
+// The gene-range partials s are summed in a FIXED order (8 interleaved lanes of partial sums, then a
+// fixed tree), so the result does not depend on the launch.  256 threads = 32 column quads x 8 lanes
+// of s: with the ~150 gene ranges of a small minibatch a thread adds ~20 partials, not 150.
+__global__ void __launch_bounds__(256)
+fused_finish_kernel(const float *__restrict__ part, int64_t part_stride, int gsplit, int M,
+                    const float *__restrict__ row_const, int t_rows, float *__restrict__ logp,
+                    const float *__restrict__ dd_part, float *__restrict__ dd, int64_t lddd, int dd_cols) {
+    __shared__ float4 red[8][32];
+    __shared__ float red_lp[8];
+    const int m = blockIdx.x;
+    const int cq = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    // log p: thread t adds s = t, t + 256, ...
+    float lp = 0.f;
+    for (int s = threadIdx.x; s < gsplit; s += 256) lp += part[(int64_t)s * part_stride + m];
+    lp = warp_sum(lp);
+    if (cq == 0) red_lp[sl] = lp;
+    const int c = cq << 2;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < gsplit; ++s) {
-        const float4 v = *reinterpret_cast<const float4 *>(part + ((int64_t)s * part_stride + m) * FK + c);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    if (dd_part) {
+        const float *src = dd_part + (int64_t)m * FK + c;
+        const int64_t step = part_stride * FK;
+        int s = sl;
+        for (; s + 24 < gsplit; s += 32) {          // four loads in flight
+            const float4 v0 = *reinterpret_cast<const float4 *>(src + (int64_t)s * step);
+            const float4 v1 = *reinterpret_cast<const float4 *>(src + (int64_t)(s + 8) * step);
+            const float4 v2 = *reinterpret_cast<const float4 *>(src + (int64_t)(s + 16) * step);
+            const float4 v3 = *reinterpret_cast<const float4 *>(src + (int64_t)(s + 24) * step);
+            acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+            acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+            acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+            acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+        }
+        for (; s < gsplit; s += 8) {
+            const float4 v = *reinterpret_cast<const float4 *>(src + (int64_t)s * step);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        red[sl][cq] = acc;
     }
-    if (c + 0 >= dd_cols) acc.x = 0.f;
-    if (c + 1 >= dd_cols) acc.y = 0.f;
-    if (c + 2 >= dd_cols) acc.z = 0.f;
-    if (c + 3 >= dd_cols) acc.w = 0.f;
-    *reinterpret_cast<float4 *>(dd + m * lddd + c) = acc;     // lddd % 4 == 0
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += red_lp[j];
+        logp[m] = t - (row_const ? row_const[m % t_rows] : 0.f);
+    }
+    if (dd_part && sl == 0 && c < lddd) {
+        float4 t = red[0][cq];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) {
+            const float4 v = red[j][cq];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        if (c + 0 >= dd_cols) t.x = 0.f;
+        if (c + 1 >= dd_cols) t.y = 0.f;
+        if (c + 2 >= dd_cols) t.z = 0.f;
+        if (c + 3 >= dd_cols) t.w = 0.f;
+        *reinterpret_cast<float4 *>(dd + (int64_t)m * lddd + c) = t;     // lddd % 4 == 0
+    }
 }
 
 static inline int make_map_u16(CUtensorMap *map, const void *base, int64_t rows, int64_t cols, int64_t ld,
@@ -683,15 +716,10 @@ static int launch_fused_t(const void *d16, const void *w16, const void *t16, int
     }
     heads_fused_kernel<KIND, T_HALF, BWD><<<f.row_tiles * f.gsplit, fused_threads(P), smem, s>>>(tmD, tmW, tmT, tmDA, tmDD, p);
     SCVAE_CHECK_LAUNCH("heads_fused");
-    fused_finish_kernel<<<(M + 255) / 256, 256, 0, s>>>(logp_part, p.part_stride, f.gsplit, M, row_const, t_rows,
-                                                        logp);
+    const float *dd_part = BWD ? logp_part + (int64_t)f.gsplit * f.row_tiles * FM : nullptr;
+    fused_finish_kernel<<<M, 256, 0, s>>>(logp_part, p.part_stride, f.gsplit, M, row_const, t_rows, logp, dd_part,
+                                          dd, lddd, dd_cols);
     SCVAE_CHECK_LAUNCH("heads_fused_finish");
-    if (BWD) {
-        const int64_t items = (int64_t)M * 32;
-        fused_dd_finish_kernel<<<(unsigned)((items + 255) / 256), 256, 0, s>>>(
-            logp_part + (int64_t)f.gsplit * f.row_tiles * FM, p.part_stride, f.gsplit, M, dd, lddd, dd_cols);
-        SCVAE_CHECK_LAUNCH("heads_fused_dd_finish");
-    }
     return 0;
 }
 

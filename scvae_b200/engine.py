@@ -656,6 +656,9 @@ class VAEEngine:
     def _mid_rows(self, B, ctas):
         """Cells per CTA (a multiple of 4, <= 64) so that at most ``ctas`` CTAs cover B cells."""
         rows = max(4, -(-B // max(ctas, 1)))
+        # a CTA covers 32 cells per pass whatever it is given: never spread a small minibatch
+        # over more CTAs (more weight staging, wider grid barriers) than that needs
+        rows = max(rows, min(32, B))
         return min(64, (rows + 3) & ~3)
 
     def _mid_desc(self, p, backward):
@@ -1336,22 +1339,45 @@ class VAEEngine:
         self._all_reduce = all_reduce if world_size > 1 else None
 
     # ------------------------------------------------------------------ evaluate extras ----
-    def moments(self, p, R, S, deterministic=False):
-        """p_x_mean, p_x_stddev, stddev_of_p_x_given_z_mean (VAE:2665-2713) for the batch."""
-        RS = 1 if deterministic else R * S
-        outs = [torch.empty(p.B, self.Gn, dtype=torch.float32, device=self.device)
-                for _ in range(3)]
+    def _moments_launch(self, p, RS, mean, stddev, stddev_of_mean):
+        """One launch of the moments kernel of this likelihood; any output may be None (skipped),
+        the given ones share a row pitch."""
+        outs = (mean, stddev, stddev_of_mean)
         if self.k_max:
             K.piecewise_moments(self.kind, self.k_max, p.A, self.Gn, p.B, self.G, RS, *outs)
-            return [o[:, :self.G] for o in outs]
-        if self.constrained:
+        elif self.constrained:
             K.constrained_poisson_moments(p.A, p.lse, p.count_sum_parameter, p.B, self.G, RS, *outs)
-            return [o[:, :self.G] for o in outs]
-        if self.continuous:
+        elif self.continuous:
             K.continuous_moments(self.kind, p.A, self.Gn, p.B, self.G, RS, 1, None, *outs)
-            return [o[:, :self.G] for o in outs]
-        K.likelihood_moments(self.kind, p.A, self.Gn, p.B, self.G, RS, 1, None, *outs)
-        return [o[:, :self.G] for o in outs]
+        else:
+            K.likelihood_moments(self.kind, p.A, self.Gn, p.B, self.G, RS, 1, None, *outs)
+
+    def _moment_buffers(self, p):
+        """Three (B, Gn) result buffers kept with the plan (evaluation passes reuse them)."""
+        bufs = getattr(p, "moment_bufs", None)
+        if bufs is None:
+            bufs = p.moment_bufs = [torch.empty(p.B, self.Gn, dtype=torch.float32, device=self.device)
+                                    for _ in range(3)]
+        return bufs
+
+    def moments(self, p, R, S, deterministic=False, mean_out=None, want_stddev=True):
+        """p_x_mean, p_x_stddev, stddev_of_p_x_given_z_mean (VAE:2665-2713) for the batch.
+        ``mean_out`` (B, >= G; any row pitch): p_x_mean goes there (the staging buffer of a
+        ``hotloop.ReconstructionSink``) instead of the plan's buffer; ``want_stddev=False`` skips
+        the two deviation outputs (returned as None)."""
+        RS = 1 if deterministic else R * S
+        bufs = self._moment_buffers(p)
+        if mean_out is None:
+            self._moments_launch(p, RS, bufs[0], bufs[1] if want_stddev else None,
+                                 bufs[2] if want_stddev else None)
+            mean = bufs[0]
+        else:
+            self._moments_launch(p, RS, mean_out, None, None)
+            if want_stddev:
+                self._moments_launch(p, RS, None, bufs[1], bufs[2])
+            mean = mean_out
+        return [mean[:, :self.G], bufs[1][:, :self.G] if want_stddev else None,
+                bufs[2][:, :self.G] if want_stddev else None]
 
     def kl_neurons(self, p):
         K.col_mean(p.kl_elem, p.B, self.L, p.kl_neurons)

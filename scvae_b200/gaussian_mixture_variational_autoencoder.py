@@ -154,7 +154,8 @@ class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
             seed=self._seed, tensor_cores=self._tensor_cores,
             number_of_batches=self.number_of_batches if self.batch_correction else 0,
             count_sum_feature=bool(self.use_count_sum_as_feature),
-            number_of_reconstruction_classes=self.k_max)
+            number_of_reconstruction_classes=self.k_max,
+            dropout_keep_probabilities=self.dropout_keep_probabilities)
 
     def _evaluate_pass(self, engine, x_csr, t_csr, minibatch_size, R, S, deterministic=False,
                        seed=0, on_batch=None):

@@ -30,7 +30,8 @@ class GMVAEEngine(VAEEngine):
                  prior_probabilities_method="uniform", prior_probabilities=None,
                  proportion_of_free_nats_for_y_kl_divergence=0.0, device="cuda", seed=0,
                  tensor_cores=True, head_buffer_bytes=4 << 30, number_of_batches=0,
-                 count_sum_feature=False, number_of_reconstruction_classes=0):
+                 count_sum_feature=False, number_of_reconstruction_classes=0,
+                 dropout_keep_probabilities=None):
         if reconstruction_distribution not in K.LIKELIHOOD_KINDS:
             raise ValueError("reconstruction distribution `{}` is not supported by the "
                              "B200 hot path".format(reconstruction_distribution))
@@ -64,7 +65,19 @@ class GMVAEEngine(VAEEngine):
         self._adam_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._scalars_host = (None, None)
         self.mid_fused = False
-        self.dropout_active = False
+        # dropout keep probabilities [hidden, x, z, y] (GMVAE:276-296; a scalar means hidden only;
+        # False / None / 0 / 1 switch a kind off, MU:45-46).  Every build of a shared layer -- one
+        # per cluster -- is a dropout op of its own (reuse=True shares variables, not masks); the
+        # fourth value drops the one-hot input of the p(z|y) heads (GMVAE:3036-3040).
+        keep = dropout_keep_probabilities
+        keep = (list(keep) if isinstance(keep, (list, tuple)) else [keep]) + [False] * 4
+        self.keep_h, self.keep_x, self.keep_z, self.keep_y = [
+            float(k) if (k and k != 1) else None for k in keep[:4]]
+        self.dropout_active = any(k is not None for k in (self.keep_h, self.keep_x, self.keep_z,
+                                                          self.keep_y))
+        self.dropout_seed = int(seed) + 104729
+        if self.dropout_active:
+            self.fused_heads = False      # every head multiplies its own dropped operand copy
         # decoder-input extras concatenated to every z_k (GMVAE:3097-3132), as in the VAE engine
         self.number_of_batches = int(number_of_batches or 0)
         self.count_sum_feature = bool(count_sum_feature)
@@ -356,6 +369,7 @@ class GMVAEEngine(VAEEngine):
         p.t16_is_x16 = False
         p.fused_ready = False
         p.fused_done = False
+        p.drop, p.drop_on, p.drop_injected, p.drop_masks = {}, False, False, None
         self._plans[key] = p
         return p
 
@@ -399,6 +413,110 @@ class GMVAEEngine(VAEEngine):
                          relu=True, groups=groups, accumulate_dbeta=accumulate)
         else:
             K.act_bwd(dH, H, layer.n_out, dY, relu=True)
+
+    # ---- dropout (MU:45-50; GMVAE:276-296) -------------------------------------------------------
+    # A site covers `total` tall rows ordered (cluster, sample, cell): the K builds of a shared
+    # layer are K row groups with independent masks (recorded as `site`, `site#1`, ... in the
+    # reference-graph fixtures).  The decoder sites are visited chunk by chunk (rows [r0, r0+rows)).
+    def _gdrop(self, p, site, src, r0, rows, total, n, skip_col, keep, groups):
+        st = p.drop.get(site)
+        if st is None:
+            import statistics
+            st = p.drop[site] = type("DropSite", (), {})()
+            st.index = len(p.drop)
+            st.n, st.skip, st.keep, st.total = n, skip_col, keep, total
+            st.threshold = statistics.NormalDist().inv_cdf(keep)
+            rank = torch.distributed.get_rank() if (
+                torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
+            st.seed = self.dropout_seed + 7919 * st.index + 15485863 * rank
+            st.noise = torch.zeros(total, n, dtype=torch.float32, device=self.device)
+            st.copy = torch.zeros(rows, src.shape[1], dtype=torch.float32, device=self.device)
+        if r0 == 0:          # once per step: the whole site's masks
+            if p.drop_injected:
+                per = total // groups
+                for k in range(groups):
+                    mask = p.drop_masks[site if k == 0 else "{}#{}".format(site, k)]
+                    st.noise[k * per:(k + 1) * per].copy_(
+                        (0.5 - mask.to(self.device, torch.float32)) * 2e9)
+            else:
+                K.fill_normal(st.noise, st.seed, 0, self.store.step)
+        K.dropout_fwd(src, rows, n, skip_col, st.noise[r0:r0 + rows], st.threshold, keep,
+                      st.copy[:rows], src.shape[1])
+        st.r0, st.rows = r0, rows
+        return st
+
+    def _gdrop_bwd(self, st, dx, dsrc=None, accumulate=False):
+        """Gradient through the site's last forward call (rows [st.r0, st.r0 + st.rows))."""
+        K.dropout_bwd(dx, st.rows, st.n, st.skip, st.noise[st.r0:st.r0 + st.rows], st.threshold,
+                      st.keep, dsrc=dsrc, accumulate=accumulate)
+
+    def inject_dropout_masks(self, p, masks):
+        """Parity tests: 0/1 keep masks by site name (`site`, `site#k` per cluster build)."""
+        p.drop_injected = masks is not None
+        p.drop_masks = masks
+
+    def _drop_tmp(self, p, rows, cols):
+        key = "_drop_tmp_{}".format(rows)
+        buf = getattr(p, key, None)
+        if buf is None or buf.shape[1] < cols:
+            buf = torch.zeros(rows, round4(cols), dtype=torch.float32, device=self.device)
+            setattr(p, key, buf)
+        return buf
+
+    def _head_blocks(self):
+        """(first row, rows, site) of every likelihood head in the stacked head weight."""
+        blocks = [(h * self.Gn, self.Gn, "X/DISTRIBUTION/" + head.upper())
+                  for h, head in enumerate(self.heads)]
+        if self.k_max:
+            blocks.append((self.P * self.Gn, (self.k_max + 1) * self.Gn, self.PK_SCOPE))
+        return blocks
+
+    def _qz_first_layer_dropped(self, p):
+        """First q(z|x,y) layer under input dropout (keep_x): every cluster build drops its own
+        copy of [x | e_k], so the shared x W_x product does not apply -- the K dropped copies are K
+        row groups of one tall operand against [W_x | W_y | b] (GMVAE:2942-2956)."""
+        l, Kc, B, G = self.qz_enc[0], self.K, p.B, self.G
+        Wc = round4(G + Kc + 1)
+        if getattr(p, "XE", None) is None:
+            p.XE = torch.zeros(Kc * B, Wc, dtype=torch.float32, device=self.device)
+            view = p.XE.view(Kc, B, Wc)
+            for k in range(Kc):
+                view[k, :, G + k] = 1.0          # e_k
+            view[:, :, G + Kc] = 1.0             # bias column
+            p.Wcat = torch.zeros(l.n_out, Wc, dtype=torch.float32, device=self.device)
+            p.dWcat = torch.zeros(l.n_out, Wc, dtype=torch.float32, device=self.device)
+        p.XE.view(Kc, B, Wc)[:, :, :G].copy_(p.X[:, :G])
+        p.Wcat[:, :G].copy_(l.w[:, :G])
+        p.Wcat[:, G:G + Kc].copy_(self.qz_wy[:, :l.n_out].t())
+        p.Wcat[:, G + Kc].copy_(l.w[:, G])
+        st = self._gdrop(p, l.name, p.XE, 0, Kc * B, Kc * B, G + Kc, G + Kc, self.keep_x, Kc)
+        self._gemm(p, K.GEMM_NT, Kc * B, l.n_out, G + Kc + 1, st.copy, p.Wcat, p.qzY[0])
+
+    def _qz_first_layer_dropped_bwd(self, p):
+        l, Kc, B, G = self.qz_enc[0], self.K, p.B, self.G
+        st = p.drop[l.name]
+        self._gemm(p, K.GEMM_TN, l.n_out, p.Wcat.shape[1], Kc * B, p.d_qzY[0], st.copy, p.dWcat)
+        l.dw.zero_()
+        l.dw[:, :G].copy_(p.dWcat[:, :G])
+        l.dw[:, G].copy_(p.dWcat[:, G + Kc])
+        self.d_qz_wy.zero_()
+        self.d_qz_wy[:, :l.n_out].copy_(p.dWcat[:, G:G + Kc].t())
+
+    def _pz_scales(self, p):
+        """p(z|y) under dropout of its one-hot input (keep_y): mean / scale rows of cluster k are
+        b + (mask_kk / keep) W[k], one mask per head and cluster (GMVAE:3009-3048)."""
+        Kc, L = self.K, self.L
+        if getattr(p, "eye", None) is None:
+            p.eye = torch.zeros(Kc, round4(Kc), dtype=torch.float32, device=self.device)
+            p.eye[:, :Kc] = torch.eye(Kc, device=self.device)
+            p.pz_scale = torch.ones(Kc, 2 * L, dtype=torch.float32, device=self.device)
+            p.pz_wd = torch.zeros_like(self.pz_w)
+        for part, name in enumerate(("MEAN", "SOFTPLUS_SCALE")):
+            st = self._gdrop(p, "Z/P/SOFTPLUS_GAUSSIAN/" + name, p.eye, 0, Kc, Kc, Kc, Kc,
+                             self.keep_y, Kc)
+            p.pz_scale[:, part * L:(part + 1) * L] = torch.diagonal(st.copy[:, :Kc]).reshape(Kc, 1)
+        torch.mul(self.pz_w, p.pz_scale, out=p.pz_wd)
+        return p.pz_wd
 
     # ---- gene-axis products of the two encoders --------------------------------------------------
     # With the 16-bit minibatch at hand (integer counts) they run as fp16 products with the weight
@@ -451,9 +569,14 @@ class GMVAEEngine(VAEEngine):
         if with_backward:
             self._plan_backward(p)
         # --- q(y|x) ---------------------------------------------------------------------------
+        drop = p.drop_on = bool(self.dropout_active and is_training)
         h = p.X
         for i, l in enumerate(self.qy_enc):
-            if i == 0:
+            keep = (self.keep_x if i == 0 else self.keep_h) if drop else None
+            if keep:
+                st = self._gdrop(p, l.name, h, 0, B, B, l.n_in, l.n_in, keep, 1)
+                self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, st.copy, l.w, p.qyY[i])
+            elif i == 0:
                 self._x_product(p, l, p.qyY[i])
             else:
                 self._gemm(p, K.GEMM_NT, B, l.n_out, l.n_in + 1, h, l.w, p.qyY[i])
@@ -461,25 +584,42 @@ class GMVAEEngine(VAEEngine):
                          update_moving, 1)
             h = p.qyH[i]
         l = self.qy_logits
+        if drop and self.keep_h:
+            h = self._gdrop(p, l.name, h, 0, B, B, l.n_in, l.n_in, self.keep_h, 1).copy
         self._gemm(p, K.GEMM_NT, B, Kc, l.n_in + 1, h, l.w, p.logits)
         K.softmax_fwd(p.logits, B, Kc, p.y, p.logy)
         if self.prior_method == "learn":
             self._refresh_log_py()
         # --- q(z|x, y=k) for all k ----------------------------------------------------------
         l = self.qz_enc[0]
-        self._x_product(p, l, p.XW)
-        K.group_offset_fwd(p.XW, self.qz_wy, Kc, B, l.n_out, p.qzY[0])
+        if drop and self.keep_x:
+            self._qz_first_layer_dropped(p)
+        else:
+            self._x_product(p, l, p.XW)
+            K.group_offset_fwd(p.XW, self.qz_wy, Kc, B, l.n_out, p.qzY[0])
         self._bn_fwd(p, l, p.qzY[0], p.qzH[0], p.qz_mean[0], p.qz_rstd[0], is_training,
                      update_moving, Kc)
         for i in range(1, len(self.qz_enc)):
             l = self.qz_enc[i]
-            self._gemm(p, K.GEMM_NT, KB, l.n_out, l.n_in + 1, p.qzH[i - 1], l.w, p.qzY[i])
+            h = p.qzH[i - 1]
+            if drop and self.keep_h:
+                h = self._gdrop(p, l.name, h, 0, KB, KB, l.n_in, l.n_in, self.keep_h, Kc).copy
+            self._gemm(p, K.GEMM_NT, KB, l.n_out, l.n_in + 1, h, l.w, p.qzY[i])
             self._bn_fwd(p, l, p.qzY[i], p.qzH[i], p.qz_mean[i], p.qz_rstd[i], is_training,
                          update_moving, Kc)
         l = self.qz_head
-        self._gemm(p, K.GEMM_NT, KB, l.n_out, l.n_in + 1, p.qzH[-1], l.w, p.QH)
+        if drop and self.keep_h:
+            # one mask per posterior parameter (and cluster build) over the same activation
+            for part, name in enumerate(("MEAN", "SOFTPLUS_SCALE")):
+                st = self._gdrop(p, l.name + "/" + name, p.qzH[-1], 0, KB, KB, l.n_in, l.n_in,
+                                 self.keep_h, Kc)
+                K.gemm(K.GEMM_NT, KB, L, l.n_in + 1, st.copy, l.w[part * L:(part + 1) * L],
+                       p.QH[:, part * L:(part + 1) * L], tensor_cores=False)
+        else:
+            self._gemm(p, K.GEMM_NT, KB, l.n_out, l.n_in + 1, p.qzH[-1], l.w, p.QH)
         # --- p(z|y=k) = FC(e_k) ---------------------------------------------------------------
-        K.group_offset_fwd(self.pz_b, self.pz_w, Kc, 1, 2 * L, p.PZ)
+        pz_w = self._pz_scales(p) if (drop and self.keep_y) else self.pz_w
+        K.group_offset_fwd(self.pz_b, pz_w, Kc, 1, 2 * L, p.PZ)
         K.gmvae_latent_fwd(p.QH, p.PZ, Kc, B, L, RS, p.eps, p.Z, p.klz, p.kl_elem)
         self._decoder_features(p, p.M)
         K.gmvae_row_coefficients(p.y, Kc, RS, B, weight, p.go, p.coef)
@@ -504,7 +644,12 @@ class GMVAEEngine(VAEEngine):
                 p.lse = p.lse_all[r0:r0 + rows]
             d = p.Z[r0:r0 + rows]
             for j, l in enumerate(self.dec):
-                self._gemm(p, K.GEMM_NT, rows, l.n_out, l.k_in, d, l.w, p.decY[j][:rows])
+                keep = (self.keep_z if j == 0 else self.keep_h) if drop else None
+                src = d
+                if keep:
+                    src = self._gdrop(p, l.name, d[:rows], r0, rows, p.M, l.n_in + l.n_extra,
+                                      l.n_in, keep, Kc).copy
+                self._gemm(p, K.GEMM_NT, rows, l.n_out, l.k_in, src, l.w, p.decY[j][:rows])
                 self._bn_fwd(p, l, p.decY[j][:rows], p.decH[j][:rows], p.dec_mean[j], p.dec_rstd[j],
                              is_training, update_moving, kc)
                 d = p.decH[j]
@@ -528,7 +673,15 @@ class GMVAEEngine(VAEEngine):
                 if getattr(p, "on_chunk", None) is not None:
                     p.on_chunk(c0, kc, rows)
                 continue
-            self._gemm(p, K.GEMM_NT, rows, l.n_out, l.n_in + 1, d, l.w, p.A[:rows])
+            if drop and self.keep_h:
+                # every head is a dense layer of its own with its own mask (GMVAE:3140-3218)
+                for b0, nr, site in self._head_blocks():
+                    st = self._gdrop(p, site, d[:rows], r0, rows, p.M, l.n_in, l.n_in,
+                                     self.keep_h, Kc)
+                    K.gemm(K.GEMM_NT, rows, nr, l.n_in + 1, st.copy, l.w[b0:b0 + nr],
+                           p.A[:rows, b0:b0 + nr], tensor_cores=False)
+            else:
+                self._gemm(p, K.GEMM_NT, rows, l.n_out, l.n_in + 1, d, l.w, p.A[:rows])
             if with_backward:
                 self._likelihood(p, tgt, p.A[:rows], rows, rc, logp=p.logp[r0:r0 + rows],
                                  da=p.dA[:rows], go=p.go[r0:r0 + rows])
@@ -568,7 +721,16 @@ class GMVAEEngine(VAEEngine):
         l = self.head
         d_in = p.decH[-1] if self.dec else p.Z[r0:r0 + rows]
         dd_in = p.d_decH[-1] if self.dec else p.dZ[r0:r0 + rows]
-        if not heads_done:
+        if not heads_done and p.drop_on and self.keep_h:
+            tmp = self._drop_tmp(p, p.decH[-1].shape[0] if self.dec else p.M, l.in_p)
+            for b, (b0, nr, site) in enumerate(self._head_blocks()):
+                st = p.drop[site]
+                K.gemm(K.GEMM_TN, nr, l.in_p, rows, p.dA[:rows, b0:b0 + nr], st.copy[:rows],
+                       l.dw[b0:b0 + nr], accumulate=accumulate, tensor_cores=False)
+                K.gemm(K.GEMM_NN, rows, l.n_in, nr, p.dA[:rows, b0:b0 + nr], l.w[b0:b0 + nr],
+                       tmp[:rows], tensor_cores=False)
+                self._gdrop_bwd(st, dd_in[:rows], dsrc=tmp[:rows], accumulate=b > 0)
+        elif not heads_done:
             self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, rows, p.dA[:rows], d_in[:rows], l.dw,
                        accumulate=accumulate)
             self._gemm(p, K.GEMM_NN, rows, l.n_in, l.n_out, p.dA[:rows], l.w, dd_in[:rows])
@@ -578,9 +740,14 @@ class GMVAEEngine(VAEEngine):
                          p.dec_mean[j], p.dec_rstd[j], p.d_decY[j][:rows], kc, accumulate)
             d_in = p.decH[j - 1][:rows] if j > 0 else p.Z[r0:r0 + rows]
             dd_in = p.d_decH[j - 1][:rows] if j > 0 else p.dZ[r0:r0 + rows]
+            st = p.drop.get(l.name) if p.drop_on else None
+            if st is not None:
+                d_in = st.copy[:rows]
             self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, rows, p.d_decY[j][:rows], d_in, l.dw,
                        accumulate=accumulate)
             self._gemm(p, K.GEMM_NN, rows, l.n_in, l.n_out, p.d_decY[j][:rows], l.w, dd_in)
+            if st is not None:
+                self._gdrop_bwd(st, dd_in)      # gradient w.r.t. the un-dropped input, in place
 
     # ------------------------------------------------------------------ backward -----------
     def backward(self, p, R, S, warm_up_weight=1.0):
@@ -588,37 +755,67 @@ class GMVAEEngine(VAEEngine):
         B, Kc, L, RS, KB = p.B, self.K, self.L, p.RS, p.KB
         K.gmvae_latent_bwd(p.QH, p.PZ, Kc, B, L, RS, p.eps, p.dZ, p.coef, p.dQH, p.dPZ)
         # p(z|y) parameters: W[k] gets dPZ[k], the shared bias their sum
-        self.d_pz_w.copy_(p.dPZ)
+        drop = p.drop_on
+        if drop and self.keep_y:
+            torch.mul(p.dPZ, p.pz_scale, out=self.d_pz_w)     # W[k] enters as (mask_kk / keep) W[k]
+        else:
+            self.d_pz_w.copy_(p.dPZ)
         K.group_offset_bwd(p.dPZ, 1, Kc, 2 * L, dt=self.d_pz_b)
         # q(z|x,y) encoder on K*B rows
         l = self.qz_head
-        self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, KB, p.dQH, p.qzH[-1], l.dw)
-        self._gemm(p, K.GEMM_NN, KB, l.n_in, l.n_out, p.dQH, l.w, p.d_qzH[-1])
+        if drop and self.keep_h:
+            tmp = self._drop_tmp(p, KB, l.in_p)
+            for part, name in enumerate(("MEAN", "SOFTPLUS_SCALE")):
+                st = p.drop[l.name + "/" + name]
+                cols = slice(part * L, (part + 1) * L)
+                K.gemm(K.GEMM_TN, L, l.in_p, KB, p.dQH[:, cols], st.copy, l.dw[cols],
+                       tensor_cores=False)
+                K.gemm(K.GEMM_NN, KB, l.n_in, L, p.dQH[:, cols], l.w[cols], tmp, tensor_cores=False)
+                self._gdrop_bwd(st, p.d_qzH[-1], dsrc=tmp, accumulate=part > 0)
+        else:
+            self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, KB, p.dQH, p.qzH[-1], l.dw)
+            self._gemm(p, K.GEMM_NN, KB, l.n_in, l.n_out, p.dQH, l.w, p.d_qzH[-1])
         for i in range(len(self.qz_enc) - 1, -1, -1):
             l = self.qz_enc[i]
             self._bn_bwd(p, l, p.d_qzH[i], p.qzY[i], p.qzH[i], p.qz_mean[i], p.qz_rstd[i],
                          p.d_qzY[i], Kc, False)
             if i > 0:
-                self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, KB, p.d_qzY[i], p.qzH[i - 1], l.dw)
+                st = p.drop.get(l.name) if drop else None
+                h_in = st.copy if st is not None else p.qzH[i - 1]
+                self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, KB, p.d_qzY[i], h_in, l.dw)
                 self._gemm(p, K.GEMM_NN, KB, l.n_in, l.n_out, p.d_qzY[i], l.w, p.d_qzH[i - 1])
+                if st is not None:
+                    self._gdrop_bwd(st, p.d_qzH[i - 1])
+            elif drop and self.keep_x:
+                self._qz_first_layer_dropped_bwd(p)
             else:
                 K.group_offset_bwd(p.d_qzY[0], Kc, B, l.n_out, dx=p.dXW, dt=self.d_qz_wy)
                 self._x_wgrad(p, l, p.dXW)
         # q(y|x) encoder
         p.dlogits[:, :Kc].copy_(p.dlogits_c)
         l = self.qy_logits
-        self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.dlogits, p.qyH[-1], l.dw)
+        st = p.drop.get(l.name) if drop else None
+        self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.dlogits,
+                   st.copy if st is not None else p.qyH[-1], l.dw)
         self._gemm(p, K.GEMM_NN, B, l.n_in, l.n_out, p.dlogits, l.w, p.d_qyH[-1])
+        if st is not None:
+            self._gdrop_bwd(st, p.d_qyH[-1])
         for i in range(len(self.qy_enc) - 1, -1, -1):
             l = self.qy_enc[i]
             self._bn_bwd(p, l, p.d_qyH[i], p.qyY[i], p.qyH[i], p.qy_mean[i], p.qy_rstd[i],
                          p.d_qyY[i], 1, False)
+            st = p.drop.get(l.name) if drop else None
             if i > 0:
-                self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.d_qyY[i], p.qyH[i - 1], l.dw)
+                self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.d_qyY[i],
+                           st.copy if st is not None else p.qyH[i - 1], l.dw)
+            elif st is not None:
+                self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.d_qyY[i], st.copy, l.dw)
             else:
                 self._x_wgrad(p, l, p.d_qyY[i])
             if i > 0:
                 self._gemm(p, K.GEMM_NN, B, l.n_in, l.n_out, p.d_qyY[i], l.w, p.d_qyH[i - 1])
+                if st is not None:
+                    self._gdrop_bwd(st, p.d_qyH[i - 1])
 
     def train_step(self, p, R, S, learning_rate, warm_up_weight=1.0):
         """One ``session.run([optimiser, lower_bound])`` (GMVAE:1109-1112)."""
@@ -632,28 +829,42 @@ class GMVAEEngine(VAEEngine):
         K.gmvae_z_mean(p.QH, p.y, self.K, p.B, self.L, p.z_mean)
         return p.z_mean
 
-    def moments(self, p, R, S, deterministic=False):
-        """p_x_mean, p_x_stddev, stddev_of_p_x_given_z_mean marginalised over y
-        (GMVAE:3312-3386, including the y-weighted per-cluster mean of quirk Q7).  Needs the
-        head pre-activations of all K clusters, i.e. a plan whose decoder runs in one chunk."""
-        if p.chunk != self.K:
-            raise ValueError("moments need a single-chunk plan: lower the evaluation minibatch "
-                             "size or raise head_buffer_bytes")
-        outs = [torch.empty(p.B, self.Gn, dtype=torch.float32, device=self.device)
-                for _ in range(3)]
+    def _moments_launch(self, p, RS, mean, stddev, stddev_of_mean):
+        outs = (mean, stddev, stddev_of_mean)
         if self.k_max:
             K.piecewise_moments(self.kind, self.k_max, p.A, self.Gn, p.B, self.G, p.RS, *outs,
                                 K_=self.K, y=p.y)
-            return [o[:, :self.G] for o in outs]
-        if self.constrained:
+        elif self.constrained:
             K.constrained_poisson_mixture_moments(p.A, p.lse_all, p.count_sum_parameter, p.B,
                                                   self.G, p.RS, self.K, p.y, *outs)
-            return [o[:, :self.G] for o in outs]
-        if self.continuous:
+        elif self.continuous:
             K.continuous_moments(self.kind, p.A, self.Gn, p.B, self.G, p.RS, self.K, p.y, *outs)
-            return [o[:, :self.G] for o in outs]
-        K.likelihood_moments(self.kind, p.A, self.Gn, p.B, self.G, p.RS, self.K, p.y, *outs)
-        return [o[:, :self.G] for o in outs]
+        else:
+            K.likelihood_moments(self.kind, p.A, self.Gn, p.B, self.G, p.RS, self.K, p.y, *outs)
+
+    def moments(self, p, R, S, deterministic=False, mean_out=None, want_stddev=True):
+        """p_x_mean, p_x_stddev, stddev_of_p_x_given_z_mean marginalised over y
+        (GMVAE:3312-3386, including the y-weighted per-cluster mean of quirk Q7).  Needs the
+        head pre-activations of all K clusters, i.e. a plan whose decoder runs in one chunk.
+        ``mean_out`` / ``want_stddev`` as VAEEngine.moments."""
+        if p.chunk != self.K:
+            raise ValueError("moments need a single-chunk plan: lower the evaluation minibatch "
+                             "size or raise head_buffer_bytes")
+        bufs = getattr(p, "moment_bufs", None)
+        if bufs is None:
+            bufs = p.moment_bufs = [torch.empty(p.B, self.Gn, dtype=torch.float32, device=self.device)
+                                    for _ in range(3)]
+        if mean_out is None:
+            self._moments_launch(p, p.RS, bufs[0], bufs[1] if want_stddev else None,
+                                 bufs[2] if want_stddev else None)
+            mean = bufs[0]
+        else:
+            self._moments_launch(p, p.RS, mean_out, None, None)
+            if want_stddev:
+                self._moments_launch(p, p.RS, None, bufs[1], bufs[2])
+            mean = mean_out
+        return [mean[:, :self.G], bufs[1][:, :self.G] if want_stddev else None,
+                bufs[2][:, :self.G] if want_stddev else None]
 
     def max_single_chunk_minibatch(self, RS):
         """Largest minibatch whose K cluster passes fit the head buffers in one chunk."""

@@ -252,6 +252,76 @@ class PackedStream:
         return slot
 
 
+class ReconstructionSink:
+    """Streams the (N, G) reconstruction of an evaluation pass to the host (VAE:1939-2052, where
+    the reference concatenates ``p_x_mean`` of every ``session.run`` in host memory).
+
+    The moments kernel of minibatch b writes ``p_x_mean`` straight into one of two device staging
+    buffers (row pitch = the host row pitch, so the copy is ONE contiguous transfer); a copy
+    stream moves it into its rows of the pinned (N, G) result while minibatch b + 1 computes.
+    ``dtype`` float16 halves the transfer (an option the reference does not have; default fp32).
+    """
+
+    def __init__(self, number_of_rows, number_of_features, minibatch_size, device, dtype="float32"):
+        self.n, self.G, self.B = int(number_of_rows), int(number_of_features), int(minibatch_size)
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        if dtype not in ("float32", "float16"):
+            raise ValueError("reconstruction dtype: float32 or float16")
+        self.half = dtype == "float16"
+        # fp16 rows are written 8 columns per thread (scvae_f32_to_f16): pitch a multiple of 8
+        self.ld = -(-self.G // 8) * 8 if self.half else self.G
+        tdtype = torch.float16 if self.half else torch.float32
+        self.host = torch.empty(self.n, self.ld, dtype=tdtype, pin_memory=self.cuda)
+        self.mean32 = [torch.empty(self.B, self.ld, dtype=torch.float32, device=self.device)
+                       for _ in range(2 if not self.half else 1)]
+        self.stage16 = ([torch.empty(self.B, self.ld, dtype=tdtype, device=self.device)
+                         for _ in range(2)] if self.half else None)
+        self._copy_stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self._free = [None, None]
+        self.bytes_copied = 0
+        self.count = 0
+
+    def mean_buffer(self):
+        """Device buffer (B, ld) the moments kernel writes this minibatch's ``p_x_mean`` into."""
+        slot = self.count % 2
+        if self.cuda and not self.half and self._free[slot] is not None:
+            torch.cuda.current_stream().wait_event(self._free[slot])   # its last copy has left
+        return self.mean32[0 if self.half else slot]
+
+    def push(self, start, rows):
+        """Enqueue the transfer of the rows just written by the moments kernel."""
+        slot = self.count % 2
+        self.count += 1
+        if self.half:
+            if self.cuda and self._free[slot] is not None:
+                torch.cuda.current_stream().wait_event(self._free[slot])
+            K.f32_to_f16(self.mean32[0][:rows], self.ld, self.stage16[slot][:rows])
+            src = self.stage16[slot]
+        else:
+            src = self.mean32[slot]
+        dst = self.host[start:start + rows]
+        self.bytes_copied += dst.numel() * dst.element_size()
+        if not self.cuda:
+            dst.copy_(src[:rows])
+            return
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            dst.copy_(src[:rows], non_blocking=True)
+            if self._free[slot] is None:
+                self._free[slot] = torch.cuda.Event()
+            self._free[slot].record(self._copy_stream)
+
+    def finish(self):
+        """Wait for the last transfer; the (N, G) result as a numpy view of the pinned buffer."""
+        if self.cuda:
+            self._copy_stream.synchronize()
+        out = self.host.numpy()
+        return out if self.ld == self.G else out[:, :self.G]
+
+
 class TrainLoop:
     """One (engine, minibatch size) training loop with a CUDA-graph-captured step."""
 

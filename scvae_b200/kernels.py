@@ -150,11 +150,19 @@ def continuous_likelihood(kind, t, a, head_stride, M, G, logp=None, go=None, go_
                                                _p(logp), _stream()), "continuous_likelihood")
 
 
+def _ldo(*outs):
+    """Row pitch shared by the moment outputs that are requested (None = skipped)."""
+    given = [o for o in outs if o is not None]
+    if not given or any(_ld(o) != _ld(given[0]) for o in given):
+        raise ValueError("moment outputs: at least one, all with the same row pitch")
+    return _ld(given[0])
+
+
 def continuous_moments(kind, a, head_stride, B, G, RS, K_, y, p_x_mean, p_x_stddev, stddev_of_mean):
     lib = _lib.load()
     _lib.check(lib.scvae_continuous_moments(kind, _p(a), _ld(a), head_stride, B, G, RS, K_, _p(y),
                                             _ld(y) if y is not None else 0, _p(p_x_mean),
-                                            _p(p_x_stddev), _p(stddev_of_mean), _ld(p_x_mean),
+                                            _p(p_x_stddev), _p(stddev_of_mean), _ldo(p_x_mean, p_x_stddev, stddev_of_mean),
                                             _stream()), "continuous_moments")
 
 
@@ -332,7 +340,7 @@ def piecewise_moments(kind, k_max, a, head_stride, B, G, RS, p_x_mean, p_x_stdde
     lib = _lib.load()
     _lib.check(lib.scvae_piecewise_moments(kind, k_max, _p(a), _ld(a), head_stride, B, G, RS, K_,
                                            _p(y), _ld(y) if y is not None else 0, _p(p_x_mean),
-                                           _p(p_x_stddev), _p(stddev_of_mean), _ld(p_x_mean),
+                                           _p(p_x_stddev), _p(stddev_of_mean), _ldo(p_x_mean, p_x_stddev, stddev_of_mean),
                                            _stream()), "piecewise_moments")
 
 
@@ -351,7 +359,7 @@ def constrained_poisson_moments(a, lse, count_sum, B, G, RS, p_x_mean, p_x_stdde
     lib = _lib.load()
     _lib.check(lib.scvae_constrained_poisson_moments(_p(a), _ld(a), _p(lse), _p(count_sum), B, G, RS,
                                                      _p(p_x_mean), _p(p_x_stddev), _p(stddev_of_mean),
-                                                     _ld(p_x_mean), _stream()),
+                                                     _ldo(p_x_mean, p_x_stddev, stddev_of_mean), _stream()),
                "constrained_poisson_moments")
 
 
@@ -361,7 +369,7 @@ def constrained_poisson_mixture_moments(a, lse, count_sum, B, G, RS, K_, y, p_x_
     lib = _lib.load()
     _lib.check(lib.scvae_constrained_poisson_mixture_moments(
         _p(a), _ld(a), _p(lse), _p(count_sum), B, G, RS, K_, _p(y), _ld(y), _p(p_x_mean),
-        _p(p_x_stddev), _p(stddev_of_mean), _ld(p_x_mean), _stream()),
+        _p(p_x_stddev), _p(stddev_of_mean), _ldo(p_x_mean, p_x_stddev, stddev_of_mean), _stream()),
         "constrained_poisson_mixture_moments")
 
 
@@ -386,8 +394,7 @@ def likelihood_bwd(kind, t, a, head_stride, M, G, da, logp=None, row_const=None,
 def likelihood_moments(kind, a, head_stride, B, G, RS, K, y, p_x_mean, p_x_stddev,
                        stddev_of_mean):
     lib = _lib.load()
-    outs = [o for o in (p_x_mean, p_x_stddev, stddev_of_mean) if o is not None]
-    ldo = _ld(outs[0])
+    ldo = _ldo(p_x_mean, p_x_stddev, stddev_of_mean)
     _lib.check(lib.scvae_likelihood_moments(kind, _p(a), _ld(a), head_stride, B, G, RS, K,
                                             _p(y), _ld(y) if y is not None else 0,
                                             _p(p_x_mean), _p(p_x_stddev), _p(stddev_of_mean),

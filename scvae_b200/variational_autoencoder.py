@@ -154,8 +154,6 @@ class VariationalAutoencoder:
                 and self.reconstruction_distribution_name != "constrained poisson":
             problems.append("count-sum-parameterised likelihoods other than the constrained "
                             "Poisson")
-        if self.dropout_parts and self.type != "VAE":
-            problems.append("dropout for the GMVAE")
         if self.parameterise_latent_posterior:
             problems.append("parameterised latent posteriors")
         if problems:
@@ -774,6 +772,34 @@ class VariationalAutoencoder:
             raise Exception("Cannot {} model when it has not been trained.".format(what))
         return engine, directory, epoch
 
+    def _reconstruction_collector(self, engine, n, minibatch_size, R, S, deterministic, subset,
+                                  dtype):
+        """The per-minibatch consumer of an evaluation pass that assembles the reconstruction
+        (VAE:1939-2052): ``p_x_mean`` streams to pinned host memory behind the next minibatch
+        (hotloop.ReconstructionSink; ``dtype`` None = no reconstruction wanted); the two deviation
+        matrices are computed only for the minibatches that hold rows of ``subset``."""
+        import torch
+        from .hotloop import ReconstructionSink
+        G = self.feature_size
+        p_x_stddev = scipy.sparse.lil_matrix((n, G), dtype=numpy.float32)
+        stddev_of_p_x_mean = scipy.sparse.lil_matrix((n, G), dtype=numpy.float32)
+        sink = ReconstructionSink(n, G, minibatch_size, engine.device, dtype) if dtype else None
+
+        def collect(plan, start, rows):
+            if sink is None:
+                return
+            wanted = [i for i in subset if start <= i < start + rows]
+            out = sink.mean_buffer()
+            _, stddev, stddev_of_mean = engine.moments(
+                plan, R, S, deterministic, mean_out=out[:plan.B], want_stddev=bool(wanted))
+            sink.push(start, rows)
+            if wanted:
+                local = torch.tensor([i - start for i in wanted], device=engine.device)
+                p_x_stddev[wanted] = stddev[local].cpu().numpy()
+                stddev_of_p_x_mean[wanted] = stddev_of_mean[local].cpu().numpy()
+
+        return collect, sink, p_x_stddev, stddev_of_p_x_mean
+
     def evaluate(self, evaluation_set, minibatch_size=None, run_id=None,
                  use_early_stopping_model=False, use_best_model=False, **kwargs):
         """Evaluate a trained model (VAE:1781-2217).  Returns, in ``output_versions`` order, the
@@ -807,21 +833,10 @@ class VariationalAutoencoder:
         t_csr = x_csr if t_eval is x_eval else scipy.sparse.csr_matrix(t_eval, dtype=numpy.float32)
 
         want_reconstruction = "reconstructed" in output_versions
-        p_x_mean = numpy.empty((n, G), numpy.float32) if want_reconstruction else None
-        p_x_stddev = scipy.sparse.lil_matrix((n, G), dtype=numpy.float32)
-        stddev_of_p_x_mean = scipy.sparse.lil_matrix((n, G), dtype=numpy.float32)
         subset = sorted(int(i) for i in subset)
-
-        def collect(plan, start, rows):
-            if not want_reconstruction:
-                return
-            mean, stddev, stddev_of_mean = engine.moments(plan, R, S, deterministic)
-            p_x_mean[start:start + rows] = mean[:rows].cpu().numpy()
-            wanted = [i for i in subset if start <= i < start + rows]
-            if wanted:
-                local = torch.tensor([i - start for i in wanted], device=engine.device)
-                p_x_stddev[wanted] = stddev[local].cpu().numpy()
-                stddev_of_p_x_mean[wanted] = stddev_of_mean[local].cpu().numpy()
+        collect, sink, p_x_stddev, stddev_of_p_x_mean = self._reconstruction_collector(
+            engine, n, minibatch_size, R, S, deterministic, subset,
+            kwargs.get("reconstruction_dtype", "float32") if want_reconstruction else None)
 
         evaluating_time_start = time()
         from .hotloop import ResidentCSR
@@ -829,6 +844,7 @@ class VariationalAutoencoder:
         result = self._evaluate_pass(engine, x_data, x_data if t_csr is x_csr else t_csr,
                                      minibatch_size, R, S, deterministic=deterministic,
                                      seed=kwargs.get("noise_seed", 7), on_batch=collect)
+        p_x_mean = sink.finish() if sink is not None else None
         if numpy.isnan(result["lower_bound"]):
             raise ArithmeticError("Aborting. The ELBO for the evaluation set became indefinite.")
         if log_results:

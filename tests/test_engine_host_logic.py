@@ -257,3 +257,59 @@ def test_gmvae_engine_constrained_poisson_chunked_against_the_oracle(engine_on_c
     for key, g in grads.items():
         error = (got[key].double() - g).abs().max().item()
         assert error <= 3e-4 * g.abs().max().item() + 1e-5 * gmax, (key, error)
+
+
+@pytest.mark.parametrize("head_buffer_bytes,keep,lik,k_max", [
+    (4 << 30, [0.8, 0.9, 0.7, 0.6], "negative binomial", 0),
+    (20000, [0.8, 0.9, 0.7, 0.6], "zero-inflated negative binomial", 0),    # chunked decoder
+    (20000, [0.7, False, 0.8], "poisson", 2),              # no x / y dropout: the shared x W_x path
+])
+def test_gmvae_engine_dropout_against_the_oracle(engine_on_cpu, head_buffer_bytes, keep, lik, k_max):
+    """GMVAE dropout (GMVAE:276-296, :3036-3040): one mask per site AND per cluster build, the
+    first q(z|x,y) layer on K dropped copies of [x | e_k], the p(z|y) heads behind a dropped
+    one-hot, decoder sites sliced by the cluster chunks -- odd shapes, masks shared with the
+    oracle, with and without chunking."""
+    import numpy
+    from oracle import scvae_oracle as O
+    from scvae_b200.gmvae_engine import GMVAEEngine
+    G, L, Kc, hidden, B, R, S = 37, 3, 4, [7, 5], 9, 1, 2
+    cfg = O.GMVAEConfig(G, L, Kc, hidden, lik, R, S, True, kl_weight=0.8,
+                        number_of_reconstruction_classes=k_max, dropout_keep_probabilities=keep)
+    params = O.gmvae_init_params(cfg, seed=3, dtype=torch.float64)
+    gen = torch.Generator().manual_seed(4)
+    for k in params:
+        if k.endswith("biases") or k.endswith("beta"):
+            params[k] = torch.randn(params[k].shape, generator=gen, dtype=torch.float64) * 0.2
+    x = torch.tensor(numpy.minimum(O.synthetic_counts(B, G, n_types=3, seed=5)[0], 40.0),
+                     dtype=torch.float64)
+    eps = torch.randn(Kc, R * S, B, L, generator=gen, dtype=torch.float64)
+    state = O.AdamState(params)
+    reference = {k: v.clone() for k, v in params.items()}
+    dropout = {"generator": torch.Generator().manual_seed(11)}
+    out, grads = O.train_step(cfg, reference, state, x, x, eps, 1e-3, warm_up_weight=0.7,
+                              dropout=dropout)
+    eng = GMVAEEngine(G, L, Kc, hidden, lik, True, 0.8, "uniform", None, 0.0, tensor_cores=False,
+                      head_buffer_bytes=head_buffer_bytes, number_of_reconstruction_classes=k_max,
+                      dropout_keep_probabilities=keep)
+    eng.import_parameters(params)
+    plan = eng._plan(B, R * S)
+    assert (plan.chunk < Kc) == (head_buffer_bytes < 1 << 20)
+    eng.inject_dropout_masks(plan, dropout["masks"])
+    eng.set_batch_dense(plan, x.float())
+    plan.eps.copy_(eps.reshape(-1, L).float())
+    bound = eng.train_step(plan, R, S, 1e-3, warm_up_weight=0.7)
+    for i, key in enumerate(["lower_bound", "lower_bound_weighted", "reconstruction_error"]):
+        assert abs(bound[i].item() - out[key].item()) <= 5e-5 * abs(out[key].item()), key
+    # every mask the oracle drew was consumed: site names + one per cluster build
+    assert sorted(k for k in dropout["masks"] if "#" not in k) == sorted(plan.drop)
+    got = eng.export_gradients()
+    gmax = max(g.abs().max().item() for g in grads.values())
+    for key, g in grads.items():
+        error = (got[key].double() - g).abs().max().item()
+        assert error <= 3e-4 * g.abs().max().item() + 1e-5 * gmax, (key, error)
+    # evaluation never drops
+    eng.forward(plan, False, R, S, 1.0)
+    now = {k: v.double() for k, v in eng.export_parameters().items()}
+    ref_eval = O.gmvae_forward(cfg, now, x, x, eps, is_training=False)
+    assert abs(plan.bound[0].item() - ref_eval["lower_bound"].item()) <= 5e-5 * abs(
+        ref_eval["lower_bound"].item())

@@ -324,3 +324,36 @@ def test_training_from_host_resident_data_matches_device_resident(tmp_path):
         a, b = numpy.asarray(curves["device"][key]), numpy.asarray(curves["host"][key])
         assert numpy.allclose(a, b, rtol=2e-4), (key, a, b)
     assert curves["host"]["lower_bound"][-1] > curves["host"]["lower_bound"][0]
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float16"])
+def test_evaluate_streams_the_reconstruction_to_the_host(tmp_path, dtype):
+    """f2: p_x_mean of every minibatch goes through hotloop.ReconstructionSink (device staging
+    buffers, copy stream, pinned (N, G) result) -- several minibatches, a ragged last one, subset
+    rows with deviations -- and equals the oracle's moments of the restored variables."""
+    from scvae_b200.variational_autoencoder import VariationalAutoencoder
+    ds = _data(n=210, g=52, seed=12)           # 52 genes: not a multiple of 8 (fp16 row pitch)
+    model = VariationalAutoencoder(
+        feature_size=52, latent_size=3, hidden_sizes=[16],
+        reconstruction_distribution="negative binomial", log_directory=str(tmp_path), seed=2)
+    model.train(ds, number_of_epochs=2, minibatch_size=70, learning_rate=1e-2)
+    subset = {1, 40, 209}
+    _, reconstructed, latent = model.evaluate(
+        ds, minibatch_size=32, evaluation_subset_indices=subset, use_deterministic_z=True,
+        reconstruction_dtype=dtype, log_results=False)
+    values = reconstructed.values
+    assert values.shape == (210, 52)
+    params = {k: v.double() for k, v in model._get_engine().export_parameters().items()}
+    cfg = O.VAEConfig(52, 3, [16], "negative binomial")
+    x = torch.tensor(ds.values.toarray(), dtype=torch.float64)
+    out = O.vae_forward(cfg, params, x, x, torch.zeros(1, 210, 3, dtype=torch.float64),
+                        is_training=False, use_deterministic_z=True, moments=True)
+    want = out["p_x_mean"].numpy()
+    tol = 2e-3 if dtype == "float16" else 2e-4
+    assert numpy.abs(values.astype(numpy.float64) - want).max() <= tol * max(1.0, numpy.abs(want).max())
+    total = reconstructed.total_standard_deviations
+    for i in subset:
+        got = total[i].toarray().reshape(-1)
+        ref = out["p_x_stddev"][i].numpy()
+        assert numpy.abs(got - ref).max() <= 2e-4 * max(1.0, numpy.abs(ref).max())
+    assert total[2].toarray().max() == 0

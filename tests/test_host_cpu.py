@@ -40,10 +40,10 @@ def test_option_validation_mirrors_the_scope():
     # still outside: loud, never silently degraded
     VariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
                            dropout_keep_probabilities=[0.9])          # VAE: built
-    with pytest.raises(NotImplementedError):
-        GaussianMixtureVariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
-                                              number_of_latent_clusters=3,
-                                              dropout_keep_probabilities=[0.9])
+    model = GaussianMixtureVariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
+                                                  number_of_latent_clusters=3,
+                                                  dropout_keep_probabilities=[0.9, 0.8, 0.7, 0.6])
+    assert "dropout_0.9_0.8_0.7_0.6" in model.name          # GMVAE: built, four keep probabilities
     GaussianMixtureVariationalAutoencoder(feature_size=50, latent_size=4, hidden_sizes=[16],
                                           number_of_latent_clusters=3,
                                           reconstruction_distribution="constrained poisson")

@@ -93,6 +93,12 @@ def test_dropout_through_the_model_class_on_cpu(shell_on_cpu, tmp_path):
     assert "dropout_fwd" in shell_on_cpu and "dropout_bwd" in shell_on_cpu
 
 
+def test_gmvae_dropout_through_the_model_class_on_cpu(shell_on_cpu, tmp_path):
+    import test_zz_gpu_reference_graph as Z
+    Z.test_gmvae_train_evaluate_with_dropout(tmp_path)
+    assert "dropout_fwd" in shell_on_cpu and "dropout_bwd" in shell_on_cpu
+
+
 def test_gmvae_constrained_poisson_through_the_model_class_on_cpu(shell_on_cpu, tmp_path):
     import test_zz_gpu_reference_graph as Z
     Z.test_gmvae_train_evaluate_constrained_poisson(tmp_path)

@@ -29,7 +29,7 @@ VAE_EVAL = ["vae_c1_poisson_eval", "vae_nb_eval", "vae_nb_eval_deterministic", "
 # batch norm -- come last)
 GMVAE_TRAIN = ["gmvae_nb_train", "gmvae_zinb_train_mc", "gmvae_poisson_learn_train",
                "gmvae_nb_free_nats_train", "gmvae_nb_k2_train", "gmvae_nb_bc_count_sum_train",
-               "gmvae_nb_custom_prior_train"]
+               "gmvae_nb_custom_prior_train", "gmvae_nb_dropout_train"]
 GMVAE_EVAL = ["gmvae_nb_eval", "gmvae_nb_no_bn_eval"]
 
 
@@ -180,11 +180,15 @@ def _gmvae(name):
         tensor_cores=False,
         number_of_batches=kw.get("number_of_batches", 0) if kw.get("batch_correction") else 0,
         count_sum_feature=kw.get("count_sum", False),
-        number_of_reconstruction_classes=kw.get("number_of_reconstruction_classes", 0))
+        number_of_reconstruction_classes=kw.get("number_of_reconstruction_classes", 0),
+        dropout_keep_probabilities=kw.get("dropout_keep_probabilities"))
     eng.import_parameters(_params(meta, groups))
     feeds = groups["in_feed"]
     B = feeds["X"].shape[0]
     plan = eng._plan(B, R * S)
+    if "in_dropout" in groups:           # the recorded per-site, per-build keep masks
+        eng.inject_dropout_masks(plan, {site: torch.tensor(mask, dtype=torch.float32)
+                                        for site, mask in groups["in_dropout"].items()})
     eng.set_batch_dense(plan, torch.tensor(feeds["X"], dtype=torch.float32).cuda())
     if kw.get("batch_correction") or kw.get("count_sum"):
         eng.set_batch_features(
@@ -392,6 +396,34 @@ def test_train_evaluate_with_dropout(tmp_path):
     assert numpy.isfinite(reconstructed.values).all()
     # evaluation is deterministic given the noise seed: no dropout outside training
     again = model.evaluate(test, minibatch_size=64, output_versions="reconstructed")
+    assert numpy.allclose(reconstructed.values, again.values, rtol=1e-5, atol=1e-6)
+
+
+def test_gmvae_train_evaluate_with_dropout(tmp_path):
+    """GMVAE with all four keep probabilities end to end through the model class: masks drawn on
+    the device inside the captured step (one per site and cluster build), none in evaluation."""
+    import scipy.sparse
+    from oracle import scvae_oracle as O
+    from scvae_b200 import model_utilities as MU
+    from scvae_b200.data_set import DataSet
+    from scvae_b200.gaussian_mixture_variational_autoencoder import (
+        GaussianMixtureVariationalAutoencoder)
+    x, labels = O.synthetic_counts(240, 64, n_types=3, seed=3, target_zero_fraction=0.8)
+    full = DataSet("toy", values=scipy.sparse.csr_matrix(numpy.minimum(x, 50.0)),
+                   labels=labels.astype(str))
+    training, validation, test = full.split()
+    model = GaussianMixtureVariationalAutoencoder(
+        feature_size=64, latent_size=4, hidden_sizes=[32, 16], number_of_latent_clusters=3,
+        reconstruction_distribution="negative binomial",
+        dropout_keep_probabilities=[0.8, 0.9, 0.7, 0.6], log_directory=str(tmp_path), seed=1)
+    assert "dropout_0.8_0.9_0.7_0.6" in model.name
+    assert model.train(training, validation, number_of_epochs=3, minibatch_size=48,
+                       learning_rate=1e-2, shuffle_seed=0) == 0
+    curve = MU.load_learning_curves(model, "training")["lower_bound"]
+    assert len(curve) == 3 and numpy.isfinite(curve).all()
+    reconstructed = model.evaluate(test, minibatch_size=32, output_versions="reconstructed")
+    again = model.evaluate(test, minibatch_size=32, output_versions="reconstructed")
+    assert numpy.isfinite(reconstructed.values).all()
     assert numpy.allclose(reconstructed.values, again.values, rtol=1e-5, atol=1e-6)
 
 

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv \
+    --log-file gpurun_out/launches_b100.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-extra --no-parity --no-e2e --minibatch 100 \
+    > gpurun_out/bench_under_ncu.log 2>&1
+tail -2 gpurun_out/bench_under_ncu.log | cut -c1-200

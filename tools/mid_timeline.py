@@ -7,6 +7,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from scvae_b200.engine import VAEEngine
 from scvae_b200.hotloop import ResidentCSR, TrainLoop
 B, G, L = 4096, 20000, 50
+for a in sys.argv[1:]:
+    if a.isdigit():
+        B = int(a)
 dev = torch.device("cuda:0")
 rng = numpy.random.RandomState(1)
 x = ((rng.rand(2 * B, G) < 0.07) * numpy.floor(1 - numpy.log(rng.rand(2 * B, G)) * 1.2)).astype(numpy.float32)
