@@ -91,16 +91,25 @@ int scvae_csr_densify_u16(const int64_t *indptr, const void *indices_u16, const 
                           const int64_t *rows, int B, int G, float *x, int64_t ldx,
                           float *row_const, int rebase, void *t16, int64_t ldt16, void *x16,
                           int64_t ldx16, void *stream);
-/* Streamed form of the same gather: the B rows of a minibatch arrive as ONE packed slab (a single
- * host -> device copy per step, ~2 bytes per non-zero):
- *   int32 rowptr[B + 1] at offset 0 (entry offsets relative to the slab's first entry),
- *   float row_const[B] at off_const, uint8 blocks[B][ceil(G / 255)] at off_blocks (non-zeros of the
- *   row per block of 255 genes: a count fits one byte), uint8 entries[nnz][1 + value_bytes] at
- *   off_entries (gene index within its block, then the count as uint8 or little-endian uint16).
- * Outputs as the 16-bit outputs of scvae_csr_densify; row_const (nullable) receives the slab's copy. */
-int scvae_csr_densify_packed(const void *slab, int64_t off_const, int64_t off_blocks,
-                             int64_t off_entries, int value_bytes, int B, int G, float *row_const,
-                             void *t16, int64_t ldt16, void *x16, int64_t ldx16, void *stream);
+/* Streamed form of the same gather (hotloop.PackedStream; replaces the reference's per-step
+ * `x_train[batch_indices].toarray()` + feed_dict copy, VAE:985-1029, for matrices that stay in
+ * host memory): the B rows of a minibatch arrive as ONE packed slab -- a single host -> device
+ * copy per step, ~2 bytes per non-zero:
+ *   int32 row_offset[B + 1] | float row_const[B] | (pad: strings start at
+ *   scvae_packed_rows_offset(B)) | row strings, a row string (little endian, byte aligned) being
+ *   u16 nesc | u8 blocks[ceil(G / 255)] | (u8 index in block, u8 count)[nnz] | (u16 entry, u16 count)[nesc]
+ * blocks[k] = non-zeros of the row among the genes [255 k, 255 k + 255); a count byte of 255 is an
+ * escape whose value is the escape-list entry with that entry position.  G <= 65280.
+ * Outputs as the 16-bit outputs of scvae_csr_densify; row_const (nullable) receives the slab's copy.
+ * scvae_pack_row_slab is the HOST routine that assembles such a slab (into pinned memory) from
+ * the per-row strings encoded once per data set: store + row_off[n_rows + 1] (byte offsets),
+ * order[rows] = the minibatch's rows; `threads` host threads copy the strings. */
+int64_t scvae_packed_rows_offset(int B);
+int scvae_csr_densify_packed(const void *slab, int B, int G, float *row_const, void *t16,
+                             int64_t ldt16, void *x16, int64_t ldx16, void *stream);
+int scvae_pack_row_slab(const uint8_t *store, const int64_t *row_off, const float *row_const_all,
+                        const int64_t *order, int rows, int64_t n_rows, uint8_t *dst,
+                        int64_t dst_capacity, int threads, int64_t *bytes_out);
 /* Dense fp32 counts -> uint16 (clamped), zero padded to ldt16 columns. */
 int scvae_f32_to_u16(const float *x, int64_t ldx, int64_t rows, int G, void *t16, int64_t ldt16,
                      void *stream);

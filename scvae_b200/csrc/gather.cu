@@ -222,31 +222,34 @@ static int launch_densify(const int64_t *indptr, const IdxT *indices, const ValT
     return 0;
 }
 
-// ---- packed row slab (the streamed wire format, 2 bytes per non-zero) ---------------------------------
-// A minibatch of B rows travels host -> device as ONE contiguous slab:
-//   int32  rowptr[B + 1]         entry offsets relative to the slab's first entry
-//   float  row_const[B]          sum_g lgamma(1 + x) per cell
-//   uint8  blocks[B][nblk]       non-zeros of the row per block of 255 genes (nblk = ceil(G / 255))
-//   uint8  entries[nnz][1 + VB]  gene index within its block, then the count (VB = 1: counts <= 255,
-//                                VB = 2: little-endian uint16)
-// (8 bytes per non-zero as int32 + fp32 CSR, 4 as uint16 + uint16, ~2.06 here at 7 % density.)
+// ---- packed row slabs (hotloop.PackedStream) -----------------------------------------------------
+// slab = int32 row_offset[B + 1] | float row_const[B] | (pad to 16) | row strings; a row string is
+//   u16 nesc | u8 blocks[nblk] | (u8 index in block, u8 count)[nnz] | (u16 entry, u16 count)[nesc]
+// (little endian, byte aligned): blocks[k] = non-zeros of the row among the genes [255 k, 255 k + 255)
+// (so a count fits one byte), a count byte of 255 is an escape whose value is looked up by entry
+// position in the row's (sorted) escape list.  ~2 bytes per non-zero.
 // One CTA per row: block counts -> prefix sums in shared memory; every entry finds its block by
 // binary search of its position in the row; the row is assembled in shared memory as for the CSR
 // form and written as fp16 (x16, augmented) and / or uint16 (t16).
 constexpr int kPackedBlock = 255;      // genes per block: a block's non-zero count fits one byte
-template <bool X16_DIRECT, int VB>
+__host__ __device__ inline int64_t packed_rows_offset(int B) { return (((int64_t)8 * B + 4) + 15) & ~(int64_t)15; }
+template <bool X16_DIRECT>
 __global__ void __launch_bounds__(256)
-csr_densify_packed_kernel(const uint8_t *__restrict__ slab, int64_t off_const, int64_t off_blocks, int64_t off_entries,
-                          int G, int nblk, float *__restrict__ row_const, uint16_t *__restrict__ t16, int64_t ldt16,
-                          __half *__restrict__ x16, int64_t ldx16, int width8) {
+csr_densify_packed_kernel(const uint8_t *__restrict__ slab, int B, int G, int nblk, float *__restrict__ row_const,
+                          uint16_t *__restrict__ t16, int64_t ldt16, __half *__restrict__ x16, int64_t ldx16,
+                          int width8) {
     extern __shared__ __align__(16) uint16_t row16[];
     __shared__ int prefix[260];
     __shared__ int warp_tot[8];
     const int b = blockIdx.x;
-    const int32_t *rp = reinterpret_cast<const int32_t *>(slab);
-    const int s = rp[b], e = rp[b + 1];
-    const uint8_t *blocks = slab + off_blocks + (int64_t)b * nblk;
-    const uint8_t *entries = slab + off_entries;
+    const int32_t *ro = reinterpret_cast<const int32_t *>(slab);
+    const uint8_t *str = slab + packed_rows_offset(B) + ro[b];
+    const int len = ro[b + 1] - ro[b];
+    const int nesc = (int)str[0] | ((int)str[1] << 8);
+    const uint8_t *blocks = str + 2;
+    const uint8_t *entries = blocks + nblk;
+    const int nnz = (len - 2 - nblk - 4 * nesc) >> 1;
+    const uint8_t *esc = entries + 2 * nnz;
     uint4 *row4 = reinterpret_cast<uint4 *>(row16);
     for (int i = threadIdx.x; i < width8; i += blockDim.x) row4[i] = make_uint4(0u, 0u, 0u, 0u);
     // inclusive scan of the block counts (nblk <= 256: one element per thread)
@@ -266,20 +269,30 @@ csr_densify_packed_kernel(const uint8_t *__restrict__ slab, int64_t off_const, i
         prefix[threadIdx.x + 1] = v + base;       // prefix[k] = entries of the blocks < k
     }
     __syncthreads();
-    for (int i0 = s + threadIdx.x; i0 < e; i0 += 4 * blockDim.x) {
+    for (int i0 = threadIdx.x; i0 < nnz; i0 += 4 * blockDim.x) {
         int lo8[4], val[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int i = i0 + k * (int)blockDim.x;
-            const bool in = i < e;
-            const uint8_t *p = entries + (int64_t)i * (1 + VB);
+            const bool in = i < nnz;
+            const uint8_t *p = entries + 2 * i;
             lo8[k] = in ? (int)p[0] : -1;
-            val[k] = in ? (VB == 1 ? (int)p[1] : ((int)p[1] | ((int)p[2] << 8))) : 0;
+            val[k] = in ? (int)p[1] : 0;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (lo8[k] < 0) continue;
-            const int pos = i0 + k * (int)blockDim.x - s;
+            const int pos = i0 + k * (int)blockDim.x;
+            if (val[k] == 255) {                         // escape: counts >= 255, by entry position
+                int lo = 0, hi = nesc - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const int at = (int)esc[4 * mid] | ((int)esc[4 * mid + 1] << 8);
+                    if (at < pos) lo = mid + 1;
+                    else hi = mid;
+                }
+                val[k] = (int)esc[4 * lo + 2] | ((int)esc[4 * lo + 3] << 8);
+            }
             int lo = 0, hi = nblk;                       // largest blk with prefix[blk] <= pos
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
@@ -292,7 +305,7 @@ csr_densify_packed_kernel(const uint8_t *__restrict__ slab, int64_t off_const, i
         }
     }
     if (X16_DIRECT && threadIdx.x == 0) row16[G] = 0x3C00;   // ones column
-    if (row_const && threadIdx.x == 0) row_const[b] = reinterpret_cast<const float *>(slab + off_const)[b];
+    if (row_const && threadIdx.x == 0) row_const[b] = reinterpret_cast<const float *>(slab + 4 * (B + 1))[b];
     __syncthreads();
     for (int i = threadIdx.x; i < width8; i += blockDim.x) {
         const int c = i << 3;
@@ -382,15 +395,13 @@ extern "C" int scvae_csr_densify_u16(const int64_t *indptr, const void *indices_
                                               (__half *)x16, ldx16, (cudaStream_t)stream);
 }
 
-extern "C" int scvae_csr_densify_packed(const void *slab, int64_t off_const, int64_t off_blocks,
-                                        int64_t off_entries, int value_bytes, int B, int G,
-                                        float *row_const, void *t16, int64_t ldt16, void *x16, int64_t ldx16,
-                                        void *stream) {
+extern "C" int64_t scvae_packed_rows_offset(int B) { return scvae::packed_rows_offset(B); }
+
+extern "C" int scvae_csr_densify_packed(const void *slab, int B, int G, float *row_const, void *t16, int64_t ldt16,
+                                        void *x16, int64_t ldx16, void *stream) {
     using namespace scvae;
-    SCVAE_CHECK_ARG(slab && (x16 || t16) && B >= 0 && G > 0 && G <= 65536, "csr_densify_packed: bad arguments");
-    SCVAE_CHECK_ARG(value_bytes == 1 || value_bytes == 2, "csr_densify_packed: counts travel as 1 or 2 bytes");
-    SCVAE_CHECK_ARG((reinterpret_cast<uintptr_t>(slab) & 3u) == 0 && off_const % 4 == 0,
-                    "csr_densify_packed: the slab must be 4-byte aligned");
+    SCVAE_CHECK_ARG(slab && (x16 || t16) && B >= 0 && G > 0 && G <= 65280, "csr_densify_packed: bad arguments");
+    SCVAE_CHECK_ARG((reinterpret_cast<uintptr_t>(slab) & 3u) == 0, "csr_densify_packed: the slab must be 4-byte aligned");
     SCVAE_CHECK_ARG(!t16 || (ldt16 % 8 == 0 && ldt16 >= G && aligned16(t16)), "csr_densify_packed: bad t16 layout");
     SCVAE_CHECK_ARG(!x16 || (ldx16 % 8 == 0 && ldx16 > G && aligned16(x16)), "csr_densify_packed: bad x16 layout");
     if (B == 0) return 0;
@@ -401,29 +412,21 @@ extern "C" int scvae_csr_densify_packed(const void *slab, int64_t off_const, int
     const int smem = width8 * 16;
     SCVAE_CHECK_ARG(smem <= 200 * 1024, "csr_densify_packed: row too wide");
     const int nblk = (G + kPackedBlock - 1) / kPackedBlock;
-    SCVAE_CHECK_ARG(nblk <= 256, "csr_densify_packed: at most 65280 genes");
     const uint8_t *sl = (const uint8_t *)slab;
     cudaStream_t s = (cudaStream_t)stream;
-#define PACKED(DIRECT, VBYTES)                                                                                   \
-    do {                                                                                                         \
-        static bool attr_set = false;                                                                            \
-        if (!attr_set) {                                                                                         \
-            cudaFuncSetAttribute(csr_densify_packed_kernel<DIRECT, VBYTES>,                                      \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);                       \
-            attr_set = true;                                                                                     \
-        }                                                                                                        \
-        csr_densify_packed_kernel<DIRECT, VBYTES><<<B, 256, smem, s>>>(sl, off_const, off_blocks, off_entries, G, \
-                                                                       nblk, row_const, (uint16_t *)t16, ldt16,   \
-                                                                       (__half *)x16, ldx16, width8);            \
+#define PACKED(DIRECT)                                                                                            \
+    do {                                                                                                          \
+        static bool attr_set = false;                                                                             \
+        if (!attr_set) {                                                                                          \
+            cudaFuncSetAttribute(csr_densify_packed_kernel<DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                 200 * 1024);                                                                     \
+            attr_set = true;                                                                                      \
+        }                                                                                                         \
+        csr_densify_packed_kernel<DIRECT><<<B, 256, smem, s>>>(sl, B, G, nblk, row_const, (uint16_t *)t16, ldt16, \
+                                                               (__half *)x16, ldx16, width8);                     \
     } while (0)
-    const bool direct = x16 && !t16;
-    if (direct) {
-        if (value_bytes == 1) PACKED(true, 1);
-        else PACKED(true, 2);
-    } else {
-        if (value_bytes == 1) PACKED(false, 1);
-        else PACKED(false, 2);
-    }
+    if (x16 && !t16) PACKED(true);
+    else PACKED(false);
 #undef PACKED
     SCVAE_CHECK_LAUNCH("csr_densify_packed");
     return 0;

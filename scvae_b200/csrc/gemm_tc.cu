@@ -29,6 +29,11 @@ constexpr int kDualStages = 4;
 constexpr int kDualStageBytes = 3 * kTileBytes;
 constexpr int kSmemBytes = kStages * kStageBytes + 2 * kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int kSmemBytesDual = kDualStages * kDualStageBytes + 2 * kEpiBytes + 1024 + 256;
+// pair mode (dual forward only): one work item covers TWO m-tiles that share the (high, low) weight
+// tiles -- four tiles per stage for two output tiles instead of six, three stages
+constexpr int kPairStages = 3;
+constexpr int kPairStageBytes = 4 * kTileBytes;
+constexpr int kSmemBytesPair = kPairStages * kPairStageBytes + 2 * kEpiBytes + 1024 + 256;
 constexpr int kTmemCols = 2 * BN;                // double-buffered fp32 accumulator
 constexpr int kThreads = 256;
 
@@ -43,6 +48,7 @@ struct GemmParams {
     int units_per_cta, total_units;
     int dual;                 // 0: C = A B;  1: C = (A + X) B;  2: C = A (B + X)   (X: the low-order half
                               // of an fp32 operand split into two fp16 matrices, same shape and major)
+    int m_mult;               // m-tiles per work item (2 in pair mode: tiles_m counts pairs)
 };
 
 // One unit of work of a CTA: k-blocks [kb0, kb1) of output tile (tm, tn).
@@ -71,7 +77,7 @@ struct WorkIter {
             u += s.kb1 - s.kb0;
             s.tm = tile % p.tiles_m;
             s.tn = tile / p.tiles_m;
-            s.out_row = s.tm * BM;
+            s.out_row = s.tm * BM * p.m_mult;
             s.partial = !(s.kb0 == 0 && s.kb1 == p.nkb);
             return true;
         }
@@ -83,7 +89,7 @@ struct WorkIter {
         const int sp = item / (p.tiles_m * p.tiles_n);
         s.kb0 = sp * p.kb_per_split;
         s.kb1 = min(s.kb0 + p.kb_per_split, p.nkb);
-        s.out_row = (p.nsplit > 1 ? sp * p.ws_rows : 0) + s.tm * BM;
+        s.out_row = (p.nsplit > 1 ? sp * p.ws_rows : 0) + s.tm * BM * p.m_mult;
         s.partial = false;
         return true;
     }
@@ -93,15 +99,18 @@ struct WorkIter {
 // otherwise fp32 consumed as tf32 (32-element k-blocks, 32-byte-atom swizzle for MN-major).
 // DUAL (compile time, so that no tcgen05.mma sits under a run-time predicate): 0: C = A B;
 // 1: C = (A + X) B;  2: C = A (B + X).
-template <bool F16, bool A_MN, bool B_MN, int DUAL = 0>
+template <bool F16, bool A_MN, bool B_MN, int DUAL = 0, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX,
                  const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    constexpr int nstages = DUAL ? kDualStages : kStages;
-    constexpr int stage_bytes = DUAL ? kDualStageBytes : kStageBytes;
+    static_assert(!PAIR || (DUAL == 2 && !A_MN), "pair mode: forward with split weights only");
+    constexpr int nstages = PAIR ? kPairStages : (DUAL ? kDualStages : kStages);
+    constexpr int stage_bytes = PAIR ? kPairStageBytes : (DUAL ? kDualStageBytes : kStageBytes);
+    constexpr int ACC_COLS = PAIR ? 2 * BN : BN;     // TMEM columns of one work item's accumulators
+    constexpr int TMEM_COLS = 2 * ACC_COLS;          // double buffered
     uint8_t *epi = smem + nstages * stage_bytes;
     uint64_t *bars = (uint64_t *)(epi + 2 * kEpiBytes);
     // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem base address
@@ -140,7 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "n"(kTmemCols)
+                     "n"(TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -157,7 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             WorkIter work;
             Segment sg;
             while (work.next(p, sg)) {
-                const int tm = sg.tm, tn = sg.tn, kb0 = sg.kb0, kb1 = sg.kb1;
+                const int tm = PAIR ? 2 * sg.tm : sg.tm, tn = sg.tn, kb0 = sg.kb0, kb1 = sg.kb1;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t sa = smem_u32(smem + stage * stage_bytes);
@@ -165,6 +174,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t sx = sb + kTileBytes;
                     const uint32_t full = bar_full + 8 * stage;
                     mbar_expect_tx(full, stage_bytes);
+                    // pair mode: the second m-tile (rows beyond M arrive as zeros)
+                    if (PAIR) tma_load_2d(sx + kTileBytes, &tmA, kb * BKE, (tm + 1) * BM, full);
                     if (DUAL == 1) {
                         if (A_MN) {
 #pragma unroll
@@ -219,7 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t acc_phase = (t >> 1) & 1;
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
+                const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
@@ -245,6 +256,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint64_t a2 = DUAL == 1 ? dx : da, b2 = DUAL == 1 ? db : dx;
 #pragma unroll
                         for (int k = 0; k < BKE / UK; ++k) tc_mma_f16(tmem_d, a2 + k * sta, b2 + k * stb, idesc, 1u);
+                        if constexpr (PAIR) {
+                            // second m-tile against the same (high, low) weight tiles
+                            const uint64_t da1 = make_desc(sx + kTileBytes, 16, 1024, 2);
+#pragma unroll
+                            for (int k = 0; k < BKE / UK; ++k)
+                                tc_mma_f16(tmem_d + BN, da1 + k * sta, db + k * stb, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                            for (int k = 0; k < BKE / UK; ++k) tc_mma_f16(tmem_d + BN, da1 + k * sta, dx + k * stb, idesc, 1u);
+                        }
                     }
                     tc_commit(bar_empty + 8 * stage);  // frees the smem slot once the MMAs retire
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -267,12 +287,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t acc_phase = (t >> 1) & 1;
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            const int out_row = sg.out_row;
+#pragma unroll 1
+            for (int half = 0; half < (PAIR ? 2 : 1); ++half) {
+            const int out_row = sg.out_row + half * BM;
+            if (half && (2 * sg.tm + 1) * BM >= p.M) break;      // (uniform) no second m-tile
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 if (tn * BN + c * 32 >= p.N) break;   // uniform: nothing to store
                 uint32_t v[32];
-                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + half * BN + c * 32, v);
                 tc_wait_ld();
                 if (issuer) tma_wait_read<1>();       // staging buffer `buf` is free again
                 epi_bar_sync();
@@ -298,6 +321,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 buf ^= 1;
             }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
@@ -309,7 +333,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS)
                      : "memory");
     }
 }
@@ -367,10 +391,11 @@ static double wave_efficiency(int items, int sms) {
     return (double)items / ((double)rounds * sms);
 }
 
-static SplitPlan plan_split(int M, int N, int K, int bke = BK, bool allow_streamk = false) {
+static SplitPlan plan_split(int M, int N, int K, int bke = BK, bool allow_streamk = false, bool pair_m = false) {
     SplitPlan s;
     const int sms = num_sms();
     s.tiles_m = (M + BM - 1) / BM;
+    if (pair_m) s.tiles_m = (s.tiles_m + 1) / 2;      // work items cover two m-tiles
     s.tiles_n = (N + BN - 1) / BN;
     s.nkb = (K + bke - 1) / bke;
     s.streamk = 0;
@@ -405,12 +430,27 @@ static SplitPlan plan_split(int M, int N, int K, int bke = BK, bool allow_stream
     return s;
 }
 
+// Pair mode (two m-tiles per work item) of the dual forward product: off with SCVAE_TC_PAIR=0.
+static bool pair_enabled(int M) {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("SCVAE_TC_PAIR");
+        on = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return on && M > BM;
+}
+
 static int64_t workspace_bytes(int M, int N, int K, int bke) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
-    const SplitPlan s = plan_split(M, N, K, bke);
-    if (s.nsplit == 1) return 0;
     const int64_t ldw = (N + 3) & ~3;
-    return (int64_t)s.nsplit * s.tiles_m * BM * ldw * 4;
+    const SplitPlan s = plan_split(M, N, K, bke);
+    int64_t need = s.nsplit == 1 ? 0 : (int64_t)s.nsplit * s.tiles_m * BM * ldw * 4;
+    if (bke == 64 && pair_enabled(M)) {       // the same product may run in pair mode (split operand)
+        const SplitPlan q = plan_split(M, N, K, bke, false, true);
+        const int64_t alt = q.nsplit == 1 ? 0 : (int64_t)q.nsplit * q.tiles_m * 2 * BM * ldw * 4;
+        if (alt > need) need = alt;
+    }
+    return need;
 }
 
 template <bool F16>
@@ -424,9 +464,10 @@ static int launch_gemm(const char *name, int layout, int M, int N, int K, const 
     SCVAE_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "%s: bad arguments", name);
     SCVAE_CHECK_ARG(aligned16(A) && aligned16(B) && aligned16(C) && lda % LDM == 0 && ldb % LDM == 0 && ldc % 4 == 0,
                     "%s: operands must be 16-byte aligned with 16-byte-multiple leading dimensions", name);
-    SplitPlan sp = plan_split(M, N, K, BKE, /*allow_streamk=*/!accumulate);
+    const bool pair = F16 && dual == 2 && layout == SCVAE_GEMM_NT && pair_enabled(M);
+    SplitPlan sp = plan_split(M, N, K, BKE, /*allow_streamk=*/!accumulate && !pair, pair);
     const int64_t ldw = (N + 3) & ~3;
-    const int ws_rows = sp.tiles_m * BM;
+    const int ws_rows = sp.tiles_m * BM * (pair ? 2 : 1);
     if (sp.nsplit > 1) {
         const int64_t need = (int64_t)sp.nsplit * ws_rows * ldw * 4;
         if (!workspace || workspace_bytes_given < need) {  // no workspace: run unsplit
@@ -472,6 +513,7 @@ static int launch_gemm(const char *name, int layout, int M, int N, int K, const 
     if (const char *e = getenv("SCVAE_TC_MN_SBO")) p.mn_sbo = (uint32_t)atoi(e);
 
     p.dual = dual;
+    p.m_mult = pair ? 2 : 1;
     p.streamk = sp.streamk;
     p.units_per_cta = sp.units_per_cta;
     p.total_units = sp.tiles_m * sp.tiles_n * sp.nkb;
@@ -485,30 +527,31 @@ static int launch_gemm(const char *name, int layout, int M, int N, int K, const 
         cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), s);
         SCVAE_CHECK_ARG(e == cudaSuccess, "%s: memset failed: %s", name, cudaGetErrorString(e));
     }
-#define LAUNCH(AM, BMN, DU)                                                                                 \
+#define LAUNCH(AM, BMN, DU, PR)                                                                             \
     do {                                                                                                    \
-        constexpr int smem_bytes = (DU) ? kSmemBytesDual : kSmemBytes;                                      \
+        constexpr int smem_bytes = (PR) ? kSmemBytesPair : ((DU) ? kSmemBytesDual : kSmemBytes);            \
         static bool attr_set = false;                                                                       \
         if (!attr_set) {                                                                                    \
-            cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<F16, AM, BMN, DU>,                          \
+            cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<F16, AM, BMN, DU, PR>,                      \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);  \
             SCVAE_CHECK_ARG(e == cudaSuccess, "%s: cannot set smem attribute: %s", name,                    \
                             cudaGetErrorString(e));                                                         \
             attr_set = true;                                                                                \
         }                                                                                                   \
-        gemm_tc_kernel<F16, AM, BMN, DU><<<grid, kThreads, smem_bytes, s>>>(tmA, tmB, tmC, tmX, p);         \
+        gemm_tc_kernel<F16, AM, BMN, DU, PR><<<grid, kThreads, smem_bytes, s>>>(tmA, tmB, tmC, tmX, p);     \
     } while (0)
     if (dual == 0) {
         switch (layout) {
-            case SCVAE_GEMM_NT: LAUNCH(false, false, 0); break;
-            case SCVAE_GEMM_NN: LAUNCH(false, true, 0); break;
-            case SCVAE_GEMM_TN: LAUNCH(true, true, 0); break;
+            case SCVAE_GEMM_NT: LAUNCH(false, false, 0, false); break;
+            case SCVAE_GEMM_NN: LAUNCH(false, true, 0, false); break;
+            case SCVAE_GEMM_TN: LAUNCH(true, true, 0, false); break;
             default: set_error("%s: unknown layout %d", name, layout); return 1;
         }
     } else if (F16 && dual == 2 && layout == SCVAE_GEMM_NT) {
-        LAUNCH(false, false, 2);          // forward with split weights
+        if (pair) LAUNCH(false, false, 2, true);     // forward with split weights, two m-tiles per item
+        else LAUNCH(false, false, 2, false);
     } else if (F16 && dual == 1 && layout == SCVAE_GEMM_TN) {
-        LAUNCH(true, true, 1);            // weight gradient with split output gradient
+        LAUNCH(true, true, 1, false);     // weight gradient with split output gradient
     } else {
         set_error("%s: split operands are built for NT (which = 2) and TN (which = 1)", name);
         return 1;

@@ -142,30 +142,78 @@ class PackedStream:
     ``scvae_csr_densify_packed``: ~2 bytes per non-zero, a single host -> device copy per step)
     into one of two device staging buffers on a copy stream while the previous step computes.
 
-    ``pack_epoch(order)`` lays the epoch out slab by slab in pinned memory (row order = the
-    epoch's permutation); ``fetch(slot, k)`` enqueues the copy of slab k.  For matrices beyond
-    HBM, and the host-to-device leg of `bench.py`'s end-to-end number."""
+    Every row is encoded ONCE (block counts, (index, count) byte pairs, an escape list for counts
+    >= 255).  ``pack_epoch(order)`` fixes the epoch's row order; a feeder thread then assembles
+    slab after slab in a ring of pinned buffers (``scvae_pack_row_slab``: a gather of the rows'
+    strings, GIL released) ahead of the GPU, and ``fetch(slot, k)`` enqueues the copy of slab k.
+    For matrices beyond HBM, and the host-to-device leg of `bench.py`'s end-to-end number."""
 
     BLOCK = 255          # genes per block: a block's non-zero count fits one byte
+    RING = 4             # pinned slab buffers the feeder thread may run ahead by
 
-    def __init__(self, matrix, device, minibatch_size):
+    def __init__(self, matrix, device, minibatch_size, pack_threads=None):
         indptr, indices, data, shape = _as_csr_arrays(matrix)
-        if not (_counts_fit_u16(data) and shape[1] <= 65535):
-            raise ValueError("the packed stream carries integer counts <= 65504 of <= 65535 genes")
+        if not (_counts_fit_u16(data) and shape[1] <= 65280):
+            raise ValueError("the packed stream carries integer counts <= 65504 of <= 65280 genes")
+        import time
+        t0 = time.perf_counter()
         self.shape = shape
         self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
         self.B = int(minibatch_size)
-        self.indptr, self.indices = indptr, indices
-        self.values = data.astype(numpy.uint16)
-        self.value_bytes = 1 if (data.size == 0 or data.max() <= 255) else 2
+        if pack_threads is None:          # host threads of the slab gather, shared between the ranks of a node
+            import os
+            world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+            pack_threads = max(1, min(8, (os.cpu_count() or 8) // max(world, 1) - 1))
+        self.pack_threads = int(pack_threads)
         self.u16_ok = True
         self.f16_exact = bool(data.size == 0 or data.max() <= 2048)
-        self.nblk = -(-shape[1] // self.BLOCK)
+        n, G = shape
+        self.nblk = nblk = -(-G // self.BLOCK)
         from scipy.special import gammaln
         csum = numpy.concatenate([[0.0], numpy.cumsum(gammaln(1.0 + data.astype(numpy.float64)))])
-        self.row_const = (csum[indptr[1:]] - csum[indptr[:-1]]).astype(numpy.float32)
+        self.row_const = numpy.ascontiguousarray((csum[indptr[1:]] - csum[indptr[:-1]]).astype(numpy.float32))
+        # ---- encode every row once --------------------------------------------------------------
+        nnz = numpy.diff(indptr)
+        if nnz.size and nnz.max() > 65535:
+            raise ValueError("the packed stream carries at most 65535 non-zeros per row")
+        total = int(indices.size)
+        row_of = numpy.repeat(numpy.arange(n, dtype=numpy.int64), nnz)
+        pos_in_row = numpy.arange(total, dtype=numpy.int64) - numpy.repeat(indptr[:-1], nnz)
+        blk = indices // self.BLOCK
+        big = data >= 255
+        nesc = numpy.bincount(row_of[big], minlength=n).astype(numpy.int64)
+        lens = 2 + nblk + 2 * nnz + 4 * nesc
+        self.row_off = numpy.concatenate([[0], numpy.cumsum(lens)]).astype(numpy.int64)
+        store = numpy.zeros(int(self.row_off[-1]), dtype=numpy.uint8)
+        base = self.row_off[:-1]
+        store[base] = nesc & 255
+        store[base + 1] = nesc >> 8
+        blocks = numpy.bincount(row_of * nblk + blk, minlength=n * nblk)
+        store[(base[:, None] + 2 + numpy.arange(nblk)[None, :]).reshape(-1)] = blocks.astype(numpy.uint8)
+        ent = numpy.repeat(base + 2 + nblk, nnz) + 2 * pos_in_row
+        store[ent] = (indices - blk * self.BLOCK).astype(numpy.uint8)
+        store[ent + 1] = numpy.minimum(data, 255).astype(numpy.uint8)
+        if big.any():
+            rows_big = row_of[big]
+            first_big = numpy.concatenate([[0], numpy.cumsum(nesc)])[:-1]
+            k_in_row = numpy.arange(rows_big.size) - numpy.repeat(first_big, nesc)
+            esc = (base + 2 + nblk + 2 * nnz)[rows_big] + 4 * k_in_row
+            p, v = pos_in_row[big], data[big].astype(numpy.int64)
+            store[esc], store[esc + 1] = p & 255, p >> 8
+            store[esc + 2], store[esc + 3] = v & 255, v >> 8
+        self.store = store
+        self.bytes_per_nonzero = float(store.size) / max(total, 1)
+        self.encode_seconds = time.perf_counter() - t0
+        # the largest slab any B rows can make: the B longest strings
+        top = numpy.sort(lens)[::-1][:self.B]
+        self.max_slab_bytes = (K.packed_rows_offset(self.B) + int(top.sum()) + 15) & ~15
         self._copy_stream = None
-        self.slabs, self.buf, self.slots = [], None, None
+        self._ring = self._ring_np = None
+        self.slots = None
+        self.slabs = []
+        self._thread = None
+        self._cv = None
         self.pack_seconds = 0.0
 
     @property
@@ -178,76 +226,116 @@ class PackedStream:
     def number_of_examples(self):
         return self.shape[0]
 
-    def slab_layout(self, rows):
-        """(off_const, off_blocks, off_entries) of a slab of ``rows`` rows."""
-        off_const = 4 * (rows + 1)
-        off_blocks = off_const + 4 * rows
-        return off_const, off_blocks, off_blocks + rows * self.nblk
-
-    def pack_epoch(self, order=None):
-        """Lay out the rows ``order`` (default: data order) as slabs of ``B`` rows in pinned memory."""
-        import time
-        t0 = time.perf_counter()
-        n, B, eb = self.shape[0], self.B, 1 + self.value_bytes
-        order = numpy.arange(n) if order is None else numpy.asarray(order, dtype=numpy.int64)
-        starts, lens = self.indptr[order], numpy.diff(self.indptr)[order]
-        total = int(lens.sum())
-        first = numpy.concatenate([[0], numpy.cumsum(lens)])            # entry offsets in epoch order
-        src = numpy.repeat(starts - first[:-1], lens) + numpy.arange(total)
-        cols = self.indices[src]
-        blk = cols // self.BLOCK
-        ent = numpy.empty((total, eb), dtype=numpy.uint8)
-        ent[:, 0] = cols - blk * self.BLOCK
-        vals = self.values[src]
-        ent[:, 1] = vals & 255
-        if self.value_bytes == 2:
-            ent[:, 2] = vals >> 8
-        row_of = numpy.repeat(numpy.arange(order.size), lens)
-        blocks = numpy.bincount(row_of * self.nblk + blk, minlength=order.size * self.nblk).astype(
-            numpy.uint8).reshape(order.size, self.nblk)
-        # slab-major byte buffer
-        bounds = [(i, min(i + B, order.size)) for i in range(0, order.size, B)]
-        sizes = []
-        for i0, i1 in bounds:
-            rows = i1 - i0
-            sizes.append((self.slab_layout(rows)[2] + int(first[i1] - first[i0]) * eb + 15) & ~15)
-        offsets = numpy.concatenate([[0], numpy.cumsum(sizes)])
-        if self.buf is None or self.buf.numel() < int(offsets[-1]):
-            self.buf = torch.empty(int(offsets[-1]), dtype=torch.uint8)
-            if self.device.type == "cuda":
-                self.buf = self.buf.pin_memory()
-        host = self.buf.numpy()
-        self.slabs = []
-        for k, (i0, i1) in enumerate(bounds):
-            rows, o = i1 - i0, int(offsets[k])
-            oc, ob, oe = self.slab_layout(rows)
-            e0, e1 = int(first[i0]), int(first[i1])
-            host[o:o + 4 * (rows + 1)].view(numpy.int32)[:] = (first[i0:i1 + 1] - e0).astype(numpy.int32)
-            host[o + oc:o + oc + 4 * rows].view(numpy.float32)[:] = self.row_const[order[i0:i1]]
-            host[o + ob:o + oe] = blocks[i0:i1].reshape(-1)
-            host[o + oe:o + oe + (e1 - e0) * eb] = ent[e0:e1].reshape(-1)
-            self.slabs.append({"offset": o, "bytes": oe + (e1 - e0) * eb, "rows": rows})
-        need = (int(1.25 * max(sizes)) + 15) & ~15 if sizes else 16      # (slack: later epochs' orders differ)
-        if self.device.type == "cuda" and (self.slots is None or self.slots[0]["buf"].numel() < need):
+    def _buffers(self):
+        if self._ring is not None:
+            return
+        ring = [torch.empty(self.max_slab_bytes, dtype=torch.uint8) for _ in range(self.RING)]
+        if self.cuda:
+            ring = [r.pin_memory() for r in ring]
             self.slots = []
             for _ in range(2):
-                slot = {"packed": True, "buf": torch.empty(need, dtype=torch.uint8, device=self.device),
+                slot = {"packed": True,
+                        "buf": torch.empty(self.max_slab_bytes, dtype=torch.uint8, device=self.device),
                         "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "bytes": 0, "rows": 0,
-                        "value_bytes": self.value_bytes, "u16_ok": True, "f16_exact": self.f16_exact,
-                        "stream": self}
+                        "u16_ok": True, "f16_exact": self.f16_exact, "stream": self}
                 slot["free"].record()
                 self.slots.append(slot)
-        self.pack_seconds = time.perf_counter() - t0
+        self._ring, self._ring_np = ring, [r.numpy() for r in ring]
+
+    def pack_slab_host(self, k, dst=None):
+        """Assemble slab ``k`` of the current epoch (numpy uint8 view of its bytes)."""
+        slab = self.slabs[k]
+        if dst is None:
+            dst = numpy.empty(self.max_slab_bytes, dtype=numpy.uint8)
+        nbytes = K.pack_row_slab(self.store, self.row_off, self.row_const, slab["order"], dst,
+                                 threads=self.pack_threads)
+        slab["bytes"] = nbytes
+        return dst[:nbytes]
+
+    def pack_epoch(self, order=None):
+        """Fix the epoch's row order (default: data order) and start assembling its slabs of ``B``
+        rows ahead of the GPU.  Returns the number of slabs."""
+        import threading
+        self.close()
+        n, B = self.shape[0], self.B
+        order = numpy.arange(n, dtype=numpy.int64) if order is None else \
+            numpy.ascontiguousarray(order, dtype=numpy.int64)
+        self.slabs = [{"rows": min(B, order.size - i), "bytes": 0,
+                       "order": numpy.ascontiguousarray(order[i:i + B])}
+                      for i in range(0, order.size, B)]
+        self._buffers()
+        self._cv = threading.Condition()
+        self._packed_upto = 0                 # slabs [0, _packed_upto) sit in the ring
+        self._taken_upto = 0                  # slabs [0, _taken_upto) have had their copy enqueued
+        self._copied = [None] * self.RING     # event after the copy out of each ring buffer
+        self._stop = False
+        self._error = None
+        self.pack_seconds = 0.0
+        self._thread = threading.Thread(target=self._feed, daemon=True)
+        self._thread.start()
         return len(self.slabs)
 
+    def _feed(self):
+        import time
+        try:
+            for k in range(len(self.slabs)):
+                j = k % self.RING
+                with self._cv:
+                    while not self._stop and k - self._taken_upto >= self.RING:
+                        self._cv.wait()
+                    if self._stop:
+                        return
+                    done = self._copied[j]
+                if done is not None:
+                    done.synchronize()        # the previous slab in this buffer has left the host
+                t0 = time.perf_counter()
+                self.pack_slab_host(k, self._ring_np[j])
+                self.pack_seconds += time.perf_counter() - t0
+                with self._cv:
+                    self._packed_upto = k + 1
+                    self._cv.notify_all()
+        except BaseException as exc:          # surfaced by the next fetch
+            with self._cv:
+                self._error = exc
+                self._cv.notify_all()
+
+    def close(self):
+        """Stop the feeder thread of the current epoch (if any)."""
+        if self._thread is not None:
+            with self._cv:
+                self._stop = True
+                self._cv.notify_all()
+            self._thread.join()
+            self._thread = None
+
     def fetch(self, slot_id, k):
-        """Enqueue the host -> device copy of slab ``k`` into staging slot ``slot_id``."""
-        slab, slot = self.slabs[k], self.slots[slot_id]
+        """Enqueue the host -> device copy of slab ``k`` (slabs are taken in order) into staging
+        slot ``slot_id``."""
+        with self._cv:
+            if k != self._taken_upto:
+                raise ValueError("packed slabs are fetched in epoch order")
+            while self._packed_upto <= k and self._error is None:
+                self._cv.wait()
+            if self._error is not None:
+                raise self._error
+        slab, j = self.slabs[k], k % self.RING
+        if not self.cuda:
+            with self._cv:
+                self._taken_upto = k + 1
+                self._cv.notify_all()
+            return {"packed": True, "host": self._ring_np[j][:slab["bytes"]].copy(), "rows": slab["rows"],
+                    "bytes": slab["bytes"]}
+        slot = self.slots[slot_id]
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(slot["free"])
-            slot["buf"][:slab["bytes"]].copy_(self.buf[slab["offset"]:slab["offset"] + slab["bytes"]],
-                                              non_blocking=True)
+            slot["buf"][:slab["bytes"]].copy_(self._ring[j][:slab["bytes"]], non_blocking=True)
             slot["ready"].record(self.copy_stream)
+            done = torch.cuda.Event()
+            done.record(self.copy_stream)
+        with self._cv:
+            self._copied[j] = done
+            self._taken_upto = k + 1
+            self._cv.notify_all()
         slot["bytes"], slot["rows"] = slab["bytes"], slab["rows"]
         return slot
 
@@ -347,8 +435,7 @@ class TrainLoop:
                               u16_ok=src.u16_ok, f16_exact=src.f16_exact, train16=self.R == 1,
                               row_const_all=src.row_const)
         elif src.get("packed"):      # staging slot of a PackedStream: one slab = this minibatch
-            eng.set_batch_packed(p, src["buf"], src["stream"].slab_layout(self.B), src["value_bytes"],
-                                 f16_exact=src["f16_exact"])
+            eng.set_batch_packed(p, src["buf"], f16_exact=src["f16_exact"])
         else:  # staging slot of a StreamedCSR
             eng.set_batch_csr(p, src["indptr"], src["indices"], src["values"], None, rebase=True,
                               u16_ok=src["u16_ok"], f16_exact=src["f16_exact"],

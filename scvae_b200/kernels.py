@@ -86,15 +86,31 @@ def csr_densify(indptr, indices, values, rows, G, x, row_const=None, rebase=Fals
                "csr_densify")
 
 
-def csr_densify_packed(slab, off_const, off_blocks, off_entries, value_bytes, B, G, row_const=None,
-                       t16=None, x16=None):
-    """Packed row slab (uint8 device tensor, see include/scvae_b200.h) -> 16-bit minibatch."""
+def csr_densify_packed(slab, B, G, row_const=None, t16=None, x16=None):
+    """Minibatch from one packed row slab (layout: include/scvae_b200.h, hotloop.PackedStream)."""
     lib = _lib.load()
-    _lib.check(lib.scvae_csr_densify_packed(_p(slab), int(off_const), int(off_blocks), int(off_entries),
-                                            int(value_bytes), B, G, _p(row_const), _p(t16),
+    _lib.check(lib.scvae_csr_densify_packed(_p(slab), B, G, _p(row_const), _p(t16),
                                             _ld(t16) if t16 is not None else 0, _p(x16),
                                             _ld(x16) if x16 is not None else 0, _stream()),
                "csr_densify_packed")
+
+
+def packed_rows_offset(B):
+    return int(_lib.load().scvae_packed_rows_offset(int(B)))
+
+
+def pack_row_slab(store, row_off, row_const_all, order, dst, threads=4):
+    """HOST: assemble the packed slab of the rows ``order`` in ``dst`` (numpy uint8, e.g. a view of
+    pinned memory) from the per-row strings ``store`` / ``row_off``; returns the slab's bytes.
+    The call releases the GIL (ctypes), so a feeder thread packs ahead of the GPU."""
+    import ctypes
+    lib = _lib.load()
+    out = ctypes.c_int64(0)
+    _lib.check(lib.scvae_pack_row_slab(store.ctypes.data, row_off.ctypes.data, row_const_all.ctypes.data,
+                                       order.ctypes.data, int(order.size), int(row_off.size - 1),
+                                       dst.ctypes.data, int(dst.size), int(threads), ctypes.byref(out)),
+               "pack_row_slab")
+    return int(out.value)
 
 
 def csr_row_constants(indptr, values, out):

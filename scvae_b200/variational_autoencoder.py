@@ -351,9 +351,11 @@ class VariationalAutoencoder:
     # forward passes over a whole data set (per-epoch evaluation, evaluate())
     # ------------------------------------------------------------------------------------------
     def _evaluate_pass(self, engine, x_csr, t_csr, minibatch_size, R, S, deterministic=False,
-                       seed=0, on_batch=None):
+                       seed=0, on_batch=None, total_examples=None):
         """Forward-only pass in data order.  Aggregation follows the reference:
-        per-batch means are summed and divided by N / B."""
+        per-batch means are summed and divided by N / B.  ``total_examples``: the matrix is this
+        rank's shard of a data set of that many cells -- the per-batch sums are added over the
+        ranks before the division."""
         import torch
         from .hotloop import ResidentCSR
         from . import kernels as K
@@ -366,9 +368,9 @@ class VariationalAutoencoder:
             # host-resident matrix: the rows stream through in data order as packed slabs
             if on_batch is not None or (t_csr is not None and t_csr is not x_csr):
                 raise NotImplementedError("host-resident data feeds the lean evaluation passes only")
-            if packed.B != minibatch_size or not packed.slabs:
-                packed.B = int(minibatch_size)
-                packed.pack_epoch(None)
+            if packed.B != minibatch_size:
+                raise ValueError("the packed stream was built for minibatches of {} rows".format(packed.B))
+            packed.pack_epoch(None)          # (starts the feeder thread: slabs in data order)
         data = packed if packed is not None else (
             x_csr if isinstance(x_csr, ResidentCSR) else ResidentCSR(x_csr, dev))
         targets = None
@@ -387,8 +389,7 @@ class VariationalAutoencoder:
             if packed is not None:
                 slot = packed.fetch(b % 2, b)
                 torch.cuda.current_stream().wait_event(slot["ready"])
-                engine.set_batch_packed(plan, slot["buf"], packed.slab_layout(rows),
-                                        packed.value_bytes, f16_exact=packed.f16_exact)
+                engine.set_batch_packed(plan, slot["buf"], f16_exact=packed.f16_exact)
                 slot["free"].record(torch.cuda.current_stream())
             else:
                 engine.set_batch_csr(plan, data.indptr, data.indices, data.values, idx,
@@ -416,13 +417,18 @@ class VariationalAutoencoder:
             q_z_mean[i:i + rows].copy_(plan.PH[:rows, :L])
             if on_batch is not None:
                 on_batch(plan, i, rows)
-        log = log.cpu().numpy().astype(numpy.float64)
+        sums = log.sum(dim=0, dtype=torch.float64)
         divisor = n / minibatch_size
+        if total_examples is not None:
+            from . import distributed as D
+            D.all_reduce_sum_(sums)
+            divisor = total_examples / minibatch_size
+        sums = sums.cpu().numpy()
         return {
-            "lower_bound": log[:, 0].sum() / divisor,
-            "reconstruction_error": log[:, 2].sum() / divisor,
-            "kl_divergence": log[:, 3].sum() / divisor,
-            "kl_divergence_neurons": log[:, 4:].sum(axis=0) / divisor,
+            "lower_bound": sums[0] / divisor,
+            "reconstruction_error": sums[2] / divisor,
+            "kl_divergence": sums[3] / divisor,
+            "kl_divergence_neurons": sums[4:] / divisor,
             "q_z_mean": q_z_mean.cpu().numpy(),
         }
 
@@ -498,6 +504,10 @@ class VariationalAutoencoder:
         # data_residency="host": the count matrix stays in (pinned) host memory and every step's rows
         # travel as one packed slab (hotloop.PackedStream) -- for matrices beyond HBM
         host_resident = kwargs.get("data_residency", "device") == "host"
+        sharding = kwargs.get("data_sharding", "replicated")
+        if sharding not in ("replicated", "rank"):
+            raise ValueError("`data_sharding` is `replicated` or `rank`.")
+        rank_sharded = world > 1 and sharding == "rank" and not host_resident
         stream = eval_stream = None
         if host_resident:
             from .hotloop import PackedStream
@@ -509,6 +519,20 @@ class VariationalAutoencoder:
             stream = PackedStream(csr_train, engine.device, per_rank)
             eval_stream = PackedStream(csr_train, engine.device, minibatch_size)
             data = eval_stream
+        elif rank_sharded:
+            # data_sharding="rank" (SURVEY §8e): rank r keeps the cells r::W in HBM and nothing
+            # else; every step it takes its share of the minibatch from a shuffle of ITS cells
+            if self.type != "VAE" or t_train is not x_train or getattr(engine, "n_extra", 0) \
+                    or getattr(engine, "constrained", False):
+                raise NotImplementedError("rank-sharded training data: VAE on counts only (no "
+                                          "separate targets, batch correction or count-sum inputs)")
+            local = scipy.sparse.csr_matrix(x_train, dtype=numpy.float32)[rank::world]
+            data = ResidentCSR(local, engine.device)
+            n_local = local.shape[0]
+            if n_local < -(-n_train // minibatch_size):
+                raise ValueError("rank-sharded training data: fewer cells per rank than steps")
+            local_rng = numpy.random.RandomState(
+                (int(kwargs.get("shuffle_seed", 0)) + 1) * 7919 + rank)
         else:
             data = ResidentCSR(scipy.sparse.csr_matrix(x_train, dtype=numpy.float32), engine.device)
             self._attach_features(data, training_set)
@@ -605,9 +629,15 @@ class VariationalAutoencoder:
                     bound = loops[rows].step(slot, learning_rate, warm_up_weight)
                     slot["free"].record(compute)
                     step_bounds[s, :bound.numel()].copy_(bound)
+            if rank_sharded:
+                # a shuffle of this rank's own cells, cut into one share per global step
+                shuffled = torch.from_numpy(local_rng.permutation(n_local)).to(engine.device)
+                cuts = numpy.linspace(0, n_local, n_steps + 1).astype(numpy.int64)
             for s, i in enumerate(range(0, n_train, minibatch_size) if stream is None else []):
                 rows = min(minibatch_size, n_train - i)
-                if world > 1:   # this rank's slice of the global minibatch
+                if rank_sharded:
+                    i, rows = int(cuts[s]), int(cuts[s + 1] - cuts[s])
+                elif world > 1:   # this rank's slice of the global minibatch
                     i, hi = D.shard_bounds(i, rows, rank, world)
                     rows = hi - i
                     if rows == 0:
@@ -634,7 +664,9 @@ class VariationalAutoencoder:
             # evaluation passes with the *training* sample counts (VAE:1103-1106, 1262-1265)
             results = {"training": self._evaluate_pass(engine, data, getattr(data, "targets", None),
                                                        minibatch_size, R, S,
-                                                       seed=noise_seed + 1000 + epoch)}
+                                                       seed=noise_seed + 1000 + epoch,
+                                                       **({"total_examples": n_train}
+                                                          if rank_sharded else {}))}
             if validation_set:
                 results["validation"] = self._evaluate_pass(
                     engine, valid_data, valid_data.targets,

@@ -138,3 +138,57 @@ def test_two_engine_replicas_match_the_global_minibatch_step():
     for worst, drift in results.values():
         assert worst < 2e-5          # fp32 engine state against the fp64 whole-minibatch step
         assert drift == 0.0          # replicas bit-identical after the exchange
+
+
+def _sharded_train_worker(rank, world, port, results, tmp):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import scipy.sparse
+    import shell_cpu_patch
+    shell_cpu_patch.apply()
+    from oracle import scvae_oracle as O
+    from scvae_b200 import distributed as D
+    from scvae_b200 import hotloop as H
+    from scvae_b200.data_set import DataSet
+    from scvae_b200.variational_autoencoder import VariationalAutoencoder
+    torch.set_num_threads(1)
+    D.initialise_from_environment(backend="gloo")
+    x, labels = O.synthetic_counts(90, 24, n_types=3, seed=3, target_zero_fraction=0.7)
+    ds = DataSet("toy", values=scipy.sparse.csr_matrix(numpy.minimum(x, 30.0)), labels=labels.astype(str))
+    uploaded = []
+    original = H.ResidentCSR.__init__
+
+    def spy(self, matrix, device):
+        original(self, matrix, device)
+        uploaded.append(self.shape[0])
+    H.ResidentCSR.__init__ = spy
+    model = VariationalAutoencoder(feature_size=24, latent_size=3, hidden_sizes=[8],
+                                   reconstruction_distribution="poisson",
+                                   log_directory=os.path.join(tmp, "rank{}".format(rank)), seed=2)
+    model.train(ds, number_of_epochs=2, minibatch_size=30, learning_rate=1e-2, shuffle_seed=4,
+                data_sharding="rank")
+    eng = model._get_engine()
+    flat = eng.store.param.clone()
+    D.all_reduce_sum_(flat)
+    from scvae_b200 import model_utilities as MU
+    curve = MU.load_learning_curves(model, "training")["lower_bound"] if rank == 0 else [0.0, 0.0]
+    results[rank] = (uploaded[0], (flat / world - eng.store.param).abs().max().item(),
+                     [float(v) for v in curve])
+    dist.destroy_process_group()
+
+
+def test_rank_sharded_resident_training_data(tmp_path):
+    """train(..., data_sharding="rank") on two gloo ranks: each rank uploads only its cells r::W,
+    the replicas stay identical, and the logged training ELBO is the all-rank aggregate."""
+    port = 33500 + (os.getpid() % 2000)
+    manager = mp.Manager()
+    results = manager.dict()
+    mp.spawn(_sharded_train_worker, args=(2, port, results, str(tmp_path)), nprocs=2, join=True)
+    assert len(results) == 2
+    assert results[0][0] == 45 and results[1][0] == 45         # half of the 90 cells each
+    for _, drift, _ in results.values():
+        assert drift == 0.0
+    curve = results[0][2]
+    assert len(curve) == 2 and all(numpy.isfinite(curve))

@@ -9,7 +9,8 @@ from oracle import scvae_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-KINDS = [k for k in O.LIKELIHOODS if k != "constrained poisson"]   # (own row kernel, own test)
+KINDS = [k for k in O.LIKELIHOODS if k != "constrained poisson"      # (own row kernel, own test)
+         and k not in getattr(O, "CONTINUOUS", ())]                 # (csrc/continuous.cu, own tests)
 
 
 def _dev():
@@ -738,7 +739,11 @@ def test_piecewise_categorical_likelihood(kind, k_max):
 
 
 @pytest.mark.parametrize("layout,which,M,N,Kd", [(0, 2, 512, 100, 5000), (2, 1, 100, 5004, 1024),
-                                                  (0, 2, 4096, 100, 20001), (2, 1, 100, 20004, 4096)])
+                                                  (0, 2, 4096, 100, 20001), (2, 1, 100, 20004, 4096),
+                                                  # pair mode of the forward: odd tile count (the last
+                                                  # pair is half empty), ragged rows, one tile (no pair)
+                                                  (0, 2, 384, 100, 3000), (0, 2, 300, 36, 700),
+                                                  (0, 2, 100, 100, 20001), (0, 2, 1280, 127, 1000)])
 def test_gemm_f16_split_operand(layout, which, M, N, Kd):
     """One fp32 operand as fp16 + its fp16 rounding remainder (scvae_gemm_f16_split): the product
     carries ~22 bits of that operand -- first encoder layer (weights split, NT) and its weight
@@ -853,7 +858,8 @@ def test_continuous_likelihood_fwd_bwd_and_moments(kind, M, G, tile):
 @pytest.mark.parametrize("cap,direct", [(200.0, True), (3000.0, False), (60000.0, False)])
 def test_csr_densify_packed_matches_csr_densify(cap, direct):
     """The streamed wire format (packed row slabs, scvae_csr_densify_packed) against the CSR form:
-    identical 16-bit minibatch and per-cell constants, one- and two-byte counts, a ragged last slab."""
+    identical 16-bit minibatch and per-cell constants, counts with and without escapes (>= 255), a
+    ragged last slab, slabs assembled by the feeder thread (scvae_pack_row_slab)."""
     import scipy.sparse
     from scvae_b200 import kernels as K
     from scvae_b200.hotloop import PackedStream
@@ -864,7 +870,7 @@ def test_csr_densify_packed_matches_csr_densify(cap, direct):
     csr = scipy.sparse.csr_matrix(dense)
     dev = _dev()
     stream = PackedStream(csr, dev, B)
-    assert stream.value_bytes == (1 if cap <= 255 else 2)
+    assert 2.0 < stream.bytes_per_nonzero < 3.2
     order = rng.permutation(N)
     stream.pack_epoch(order)
     indptr = torch.tensor(csr.indptr.astype(numpy.int64)).to(dev)
@@ -878,8 +884,7 @@ def test_csr_densify_packed_matches_csr_densify(cap, direct):
         x16 = torch.full((rows, ld16), 3.0, dtype=torch.float16, device=dev)
         t16 = None if direct else torch.full((rows, (G + 7) & ~7), 7, dtype=torch.int16, device=dev)
         rc = torch.zeros(rows, device=dev)
-        K.csr_densify_packed(slot["buf"], *stream.slab_layout(rows), stream.value_bytes, rows, G,
-                             row_const=rc, t16=t16, x16=x16)
+        K.csr_densify_packed(slot["buf"], rows, G, row_const=rc, t16=t16, x16=x16)
         slot["free"].record()
         idx = torch.tensor(order[k * B:k * B + rows].astype(numpy.int64)).to(dev)
         x16_ref = torch.full((rows, ld16), 5.0, dtype=torch.float16, device=dev)

@@ -349,8 +349,13 @@ def test_evaluate_streams_the_reconstruction_to_the_host(tmp_path, dtype):
     out = O.vae_forward(cfg, params, x, x, torch.zeros(1, 210, 3, dtype=torch.float64),
                         is_training=False, use_deterministic_z=True, moments=True)
     want = out["p_x_mean"].numpy()
-    tol = 2e-3 if dtype == "float16" else 2e-4
-    assert numpy.abs(values.astype(numpy.float64) - want).max() <= tol * max(1.0, numpy.abs(want).max())
+    if dtype == "float16":
+        # (fp16 carries 11 bits and saturates beyond 65504: an untrained NB head can exceed that)
+        ok = want < 6e4
+        assert ok.mean() > 0.99
+        assert (numpy.abs(values.astype(numpy.float64) - want)[ok] <= 2e-3 * numpy.maximum(want[ok], 1.0)).all()
+    else:
+        assert numpy.abs(values.astype(numpy.float64) - want).max() <= 2e-4 * max(1.0, numpy.abs(want).max())
     total = reconstructed.total_standard_deviations
     for i in subset:
         got = total[i].toarray().reshape(-1)

@@ -167,6 +167,7 @@ def test_train_loop_step_at_baseline_shape(case, source):
         stream = PackedStream(csr, dev, B)
         order = rng.permutation(N)
         stream.pack_epoch(order)
+        stream.fetch(0, 0)                              # (slabs are taken in epoch order)
         src = stream.fetch(1, 1)                        # the second slab of the epoch
         torch.cuda.current_stream().wait_event(src["ready"])
         rows_host = order[B:2 * B]

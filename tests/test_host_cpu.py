@@ -61,42 +61,57 @@ def test_option_validation_mirrors_the_scope():
 
 
 def test_packed_stream_slabs_decode_to_the_rows_of_the_matrix():
-    """Host logic of the streamed wire format (scvae_csr_densify_packed): every slab of an epoch,
-    decoded with numpy exactly as the kernel reads it, reproduces its rows in epoch order."""
+    """Host logic of the streamed wire format (scvae_csr_densify_packed / scvae_pack_row_slab):
+    every slab of an epoch -- assembled by the native host packer from the per-row strings, through
+    the feeder thread -- decoded with numpy exactly as the kernel reads it, reproduces its rows in
+    epoch order, escapes (counts >= 255) included."""
     import numpy
     import scipy.sparse
+    from scvae_b200 import kernels as K
     from scvae_b200.hotloop import PackedStream
     rng = numpy.random.RandomState(0)
     n, G, B = 37, 700, 8
     dense = ((rng.rand(n, G) < 0.1) * rng.randint(1, 400, size=(n, G))).astype(numpy.float32)
     dense[3] = 0                      # an empty row
     dense[5, :] = 7                   # a full row: every block holds 255 entries
-    stream = PackedStream(scipy.sparse.csr_matrix(dense), "cpu", B)
-    assert stream.value_bytes == 2 and stream.nblk == 3
+    dense[6, :] = 300                 # every entry an escape
+    stream = PackedStream(scipy.sparse.csr_matrix(dense), "cpu", B, pack_threads=3)
+    assert stream.nblk == 3
     order = rng.permutation(n)
     assert stream.pack_epoch(order) == 5
-    host = stream.buf.numpy()
-    eb = 1 + stream.value_bytes
+    nblk = stream.nblk
     seen = 0
-    for k, slab in enumerate(stream.slabs):
-        rows = slab["rows"]
-        oc, ob, oe = stream.slab_layout(rows)
-        base = host[slab["offset"]:slab["offset"] + slab["bytes"]]
-        rowptr = base[:4 * (rows + 1)].view(numpy.int32)
-        consts = base[oc:oc + 4 * rows].view(numpy.float32)
-        blocks = base[ob:oe].reshape(rows, stream.nblk)
-        ent = base[oe:].reshape(-1, eb)
+    for k in range(5):
+        slot = stream.fetch(k % 2, k)
+        rows, host = slot["rows"], slot["host"]
+        assert rows == min(B, n - k * B) and host.size == slot["bytes"]
+        off = host[:4 * (rows + 1)].view(numpy.int32)
+        consts = host[4 * (rows + 1):4 * (rows + 1) + 4 * rows].view(numpy.float32)
+        strings = host[K.packed_rows_offset(rows):]
         for r in range(rows):
+            s = strings[off[r]:off[r + 1]].astype(numpy.int64)
+            nesc = s[0] | (s[1] << 8)
+            blocks = s[2:2 + nblk]
+            nnz = (s.size - 2 - nblk - 4 * nesc) // 2
+            assert blocks.sum() == nnz
+            e = s[2 + nblk:2 + nblk + 2 * nnz].reshape(nnz, 2)
+            esc = s[2 + nblk + 2 * nnz:].reshape(nesc, 4)
+            values = e[:, 1].copy()
+            lookup = {int(a | (b << 8)): int(c | (d << 8)) for a, b, c, d in esc}
+            for i in numpy.nonzero(values == 255)[0]:
+                values[i] = lookup[int(i)]
             out = numpy.zeros(G, numpy.float32)
-            e = ent[rowptr[r]:rowptr[r + 1]]
-            assert blocks[r].sum() == len(e)
-            blk = numpy.repeat(numpy.arange(stream.nblk), blocks[r])
-            out[blk * 255 + e[:, 0]] = e[:, 1].astype(numpy.int32) | (e[:, 2].astype(numpy.int32) << 8)
+            out[numpy.repeat(numpy.arange(nblk), blocks) * 255 + e[:, 0]] = values
             want = dense[order[k * B + r]]
             assert numpy.array_equal(out, want)
-            assert abs(consts[r] - stream.row_const[order[k * B + r]]) == 0
+            assert consts[r] == stream.row_const[order[k * B + r]]
             seen += 1
     assert seen == n
-    # 2 bytes per non-zero when the counts fit one byte
+    stream.close()
+    stream.pack_epoch(order)
+    with pytest.raises(ValueError):                      # slabs leave in epoch order
+        stream.fetch(0, 1)
+    stream.close()
+    # ~2 bytes per non-zero when the counts fit one byte
     small = PackedStream(scipy.sparse.csr_matrix(numpy.minimum(dense, 200.0)), "cpu", B)
-    assert small.value_bytes == 1
+    assert small.bytes_per_nonzero < 2.0 + (2 + nblk) * n / (dense > 0).sum() + 1e-9
