@@ -705,13 +705,15 @@ def run_b200(args):
         e2e = {"value": args.steps * B * world / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": 16,
                "path": "hotloop.PackedStream (the feeder of train(..., data_residency='host')): the "
-                       "matrix stays in host memory as per-row strings; every step a feeder thread "
-                       "gathers the shuffled minibatch's strings into a pinned slab "
-                       "(scvae_pack_row_slab, inside the timed region) -> ONE H2D per step (copy "
-                       "stream, double-buffered) -> scvae_csr_densify_packed -> train step -> D2H of "
-                       "the bound (async to pinned memory, read by the host one step later)",
-               "bytes_per_nonzero": round(stream.bytes_per_nonzero, 3),
+                       "matrix stays in host memory as per-row strings (encoded once per data set); "
+                       "every step a feeder thread gathers the shuffled minibatch's strings into a "
+                       "pinned slab (scvae_pack_row_slab, {} host threads, INSIDE the timed region) "
+                       "-> ONE H2D per step (copy stream, double-buffered) -> "
+                       "scvae_csr_densify_packed -> train step -> D2H of the bound (async to pinned "
+                       "memory, read one step later)".format(stream.pack_threads),
+               "feeder": stream.feeder,
                "host_pack_ms_per_step": round(1e3 * stream.pack_seconds / max(need, 1), 3),
+               "bytes_per_nonzero": round(stream.bytes_per_nonzero, 3),
                "encode_once_seconds": round(stream.encode_seconds, 2),
                "encode_note": "the per-row strings are encoded once per data set (numpy), outside "
                               "the timed steps; the per-step gather, shuffle included, is inside"}

@@ -97,7 +97,8 @@ int scvae_csr_densify_u16(const int64_t *indptr, const void *indices_u16, const 
  * copy per step, ~2 bytes per non-zero:
  *   int32 row_offset[B + 1] | float row_const[B] | (pad: strings start at
  *   scvae_packed_rows_offset(B)) | row strings, a row string (little endian, byte aligned) being
- *   u16 nesc | u8 blocks[ceil(G / 255)] | (u8 index in block, u8 count)[nnz] | (u16 entry, u16 count)[nesc]
+ *   u16 nesc | u16 nnz | u8 blocks[ceil(G / 255)] | (u8 index in block, u8 count)[nnz] |
+ *   (u16 entry, u16 count)[nesc] | pad to a multiple of 16 bytes
  * blocks[k] = non-zeros of the row among the genes [255 k, 255 k + 255); a count byte of 255 is an
  * escape whose value is the escape-list entry with that entry position.  G <= 65280.
  * Outputs as the 16-bit outputs of scvae_csr_densify; row_const (nullable) receives the slab's copy.
@@ -107,6 +108,18 @@ int scvae_csr_densify_u16(const int64_t *indptr, const void *indices_u16, const 
 int64_t scvae_packed_rows_offset(int B);
 int scvae_csr_densify_packed(const void *slab, int B, int G, float *row_const, void *t16,
                              int64_t ldt16, void *x16, int64_t ldx16, void *stream);
+/* The same assembly done by the GPU: `store` is PINNED HOST memory (read over PCIe through its
+ * unified address), row_off / row_const_all / order are device arrays; two small kernels write
+ * the slab into device memory.  No host work per step. */
+int scvae_packed_pull(const void *store, const int64_t *row_off, const float *row_const_all,
+                      const int64_t *order, int B, void *slab, int64_t slab_capacity, void *stream);
+/* The same assembly done by the copy engine: the header goes through `header` (pinned, reusable
+ * once the batch has executed), then ONE cudaMemcpyBatchAsync moves header + row strings from the
+ * pinned store to the device slab.  Returns 2 when the runtime has no batched copies. */
+int scvae_packed_copy_batch(const uint8_t *store, const int64_t *row_off, const float *row_const_all,
+                            const int64_t *order, int rows, int64_t n_rows, uint8_t *header,
+                            uint8_t *slab_dev, int64_t slab_capacity, int device, void *stream,
+                            int64_t *bytes_out);
 int scvae_pack_row_slab(const uint8_t *store, const int64_t *row_off, const float *row_const_all,
                         const int64_t *order, int rows, int64_t n_rows, uint8_t *dst,
                         int64_t dst_capacity, int threads, int64_t *bytes_out);

@@ -77,6 +77,9 @@ SIGNATURES = {
                                       c_int, c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
     "scvae_packed_rows_offset": (c_i64, [c_int]),
     "scvae_csr_densify_packed": (c_int, [c_ptr, c_int, c_int, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
+    "scvae_packed_pull": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
+    "scvae_packed_copy_batch": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr, c_ptr, c_i64, c_int,
+                                        c_ptr, c_ptr]),
     "scvae_pack_row_slab": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr, c_i64, c_int, c_ptr]),
     "scvae_f32_to_u16": (c_int, [c_ptr, c_i64, c_i64, c_int, c_ptr, c_i64, c_ptr]),
     "scvae_csr_row_constants": (c_int, [c_ptr, c_ptr, c_int, c_i64, c_ptr, c_ptr]),

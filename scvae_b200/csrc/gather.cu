@@ -224,10 +224,10 @@ static int launch_densify(const int64_t *indptr, const IdxT *indices, const ValT
 
 // ---- packed row slabs (hotloop.PackedStream) -----------------------------------------------------
 // slab = int32 row_offset[B + 1] | float row_const[B] | (pad to 16) | row strings; a row string is
-//   u16 nesc | u8 blocks[nblk] | (u8 index in block, u8 count)[nnz] | (u16 entry, u16 count)[nesc]
-// (little endian, byte aligned): blocks[k] = non-zeros of the row among the genes [255 k, 255 k + 255)
-// (so a count fits one byte), a count byte of 255 is an escape whose value is looked up by entry
-// position in the row's (sorted) escape list.  ~2 bytes per non-zero.
+//   u16 nesc | u16 nnz | u8 blocks[nblk] | (u8 index in block, u8 count)[nnz] | (u16 entry, u16 count)[nesc]
+// (little endian), padded to a multiple of 16 bytes: blocks[k] = non-zeros of the row among the genes
+// [255 k, 255 k + 255) (so a count fits one byte), a count byte of 255 is an escape whose value is
+// looked up by entry position in the row's (sorted) escape list.  ~2 bytes per non-zero.
 // One CTA per row: block counts -> prefix sums in shared memory; every entry finds its block by
 // binary search of its position in the row; the row is assembled in shared memory as for the CSR
 // form and written as fp16 (x16, augmented) and / or uint16 (t16).
@@ -244,11 +244,10 @@ csr_densify_packed_kernel(const uint8_t *__restrict__ slab, int B, int G, int nb
     const int b = blockIdx.x;
     const int32_t *ro = reinterpret_cast<const int32_t *>(slab);
     const uint8_t *str = slab + packed_rows_offset(B) + ro[b];
-    const int len = ro[b + 1] - ro[b];
     const int nesc = (int)str[0] | ((int)str[1] << 8);
-    const uint8_t *blocks = str + 2;
+    const int nnz = (int)str[2] | ((int)str[3] << 8);
+    const uint8_t *blocks = str + 4;
     const uint8_t *entries = blocks + nblk;
-    const int nnz = (len - 2 - nblk - 4 * nesc) >> 1;
     const uint8_t *esc = entries + 2 * nnz;
     uint4 *row4 = reinterpret_cast<uint4 *>(row16);
     for (int i = threadIdx.x; i < width8; i += blockDim.x) row4[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -329,6 +328,67 @@ csr_densify_packed_kernel(const uint8_t *__restrict__ slab, int B, int G, int nb
             *reinterpret_cast<uint4 *>(x16 + (int64_t)b * ldx16 + c) = make_uint4(o[0], o[1], o[2], o[3]);
         }
     }
+}
+
+// ---- device-side assembly of a packed slab: the GPU pulls the minibatch's row strings itself -------
+// store: all row strings (16-byte aligned, 16-byte multiples) in PINNED HOST memory, read over PCIe
+// through its unified address; row_off / row_const_all / order live in device memory.  Kernel 1 (one
+// CTA) turns the B string lengths into the slab's offset table, kernel 2 (one CTA per row) copies the
+// strings with 128-bit loads.  No host work per step beyond the two launches.
+__global__ void __launch_bounds__(1024)
+packed_offsets_kernel(const int64_t *__restrict__ row_off, const float *__restrict__ row_const_all,
+                      const int64_t *__restrict__ order, int B, uint8_t *__restrict__ slab) {
+    __shared__ int warp_sum_s[32];
+    __shared__ int carry_s;
+    int32_t *ro = reinterpret_cast<int32_t *>(slab);
+    float *rc = reinterpret_cast<float *>(slab + 4 * (int64_t)(B + 1));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int r0 = 0; r0 < B; r0 += 1024) {
+        const int r = r0 + threadIdx.x;
+        int len = 0;
+        if (r < B) {
+            const int64_t i = order[r];
+            len = (int)(row_off[i + 1] - row_off[i]);
+            rc[r] = row_const_all[i];
+        }
+        int v = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += n;
+        }
+        if (lane == 31) warp_sum_s[warp] = v;
+        __syncthreads();
+        int base = carry_s;
+        for (int w = 0; w < warp; ++w) base += warp_sum_s[w];
+        if (r < B) ro[r] = base + v - len;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = base + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ro[B] = carry_s;
+}
+
+__global__ void __launch_bounds__(128)
+packed_pull_kernel(const uint8_t *__restrict__ store, const int64_t *__restrict__ row_off,
+                   const int64_t *__restrict__ order, int B, uint8_t *__restrict__ slab, int64_t capacity) {
+    const int b = blockIdx.x;
+    const int32_t *ro = reinterpret_cast<const int32_t *>(slab);
+    const int64_t i = order[b];
+    const int64_t base = packed_rows_offset(B);
+    const int n16 = (int)((row_off[i + 1] - row_off[i]) >> 4);
+    if (base + ro[b] + ((int64_t)n16 << 4) > capacity) return;     // (never: the buffer holds the worst case)
+    const uint4 *src = reinterpret_cast<const uint4 *>(store + row_off[i]);
+    uint4 *dst = reinterpret_cast<uint4 *>(slab + base + ro[b]);
+    // several 128-bit loads per thread in flight: the latency is a PCIe round trip
+    int k = threadIdx.x;
+    for (; k + 3 * 128 < n16; k += 4 * 128) {
+        const uint4 v0 = src[k], v1 = src[k + 128], v2 = src[k + 256], v3 = src[k + 384];
+        dst[k] = v0; dst[k + 128] = v1; dst[k + 256] = v2; dst[k + 384] = v3;
+    }
+    for (; k < n16; k += 128) dst[k] = src[k];
 }
 
 // sum_g lgamma(1 + x) of every CSR row (one warp per row): a per-cell constant of the data set,
@@ -429,6 +489,21 @@ extern "C" int scvae_csr_densify_packed(const void *slab, int B, int G, float *r
     else PACKED(false);
 #undef PACKED
     SCVAE_CHECK_LAUNCH("csr_densify_packed");
+    return 0;
+}
+
+extern "C" int scvae_packed_pull(const void *store, const int64_t *row_off, const float *row_const_all,
+                                 const int64_t *order, int B, void *slab, int64_t slab_capacity, void *stream) {
+    using namespace scvae;
+    SCVAE_CHECK_ARG(store && row_off && row_const_all && order && slab && B >= 0, "packed_pull: bad arguments");
+    SCVAE_CHECK_ARG(aligned16(store) && aligned16(slab) && slab_capacity >= packed_rows_offset(B),
+                    "packed_pull: store and slab must be 16-byte aligned, the slab large enough");
+    if (B == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    packed_offsets_kernel<<<1, 1024, 0, s>>>(row_off, row_const_all, order, B, (uint8_t *)slab);
+    SCVAE_CHECK_LAUNCH("packed_offsets");
+    packed_pull_kernel<<<B, 128, 0, s>>>((const uint8_t *)store, row_off, order, B, (uint8_t *)slab, slab_capacity);
+    SCVAE_CHECK_LAUNCH("packed_pull");
     return 0;
 }
 

@@ -151,7 +151,7 @@ class PackedStream:
     BLOCK = 255          # genes per block: a block's non-zero count fits one byte
     RING = 4             # pinned slab buffers the feeder thread may run ahead by
 
-    def __init__(self, matrix, device, minibatch_size, pack_threads=None):
+    def __init__(self, matrix, device, minibatch_size, pack_threads=None, feeder=None):
         indptr, indices, data, shape = _as_csr_arrays(matrix)
         if not (_counts_fit_u16(data) and shape[1] <= 65280):
             raise ValueError("the packed stream carries integer counts <= 65504 of <= 65280 genes")
@@ -160,11 +160,12 @@ class PackedStream:
         self.shape = shape
         self.device = torch.device(device)
         self.cuda = self.device.type == "cuda"
+        self._copy_stream = None
         self.B = int(minibatch_size)
         if pack_threads is None:          # host threads of the slab gather, shared between the ranks of a node
             import os
             world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
-            pack_threads = max(1, min(8, (os.cpu_count() or 8) // max(world, 1) - 1))
+            pack_threads = max(1, min(8, (os.cpu_count() or 8) // max(world, 1)))
         self.pack_threads = int(pack_threads)
         self.u16_ok = True
         self.f16_exact = bool(data.size == 0 or data.max() <= 2048)
@@ -183,38 +184,81 @@ class PackedStream:
         blk = indices // self.BLOCK
         big = data >= 255
         nesc = numpy.bincount(row_of[big], minlength=n).astype(numpy.int64)
-        lens = 2 + nblk + 2 * nnz + 4 * nesc
+        lens = (4 + nblk + 2 * nnz + 4 * nesc + 15) & ~15        # strings are 16-byte multiples
         self.row_off = numpy.concatenate([[0], numpy.cumsum(lens)]).astype(numpy.int64)
-        store = numpy.zeros(int(self.row_off[-1]), dtype=numpy.uint8)
+        store = self._host_bytes(int(self.row_off[-1]))
         base = self.row_off[:-1]
-        store[base] = nesc & 255
-        store[base + 1] = nesc >> 8
+        store[base], store[base + 1] = nesc & 255, nesc >> 8
+        store[base + 2], store[base + 3] = nnz & 255, nnz >> 8
         blocks = numpy.bincount(row_of * nblk + blk, minlength=n * nblk)
-        store[(base[:, None] + 2 + numpy.arange(nblk)[None, :]).reshape(-1)] = blocks.astype(numpy.uint8)
-        ent = numpy.repeat(base + 2 + nblk, nnz) + 2 * pos_in_row
+        store[(base[:, None] + 4 + numpy.arange(nblk)[None, :]).reshape(-1)] = blocks.astype(numpy.uint8)
+        ent = numpy.repeat(base + 4 + nblk, nnz) + 2 * pos_in_row
         store[ent] = (indices - blk * self.BLOCK).astype(numpy.uint8)
         store[ent + 1] = numpy.minimum(data, 255).astype(numpy.uint8)
         if big.any():
             rows_big = row_of[big]
             first_big = numpy.concatenate([[0], numpy.cumsum(nesc)])[:-1]
             k_in_row = numpy.arange(rows_big.size) - numpy.repeat(first_big, nesc)
-            esc = (base + 2 + nblk + 2 * nnz)[rows_big] + 4 * k_in_row
+            esc = (base + 4 + nblk + 2 * nnz)[rows_big] + 4 * k_in_row
             p, v = pos_in_row[big], data[big].astype(numpy.int64)
             store[esc], store[esc + 1] = p & 255, p >> 8
             store[esc + 2], store[esc + 3] = v & 255, v >> 8
         self.store = store
+        self.lens = lens
         self.bytes_per_nonzero = float(store.size) / max(total, 1)
+        # feeder "host" (default): a thread gathers each minibatch's strings into a pinned slab
+        # (scvae_pack_row_slab) that ONE copy ships; "device": the strings sit in pinned memory and
+        # the GPU pulls the rows itself (scvae_packed_pull) -- no host work per step, but SM-issued
+        # reads over PCIe reached only ~15 GB/s on the B200 box against ~50 GB/s for the copy engine
+        # "batch": the strings sit in pinned memory and ONE batched copy (cudaMemcpyBatchAsync: the
+        # copy engine walks the B row strings) moves them into the device slab -- measured 1.5 ms
+        # of driver time per 4096-row batch, so the host gather stays the default
+        self.feeder = feeder or "host"
+        if self.feeder not in ("device", "host", "batch") or (self.feeder != "host" and not self.cuda):
+            raise ValueError("feeder: `batch` / `device` (CUDA only) or `host`")
+        if self.feeder in ("device", "batch"):
+            self.store_pinned = torch.from_numpy(store).pin_memory()
+            self.store = self.store_pinned.numpy()
+        if self.feeder == "device":
+            self.row_off_dev = torch.from_numpy(self.row_off).to(self.device)
+            self.row_const_dev = torch.from_numpy(self.row_const).to(self.device)
+        if self.feeder == "batch":
+            hb = K.packed_rows_offset(self.B)
+            self._headers = [torch.empty(hb, dtype=torch.uint8).pin_memory() for _ in range(self.RING)]
+            self._headers_np = [h.numpy() for h in self._headers]
+            self._header_done = [None] * self.RING
+            probe = torch.empty(K.packed_rows_offset(1) + int(lens.max() if n else 16) + 16,
+                                dtype=torch.uint8, device=self.device)
+            with torch.cuda.stream(self.copy_stream):
+                if n == 0 or K.packed_copy_batch(self.store, self.row_off, self.row_const,
+                                                 numpy.zeros(1, dtype=numpy.int64), self._headers_np[0],
+                                                 probe) is None:
+                    self.feeder = "host"          # no batched copies in this runtime
+            torch.cuda.synchronize(self.device)
         self.encode_seconds = time.perf_counter() - t0
         # the largest slab any B rows can make: the B longest strings
         top = numpy.sort(lens)[::-1][:self.B]
         self.max_slab_bytes = (K.packed_rows_offset(self.B) + int(top.sum()) + 15) & ~15
-        self._copy_stream = None
         self._ring = self._ring_np = None
         self.slots = None
         self.slabs = []
         self._thread = None
         self._cv = None
         self.pack_seconds = 0.0
+
+    def _host_bytes(self, size):
+        """Zeroed host bytes for the row strings, in transparent huge pages when the kernel grants
+        them (the per-step gather reads ~3 KB strings at random: 4 KB pages mean a TLB miss each)."""
+        import mmap
+        if size >= (8 << 20) and hasattr(mmap, "MADV_HUGEPAGE"):
+            try:
+                mem = mmap.mmap(-1, (size + (2 << 20) - 1) & ~((2 << 20) - 1))
+                mem.madvise(mmap.MADV_HUGEPAGE)
+                self._store_mmap = mem
+                return numpy.frombuffer(mem, dtype=numpy.uint8, count=size)
+            except (OSError, ValueError):
+                pass
+        return numpy.zeros(size, dtype=numpy.uint8)
 
     @property
     def copy_stream(self):
@@ -229,7 +273,8 @@ class PackedStream:
     def _buffers(self):
         if self._ring is not None:
             return
-        ring = [torch.empty(self.max_slab_bytes, dtype=torch.uint8) for _ in range(self.RING)]
+        ring = [] if self.feeder in ("device", "batch") else [
+            torch.empty(self.max_slab_bytes, dtype=torch.uint8) for _ in range(self.RING)]
         if self.cuda:
             ring = [r.pin_memory() for r in ring]
             self.slots = []
@@ -264,6 +309,11 @@ class PackedStream:
                        "order": numpy.ascontiguousarray(order[i:i + B])}
                       for i in range(0, order.size, B)]
         self._buffers()
+        if self.feeder == "device":
+            self.order_dev = torch.from_numpy(order).to(self.device)      # the epoch's row order
+        if self.feeder in ("device", "batch"):
+            self._taken_upto = 0
+            return len(self.slabs)
         self._cv = threading.Condition()
         self._packed_upto = 0                 # slabs [0, _packed_upto) sit in the ring
         self._taken_upto = 0                  # slabs [0, _taken_upto) have had their copy enqueued
@@ -311,6 +361,29 @@ class PackedStream:
     def fetch(self, slot_id, k):
         """Enqueue the host -> device copy of slab ``k`` (slabs are taken in order) into staging
         slot ``slot_id``."""
+        if self.feeder in ("device", "batch"):
+            if k != self._taken_upto:
+                raise ValueError("packed slabs are fetched in epoch order")
+            self._taken_upto = k + 1
+            slab, slot = self.slabs[k], self.slots[slot_id]
+            rows = slab["rows"]
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(slot["free"])
+                if self.feeder == "device":
+                    K.packed_pull(self.store_pinned, self.row_off_dev, self.row_const_dev,
+                                  self.order_dev[k * self.B:k * self.B + rows], slot["buf"])
+                    slab["bytes"] = K.packed_rows_offset(rows) + int(self.lens[slab["order"]].sum())
+                else:
+                    j = k % self.RING
+                    if self._header_done[j] is not None:
+                        self._header_done[j].synchronize()     # (four steps old: already executed)
+                    slab["bytes"] = K.packed_copy_batch(self.store, self.row_off, self.row_const,
+                                                        slab["order"], self._headers_np[j], slot["buf"])
+                    self._header_done[j] = torch.cuda.Event()
+                    self._header_done[j].record(self.copy_stream)
+                slot["ready"].record(self.copy_stream)
+            slot["bytes"], slot["rows"] = slab["bytes"], rows
+            return slot
         with self._cv:
             if k != self._taken_upto:
                 raise ValueError("packed slabs are fetched in epoch order")

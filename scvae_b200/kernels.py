@@ -95,6 +95,32 @@ def csr_densify_packed(slab, B, G, row_const=None, t16=None, x16=None):
                "csr_densify_packed")
 
 
+def packed_pull(store_pinned, row_off, row_const_all, order, slab):
+    """The GPU assembles the packed slab of the rows ``order`` (device int64) itself, reading the
+    row strings from pinned host memory (``store_pinned``: a pinned uint8 tensor)."""
+    lib = _lib.load()
+    _lib.check(lib.scvae_packed_pull(store_pinned.data_ptr(), _p(row_off), _p(row_const_all), _p(order),
+                                     int(order.numel()), _p(slab), int(slab.numel()), _stream()),
+               "packed_pull")
+
+
+def packed_copy_batch(store, row_off, row_const_all, order, header, slab):
+    """One batched copy (copy engine) of the rows ``order`` from the pinned ``store`` (numpy view of
+    pinned memory) into the device ``slab``; ``header``: numpy view of a pinned staging area.
+    Returns the slab's bytes, or None when the runtime has no batched copies."""
+    import ctypes
+    lib = _lib.load()
+    out = ctypes.c_int64(0)
+    status = lib.scvae_packed_copy_batch(store.ctypes.data, row_off.ctypes.data, row_const_all.ctypes.data,
+                                         order.ctypes.data, int(order.size), int(row_off.size - 1),
+                                         header.ctypes.data, _p(slab), int(slab.numel()),
+                                         slab.device.index or 0, _stream(), ctypes.byref(out))
+    if status == 2:
+        return None
+    _lib.check(status, "packed_copy_batch")
+    return int(out.value)
+
+
 def packed_rows_offset(B):
     return int(_lib.load().scvae_packed_rows_offset(int(B)))
 

@@ -855,8 +855,9 @@ def test_continuous_likelihood_fwd_bwd_and_moments(kind, M, G, tile):
         assert (got[ok] - w[ok]).abs().max().item() <= 1e-3 * scale + 1e-6
 
 
+@pytest.mark.parametrize("feeder", ["batch", "device", "host"])
 @pytest.mark.parametrize("cap,direct", [(200.0, True), (3000.0, False), (60000.0, False)])
-def test_csr_densify_packed_matches_csr_densify(cap, direct):
+def test_csr_densify_packed_matches_csr_densify(cap, direct, feeder):
     """The streamed wire format (packed row slabs, scvae_csr_densify_packed) against the CSR form:
     identical 16-bit minibatch and per-cell constants, counts with and without escapes (>= 255), a
     ragged last slab, slabs assembled by the feeder thread (scvae_pack_row_slab)."""
@@ -869,7 +870,7 @@ def test_csr_densify_packed_matches_csr_densify(cap, direct):
     dense[7] = 0
     csr = scipy.sparse.csr_matrix(dense)
     dev = _dev()
-    stream = PackedStream(csr, dev, B)
+    stream = PackedStream(csr, dev, B, feeder=feeder)       # GPU pull from pinned memory / host gather
     assert 2.0 < stream.bytes_per_nonzero < 3.2
     order = rng.permutation(N)
     stream.pack_epoch(order)

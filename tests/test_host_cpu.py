@@ -90,12 +90,12 @@ def test_packed_stream_slabs_decode_to_the_rows_of_the_matrix():
         strings = host[K.packed_rows_offset(rows):]
         for r in range(rows):
             s = strings[off[r]:off[r + 1]].astype(numpy.int64)
-            nesc = s[0] | (s[1] << 8)
-            blocks = s[2:2 + nblk]
-            nnz = (s.size - 2 - nblk - 4 * nesc) // 2
-            assert blocks.sum() == nnz
-            e = s[2 + nblk:2 + nblk + 2 * nnz].reshape(nnz, 2)
-            esc = s[2 + nblk + 2 * nnz:].reshape(nesc, 4)
+            nesc, nnz = s[0] | (s[1] << 8), s[2] | (s[3] << 8)
+            blocks = s[4:4 + nblk]
+            assert blocks.sum() == nnz and s.size % 16 == 0
+            assert s.size == (4 + nblk + 2 * nnz + 4 * nesc + 15) // 16 * 16
+            e = s[4 + nblk:4 + nblk + 2 * nnz].reshape(nnz, 2)
+            esc = s[4 + nblk + 2 * nnz:4 + nblk + 2 * nnz + 4 * nesc].reshape(nesc, 4)
             values = e[:, 1].copy()
             lookup = {int(a | (b << 8)): int(c | (d << 8)) for a, b, c, d in esc}
             for i in numpy.nonzero(values == 255)[0]:
@@ -114,4 +114,4 @@ def test_packed_stream_slabs_decode_to_the_rows_of_the_matrix():
     stream.close()
     # ~2 bytes per non-zero when the counts fit one byte
     small = PackedStream(scipy.sparse.csr_matrix(numpy.minimum(dense, 200.0)), "cpu", B)
-    assert small.bytes_per_nonzero < 2.0 + (2 + nblk) * n / (dense > 0).sum() + 1e-9
+    assert small.bytes_per_nonzero < 2.0 + (4 + nblk + 15) * n / (dense > 0).sum() + 1e-9
