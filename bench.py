@@ -248,7 +248,7 @@ def workload_config(args, minibatch):
 # ---------------------------------------------------------------------------------------------
 # parity of the benchmarked path against the oracle (checker only, outside every timed region)
 # ---------------------------------------------------------------------------------------------
-def parity_check(args, eng, loop, data, csr, rows):
+def parity_check(args, eng, loop, data, csr, rows, compare=True):
     """Replays the captured training step (the object the timed region replays) on ``rows`` and
     compares ELBO / reconstruction error / KL / per-cell log p / per-cell latent means with
     ``oracle.train_step`` (fp64) on the same rows, variables and reparameterisation noise.
@@ -261,6 +261,8 @@ def parity_check(args, eng, loop, data, csr, rows):
     bound = loop.step(data, 1e-4, 1.0)
     torch.cuda.synchronize()
     plan = loop.plan
+    if compare is False:          # ranks > 0: they only take part in the step's gradient exchange
+        return None
     bound = bound.cpu().numpy().astype(numpy.float64)
     eps = plan.eps.cpu().double().reshape(1, B, L)
     x = torch.from_numpy(csr[rows.cpu().numpy()].toarray()).double()
@@ -685,6 +687,7 @@ def run_b200(args):
                 elbos.append(float(elbo_host[(i - 1) % 2][0]))
             return nxt, None
 
+        sync_all()            # (ranks finish encoding their shards at different times)
         _dbg("e2e: streamed CSR ready")
         pending = stream.fetch(0, 0)
         for i in range(args.warmup):
@@ -721,30 +724,40 @@ def run_b200(args):
     # ---- parity of the timed path (untimed): one more replay of the SAME captured step on the
     # rows of the first timed minibatch, checked against the oracle on those rows / weights / noise
     parity = None
-    if rank == 0 and not args.no_parity:
+    if not args.no_parity:
+        # (every rank replays the step -- it contains the gradient exchange; rank 0 compares)
         try:
             parity = parity_check(args, eng, loop, data, csr, perm[args.warmup % n_batches * B:
-                                                                   (args.warmup % n_batches + 1) * B])
+                                                                   (args.warmup % n_batches + 1) * B],
+                                  compare=rank == 0)
         except Exception as exc:      # reported, never silently dropped
             parity = {"error": repr(exc)}
     replicas = None
     if world > 1:
-        # replica identity after the timed steps: every rank must hold the same variables and Adam
-        # slots (max |theta_r - theta_0| over ranks and entries, via one max- and one min-all-reduce)
+        # replica identity after the timed steps: every rank must hold the same variables
+        # (max |theta_r - theta_0| over ranks and entries, via one max- and one min-all-reduce) and
+        # step counter.  The Adam slots are compared after PeerExchange.gather_slots: between
+        # checkpoints each rank keeps only its own slice of them live (the fused exchange shards
+        # the optimiser state).
         torch.cuda.synchronize()
-        worst = 0.0
-        for buf in (eng.store.param, eng.store.m, eng.store.v):
+
+        def spread(buf):
             hi, lo = buf.clone(), buf.clone()
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
             dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-            worst = max(worst, float((hi - lo).abs().max().item()))
-        steps_t = eng.store.step.clone().float()
-        s_hi, s_lo = steps_t.clone(), steps_t.clone()
-        dist.all_reduce(s_hi, op=dist.ReduceOp.MAX)
-        dist.all_reduce(s_lo, op=dist.ReduceOp.MIN)
-        failed = bool(getattr(eng, "_peer", None) is not None and eng._peer.timed_out())
-        replicas = {"identical": bool(worst == 0.0 and float(s_hi) == float(s_lo) and not failed),
-                    "max_abs_difference": worst, "exchange_timed_out": failed}
+            return float((hi - lo).abs().max().item())
+        worst = spread(eng.store.param)
+        peer = getattr(eng, "_peer", None)
+        if peer is not None and getattr(eng, "_last_ranges", None):
+            peer.gather_slots(eng._last_ranges)
+        worst_slots = max(spread(eng.store.m), spread(eng.store.v))
+        steps_spread = spread(eng.store.step.clone().float())
+        failed = bool(peer is not None and peer.timed_out())
+        replicas = {"identical": bool(worst == 0.0 and worst_slots == 0.0 and steps_spread == 0.0
+                                      and not failed),
+                    "max_abs_difference_variables": worst,
+                    "max_abs_difference_adam_slots": worst_slots,
+                    "exchange_timed_out": failed}
         dist.barrier()
 
     extra = None

@@ -12,7 +12,7 @@
 // launch on a symmetric flag buffer, sequence-numbered so that flags never need resetting:
 //   entry  "my gradients are complete"            - then peers' gradient slices are read;
 //   exit   "my parameter stores to you are done"  - then the stream may go on to read them.
-// Waiting is bounded: after ~2 s without progress a rank sets an error word and carries on
+// Waiting is bounded: after 30 s without progress a rank sets an error word and carries on
 // (results are then invalid, but the GPU is not left hanging).
 #include "common.cuh"
 
@@ -42,14 +42,23 @@ __device__ __forceinline__ float4 ld_peer4(const float *p) {
                  : "memory");
     return v;
 }
-// returns false on timeout
+// returns false on timeout.  The bound is wall time (30 s): ranks legitimately drift apart by seconds
+// between steps (one of them writes a checkpoint, encodes a data set, captures a graph); only a rank
+// that is gone should trip it.  The host checks the error word (PeerExchange.timed_out) every epoch.
+constexpr unsigned long long kFlagWaitNs = 30ull * 1000ull * 1000ull * 1000ull;
 __device__ __forceinline__ bool wait_flag(const uint32_t *f, uint32_t seq) {
-    for (int it = 0; it < (1 << 24); ++it) {
+    unsigned long long t0 = 0;
+    for (unsigned it = 0;; ++it) {
         // sequence numbers only grow; signed distance tolerates wrap-around
         if ((int32_t)(ld_acquire_sys(f) - seq) >= 0) return true;
         __nanosleep(100);
+        if ((it & 1023u) == 1023u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kFlagWaitNs) return false;
+        }
     }
-    return false;
 }
 
 // ctl (local, zero-initialised): [0] last completed sequence number, [1] CTAs done, [2] error

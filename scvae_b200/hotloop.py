@@ -317,7 +317,8 @@ class PackedStream:
         self._cv = threading.Condition()
         self._packed_upto = 0                 # slabs [0, _packed_upto) sit in the ring
         self._taken_upto = 0                  # slabs [0, _taken_upto) have had their copy enqueued
-        self._copied = [None] * self.RING     # event after the copy out of each ring buffer
+        self._released_upto = 0               # slabs [0, _released_upto) have left their ring buffer
+        self._copied = {}                     # slab -> event behind its copy out of the ring
         self._stop = False
         self._error = None
         self.pack_seconds = 0.0
@@ -331,13 +332,12 @@ class PackedStream:
             for k in range(len(self.slabs)):
                 j = k % self.RING
                 with self._cv:
-                    while not self._stop and k - self._taken_upto >= self.RING:
+                    # (no CUDA call in this thread -- it runs beside stream captures: the main
+                    # thread reports which slabs have left the host, see fetch)
+                    while not self._stop and k - self._released_upto >= self.RING:
                         self._cv.wait()
                     if self._stop:
                         return
-                    done = self._copied[j]
-                if done is not None:
-                    done.synchronize()        # the previous slab in this buffer has left the host
                 t0 = time.perf_counter()
                 self.pack_slab_host(k, self._ring_np[j])
                 self.pack_seconds += time.perf_counter() - t0
@@ -393,11 +393,12 @@ class PackedStream:
                 raise self._error
         slab, j = self.slabs[k], k % self.RING
         if not self.cuda:
+            out = {"packed": True, "host": self._ring_np[j][:slab["bytes"]].copy(), "rows": slab["rows"],
+                   "bytes": slab["bytes"]}
             with self._cv:
-                self._taken_upto = k + 1
+                self._taken_upto = self._released_upto = k + 1
                 self._cv.notify_all()
-            return {"packed": True, "host": self._ring_np[j][:slab["bytes"]].copy(), "rows": slab["rows"],
-                    "bytes": slab["bytes"]}
+            return out
         slot = self.slots[slot_id]
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(slot["free"])
@@ -405,8 +406,15 @@ class PackedStream:
             slot["ready"].record(self.copy_stream)
             done = torch.cuda.Event()
             done.record(self.copy_stream)
+        self._copied[k] = done
+        # slabs whose copy was enqueued two fetches ago have long left the host: release their ring
+        # buffers to the feeder (the wait below returns at once)
+        released = self._released_upto
+        while released <= k - 2:
+            self._copied.pop(released).synchronize()
+            released += 1
         with self._cv:
-            self._copied[j] = done
+            self._released_upto = released
             self._taken_upto = k + 1
             self._cv.notify_all()
         slot["bytes"], slot["rows"] = slab["bytes"], slab["rows"]
