@@ -1,4 +1,5 @@
 """The C-ABI shared library loads without a GPU and exports every symbol the header declares."""
+import pytest
 import os
 import re
 
@@ -55,3 +56,33 @@ def test_product_path_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("oracle/", ""), f + " references the oracle"
+
+
+def test_ctypes_structures_match_the_header_layout(tmp_path):
+    """The descriptor structs cross the C ABI by pointer: every field of the ctypes mirrors in
+    `_lib.py` must sit at the offset the C compiler gives it in `include/scvae_b200.h`."""
+    import ctypes
+    import shutil
+    import subprocess
+    from scvae_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    pairs = [("scvae_mid_layer", _lib.MidLayer), ("scvae_mid_desc", _lib.MidDesc),
+             ("scvae_shadow", _lib.Shadow)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "scvae_b200.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append('printf("%s %zu\\n", "{0}", sizeof({0}));'.format(cname))
+        for field, _ in cls._fields_:
+            lines.append('printf("%s.%s %zu\\n", "{0}", "{1}", offsetof({0}, {1}));'.format(cname, field))
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True,
+                                                       text=True).stdout.splitlines())
+    for cname, cls in pairs:
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for field, _ in cls._fields_:
+            assert int(out["{}.{}".format(cname, field)]) == getattr(cls, field).offset, (cname, field)
