@@ -436,6 +436,17 @@ def extra_configs(dev):
         lambda cfg, prm, x, eps, b: O.vae_forward(cfg, prm, x, x, eps.reshape(1, b, L3), is_training=True),
         32768, G3, L3, 4096, 1024, 30,
         ["lower_bound", "lower_bound_weighted", "reconstruction_error", "kl_divergence"])
+    # the headline configuration at two other minibatch sizes: twice the benchmarked one (the fixed
+    # per-step latencies amortise further) and the reference's default of 100 cells (pure latency)
+    G2, L2 = 20000, 50
+    cfg2 = O.VAEConfig(G2, L2, [100], "negative binomial")
+    for B2, pB2, steps2 in ((8192, 512, 30), (100, 100, 200)):
+        one("C2 shape at minibatch {}: VAE, 68000 x 20000 genes synthetic (16384-cell shard resident), "
+            "negative binomial, latent 50, hidden [100], R=S=1".format(B2),
+            lambda: VAEEngine(G2, L2, [100], "negative binomial", device=dev, seed=0), cfg2,
+            lambda cfg, prm, x, eps, b: O.vae_forward(cfg, prm, x, x, eps.reshape(1, b, L2), is_training=True),
+            16384, G2, L2, B2, pB2, steps2,
+            ["lower_bound", "lower_bound_weighted", "reconstruction_error", "kl_divergence"])
     G4, L4, K4 = 20000, 50, 20
     cfg4 = O.GMVAEConfig(G4, L4, K4, [100], "negative binomial", 1, 1, True)
     one("C4 shape: GMVAE, K=20 clusters, 68000 x 20000 genes synthetic (16384-cell shard resident), "

@@ -358,6 +358,47 @@ __device__ __noinline__ void mid_bn_partial(const MidCtx &c, const float *Y, int
         ws_stat[((int64_t)blockIdx.x * 2 + 1) * kMidCols + col] = fmaxf(t2 - t1 * t1 * inv_n, 0.f);
     }
 }
+// The fold for grids of at most 8 CTAs: thread t < 128 owns column t and adds the <= 8 partials in CTA
+// order (the same arithmetic as the general fold, whose 8 warp lanes then hold one partial each).
+__device__ __noinline__ void mid_bn_fold_small(const MidCtx &c, const MidDesc &d, const MidLayer &l, const float *ws_stat,
+                                               float *scratch, float *s_mean, float *s_rstd) {
+    (void)scratch;
+    const int N = l.n_out, G = gridDim.x, col = threadIdx.x;
+    const float inv_b = 1.f / (float)d.B;
+    if (col < N) {
+        float mk[kMidThreads / 32], qk[kMidThreads / 32];
+#pragma unroll
+        for (int k = 0; k < kMidThreads / 32; ++k) {
+            mk[k] = k < G ? __ldcg(ws_stat + ((int64_t)k * 2 + 0) * kMidCols + col) : 0.f;
+            qk[k] = k < G ? __ldcg(ws_stat + ((int64_t)k * 2 + 1) * kMidCols + col) : 0.f;
+        }
+        float m = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMidThreads / 32; ++k) m += fmaf((float)mid_rows_of(k, d.rows_per_cta, d.B), mk[k], 0.f);
+        const float mean_all = m * inv_b;
+        float q_all = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMidThreads / 32; ++k) {
+            const float nb = (float)mid_rows_of(k, d.rows_per_cta, d.B);
+            const float dm = mk[k] - mean_all;
+            q_all += qk[k] + nb * dm * dm;
+        }
+        const float var = q_all * inv_b;
+        const float rstd = rsqrtf(var + kBnEps);
+        s_mean[col] = mean_all;
+        s_rstd[col] = rstd;
+        if (blockIdx.x == 0) {
+            l.mean[col] = mean_all;
+            l.rstd[col] = rstd;
+            if (d.update_moving) {      // Bessel-corrected variance (tf fused batch norm)
+                const float vu = var * ((float)d.B / (float)max(d.B - 1, 1));
+                l.moving_mean[col] -= (1.f - kBnDecay) * (l.moving_mean[col] - mean_all);
+                l.moving_var[col] -= (1.f - kBnDecay) * (l.moving_var[col] - vu);
+            }
+        }
+    }
+    __syncthreads();
+}
 // Every CTA folds all partials in the same fixed order.  With n_k cells, mean m_k and M2 q_k per CTA:
 //   mean = sum n_k m_k / B,   M2 = sum q_k + sum n_k (m_k - mean)^2     (exact, no cancellation),
 // each as plain sums: warp w takes the CTAs k = w mod 8 for 4 columns per lane, then the 8 per-warp
@@ -372,6 +413,12 @@ __device__ __noinline__ void mid_bn_fold(const MidCtx &c, const MidDesc &d, cons
     // (all loads of a pass are issued before the first use: the fold costs two L2 round trips)
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     float mb[kMidFoldIt][4];
+    if (G <= kMidThreads / 32) {
+        // small grids (minibatches of a few hundred cells): one partial per warp, none of the
+        // unrolled load sequence below is fetched or issued
+        mid_bn_fold_small(c, d, l, ws_stat, scratch, s_mean, s_rstd);
+        return;
+    }
 #pragma unroll
     for (int it = 0; it < kMidFoldIt; ++it) {
         const int k = warp + it * (kMidThreads / 32);
@@ -775,7 +822,27 @@ __device__ __noinline__ void mid_bn_relu_bwd(const MidCtx &c, const MidDesc &d, 
     }
     mid_grid_sync(d.barrier, d.error);
     float *t1 = c.stat, *t2 = c.stat + kMidCols;
-    {
+    if (gridDim.x <= kMidThreads / 32) {
+        // small grids: thread t < N adds the <= 8 partials of column t in CTA order
+        const int col = threadIdx.x, G = gridDim.x;
+        if (col < N) {
+            float v1[kMidThreads / 32], v2[kMidThreads / 32];
+#pragma unroll
+            for (int k = 0; k < kMidThreads / 32; ++k) {
+                v1[k] = k < G ? __ldcg(ws_stat + ((int64_t)k * 2 + 0) * kMidCols + col) : 0.f;
+                v2[k] = k < G ? __ldcg(ws_stat + ((int64_t)k * 2 + 1) * kMidCols + col) : 0.f;
+            }
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < kMidThreads / 32; ++k) {
+                s1 += v1[k];
+                s2 += v2[k];
+            }
+            t1[col] = s1;
+            t2[col] = s2;
+            if (blockIdx.x == 0) l.dbeta[col] = s1;
+        }
+    } else {
         // fixed-order fold of the CTA partials: warp w takes the CTAs k = w mod 8
         const int G = gridDim.x;
         float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1089,11 +1156,30 @@ __global__ void __launch_bounds__(kMidThreads, 1) vae_mid_bwd_kernel(const __gri
         const int G = gridDim.x;
         auto reduce = [&](const MidLayer &l) {
             const int64_t n = (int64_t)l.n_out * l.ldw;
-            for (int64_t e = (int64_t)blockIdx.x * kMidThreads + threadIdx.x; e < n; e += (int64_t)gridDim.x * kMidThreads) {
-                float s = 0.f;
+            const int64_t stride = (int64_t)gridDim.x * kMidThreads;
+            // four elements per thread and trip: with a small grid a thread owns many elements, and
+            // one element's few partials alone would leave a single load in flight
+            for (int64_t e = (int64_t)blockIdx.x * kMidThreads + threadIdx.x; e < n; e += 4 * stride) {
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                const bool in1 = e + stride < n, in2 = e + 2 * stride < n, in3 = e + 3 * stride < n;
+                if (!in1) {          // large grids: one element per thread, eight partials in flight
 #pragma unroll 8
-                for (int k = 0; k < G; ++k) s += __ldcg(cursor + (int64_t)k * n + e);      // CTA order
-                l.dw[e] = s;
+                    for (int k = 0; k < G; ++k) s0 += __ldcg(cursor + (int64_t)k * n + e);
+                    l.dw[e] = s0;
+                    continue;
+                }
+#pragma unroll 4
+                for (int k = 0; k < G; ++k) {                                              // CTA order
+                    const float *src = cursor + (int64_t)k * n + e;
+                    s0 += __ldcg(src);
+                    if (in1) s1 += __ldcg(src + stride);
+                    if (in2) s2 += __ldcg(src + 2 * stride);
+                    if (in3) s3 += __ldcg(src + 3 * stride);
+                }
+                l.dw[e] = s0;
+                if (in1) l.dw[e + stride] = s1;
+                if (in2) l.dw[e + 2 * stride] = s2;
+                if (in3) l.dw[e + 3 * stride] = s3;
             }
             cursor += (int64_t)gridDim.x * n;
         };
