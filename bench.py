@@ -565,6 +565,9 @@ def run_b200(args):
         "gemm": (None, "gemm_tc_kernel (tf32)"),
         "gemm_f16": (None, "gemm_tc_kernel (fp16)"),
         "adam_clip_step": (7 * 4.0 * eng.store.total, "adam_clip_kernel"),
+        "gemm_f16_split": (None, "gemm_tc_kernel (fp16, split operand: first layer forward / weight gradient)"),
+        "vae_mid_fwd": (None, "vae_mid_fwd_kernel (hidden layers, posterior, sample, KL)"),
+        "vae_mid_bwd": (None, "vae_mid_bwd_kernel (their backward + the bound)"),
     }
     evs = {k: [] for k in families}
     originals = {k: getattr(K, k) for k in families}

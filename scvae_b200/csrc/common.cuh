@@ -59,6 +59,14 @@ __device__ __forceinline__ void stg_stream4(float *p, const float4 &v) {
 }
 
 // ---- reductions -------------------------------------------------------------------------
+// TF Adam's step size lr * sqrt(1 - beta2^t) / (1 - beta1^t) in double: 1 - beta^t = -expm1(t ln beta)
+// (exact for small t; cheaper than two double pow in a prologue that every optimiser CTA pays).
+// One definition for the single-GPU and the data-parallel optimiser kernels: their updates must agree
+// bit for bit.
+__device__ __forceinline__ float adam_step_size(double lr_eff, float beta1, float beta2, double t) {
+    return (float)(lr_eff * sqrt(-expm1(t * log((double)beta2))) / (-expm1(t * log((double)beta1))));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

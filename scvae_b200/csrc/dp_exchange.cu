@@ -77,7 +77,7 @@ dp_reduce_adam_kernel(DpPeers peers, int world_rt, int rank, float *__restrict__
     if (threadIdx.x == 0) {
         const double t = (double)(*step + 1);
         const double lr_eff = (double)lr * (scalars ? (double)scalars[0] : 1.0);
-        s_lr_t = (float)(lr_eff * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t)));
+        s_lr_t = adam_step_size(lr_eff, beta1, beta2, t);
         s_seq = ctl[0] + 1u;
     }
     __syncthreads();

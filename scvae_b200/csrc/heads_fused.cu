@@ -641,6 +641,38 @@ fused_finish_kernel(const float *__restrict__ part, int64_t part_stride, int gsp
     }
 }
 
+// The same reduction for few gene ranges and many cells (the training minibatch: gsplit ~ 9, M = 4096):
+// one thread per (cell, column quad), the partials added in s order with all loads of a thread in
+// flight; the lane of column quad 0 also adds the cell's log p partials.  (The CTA-per-cell form above
+// spends its time in block scheduling when there is next to nothing to add per cell.)
+__global__ void __launch_bounds__(256)
+fused_finish_wide_kernel(const float *__restrict__ part, int64_t part_stride, int gsplit, int M,
+                         const float *__restrict__ row_const, int t_rows, float *__restrict__ logp,
+                         const float *__restrict__ dd_part, float *__restrict__ dd, int64_t lddd, int dd_cols) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (int)(i & 31) << 2;
+    const int64_t m = i >> 5;
+    if (m >= M) return;
+    if (c == 0) {
+        float lp = 0.f;
+#pragma unroll 4
+        for (int s = 0; s < gsplit; ++s) lp += part[(int64_t)s * part_stride + m];
+        logp[m] = lp - (row_const ? row_const[m % t_rows] : 0.f);
+    }
+    if (!dd_part || c >= lddd) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int s = 0; s < gsplit; ++s) {
+        const float4 v = *reinterpret_cast<const float4 *>(dd_part + ((int64_t)s * part_stride + m) * FK + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (c + 0 >= dd_cols) acc.x = 0.f;
+    if (c + 1 >= dd_cols) acc.y = 0.f;
+    if (c + 2 >= dd_cols) acc.z = 0.f;
+    if (c + 3 >= dd_cols) acc.w = 0.f;
+    *reinterpret_cast<float4 *>(dd + m * lddd + c) = acc;     // lddd % 4 == 0
+}
+
 static inline int make_map_u16(CUtensorMap *map, const void *base, int64_t rows, int64_t cols, int64_t ld,
                                int box_cols, int box_rows) {
     EncodeTiledFn enc = get_encode();
@@ -717,8 +749,12 @@ static int launch_fused_t(const void *d16, const void *w16, const void *t16, int
     heads_fused_kernel<KIND, T_HALF, BWD><<<f.row_tiles * f.gsplit, fused_threads(P), smem, s>>>(tmD, tmW, tmT, tmDA, tmDD, p);
     SCVAE_CHECK_LAUNCH("heads_fused");
     const float *dd_part = BWD ? logp_part + (int64_t)f.gsplit * f.row_tiles * FM : nullptr;
-    fused_finish_kernel<<<M, 256, 0, s>>>(logp_part, p.part_stride, f.gsplit, M, row_const, t_rows, logp, dd_part,
-                                          dd, lddd, dd_cols);
+    if (f.gsplit <= 16)
+        fused_finish_wide_kernel<<<(unsigned)(((int64_t)M * 32 + 255) / 256), 256, 0, s>>>(
+            logp_part, p.part_stride, f.gsplit, M, row_const, t_rows, logp, dd_part, dd, lddd, dd_cols);
+    else
+        fused_finish_kernel<<<M, 256, 0, s>>>(logp_part, p.part_stride, f.gsplit, M, row_const, t_rows, logp, dd_part,
+                                              dd, lddd, dd_cols);
     SCVAE_CHECK_LAUNCH("heads_fused_finish");
     return 0;
 }

@@ -49,7 +49,7 @@ adam_clip_kernel(float *__restrict__ p, const float *__restrict__ g, float *__re
     if (threadIdx.x == 0) {
         const double t = (double)(*step + 1);
         const double lr_eff = (double)lr * (scalars ? (double)scalars[0] : 1.0);
-        s_lr_t = (float)(lr_eff * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t)));
+        s_lr_t = adam_step_size(lr_eff, beta1, beta2, t);
     }
     __syncthreads();
     const float lr_t = s_lr_t;
