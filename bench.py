@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--feeder", default=None, choices=["host", "device", "batch"],
+                    help="hotloop.PackedStream feeder of the e2e leg (default: the stream's own choice)")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the C3 / C4 shaped extra configurations (BASELINE.json configs[2..3])")
     ap.add_argument("--no-parity", action="store_true",
@@ -667,7 +669,7 @@ def run_b200(args):
         # the product path for host-resident data (VariationalAutoencoder.train(...,
         # data_residency="host")): the epoch's rows, in shuffled order, as packed slabs in pinned
         # memory (hotloop.PackedStream, ~2 bytes per non-zero); one host -> device copy per step
-        stream = PackedStream(csr, dev, B)
+        stream = PackedStream(csr, dev, B, feeder=args.feeder)
         # shuffled epochs back to back, full minibatches only: the feeder thread assembles each
         # step's slab in pinned memory (scvae_pack_row_slab) WHILE the timed steps run
         full = n_batches * B

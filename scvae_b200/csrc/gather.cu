@@ -371,24 +371,29 @@ packed_offsets_kernel(const int64_t *__restrict__ row_off, const float *__restri
     if (threadIdx.x == 0) ro[B] = carry_s;
 }
 
-__global__ void __launch_bounds__(128)
+// <= 32 registers and no shared memory, so that a CTA fits beside ANY kernel of the training step it
+// runs next to (the fused heads kernel leaves 4096 registers per SM): the pull is hidden behind the
+// previous step only if its CTAs are resident while that step's kernels are.
+__global__ void __launch_bounds__(128, 16)
 packed_pull_kernel(const uint8_t *__restrict__ store, const int64_t *__restrict__ row_off,
                    const int64_t *__restrict__ order, int B, uint8_t *__restrict__ slab, int64_t capacity) {
-    const int b = blockIdx.x;
     const int32_t *ro = reinterpret_cast<const int32_t *>(slab);
-    const int64_t i = order[b];
     const int64_t base = packed_rows_offset(B);
-    const int n16 = (int)((row_off[i + 1] - row_off[i]) >> 4);
-    if (base + ro[b] + ((int64_t)n16 << 4) > capacity) return;     // (never: the buffer holds the worst case)
-    const uint4 *src = reinterpret_cast<const uint4 *>(store + row_off[i]);
-    uint4 *dst = reinterpret_cast<uint4 *>(slab + base + ro[b]);
-    // several 128-bit loads per thread in flight: the latency is a PCIe round trip
-    int k = threadIdx.x;
-    for (; k + 3 * 128 < n16; k += 4 * 128) {
-        const uint4 v0 = src[k], v1 = src[k + 128], v2 = src[k + 256], v3 = src[k + 384];
-        dst[k] = v0; dst[k + 128] = v1; dst[k + 256] = v2; dst[k + 384] = v3;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const int64_t i = order[b];
+        const int64_t off = row_off[i];
+        const int n16 = (int)((row_off[i + 1] - off) >> 4);
+        if (base + ro[b] + ((int64_t)n16 << 4) > capacity) continue;     // (never: the buffer holds the worst case)
+        const uint4 *src = reinterpret_cast<const uint4 *>(store + off);
+        uint4 *dst = reinterpret_cast<uint4 *>(slab + base + ro[b]);
+        // several 128-bit loads per thread in flight: the latency is a PCIe round trip
+        int k = threadIdx.x;
+        for (; k + 3 * 128 < n16; k += 4 * 128) {
+            const uint4 v0 = src[k], v1 = src[k + 128], v2 = src[k + 256], v3 = src[k + 384];
+            dst[k] = v0; dst[k + 128] = v1; dst[k + 256] = v2; dst[k + 384] = v3;
+        }
+        for (; k < n16; k += 128) dst[k] = src[k];
     }
-    for (; k < n16; k += 128) dst[k] = src[k];
 }
 
 // sum_g lgamma(1 + x) of every CSR row (one warp per row): a per-cell constant of the data set,
@@ -502,7 +507,10 @@ extern "C" int scvae_packed_pull(const void *store, const int64_t *row_off, cons
     cudaStream_t s = (cudaStream_t)stream;
     packed_offsets_kernel<<<1, 1024, 0, s>>>(row_off, row_const_all, order, B, (uint8_t *)slab);
     SCVAE_CHECK_LAUNCH("packed_offsets");
-    packed_pull_kernel<<<B, 128, 0, s>>>((const uint8_t *)store, row_off, order, B, (uint8_t *)slab, slab_capacity);
+    // persistent CTAs walk the rows
+    const int pull_ctas = B < 148 ? B : 148;      // one per SM: the step's big kernels leave room for exactly one
+    packed_pull_kernel<<<pull_ctas, 128, 0, s>>>((const uint8_t *)store, row_off, order, B, (uint8_t *)slab,
+                                                  slab_capacity);
     SCVAE_CHECK_LAUNCH("packed_pull");
     return 0;
 }

@@ -40,6 +40,11 @@ constexpr int kMidRows = 64;        // most cells per CTA
 constexpr int kMidWP = 132;         // row pitch of the staged weight tile: 4 mod 32 (conflict-free 128-bit rows)
 constexpr int kMidSlots = 2 * SCVAE_MID_MAX_LAYERS;                // batch-normed layers (encoder + decoder)
 constexpr int kMidFoldIt = 20;                                      // CTAs per warp in a fold: grid <= 160
+// 240 registers per thread (256 threads -> 61 440 of the SM's 65 536): one 128-thread / 32-register CTA of
+// the streamed feeder's pull kernel (gather.cu) fits beside a resident middle-kernel CTA, exactly as it
+// does beside the fused heads kernel (640 x 96 registers) -- the pull of the next minibatch is hidden
+// behind the step only while its CTAs can be resident
+constexpr int kMidMaxRegs = 240;
 constexpr long long kMidSpinLimit = 4000000000ll;   // ~2 s of clock64 ticks: bounded barrier wait
 
 typedef scvae_mid_layer MidLayer;
@@ -599,7 +604,7 @@ __device__ __noinline__ void mid_fwd_bn_relu(const MidCtx &c, const MidDesc &d, 
 }
 
 template <int TM>
-__global__ void __launch_bounds__(kMidThreads, 1) vae_mid_fwd_kernel(const __grid_constant__ MidDesc param) {
+__global__ void __maxnreg__(kMidMaxRegs) vae_mid_fwd_kernel(const __grid_constant__ MidDesc param) {
     constexpr int SPAN = MidTraits<TM>::kSpan;
     extern __shared__ __align__(16) float mid_smem[];
     __shared__ MidShared sh;
@@ -897,7 +902,7 @@ __device__ __noinline__ void mid_bn_relu_bwd(const MidCtx &c, const MidDesc &d, 
 }
 
 template <int TM>
-__global__ void __launch_bounds__(kMidThreads, 1) vae_mid_bwd_kernel(const __grid_constant__ MidDesc param) {
+__global__ void __maxnreg__(kMidMaxRegs) vae_mid_bwd_kernel(const __grid_constant__ MidDesc param) {
     constexpr int SPAN = MidTraits<TM>::kSpan;
     extern __shared__ __align__(16) float mid_smem[];
     __shared__ MidShared sh;

@@ -162,10 +162,11 @@ class PackedStream:
         self.cuda = self.device.type == "cuda"
         self._copy_stream = None
         self.B = int(minibatch_size)
+        import os
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+        cores_per_rank = (os.cpu_count() or 8) // max(local_world, 1)
         if pack_threads is None:          # host threads of the slab gather, shared between the ranks of a node
-            import os
-            world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
-            pack_threads = max(1, min(8, (os.cpu_count() or 8) // max(world, 1)))
+            pack_threads = max(1, min(8, cores_per_rank))
         self.pack_threads = int(pack_threads)
         self.u16_ok = True
         self.f16_exact = bool(data.size == 0 or data.max() <= 2048)
@@ -206,14 +207,16 @@ class PackedStream:
         self.store = store
         self.lens = lens
         self.bytes_per_nonzero = float(store.size) / max(total, 1)
-        # feeder "host" (default): a thread gathers each minibatch's strings into a pinned slab
-        # (scvae_pack_row_slab) that ONE copy ships; "device": the strings sit in pinned memory and
-        # the GPU pulls the rows itself (scvae_packed_pull) -- no host work per step, but SM-issued
-        # reads over PCIe reached only ~15 GB/s on the B200 box against ~50 GB/s for the copy engine
+        # feeder "host": a thread gathers each minibatch's strings into a pinned slab
+        # (scvae_pack_row_slab, ~9 GB/s per host thread) that ONE copy ships -- the default when the
+        # rank has host cores to spare (>= 6); "device": the strings sit in pinned memory and the GPU
+        # pulls the rows itself (scvae_packed_pull: 45 GB/s alone, but its CTAs share the SMs with the
+        # step they run beside, which costs ~0.2 ms per step) -- no host work per step, the default
+        # when several ranks share few cores (8 GPUs on a 16-core host: 2.6 x the host feeder)
         # "batch": the strings sit in pinned memory and ONE batched copy (cudaMemcpyBatchAsync: the
         # copy engine walks the B row strings) moves them into the device slab -- measured 1.5 ms
         # of driver time per 4096-row batch, so the host gather stays the default
-        self.feeder = feeder or "host"
+        self.feeder = feeder or ("host" if (cores_per_rank >= 6 or not self.cuda) else "device")
         if self.feeder not in ("device", "host", "batch") or (self.feeder != "host" and not self.cuda):
             raise ValueError("feeder: `batch` / `device` (CUDA only) or `host`")
         if self.feeder in ("device", "batch"):
