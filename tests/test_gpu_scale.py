@@ -257,3 +257,48 @@ def test_gmvae_step_k20_at_20k_genes():
     for k, g in grads.items():
         err = (got[k].double() - g).abs().max().item()
         assert err <= 1e-2 * g.abs().max().item() + 1e-4 * gmax, (k, err, g.abs().max().item())
+
+
+def test_resident_csr_beyond_two_to_the_31_non_zeros():
+    """C3 at full size holds 2.5 G non-zeros: the CSR offsets are 64-bit end to end.  A synthetic
+    matrix with > 2^31 stored entries (1400 per row, built on the device: 17.6 GB) is densified and
+    its row constants computed for rows on both sides of the 2^31 boundary."""
+    from scvae_b200 import kernels as K
+    dev = _dev()
+    free, _ = torch.cuda.mem_get_info(dev)
+    if free < 40 << 30:
+        pytest.skip("needs 40 GB of free device memory")
+    G, per_row = 20000, 1400
+    n_rows = (1 << 31) // per_row + 4096              # ~1.54 M rows, nnz = 2.153 G > 2^31
+    nnz = n_rows * per_row
+    assert nnz > (1 << 31)
+    indptr = torch.arange(n_rows + 1, dtype=torch.int64, device=dev) * per_row
+    indices = torch.empty(nnz, dtype=torch.int32, device=dev)
+    values = torch.empty(nnz, dtype=torch.float32, device=dev)
+    chunk = 1 << 27
+    for s in range(0, nnz, chunk):
+        i = torch.arange(s, min(s + chunk, nnz), dtype=torch.int64, device=dev)
+        pos, row = i % per_row, i // per_row
+        indices[s:s + i.numel()] = (pos * 14 + row % 14).to(torch.int32)       # sorted within a row, < 19 600
+        values[s:s + i.numel()] = (1 + (i % 3)).to(torch.float32)
+        del i, pos, row
+    rows = torch.tensor([0, 5, (1 << 31) // per_row - 1, (1 << 31) // per_row, (1 << 31) // per_row + 1,
+                         n_rows - 1], dtype=torch.int64, device=dev)
+    B = rows.numel()
+    ld16 = (G + 8) & ~7
+    x16 = torch.zeros(B, ld16, dtype=torch.float16, device=dev)
+    x32 = torch.zeros(B, (G + 4) & ~3, dtype=torch.float32, device=dev)
+    rc = torch.zeros(B, device=dev)
+    K.csr_densify(indptr, indices, values, rows, G, None, rc, x16=x16)          # 16-bit form
+    K.csr_densify(indptr, indices, values, rows, G, x32, None)                  # general form
+    rc_all = torch.zeros(n_rows, device=dev)
+    K.csr_row_constants(indptr, values, rc_all)
+    torch.cuda.synchronize()
+    for b, r in enumerate(rows.tolist()):
+        want = torch.zeros(G, dtype=torch.float64)
+        i = torch.arange(r * per_row, (r + 1) * per_row, dtype=torch.int64)
+        want[(i % per_row) * 14 + r % 14] = (1 + (i % 3)).double()
+        assert torch.equal(x16[b, :G].cpu().double(), want), r
+        assert torch.equal(x32[b, :G].cpu().double(), want), r
+        ref = torch.lgamma(1.0 + want).sum().item()
+        assert abs(rc[b].item() - ref) <= 1e-4 * ref and abs(rc_all[r].item() - ref) <= 1e-4 * ref, r
