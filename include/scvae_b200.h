@@ -445,6 +445,28 @@ int scvae_gmvae_latent_bwd(const float *qh, int64_t ldq, const float *pz, int K,
                            int RS, const float *eps, const float *dz, int64_t lddz,
                            const float *coef, float *dqh, int64_t lddq, float *dpz,
                            void *stream);
+/* The same block for the FULL-COVARIANCE mixture (`-q "full-covariance gaussian mixture"`): q and p
+ * are multivariate Gaussians with a lower-triangular scale matrix S (DU:75-93: L locations +
+ * T = L (L + 1) / 2 scales, softplus clipped at tiny from below, laid out by
+ * tfp.distributions.fill_triangular; multivariate_normal.py:90-150; call sites GMVAE:2958-3048,
+ * :3270-3289).  qh (K*B, ldq) = [locations | raw scales] (L + T columns), pz (K, ldp) likewise;
+ * z = loc_q + S_q eps; klz = log q(z) - log p(z|y=k) with one triangular solve per row.
+ * scvae_gmvae_full_prior expands the K activated prior scale matrices pl (K, L, L) once per step;
+ * the forward keeps w (K*RS*B, L) = S_p^-1 (z - loc_p) for the backward, whose scratch cu has the
+ * same shape; dqh (K*B, lddq), dpz (K, lddp) receive the gradients w.r.t. the pre-activations.
+ * scvae_gmvae_full_covariance_mean: cov (K, L, L) = mean over the cells of S_q S_q^T
+ * (q_z_covariances; its diagonal = q_z_variances, GMVAE:2881-2893).  L <= 128. */
+int scvae_gmvae_full_prior(const float *pz, int64_t ldp, int K, int L, float *pl, void *stream);
+int scvae_gmvae_latent_full_fwd(const float *qh, int64_t ldq, const float *pz, int64_t ldp,
+                                const float *pl, int K, int B, int L, int RS, const float *eps,
+                                float *z, int64_t ldz, float *klz, float *w, void *stream);
+int scvae_gmvae_latent_full_bwd(const float *qh, int64_t ldq, const float *pz, int64_t ldp,
+                                const float *pl, int K, int B, int L, int RS, const float *eps,
+                                const float *dz, int64_t lddz, const float *coef, const float *w,
+                                float *cu, float *dqh, int64_t lddq, float *dpz, int64_t lddp,
+                                void *stream);
+int scvae_gmvae_full_covariance_mean(const float *qh, int64_t ldq, int K, int B, int L, float *cov,
+                                     void *stream);
 /* go = -y[b,k]/(B RS) (gradient of the loss w.r.t. each row's log-likelihood),
  * coef = weight * y[b,k]/(B RS) (w.r.t. each row's KL_z); both [K*RS*B]. */
 int scvae_gmvae_row_coefficients(const float *y, int K, int RS, int B, float weight, float *go,

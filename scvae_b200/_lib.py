@@ -166,6 +166,12 @@ SIGNATURES = {
     "scvae_softmax_fwd": (c_int, [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "scvae_gmvae_latent_fwd": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr,
                                        c_i64, c_ptr, c_ptr, c_ptr]),
+    "scvae_gmvae_full_prior": (c_int, [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr]),
+    "scvae_gmvae_latent_full_fwd": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_int, c_int, c_int, c_int, c_ptr,
+                                            c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
+    "scvae_gmvae_latent_full_bwd": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_int, c_int, c_int, c_int, c_ptr,
+                                            c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
+    "scvae_gmvae_full_covariance_mean": (c_int, [c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_ptr]),
     "scvae_gmvae_latent_bwd": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr,
                                        c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "scvae_gmvae_row_coefficients": (c_int, [c_ptr, c_int, c_int, c_int, c_f32, c_ptr, c_ptr, c_ptr]),

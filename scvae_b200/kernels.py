@@ -538,6 +538,31 @@ def gmvae_latent_fwd(qh, pz, K_, B, L, RS, eps, z, klz, kl_elem=None):
                "gmvae_latent_fwd")
 
 
+def gmvae_full_prior(pz, K_, L, pl):
+    lib = _lib.load()
+    _lib.check(lib.scvae_gmvae_full_prior(_p(pz), _ld(pz), K_, L, _p(pl), _stream()), "gmvae_full_prior")
+
+
+def gmvae_latent_full_fwd(qh, pz, pl, K_, B, L, RS, eps, z, klz, w):
+    lib = _lib.load()
+    _lib.check(lib.scvae_gmvae_latent_full_fwd(_p(qh), _ld(qh), _p(pz), _ld(pz), _p(pl), K_, B, L, RS, _p(eps),
+                                               _p(z), _ld(z), _p(klz), _p(w), _stream()),
+               "gmvae_latent_full_fwd")
+
+
+def gmvae_latent_full_bwd(qh, pz, pl, K_, B, L, RS, eps, dz, coef, w, cu, dqh, dpz):
+    lib = _lib.load()
+    _lib.check(lib.scvae_gmvae_latent_full_bwd(_p(qh), _ld(qh), _p(pz), _ld(pz), _p(pl), K_, B, L, RS, _p(eps),
+                                               _p(dz), _ld(dz), _p(coef), _p(w), _p(cu), _p(dqh), _ld(dqh),
+                                               _p(dpz), _ld(dpz), _stream()), "gmvae_latent_full_bwd")
+
+
+def gmvae_full_covariance_mean(qh, K_, B, L, cov):
+    lib = _lib.load()
+    _lib.check(lib.scvae_gmvae_full_covariance_mean(_p(qh), _ld(qh), K_, B, L, _p(cov), _stream()),
+               "gmvae_full_covariance_mean")
+
+
 def gmvae_latent_bwd(qh, pz, K_, B, L, RS, eps, dz, coef, dqh, dpz):
     lib = _lib.load()
     _lib.check(lib.scvae_gmvae_latent_bwd(_p(qh), _ld(qh), _p(pz), K_, B, L, RS, _p(eps), _p(dz),

@@ -512,6 +512,61 @@ def gmvae_latent_bwd(qh, pz, K_, B, L, RS, eps, dz, coef, dqh, dpz):
     dpz[:K_, :2 * L] = gp
 
 
+def _gmvae_latent_full(qh, pz, K_, B, L, RS, eps):
+    """(z, kl) of the full-covariance mixture, rows ordered (k, rs, b), via the oracle's helpers."""
+    T = L * (L + 1) // 2
+    q_loc = qh[:K_ * B, :L].reshape(K_, 1, B, L)
+    q_tril = O.fill_triangular(torch.clamp(torch.nn.functional.softplus(qh[:K_ * B, L:L + T]),
+                                           min=O.F32_MIN)).reshape(K_, 1, B, L, L)
+    p_loc = pz[:K_, :L].reshape(K_, 1, 1, L)
+    p_tril = O.fill_triangular(torch.clamp(torch.nn.functional.softplus(pz[:K_, L:L + T]),
+                                           min=O.F32_MIN)).reshape(K_, 1, 1, L, L)
+    e = eps.reshape(-1)[:K_ * RS * B * L].double().reshape(K_, RS, B, L)
+    z = q_loc + (q_tril @ e.unsqueeze(-1)).squeeze(-1)
+    kl = O._mvn_log_prob(z, q_loc, q_tril) - O._mvn_log_prob(z, p_loc, p_tril)
+    return z, kl, p_tril
+
+
+def gmvae_full_prior(pz, K_, L, pl):
+    _log("gmvae_full_prior")
+    T = L * (L + 1) // 2
+    pl.reshape(-1)[:K_ * L * L] = O.fill_triangular(torch.clamp(torch.nn.functional.softplus(
+        pz[:K_, L:L + T].double()), min=O.F32_MIN)).reshape(-1)
+
+
+def gmvae_latent_full_fwd(qh, pz, pl, K_, B, L, RS, eps, z, klz, w):
+    _log("gmvae_latent_full_fwd")
+    zz, kl, p_tril = _gmvae_latent_full(qh.double(), pz.double(), K_, B, L, RS, eps)
+    M = K_ * RS * B
+    z[:M, :L] = zz.reshape(M, L)
+    z[:M, L] = 1.0
+    z[:M, L + 1:] = 0.0
+    klz[:M] = kl.reshape(M)
+    r = (zz - pz[:K_, :L].double().reshape(K_, 1, 1, L)).unsqueeze(-1)
+    w.reshape(-1)[:M * L] = torch.linalg.solve_triangular(
+        p_tril.expand(K_, RS, B, L, L), r, upper=False).reshape(-1)
+
+
+def gmvae_latent_full_bwd(qh, pz, pl, K_, B, L, RS, eps, dz, coef, w, cu, dqh, dpz):
+    _log("gmvae_latent_full_bwd")
+    M, T = K_ * RS * B, L * (L + 1) // 2
+    q_leaf = qh[:K_ * B, :L + T].double().detach().clone().requires_grad_(True)
+    p_leaf = pz[:K_, :L + T].double().detach().clone().requires_grad_(True)
+    zz, kl, _ = _gmvae_latent_full(q_leaf, p_leaf, K_, B, L, RS, eps)
+    total = (dz[:M, :L].double() * zz.reshape(M, L)).sum() + (coef[:M].double() * kl.reshape(M)).sum()
+    gq, gp = torch.autograd.grad(total, [q_leaf, p_leaf])
+    dqh[:K_ * B, :L + T] = gq
+    dpz[:K_, :L + T] = gp
+
+
+def gmvae_full_covariance_mean(qh, K_, B, L, cov):
+    _log("gmvae_full_covariance_mean")
+    T = L * (L + 1) // 2
+    tril = O.fill_triangular(torch.clamp(torch.nn.functional.softplus(qh[:K_ * B, L:L + T].double()),
+                                         min=O.F32_MIN)).reshape(K_, B, L, L)
+    cov.reshape(-1)[:K_ * L * L] = (tril @ tril.transpose(-1, -2)).mean(dim=1).reshape(-1)
+
+
 def gmvae_row_coefficients(y, K_, RS, B, weight, go, coef):
     _log("gmvae_row_coefficients")
     w = (y.reshape(-1)[:B * K_].double().reshape(B, K_).t() / (B * RS))     # (K, B)

@@ -204,3 +204,44 @@ def test_gmvae_piecewise_categorical(lik):
         assert got[k].shape == g.shape, (k, got[k].shape, g.shape)
         err = (got[k].double() - g).abs().max().item()
         assert err <= 3e-4 * g.abs().max().item() + 1e-5 * gmax, (k, err, g.abs().max().item())
+
+
+
+@pytest.mark.parametrize("K_,B,L,RS", [(3, 5, 4, 2), (4, 37, 50, 1), (2, 8, 33, 3)])
+def test_full_covariance_latent_kernels(K_, B, L, RS):
+    """csrc/gmvae_full.cu (multivariate-Gaussian q(z|x,y) / p(z|y), f4) against the autograd
+    restatement in tests/kernel_standins.py (fp64; fill_triangular, sampled KL with a triangular
+    solve, gradients w.r.t. the head pre-activations of both distributions, covariance means)."""
+    import kernel_standins as C
+    from scvae_b200 import kernels as K
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(K_ * 100 + L)
+    T = L * (L + 1) // 2
+    M = K_ * RS * B
+    ld = (L + T + 3) & ~3
+    qh = torch.zeros(K_ * B, ld)
+    qh[:, :L + T] = torch.randn(K_ * B, L + T, generator=gen) * 0.7
+    pz = torch.zeros(K_, ld)
+    pz[:, :L + T] = torch.randn(K_, L + T, generator=gen) * 0.7
+    eps = torch.randn(M, L, generator=gen)
+    dz = torch.zeros(M, (L + 4) & ~3)
+    dz[:, :L] = torch.randn(M, L, generator=gen) * 0.1
+    coef = torch.rand(M, generator=gen) * 0.05
+    Zp = (L + 4) & ~3
+
+    def run(mod, to):
+        pl = to(torch.zeros(K_, L, L))
+        z, klz, w, cu = to(torch.zeros(M, Zp)), to(torch.zeros(M)), to(torch.zeros(M, L)), to(torch.zeros(M, L))
+        dqh, dpz, cov = to(torch.zeros(K_ * B, ld)), to(torch.zeros(K_, ld)), to(torch.zeros(K_, L, L))
+        mod.gmvae_full_prior(to(pz), K_, L, pl)
+        mod.gmvae_latent_full_fwd(to(qh), to(pz), pl, K_, B, L, RS, to(eps), z, klz, w)
+        mod.gmvae_latent_full_bwd(to(qh), to(pz), pl, K_, B, L, RS, to(eps), to(dz), to(coef), w, cu, dqh, dpz)
+        mod.gmvae_full_covariance_mean(to(qh), K_, B, L, cov)
+        return [t.cpu().double() for t in (z, klz, w, dqh, dpz, cov, pl)]
+
+    got = run(K, lambda t: t.to(dev))
+    torch.cuda.synchronize()
+    want = run(C, lambda t: t.clone())
+    for name, g, r in zip(("z", "klz", "w", "dqh", "dpz", "cov", "pl"), got, want):
+        err = (g - r).abs().max().item()
+        assert err <= 2e-4 * max(r.abs().max().item(), 1.0), (name, err, r.abs().max().item())
