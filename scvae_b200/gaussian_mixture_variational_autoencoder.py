@@ -86,7 +86,7 @@ class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
         self.n_clusters = self.number_of_latent_clusters
         # the flag only affects the model name for the GMVAE (quirk Q8)
         self.analytical_kl_term = bool(kwargs.get("analytical_kl_term") or False)
-        if self.latent_distribution_name != "gaussian mixture":
+        if self.latent_distribution_name not in ("gaussian mixture", "full-covariance gaussian mixture"):
             raise NotImplementedError(
                 "Not on the B200 hot path yet (SURVEY §8 f4): latent distribution `{}`.".format(
                     self.latent_distribution_name))
@@ -155,7 +155,8 @@ class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
             number_of_batches=self.number_of_batches if self.batch_correction else 0,
             count_sum_feature=bool(self.use_count_sum_as_feature),
             number_of_reconstruction_classes=self.k_max,
-            dropout_keep_probabilities=self.dropout_keep_probabilities)
+            dropout_keep_probabilities=self.dropout_keep_probabilities,
+            latent_distribution=self.latent_distribution_name)
 
     def _evaluate_pass(self, engine, x_csr, t_csr, minibatch_size, R, S, deterministic=False,
                        seed=0, on_batch=None):
@@ -174,6 +175,8 @@ class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
         n_batches = -(-n // minibatch_size)
         log = torch.zeros(n_batches, 6, dtype=torch.float32, device=dev)
         stats = torch.zeros(n_batches, 2, Kc, L, dtype=torch.float32, device=dev)
+        full_cov = bool(getattr(engine, "full_cov", False))
+        q_cov = torch.zeros(n_batches, Kc, L, L, dtype=torch.float32, device=dev) if full_cov else None
         q_y_probabilities = torch.zeros(n_batches, Kc, dtype=torch.float32, device=dev)
         z_mean = torch.zeros(n, L, dtype=torch.float32, device=dev)
         y_mean = torch.zeros(n, Kc, dtype=torch.float32, device=dev)
@@ -200,18 +203,17 @@ class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
             qh = plan.QH.view(Kc, rows, -1)
             for k in range(Kc):
                 K.col_mean(qh[k], rows, L, stats[b, 0, k])
-            stats[b, 1].copy_(self._posterior_variances(plan, rows, L))
+            if full_cov:      # mean over the cells of S S^T; its diagonal = stddev^2 (GMVAE:2883-2893)
+                K.gmvae_full_covariance_mean(plan.QH, Kc, rows, L, q_cov[b])
+                stats[b, 1].copy_(torch.diagonal(q_cov[b], dim1=-2, dim2=-1))
+            else:
+                stats[b, 1].copy_(self._posterior_variances(plan, rows, L))
             if on_batch is not None:
                 on_batch(plan, i, rows)
         log = log.cpu().numpy().astype(numpy.float64)
         divisor = n / minibatch_size
         stats = stats.cpu().numpy().astype(numpy.float64).sum(axis=0) / divisor
-        prior = engine.export_parameters()
-        softplus = lambda a: numpy.log1p(numpy.exp(-numpy.abs(a))) + numpy.maximum(a, 0)
-        p_mean = (prior["Z/P/SOFTPLUS_GAUSSIAN/MEAN/DENSE/weights"]
-                  + prior["Z/P/SOFTPLUS_GAUSSIAN/MEAN/DENSE/biases"]).numpy()
-        p_var = softplus((prior["Z/P/SOFTPLUS_GAUSSIAN/SOFTPLUS_SCALE/DENSE/weights"]
-                          + prior["Z/P/SOFTPLUS_GAUSSIAN/SOFTPLUS_SCALE/DENSE/biases"]).numpy())
+        p_mean, p_var, p_cov, _ = self._prior_moments(engine)
         result = {
             "lower_bound": log[:, 0].sum() / divisor,
             "reconstruction_error": log[:, 2].sum() / divisor,
@@ -224,9 +226,37 @@ class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
             "p_y_probabilities": numpy.exp(engine.log_py.cpu().numpy()),
             "p_z_means": p_mean, "p_z_variances": p_var,
         }
+        if full_cov:
+            result["q_z_covariances"] = q_cov.cpu().numpy().astype(numpy.float64).sum(axis=0) / divisor
+            result["p_z_covariances"] = p_cov
         result["kl_divergence"] = result["kl_divergence_z"] + result["kl_divergence_y"]
         result["kl_divergence_neurons"] = numpy.array([result["kl_divergence"]])  # GMVAE:3401
         return result
+
+    @staticmethod
+    def _fill_triangular(scales):
+        """tfp.distributions.fill_triangular (lower) on a (K, L (L + 1) / 2) numpy array."""
+        m = scales.shape[-1]
+        n = int(round((numpy.sqrt(8 * m + 1) - 1) / 2))
+        full = numpy.concatenate([scales[..., n:], scales[..., ::-1]], axis=-1)
+        return numpy.tril(full.reshape(scales.shape[:-1] + (n, n)))
+
+    def _prior_moments(self, engine):
+        """(means (K, L), variances (K, L), covariances (K, L, L) or None, scale matrices or
+        None) of p(z|y=k) from the variables (GMVAE:2877-2893; K * L-sized host glue)."""
+        prior = engine.export_parameters()
+        softplus = lambda a: numpy.log1p(numpy.exp(-numpy.abs(a))) + numpy.maximum(a, 0)
+        base = "Z/P/{}/".format(engine.z_scope)
+
+        def head(name):
+            return (prior[base + name + "/DENSE/weights"] + prior[base + name + "/DENSE/biases"]).numpy()
+        means = head(engine.z_heads[0])
+        if engine.full_cov:
+            tril = self._fill_triangular(numpy.maximum(softplus(head("SCALES").astype(numpy.float64)),
+                                                       numpy.finfo(numpy.float32).tiny))
+            cov = tril @ numpy.swapaxes(tril, -1, -2)
+            return means, numpy.diagonal(cov, axis1=-2, axis2=-1).copy(), cov, tril
+        return means, softplus(head("SOFTPLUS_SCALE")), None, None
 
     @staticmethod
     def _posterior_variances(plan, rows, L):
@@ -275,16 +305,22 @@ class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
                         result[key + "_means"][k, l]
                     scalars["{}/cluster_{}/variance/dimension_{}".format(dist, k, l)] = \
                         result[key + "_variances"][k, l]
+                    if key + "_covariances" in result:          # GMVAE:1406-1417
+                        for l_ in range(self.latent_size):
+                            scalars["{}/cluster_{}/covariance/dimension_{}_{}".format(dist, k, l, l_)] = \
+                                result[key + "_covariances"][k, l, l_]
         return scalars
 
     def _centroids(self, result):
-        def pack(probabilities, means, variances):
+        def pack(probabilities, means, variances, covariances):
+            if covariances is None:                             # GMVAE:1837-1859
+                covariances = numpy.stack([numpy.diag(v) for v in variances])
             return {"probabilities": probabilities, "means": means,
-                    "covariance_matrices": numpy.stack([numpy.diag(v) for v in variances])}
+                    "covariance_matrices": covariances}
         return {"prior": pack(result["p_y_probabilities"], result["p_z_means"],
-                              result["p_z_variances"]),
+                              result["p_z_variances"], result.get("p_z_covariances")),
                 "posterior": pack(result["q_y_probabilities"], result["q_z_means"],
-                                  result["q_z_variances"])}
+                                  result["q_z_variances"], result.get("q_z_covariances"))}
 
     def _latent_sets(self, evaluation_set, result, common):
         L, Kc = self.latent_size, self.number_of_latent_clusters
@@ -319,15 +355,12 @@ class GaussianMixtureVariationalAutoencoder(VariationalAutoencoder):
         rng = numpy.random.RandomState(kwargs.get("noise_seed", 11))
         p_y = numpy.exp(engine.log_py.cpu().numpy().astype(numpy.float64))
         clusters = rng.choice(Kc, size=sample_size, p=p_y / p_y.sum())
-        prior = engine.export_parameters()
-        softplus = lambda a: numpy.log1p(numpy.exp(-numpy.abs(a))) + numpy.maximum(a, 0)
-        means = (prior["Z/P/SOFTPLUS_GAUSSIAN/MEAN/DENSE/weights"]
-                 + prior["Z/P/SOFTPLUS_GAUSSIAN/MEAN/DENSE/biases"]).numpy()
-        scales = numpy.sqrt(softplus((prior["Z/P/SOFTPLUS_GAUSSIAN/SOFTPLUS_SCALE/DENSE/weights"]
-                                      + prior["Z/P/SOFTPLUS_GAUSSIAN/SOFTPLUS_SCALE/DENSE/biases"])
-                                     .numpy()))
-        z = (means[clusters] + scales[clusters] * rng.standard_normal((sample_size, L))).astype(
-            numpy.float32)
+        means, variances, _, tril = self._prior_moments(engine)
+        noise = rng.standard_normal((sample_size, L))
+        if tril is not None:          # z = loc + S eps
+            z = (means[clusters] + numpy.einsum("nij,nj->ni", tril[clusters], noise)).astype(numpy.float32)
+        else:
+            z = (means[clusters] + numpy.sqrt(variances)[clusters] * noise).astype(numpy.float32)
         x = numpy.empty((sample_size, G), numpy.float32)
         from .engine import VAEEngine
         for i in range(0, sample_size, minibatch_size):

@@ -31,7 +31,7 @@ class GMVAEEngine(VAEEngine):
                  proportion_of_free_nats_for_y_kl_divergence=0.0, device="cuda", seed=0,
                  tensor_cores=True, head_buffer_bytes=4 << 30, number_of_batches=0,
                  count_sum_feature=False, number_of_reconstruction_classes=0,
-                 dropout_keep_probabilities=None):
+                 dropout_keep_probabilities=None, latent_distribution="gaussian mixture"):
         if reconstruction_distribution not in K.LIKELIHOOD_KINDS:
             raise ValueError("reconstruction distribution `{}` is not supported by the "
                              "B200 hot path".format(reconstruction_distribution))
@@ -97,7 +97,22 @@ class GMVAEEngine(VAEEngine):
         if self.k_max or self.constrained or self.continuous:
             self.fused_heads = False
         self.unit_variance = False
-        self.nL = 2 * self.L
+        # "gaussian mixture": softplus Gaussians, heads [mean | softplus_scale];
+        # "full-covariance gaussian mixture": multivariate Gaussians with a lower-triangular scale,
+        # heads [locations | L (L + 1) / 2 scales] (DU:75-93, :345-348; csrc/gmvae_full.cu)
+        if latent_distribution not in ("gaussian mixture", "full-covariance gaussian mixture"):
+            raise ValueError("unknown GMVAE latent distribution `{}`".format(latent_distribution))
+        self.full_cov = latent_distribution.startswith("full-covariance")
+        self.T = self.L * (self.L + 1) // 2
+        self.nL = self.L + self.T if self.full_cov else 2 * self.L      # head pre-activations per row
+        if self.full_cov:
+            if self.L > 128:
+                raise ValueError("the full-covariance mixture is built for latent sizes <= 128")
+            if self.keep_h is not None or self.keep_y is not None:
+                raise NotImplementedError("hidden / y dropout around the full-covariance mixture heads")
+        self.z_scope = "MULTIVARIATE_GAUSSIAN" if self.full_cov else "SOFTPLUS_GAUSSIAN"
+        self.z_heads = ("LOCATIONS", "SCALES") if self.full_cov else ("MEAN", "SOFTPLUS_SCALE")
+        self.z_head_cols = [slice(0, self.L), slice(self.L, self.nL)]
 
         def stack(prefix, first_in):
             layers, width = [], first_in
@@ -109,7 +124,7 @@ class GMVAEEngine(VAEEngine):
         self.qy_enc, width = stack("Y/CATEGORICAL/ENCODER", self.G)
         self.qy_logits = _Layer("Y/CATEGORICAL/LOGITS", width, self.K, False)
         self.qz_enc, width = stack("Z/Q/ENCODER", self.G)
-        self.qz_head = _Layer("Z/Q/SOFTPLUS_GAUSSIAN", width, 2 * self.L, False)
+        self.qz_head = _Layer("Z/Q/" + self.z_scope, width, self.nL, False)
         self.dec, width = [], self.L
         for i, h in enumerate(self.hidden_sizes[::-1]):
             self.dec.append(_Layer("X/DECODER/LAYER_{}".format(i + 1), width, h, self.bn,
@@ -127,8 +142,8 @@ class GMVAEEngine(VAEEngine):
             if layer.bn:
                 store.add(layer.name + "/beta", (layer.n_out,))
         store.add("Z/Q/WY", (self.K, H1p))            # rows of LAYER_1 weights acting on e_k
-        store.add("Z/P/W", (self.K, 2 * self.L))      # p(z|y): [mean | softplus_scale] weights
-        store.add("Z/P/B", (1, 2 * self.L))
+        store.add("Z/P/W", (self.K, self.nL))         # p(z|y): [mean | softplus_scale] weights
+        store.add("Z/P/B", (1, self.nL))
         if self.prior_method == "learn":
             store.add("Y/P/LOGITS", (self.K,))
         store.allocate()
@@ -167,10 +182,10 @@ class GMVAEEngine(VAEEngine):
         out.append((self.qy_logits, slice(0, self.K), self.qy_logits.name, slice(0, self.qy_logits.n_in)))
         for layer in self.qz_enc:
             out.append((layer, slice(0, layer.n_out), layer.name, slice(0, layer.n_in)))
-        base = "Z/Q/SOFTPLUS_GAUSSIAN/"
+        base = "Z/Q/{}/".format(self.z_scope)
         n_in = self.qz_head.n_in
-        out.append((self.qz_head, slice(0, self.L), base + "MEAN", slice(0, n_in)))
-        out.append((self.qz_head, slice(self.L, 2 * self.L), base + "SOFTPLUS_SCALE", slice(0, n_in)))
+        for name, cols in zip(self.z_heads, self.z_head_cols):
+            out.append((self.qz_head, cols, base + name, slice(0, n_in)))
         return out
 
     def _tf_tail(self):
@@ -195,10 +210,11 @@ class GMVAEEngine(VAEEngine):
             fan_in = layer.n_in + (self.K if scope == "Z/Q/ENCODER/LAYER_1" else 0)
             params[scope + "/DENSE/weights"] = xavier(fan_in, rows.stop - rows.start)
             params[scope + "/DENSE/biases"] = torch.zeros(rows.stop - rows.start)
-            if scope == "Z/Q/SOFTPLUS_GAUSSIAN/SOFTPLUS_SCALE":
-                for name in ("MEAN", "SOFTPLUS_SCALE"):
-                    params["Z/P/SOFTPLUS_GAUSSIAN/{}/DENSE/weights".format(name)] = xavier(self.K, self.L)
-                    params["Z/P/SOFTPLUS_GAUSSIAN/{}/DENSE/biases".format(name)] = torch.zeros(self.L)
+            if scope == "Z/Q/{}/{}".format(self.z_scope, self.z_heads[1]):
+                for name, cols in zip(self.z_heads, self.z_head_cols):
+                    width = cols.stop - cols.start
+                    params["Z/P/{}/{}/DENSE/weights".format(self.z_scope, name)] = xavier(self.K, width)
+                    params["Z/P/{}/{}/DENSE/biases".format(self.z_scope, name)] = torch.zeros(width)
         for layer, rows, scope, _ in self._tf_tail():
             params[scope + "/DENSE/weights"] = xavier(layer.n_in + layer.n_extra, rows.stop - rows.start)
             params[scope + "/DENSE/biases"] = torch.zeros(rows.stop - rows.start)
@@ -246,9 +262,8 @@ class GMVAEEngine(VAEEngine):
                 layer.w[rows, :layer.n_in] = w[:, c::K1].t()
                 layer.w[rows, layer.n_in] = b[c::K1]
                 layer.w[rows, layer.n_in + 1:] = 0
-        for j, name in enumerate(("MEAN", "SOFTPLUS_SCALE")):
-            cols = slice(j * self.L, (j + 1) * self.L)
-            scope = "Z/P/SOFTPLUS_GAUSSIAN/" + name
+        for name, cols in zip(self.z_heads, self.z_head_cols):
+            scope = "Z/P/{}/{}".format(self.z_scope, name)
             self.pz_w[:, cols] = params[scope + "/DENSE/weights"].to(dev, torch.float32)
             self.pz_b[0, cols] = params[scope + "/DENSE/biases"].to(dev, torch.float32)
         if self.prior_method == "learn" and "Y/P/LOGITS" in params:
@@ -275,9 +290,8 @@ class GMVAEEngine(VAEEngine):
 
         for layer, rows, scope, _ in self._tf_dense():
             dense(layer, rows, scope)
-        for j, name in enumerate(("MEAN", "SOFTPLUS_SCALE")):
-            cols = slice(j * self.L, (j + 1) * self.L)
-            scope = "Z/P/SOFTPLUS_GAUSSIAN/" + name
+        for name, cols in zip(self.z_heads, self.z_head_cols):
+            scope = "Z/P/{}/{}".format(self.z_scope, name)
             out[scope + "/DENSE/weights"] = (self.d_pz_w if grads else self.pz_w)[:, cols].cpu().clone()
             out[scope + "/DENSE/biases"] = (self.d_pz_b if grads else self.pz_b)[0, cols].cpu().clone()
         for layer, rows, scope, _ in self._tf_tail():
@@ -331,8 +345,11 @@ class GMVAEEngine(VAEEngine):
         p.qzH = [zeros(KB, aug(l.n_out)) for l in self.qz_enc]
         p.qz_mean = [zeros(Kc * l.n_out) for l in self.qz_enc]
         p.qz_rstd = [zeros(Kc * l.n_out) for l in self.qz_enc]
-        p.QH = zeros(KB, round4(2 * L))
-        p.PZ = zeros(Kc, 2 * L)
+        p.QH = zeros(KB, round4(self.nL))
+        p.PZ = zeros(Kc, self.nL)
+        if self.full_cov:      # activated prior scale matrices, S_p^-1 (z - loc_p) of every row
+            p.PL = zeros(Kc, L, L)
+            p.Wsol = zeros(M, L)
         p.eps = zeros(M, L)
         p.Z = zeros(M, self.Zp)
         p.batch_index = zeros(B) if self.number_of_batches else None
@@ -387,8 +404,10 @@ class GMVAEEngine(VAEEngine):
         p.d_decH = [zeros(Mc, aug(l.n_out)) for l in self.dec]
         p.d_decY = [zeros(Mc, round4(l.n_out)) for l in self.dec]
         p.dZ = zeros(M, self.Zp)
-        p.dQH = zeros(KB, round4(2 * L))
-        p.dPZ = zeros(Kc, 2 * L)
+        p.dQH = zeros(KB, round4(self.nL))
+        p.dPZ = zeros(Kc, self.nL)
+        if self.full_cov:
+            p.CU = zeros(M, L)
         p.d_qzH = [zeros(KB, aug(l.n_out)) for l in self.qz_enc]
         p.d_qzY = [zeros(KB, round4(l.n_out)) for l in self.qz_enc]
         p.dXW = zeros(B, round4(self.hidden_sizes[0]))
@@ -619,8 +638,12 @@ class GMVAEEngine(VAEEngine):
             self._gemm(p, K.GEMM_NT, KB, l.n_out, l.n_in + 1, p.qzH[-1], l.w, p.QH)
         # --- p(z|y=k) = FC(e_k) ---------------------------------------------------------------
         pz_w = self._pz_scales(p) if (drop and self.keep_y) else self.pz_w
-        K.group_offset_fwd(self.pz_b, pz_w, Kc, 1, 2 * L, p.PZ)
-        K.gmvae_latent_fwd(p.QH, p.PZ, Kc, B, L, RS, p.eps, p.Z, p.klz, p.kl_elem)
+        K.group_offset_fwd(self.pz_b, pz_w, Kc, 1, self.nL, p.PZ)
+        if self.full_cov:
+            K.gmvae_full_prior(p.PZ, Kc, L, p.PL)
+            K.gmvae_latent_full_fwd(p.QH, p.PZ, p.PL, Kc, B, L, RS, p.eps, p.Z, p.klz, p.Wsol)
+        else:
+            K.gmvae_latent_fwd(p.QH, p.PZ, Kc, B, L, RS, p.eps, p.Z, p.klz, p.kl_elem)
         self._decoder_features(p, p.M)
         K.gmvae_row_coefficients(p.y, Kc, RS, B, weight, p.go, p.coef)
         # --- p(x|z_k): decoder + heads + likelihood, cluster chunk by cluster chunk -----------
@@ -753,14 +776,18 @@ class GMVAEEngine(VAEEngine):
     def backward(self, p, R, S, warm_up_weight=1.0):
         """Everything upstream of z (the decoder part already ran chunk-wise in forward)."""
         B, Kc, L, RS, KB = p.B, self.K, self.L, p.RS, p.KB
-        K.gmvae_latent_bwd(p.QH, p.PZ, Kc, B, L, RS, p.eps, p.dZ, p.coef, p.dQH, p.dPZ)
+        if self.full_cov:
+            K.gmvae_latent_full_bwd(p.QH, p.PZ, p.PL, Kc, B, L, RS, p.eps, p.dZ, p.coef, p.Wsol, p.CU,
+                                    p.dQH, p.dPZ)
+        else:
+            K.gmvae_latent_bwd(p.QH, p.PZ, Kc, B, L, RS, p.eps, p.dZ, p.coef, p.dQH, p.dPZ)
         # p(z|y) parameters: W[k] gets dPZ[k], the shared bias their sum
         drop = p.drop_on
         if drop and self.keep_y:
             torch.mul(p.dPZ, p.pz_scale, out=self.d_pz_w)     # W[k] enters as (mask_kk / keep) W[k]
         else:
             self.d_pz_w.copy_(p.dPZ)
-        K.group_offset_bwd(p.dPZ, 1, Kc, 2 * L, dt=self.d_pz_b)
+        K.group_offset_bwd(p.dPZ, 1, Kc, self.nL, dt=self.d_pz_b)
         # q(z|x,y) encoder on K*B rows
         l = self.qz_head
         if drop and self.keep_h:

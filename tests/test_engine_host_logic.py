@@ -313,3 +313,57 @@ def test_gmvae_engine_dropout_against_the_oracle(engine_on_cpu, head_buffer_byte
     ref_eval = O.gmvae_forward(cfg, now, x, x, eps, is_training=False)
     assert abs(plan.bound[0].item() - ref_eval["lower_bound"].item()) <= 5e-5 * abs(
         ref_eval["lower_bound"].item())
+
+
+@pytest.mark.parametrize("head_buffer_bytes,lik,R,S,prior", [
+    (4 << 30, "negative binomial", 1, 2, "uniform"),
+    (20000, "poisson", 2, 1, "learn"),                    # chunked decoder, learnt prior
+])
+def test_gmvae_engine_full_covariance_mixture_against_the_oracle(engine_on_cpu, head_buffer_bytes, lik,
+                                                                 R, S, prior):
+    """`-q "full-covariance gaussian mixture"` (f4; DU:75-93, multivariate_normal.py:90-150):
+    multivariate-Gaussian q(z|x,y) / p(z|y) heads with fill_triangular scale matrices through the
+    engine -- bound terms, gradients of every variable (incl. the L (L + 1) / 2 scale heads of both
+    distributions), post-Adam variables, evaluation -- against the oracle at odd shapes."""
+    import numpy
+    from oracle import scvae_oracle as O
+    from scvae_b200.gmvae_engine import GMVAEEngine
+    G, L, Kc, hidden, B = 37, 3, 4, [7, 5], 9
+    name = "full-covariance gaussian mixture"
+    cfg = O.GMVAEConfig(G, L, Kc, hidden, lik, R, S, True, kl_weight=0.8,
+                        prior_probabilities_method=prior, latent_distribution=name)
+    params = O.gmvae_init_params(cfg, seed=3, dtype=torch.float64)
+    gen = torch.Generator().manual_seed(4)
+    for k in params:
+        if k.endswith("biases") or k.endswith("beta") or k == "Y/P/LOGITS":
+            params[k] = torch.randn(params[k].shape, generator=gen, dtype=torch.float64) * 0.2
+    assert params["Z/Q/MULTIVARIATE_GAUSSIAN/SCALES/DENSE/weights"].shape == (5, 6)
+    x = torch.tensor(numpy.minimum(O.synthetic_counts(B, G, n_types=3, seed=5)[0], 40.0),
+                     dtype=torch.float64)
+    eps = torch.randn(Kc, R * S, B, L, generator=gen, dtype=torch.float64)
+    state = O.AdamState(params)
+    reference = {k: v.clone() for k, v in params.items()}
+    out, grads = O.train_step(cfg, reference, state, x, x, eps, 1e-3, warm_up_weight=0.7)
+    eng = GMVAEEngine(G, L, Kc, hidden, lik, True, 0.8, prior, None, 0.0, tensor_cores=False,
+                      head_buffer_bytes=head_buffer_bytes, latent_distribution=name)
+    eng.import_parameters(params)
+    assert sorted(eng.export_parameters()) == sorted(params)          # same variables, same names
+    plan = eng._plan(B, R * S)
+    eng.set_batch_dense(plan, x.float())
+    plan.eps.copy_(eps.reshape(-1, L).float())
+    bound = eng.train_step(plan, R, S, 1e-3, warm_up_weight=0.7)
+    for i, key in enumerate(["lower_bound", "lower_bound_weighted", "reconstruction_error",
+                             "kl_divergence_z", "kl_divergence_y"]):
+        assert abs(bound[i].item() - out[key].item()) <= 5e-5 * abs(out[key].item()) + 1e-6, key
+    got = eng.export_gradients()
+    gmax = max(g.abs().max().item() for g in grads.values())
+    for key, g in grads.items():
+        error = (got[key].double() - g).abs().max().item()
+        assert error <= 3e-4 * g.abs().max().item() + 1e-5 * gmax, (key, error)
+    eng.forward(plan, False, R, S, 1.0)
+    now = {k: v.double() for k, v in eng.export_parameters().items()}
+    ref_eval = O.gmvae_forward(cfg, now, x, x, eps, is_training=False)
+    assert abs(plan.bound[0].item() - ref_eval["lower_bound"].item()) <= 5e-5 * abs(
+        ref_eval["lower_bound"].item())
+    z_mean = eng.z_mean(plan)
+    assert (z_mean.double() - ref_eval["z_mean"]).abs().max().item() <= 1e-4

@@ -362,3 +362,34 @@ def test_evaluate_streams_the_reconstruction_to_the_host(tmp_path, dtype):
         ref = out["p_x_stddev"][i].numpy()
         assert numpy.abs(got - ref).max() <= 2e-4 * max(1.0, numpy.abs(ref).max())
     assert total[2].toarray().max() == 0
+
+
+
+def test_gmvae_full_covariance_mixture_train_evaluate_sample(tmp_path):
+    """`-q "full-covariance gaussian mixture"` end to end (f4): train, per-epoch centroid tags with
+    covariances, evaluate, sample."""
+    from scvae_b200.gaussian_mixture_variational_autoencoder import (
+        GaussianMixtureVariationalAutoencoder)
+    from scvae_b200 import model_utilities as MU
+    full = _data(n=240, g=40, seed=6)
+    training, validation, test = full.split()
+    model = GaussianMixtureVariationalAutoencoder(
+        feature_size=40, latent_size=3, hidden_sizes=[16], number_of_latent_clusters=3,
+        latent_distribution="full-covariance gaussian mixture",
+        reconstruction_distribution="negative binomial", log_directory=str(tmp_path), seed=1)
+    assert "full_covariance_gaussian_mixture" in model.name.replace("-", "_")
+    assert model.train(training, validation, number_of_epochs=3, minibatch_size=48,
+                       learning_rate=1e-2, shuffle_seed=0) == 0
+    curve = MU.load_learning_curves(model, "training")["lower_bound"]
+    assert len(curve) == 3 and numpy.isfinite(curve).all()
+    transformed, reconstructed, latent = model.evaluate(test, minibatch_size=32)
+    assert numpy.isfinite(reconstructed.values).all()
+    assert latent["z"].values.shape == (test.number_of_examples, 3)
+    result = model.last_evaluation
+    cov = result["q_z_covariances"]
+    assert cov.shape == (3, 3, 3) and numpy.allclose(cov, numpy.swapaxes(cov, 1, 2), atol=1e-6)
+    assert numpy.allclose(numpy.diagonal(cov, axis1=1, axis2=2), result["q_z_variances"], rtol=1e-5)
+    assert (numpy.linalg.eigvalsh(result["p_z_covariances"]) > 0).all()
+    centroids = MU.load_centroids(model, "evaluation") if hasattr(MU, "load_centroids") else None
+    sample_set, sample_latent = model.sample(sample_size=21, minibatch_size=8)
+    assert sample_set.values.shape == (21, 40) and numpy.isfinite(sample_set.values).all()

@@ -130,3 +130,10 @@ def test_gmvae_free_nats_on_cpu(shell_on_cpu, tmp_path, prior):
 def test_continuous_likelihoods_through_the_model_class_on_cpu(shell_on_cpu, tmp_path, likelihood):
     G.test_train_evaluate_with_continuous_likelihoods(tmp_path, likelihood)
     assert "continuous_likelihood" in shell_on_cpu and "continuous_moments" in shell_on_cpu
+
+
+
+def test_gmvae_full_covariance_mixture_on_cpu(shell_on_cpu, tmp_path):
+    G.test_gmvae_full_covariance_mixture_train_evaluate_sample(tmp_path)
+    assert "gmvae_latent_full_fwd" in shell_on_cpu and "gmvae_latent_full_bwd" in shell_on_cpu
+    assert "gmvae_full_covariance_mean" in shell_on_cpu
