@@ -186,6 +186,14 @@ CASES = [
     ("gmvae_nb_dropout_train", "GMVAE",
      dict(reconstruction_distribution="negative binomial", number_of_latent_clusters=3,
           hidden_sizes=[8, 5], dropout_keep_probabilities=[0.8, 0.9, 0.7, 0.6]), dict(R=1, S=2)),
+    # multivariate-Gaussian q(z|x,y) / p(z|y) with fill_triangular scale matrices (DU:75-93,
+    # multivariate_normal.py:90-150)
+    ("gmvae_nb_full_covariance_train", "GMVAE",
+     dict(reconstruction_distribution="negative binomial", number_of_latent_clusters=3,
+          latent_distribution="full-covariance gaussian mixture"), dict(R=1, S=2)),
+    ("gmvae_poisson_full_covariance_eval", "GMVAE",
+     dict(reconstruction_distribution="poisson", number_of_latent_clusters=2,
+          latent_distribution="full-covariance gaussian mixture"), dict(is_training=False, R=2, S=1)),
     ("gmvae_constrained_poisson_train", "GMVAE",
      dict(reconstruction_distribution="constrained poisson", number_of_latent_clusters=3),
      dict(R=1, S=2)),

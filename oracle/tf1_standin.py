@@ -678,8 +678,64 @@ class MultivariateNormalDiag(_NotBuilt):
     pass
 
 
-class MultivariateNormalTriL(_NotBuilt):
-    pass
+def fill_triangular(x, upper=False, name=None):
+    """tfp.distributions.fill_triangular (TFP 0.7): reshape(concat(x[n:], reverse(x)), (n, n)),
+    lower (or upper) triangle kept; [1..6] -> [[4, 0, 0], [6, 5, 0], [3, 2, 1]]."""
+    x = _t(x, STATE.dtype)
+    m = x.shape[-1]
+    n = int(round((math.sqrt(8 * m + 1) - 1) / 2))
+    assert n * (n + 1) // 2 == m, "fill_triangular: not a triangular number"
+    if upper:
+        full = torch.cat([x, torch.flip(x[..., n:], dims=[-1])], dim=-1).reshape(x.shape[:-1] + (n, n))
+        return torch.triu(full)
+    full = torch.cat([x[..., n:], torch.flip(x, dims=[-1])], dim=-1).reshape(x.shape[:-1] + (n, n))
+    return torch.tril(full)
+
+
+class MultivariateNormalTriL(Distribution):
+    """tfd.MultivariateNormalTriL: loc (..., d), scale_tril (..., d, d); batch shape = the broadcast of
+    loc.shape[:-1] and scale_tril.shape[:-2], event shape (d,)."""
+
+    def __init__(self, loc=None, scale_tril=None, validate_args=False, allow_nan_stats=True,
+                 name="MultivariateNormalTriL"):
+        super().__init__(dtype=float32, graph_parents=[loc, scale_tril], name=name)
+        self.loc, self.scale_tril = _t(loc, STATE.dtype), _t(scale_tril, STATE.dtype)
+        self.d = self.scale_tril.shape[-1]
+
+    def _batch_shape(self):
+        return _Shape(torch.broadcast_shapes(self.loc.shape[:-1], self.scale_tril.shape[:-2]))
+
+    def _batch_shape_tensor(self):
+        return tuple(self._batch_shape())
+
+    def _event_shape(self):
+        return _Shape((self.d,))
+
+    def _mean(self):
+        return self.loc.expand(tuple(self._batch_shape()) + (self.d,))
+
+    def covariance(self, name=None):
+        cov = self.scale_tril @ self.scale_tril.transpose(-1, -2)
+        return cov.expand(tuple(self._batch_shape()) + (self.d, self.d))
+
+    def _variance(self):
+        return torch.diagonal(self.covariance(), dim1=-2, dim2=-1)
+
+    def _log_prob(self, x):
+        shape = torch.broadcast_shapes(x.shape[:-1], tuple(self._batch_shape()))
+        r = (x - self.loc).expand(shape + (self.d,)).unsqueeze(-1)
+        tril = self.scale_tril.expand(shape + (self.d, self.d))
+        y = torch.linalg.solve_triangular(tril, r, upper=False).squeeze(-1)
+        log_det = torch.log(torch.abs(torch.diagonal(tril, dim1=-2, dim2=-1))).sum(dim=-1)
+        return -0.5 * (y * y).sum(dim=-1) - log_det - 0.5 * self.d * math.log(2.0 * math.pi)
+
+    def _sample(self, sample_shape):
+        shape = tuple(sample_shape) + tuple(self._batch_shape()) + (self.d,)
+        if STATE.noise:
+            eps = _t(STATE.noise.pop(0), STATE.dtype).reshape(shape)
+        else:
+            eps = torch.randn(shape, generator=STATE.generator, dtype=STATE.dtype)
+        return self.loc + (self.scale_tril @ eps.unsqueeze(-1)).squeeze(-1)
 
 
 class MultivariateNormalFullCovariance(_NotBuilt):
@@ -773,7 +829,8 @@ def install():
         NegativeBinomial=NegativeBinomial, Categorical=Categorical, kl_divergence=kl_divergence,
         Distribution=Distribution, MultivariateNormalDiag=MultivariateNormalDiag,
         MultivariateNormalTriL=MultivariateNormalTriL,
-        MultivariateNormalFullCovariance=MultivariateNormalFullCovariance)
+        MultivariateNormalFullCovariance=MultivariateNormalFullCovariance,
+        fill_triangular=fill_triangular)
     tfp = _module("tensorflow_probability", distributions=distributions)
     tfp.python = _module("tensorflow_probability.python")
     _module("tensorflow_probability.python.distributions")

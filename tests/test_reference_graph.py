@@ -61,7 +61,8 @@ def oracle_config(meta):
             prior_probabilities=kw.get("prior_probabilities"),
             proportion_of_free_nats_for_y_kl_divergence=kw.get(
                 "proportion_of_free_nats_for_y_kl_divergence", 0.0),
-            dropout_keep_probabilities=kw.get("dropout_keep_probabilities"), **common)
+            dropout_keep_probabilities=kw.get("dropout_keep_probabilities"),
+            latent_distribution=kw.get("latent_distribution", "gaussian mixture"), **common)
     return O.VAEConfig(
         latent_distribution=kw.get("latent_distribution", "gaussian"),
         # VAE:186-192: analytic KL by default only for the plain gaussian latent distribution
@@ -320,7 +321,8 @@ def _engine_for(meta, device="cpu"):
             kw.get("kl_weight", 1.0), kw.get("prior_probabilities_method", "uniform"),
             kw.get("prior_probabilities"),
             kw.get("proportion_of_free_nats_for_y_kl_divergence", 0.0), device=device,
-            tensor_cores=False, **extras)
+            tensor_cores=False, latent_distribution=kw.get("latent_distribution", "gaussian mixture"),
+            **extras)
     from scvae_b200.engine import VAEEngine
     return VAEEngine(
         meta["G"], kw["latent_size"], kw["hidden_sizes"], kw["reconstruction_distribution"],

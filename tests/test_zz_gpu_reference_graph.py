@@ -29,8 +29,9 @@ VAE_EVAL = ["vae_c1_poisson_eval", "vae_nb_eval", "vae_nb_eval_deterministic", "
 # batch norm -- come last)
 GMVAE_TRAIN = ["gmvae_nb_train", "gmvae_zinb_train_mc", "gmvae_poisson_learn_train",
                "gmvae_nb_free_nats_train", "gmvae_nb_k2_train", "gmvae_nb_bc_count_sum_train",
-               "gmvae_nb_custom_prior_train", "gmvae_nb_dropout_train"]
-GMVAE_EVAL = ["gmvae_nb_eval", "gmvae_nb_no_bn_eval"]
+               "gmvae_nb_custom_prior_train", "gmvae_nb_dropout_train",
+               "gmvae_nb_full_covariance_train"]
+GMVAE_EVAL = ["gmvae_nb_eval", "gmvae_nb_no_bn_eval", "gmvae_poisson_full_covariance_eval"]
 
 
 def _rel(got, want):
@@ -181,7 +182,8 @@ def _gmvae(name):
         number_of_batches=kw.get("number_of_batches", 0) if kw.get("batch_correction") else 0,
         count_sum_feature=kw.get("count_sum", False),
         number_of_reconstruction_classes=kw.get("number_of_reconstruction_classes", 0),
-        dropout_keep_probabilities=kw.get("dropout_keep_probabilities"))
+        dropout_keep_probabilities=kw.get("dropout_keep_probabilities"),
+        latent_distribution=kw.get("latent_distribution", "gaussian mixture"))
     eng.import_parameters(_params(meta, groups))
     feeds = groups["in_feed"]
     B = feeds["X"].shape[0]
