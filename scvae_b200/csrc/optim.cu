@@ -164,8 +164,10 @@ __global__ void step_advance_kernel(int64_t *step) { *step += 1; }
 }  // namespace scvae
 
 static int64_t adam_blocks(int64_t n) {
-    int64_t blocks = (n + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    int64_t blocks = ((n >> 2) + 255) / 256;       // one float4 per thread and trip
+    // at most four CTAs per SM, all resident at once: the double-precision step-size prologue of a CTA
+    // is then paid once per launch, not once per wave
+    if (blocks > 148 * 4) blocks = 148 * 4;
     return blocks < 1 ? 1 : blocks;
 }
 

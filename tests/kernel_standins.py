@@ -417,7 +417,7 @@ def col_mean(x, rows, cols, out):
 
 
 def adam_clip_ctas(n):
-    return max(1, min((int(n) + 255) // 256, 148 * 16))
+    return max(1, min(((int(n) >> 2) + 255) // 256, 148 * 4))
 
 
 def adam_clip_step(param, grad, m, v, step, lr, beta1=0.9, beta2=0.999, epsilon=1e-8, clip=1.0,
