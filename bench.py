@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--feeder", default=None, choices=["host", "device", "batch"],
+    ap.add_argument("--feeder", default=None, choices=["host", "device", "batch", "hybrid"],
                     help="hotloop.PackedStream feeder of the e2e leg (default: the stream's own choice)")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the C3 / C4 shaped extra configurations (BASELINE.json configs[2..3])")

@@ -800,16 +800,18 @@ class VAEEngine:
         p.have_t16 = use16
         p.use_T = False
 
-    def set_batch_packed(self, p, slab, f16_exact):
+    def set_batch_packed(self, p, slab, f16_exact, rows=None):
         """Minibatch from a packed row slab (``PackedStream``; scvae_csr_densify_packed): only the
         16-bit copies exist afterwards, so it serves the fused 16-bit passes (training with
-        R = 1, lean evaluation passes)."""
+        R = 1, lean evaluation passes).  ``rows`` = (r0, r1): the slab holds that row range of the
+        minibatch only (the hybrid feeder delivers a minibatch as two slabs)."""
         if not (self.fused_heads and self._fused_possible(p.M, p.B)) or getattr(self, "_needs_fp32_x", False) \
                 or not self.enc:
             raise NotImplementedError("packed row slabs feed the fused 16-bit path only")
+        r0, r1 = rows if rows is not None else (0, p.B)
         p.t16_is_x16 = bool(f16_exact)
-        K.csr_densify_packed(slab, p.B, self.G, row_const=p.row_const,
-                             t16=None if f16_exact else self._t16(p), x16=self._x16(p))
+        K.csr_densify_packed(slab, r1 - r0, self.G, row_const=p.row_const[r0:r1],
+                             t16=None if f16_exact else self._t16(p)[r0:r1], x16=self._x16(p)[r0:r1])
         p.have_x, p.have_row_const, p.have_t16, p.use_T = False, True, True, False
 
     # ------------------------------------------------------------------ forward ------------

@@ -151,7 +151,8 @@ class PackedStream:
     BLOCK = 255          # genes per block: a block's non-zero count fits one byte
     RING = 4             # pinned slab buffers the feeder thread may run ahead by
 
-    def __init__(self, matrix, device, minibatch_size, pack_threads=None, feeder=None):
+    def __init__(self, matrix, device, minibatch_size, pack_threads=None, feeder=None,
+                 host_fraction=None):
         indptr, indices, data, shape = _as_csr_arrays(matrix)
         if not (_counts_fit_u16(data) and shape[1] <= 65280):
             raise ValueError("the packed stream carries integer counts <= 65504 of <= 65280 genes")
@@ -216,13 +217,23 @@ class PackedStream:
         # "batch": the strings sit in pinned memory and ONE batched copy (cudaMemcpyBatchAsync: the
         # copy engine walks the B row strings) moves them into the device slab -- measured 1.5 ms
         # of driver time per 4096-row batch, so the host gather stays the default
+        # "hybrid": both at once -- the last `host_fraction` of every minibatch's rows goes through
+        # the host gather + copy, the rest is pulled by the GPU, each into its own device slab (two
+        # densify launches).  Measured on 4 / 8 GPUs sharing 16 cores: 17.1 / 24.2 M cells/s against
+        # 19.7 / 28.8 M for the pure pull (the host threads are the scarcer resource), so not a default
         self.feeder = feeder or ("host" if (cores_per_rank >= 6 or not self.cuda) else "device")
-        if self.feeder not in ("device", "host", "batch") or (self.feeder != "host" and not self.cuda):
-            raise ValueError("feeder: `batch` / `device` (CUDA only) or `host`")
-        if self.feeder in ("device", "batch"):
+        if self.feeder not in ("device", "host", "batch", "hybrid") or (self.feeder != "host" and not self.cuda):
+            raise ValueError("feeder: `hybrid` / `device` / `batch` (CUDA only) or `host`")
+        if host_fraction is None:
+            host_fraction = min(1.0, cores_per_rank / 6.0)
+        # rows [0, split) of a full minibatch are pulled by the GPU, rows [split, B) come from the host
+        self.split = 0
+        if self.feeder == "hybrid":
+            self.split = min(self.B - 1, max(1, int(round(self.B * (1.0 - float(host_fraction))))))
+        if self.feeder in ("device", "batch", "hybrid"):
             self.store_pinned = torch.from_numpy(store).pin_memory()
             self.store = self.store_pinned.numpy()
-        if self.feeder == "device":
+        if self.feeder in ("device", "hybrid"):
             self.row_off_dev = torch.from_numpy(self.row_off).to(self.device)
             self.row_const_dev = torch.from_numpy(self.row_const).to(self.device)
         if self.feeder == "batch":
@@ -285,7 +296,10 @@ class PackedStream:
                 slot = {"packed": True,
                         "buf": torch.empty(self.max_slab_bytes, dtype=torch.uint8, device=self.device),
                         "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "bytes": 0, "rows": 0,
-                        "u16_ok": True, "f16_exact": self.f16_exact, "stream": self}
+                        "u16_ok": True, "f16_exact": self.f16_exact, "stream": self, "split": 0}
+                if self.feeder == "hybrid":      # second slab: the rows the host gathers
+                    slot["buf_host"] = torch.empty(self.max_slab_bytes, dtype=torch.uint8,
+                                                   device=self.device)
                 slot["free"].record()
                 self.slots.append(slot)
         self._ring, self._ring_np = ring, [r.numpy() for r in ring]
@@ -295,10 +309,18 @@ class PackedStream:
         slab = self.slabs[k]
         if dst is None:
             dst = numpy.empty(self.max_slab_bytes, dtype=numpy.uint8)
-        nbytes = K.pack_row_slab(self.store, self.row_off, self.row_const, slab["order"], dst,
+        first = self._split_of(slab)        # (hybrid: the host packs the rows behind the split)
+        nbytes = K.pack_row_slab(self.store, self.row_off, self.row_const,
+                                 numpy.ascontiguousarray(slab["order"][first:]), dst,
                                  threads=self.pack_threads)
-        slab["bytes"] = nbytes
+        slab["bytes_host"] = nbytes
+        if first == 0:
+            slab["bytes"] = nbytes
         return dst[:nbytes]
+
+    def _split_of(self, slab):
+        """Rows of this slab the GPU pulls (hybrid feeder; a ragged last slab keeps >= 1 host row)."""
+        return max(0, min(self.split, slab["rows"] - 1)) if self.feeder == "hybrid" else 0
 
     def pack_epoch(self, order=None):
         """Fix the epoch's row order (default: data order) and start assembling its slabs of ``B``
@@ -312,7 +334,7 @@ class PackedStream:
                        "order": numpy.ascontiguousarray(order[i:i + B])}
                       for i in range(0, order.size, B)]
         self._buffers()
-        if self.feeder == "device":
+        if self.feeder in ("device", "hybrid"):
             self.order_dev = torch.from_numpy(order).to(self.device)      # the epoch's row order
         if self.feeder in ("device", "batch"):
             self._taken_upto = 0
@@ -403,9 +425,19 @@ class PackedStream:
                 self._cv.notify_all()
             return out
         slot = self.slots[slot_id]
+        first = self._split_of(slab)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(slot["free"])
-            slot["buf"][:slab["bytes"]].copy_(self._ring[j][:slab["bytes"]], non_blocking=True)
+            if first:       # hybrid: the GPU pulls rows [0, first) itself, the host's rows follow by copy
+                K.packed_pull(self.store_pinned, self.row_off_dev, self.row_const_dev,
+                              self.order_dev[k * self.B:k * self.B + first], slot["buf"])
+                slot["buf_host"][:slab["bytes_host"]].copy_(self._ring[j][:slab["bytes_host"]],
+                                                            non_blocking=True)
+                slab["bytes"] = slab["bytes_host"] + K.packed_rows_offset(first) + int(
+                    self.lens[slab["order"][:first]].sum())
+            else:
+                slot["buf"][:slab["bytes"]].copy_(self._ring[j][:slab["bytes"]], non_blocking=True)
+            slot["split"] = first
             slot["ready"].record(self.copy_stream)
             done = torch.cuda.Event()
             done.record(self.copy_stream)
@@ -519,7 +551,12 @@ class TrainLoop:
                               u16_ok=src.u16_ok, f16_exact=src.f16_exact, train16=self.R == 1,
                               row_const_all=src.row_const)
         elif src.get("packed"):      # staging slot of a PackedStream: one slab = this minibatch
-            eng.set_batch_packed(p, src["buf"], f16_exact=src["f16_exact"])
+            split = src.get("split", 0)
+            if split:                # hybrid feeder: pulled rows, then the host-gathered rows
+                eng.set_batch_packed(p, src["buf"], f16_exact=src["f16_exact"], rows=(0, split))
+                eng.set_batch_packed(p, src["buf_host"], f16_exact=src["f16_exact"], rows=(split, p.B))
+            else:
+                eng.set_batch_packed(p, src["buf"], f16_exact=src["f16_exact"])
         else:  # staging slot of a StreamedCSR
             eng.set_batch_csr(p, src["indptr"], src["indices"], src["values"], None, rebase=True,
                               u16_ok=src["u16_ok"], f16_exact=src["f16_exact"],

@@ -389,7 +389,13 @@ class VariationalAutoencoder:
             if packed is not None:
                 slot = packed.fetch(b % 2, b)
                 torch.cuda.current_stream().wait_event(slot["ready"])
-                engine.set_batch_packed(plan, slot["buf"], f16_exact=packed.f16_exact)
+                split = slot.get("split", 0)
+                if split:        # hybrid feeder: two slabs per minibatch
+                    engine.set_batch_packed(plan, slot["buf"], f16_exact=packed.f16_exact, rows=(0, split))
+                    engine.set_batch_packed(plan, slot["buf_host"], f16_exact=packed.f16_exact,
+                                            rows=(split, rows))
+                else:
+                    engine.set_batch_packed(plan, slot["buf"], f16_exact=packed.f16_exact)
                 slot["free"].record(torch.cuda.current_stream())
             else:
                 engine.set_batch_csr(plan, data.indptr, data.indices, data.values, idx,

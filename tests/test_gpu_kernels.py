@@ -855,7 +855,7 @@ def test_continuous_likelihood_fwd_bwd_and_moments(kind, M, G, tile):
         assert (got[ok] - w[ok]).abs().max().item() <= 1e-3 * scale + 1e-6
 
 
-@pytest.mark.parametrize("feeder", ["batch", "device", "host"])
+@pytest.mark.parametrize("feeder", ["batch", "device", "host", "hybrid"])
 @pytest.mark.parametrize("cap,direct", [(200.0, True), (3000.0, False), (60000.0, False)])
 def test_csr_densify_packed_matches_csr_densify(cap, direct, feeder):
     """The streamed wire format (packed row slabs, scvae_csr_densify_packed) against the CSR form:
@@ -870,7 +870,7 @@ def test_csr_densify_packed_matches_csr_densify(cap, direct, feeder):
     dense[7] = 0
     csr = scipy.sparse.csr_matrix(dense)
     dev = _dev()
-    stream = PackedStream(csr, dev, B, feeder=feeder)       # GPU pull from pinned memory / host gather
+    stream = PackedStream(csr, dev, B, feeder=feeder, host_fraction=0.4)
     assert 2.0 < stream.bytes_per_nonzero < 3.2
     order = rng.permutation(N)
     stream.pack_epoch(order)
@@ -885,7 +885,15 @@ def test_csr_densify_packed_matches_csr_densify(cap, direct, feeder):
         x16 = torch.full((rows, ld16), 3.0, dtype=torch.float16, device=dev)
         t16 = None if direct else torch.full((rows, (G + 7) & ~7), 7, dtype=torch.int16, device=dev)
         rc = torch.zeros(rows, device=dev)
-        K.csr_densify_packed(slot["buf"], rows, G, row_const=rc, t16=t16, x16=x16)
+        split = slot.get("split", 0)
+        if split:       # hybrid feeder: the pulled rows and the host-gathered rows arrive as two slabs
+            assert 0 < split < rows
+            K.csr_densify_packed(slot["buf"], split, G, row_const=rc[:split],
+                                 t16=None if t16 is None else t16[:split], x16=x16[:split])
+            K.csr_densify_packed(slot["buf_host"], rows - split, G, row_const=rc[split:],
+                                 t16=None if t16 is None else t16[split:], x16=x16[split:])
+        else:
+            K.csr_densify_packed(slot["buf"], rows, G, row_const=rc, t16=t16, x16=x16)
         slot["free"].record()
         idx = torch.tensor(order[k * B:k * B + rows].astype(numpy.int64)).to(dev)
         x16_ref = torch.full((rows, ld16), 5.0, dtype=torch.float16, device=dev)
