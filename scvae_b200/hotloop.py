@@ -167,7 +167,7 @@ class PackedStream:
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
         cores_per_rank = (os.cpu_count() or 8) // max(local_world, 1)
         if pack_threads is None:          # host threads of the slab gather, shared between the ranks of a node
-            pack_threads = max(1, min(8, cores_per_rank))
+            pack_threads = max(1, min(8, cores_per_rank - 2))     # (two cores stay with the rank's own threads)
         self.pack_threads = int(pack_threads)
         self.u16_ok = True
         self.f16_exact = bool(data.size == 0 or data.max() <= 2048)
