@@ -49,6 +49,7 @@ struct GemmParams {
     int dual;                 // 0: C = A B;  1: C = (A + X) B;  2: C = A (B + X)   (X: the low-order half
                               // of an fp32 operand split into two fp16 matrices, same shape and major)
     int m_mult;               // m-tiles per work item (2 in pair mode: tiles_m counts pairs)
+    int stream_hint;          // bit 0 / 1: operand A / B streams through once -> L2 evict-first loads
 };
 
 // One unit of work of a CTA: k-blocks [kb0, kb1) of output tile (tm, tn).
@@ -165,6 +166,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t phase = 0;
             WorkIter work;
             Segment sg;
+            const bool hint_a = (p.stream_hint & 1) != 0, hint_b = (p.stream_hint & 2) != 0;
+            const uint64_t pol = l2_policy_evict_first();
             while (work.next(p, sg)) {
                 const int tm = PAIR ? 2 * sg.tm : sg.tm, tn = sg.tn, kb0 = sg.kb0, kb1 = sg.kb1;
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -175,7 +178,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t full = bar_full + 8 * stage;
                     mbar_expect_tx(full, stage_bytes);
                     // pair mode: the second m-tile (rows beyond M arrive as zeros)
-                    if (PAIR) tma_load_2d(sx + kTileBytes, &tmA, kb * BKE, (tm + 1) * BM, full);
+                    if (PAIR) {
+                        if (hint_a) tma_load_2d_hint(sx + kTileBytes, &tmA, kb * BKE, (tm + 1) * BM, full, pol);
+                        else tma_load_2d(sx + kTileBytes, &tmA, kb * BKE, (tm + 1) * BM, full);
+                    }
                     if (DUAL == 1) {
                         if (A_MN) {
 #pragma unroll
@@ -195,17 +201,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     if (A_MN) {
 #pragma unroll
-                        for (int j = 0; j < MN_BOXES; ++j)
-                            tma_load_2d(sa + j * MN_BOX_BYTES, &tmA, tm * BM + MN_BOX * j, kb * BKE, full);
+                        for (int j = 0; j < MN_BOXES; ++j) {
+                            if (hint_a) tma_load_2d_hint(sa + j * MN_BOX_BYTES, &tmA, tm * BM + MN_BOX * j, kb * BKE, full, pol);
+                            else tma_load_2d(sa + j * MN_BOX_BYTES, &tmA, tm * BM + MN_BOX * j, kb * BKE, full);
+                        }
                     } else {
-                        tma_load_2d(sa, &tmA, kb * BKE, tm * BM, full);
+                        if (hint_a) tma_load_2d_hint(sa, &tmA, kb * BKE, tm * BM, full, pol);
+                        else tma_load_2d(sa, &tmA, kb * BKE, tm * BM, full);
                     }
                     if (B_MN) {
 #pragma unroll
-                        for (int j = 0; j < MN_BOXES; ++j)
-                            tma_load_2d(sb + j * MN_BOX_BYTES, &tmB, tn * BN + MN_BOX * j, kb * BKE, full);
+                        for (int j = 0; j < MN_BOXES; ++j) {
+                            if (hint_b) tma_load_2d_hint(sb + j * MN_BOX_BYTES, &tmB, tn * BN + MN_BOX * j, kb * BKE, full, pol);
+                            else tma_load_2d(sb + j * MN_BOX_BYTES, &tmB, tn * BN + MN_BOX * j, kb * BKE, full);
+                        }
                     } else {
-                        tma_load_2d(sb, &tmB, kb * BKE, tn * BN, full);
+                        if (hint_b) tma_load_2d_hint(sb, &tmB, kb * BKE, tn * BN, full, pol);
+                        else tma_load_2d(sb, &tmB, kb * BKE, tn * BN, full);
                     }
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
@@ -514,6 +526,22 @@ static int launch_gemm(const char *name, int layout, int M, int N, int K, const 
 
     p.dual = dual;
     p.m_mult = pair ? 2 : 1;
+    // which operand streams through once: the (cells x genes)-sized one.  NT: A (the minibatch);
+    // TN: A (the head pre-activation gradient), or, with the output gradient split (dual 1), B (the
+    // minibatch).  Only for operands far larger than the other one.
+    p.stream_hint = 0;
+    {
+        static int enabled = -1;
+        if (enabled < 0) {
+            const char *e = getenv("SCVAE_TC_L2_HINT");
+            enabled = (e && atoi(e) == 0) ? 0 : 1;
+        }
+        if (enabled && F16) {
+            if (layout == SCVAE_GEMM_NT && (int64_t)M >= 8 * (int64_t)N) p.stream_hint = 1;
+            if (layout == SCVAE_GEMM_TN && dual == 1 && (int64_t)N >= 8 * (int64_t)M) p.stream_hint = 2;
+            if (layout == SCVAE_GEMM_TN && dual == 0 && (int64_t)M >= 8 * (int64_t)N) p.stream_hint = 1;
+        }
+    }
     p.streamk = sp.streamk;
     p.units_per_cta = sp.units_per_cta;
     p.total_units = sp.tiles_m * sp.tiles_n * sp.nkb;

@@ -41,6 +41,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// The same load with an L2 eviction policy (createpolicy): operands that stream through once (the
+// (cells x genes) minibatch, the head pre-activation gradients) are marked evict-first so that they do
+// not flush the small, reused working set of the kernels running beside the GEMM out of the L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], "
+        "[%4], %5;" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, uint32_t src) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map),
                  "r"(c0), "r"(c1), "r"(src)
