@@ -527,19 +527,20 @@ static int launch_gemm(const char *name, int layout, int M, int N, int K, const 
     p.dual = dual;
     p.m_mult = pair ? 2 : 1;
     // which operand streams through once: the (cells x genes)-sized one.  NT: A (the minibatch);
-    // TN: A (the head pre-activation gradient), or, with the output gradient split (dual 1), B (the
-    // minibatch).  Only for operands far larger than the other one.
+    // TN: A (the head pre-activation gradient).  Only for operands far larger than the other one.
+    // (TN with the output gradient split, B = the minibatch: marking it costs 6 us per step -- it is
+    // the last reader of X16 in a step and the next densify rewrites the buffer -- so it is off.)
     p.stream_hint = 0;
     {
-        static int enabled = -1;
+        static int enabled = -1;       // bit 0: NT forward, bit 1: TN with split output gradient, bit 2: TN
         if (enabled < 0) {
             const char *e = getenv("SCVAE_TC_L2_HINT");
-            enabled = (e && atoi(e) == 0) ? 0 : 1;
+            enabled = e ? atoi(e) : 5;      // (measured at C2: none 0.575, 4: 0.565, 5: 0.560, 7: 0.566 ms per step)
         }
         if (enabled && F16) {
-            if (layout == SCVAE_GEMM_NT && (int64_t)M >= 8 * (int64_t)N) p.stream_hint = 1;
-            if (layout == SCVAE_GEMM_TN && dual == 1 && (int64_t)N >= 8 * (int64_t)M) p.stream_hint = 2;
-            if (layout == SCVAE_GEMM_TN && dual == 0 && (int64_t)M >= 8 * (int64_t)N) p.stream_hint = 1;
+            if ((enabled & 1) && layout == SCVAE_GEMM_NT && (int64_t)M >= 8 * (int64_t)N) p.stream_hint = 1;
+            if ((enabled & 2) && layout == SCVAE_GEMM_TN && dual == 1 && (int64_t)N >= 8 * (int64_t)M) p.stream_hint = 2;
+            if ((enabled & 4) && layout == SCVAE_GEMM_TN && dual == 0 && (int64_t)M >= 8 * (int64_t)N) p.stream_hint = 1;
         }
     }
     p.streamk = sp.streamk;

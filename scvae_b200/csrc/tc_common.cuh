@@ -62,6 +62,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int
                  "r"(c0), "r"(c1), "r"(src)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap *map, int c0, int c1, uint32_t src, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(map),
+                 "r"(c0), "r"(c1), "r"(src), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *map, int c0, int c1, uint32_t src) {
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map),
                  "r"(c0), "r"(c1), "r"(src)
