@@ -697,7 +697,12 @@ static FusedPlan fused_plan(int M, int G) {
     FusedPlan f;
     f.row_tiles = (M + FM - 1) / FM;
     f.n_tiles = (G + FG - 1) / FG;
-    int target = (2 * 148 + f.row_tiles / 2) / f.row_tiles;   // about two waves of CTAs
+    static int waves = 0;                                      // CTA waves over the 148 SMs (default 2)
+    if (!waves) {
+        const char *e = getenv("SCVAE_FUSED_WAVES");
+        waves = (e && atoi(e) > 0) ? atoi(e) : 2;
+    }
+    int target = (waves * 148 + f.row_tiles / 2) / f.row_tiles;
     if (target < 1) target = 1;
     if (target > f.n_tiles) target = f.n_tiles;
     f.tiles_per_cta = (f.n_tiles + target - 1) / target;

@@ -156,6 +156,7 @@ class VAEEngine:
         # CTAs of the backward middle kernel when it shares the SMs with the side-stream GEMMs
         # (0: never share, run it first on all SMs)
         self.mid_bwd_ctas = int(__import__("os").environ.get("SCVAE_MID_BWD_CTAS", "74"))
+        self.mid_fwd_ctas = int(__import__("os").environ.get("SCVAE_MID_FWD_CTAS", "148"))
 
         for arch in (inference_architecture, generative_architecture):
             if arch not in ("MLP", "LFM"):
@@ -677,7 +678,7 @@ class VAEEngine:
         d.B, d.L, d.n_enc, d.n_dec = B, L, len(self.enc), len(self.dec)
         sms = self._sm_count()
         d.rows_per_cta = self._mid_rows(B, min(sms, self.mid_bwd_ctas) if (
-            backward and self.mid_bwd_ctas > 0 and self.overlap_streams) else sms)
+            backward and self.mid_bwd_ctas > 0 and self.overlap_streams) else min(sms, self.mid_fwd_ctas))
         for i, l in enumerate(self.enc):
             d.enc[i] = K.mid_layer(
                 w=l.w if i else None, dw=l.dw if i else None, beta=l.beta if l.bn else None,
