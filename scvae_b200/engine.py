@@ -157,6 +157,10 @@ class VAEEngine:
         # (0: never share, run it first on all SMs)
         self.mid_bwd_ctas = int(__import__("os").environ.get("SCVAE_MID_BWD_CTAS", "74"))
         self.mid_fwd_ctas = int(__import__("os").environ.get("SCVAE_MID_FWD_CTAS", "148"))
+        # CTAs of the head-slice gradient exchange on the side stream (data parallel).  The kernel needs
+        # no shared memory, so its CTAs sit beside the tensor-core GEMMs' (2 GPUs: 58 / 100 / 148 CTAs ->
+        # 0.626 / 0.610 / 0.608 ms per step)
+        self.dp_side_ctas = int(__import__("os").environ.get("SCVAE_DP_SIDE_CTAS", "148"))
 
         for arch in (inference_architecture, generative_architecture):
             if arch not in ("MLP", "LFM"):
@@ -1300,7 +1304,7 @@ class VAEEngine:
             with torch.cuda.stream(side):
                 if peer is not None:        # exchange + Adam of the head slice in one kernel
                     peer.reduce_adam(off, s.total, 1.0, channel=1,
-                                     max_ctas=self.side_gemm_ctas // 2, scalars=self.scalars)
+                                     max_ctas=self.dp_side_ctas, scalars=self.scalars)
                 else:
                     self._adam(off, s.total, advance)
                 p.head_ev[1].record(side)
