@@ -120,6 +120,11 @@ __device__ __forceinline__ int mid_rows_of(int cta, int rows_per_cta, int B) {
 // (not inlined), and asynchronous copies (cp.async) for every global -> shared transfer: all of a
 // phase's loads are in flight together without holding registers, and they can be issued ahead of a
 // grid barrier or another phase's arithmetic.
+// The activation / weight buffers are reached through pointers kept in a shared-memory context, so the
+// compiler sees generic addresses: without this hint every operand load of the product loops is a
+// 64-bit generic LD.E.128 with its descriptor moves instead of an LDS.128 with a 32-bit address.
+#define MID_SHARED(p) __builtin_assume(__isShared(p))
+
 template <int TM>
 struct MidTraits {
     static constexpr int kSpan = TM * 8;          // rows covered by a product tile: 32 or 64
@@ -140,6 +145,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_al
 // Lanes run along the column index (coalesced global reads), warps along the cells.
 __device__ __noinline__ void slab_copy_async(const MidCtx &c, float *dst, const float *__restrict__ src, int64_t ld,
                                              int ncol, int span) {
+    MID_SHARED(&c); MID_SHARED(dst);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int r = warp; r < span; r += kMidThreads / 32) {
         const bool valid = r < c.nr;
@@ -150,6 +156,7 @@ __device__ __noinline__ void slab_copy_async(const MidCtx &c, float *dst, const 
 // dst[col][r] = alpha * sum_s src_s[r0 + r][col] (s < nsplit slices, `slice` floats apart), fixed order
 __device__ __noinline__ void slab_sum(const MidCtx &c, float *dst, const float *__restrict__ src, int64_t ld, int ncol,
                                       int span, int nsplit, int64_t slice, float alpha) {
+    MID_SHARED(&c); MID_SHARED(dst);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int r = warp; r < span; r += kMidThreads / 32) {
         const bool valid = r < c.nr;
@@ -166,6 +173,7 @@ __device__ __noinline__ void slab_sum(const MidCtx &c, float *dst, const float *
 }
 // HBM[r0 + r][col] <- src[col][r] (row-major copy of a shared activation, valid cells only)
 __device__ __noinline__ void slab_store(const MidCtx &c, const float *src, float *__restrict__ dst, int64_t ld, int ncol) {
+    MID_SHARED(&c); MID_SHARED(src);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int r = warp; r < c.nr; r += kMidThreads / 32)
         for (int col = lane; col < ncol; col += 32) dst[(int64_t)(c.r0 + r) * ld + col] = src[col * c.RP + r];
@@ -174,6 +182,7 @@ __device__ __noinline__ void slab_store(const MidCtx &c, const float *src, float
 // ---- weight staging: sw[n][k] = W[row0 + n][k], n < N, k < round4(Kc) (natural layout, async) ---------
 // (columns beyond the reduction length are zero in the stored weights -- forward -- or unused -- dgrad)
 __device__ __noinline__ void stage_w_async(const MidCtx &c, const float *__restrict__ W, int64_t ldw, int row0, int N, int Kc) {
+    MID_SHARED(&c);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int K4 = (Kc + 3) >> 2;
     for (int n = warp; n < N; n += kMidThreads / 32)
@@ -188,9 +197,11 @@ __device__ __noinline__ void stage_w_async(const MidCtx &c, const float *__restr
 template <int TM>
 __device__ __noinline__ void mid_product(const MidCtx &c, const float *__restrict__ A, int K, float *__restrict__ C, int N,
                                          float *__restrict__ Y, int64_t ldy) {
+    MID_SHARED(&c);
     const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
     const float *a = A + ty * TM;
     const float *sw = c.sw;
+    MID_SHARED(a); MID_SHARED(sw); MID_SHARED(C);
     const int K4 = (K + 3) & ~3;
     float acc[TM][4];
 #pragma unroll
@@ -242,9 +253,11 @@ __device__ __noinline__ void mid_product(const MidCtx &c, const float *__restric
 template <int TM>
 __device__ __noinline__ void mid_dgrad_tile(const MidCtx &c, const float *__restrict__ G, int Nred, float *__restrict__ Out,
                                             int Kout, bool first) {
+    MID_SHARED(&c);
     const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
     const float *a = G + ty * TM;
     const float *w = c.sw + tx * 4;
+    MID_SHARED(a); MID_SHARED(w); MID_SHARED(Out);
     float acc[TM][4];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
@@ -294,8 +307,10 @@ __device__ __noinline__ void mid_dgrad_tile(const MidCtx &c, const float *__rest
 template <int NJ>
 __device__ __noinline__ void mid_wgrad_t(const MidCtx &c, const float *__restrict__ G, int N, const float *__restrict__ I,
                                          int Kp, float *__restrict__ out) {
+    MID_SHARED(&c);
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     const int ni = (N - ty + 15) >> 4, kj = (Kp - tx + 15) >> 4;    // valid i / j counts
+    MID_SHARED(G); MID_SHARED(I);
     float acc[8][NJ];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -329,6 +344,7 @@ __device__ __forceinline__ void mid_wgrad(const MidCtx &c, const float *G, int N
 
 // augmented ones column (valid cells only) at `col`, zero columns behind it up to `col_end`
 __device__ __noinline__ void set_aug_cols(const MidCtx &c, float *dst, int col, int col_end, int span) {
+    MID_SHARED(&c); MID_SHARED(dst);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int cc = col + warp; cc < col_end; cc += kMidThreads / 32)
         for (int r = lane; r < span; r += 32) dst[cc * c.RP + r] = (cc == col && r < c.nr) ? 1.f : 0.f;
@@ -337,6 +353,7 @@ __device__ __noinline__ void set_aug_cols(const MidCtx &c, float *dst, int col, 
 // Per-CTA partial statistics of Y[c][r] (columns < N over this CTA's cells): (mean, M2) -> workspace.
 // One thread per (column, half of the cells); the two halves meet in shared memory in fixed order.
 __device__ __noinline__ void mid_bn_partial(const MidCtx &c, const float *Y, int N, float *ws_stat) {
+    MID_SHARED(&c); MID_SHARED(Y);
     // one pass: sums of (y - pivot) and (y - pivot)^2 with the column's first cell as the pivot (a
     // value within the spread of the data, so neither sum cancels): mean = pivot + s1 / n,
     // M2 = s2 - s1^2 / n
@@ -367,6 +384,7 @@ __device__ __noinline__ void mid_bn_partial(const MidCtx &c, const float *Y, int
 // order (the same arithmetic as the general fold, whose 8 warp lanes then hold one partial each).
 __device__ __noinline__ void mid_bn_fold_small(const MidCtx &c, const MidDesc &d, const MidLayer &l, const float *ws_stat,
                                                float *scratch, float *s_mean, float *s_rstd) {
+    MID_SHARED(&c); MID_SHARED(&d); MID_SHARED(s_mean); MID_SHARED(s_rstd);
     (void)scratch;
     const int N = l.n_out, G = gridDim.x, col = threadIdx.x;
     const float inv_b = 1.f / (float)d.B;
@@ -411,6 +429,7 @@ __device__ __noinline__ void mid_bn_fold_small(const MidCtx &c, const MidDesc &d
 // s_mean / s_rstd [N]; CTA 0 writes the saved statistics and the moving averages.
 __device__ __noinline__ void mid_bn_fold(const MidCtx &c, const MidDesc &d, const MidLayer &l, const float *ws_stat,
                                          float *scratch, float *s_mean, float *s_rstd) {
+    MID_SHARED(&c); MID_SHARED(&d); MID_SHARED(scratch); MID_SHARED(s_mean); MID_SHARED(s_rstd);
     const int N = l.n_out;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x;
@@ -540,6 +559,7 @@ __device__ __forceinline__ float *bnv_beta(const MidCtx &c, int s) { return c.bn
 // batch statistics follow from the folds), 1: + moving statistics (evaluation), 2: + saved batch
 // statistics (backward).  Layers without batch norm get (0, 1, 0): the identity.
 __device__ __noinline__ void mid_load_bnv(const MidCtx &c, const MidDesc &d, int mode) {
+    MID_SHARED(&c); MID_SHARED(&d);
     const int nl = d.n_enc + d.n_dec;
     for (int s = 0; s < nl; ++s) {
         const MidLayer &l = s < d.n_enc ? d.enc[s] : d.dec[s - d.n_enc];
@@ -565,6 +585,7 @@ __device__ __noinline__ void mid_load_bnv(const MidCtx &c, const MidDesc &d, int
 // H[c][r] = relu((Y[c][r] - mean) rstd + beta) for valid cells, 0 otherwise; X (nullable) = xhat.
 // (lanes along the cells: conflict-free shared-memory access)
 __device__ __noinline__ void mid_normalise(const MidCtx &c, int slot, int N, int span, const float *Y, float *X, float *H) {
+    MID_SHARED(&c); MID_SHARED(Y); MID_SHARED(X); MID_SHARED(H);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float *m = bnv_mean(c, slot), *rs = bnv_rstd(c, slot), *bt = bnv_beta(c, slot);
 #pragma unroll 4
@@ -590,6 +611,7 @@ __device__ __noinline__ void mid_normalise(const MidCtx &c, int slot, int N, int
 // barrier (H doubles as the scratch of the fold: it is written only afterwards).
 __device__ __noinline__ void mid_fwd_bn_relu(const MidCtx &c, const MidDesc &d, const MidLayer &l, int slot, const float *Y,
                                              float *H, bool training, int span) {
+    MID_SHARED(&c); MID_SHARED(&d); MID_SHARED(Y);
     const int N = l.n_out;
     if (l.beta && training) {
         mid_bn_partial(c, Y, N, ws_stat_slot(d, slot));
@@ -615,6 +637,7 @@ __global__ void __maxnreg__(kMidMaxRegs) vae_mid_fwd_kernel(const __grid_constan
     const int L = d.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *E = c.act[3];       // noise slab [l][r]
+    MID_SHARED(E);
     mid_stamp(d, 0);
 
     // ---- prologue: every load that depends on no other CTA, in ONE round trip ------------------------
@@ -700,6 +723,7 @@ __global__ void __maxnreg__(kMidMaxRegs) vae_mid_fwd_kernel(const __grid_constan
     // ---- sample and KL (VAE:2353-2369, :2624-2627) ----------------------------------------------------
     {
         float *sMu = c.act[mb], *sLs = post_parts == 1 ? c.act[mb] + L * c.RP : c.act[lb], *sZ = c.act[cur];
+        MID_SHARED(sMu); MID_SHARED(sLs); MID_SHARED(sZ);
         const int Kzp = (dl0.k_in + 3) & ~3;
         // lanes along the latent dimension: coalesced HBM copies of [mu | raw log_sigma] and z
         for (int r = warp; r < SPAN; r += kMidThreads / 32) {
@@ -765,6 +789,7 @@ __global__ void __maxnreg__(kMidMaxRegs) vae_mid_fwd_kernel(const __grid_constan
     {
         const int N = d.dec[d.n_dec - 1].n_out;
         const float *H = c.act[cur];
+        MID_SHARED(H);
         const int groups = (int)(d.ldd16 >> 3);
         __half *out = reinterpret_cast<__half *>(d.d16);
         for (int r = warp; r < c.nr; r += kMidThreads / 32) {
@@ -789,6 +814,7 @@ __global__ void __maxnreg__(kMidMaxRegs) vae_mid_fwd_kernel(const __grid_constan
 // `scratch`: [8 warps][2][128] floats of idle shared memory.
 __device__ __noinline__ void mid_bn_relu_bwd(const MidCtx &c, const MidDesc &d, const MidLayer &l, int s, int span, float *Gd,
                                              const float *X, float *ws_stat, float *scratch) {
+    MID_SHARED(&c); MID_SHARED(&d); MID_SHARED(Gd); MID_SHARED(X); MID_SHARED(scratch);
     const int N = l.n_out;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float *rs = bnv_rstd(c, s), *bt = bnv_beta(c, s);
@@ -929,6 +955,7 @@ __global__ void __maxnreg__(kMidMaxRegs) vae_mid_bwd_kernel(const __grid_constan
     const MidLayer &last = d.dec[d.n_dec - 1];
     const int s_last = d.n_enc + d.n_dec - 1;
     float *Gd = c.act[0], *X = c.act[1], *T = c.act[2], *F = c.act[3];
+    MID_SHARED(Gd); MID_SHARED(X); MID_SHARED(T); MID_SHARED(F);
     mid_stamp(d, 0);
     {
         const int N = last.n_out;
@@ -1044,6 +1071,7 @@ __global__ void __maxnreg__(kMidMaxRegs) vae_mid_bwd_kernel(const __grid_constan
     const int post_parts = (2 * L <= kMidCols) ? 1 : 2;
     const int NP = post_parts == 1 ? 2 * L : L;
     float *Gmu = Gd, *Gls = post_parts == 1 ? Gd + L * c.RP : X;     // (one buffer when both halves fit)
+    MID_SHARED(Gd); MID_SHARED(Gmu); MID_SHARED(Gls);
     const MidLayer &pl = d.post;
     const MidLayer &prev = d.enc[d.n_enc - 1];
     stage_w_async(c, pl.w, pl.ldw, 0, NP, pl.n_in);
