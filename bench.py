@@ -131,6 +131,11 @@ class ClockSampler:
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            # nvidia-smi needs a moment before its first line: wait for it (bounded), so that a
+            # timed region of ~0.1 s is not over before the sampler has started printing
+            t0 = time.perf_counter()
+            while not self.samples and time.perf_counter() - t0 < 5.0 and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 

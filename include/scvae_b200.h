@@ -505,7 +505,10 @@ int scvae_gmvae_z_mean(const float *qh, int64_t ldq, const float *y, int K, int 
  *   {lower_bound, lower_bound_weighted, reconstruction_error, kl_divergence} (VAE:2715-2734, R = 1),
  *   dw / dbeta of every layer but the first encoder layer, and dy1_16 (+ dy1_16_lo, nullable: the
  *   rounding remainder, see scvae_gemm_f16_split) = fp16(dy1_scale * dY1) for that layer's
- *   weight-gradient product.  kl weight = kl_weight * scalars[1] (scalars nullable,
+ *   weight-gradient product.  enc[0].dw (nullable; ldw = its row pitch): only its bias column n_in
+ *   is written, = the column sums of dY1 in fp32 -- for callers that form the gene columns from a
+ *   single fp16 dy1_16, whose rounding would otherwise be all there is in that (behind a batch
+ *   norm: mathematically zero) gradient.  kl weight = kl_weight * scalars[1] (scalars nullable,
  *   device: {learning rate, warm-up weight}).
  * A barrier wait that exceeds ~2 s sets *error (device int) instead of hanging. */
 #define SCVAE_MID_MAX_LAYERS 4

@@ -553,7 +553,10 @@ static int launch_gemm(const char *name, int layout, int M, int N, int K, const 
     }
     const int grid = sp.grid;
     if (sp.streamk) {   // partial tiles are reduce-added into C
-        cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), s);
+        // (the N columns of the product only: the caller may keep other columns of a wider C)
+        cudaError_t e = (int64_t)N == ldc ? cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), s)
+                                          : cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0,
+                                                              (size_t)N * sizeof(float), (size_t)M, s);
         SCVAE_CHECK_ARG(e == cudaSuccess, "%s: memset failed: %s", name, cudaGetErrorString(e));
     }
 #define LAUNCH(AM, BMN, DU, PR)                                                                             \

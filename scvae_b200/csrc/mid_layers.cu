@@ -203,6 +203,12 @@ __device__ __noinline__ void mid_product(const MidCtx &c, const float *__restric
     const float *sw = c.sw;
     MID_SHARED(a); MID_SHARED(sw); MID_SHARED(C);
     const int K4 = (K + 3) & ~3;
+    const int RP = c.RP;           // (kept in a register: c lives in shared memory and would be re-read)
+    // rows of sw this thread reads: clamped, so that the loads are unconditional (no branch per load);
+    // the products of the clamped duplicates are simply not stored
+    int wrow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wrow[j] = min(tx + 32 * j, N - 1) * kMidWP;
     float acc[TM][4];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
@@ -212,15 +218,13 @@ __device__ __noinline__ void mid_product(const MidCtx &c, const float *__restric
     for (int k = 0; k < K4; k += 4) {
         float4 wv[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            wv[j] = (tx + 32 * j < N) ? *reinterpret_cast<const float4 *>(sw + (tx + 32 * j) * kMidWP + k)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 4; ++j) wv[j] = *reinterpret_cast<const float4 *>(sw + wrow[j] + k);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             float av[TM];
 #pragma unroll
             for (int i = 0; i < TM; i += 4) {
-                const float4 t = *reinterpret_cast<const float4 *>(a + (k + kk) * c.RP + i);
+                const float4 t = *reinterpret_cast<const float4 *>(a + (k + kk) * RP + i);
                 av[i] = t.x; av[i + 1] = t.y; av[i + 2] = t.z; av[i + 3] = t.w;
             }
 #pragma unroll
@@ -237,7 +241,7 @@ __device__ __noinline__ void mid_product(const MidCtx &c, const float *__restric
         if (n < N) {
 #pragma unroll
             for (int i = 0; i < TM; i += 4)
-                *reinterpret_cast<float4 *>(C + n * c.RP + ty * TM + i) =
+                *reinterpret_cast<float4 *>(C + n * RP + ty * TM + i) =
                     make_float4(acc[i][j], acc[i + 1][j], acc[i + 2][j], acc[i + 3][j]);
             if (Y) {
 #pragma unroll
@@ -258,6 +262,7 @@ __device__ __noinline__ void mid_dgrad_tile(const MidCtx &c, const float *__rest
     const float *a = G + ty * TM;
     const float *w = c.sw + tx * 4;
     MID_SHARED(a); MID_SHARED(w); MID_SHARED(Out);
+    const int RP = c.RP;
     float acc[TM][4];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
@@ -270,7 +275,7 @@ __device__ __noinline__ void mid_dgrad_tile(const MidCtx &c, const float *__rest
             float av[TM];
 #pragma unroll
             for (int i = 0; i < TM; i += 4) {
-                const float4 t = *reinterpret_cast<const float4 *>(a + n * c.RP + i);
+                const float4 t = *reinterpret_cast<const float4 *>(a + n * RP + i);
                 av[i] = t.x; av[i + 1] = t.y; av[i + 2] = t.z; av[i + 3] = t.w;
             }
 #pragma unroll
@@ -289,7 +294,7 @@ __device__ __noinline__ void mid_dgrad_tile(const MidCtx &c, const float *__rest
         if (k < Kout) {
 #pragma unroll
             for (int i = 0; i < TM; i += 4) {
-                float4 *dst = reinterpret_cast<float4 *>(Out + k * c.RP + ty * TM + i);
+                float4 *dst = reinterpret_cast<float4 *>(Out + k * RP + ty * TM + i);
                 float4 v = make_float4(acc[i][j], acc[i + 1][j], acc[i + 2][j], acc[i + 3][j]);
                 if (!first) {
                     const float4 o = *dst;
@@ -311,20 +316,25 @@ __device__ __noinline__ void mid_wgrad_t(const MidCtx &c, const float *__restric
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     const int ni = (N - ty + 15) >> 4, kj = (Kp - tx + 15) >> 4;    // valid i / j counts
     MID_SHARED(G); MID_SHARED(I);
+    const int RP = c.RP, nr4 = c.nr4;
+    // clamped rows: unconditional loads (the duplicates' sums are not stored)
+    int grow[8], irow[NJ];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) grow[i] = min(ty + 16 * i, N - 1) * RP;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) irow[j] = min(tx + 16 * j, Kp - 1) * RP;
     float acc[8][NJ];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
 #pragma unroll 1
-    for (int r = 0; r < c.nr4; r += 4) {
+    for (int r = 0; r < nr4; r += 4) {
         float4 g[8], x[NJ];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            g[i] = i < ni ? *reinterpret_cast<const float4 *>(G + (ty + 16 * i) * c.RP + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; ++i) g[i] = *reinterpret_cast<const float4 *>(G + grow[i] + r);
 #pragma unroll
-        for (int j = 0; j < NJ; ++j)
-            x[j] = j < kj ? *reinterpret_cast<const float4 *>(I + (tx + 16 * j) * c.RP + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < NJ; ++j) x[j] = *reinterpret_cast<const float4 *>(I + irow[j] + r);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -549,6 +559,10 @@ __device__ __forceinline__ float *ws_bound(const MidDesc &d) {
     return d.workspace + (int64_t)kMidSlots * gridDim.x * 2 * kMidCols;
 }
 __device__ __forceinline__ float *ws_dw_base(const MidDesc &d) { return ws_bound(d) + (int64_t)gridDim.x * 4; }
+// [grid][128] column sums of dY1: the last block of the workspace (behind the dW partials)
+__device__ __forceinline__ float *ws_db1(const MidDesc &d) {
+    return d.workspace + d.workspace_floats - (int64_t)gridDim.x * kMidCols;
+}
 
 // mean / rstd / beta of layer slot `s` (encoder layers first, then decoder layers) in shared memory
 __device__ __forceinline__ float *bnv_mean(const MidCtx &c, int s) { return c.bnv + (s * 3 + 0) * kMidCols; }
@@ -1179,6 +1193,23 @@ __global__ void __maxnreg__(kMidMaxRegs) vae_mid_bwd_kernel(const __grid_constan
             }
         }
         if (d.dy1) slab_store(c, Gd, d.dy1, d.lddy1_f32, N);
+        if (d.enc[0].dw) {
+            // bias gradient of the first layer = column sums of dY1, in fp32 (behind a batch norm it is
+            // zero up to rounding, and the fp16 copy above would turn it into rounding noise that Adam
+            // normalises to +-lr): per-CTA sums here, folded in CTA order after the barrier
+            const int col = threadIdx.x & (kMidCols - 1), half = threadIdx.x >> 7;
+            const int h0 = half ? (c.nr >> 1) : 0, h1 = half ? c.nr : (c.nr >> 1);
+            float s1 = 0.f;
+            if (col < N) {
+#pragma unroll 4
+                for (int r = h0; r < h1; ++r) s1 += Gd[col * c.RP + r];
+            }
+            float *x = c.stat + 4 * kMidCols;
+            __syncthreads();
+            x[half * kMidCols + col] = s1;
+            __syncthreads();
+            if (half == 0) ws_db1(d)[(int64_t)blockIdx.x * kMidCols + col] = x[col] + x[kMidCols + col];
+        }
     }
     // ---- all partials are in the workspace: fold them in fixed order --------------------------------
     mid_stamp(d, 11);
@@ -1219,6 +1250,24 @@ __global__ void __maxnreg__(kMidMaxRegs) vae_mid_bwd_kernel(const __grid_constan
         for (int j = d.n_dec - 1; j >= 0; --j) reduce(d.dec[j]);
         reduce(d.post);
         for (int i = d.n_enc - 1; i >= 1; --i) reduce(d.enc[i]);
+        if (d.enc[0].dw && blockIdx.x == (gridDim.x > 1 ? gridDim.x - 2 : 0)) {
+            // first-layer bias gradient: thread (column, half) adds its half of the CTA partials in
+            // CTA order, the two halves are added in order (a CTA near the end of the grid: it
+            // owns few or none of the elements folded above)
+            const int col = threadIdx.x & (kMidCols - 1), half = threadIdx.x >> 7;
+            const int k0 = half ? (G >> 1) : 0, k1 = half ? G : (G >> 1);
+            const float *src = ws_db1(d) + col;
+            float s0 = 0.f;
+#pragma unroll 8
+            for (int k = k0; k < k1; ++k) s0 += __ldcg(src + (int64_t)k * kMidCols);
+            float *x = c.stat + 4 * kMidCols;
+            __syncthreads();
+            x[half * kMidCols + col] = s0;
+            __syncthreads();
+            const MidLayer &l0 = d.enc[0];
+            if (half == 0 && col < l0.n_out) l0.dw[(int64_t)col * l0.ldw + l0.n_in] = x[col] + x[kMidCols + col];
+            __syncthreads();
+        }
         if (blockIdx.x == gridDim.x - 1) {       // (the last CTA has the fewest cells: least other work)
             for (int k = threadIdx.x; k < G; k += kMidThreads) {
                 c.stat[k] = __ldcg(ws_bound(d) + k * 4 + 0);
@@ -1298,6 +1347,7 @@ static int64_t mid_workspace_floats_impl(const MidDesc *d) {
     for (int j = 0; j < d->n_dec; ++j) n += grid * d->dec[j].n_out * d->dec[j].ldw;
     n += grid * d->post.n_out * d->post.ldw;
     for (int i = 1; i < d->n_enc; ++i) n += grid * d->enc[i].n_out * d->enc[i].ldw;
+    n += grid * kMidCols;          // per-CTA column sums of dY1 (bias gradient of the first layer)
     return n;
 }
 

@@ -153,6 +153,11 @@ class VAEEngine:
         # the (cells x ~100) middle of a 16-bit training / lean evaluation step as one persistent
         # kernel per direction (csrc/mid_layers.cu) instead of ~20 small launches
         self.mid_fused = __import__("os").environ.get("SCVAE_MID_FUSED", "1") != "0"
+        # first-layer weight gradient dW1 = dY1^T X behind the middle kernel: dY1 as ONE loss-scaled
+        # fp16 matrix (default; measured error 2e-4 .. 4e-4 of max|dW1| at the C2 / C3 shapes, the bias
+        # column comes from the fp32 values) or, SCVAE_DY1_SPLIT=1, as fp16 + rounding remainder (two
+        # MMA sets, 1.5 x the operand tiles, ~2 % of the step)
+        self.dy1_split = __import__("os").environ.get("SCVAE_DY1_SPLIT", "0") != "0"
         # CTAs of the backward middle kernel when it shares the SMs with the side-stream GEMMs
         # (0: never share, run it first on all SMs)
         self.mid_bwd_ctas = int(__import__("os").environ.get("SCVAE_MID_BWD_CTAS", "74"))
@@ -490,7 +495,11 @@ class VAEEngine:
         """fp16 augmented copy of the minibatch: operand of the fp16 first layer and, when all
         counts are <= 2048 (exact in fp16), also the target matrix of the fused heads."""
         if getattr(p, "X16", None) is None:
-            p.X16 = torch.zeros(p.B, (self.G + 8) & ~7, dtype=torch.float16, device=self.device)
+            # row pitch = a multiple of 128 bytes: every 128-byte row of a TMA box is then ONE aligned
+            # cache line (with the 16-byte-aligned pitch of G = 20 000 each row straddled two lines and
+            # odd rows five 32-byte sectors: dW1 = dY1^T X 60 -> 42 us, tools/wgrad_probe.py)
+            w = (self.G + 8) & ~7
+            p.X16 = torch.zeros(p.B, (w + 63) & ~63, dtype=torch.float16, device=self.device)[:, :w]
         return p.X16
 
     def _plan_backward(self, p):
@@ -685,7 +694,8 @@ class VAEEngine:
             backward and self.mid_bwd_ctas > 0 and self.overlap_streams) else min(sms, self.mid_fwd_ctas))
         for i, l in enumerate(self.enc):
             d.enc[i] = K.mid_layer(
-                w=l.w if i else None, dw=l.dw if i else None, beta=l.beta if l.bn else None,
+                w=l.w if i else None, dw=l.dw if (i or (backward and not self.dy1_split)) else None,
+                beta=l.beta if l.bn else None,
                 dbeta=l.dbeta if l.bn else None, moving_mean=l.moving_mean, moving_var=l.moving_var,
                 mean=p.enc_mean[i], rstd=p.enc_rstd[i], y=p.encY[i], n_in=l.n_in, k_in=l.k_in,
                 n_out=l.n_out)
@@ -717,7 +727,7 @@ class VAEEngine:
             self._dy1_16(p)
             d.logp, d.bound = p.logp.data_ptr(), p.bound.data_ptr()
             d.dy1_16, d.lddy1 = p.dY1_16.data_ptr(), p.dY1_16.stride(0)
-            d.dy1_16_lo = p.dY1_16_lo.data_ptr()
+            d.dy1_16_lo = p.dY1_16_lo.data_ptr() if self.dy1_split else None
         setattr(p, key, d)
         need = K.vae_mid_workspace_floats(d)
         if p.mid_ws is None or p.mid_ws.numel() < need:
@@ -750,11 +760,25 @@ class VAEEngine:
             ws = p.workspace
         K.gemm_f16_split(layout, M, N, Kd, A, Bm, X, which, C, alpha=alpha, workspace=ws)
 
+    def _wgrad1_16(self, p, l, B, single):
+        """dW1 = dY1^T X on the tensor cores from the loss-scaled fp16 dY1: with its rounding
+        remainder, or (``single``, behind vae_mid_bwd) from the one fp16 matrix."""
+        if not single:
+            self._gemm16_split(p, K.GEMM_TN, l.n_out, l.in_p, B, p.dY1_16, p.X16, p.dY1_16_lo, 1, l.dw,
+                               alpha=1.0 / p.fused_scale)
+        else:
+            # the gene columns only: the bias column (= the column sums of dY1, zero up to rounding
+            # behind a batch norm) was written by vae_mid_bwd from the fp32 values
+            n = l.n_in
+            self._gemm16(p, K.GEMM_TN, l.n_out, n, B, p.dY1_16, p.X16[:, :n], l.dw[:, :n],
+                         alpha=1.0 / p.fused_scale)
+
     def _dy1_16(self, p):
         if getattr(p, "dY1_16", None) is None:
-            p.dY1_16 = torch.zeros(p.B, (self.enc[0].n_out + 7) & ~7, dtype=torch.float16,
-                                   device=self.device)
-            p.dY1_16_lo = torch.zeros_like(p.dY1_16)
+            w = (self.enc[0].n_out + 7) & ~7
+            wp = (w + 63) & ~63                  # 128-byte row pitch, as for X16
+            p.dY1_16 = torch.zeros(p.B, wp, dtype=torch.float16, device=self.device)[:, :w]
+            p.dY1_16_lo = torch.zeros(p.B, wp, dtype=torch.float16, device=self.device)[:, :w]
         return p.dY1_16
 
     # ------------------------------------------------------------------ inputs -------------
@@ -1168,9 +1192,7 @@ class VAEEngine:
                 mid_backward()
             # the first layer's weight gradient on the tensor cores
             l = self.enc[0]
-            # (dY1 as fp16 + remainder: the batch-norm backward makes this sum cancel heavily)
-            self._gemm16_split(p, K.GEMM_TN, l.n_out, l.in_p, B, p.dY1_16, p.X16, p.dY1_16_lo, 1, l.dw,
-                               alpha=1.0 / p.fused_scale)
+            self._wgrad1_16(p, l, B, single=not self.dy1_split)
             self._finish_backward(p, defer_join)
             return
         for j in range(len(self.dec) - 1, -1, -1):
@@ -1233,8 +1255,7 @@ class VAEEngine:
                 # dW1 = dY1^T X with the fp16 minibatch (dY1 scaled into fp16 range)
                 self._dy1_16(p)
                 K.f32_to_f16_split(p.d_encY[0], l.n_out, p.dY1_16, p.dY1_16_lo, scale=p.fused_scale)
-                self._gemm16_split(p, K.GEMM_TN, l.n_out, l.in_p, B, p.dY1_16, p.X16, p.dY1_16_lo, 1,
-                                   l.dw, alpha=1.0 / p.fused_scale)
+                self._wgrad1_16(p, l, B, single=False)
             else:
                 self._gemm(p, K.GEMM_TN, l.n_out, l.in_p, B, p.d_encY[i], h_in, l.dw)
             if i > 0:

@@ -600,7 +600,7 @@ def mid_layer(w=None, dw=None, beta=None, dbeta=None, moving_mean=None, moving_v
                     ("moving_mean", moving_mean), ("moving_var", moving_var), ("mean", mean),
                     ("rstd", rstd), ("y", y)):
         setattr(l, name, _p(t))
-    l.ldw = _ld(w) if w is not None else 0
+    l.ldw = _ld(w) if w is not None else (_ld(dw) if dw is not None else 0)
     l.ldy = _ld(y) if y is not None else 0
     l.n_in, l.k_in, l.n_out = int(n_in), int(k_in), int(n_out)
     return l

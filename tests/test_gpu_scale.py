@@ -199,6 +199,8 @@ def test_train_loop_step_at_baseline_shape(case, source):
     gmax = max(g.abs().max().item() for g in grads.values())
     for k, g in grads.items():
         err = (got[k].double() - g).abs().max().item()
+        print("gradient error", name, source, k, "max|err| %.3e  max|g| %.3e  ratio %.2e"
+              % (err, g.abs().max().item(), err / (g.abs().max().item() + 1e-30)))      # (shown with -s)
         assert err <= 1e-2 * g.abs().max().item() + 1e-4 * gmax, (k, err, g.abs().max().item())
     new = eng.export_parameters()
     noise = 3e-2 * gmax
