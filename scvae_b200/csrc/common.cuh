@@ -31,6 +31,35 @@ void count_launch();
         }                                                                          \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// A kernel launched with launch_pdl(site, ...) may be SCHEDULED while its predecessor in the stream
+// (or in the captured graph) still runs: its CTAs become resident as the predecessor's CTAs retire
+// and park in pdl_wait(), which returns once the whole predecessor grid has completed and flushed.
+// Every kernel calls pdl_wait() before anything else, so the data dependencies are those of plain
+// stream order; what overlaps is the launch latency and the ramp-up (~3 us per kernel boundary of
+// the training step).  pdl_trigger() in the predecessor allows that early scheduling.  Both are
+// no-ops in launches without the attribute.  SCVAE_PDL = bit mask of the launch sites (0 = off).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+enum PdlSite { kPdlGemm = 1, kPdlReduce = 2, kPdlMidFwd = 4, kPdlHeads = 8, kPdlFinish = 16, kPdlMidBwd = 32,
+               kPdlAdam = 64 };
+int pdl_mask();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(int site, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl_mask() & site) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __host__ __device__ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- constants --------------------------------------------------------------------------

@@ -1,5 +1,6 @@
 // Thread-local error string + ABI version for libscvae_b200.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -13,6 +14,14 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 static long long g_launches = 0;
+int pdl_mask() {
+    static int mask = -1;
+    if (mask < 0) {
+        const char *e = getenv("SCVAE_PDL");
+        mask = e ? atoi(e) : 0;
+    }
+    return mask;
+}
 void count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
 }  // namespace scvae
 

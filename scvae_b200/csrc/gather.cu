@@ -116,6 +116,7 @@ csr_densify16_kernel(const int64_t *__restrict__ indptr, const IdxT *__restrict_
                      __half *__restrict__ x16, int64_t ldx16, int width8, int part8) {
     // blockIdx.y selects a column part of the row (part8 groups of 8 columns each): more CTAs in
     // flight hide the dependent indptr -> indices -> values load chain
+    pdl_trigger();       // (the first-layer product behind this kernel may be scheduled early: common.cuh)
     extern __shared__ __align__(16) uint16_t row16[];
     __shared__ float red[32];
     const int b = blockIdx.x;
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(256)
 csr_densify_packed_kernel(const uint8_t *__restrict__ slab, int B, int G, int nblk, float *__restrict__ row_const,
                           uint16_t *__restrict__ t16, int64_t ldt16, __half *__restrict__ x16, int64_t ldx16,
                           int width8) {
+    pdl_trigger();       // (as in csr_densify16_kernel)
     extern __shared__ __align__(16) uint16_t row16[];
     __shared__ int prefix[260];
     __shared__ int warp_tot[8];

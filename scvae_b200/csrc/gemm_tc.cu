@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX,
                  const GemmParams p) {
+    pdl_wait();          // (programmatic dependent launch: common.cuh)
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     static_assert(!PAIR || (DUAL == 2 && !A_MN), "pair mode: forward with split weights only");
@@ -354,6 +356,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float *__restrict__ ws, int64_t ldw, int ws_rows, int nsplit, int M, int N,
                      float *__restrict__ C, int64_t ldc, int accumulate, float alpha) {
+    pdl_wait();          // (programmatic dependent launch: common.cuh)
+    pdl_trigger();
     const int n4 = (N + 3) >> 2;
     const int64_t total = (int64_t)M * n4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -570,7 +574,9 @@ static int launch_gemm(const char *name, int layout, int M, int N, int K, const 
                             cudaGetErrorString(e));                                                         \
             attr_set = true;                                                                                \
         }                                                                                                   \
-        gemm_tc_kernel<F16, AM, BMN, DU, PR><<<grid, kThreads, smem_bytes, s>>>(tmA, tmB, tmC, tmX, p);     \
+        /* (behind the stream-K memset the predecessor is not a kernel: plain launch) */                   \
+        launch_pdl(sp.streamk ? 0 : kPdlGemm, gemm_tc_kernel<F16, AM, BMN, DU, PR>, dim3(grid), dim3(kThreads), \
+                   smem_bytes, s, tmA, tmB, tmC, tmX, p);                                                   \
     } while (0)
     if (dual == 0) {
         switch (layout) {
@@ -593,8 +599,8 @@ static int launch_gemm(const char *name, int layout, int M, int N, int K, const 
     if (sp.nsplit > 1) {
         int64_t blocks = ((int64_t)M * ((N + 3) >> 2) + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
-        splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>((const float *)workspace, ldw, ws_rows, sp.nsplit, M, N, C, ldc,
-                                                   accumulate, alpha);
+        launch_pdl(kPdlReduce, splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, s, (const float *)workspace, ldw,
+                   ws_rows, sp.nsplit, M, N, C, ldc, accumulate, alpha);
         SCVAE_CHECK_LAUNCH("splitk_reduce");
     }
     return 0;

@@ -161,6 +161,8 @@ __global__ void __launch_bounds__(fused_threads(Lik<KIND>::P), 1)
 heads_fused_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmDA,
                    const __grid_constant__ CUtensorMap tmDD, const FusedParams p) {
+    pdl_wait();          // (programmatic dependent launch: common.cuh)
+    pdl_trigger();
     constexpr int P = Lik<KIND>::P;
     constexpr int EW = fused_epi_warps(P);       // epilogue warps
     constexpr int EJ = EW / 4;                   // epilogue warps per TMEM lane quadrant
@@ -649,6 +651,8 @@ __global__ void __launch_bounds__(256)
 fused_finish_wide_kernel(const float *__restrict__ part, int64_t part_stride, int gsplit, int M,
                          const float *__restrict__ row_const, int t_rows, float *__restrict__ logp,
                          const float *__restrict__ dd_part, float *__restrict__ dd, int64_t lddd, int dd_cols) {
+    pdl_wait();          // (programmatic dependent launch: common.cuh)
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int c = (int)(i & 31) << 2;
     const int64_t m = i >> 5;
@@ -751,12 +755,13 @@ static int launch_fused_t(const void *d16, const void *w16, const void *t16, int
         SCVAE_CHECK_ARG(e == cudaSuccess, "heads_fused: cannot set smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    heads_fused_kernel<KIND, T_HALF, BWD><<<f.row_tiles * f.gsplit, fused_threads(P), smem, s>>>(tmD, tmW, tmT, tmDA, tmDD, p);
+    launch_pdl(kPdlHeads, heads_fused_kernel<KIND, T_HALF, BWD>, dim3(f.row_tiles * f.gsplit), dim3(fused_threads(P)), smem, s,
+               tmD, tmW, tmT, tmDA, tmDD, p);
     SCVAE_CHECK_LAUNCH("heads_fused");
     const float *dd_part = BWD ? logp_part + (int64_t)f.gsplit * f.row_tiles * FM : nullptr;
     if (f.gsplit <= 16)
-        fused_finish_wide_kernel<<<(unsigned)(((int64_t)M * 32 + 255) / 256), 256, 0, s>>>(
-            logp_part, p.part_stride, f.gsplit, M, row_const, t_rows, logp, dd_part, dd, lddd, dd_cols);
+        launch_pdl(kPdlFinish, fused_finish_wide_kernel, dim3((unsigned)(((int64_t)M * 32 + 255) / 256)), dim3(256), 0, s,
+                   (const float *)logp_part, p.part_stride, f.gsplit, M, row_const, t_rows, logp, dd_part, dd, lddd, dd_cols);
     else
         fused_finish_kernel<<<M, 256, 0, s>>>(logp_part, p.part_stride, f.gsplit, M, row_const, t_rows, logp, dd_part,
                                               dd, lddd, dd_cols);

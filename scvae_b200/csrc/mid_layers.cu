@@ -642,6 +642,8 @@ __device__ __noinline__ void mid_fwd_bn_relu(const MidCtx &c, const MidDesc &d, 
 template <int TM>
 __global__ void __maxnreg__(kMidMaxRegs) vae_mid_fwd_kernel(const __grid_constant__ MidDesc param) {
     constexpr int SPAN = MidTraits<TM>::kSpan;
+    pdl_wait();          // (programmatic dependent launch: common.cuh)
+    pdl_trigger();
     extern __shared__ __align__(16) float mid_smem[];
     __shared__ MidShared sh;
     mid_setup(sh, param, mid_smem);
@@ -944,6 +946,8 @@ __device__ __noinline__ void mid_bn_relu_bwd(const MidCtx &c, const MidDesc &d, 
 template <int TM>
 __global__ void __maxnreg__(kMidMaxRegs) vae_mid_bwd_kernel(const __grid_constant__ MidDesc param) {
     constexpr int SPAN = MidTraits<TM>::kSpan;
+    pdl_wait();          // (programmatic dependent launch: common.cuh)
+    pdl_trigger();
     extern __shared__ __align__(16) float mid_smem[];
     __shared__ MidShared sh;
     mid_setup(sh, param, mid_smem);
@@ -1361,7 +1365,7 @@ static int mid_launch_t(const char *name, const MidDesc *d, int grid, cudaStream
         SCVAE_CHECK_ARG(e == cudaSuccess, "%s: cannot set smem attribute (%d bytes): %s", name, smem, cudaGetErrorString(e));
         have = smem;
     }
-    kern<<<grid, kMidThreads, smem, s>>>(*d);
+    launch_pdl(BWD ? kPdlMidBwd : kPdlMidFwd, kern, dim3(grid), dim3(kMidThreads), smem, s, *d);
     SCVAE_CHECK_LAUNCH(name);
     return 0;
 }

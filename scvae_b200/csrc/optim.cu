@@ -45,6 +45,8 @@ adam_clip_kernel(float *__restrict__ p, const float *__restrict__ g, float *__re
                  float beta1, float beta2, float eps, float clip, float gscale,
                  const float *__restrict__ scalars, const AdamShadows sh, int *__restrict__ advance_counter,
                  int advance_total) {
+    pdl_wait();          // (programmatic dependent launch: common.cuh)
+    pdl_trigger();
     __shared__ float s_lr_t;
     if (threadIdx.x == 0) {
         const double t = (double)(*step + 1);
@@ -194,9 +196,9 @@ extern "C" int scvae_adam_clip_step(float *param, const float *grad, float *m, f
                         "adam_clip_step: bad shadow %d", k);
         sh.s[k] = s;
     }
-    adam_clip_kernel<<<(int)::adam_blocks(n), 256, 0, (cudaStream_t)stream>>>(
-        param, grad, m, v, n, step, lr, beta1, beta2, epsilon, clip, grad_scale, scalars, sh, advance_counter,
-        advance_total);
+    launch_pdl(kPdlAdam, adam_clip_kernel, dim3((unsigned)::adam_blocks(n)), dim3(256), 0, (cudaStream_t)stream,
+               param, grad, m, v, n, step, lr, beta1, beta2, epsilon, clip, grad_scale, scalars, sh, advance_counter,
+               advance_total);
     SCVAE_CHECK_LAUNCH("adam_clip_step");
     return 0;
 }
