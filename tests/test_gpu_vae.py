@@ -320,6 +320,10 @@ MID_CASES = [
     ("batch-correction-count-sum", 256, 6, [32, 16], "negative binomial", 130, True,
      dict(number_of_batches=3, count_sum_feature=True)),
     ("reference-default-minibatch", 1000, 10, [100], "negative binomial", 100, True, {}),
+    # the first-layer weight gradient from dY1 as fp16 + rounding remainder (SCVAE_DY1_SPLIT=1; the
+    # default is one loss-scaled fp16 dY1 with the bias column summed in fp32 by vae_mid_bwd)
+    ("one-layer-split-dy1", 256, 10, [64], "negative binomial", 128, True, dict(dy1_split=True)),
+    ("no-batch-norm-split-dy1", 256, 6, [40], "zero-inflated poisson", 96, False, dict(dy1_split=True)),
 ]
 
 
@@ -330,6 +334,8 @@ def test_fused_middle_training_step_matches_oracle(case):
     oracle: bound terms, per-cell tensors, raw gradients, variables after clip + Adam."""
     from scvae_b200.engine import VAEEngine
     name, G, L, hidden, lik, B, bn, opts = case
+    opts = dict(opts)
+    dy1_split = opts.pop("dy1_split", None)
     cfg = O.VAEConfig(G, L, hidden, lik, "gaussian", 1, 1, bn, True, kl_weight=0.7, **opts)
     params = O.vae_init_params(cfg, seed=3, dtype=torch.float64)
     gen = torch.Generator().manual_seed(11)
@@ -356,6 +362,8 @@ def test_fused_middle_training_step_matches_oracle(case):
             params[scope + "/BATCH_NORM/moving_variance"] = var[0] * 1.1
     eng = VAEEngine(G, L, hidden, lik, "gaussian", bn, kl_weight=0.7, device="cuda:0",
                     tensor_cores=True, **opts)
+    if dy1_split is not None:
+        eng.dy1_split = dy1_split
     eng.import_parameters(params)
     plan = eng._plan(B, 1)
     eng.set_batch_dense(plan, torch.tensor(x).cuda())
