@@ -142,3 +142,69 @@ def test_xavier_uniform_bound_matches_torch():
     # both fill the interval: the largest of 60 000 uniform draws lies within 0.1 % of the bound
     assert w.abs().max().item() > 0.999 * bound and ref.abs().max().item() > 0.999 * bound
     assert abs(w.var().item() - bound ** 2 / 3.0) < 0.02 * bound ** 2 / 3.0
+
+
+# ---------------------------------------------------------------------------------------------
+# the TF stand-in that produced the reference-graph fixtures (oracle/tf1_standin.py): the same two
+# primitives, independently of the oracle
+# ---------------------------------------------------------------------------------------------
+def test_standin_adam_against_scikit_learn_with_carried_slots():
+    from sklearn.neural_network._stochastic_optimizers import AdamOptimizer
+    from oracle import tf1_standin as T
+    rng = numpy.random.RandomState(5)
+    w0 = rng.randn(4, 3)
+    sk_params = [w0.copy()]
+    sk = AdamOptimizer(sk_params, learning_rate_init=2e-3)
+    w, m, v = w0.copy(), numpy.zeros_like(w0), numpy.zeros_like(w0)
+    for step in range(12):
+        c = rng.uniform(-1, 1, size=w0.shape)           # d loss / d w of loss = sum(c * w)
+        c[0, 0] = 1e-9
+        T.STATE.reset(initial={"L/weights": w, "__adam_m__": {"L/weights": m},
+                               "__adam_v__": {"L/weights": v}, "__adam_step__": step})
+        var = T.get_variable("L/weights", None)
+        opt = T.AdamOptimizer(2e-3)
+        pairs = opt.compute_gradients((var * torch.tensor(c)).sum())
+        opt.apply_gradients([(T.clip_by_value(g, -1.0, 1.0), x) for g, x in pairs])
+        w = T.STATE.updates["L/weights"].numpy()
+        m = T.STATE.updates["__adam_m__/L/weights"].numpy()
+        v = T.STATE.updates["__adam_v__/L/weights"].numpy()
+        sk.update_params(sk_params, [c])
+        assert numpy.allclose(w, sk_params[0], rtol=1e-12, atol=1e-15), step
+
+
+@pytest.mark.parametrize("rows", [2, 5, 33])
+def test_standin_batch_norm_against_aten(rows):
+    from oracle import tf1_standin as T
+    gen = torch.Generator().manual_seed(100 + rows)
+    y = torch.randn(rows, 4, generator=gen, dtype=D) * 2.0 - 0.5
+    beta = torch.randn(4, generator=gen, dtype=D)
+    mm = torch.randn(4, generator=gen, dtype=D)
+    mv = torch.rand(4, generator=gen, dtype=D) + 0.5
+    T.STATE.reset(initial={"L/BATCH_NORM/beta": beta.numpy(), "L/BATCH_NORM/moving_mean": mm.numpy(),
+                           "L/BATCH_NORM/moving_variance": mv.numpy()})
+    with T.variable_scope("L"):
+        out = T.batch_norm(y, is_training=True, scope="BATCH_NORM")
+    rm, rv = mm.clone(), mv.clone()
+    ref = torch.nn.functional.batch_norm(y, rm, rv, weight=None, bias=beta, training=True,
+                                         momentum=0.001, eps=1e-3)
+    assert torch.allclose(torch.as_tensor(out.detach()), ref, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(torch.as_tensor(T.STATE.updates["L/BATCH_NORM/moving_mean"]), rm, rtol=1e-12, atol=1e-14)
+    assert torch.allclose(torch.as_tensor(T.STATE.updates["L/BATCH_NORM/moving_variance"]), rv, rtol=1e-12, atol=1e-14)
+    with T.variable_scope("L"):
+        out_eval = T.batch_norm(y, is_training=False, scope="BATCH_NORM")
+    ref_eval = torch.nn.functional.batch_norm(y, mm, mv, weight=None, bias=beta, training=False, eps=1e-3)
+    assert torch.allclose(torch.as_tensor(out_eval.detach()), ref_eval, rtol=1e-12, atol=1e-12)
+
+
+def test_standin_normal_kl_against_torch_distributions():
+    from oracle import tf1_standin as T
+    gen = torch.Generator().manual_seed(8)
+    mu, sigma = torch.randn(6, 3, generator=gen, dtype=D), torch.rand(6, 3, generator=gen, dtype=D) + 0.2
+    T.STATE.reset()
+    kl = T.kl_divergence(T.Normal(mu, sigma), T.Normal(torch.zeros_like(mu), torch.ones_like(mu)))
+    ref = torch.distributions.kl_divergence(torch.distributions.Normal(mu, sigma),
+                                            torch.distributions.Normal(torch.zeros_like(mu), torch.ones_like(mu)))
+    assert torch.allclose(torch.as_tensor(kl), ref, rtol=1e-12, atol=1e-14)
+    z = torch.randn(6, 3, generator=gen, dtype=D)
+    assert torch.allclose(torch.as_tensor(T.Normal(mu, sigma).log_prob(z)),
+                          torch.distributions.Normal(mu, sigma).log_prob(z), rtol=1e-12, atol=1e-13)
