@@ -469,6 +469,22 @@ def extra_configs(dev):
 # ---------------------------------------------------------------------------------------------
 # this repository's arm
 # ---------------------------------------------------------------------------------------------
+def measure_blocks(timed_block, world, device, budget_ms=250.0, most=25):
+    """``timed_block(b)`` -> milliseconds of block ``b`` (already the maximum over the ranks).  Block
+    0 is the contract's region; while the measurement is short, further blocks follow until about
+    ``budget_ms`` in all (at most ``most`` blocks).  Every rank runs the SAME number of blocks:
+    rank 0's count is broadcast (the blocks contain barriers and collectives)."""
+    import torch.distributed as dist
+    blocks = [timed_block(0)]
+    more = torch.tensor([max(0, min(most, int(budget_ms / max(blocks[0], 1e-3))) - 1)],
+                        dtype=torch.int64, device=device)
+    if world > 1:
+        dist.broadcast(more, src=0)
+    for b in range(int(more.item())):
+        blocks.append(timed_block(b + 1))
+    return blocks
+
+
 def _dbg(msg):
     if os.environ.get("SCVAE_BENCH_DEBUG"):
         print("[bench rank {}] {}".format(os.environ.get("RANK", "0"), msg), file=sys.stderr,
@@ -558,12 +574,7 @@ def run_b200(args):
     # The contract's region: `steps` steps behind the warm-up.  A region of 20 steps lasts 10 ms, so
     # while the measurement is short further blocks of exactly `steps` steps follow (about 0.25 s in
     # all) and the MEDIAN block is reported; every block is listed in `timed_blocks`.
-    blocks = [timed_block(args.warmup)]
-    more = torch.tensor([max(0, min(24, int(250.0 / max(blocks[0], 1e-3)) - 1))], device=dev)
-    if world > 1:
-        dist.broadcast(more, src=0)            # (every rank times the same number of blocks)
-    for b in range(int(more.item())):
-        blocks.append(timed_block(args.warmup + (b + 1) * args.steps))
+    blocks = measure_blocks(lambda b: timed_block(args.warmup + b * args.steps), world, dev)
     sampler.mark()
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = float(numpy.median(blocks))

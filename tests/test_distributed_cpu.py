@@ -192,3 +192,44 @@ def test_rank_sharded_resident_training_data(tmp_path):
         assert drift == 0.0
     curve = results[0][2]
     assert len(curve) == 2 and all(numpy.isfinite(curve))
+
+
+def _blocks_worker(rank, world, port, results):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import bench
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    calls = []
+
+    def timed_block(b):
+        # as bench.py's: a collective inside every block, the maximum over the ranks returned.
+        # The ranks see different local times (rank 1 is 4 x slower in block 0): the block count
+        # must still agree, or the next collective would hang
+        calls.append(b)
+        local = (10.0 if rank == 0 else 40.0) + b
+        t = torch.tensor([local])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    blocks = bench.measure_blocks(timed_block, world, torch.device("cpu"), budget_ms=250.0, most=25)
+    results[rank] = (blocks, calls)
+    dist.destroy_process_group()
+
+
+def test_bench_blocks_agree_across_ranks():
+    """bench.py times several blocks of K steps and reports the median: every rank must run the
+    same number of blocks (each contains barriers and an all-reduce)."""
+    port = 31500 + (os.getpid() % 2000)
+    manager = mp.Manager()
+    results = manager.dict()
+    mp.spawn(_blocks_worker, args=(2, port, results), nprocs=2, join=True)
+    assert len(results) == 2
+    (b0, c0), (b1, c1) = results[0], results[1]
+    assert b0 == b1 and c0 == c1
+    assert len(b0) == 6 and b0[0] == 40.0            # 250 ms / 40 ms -> 6 blocks in all
+    # a single process: no collective, the same arithmetic
+    import bench
+    assert len(bench.measure_blocks(lambda b: 100.0, 1, torch.device("cpu"))) == 2
+    assert len(bench.measure_blocks(lambda b: 1000.0, 1, torch.device("cpu"))) == 1
+    assert len(bench.measure_blocks(lambda b: 0.5, 1, torch.device("cpu"))) == 25
